@@ -1,0 +1,163 @@
+/*
+ * include/kmerguts.h -- flat C ABI of libkmerguts_b200.so
+ *
+ * The B200 (sm_100a) replacement for the middle of KmerGutsJava.run()
+ * (lib/src/kmergutsjava/KmerGutsJava.java, "KGJ" below): everything between the
+ * FASTA callback (KGJ:778-784) and the per-sequence printing loop (KGJ:810-818),
+ * i.e. prepareQuery + QueryKmerStorage + lookup + gatherHits/processSetOfHits.
+ * The reference has no FFI for this path (it is one Java file); these entry
+ * points are what a JNI / Panama binding inside run() would bind -- see
+ * INTEGRATION.md for the Java side.
+ *
+ * Conventions: plain pointers and sizes only; every int-returning function gives
+ * 0 on success and a negative KG_E* code on failure, with a message available
+ * from kg_last_error(); the library owns every buffer it returns until the
+ * matching *_free; inputs are borrowed only for the duration of the call.
+ * There is NO CPU fallback: without a CUDA device kg_init fails with KG_ENODEV.
+ */
+#ifndef KMERGUTS_H
+#define KMERGUTS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KG_K 8                          /* KGJ:85 */
+#define KG_MAX_ENCODED 25600000000LL    /* 20^8, KGJ:87 */
+#define KG_OI_BUFSZ 5                   /* KGJ:99 */
+#define KG_MAX_HITS_PER_SEQ 40000       /* KGJ:98 */
+
+enum {
+    KG_OK = 0,
+    KG_EINVAL = -1,     /* bad argument (incl. min_hits < 2, see kg_params) */
+    KG_ENODEV = -2,     /* no usable CUDA device / driver */
+    KG_ECUDA = -3,      /* CUDA runtime error (message has the detail) */
+    KG_EIO = -4,        /* file missing / unreadable / truncated */
+    KG_EFORMAT = -5,    /* kmer.table.mem_map violates the format (entrySize != 24, ...) */
+    KG_ENOMEM = -6,     /* host or device allocation failed */
+    KG_ERANGE = -7      /* batch too large for one call (positions must fit 32 bits after splitting) */
+};
+
+enum { KG_MODE_DNA = 0, KG_MODE_AA = 1 }; /* "-a" flag, KGJ:102, 578, 1054 */
+
+typedef struct kg_context kg_context; /* one GPU: device id, streams, scratch arena */
+typedef struct kg_table kg_table;     /* immutable GPU-resident signature table; shareable between runs */
+typedef struct kg_batch kg_batch;     /* sequences resident in HBM */
+typedef struct kg_result kg_result;   /* calls / OTU counts / optional hits of one run */
+
+/* Instance fields of KmerGutsJava that steer the path (KGJ:102-107, flags KGJ:578-595). */
+typedef struct kg_params {
+    int32_t min_hits;          /* -m, default 5.  Must be >= 2: KGJ:442 indexes hits[n-2] */
+    int32_t min_weighted_hits; /* -M, default 0 (compared as float, KGJ:397) */
+    int32_t max_gap;           /* -g, default 200 */
+    int32_t order_constraint;  /* -O, default 0 */
+    int32_t emit_hits;         /* 1: also return every hit (the "-d" HIT lines, KGJ:472-475) */
+} kg_params;
+
+/* One CALL line (KGJ:398-404), in the order the reference prints them: by sequence, then
+ * strand/frame (+0,+1,+2,-0,-1,-2), then position. */
+typedef struct kg_call {
+    uint32_t seq;          /* index of the sequence in the batch */
+    int32_t strand_frame;  /* 0..5 = +0,+1,+2,-0,-1,-2; always 0 in aa mode */
+    int32_t start;         /* hits.get(0).from0InProt */
+    int32_t end;           /* hits.get(lastHit).from0InProt + K-1 */
+    int32_t count;         /* fICount */
+    int32_t fI;            /* currentFI: index into function.index */
+    float weighted;        /* weightedHits: fp32 sum in list order (bit-exact with the reference) */
+    int32_t hits_before;   /* HIT lines of this (seq, strand_frame) printed before this CALL (for "-d" output) */
+} kg_call;
+
+/* One OTU-COUNTS line (KGJ:516-524): the top-5 buffer of KGJ:413-438 after the sequence's last frame. */
+typedef struct kg_otu {
+    int32_t n;                  /* entries in use, 0..5 */
+    int32_t count[KG_OI_BUFSZ];
+    int32_t oI[KG_OI_BUFSZ];
+} kg_otu;
+
+/* One table hit (Hit, KGJ:1213-1219, plus its container), sorted by (seq, strand_frame, pos). */
+typedef struct kg_hit {
+    uint32_t seq;
+    int32_t strand_frame;
+    int32_t pos;              /* from0InProt */
+    int32_t oI;
+    int32_t avg_off_from_end;
+    int32_t fI;
+    float function_wt;
+} kg_hit;
+
+typedef struct kg_table_info {
+    int64_t num_slots;        /* "numSigs" header field (KGJ:933): slot count and hash modulus of the file */
+    int64_t entry_size;       /* header field, must be 24 (KGJ:934, 992 vs 995-999) */
+    int64_t version;          /* header field (KGJ:935), never checked by the reference either */
+    int64_t num_signatures;   /* occupied slots that the reference's no-wrap probe chain can reach */
+    int64_t num_unreachable;  /* occupied slots the reference could never return (dropped) */
+    int64_t tail_run;         /* occupied slots at the very end of the file: probes into them can run off
+                                 the end in the reference (EOFException, KGJ:799-802); 0 for well-formed tables */
+    int64_t num_buckets;      /* 32-byte buckets of the GPU layout */
+    int64_t flagged_buckets;  /* buckets whose overflow flag is set (a miss there costs a second sector) */
+    int64_t device_bytes;     /* HBM used by the table */
+} kg_table_info;
+
+typedef struct kg_run_stats {
+    uint64_t num_sequences;
+    uint64_t num_positions;   /* residue positions scanned (all frames) */
+    uint64_t num_kmers;       /* valid 8-mer windows = lookups (what addKmers enumerates, KGJ:912-921) */
+    uint64_t num_hits;
+    uint64_t num_calls;
+    uint32_t num_launches;    /* kernels of this library launched for the run */
+    float ms_h2d, ms_device, ms_d2h; /* CUDA-event times of the last run (0 when not applicable) */
+} kg_run_stats;
+
+/* ---- context ---- */
+int kg_init(int device, kg_context** ctx);
+void kg_shutdown(kg_context* ctx);
+const char* kg_last_error(void); /* thread-local, valid until the next failing call on this thread */
+const char* kg_version(void);
+
+/* ---- table: replaces readKmerTableHeader (KGJ:924-942) + the streamed table of lookup (KGJ:944-1034) ---- */
+/* data_dir holds kmer.table.mem_map or kmer.table.mem_map.gz (the .gz wins when both exist, KGJ:749-753). */
+int kg_table_load(kg_context* ctx, const char* data_dir, kg_table** table);
+int kg_table_load_file(kg_context* ctx, const char* path, kg_table** table);
+/* Same, from a file image already in memory (24-byte header + 24-byte little-endian entries). */
+int kg_table_from_image(kg_context* ctx, const void* image, size_t nbytes, kg_table** table);
+/* From DEVICE arrays of n distinct keys (< 20^8) and 16-byte payloads {oI, avgFromEnd, fI, wt-bits}. */
+int kg_table_from_device_entries(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, size_t n,
+                                 kg_table** table);
+int kg_table_get_info(const kg_table* table, kg_table_info* info);
+void kg_table_free(kg_table* table);
+
+/* ---- the path ---- */
+void kg_params_default(kg_params* p);
+
+/* Host buffers in, host results out: prepareQuery + lookup + gatherHits for n sequences.
+ * seq_bytes = the sequences exactly as FastaCallback.nextEntry receives them (KGJ:780), concatenated;
+ * offsets[n+1] delimit them.  Includes the H2D and D2H copies (this is the end-to-end call). */
+int kg_run(kg_context* ctx, const kg_table* table, int mode, const uint8_t* seq_bytes, const uint64_t* offsets,
+           size_t n, const kg_params* params, kg_result** result);
+
+/* Split form: keep the sequences resident in HBM and run the device pipeline on them (possibly many times). */
+int kg_batch_upload(kg_context* ctx, int mode, const uint8_t* seq_bytes, const uint64_t* offsets, size_t n,
+                    kg_batch** batch);
+/* Adopt sequences that are ALREADY in device memory (d_seq_bytes is modified in place in aa mode; d_offsets is a
+ * device array of n+1 uint64).  The batch does not own the two buffers. */
+int kg_batch_from_device(kg_context* ctx, int mode, uint8_t* d_seq_bytes, const uint64_t* d_offsets, size_t n,
+                         uint64_t total_bytes, kg_batch** batch);
+void kg_batch_free(kg_batch* batch);
+/* Device pipeline only; results stay on the device until kg_result_fetch. */
+int kg_batch_run(kg_context* ctx, const kg_table* table, kg_batch* batch, const kg_params* params,
+                 kg_result** result);
+int kg_result_fetch(kg_result* result); /* D2H of calls, OTU counts and (if requested) hits; idempotent */
+
+int kg_result_stats(const kg_result* result, kg_run_stats* stats);
+int kg_result_calls(kg_result* result, const kg_call** calls, size_t* n);
+int kg_result_otus(kg_result* result, const kg_otu** otus, size_t* n); /* one per sequence */
+int kg_result_hits(kg_result* result, const kg_hit** hits, size_t* n); /* needs params.emit_hits */
+void kg_result_free(kg_result* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERGUTS_H */

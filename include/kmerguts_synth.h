@@ -1,0 +1,61 @@
+/*
+ * include/kmerguts_synth.h -- bench / test tooling shipped inside libkmerguts_b200.so.  NOT part of the drop-in
+ * surface (that is include/kmerguts.h): the reference has no counterpart for any of this.
+ *
+ *   - the random-sector probe roofline microbenchmark (R_probe)
+ *   - CUDA generators of the synthetic universe defined in tools/kg_synth.py (same counter-based hashing, so the
+ *     bytes are identical to the numpy generator; tests/test_gpu_synth.py checks that)
+ *   - a device-side writer of the REFERENCE's table format, so that the CPU oracle can be handed the very same
+ *     200M-signature table the GPU probes
+ */
+#ifndef KMERGUTS_SYNTH_H
+#define KMERGUTS_SYNTH_H
+
+#include "kmerguts.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Parameters of tools/kg_synth.py::Universe.  cdf16 = 20 cumulative thresholds on a 16-bit draw, lenq = 4096 length
+ * quantiles; both are computed on the host (no transcendental has to agree between CPU and GPU). */
+typedef struct kg_universe {
+    uint64_t n_families;
+    uint64_t seed;
+    uint32_t sig_keep_per_1024;
+    uint32_t n_functions;
+    uint32_t n_otus;
+    uint32_t cdf16[20];
+    uint32_t lenq[4096];
+} kg_universe;
+
+/* Signature table of the universe: every selected consensus window, first occurrence in family-major order wins,
+ * truncated to max_sigs (0 = no limit).  On return *d_keys / *d_payload16 are device arrays of *n entries owned by
+ * the caller (kg_device_free). */
+int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64_t max_sigs, uint64_t** d_keys, void** d_payload16,
+                        uint64_t* n);
+
+/* Query proteins first..first+n-1 of tools/kg_synth.py::Universe.proteins(seed): device byte stream + offsets. */
+int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t first, uint64_t n, uint64_t seed,
+                      uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes);
+
+/* kmer.table.mem_map image (24-byte header + num_slots 24-byte LE entries, linear probing without wrap, last slot
+ * empty) built on the device from (keys, payload) and copied into host_image (24 + 24*num_slots bytes). */
+int kg_synth_reference_image(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, uint64_t n,
+                             uint64_t num_slots, void* host_image);
+
+void kg_device_free(void* d_ptr);
+int kg_device_to_host(kg_context* ctx, void* host, const void* dev, uint64_t bytes);
+
+/* R_probe: independent uniformly random 32-byte sector loads over a buffer of `bytes` bytes (one 256-bit load each,
+ * `loads_in_flight` per thread before the first use).  Returns sectors per second measured with CUDA events. */
+int kg_probe_roofline(kg_context* ctx, uint64_t bytes, uint64_t n_loads, int threads_per_block, int loads_in_flight,
+                      double* sectors_per_second);
+/* Same access pattern over the key array of a loaded table. */
+int kg_probe_roofline_table(kg_context* ctx, const kg_table* table, uint64_t n_loads, int threads_per_block,
+                            int loads_in_flight, double* sectors_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,347 @@
+"""kmergutsjava_b200 -- ctypes binding of libkmerguts_b200.so (include/kmerguts.h, kmerguts_host.h, kmerguts_synth.h).
+
+The product is the CUDA library; this module only loads it and wraps handles in small Python classes so that the
+tests and bench.py read like the reference's own driver (KmerGutsJava.run: load table, feed sequences, print calls).
+There is no CPU fallback: if the shared library is missing, or no B200 is visible, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkmerguts_b200.so")
+CLI_PATH = os.path.join(HERE, "bin", "kmer_guts_b200")
+
+MODE_DNA, MODE_AA = 0, 1
+
+CALL_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("start", "<i4"), ("end", "<i4"), ("count", "<i4"), ("fI", "<i4"),
+                       ("weighted", "<f4"), ("hits_before", "<i4")])
+OTU_DTYPE = np.dtype([("n", "<i4"), ("count", "<i4", (5,)), ("oI", "<i4", (5,))])
+HIT_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("pos", "<i4"), ("oI", "<i4"), ("avg", "<i4"), ("fI", "<i4"),
+                      ("wt", "<f4")])
+
+# every symbol the three headers declare (tests/test_abi.py checks the library exports exactly these)
+EXPORTS = [
+    "kg_init", "kg_shutdown", "kg_last_error", "kg_version",
+    "kg_table_load", "kg_table_load_file", "kg_table_from_image", "kg_table_from_device_entries", "kg_table_get_info",
+    "kg_table_free", "kg_params_default", "kg_run", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
+    "kg_batch_run", "kg_result_fetch", "kg_result_stats", "kg_result_calls", "kg_result_otus", "kg_result_hits",
+    "kg_result_free",
+    "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
+    "kg_functions_load", "kg_functions_read", "kg_functions_count", "kg_functions_name", "kg_functions_free",
+    "kg_format_java_f", "kg_report_write", "kg_main",
+    "kg_synth_signatures", "kg_synth_proteins", "kg_synth_reference_image", "kg_device_free", "kg_device_to_host",
+    "kg_probe_roofline", "kg_probe_roofline_table",
+]
+
+
+class KgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kmerguts error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("min_hits", C.c_int32), ("min_weighted_hits", C.c_int32), ("max_gap", C.c_int32),
+                ("order_constraint", C.c_int32), ("emit_hits", C.c_int32)]
+
+
+class TableInfo(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("num_slots", "entry_size", "version", "num_signatures", "num_unreachable",
+                                         "tail_run", "num_buckets", "flagged_buckets", "device_bytes")]
+
+
+class RunStats(C.Structure):
+    _fields_ = [("num_sequences", C.c_uint64), ("num_positions", C.c_uint64), ("num_kmers", C.c_uint64),
+                ("num_hits", C.c_uint64), ("num_calls", C.c_uint64), ("num_launches", C.c_uint32),
+                ("ms_h2d", C.c_float), ("ms_device", C.c_float), ("ms_d2h", C.c_float)]
+
+
+class UniverseStruct(C.Structure):
+    _fields_ = [("n_families", C.c_uint64), ("seed", C.c_uint64), ("sig_keep_per_1024", C.c_uint32),
+                ("n_functions", C.c_uint32), ("n_otus", C.c_uint32), ("cdf16", C.c_uint32 * 20),
+                ("lenq", C.c_uint32 * 4096)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """The shared library, or an exception: the product path must fail loudly when the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KgError(-2, f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"or `make -C kmergutsjava_b200/csrc`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64, sz = C.c_void_p, C.c_int, C.c_uint64, C.c_size_t
+    pp = C.POINTER(vp)
+    sig = {
+        "kg_init": (i32, [i32, pp]), "kg_shutdown": (None, [vp]), "kg_last_error": (C.c_char_p, []),
+        "kg_version": (C.c_char_p, []),
+        "kg_table_load": (i32, [vp, C.c_char_p, pp]), "kg_table_load_file": (i32, [vp, C.c_char_p, pp]),
+        "kg_table_from_image": (i32, [vp, vp, sz, pp]), "kg_table_from_device_entries": (i32, [vp, vp, vp, sz, pp]),
+        "kg_table_get_info": (i32, [vp, C.POINTER(TableInfo)]), "kg_table_free": (None, [vp]),
+        "kg_params_default": (None, [C.POINTER(Params)]),
+        "kg_run": (i32, [vp, vp, i32, vp, vp, sz, C.POINTER(Params), pp]),
+        "kg_batch_upload": (i32, [vp, i32, vp, vp, sz, pp]),
+        "kg_batch_from_device": (i32, [vp, i32, vp, vp, sz, u64, pp]), "kg_batch_free": (None, [vp]),
+        "kg_batch_run": (i32, [vp, vp, vp, C.POINTER(Params), pp]), "kg_result_fetch": (i32, [vp]),
+        "kg_result_stats": (i32, [vp, C.POINTER(RunStats)]),
+        "kg_result_calls": (i32, [vp, pp, C.POINTER(sz)]), "kg_result_otus": (i32, [vp, pp, C.POINTER(sz)]),
+        "kg_result_hits": (i32, [vp, pp, C.POINTER(sz)]), "kg_result_free": (None, [vp]),
+        "kg_fasta_read": (i32, [C.c_char_p, pp]), "kg_fasta_count": (sz, [vp]), "kg_fasta_id": (C.c_char_p, [vp, sz]),
+        "kg_fasta_bytes": (vp, [vp]), "kg_fasta_offsets": (vp, [vp]), "kg_fasta_free": (None, [vp]),
+        "kg_functions_load": (i32, [C.c_char_p, pp]), "kg_functions_read": (i32, [C.c_char_p, pp]),
+        "kg_functions_count": (sz, [vp]), "kg_functions_name": (C.c_char_p, [vp, sz]), "kg_functions_free": (None, [vp]),
+        "kg_format_java_f": (i32, [C.c_float, i32, C.c_char_p, sz]),
+        "kg_report_write": (i32, [C.c_char_p, i32, i32, vp, vp, vp, vp]),
+        "kg_main": (i32, [i32, C.POINTER(C.c_char_p)]),
+        "kg_synth_signatures": (i32, [vp, C.POINTER(UniverseStruct), u64, pp, pp, C.POINTER(u64)]),
+        "kg_synth_proteins": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
+        "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, vp]),
+        "kg_device_free": (None, [vp]), "kg_device_to_host": (i32, [vp, vp, vp, u64]),
+        "kg_probe_roofline": (i32, [vp, u64, u64, i32, i32, C.POINTER(C.c_double)]),
+        "kg_probe_roofline_table": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise KgError(rc, lib().kg_last_error().decode(errors="replace"))
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().kg_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, int(v))
+    return p
+
+
+def java_format_f(v: float, prec: int = 6) -> str:
+    out = C.create_string_buffer(128)
+    _check(lib().kg_format_java_f(C.c_float(v), prec, out, 128))
+    return out.value.decode()
+
+
+class Context:
+    """One GPU (kg_context)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().kg_init(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().kg_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- tables --
+    def load_table(self, data_dir: str) -> "Table":
+        h = C.c_void_p()
+        _check(lib().kg_table_load(self._h, data_dir.encode(), C.byref(h)))
+        return Table(self, h)
+
+    def table_from_image(self, image: bytes) -> "Table":
+        h = C.c_void_p()
+        buf = np.frombuffer(image, dtype=np.uint8)
+        _check(lib().kg_table_from_image(self._h, buf.ctypes.data, len(buf), C.byref(h)))
+        return Table(self, h)
+
+    def table_from_device_entries(self, d_keys: int, d_payload: int, n: int) -> "Table":
+        h = C.c_void_p()
+        _check(lib().kg_table_from_device_entries(self._h, d_keys, d_payload, n, C.byref(h)))
+        return Table(self, h)
+
+    # -- the path --
+    def run(self, table: "Table", mode: int, seq_bytes: np.ndarray, offsets: np.ndarray, params: Params) -> "Result":
+        """Host buffers in, host results out (kg_run): the end-to-end call."""
+        seq_bytes = np.ascontiguousarray(seq_bytes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(lib().kg_run(self._h, table._h, mode, seq_bytes.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                            C.byref(params), C.byref(h)))
+        return Result(h)
+
+    def run_ptr(self, table: "Table", mode: int, seq_ptr: int, off_ptr: int, n: int, params: Params) -> "Result":
+        h = C.c_void_p()
+        _check(lib().kg_run(self._h, table._h, mode, seq_ptr, off_ptr, n, C.byref(params), C.byref(h)))
+        return Result(h)
+
+    def upload(self, mode: int, seq_bytes: np.ndarray, offsets: np.ndarray) -> "Batch":
+        seq_bytes = np.ascontiguousarray(seq_bytes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(lib().kg_batch_upload(self._h, mode, seq_bytes.ctypes.data, offsets.ctypes.data, len(offsets) - 1, C.byref(h)))
+        return Batch(self, h)
+
+    def batch_from_device(self, mode: int, d_seq: int, d_off: int, n: int, total: int) -> "Batch":
+        h = C.c_void_p()
+        _check(lib().kg_batch_from_device(self._h, mode, d_seq, d_off, n, total, C.byref(h)))
+        return Batch(self, h)
+
+    def run_batch(self, table: "Table", batch: "Batch", params: Params) -> "Result":
+        h = C.c_void_p()
+        _check(lib().kg_batch_run(self._h, table._h, batch._h, C.byref(params), C.byref(h)))
+        return Result(h)
+
+    # -- tooling --
+    def probe_roofline(self, nbytes: int, n_loads: int, tpb: int = 256, inflight: int = 4) -> float:
+        out = C.c_double()
+        _check(lib().kg_probe_roofline(self._h, nbytes, n_loads, tpb, inflight, C.byref(out)))
+        return out.value
+
+    def probe_roofline_table(self, table: "Table", n_loads: int, tpb: int = 256, inflight: int = 4) -> float:
+        out = C.c_double()
+        _check(lib().kg_probe_roofline_table(self._h, table._h, n_loads, tpb, inflight, C.byref(out)))
+        return out.value
+
+    def to_host(self, d_ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        _check(lib().kg_device_to_host(self._h, out.ctypes.data, d_ptr, nbytes))
+        return out
+
+
+class Table:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self._h = ctx, h
+
+    @property
+    def info(self) -> TableInfo:
+        ti = TableInfo()
+        _check(lib().kg_table_get_info(self._h, C.byref(ti)))
+        return ti
+
+    def free(self):
+        if self._h:
+            lib().kg_table_free(self._h)
+            self._h = C.c_void_p()
+
+
+class Batch:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self._h = ctx, h
+
+    def free(self):
+        if self._h:
+            lib().kg_batch_free(self._h)
+            self._h = C.c_void_p()
+
+
+def _view(ptr, n, dtype) -> np.ndarray:
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class Result:
+    def __init__(self, h):
+        self._h = h
+
+    @property
+    def stats(self) -> RunStats:
+        s = RunStats()
+        _check(lib().kg_result_stats(self._h, C.byref(s)))
+        return s
+
+    def _arr(self, fn, dtype):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(fn(self._h, C.byref(p), C.byref(n)))
+        return _view(p.value, n.value, dtype)
+
+    @property
+    def calls(self) -> np.ndarray:
+        return self._arr(lib().kg_result_calls, CALL_DTYPE)
+
+    @property
+    def otus(self) -> np.ndarray:
+        return self._arr(lib().kg_result_otus, OTU_DTYPE)
+
+    @property
+    def hits(self) -> np.ndarray:
+        return self._arr(lib().kg_result_hits, HIT_DTYPE)
+
+    def fetch(self):
+        _check(lib().kg_result_fetch(self._h))
+
+    def free(self):
+        if self._h:
+            lib().kg_result_free(self._h)
+            self._h = C.c_void_p()
+
+
+class Fasta:
+    """readFasta (KGJ:1132-1192) through the host library."""
+
+    def __init__(self, path: str):
+        self._h = C.c_void_p()
+        _check(lib().kg_fasta_read(path.encode(), C.byref(self._h)))
+        L = lib()
+        self.n = L.kg_fasta_count(self._h)
+        self.ids = [L.kg_fasta_id(self._h, i).decode(errors="replace") for i in range(self.n)]
+        off_p = L.kg_fasta_offsets(self._h)
+        self.offsets = np.frombuffer((C.c_uint64 * (self.n + 1)).from_address(off_p), dtype=np.uint64).copy()
+        total = int(self.offsets[-1])
+        b_p = L.kg_fasta_bytes(self._h)
+        self.bytes = np.frombuffer((C.c_uint8 * total).from_address(b_p), dtype=np.uint8).copy() if total else np.zeros(0, np.uint8)
+
+    def free(self):
+        if self._h:
+            lib().kg_fasta_free(self._h)
+            self._h = C.c_void_p()
+
+
+def make_universe(u) -> UniverseStruct:
+    """tools.kg_synth.Universe -> the C struct the CUDA generators take."""
+    s = UniverseStruct()
+    s.n_families, s.seed, s.sig_keep_per_1024 = u.n_families, u.seed, u.sig_keep_per_1024
+    s.n_functions, s.n_otus = u.n_functions, u.n_otus
+    for i, v in enumerate(u.cdf):
+        s.cdf16[i] = int(v)
+    for i, v in enumerate(u.lenq):
+        s.lenq[i] = int(v)
+    return s
+
+
+def synth_signatures(ctx: Context, u, max_sigs: int = 0):
+    dk, dp, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    us = make_universe(u)
+    _check(lib().kg_synth_signatures(ctx._h, C.byref(us), max_sigs, C.byref(dk), C.byref(dp), C.byref(n)))
+    return dk.value, dp.value, n.value
+
+
+def synth_proteins(ctx: Context, u, first: int, n: int, seed: int):
+    ds, do, total = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    us = make_universe(u)
+    _check(lib().kg_synth_proteins(ctx._h, C.byref(us), first, n, seed, C.byref(ds), C.byref(do), C.byref(total)))
+    return ds.value, do.value, total.value
+
+
+def synth_reference_image(ctx: Context, d_keys: int, d_payload: int, n: int, num_slots: int) -> np.ndarray:
+    img = np.empty(24 + 24 * num_slots, dtype=np.uint8)
+    _check(lib().kg_synth_reference_image(ctx._h, d_keys, d_payload, n, num_slots, img.ctypes.data))
+    return img
+
+
+def device_free(ptr):
+    if ptr:
+        lib().kg_device_free(ptr)

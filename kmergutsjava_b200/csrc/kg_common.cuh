@@ -1,0 +1,104 @@
+// kg_common.cuh -- shared declarations of libkmerguts_b200 (sm_100a only; no CPU fallback anywhere).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/kmerguts.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+void kg_set_error(const char* fmt, ...);
+#define KG_FAIL(code, ...)            \
+    do {                              \
+        kg_set_error(__VA_ARGS__);    \
+        return (code);                \
+    } while (0)
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            kg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return e_ == cudaErrorMemoryAllocation ? KG_ENOMEM : KG_ECUDA;                              \
+        }                                                                                               \
+    } while (0)
+#define KG_TRY(call)              \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != KG_OK) return r_; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// GPU table layout.
+//
+// The reference streams 24-byte {int64 key; int32 oI; int32 avgFromEnd; int32 fI; float wt} slots of an
+// open-addressing table with linear probing and no wrap-around (KGJ:944-1034, 995-999).  All a probe has to answer
+// is "is k-mer v stored, and with which payload"; the layout is ours.  A key is < 20^8 < 2^35, so a 32-byte sector
+// holds seven of them:
+//
+//   bucket = 8 x uint32:  w[0..6] = low 32 bits of keys 0..6
+//                         w[7]    = bits [3i, 3i+3): bits 32..34 of key i (i = 0..6)
+//                                   bit  31        : overflow flag -- some key whose probe sequence passes through
+//                                                    this bucket lives in a later one
+//   empty slot = 35 one-bits (0x7FFFFFFFF > 20^8).
+//
+// A lookup reads exactly one sector unless the flag is set (a few % of buckets at load 0.6).  Payloads live in a
+// separate array of 16-byte records indexed by slot = bucket*7 + lane and are read only on a hit.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KG_BUCKET_KEYS = 7;
+constexpr uint32_t KG_W7_EMPTY = 0x001FFFFFu; // all seven 3-bit high fields = 7, flag clear
+constexpr uint32_t KG_W7_FLAG = 0x80000000u;
+constexpr uint32_t KG_TAIL_BUCKETS = 4096;    // spill room past the last home bucket (no wrap-around in our layout either)
+
+struct KgTableView {
+    const uint4* buckets;   // 2 x uint4 per bucket
+    const int4* payload;    // {oI, avgFromEnd, fI, float bits of wt} per slot
+    uint32_t num_buckets;   // home buckets (hash range); KG_TAIL_BUCKETS more follow
+};
+
+__host__ __device__ __forceinline__ uint64_t kg_mix(uint64_t k) {
+    // murmur3 finaliser; the k-mer code is a base-20 number with very regular low digits
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+__host__ __device__ __forceinline__ uint32_t kg_home_bucket(uint64_t key, uint32_t num_buckets) {
+    uint32_t h = (uint32_t)(kg_mix(key) >> 32);
+    return (uint32_t)(((uint64_t)h * (uint64_t)num_buckets) >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device memory helpers (host side)
+// ---------------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes); // grow-only; contents are NOT preserved across a growth
+    void release();
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+struct kg_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // compute
+    cudaStream_t copy_stream = nullptr; // H2D staging for the pipelined end-to-end call
+    cudaEvent_t ev[6] = {};
+    int sm_count = 0;
+    size_t l2_bytes = 0;
+    DevBuf scan_tmp;                    // CUB temp storage
+    // pinned staging for small device->host counters
+    uint64_t* h_counters = nullptr;
+    void* scratch = nullptr;            // RunScratch (kg_run.cu)
+};
+
+// counters written by the pipeline, one block of 8 x uint64 per run
+enum { KG_CTR_HITS = 0, KG_CTR_KMERS = 1, KG_CTR_CALLS = 2, KG_CTR_OVERFLOW = 3, KG_CTR_VPOS = 4, KG_CTR_COUNT = 8 };

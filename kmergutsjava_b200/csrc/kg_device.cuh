@@ -1,0 +1,46 @@
+// kg_device.cuh -- device-side primitives shared by the table builder and the probe kernels (sm_100a).
+#pragma once
+
+#include "kg_common.cuh"
+
+struct KgBucket {
+    uint32_t w[8];
+};
+
+// One 32-byte sector in one instruction: sm_100a has 256-bit global loads (SASS LDG.E.256).  The table is
+// read-only and randomly indexed, so bypass L1 allocation; L2 keeps whatever locality there is.
+__device__ __forceinline__ KgBucket kg_load_bucket(const uint4* buckets, uint32_t b) {
+    KgBucket r;
+    const uint4* p = buckets + 2ull * b;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+
+// Bit i of the result is set when slot i of the bucket holds `key`.
+__device__ __forceinline__ uint32_t kg_bucket_match(const KgBucket& bk, uint64_t key) {
+    const uint32_t lo = (uint32_t)key;
+    const uint32_t x = bk.w[7] ^ ((uint32_t)(key >> 32) * 0x00249249u); // field i == 0  <=>  high bits agree
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < KG_BUCKET_KEYS; i++) m |= (uint32_t)((bk.w[i] == lo) & (((x >> (3 * i)) & 7u) == 0u)) << i;
+    return m;
+}
+
+// Full lookup (used where latency does not matter: verification, the rare overflow continuation).
+// Returns the slot (bucket*7 + lane) or 0xFFFFFFFF.
+__device__ __forceinline__ uint32_t kg_lookup_from(const KgTableView& t, uint64_t key, uint32_t b) {
+    const uint32_t last = t.num_buckets + KG_TAIL_BUCKETS - 1;
+    for (;;) {
+        KgBucket bk = kg_load_bucket(t.buckets, b);
+        uint32_t m = kg_bucket_match(bk, key);
+        if (m) return b * KG_BUCKET_KEYS + (__ffs(m) - 1);
+        if (!(bk.w[7] & KG_W7_FLAG) || b == last) return 0xFFFFFFFFu;
+        b++;
+    }
+}
+__device__ __forceinline__ uint32_t kg_lookup(const KgTableView& t, uint64_t key) {
+    return kg_lookup_from(t, key, kg_home_bucket(key, t.num_buckets));
+}

@@ -1,0 +1,168 @@
+// kg_fsm.cuh -- gatherHits / processSetOfHits (KGJ:457-514, 385-455) as a streaming state machine.
+//
+// The reference keeps the open run as an ArrayList<Hit> and re-scans it in processSetOfHits.  Everything that scan
+// computes is a fold over the list in list order with `currentFI` fixed for the lifetime of the list (currentFI only
+// changes when the list is empty or inside processSetOfHits), so it can be carried incrementally:
+//   n            hits.size()
+//   first_pos    hits.get(0).from0InProt
+//   cnt, w       fICount and weightedHits: fp32 additions in list order, the very additions KGJ:394 performs
+//   last_match   hits.get(lastHit).from0InProt
+//   l1, l2       the last two list entries (gap test, order constraint, pair-switch test, retained pair)
+//   otu_t        the OTU buffer as it would be after replaying every counted hit of the open run (KGJ:413-438);
+//                committed to otu_c when the run is called, dropped otherwise
+// No list, no second pass, identical results (bit-exact, including the fp32 sum).
+#pragma once
+
+#include "kg_common.cuh"
+
+struct KgOtuBuf { // ArrayList<OtuCount>, at most OI_BUFSZ entries (KGJ:99, 1221-1224)
+    int n;
+    int c[KG_OI_BUFSZ];
+    int o[KG_OI_BUFSZ];
+};
+
+__device__ __forceinline__ void kg_otu_clear(KgOtuBuf& u) {
+    u.n = 0;
+#pragma unroll
+    for (int i = 0; i < KG_OI_BUFSZ; i++) u.c[i] = u.o[i] = 0;
+}
+
+// KGJ:415-437.  Fully unrolled so the five entries stay in registers.
+__device__ __forceinline__ void kg_otu_update(KgOtuBuf& u, int oI) {
+    int j = u.n;
+#pragma unroll
+    for (int i = KG_OI_BUFSZ - 1; i >= 0; i--)
+        if (i < u.n && u.o[i] == oI) j = i;
+    if (j == u.n) {
+        if (u.n == KG_OI_BUFSZ) j = KG_OI_BUFSZ - 1; // overwrite the last entry (KGJ:419-421)
+        else u.n++;
+#pragma unroll
+        for (int i = 0; i < KG_OI_BUFSZ; i++)
+            if (i == j) {
+                u.o[i] = oI;
+                u.c[i] = 1;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < KG_OI_BUFSZ; i++)
+            if (i == j) u.c[i]++;
+    }
+#pragma unroll
+    for (int i = KG_OI_BUFSZ - 1; i >= 1; i--) { // bubble toward the front while prev.count <= cur.count (KGJ:432-437)
+        if (i == j && u.c[i - 1] <= u.c[i]) {
+            int tc = u.c[i - 1], to = u.o[i - 1];
+            u.c[i - 1] = u.c[i];
+            u.o[i - 1] = u.o[i];
+            u.c[i] = tc;
+            u.o[i] = to;
+            j = i - 1;
+        }
+    }
+}
+
+struct KgFsmParams {
+    int min_hits, max_gap, order_constraint;
+    float min_weighted;
+};
+
+struct KgHitLite {
+    int pos, fI, avg, oI;
+    float wt;
+};
+
+struct KgDevCall { // one CALL before it is tagged with (seq, strand_frame)
+    int start, end, count, fI;
+    float weighted;
+    int hits_before;
+};
+
+struct KgFsm {
+    // open run
+    int n, cur, first_pos, cnt, last_match;
+    float w;
+    KgHitLite l1, l2;
+    KgOtuBuf otu_c, otu_t;
+    int consumed;       // HIT lines so far in this container
+    int ncalls;
+
+    __device__ __forceinline__ void begin_sequence() { kg_otu_clear(otu_c); }
+    __device__ __forceinline__ void begin_container() {
+        n = 0;
+        cur = 0; // KGJ:467
+        consumed = 0;
+        ncalls = 0;
+        cnt = 0;
+        w = 0.f;
+        first_pos = last_match = 0;
+        l1 = KgHitLite{0, 0, 0, 0, 0.f};
+        l2 = l1;
+    }
+
+    __device__ __forceinline__ void append(const KgHitLite& h) {
+        if (n == 0) {
+            first_pos = h.pos;
+            cnt = 0;
+            w = 0.f;
+            otu_t = otu_c;
+        }
+        n++;
+        l2 = l1;
+        l1 = h;
+        if (h.fI == cur) { // KGJ:391-395
+            cnt++;
+            w = __fadd_rn(w, h.wt);
+            last_match = h.pos;
+            kg_otu_update(otu_t, h.oI);
+        }
+    }
+
+    // processSetOfHits, KGJ:385-455
+    template <class Emit>
+    __device__ __forceinline__ void process(const KgFsmParams& p, Emit& emit) {
+        if (cnt >= p.min_hits && w >= p.min_weighted) { // KGJ:397
+            KgDevCall c = {first_pos, last_match + (KG_K - 1), cnt, cur, w, consumed};
+            emit(ncalls, c);
+            ncalls++;
+            otu_c = otu_t; // the replay of KGJ:413-439 has already been done incrementally
+        }
+        if (n >= 2 && l2.fI != cur && l2.fI == l1.fI) { // KGJ:442-449: the pair seeds the next run
+            cur = l1.fI;
+            n = 2;
+            first_pos = l2.pos;
+            cnt = 2;
+            w = __fadd_rn(__fadd_rn(0.f, l2.wt), l1.wt);
+            last_match = l1.pos;
+            otu_t = otu_c;
+            kg_otu_update(otu_t, l2.oI);
+            kg_otu_update(otu_t, l1.oI);
+        } else {
+            n = 0; // KGJ:452
+        }
+    }
+
+    // body of the for loop of gatherHits, KGJ:468-510
+    template <class Emit>
+    __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, Emit& emit) {
+        consumed++;
+        if (n > 0 && (int)((unsigned)l1.pos + (unsigned)p.max_gap) < h.pos) { // KGJ:477-484 (Java int wrap-around kept)
+            if (n >= p.min_hits) process(p, emit);
+            else n = 0;
+        }
+        if (n == 0) cur = h.fI; // KGJ:486-488
+        bool accept = !p.order_constraint || n == 0;
+        if (!accept) { // KGJ:491-494
+            int d = (int)((unsigned)(h.pos - l1.pos) - (unsigned)(l1.avg - h.avg));
+            int ad = d < 0 ? (int)(0u - (unsigned)d) : d;
+            accept = (h.fI == l1.fI) && ad <= 20;
+        }
+        if (accept) {
+            if (n < KG_MAX_HITS_PER_SEQ - 2) append(h); // KGJ:496-497
+            if (n > 1 && cur != h.fI && l2.fI == l1.fI) process(p, emit); // KGJ:503-507 (tested even when not appended)
+        }
+    }
+
+    template <class Emit>
+    __device__ __forceinline__ void end_container(const KgFsmParams& p, Emit& emit) {
+        if (n >= p.min_hits) process(p, emit); // KGJ:511-513
+    }
+};

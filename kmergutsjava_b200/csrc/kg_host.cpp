@@ -1,0 +1,455 @@
+// kg_host.cpp -- host-side mirror of KmerGutsJava.run()'s CPU parts: FASTA, function.index, report, main() flags.
+// (include/kmerguts_host.h explains why this exists in C++: no JVM in this image.)  No lookup / call logic lives here.
+#include "../../include/kmerguts_host.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <charconv>
+#include <chrono>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+void kg_set_error(const char* fmt, ...); // kg_table.cu
+
+struct kg_fasta {
+    std::vector<std::string> ids;
+    std::vector<uint8_t> bytes;
+    std::vector<uint64_t> off{0};
+};
+struct kg_functions {
+    std::vector<std::string> names;
+};
+
+namespace {
+
+bool has_suffix(const std::string& s, const char* suf) {
+    size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+bool file_exists(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+// whole file, gunzipped when the NAME ends in .gz (the reference decides by name: KGJ:347, 764)
+bool read_all(const std::string& path, std::string& out) {
+    out.clear();
+    if (has_suffix(path, ".gz")) {
+        gzFile g = gzopen(path.c_str(), "rb");
+        if (!g) return false;
+        gzbuffer(g, 1 << 20);
+        std::vector<char> buf(4u << 20);
+        for (;;) {
+            int got = gzread(g, buf.data(), (unsigned)buf.size());
+            if (got < 0) {
+                gzclose(g);
+                return false;
+            }
+            if (got == 0) break;
+            out.append(buf.data(), (size_t)got);
+        }
+        gzclose(g);
+        return true;
+    }
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::vector<char> buf(4u << 20);
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) out.append(buf.data(), got);
+    fclose(f);
+    return true;
+}
+
+// BufferedReader.readLine(): a line ends at \n, \r or \r\n; the terminator is not part of the line
+struct Lines {
+    std::string_view text;
+    size_t pos = 0;
+    bool next(std::string_view& line) {
+        if (pos >= text.size()) return false;
+        size_t e = pos;
+        while (e < text.size() && text[e] != '\n' && text[e] != '\r') e++;
+        line = text.substr(pos, e - pos);
+        if (e < text.size()) e += (text[e] == '\r' && e + 1 < text.size() && text[e + 1] == '\n') ? 2 : 1;
+        pos = e;
+        return true;
+    }
+};
+// String.trim(): drops chars <= ' ' at both ends
+std::string_view jtrim(std::string_view s) {
+    while (!s.empty() && (unsigned char)s.front() <= ' ') s.remove_prefix(1);
+    while (!s.empty() && (unsigned char)s.back() <= ' ') s.remove_suffix(1);
+    return s;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// readFasta, KGJ:1132-1192
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
+    if (!path || !out) {
+        kg_set_error("kg_fasta_read: null argument");
+        return KG_EINVAL;
+    }
+    std::string text;
+    if (!read_all(path, text)) {
+        kg_set_error("cannot read %s", path);
+        return KG_EIO;
+    }
+    kg_fasta* fa = new kg_fasta();
+    Lines in{text};
+    std::string_view cur;
+    bool have = in.next(cur); // str1
+    for (;;) {
+        // look for the next caption; lines whose trimmed length is <= 1 are skipped (KGJ:1145, 1161)
+        std::string name;
+        bool got_caption = false;
+        while (have) {
+            std::string_view t = jtrim(cur);
+            if (t.size() > 1) {
+                if (t[0] == '>' && !jtrim(t.substr(1)).empty()) {
+                    std::string_view r = t.substr(1); // StringTokenizer(" \t").nextToken(), KGJ:1147-1148
+                    size_t a = 0;
+                    while (a < r.size() && (r[a] == ' ' || r[a] == '\t')) a++;
+                    size_t b = a;
+                    while (b < r.size() && r[b] != ' ' && r[b] != '\t') b++;
+                    name.assign(r.substr(a, b - a));
+                    got_caption = true;
+                    break;
+                }
+                kg_set_error("Wrong caption line: %.*s", (int)std::min<size_t>(t.size(), 400), t.data()); // KGJ:1158
+                delete fa;
+                return KG_EFORMAT;
+            }
+            have = in.next(cur);
+        }
+        if (!got_caption) break; // KGJ:1163-1165
+        for (;;) {               // first non-blank line after the caption, KGJ:1167-1174
+            have = in.next(cur);
+            std::string_view t = have ? jtrim(cur) : std::string_view();
+            if (!have || (!t.empty() && t[0] == '>')) {
+                kg_set_error("No sequence for caption: %s", name.c_str()); // KGJ:1170
+                delete fa;
+                return KG_EFORMAT;
+            }
+            if (!t.empty()) break;
+        }
+        for (;;) { // KGJ:1175-1180: lines are appended as they are, blanks and inner spaces included
+            fa->bytes.insert(fa->bytes.end(), cur.begin(), cur.end());
+            have = in.next(cur);
+            if (!have) break;
+            std::string_view t = jtrim(cur);
+            if (!t.empty() && t[0] == '>') break;
+        }
+        fa->ids.push_back(std::move(name));
+        fa->off.push_back(fa->bytes.size());
+    }
+    *out = fa;
+    return KG_OK;
+}
+extern "C" size_t kg_fasta_count(const kg_fasta* f) { return f ? f->ids.size() : 0; }
+extern "C" const char* kg_fasta_id(const kg_fasta* f, size_t i) { return (f && i < f->ids.size()) ? f->ids[i].c_str() : nullptr; }
+extern "C" const uint8_t* kg_fasta_bytes(const kg_fasta* f) { return f ? f->bytes.data() : nullptr; }
+extern "C" const uint64_t* kg_fasta_offsets(const kg_fasta* f) { return f ? f->off.data() : nullptr; }
+extern "C" void kg_fasta_free(kg_fasta* f) { delete f; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// loadIndexedArray, KGJ:345-373
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int kg_functions_read(const char* path, kg_functions** out) {
+    if (!path || !out) {
+        kg_set_error("kg_functions_read: null argument");
+        return KG_EINVAL;
+    }
+    std::string text;
+    if (!read_all(path, text)) {
+        kg_set_error("cannot read %s", path);
+        return KG_EIO;
+    }
+    kg_functions* fn = new kg_functions();
+    Lines in{text};
+    std::string_view line;
+    for (long line_pos = 0; in.next(line); line_pos++) {
+        size_t tab = line.find('\t');
+        long idx = -1;
+        if (tab != std::string_view::npos && tab > 0) {
+            auto r = std::from_chars(line.data(), line.data() + tab, idx);
+            if (r.ec != std::errc() || r.ptr != line.data() + tab) idx = -1;
+        }
+        if (idx != line_pos) { // KGJ:361-364
+            kg_set_error("Your index must be dense and in order (see line %ld)", line_pos);
+            delete fn;
+            return KG_EFORMAT;
+        }
+        fn->names.emplace_back(line.substr(tab + 1));
+    }
+    *out = fn;
+    return KG_OK;
+}
+extern "C" int kg_functions_load(const char* data_dir, kg_functions** out) {
+    if (!data_dir || !out) {
+        kg_set_error("kg_functions_load: null argument");
+        return KG_EINVAL;
+    }
+    std::string base = std::string(data_dir) + "/function.index";
+    if (file_exists(base + ".gz")) return kg_functions_read((base + ".gz").c_str(), out); // KGJ:754-758
+    return kg_functions_read(base.c_str(), out);
+}
+extern "C" size_t kg_functions_count(const kg_functions* f) { return f ? f->names.size() : 0; }
+extern "C" const char* kg_functions_name(const kg_functions* f, size_t i) { return (f && i < f->names.size()) ? f->names[i].c_str() : nullptr; }
+extern "C" void kg_functions_free(kg_functions* f) { delete f; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Java's %f.  Formatter widens the float to double, FloatingDecimal yields the shortest digit string that
+// round-trips, and that DECIMAL string is rounded HALF_UP to `precision` places -- so 1/128 = 0.0078125 prints as
+// 0.007813 where C's printf (exact binary value, ties to even) prints 0.007812.
+// ---------------------------------------------------------------------------------------------------------------
+static std::string java_f(float v, int prec) {
+    double d = (double)v;
+    if (std::isnan(d)) return "NaN";
+    if (std::isinf(d)) return d < 0 ? "-Infinity" : "Infinity";
+    bool neg = std::signbit(d);
+    d = std::fabs(d);
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, d, std::chars_format::scientific); // shortest round-trip
+    std::string_view s(buf, (size_t)(r.ptr - buf));
+    size_t epos = s.find('e');
+    std::string digits;
+    for (char ch : s.substr(0, epos))
+        if (ch >= '0' && ch <= '9') digits.push_back(ch);
+    int exp10 = atoi(std::string(s.substr(epos + 1)).c_str());
+    int point = exp10 + 1; // digits before the decimal point
+    std::string ip, fp;
+    if (point <= 0) {
+        ip = "0";
+        fp.assign((size_t)(-point), '0');
+        fp += digits;
+    } else if ((size_t)point >= digits.size()) {
+        ip = digits + std::string((size_t)point - digits.size(), '0');
+    } else {
+        ip = digits.substr(0, (size_t)point);
+        fp = digits.substr((size_t)point);
+    }
+    if (fp.size() < (size_t)prec + 1) fp.append((size_t)prec + 1 - fp.size(), '0');
+    bool up = fp[(size_t)prec] >= '5';
+    std::string all = ip + fp.substr(0, (size_t)prec);
+    for (size_t i = all.size(); up && i-- > 0;) {
+        if (all[i] == '9') all[i] = '0';
+        else {
+            all[i]++;
+            up = false;
+        }
+    }
+    if (up) all.insert(all.begin(), '1');
+    size_t il = all.size() - (size_t)prec;
+    std::string res = neg ? "-" : "";
+    res += all.substr(0, il);
+    if (prec > 0) {
+        res += '.';
+        res += all.substr(il);
+    }
+    return res;
+}
+extern "C" int kg_format_java_f(float v, int precision, char* out, size_t outlen) {
+    if (!out || !outlen || precision < 0 || precision > 30) return KG_EINVAL;
+    std::string s = java_f(v, precision);
+    snprintf(out, outlen, "%s", s.c_str());
+    return KG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// report, KGJ:810-818
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_fasta* fa, const kg_functions* fn,
+                               const kg_table* table, kg_result* result) {
+    if (!fa || !fn || !result) {
+        kg_set_error("kg_report_write: null argument");
+        return KG_EINVAL;
+    }
+    const kg_call* calls = nullptr;
+    const kg_otu* otus = nullptr;
+    const kg_hit* hits = nullptr;
+    size_t ncalls = 0, notus = 0, nhits = 0;
+    int rc;
+    if ((rc = kg_result_calls(result, &calls, &ncalls)) != KG_OK) return rc;
+    if ((rc = kg_result_otus(result, &otus, &notus)) != KG_OK) return rc;
+    if (debug && (rc = kg_result_hits(result, &hits, &nhits)) != KG_OK) return rc;
+    const size_t n = fa->ids.size();
+    if (notus != n) {
+        kg_set_error("kg_report_write: result has %zu sequences, FASTA has %zu", notus, n);
+        return KG_EINVAL;
+    }
+    FILE* out = path ? fopen(path, "w") : stdout;
+    if (!out) {
+        kg_set_error("cannot write %s", path);
+        return KG_EIO;
+    }
+    if (debug && table) { // KGJ:951-954
+        kg_table_info ti;
+        kg_table_get_info(table, &ti);
+        fprintf(out, "Kmer-table info: numSigs=%lld, entrySize=%lld, version=%lld\n", (long long)ti.num_slots,
+                (long long)ti.entry_size, (long long)ti.version);
+    }
+    // per-sequence ranges into the (seq, strand_frame, pos)-ordered call and hit arrays
+    std::vector<size_t> call_lo(n + 1, 0), hit_lo(n + 1, 0);
+    {
+        size_t c = 0, h = 0;
+        for (size_t s = 0; s <= n; s++) {
+            while (c < ncalls && calls[c].seq < s) c++;
+            while (h < nhits && hits[h].seq < s) h++;
+            call_lo[s] = c;
+            hit_lo[s] = h;
+        }
+    }
+    // queryIdToLen is a LinkedHashMap<String,Integer>: iteration in FIRST-insertion order with the LAST length;
+    // hitCnts.put() keeps the LAST container of a repeated (id, strand, frame).  KGJ:772, 782, 805-809.
+    std::unordered_map<std::string, size_t> last;
+    last.reserve(n * 2);
+    for (size_t i = 0; i < n; i++) last[fa->ids[i]] = i;
+    std::unordered_map<std::string, bool> seen;
+    seen.reserve(n * 2);
+    const int per_seq = mode == KG_MODE_AA ? 1 : 6;
+    char wbuf[96];
+    for (size_t i = 0; i < n; i++) {
+        if (!seen.emplace(fa->ids[i], true).second) continue;
+        const size_t s = last[fa->ids[i]];
+        const long long len = (long long)(fa->off[s + 1] - fa->off[s]);
+        const char* id = fa->ids[i].c_str();
+        if (mode == KG_MODE_AA) fprintf(out, "PROTEIN-ID\t%s\t%lld\n", id, len);       // KGJ:529
+        else fprintf(out, "processing %s[%lld]\n", id, len);                             // KGJ:541
+        size_t c = call_lo[s], h = hit_lo[s];
+        for (int k = 0; k < per_seq; k++) {
+            if (mode != KG_MODE_AA) fprintf(out, "TRANSLATION\t%s\t%lld\t%c\t%d\n", id, len, k < 3 ? '+' : '-', k % 3); // KGJ:545-548
+            int printed = 0;
+            auto flush_hits = [&](int upto) { // HIT lines precede the CALL they trigger (KGJ:472-475 before 477-508)
+                while (debug && h < hit_lo[s + 1] && hits[h].strand_frame == k && printed < upto) {
+                    kg_format_java_f(hits[h].function_wt, 3, wbuf, sizeof wbuf);
+                    fprintf(out, "HIT\t%d\t%d\t%d\t%d\t%s\t%d\n", hits[h].pos, 0, hits[h].avg_off_from_end, hits[h].fI, wbuf, hits[h].oI);
+                    h++;
+                    printed++;
+                }
+            };
+            for (; c < call_lo[s + 1] && calls[c].strand_frame == k; c++) {
+                flush_hits(calls[c].hits_before);
+                const kg_call& cl = calls[c];
+                kg_format_java_f(cl.weighted, 6, wbuf, sizeof wbuf);
+                const char* fname = (cl.fI >= 0 && (size_t)cl.fI < fn->names.size()) ? fn->names[(size_t)cl.fI].c_str() : "";
+                fprintf(out, "CALL\t%d\t%d\t%d\t%d\t%s\t%s\n", cl.start, cl.end, cl.count, cl.fI, fname, wbuf); // KGJ:398-404
+            }
+            flush_hits(0x7FFFFFFF);
+        }
+        fprintf(out, "OTU-COUNTS\t%s[%lld]", id, len); // KGJ:518-522
+        for (int j = 0; j < otus[s].n; j++) fprintf(out, "\t%d-%d", otus[s].count[j], otus[s].oI[j]);
+        fputc('\n', out);
+    }
+    if (path) fclose(out);
+    else fflush(out);
+    return KG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// main, KGJ:560-654
+// ---------------------------------------------------------------------------------------------------------------
+static void usage() { // KGJ:618-635
+    puts("Usage: kmer_guts [options] -D DataDir");
+    puts("Arguments:");
+    puts(" -a - (optional) amino acids in input FASTA (default is DNA)");
+    puts(" -d - (optional) print debug messages");
+    puts(" -m - (optional) min. number of hits in result (integer, default = 5)");
+    puts(" -M - (optional) min. sum of hit weights (integer, default = 0)");
+    puts(" -O - (optional) order constraint (don't use order by default)");
+    puts(" -g - (optional) max. gap between hits to be joined (integer, default = 200)");
+    puts(" -D - (required) data directory with kmer-table and function-index files");
+    puts(" -q - (optional) query fasta file (STDIN if not defined)");
+    puts(" -o - (optional) output file (STDOUT if not defined)");
+    puts(" -t - (optional) temporary directory (system one is used by default)");
+    puts(" -l - (optional) limit for input Kmer array (long, default = 20,000,000)");
+    puts(" -G - (extension) CUDA device index (default 0)");
+}
+
+extern "C" int kg_main(int argc, char** argv) {
+    kg_params prm;
+    kg_params_default(&prm);
+    bool aa = false, debug = false;
+    const char *dir = nullptr, *query = nullptr, *outp = nullptr;
+    int device = 0;
+    std::string err;
+    for (int i = 1; i < argc && err.empty(); i++) {
+        std::string a = argv[i];
+        if (a.empty() || a[0] != '-') { err = "Parameter name should start from '-': " + a; break; } // KGJ:569-572
+        if (a.size() != 2) { err = "Unknown parameter: " + a; break; }                               // KGJ:574-576
+        auto value = [&]() -> const char* {
+            if (i + 1 >= argc) { err = "Missing value for " + a; return "0"; }
+            return argv[++i];
+        };
+        switch (a[1]) {
+            case 'a': aa = true; break;
+            case 'd': debug = true; break;
+            case 'm': prm.min_hits = atoi(value()); break;
+            case 'M': prm.min_weighted_hits = atoi(value()); break;
+            case 'O': prm.order_constraint = 1; break;
+            case 'g': prm.max_gap = atoi(value()); break;
+            case 'D': dir = value(); break;
+            case 'q': query = value(); break;
+            case 'o': outp = value(); break;
+            // The reference's -t and -l fall through into `default` and always throw (KGJ:605-610); nothing spills to
+            // disk here, so they are accepted and ignored.
+            case 't': case 'l': value(); break;
+            case 'G': device = atoi(value()); break;
+            default: err = "Unknown parameter: " + a;
+        }
+    }
+    if (err.empty() && !dir) err = "-D parameter is required"; // KGJ:613-615
+    if (err.empty() && !query) err = "-q parameter is required (reading STDIN is unreachable in the reference too, KGJ:647)";
+    if (!err.empty()) {
+        // The reference prints this and then carries on into a NullPointerException (KGJ:616-647); exit instead.
+        printf("Error: %s\n", err.c_str());
+        usage();
+        return 2;
+    }
+    prm.emit_hits = debug ? 1 : 0;
+    auto info = [&](const std::string& msg) { // printInfoLine, KGJ:891-898 (the pw part is omitted: wall-clock lines)
+        if (outp) puts(msg.c_str());
+    };
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return (long long)std::chrono::duration_cast<std::chrono::milliseconds>(b - a).count(); };
+
+    kg_context* ctx = nullptr;
+    kg_table* table = nullptr;
+    kg_functions* fn = nullptr;
+    kg_fasta* fa = nullptr;
+    kg_result* res = nullptr;
+    int rc = 1;
+    do {
+        if (kg_init(device, &ctx) != KG_OK) break;
+        if (kg_functions_load(dir, &fn) != KG_OK) break; // KGJ:759
+        auto t0 = now();
+        if (kg_table_load(ctx, dir, &table) != KG_OK) break; // KGJ:774
+        info("Table load time: " + std::to_string(ms(t0, now())) + " ms.");
+        auto t1 = now();
+        if (kg_fasta_read(query, &fa) != KG_OK) break; // KGJ:778
+        info("Preparation time: " + std::to_string(ms(t1, now())) + " ms.");
+        auto t2 = now();
+        if (kg_run(ctx, table, aa ? KG_MODE_AA : KG_MODE_DNA, kg_fasta_bytes(fa), kg_fasta_offsets(fa), kg_fasta_count(fa), &prm, &res) != KG_OK) break;
+        info("Lookup time: " + std::to_string(ms(t2, now())) + " ms.");
+        auto t3 = now();
+        if (kg_report_write(outp, aa ? KG_MODE_AA : KG_MODE_DNA, debug, fa, fn, table, res) != KG_OK) break;
+        info("Grouping time: " + std::to_string(ms(t3, now())) + " ms.");
+        rc = 0;
+    } while (0);
+    if (rc) fprintf(stderr, "Error: %s\n", kg_last_error());
+    kg_result_free(res);
+    kg_fasta_free(fa);
+    kg_functions_free(fn);
+    kg_table_free(table);
+    kg_shutdown(ctx);
+    return rc;
+}

@@ -1,0 +1,56 @@
+// kg_internal.h -- the opaque handle types behind include/kmerguts.h.
+#pragma once
+
+#include "kg_common.cuh"
+
+struct kg_table {
+    kg_context* ctx = nullptr;
+    uint4* d_buckets = nullptr;
+    int4* d_payload = nullptr;
+    uint32_t num_buckets = 0;
+    kg_table_info info = {};
+    KgTableView view() const;
+};
+
+// Sequences resident in HBM.
+//   aa mode : the residue stream IS the uploaded byte stream (the last residue of every protein is overwritten with 0,
+//             which both separates proteins and reproduces the reference's dropped last window, KGJ:912/1055).
+//   dna mode: the residue stream is produced by the translation kernel: six virtual proteins per contig
+//             (+0,+1,+2,-0,-1,-2), each followed by at least one 0 byte.
+struct kg_batch {
+    kg_context* ctx = nullptr;
+    int mode = KG_MODE_AA;
+    uint64_t n = 0;           // sequences
+    uint64_t total = 0;       // input bytes
+    uint8_t* d_seq = nullptr; // input bytes (+ 64 bytes of zero padding)
+    uint64_t* d_off = nullptr; // n+1
+    bool owns_input = true;
+    // derived by prepare(): virtual sequences
+    uint64_t nv = 0;          // n (aa) or 6n (dna)
+    uint64_t vtotal = 0;      // residue-stream length
+    DevBuf vseq;              // dna: translated stream
+    DevBuf voff;              // dna: nv+1 uint64 offsets into the residue stream
+    const uint8_t* stream() const { return mode == KG_MODE_AA ? d_seq : vseq.as<uint8_t>(); }
+    const uint64_t* voffsets() const { return mode == KG_MODE_AA ? d_off : voff.as<uint64_t>(); }
+    bool prepared = false;
+};
+
+struct kg_result {
+    kg_context* ctx = nullptr;
+    kg_params params = {};
+    kg_run_stats stats = {};
+    int mode = KG_MODE_AA;
+    uint64_t n = 0, nv = 0;
+    // device
+    DevBuf d_calls;   // dense kg_call[num_calls]
+    DevBuf d_otus;    // kg_otu[n]
+    DevBuf d_hits;    // kg_hit[num_hits] when params.emit_hits
+    // host
+    std::vector<kg_call> calls;
+    std::vector<kg_otu> otus;
+    std::vector<kg_hit> hits;
+    bool fetched = false;
+};
+
+// kg_run.cu
+int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches);

@@ -1,0 +1,377 @@
+// kg_synth.cu -- bench/test tooling (include/kmerguts_synth.h): probe-roofline microbenchmark, CUDA generators of
+// the synthetic universe of tools/kg_synth.py, and a device-side writer of the reference's table format.
+// Nothing here is on the product path.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <algorithm>
+
+#include "../../include/kmerguts_synth.h"
+#include "kg_device.cuh"
+#include "kg_internal.h"
+
+namespace {
+
+inline unsigned blocks_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- the counter-based hashing of tools/kg_synth.py (mix64 / hash3) ----
+__host__ __device__ __forceinline__ uint64_t smix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t hash3(uint64_t seed, uint64_t a, uint64_t b) {
+    return smix64(smix64(seed + a) ^ (b * 0xD6E8FEB86659FD93ull));
+}
+
+struct DevUniverse {
+    uint64_t n_families, seed;
+    uint32_t keep, n_functions, n_otus;
+    const uint32_t* lenq; // device, 4096
+};
+__constant__ uint32_t c_cdf16[20];
+
+__device__ __forceinline__ uint32_t code_of_draw(uint32_t draw) { // np.searchsorted(cdf, draw, side="right")
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < 19; k++) c += (c_cdf16[k] <= draw);
+    return c;
+}
+__device__ __forceinline__ uint32_t family_len(const DevUniverse& u, uint64_t f) {
+    return u.lenq[hash3(u.seed, f, 0xFFFFFFFFull) & 4095];
+}
+__device__ __forceinline__ uint32_t residue_code(const DevUniverse& u, uint64_t f, uint64_t i) {
+    return code_of_draw((uint32_t)(hash3(u.seed ^ 0x11, f, i) & 0xFFFF));
+}
+__device__ __forceinline__ uint32_t random_code(uint64_t seed, uint64_t a, uint64_t b) {
+    return code_of_draw((uint32_t)(hash3(seed, a, b) & 0xFFFF));
+}
+__device__ __forceinline__ bool is_signature(const DevUniverse& u, uint64_t f, uint64_t i) {
+    return (uint32_t)(hash3(u.seed ^ 0x22, f, i) & 1023) < u.keep;
+}
+__device__ __forceinline__ float weight_of_key(uint64_t key) { // 0.5 + b/256, exact in fp32
+    uint32_t b = (uint32_t)((smix64(key) >> 17) & 0xFF);
+    return 0.5f + (float)b * (1.0f / 256.0f);
+}
+
+__global__ void k_sig_count(DevUniverse u, uint32_t* __restrict__ cnt) {
+    uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > u.n_families) return;
+    uint32_t c = 0;
+    if (f < u.n_families) {
+        uint32_t L = family_len(u, f);
+        for (uint32_t i = 0; i + KG_K <= L; i++) c += is_signature(u, f, i);
+    }
+    cnt[f] = c;
+}
+__global__ void k_sig_fill(DevUniverse u, const uint64_t* __restrict__ off, uint64_t* __restrict__ keys, int4* __restrict__ payload) {
+    uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= u.n_families) return;
+    uint32_t L = family_len(u, f);
+    uint64_t o = off[f];
+    uint64_t enc = 0;
+    for (uint32_t i = 0; i < L; i++) {
+        enc = (enc % 1280000000ull) * 20ull + residue_code(u, f, i);
+        if (i + 1 >= KG_K) {
+            uint32_t w = i + 1 - KG_K; // window start
+            if (is_signature(u, f, w)) {
+                keys[o] = enc;
+                payload[o] = make_int4((int)(f % u.n_otus), (int)(L - w), (int)(f % u.n_functions), __float_as_int(weight_of_key(enc)));
+                o++;
+            }
+        }
+    }
+}
+__global__ void k_iota(uint32_t* a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (uint32_t)i;
+}
+__global__ void k_flag_first_key(const uint64_t* __restrict__ k, size_t n, uint8_t* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0) || (k[i] != k[i - 1]);
+}
+__global__ void k_gather_entries(const uint32_t* __restrict__ r, size_t n, const uint64_t* __restrict__ ck,
+                                 const int4* __restrict__ cp, uint64_t* __restrict__ ok, int4* __restrict__ op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ok[i] = ck[r[i]];
+    op[i] = cp[r[i]];
+}
+
+// ---- proteins ----
+__global__ void k_prot_len(DevUniverse u, uint64_t first, uint64_t n, uint64_t seed, uint64_t* __restrict__ len) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n) return;
+    if (t == n) { len[t] = 0; return; }
+    uint64_t j = first + t;
+    uint64_t h = hash3(seed, j, 0xFFFFFFFFull);
+    if ((h & 0xFF) < 51) len[t] = u.lenq[(h >> 8) & 4095];
+    else len[t] = family_len(u, (h >> 8) % u.n_families);
+}
+__global__ void k_prot_fill(DevUniverse u, uint64_t first, uint64_t n, uint64_t seed, const uint64_t* __restrict__ off,
+                            uint8_t* __restrict__ out) {
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per protein
+    const int lane = threadIdx.x & 31;
+    if (t >= n) return;
+    const uint64_t j = first + t;
+    const uint64_t h = hash3(seed, j, 0xFFFFFFFFull);
+    const bool decoy = (h & 0xFF) < 51;
+    const uint64_t f = (h >> 8) % u.n_families;
+    const uint64_t o = off[t], L = off[t + 1] - o;
+    const char* alpha = "ACDEFGHIKLMNPQRSTVWY";
+    for (uint64_t i = lane; i < L; i += 32) {
+        uint32_t code;
+        if (decoy) {
+            code = random_code(seed ^ 0x33, j, i);
+        } else {
+            bool sub = (hash3(seed ^ 0x44, j, i) & 0xFFFF) < 6554;
+            code = sub ? random_code(seed ^ 0x55, j, i) : residue_code(u, f, i);
+        }
+        bool isx = ((hash3(seed ^ 0x66, j, i) >> 20) & 0xFFFFF) < 105;
+        out[o + i] = isx ? (uint8_t)'X' : (uint8_t)alpha[code];
+    }
+}
+
+// ---- reference-format image: linear probing without wrap over 24-byte slots (3 x uint64 words each) ----
+__global__ void k_image_init(unsigned long long* __restrict__ w, uint64_t num_slots) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= num_slots) return;
+    w[3 * s] = (unsigned long long)(KG_MAX_ENCODED + 1); // whichKmer > MAX_ENCODED marks an empty slot (KGJ:1000)
+    w[3 * s + 1] = 0;
+    w[3 * s + 2] = 0;
+}
+__global__ void k_image_insert(unsigned long long* __restrict__ w, uint64_t num_slots, const uint64_t* __restrict__ keys,
+                               const int4* __restrict__ payload, uint64_t n, unsigned long long* __restrict__ err) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i], empty = (unsigned long long)(KG_MAX_ENCODED + 1);
+    const int4 p = payload[i];
+    for (uint64_t s = key % num_slots;; s++) {
+        if (s + 1 >= num_slots) { // the last slot stays empty so that no chain can run off the end
+            atomicAdd(err, 1ull);
+            return;
+        }
+        unsigned long long old = atomicCAS(&w[3 * s], empty, key);
+        if (old == empty) {
+            w[3 * s + 1] = (unsigned long long)(uint32_t)p.x | ((unsigned long long)(uint32_t)p.y << 32); // otu, avgFromEnd
+            w[3 * s + 2] = (unsigned long long)(uint32_t)p.z | ((unsigned long long)(uint32_t)p.w << 32); // fI, wt bits
+            return;
+        }
+    }
+}
+
+// ---- R_probe ----
+template <int U>
+__global__ void k_random_sectors(const uint4* __restrict__ buf, uint64_t n_sectors, uint32_t per_thread, uint32_t* __restrict__ sink) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < per_thread; it += U) {
+        KgBucket b[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            uint64_t h = smix64(tid * 0x100000001B3ull + it + k);
+            uint32_t idx = (uint32_t)(((h >> 32) * n_sectors) >> 32);
+            b[k] = kg_load_bucket(buf, idx);
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) acc ^= b[k].w[0] ^ b[k].w[3] ^ b[k].w[7];
+    }
+    if (acc == 0x9E3779B9u) sink[0] = acc; // keeps the loads alive
+}
+
+int upload_universe(kg_context* ctx, const kg_universe* u, DevUniverse* du, uint32_t** d_lenq) {
+    CU(cudaMalloc(d_lenq, 4096 * 4));
+    CU(cudaMemcpyAsync(*d_lenq, u->lenq, 4096 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyToSymbolAsync(c_cdf16, u->cdf16, 20 * 4, 0, cudaMemcpyHostToDevice, ctx->stream));
+    du->n_families = u->n_families;
+    du->seed = u->seed;
+    du->keep = u->sig_keep_per_1024;
+    du->n_functions = u->n_functions;
+    du->n_otus = u->n_otus;
+    du->lenq = *d_lenq;
+    return KG_OK;
+}
+
+} // namespace
+
+extern "C" void kg_device_free(void* p) {
+    if (p) cudaFree(p);
+}
+extern "C" int kg_device_to_host(kg_context* ctx, void* host, const void* dev, uint64_t bytes) {
+    if (!ctx || (bytes && (!host || !dev))) KG_FAIL(KG_EINVAL, "kg_device_to_host: null argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KG_OK;
+}
+
+extern "C" int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64_t max_sigs, uint64_t** out_keys,
+                                   void** out_payload, uint64_t* out_n) {
+    if (!ctx || !u || !out_keys || !out_payload || !out_n) KG_FAIL(KG_EINVAL, "kg_synth_signatures: null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevUniverse du;
+    uint32_t* d_lenq = nullptr;
+    KG_TRY(upload_universe(ctx, u, &du, &d_lenq));
+    const uint64_t F = u->n_families;
+    uint32_t* cnt = nullptr;
+    uint64_t* off = nullptr;
+    CU(cudaMalloc(&cnt, (F + 1) * 4));
+    CU(cudaMalloc(&off, (F + 1) * 8));
+    k_sig_count<<<blocks_for(F + 1, 128), 128, 0, st>>>(du, cnt);
+    size_t tmp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, off, F + 1, st));
+    KG_TRY(ctx->scan_tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, cnt, off, F + 1, st));
+    uint64_t C = 0;
+    CU(cudaMemcpyAsync(&C, off + F, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (C >= (1ull << 32)) KG_FAIL(KG_ERANGE, "kg_synth_signatures: %llu candidates", (unsigned long long)C);
+    uint64_t *ck = nullptr, *ck2 = nullptr;
+    int4* cp = nullptr;
+    uint32_t *r1 = nullptr, *r2 = nullptr;
+    uint8_t* flag = nullptr;
+    size_t* d_nsel = nullptr;
+    CU(cudaMalloc(&ck, std::max<uint64_t>(C, 1) * 8));
+    CU(cudaMalloc(&ck2, std::max<uint64_t>(C, 1) * 8));
+    CU(cudaMalloc(&cp, std::max<uint64_t>(C, 1) * sizeof(int4)));
+    CU(cudaMalloc(&r1, std::max<uint64_t>(C, 1) * 4));
+    CU(cudaMalloc(&r2, std::max<uint64_t>(C, 1) * 4));
+    CU(cudaMalloc(&flag, std::max<uint64_t>(C, 1)));
+    CU(cudaMalloc(&d_nsel, sizeof(size_t)));
+    k_sig_fill<<<blocks_for(F, 128), 128, 0, st>>>(du, off, ck, cp);
+    k_iota<<<blocks_for(C, 256), 256, 0, st>>>(r1, C);
+    // first occurrence (lowest candidate rank) of every key: stable sort by key, keep the head of each run
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ck, ck2, r1, r2, C, 0, 35, st));
+    KG_TRY(ctx->scan_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, ck, ck2, r1, r2, C, 0, 35, st));
+    k_flag_first_key<<<blocks_for(C, 256), 256, 0, st>>>(ck2, C, flag);
+    CU(cub::DeviceSelect::Flagged(nullptr, tmp, r2, flag, r1, d_nsel, C, st));
+    KG_TRY(ctx->scan_tmp.ensure(tmp));
+    CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, r2, flag, r1, d_nsel, C, st));
+    size_t U = 0;
+    CU(cudaMemcpyAsync(&U, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // back to family-major order, then truncate
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, r1, r2, U, 0, 32, st));
+    KG_TRY(ctx->scan_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortKeys(ctx->scan_tmp.p, tmp, r1, r2, U, 0, 32, st));
+    uint64_t n = max_sigs ? std::min<uint64_t>(U, max_sigs) : U;
+    uint64_t* ok = nullptr;
+    int4* op = nullptr;
+    CU(cudaMalloc(&ok, std::max<uint64_t>(n, 1) * 8));
+    CU(cudaMalloc(&op, std::max<uint64_t>(n, 1) * sizeof(int4)));
+    k_gather_entries<<<blocks_for(n, 256), 256, 0, st>>>(r2, n, ck, cp, ok, op);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (void* p : {(void*)cnt, (void*)off, (void*)ck, (void*)ck2, (void*)cp, (void*)r1, (void*)r2, (void*)flag, (void*)d_nsel, (void*)d_lenq}) cudaFree(p);
+    *out_keys = ok;
+    *out_payload = op;
+    *out_n = n;
+    return KG_OK;
+}
+
+extern "C" int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t first, uint64_t n, uint64_t seed,
+                                 uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes) {
+    if (!ctx || !u || !d_seq || !d_off || !total_bytes) KG_FAIL(KG_EINVAL, "kg_synth_proteins: null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevUniverse du;
+    uint32_t* d_lenq = nullptr;
+    KG_TRY(upload_universe(ctx, u, &du, &d_lenq));
+    uint64_t *len = nullptr, *off = nullptr;
+    CU(cudaMalloc(&len, (n + 1) * 8));
+    CU(cudaMalloc(&off, (n + 1) * 8));
+    k_prot_len<<<blocks_for(n + 1, 256), 256, 0, st>>>(du, first, n, seed, len);
+    size_t tmp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, off, n + 1, st));
+    KG_TRY(ctx->scan_tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, len, off, n + 1, st));
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, off + n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint8_t* seq = nullptr;
+    CU(cudaMalloc(&seq, total + 64));
+    CU(cudaMemsetAsync(seq + total, 0, 64, st));
+    if (n) k_prot_fill<<<blocks_for(n * 32, 256), 256, 0, st>>>(du, first, n, seed, off, seq);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaFree(len);
+    cudaFree(d_lenq);
+    *d_seq = seq;
+    *d_off = off;
+    *total_bytes = total;
+    return KG_OK;
+}
+
+extern "C" int kg_synth_reference_image(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, uint64_t n,
+                                        uint64_t num_slots, void* host_image) {
+    if (!ctx || !host_image || num_slots < 2) KG_FAIL(KG_EINVAL, "kg_synth_reference_image: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    unsigned long long *w = nullptr, *err = nullptr;
+    CU(cudaMalloc(&w, num_slots * 24));
+    CU(cudaMalloc(&err, 8));
+    CU(cudaMemsetAsync(err, 0, 8, st));
+    k_image_init<<<blocks_for(num_slots, 256), 256, 0, st>>>(w, num_slots);
+    if (n) k_image_insert<<<blocks_for(n, 256), 256, 0, st>>>(w, num_slots, d_keys, (const int4*)d_payload16, n, err);
+    unsigned long long herr = 0;
+    CU(cudaMemcpyAsync(&herr, err, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int64_t hdr[3] = {(int64_t)num_slots, 24, 1}; // numSigs, entrySize, version (KGJ:933-935)
+    memcpy(host_image, hdr, 24);
+    cudaError_t e = cudaMemcpy((uint8_t*)host_image + 24, w, num_slots * 24, cudaMemcpyDeviceToHost);
+    cudaFree(w);
+    cudaFree(err);
+    if (e != cudaSuccess) KG_FAIL(KG_ECUDA, "image copy failed: %s", cudaGetErrorString(e));
+    if (herr) KG_FAIL(KG_ERANGE, "reference image: %llu keys would run off the end of %llu slots", herr, (unsigned long long)num_slots);
+    return KG_OK;
+}
+
+static int roofline_run(kg_context* ctx, const uint4* buf, uint64_t n_sectors, uint64_t n_loads, int tpb, int inflight, double* out) {
+    if (tpb < 32 || tpb > 1024 || (tpb & 31)) KG_FAIL(KG_EINVAL, "threads_per_block must be a multiple of 32 in [32, 1024]");
+    if (n_sectors == 0 || n_sectors >= (1ull << 32)) KG_FAIL(KG_EINVAL, "roofline buffer must hold 1..2^32-1 sectors");
+    cudaStream_t st = ctx->stream;
+    const uint32_t per_thread = 64;
+    uint64_t threads = (n_loads + per_thread - 1) / per_thread;
+    unsigned grid = blocks_for(threads, (unsigned)tpb);
+    uint32_t* sink = nullptr;
+    CU(cudaMalloc(&sink, 4));
+    auto launch = [&]() {
+        switch (inflight) {
+            case 1: k_random_sectors<1><<<grid, tpb, 0, st>>>(buf, n_sectors, per_thread, sink); break;
+            case 2: k_random_sectors<2><<<grid, tpb, 0, st>>>(buf, n_sectors, per_thread, sink); break;
+            case 4: k_random_sectors<4><<<grid, tpb, 0, st>>>(buf, n_sectors, per_thread, sink); break;
+            default: k_random_sectors<8><<<grid, tpb, 0, st>>>(buf, n_sectors, per_thread, sink); break;
+        }
+    };
+    launch(); // warm-up
+    CU(cudaEventRecord(ctx->ev[0], st));
+    launch();
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(cudaEventSynchronize(ctx->ev[1]));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    cudaFree(sink);
+    *out = (double)grid * tpb * per_thread / ((double)ms * 1e-3);
+    return KG_OK;
+}
+
+extern "C" int kg_probe_roofline(kg_context* ctx, uint64_t bytes, uint64_t n_loads, int tpb, int inflight, double* out) {
+    if (!ctx || !out) KG_FAIL(KG_EINVAL, "kg_probe_roofline: null argument");
+    CU(cudaSetDevice(ctx->device));
+    uint4* buf = nullptr;
+    CU(cudaMalloc(&buf, bytes));
+    CU(cudaMemsetAsync(buf, 0x5A, bytes, ctx->stream));
+    int rc = roofline_run(ctx, buf, bytes / 32, n_loads, tpb, inflight, out);
+    cudaFree(buf);
+    return rc;
+}
+extern "C" int kg_probe_roofline_table(kg_context* ctx, const kg_table* table, uint64_t n_loads, int tpb, int inflight, double* out) {
+    if (!ctx || !table || !out) KG_FAIL(KG_EINVAL, "kg_probe_roofline_table: null argument");
+    CU(cudaSetDevice(ctx->device));
+    return roofline_run(ctx, table->d_buckets, (uint64_t)table->num_buckets + KG_TAIL_BUCKETS, n_loads, tpb, inflight, out);
+}

@@ -1,0 +1,478 @@
+// kg_table.cu -- loader for the reference's kmer.table.mem_map[.gz] and the device-side builder of the
+// one-sector-per-probe bucket table (layout: kg_common.cuh).
+//
+// Replaces: readKmerTableHeader (KGJ:924-942), the 24-byte little-endian entry decode of lookup (KGJ:995-999,
+// 1097-1130) and -- semantically -- the table side of the sort-merge join (KGJ:959-1026).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <stdarg.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <algorithm>
+
+#include "kg_device.cuh"
+#include "kg_internal.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors / small host helpers (shared by all translation units)
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void kg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* kg_last_error(void) { return g_err; }
+extern "C" const char* kg_version(void) { return "kmerguts_b200 0.1 (sm_100a)"; }
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return KG_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        p = nullptr;
+        KG_FAIL(KG_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = want;
+    return KG_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reference-format image parser (streaming, so a 10-100 GB file never has to sit in host memory twice)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ImageParser {
+    int64_t num_slots = 0, entry_size = 0, version = 0;
+    bool header_done = false;
+    uint8_t carry[24];
+    size_t ncarry = 0;
+    int64_t slot = 0, run_start = 0;
+    bool in_run = false;
+    int64_t unreachable = 0, unmatchable = 0;
+    std::vector<uint64_t> keys;
+    std::vector<int4> payload;
+    std::string error;
+
+    bool header(const uint8_t* h) {
+        memcpy(&num_slots, h, 8);      // readLongLE x3, KGJ:933-935 (x86 is little-endian)
+        memcpy(&entry_size, h + 8, 8);
+        memcpy(&version, h + 16, 8);
+        header_done = true;
+        if (entry_size != 24) { // KGJ:992 skips by entrySize but KGJ:995-999 always reads 24 bytes
+            error = "kmer table: entrySize " + std::to_string(entry_size) + " != 24 is not readable by the reference either";
+            return false;
+        }
+        if (num_slots <= 0) {
+            error = "kmer table: numSigs " + std::to_string(num_slots) + " <= 0";
+            return false;
+        }
+        size_t guess = (size_t)std::min<int64_t>(num_slots / 2 + 16, (int64_t)1 << 33);
+        keys.reserve(guess);
+        payload.reserve(guess);
+        return true;
+    }
+    inline void entry(const uint8_t* e) {
+        int64_t k;
+        memcpy(&k, e, 8);
+        if (k > KG_MAX_ENCODED) { // empty slot, KGJ:1000: every pending probe chain ends here
+            in_run = false;
+        } else {
+            if (!in_run) {
+                in_run = true;
+                run_start = slot;
+            }
+            if (k >= 0 && k < KG_MAX_ENCODED) {
+                // The reference probes slots h, h+1, ... (h = key % numSigs) until an empty slot, with NO wrap-around
+                // (KGJ:959-1026).  It can therefore return this slot iff h lies inside the occupied run that ends here.
+                int64_t h = k % num_slots;
+                if (h >= run_start && h <= slot) {
+                    int4 p;
+                    memcpy(&p, e + 8, 16); // otuIndex, avgFromEnd, functionIndex, functionWt bits (KGJ:996-999)
+                    keys.push_back((uint64_t)k);
+                    payload.push_back(p);
+                } else {
+                    unreachable++;
+                }
+            } else {
+                unmatchable++; // occupies a slot (extends chains) but no valid 8-mer encodes to it
+            }
+        }
+        slot++;
+    }
+    bool feed(const uint8_t* p, size_t n) {
+        if (ncarry) {
+            size_t need = 24 - ncarry, take = std::min(need, n);
+            memcpy(carry + ncarry, p, take);
+            ncarry += take;
+            p += take;
+            n -= take;
+            if (ncarry < 24) return true;
+            ncarry = 0;
+            if (!header_done) {
+                if (!header(carry)) return false;
+            } else {
+                entry(carry);
+            }
+        }
+        if (!header_done && n >= 24) {
+            if (!header(p)) return false;
+            p += 24;
+            n -= 24;
+        }
+        if (header_done) {
+            size_t whole = n / 24;
+            for (size_t i = 0; i < whole; i++) entry(p + 24 * i);
+            p += whole * 24;
+            n -= whole * 24;
+        }
+        if (n) {
+            memcpy(carry, p, n);
+            ncarry = n;
+        }
+        return true;
+    }
+    int64_t tail_run() const { return in_run ? slot - run_start : 0; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// device builder
+// ---------------------------------------------------------------------------------------------------------------
+struct MaxI64 {
+    __host__ __device__ __forceinline__ long long operator()(long long a, long long b) const { return a > b ? a : b; }
+};
+
+__global__ void k_make_composite(const uint64_t* __restrict__ keys, size_t n, uint32_t nb, uint64_t* __restrict__ comp,
+                                 uint32_t* __restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = keys[i];
+    comp[i] = ((uint64_t)kg_home_bucket(k, nb) << 35) | k;
+    idx[i] = (uint32_t)i;
+}
+
+__global__ void k_flag_first(const uint64_t* __restrict__ comp, size_t n, uint8_t* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (i == 0) || (comp[i] != comp[i - 1]); // equal keys are adjacent; the stable sort keeps the lowest slot first
+}
+
+__global__ void k_slot_bias(const uint64_t* __restrict__ comp, size_t n, long long* __restrict__ t) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    t[i] = (long long)(comp[i] >> 35) * KG_BUCKET_KEYS - (long long)i;
+}
+
+__global__ void k_init_buckets(uint4* __restrict__ buckets, size_t nbuckets_total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbuckets_total) return;
+    buckets[2 * i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    buckets[2 * i + 1] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, KG_W7_EMPTY);
+}
+
+// Keys sorted by home bucket take the first free slot at or after their bucket's first slot:
+//   slot_r = max(slot_{r-1} + 1, 7*home_r)  <=>  slot_r = r + max_{q<=r}(7*home_q - q)     (an inclusive max-scan)
+// Bucket b gets the overflow flag iff the key in the first slot of bucket b+1 has its home at or before b.
+__global__ void k_scatter(const uint64_t* __restrict__ comp, const uint32_t* __restrict__ idx,
+                          const long long* __restrict__ tmax, size_t n, const int4* __restrict__ payload_in,
+                          uint32_t* __restrict__ words, int4* __restrict__ payload_out, uint64_t total_slots,
+                          unsigned long long* __restrict__ err) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint64_t c = comp[r];
+    uint64_t key = c & 0x7FFFFFFFFull;
+    uint64_t home = c >> 35;
+    uint64_t slot = (uint64_t)((long long)r + tmax[r]);
+    if (slot >= total_slots) {
+        atomicAdd(err, 1ull);
+        return;
+    }
+    uint64_t b = slot / KG_BUCKET_KEYS;
+    uint32_t lane = (uint32_t)(slot - b * KG_BUCKET_KEYS);
+    words[b * 8 + lane] = (uint32_t)key;
+    uint32_t hi = (uint32_t)(key >> 32);
+    atomicAnd(&words[b * 8 + 7], ~(7u << (3 * lane)) | (hi << (3 * lane)));
+    if (lane == 0 && home < b) atomicOr(&words[(b - 1) * 8 + 7], KG_W7_FLAG);
+    payload_out[slot] = payload_in[idx[r]];
+}
+
+__global__ void k_count_flagged(const uint32_t* __restrict__ words, size_t nbuckets_total, unsigned long long* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool f = i < nbuckets_total && (words[i * 8 + 7] & KG_W7_FLAG);
+    unsigned m = __ballot_sync(0xFFFFFFFFu, f);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+// every input key must be found, with the payload it came with
+__global__ void k_verify(KgTableView t, const uint64_t* __restrict__ keys, const int4* __restrict__ payload, size_t n,
+                         const uint8_t* __restrict__ keep_flag_sorted_unused, unsigned long long* bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = kg_lookup(t, keys[i]);
+    bool ok = s != 0xFFFFFFFFu;
+    if (ok) {
+        int4 a = t.payload[s], b = payload[i];
+        ok = a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
+    }
+    if (!ok) atomicAdd(bad, 1ull);
+}
+
+inline unsigned blocks_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+} // namespace
+
+KgTableView kg_table::view() const {
+    KgTableView v;
+    v.buckets = d_buckets;
+    v.payload = d_payload;
+    v.num_buckets = num_buckets;
+    return v;
+}
+
+// d_keys / d_payload: device arrays in the reference's SLOT order (so that of two equal keys the earlier slot wins).
+static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* d_payload, size_t n, double load,
+                           bool verify_payload, kg_table* t) {
+    if (n >= (1ull << 32)) KG_FAIL(KG_ERANGE, "table: %zu signatures do not fit the 32-bit slot index", n);
+    cudaStream_t st = ctx->stream;
+    uint64_t nb64 = (uint64_t)((double)n / (KG_BUCKET_KEYS * load)) + 1;
+    if (nb64 < 64) nb64 = 64;
+    if (nb64 + KG_TAIL_BUCKETS >= (1ull << 29)) KG_FAIL(KG_ERANGE, "table: %llu buckets exceed the 29-bit bucket index", (unsigned long long)nb64);
+    const uint32_t nb = (uint32_t)nb64;
+    const size_t nb_total = (size_t)nb + KG_TAIL_BUCKETS;
+    const uint64_t total_slots = (uint64_t)nb_total * KG_BUCKET_KEYS;
+    if (total_slots >= (1ull << 32)) KG_FAIL(KG_ERANGE, "table: %llu slots exceed the 32-bit slot index", (unsigned long long)total_slots);
+
+    CU(cudaMalloc(&t->d_buckets, nb_total * 32));
+    CU(cudaMalloc(&t->d_payload, total_slots * sizeof(int4)));
+    t->num_buckets = nb;
+    k_init_buckets<<<blocks_for(nb_total, 256), 256, 0, st>>>(t->d_buckets, nb_total);
+    CU(cudaMemsetAsync(t->d_payload, 0, total_slots * sizeof(int4), st));
+
+    unsigned long long* d_ctr = nullptr; // [0] scatter overflow, [1] flagged buckets, [2] verify failures
+    CU(cudaMalloc(&d_ctr, 4 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), st));
+    size_t n_unique = n;
+
+    if (n > 0) {
+        uint64_t *comp_a = nullptr, *comp_b = nullptr;
+        uint32_t *idx_a = nullptr, *idx_b = nullptr;
+        long long* tb = nullptr;
+        uint8_t* flag = nullptr;
+        size_t* d_nsel = nullptr;
+        CU(cudaMalloc(&comp_a, n * 8));
+        CU(cudaMalloc(&comp_b, n * 8));
+        CU(cudaMalloc(&idx_a, n * 4));
+        CU(cudaMalloc(&idx_b, n * 4));
+        CU(cudaMalloc(&flag, n));
+        CU(cudaMalloc(&d_nsel, sizeof(size_t)));
+        k_make_composite<<<blocks_for(n, 256), 256, 0, st>>>(d_keys, n, nb, comp_a, idx_a);
+
+        int end_bit = 35;
+        while (end_bit < 64 && (nb_total >> (end_bit - 35)) != 0) end_bit++;
+        cub::DoubleBuffer<uint64_t> dk(comp_a, comp_b);
+        cub::DoubleBuffer<uint32_t> dv(idx_a, idx_b);
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, end_bit, st));
+        KG_TRY(ctx->scan_tmp.ensure(tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp_bytes, dk, dv, n, 0, end_bit, st));
+        uint64_t* comp = dk.Current();
+        uint32_t* idx = dv.Current();
+        uint64_t* comp_o = dk.Alternate();
+        uint32_t* idx_o = dv.Alternate();
+
+        // drop repeated keys (a malformed file may hold one key twice; the reference returns the first on the chain)
+        k_flag_first<<<blocks_for(n, 256), 256, 0, st>>>(comp, n, flag);
+        size_t sel_bytes = 0;
+        CU(cub::DeviceSelect::Flagged(nullptr, sel_bytes, comp, flag, comp_o, d_nsel, n, st));
+        KG_TRY(ctx->scan_tmp.ensure(sel_bytes));
+        CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, sel_bytes, comp, flag, comp_o, d_nsel, n, st));
+        CU(cub::DeviceSelect::Flagged(nullptr, sel_bytes, idx, flag, idx_o, d_nsel, n, st));
+        KG_TRY(ctx->scan_tmp.ensure(sel_bytes));
+        CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, sel_bytes, idx, flag, idx_o, d_nsel, n, st));
+        CU(cudaMemcpyAsync(&n_unique, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        comp = comp_o;
+        idx = idx_o;
+
+        CU(cudaMalloc(&tb, n_unique * 8));
+        k_slot_bias<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, tb);
+        size_t scan_bytes = 0;
+        CU(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, tb, tb, MaxI64(), n_unique, st));
+        KG_TRY(ctx->scan_tmp.ensure(scan_bytes));
+        CU(cub::DeviceScan::InclusiveScan(ctx->scan_tmp.p, scan_bytes, tb, tb, MaxI64(), n_unique, st));
+        k_scatter<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, idx, tb, n_unique, d_payload, (uint32_t*)t->d_buckets,
+                                                            t->d_payload, total_slots, d_ctr);
+        k_count_flagged<<<blocks_for(nb_total, 256), 256, 0, st>>>((const uint32_t*)t->d_buckets, nb_total, d_ctr + 1);
+        // Every stored key must be found again.  With repeated keys only the surviving copy's payload can match, so
+        // the payload comparison is skipped for inputs that had duplicates.
+        (void)verify_payload;
+        CU(cudaStreamSynchronize(st));
+        if (n_unique == n) {
+            k_verify<<<blocks_for(n, 256), 256, 0, st>>>(t->view(), d_keys, d_payload, n, nullptr, d_ctr + 2);
+        }
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        cudaFree(comp_a);
+        cudaFree(comp_b);
+        cudaFree(idx_a);
+        cudaFree(idx_b);
+        cudaFree(flag);
+        cudaFree(d_nsel);
+        cudaFree(tb);
+    }
+    unsigned long long h_ctr[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_ctr);
+    if (h_ctr[0]) KG_FAIL(KG_EFORMAT, "table build: %llu keys spilled past the tail buckets (load %.2f too high?)", h_ctr[0], load);
+    if (h_ctr[2]) KG_FAIL(KG_ECUDA, "table build: %llu stored keys are not found again", h_ctr[2]);
+    t->info.num_signatures = (int64_t)n_unique;
+    t->info.num_buckets = (int64_t)nb_total;
+    t->info.flagged_buckets = (int64_t)h_ctr[1];
+    t->info.device_bytes = (int64_t)(nb_total * 32 + total_slots * sizeof(int4));
+    return KG_OK;
+}
+
+static double table_load_factor() {
+    const char* e = getenv("KG_TABLE_LOAD");
+    double v = e ? atof(e) : 0.0;
+    return (v > 0.05 && v < 0.95) ? v : 0.60;
+}
+
+static int table_from_parser(kg_context* ctx, ImageParser& ps, kg_table** out) {
+    if (!ps.header_done) KG_FAIL(KG_EIO, "kmer table: EOF inside the 24-byte header");
+    CU(cudaSetDevice(ctx->device));
+    kg_table* t = new kg_table();
+    t->ctx = ctx;
+    t->info.num_slots = ps.num_slots;
+    t->info.entry_size = ps.entry_size;
+    t->info.version = ps.version;
+    t->info.num_unreachable = ps.unreachable + ps.unmatchable;
+    t->info.tail_run = ps.tail_run();
+    size_t n = ps.keys.size();
+    uint64_t* d_keys = nullptr;
+    int4* d_payload = nullptr;
+    int rc = KG_OK;
+    do {
+        if (n) {
+            if (cudaMalloc(&d_keys, n * 8) != cudaSuccess || cudaMalloc(&d_payload, n * sizeof(int4)) != cudaSuccess) {
+                kg_set_error("table: device allocation for %zu entries failed", n);
+                rc = KG_ENOMEM;
+                break;
+            }
+            cudaMemcpyAsync(d_keys, ps.keys.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpyAsync(d_payload, ps.payload.data(), n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream);
+        }
+        rc = build_on_device(ctx, d_keys, d_payload, n, table_load_factor(), true, t);
+    } while (0);
+    if (d_keys) cudaFree(d_keys);
+    if (d_payload) cudaFree(d_payload);
+    if (rc != KG_OK) {
+        kg_table_free(t);
+        return rc;
+    }
+    *out = t;
+    return KG_OK;
+}
+
+extern "C" int kg_table_from_image(kg_context* ctx, const void* image, size_t nbytes, kg_table** table) {
+    if (!ctx || !image || !table) KG_FAIL(KG_EINVAL, "kg_table_from_image: null argument");
+    ImageParser ps;
+    if (!ps.feed((const uint8_t*)image, nbytes)) KG_FAIL(KG_EFORMAT, "%s", ps.error.c_str());
+    return table_from_parser(ctx, ps, table);
+}
+
+extern "C" int kg_table_load_file(kg_context* ctx, const char* path, kg_table** table) {
+    if (!ctx || !path || !table) KG_FAIL(KG_EINVAL, "kg_table_load_file: null argument");
+    ImageParser ps;
+    std::vector<uint8_t> buf(8u << 20);
+    size_t len = strlen(path);
+    bool gz = len > 3 && strcmp(path + len - 3, ".gz") == 0; // the reference keys on the suffix (KGJ:927)
+    if (gz) {
+        gzFile g = gzopen(path, "rb");
+        if (!g) KG_FAIL(KG_EIO, "cannot open %s", path);
+        gzbuffer(g, 1 << 20);
+        for (;;) {
+            int got = gzread(g, buf.data(), (unsigned)buf.size());
+            if (got < 0) {
+                gzclose(g);
+                KG_FAIL(KG_EIO, "gzip error reading %s", path);
+            }
+            if (got == 0) break;
+            if (!ps.feed(buf.data(), (size_t)got)) {
+                gzclose(g);
+                KG_FAIL(KG_EFORMAT, "%s: %s", path, ps.error.c_str());
+            }
+        }
+        gzclose(g);
+    } else {
+        FILE* f = fopen(path, "rb");
+        if (!f) KG_FAIL(KG_EIO, "cannot open %s", path);
+        for (;;) {
+            size_t got = fread(buf.data(), 1, buf.size(), f);
+            if (got == 0) break;
+            if (!ps.feed(buf.data(), got)) {
+                fclose(f);
+                KG_FAIL(KG_EFORMAT, "%s: %s", path, ps.error.c_str());
+            }
+        }
+        fclose(f);
+    }
+    return table_from_parser(ctx, ps, table);
+}
+
+extern "C" int kg_table_load(kg_context* ctx, const char* data_dir, kg_table** table) {
+    if (!ctx || !data_dir || !table) KG_FAIL(KG_EINVAL, "kg_table_load: null argument");
+    std::string base = std::string(data_dir) + "/kmer.table.mem_map";
+    std::string gz = base + ".gz";
+    struct stat st;
+    if (stat(gz.c_str(), &st) == 0) return kg_table_load_file(ctx, gz.c_str(), table); // KGJ:750-753
+    return kg_table_load_file(ctx, base.c_str(), table);
+}
+
+extern "C" int kg_table_from_device_entries(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, size_t n,
+                                            kg_table** table) {
+    if (!ctx || !table || (n && (!d_keys || !d_payload16))) KG_FAIL(KG_EINVAL, "kg_table_from_device_entries: null argument");
+    CU(cudaSetDevice(ctx->device));
+    kg_table* t = new kg_table();
+    t->ctx = ctx;
+    t->info.entry_size = 24;
+    t->info.version = 1;
+    int rc = build_on_device(ctx, d_keys, (const int4*)d_payload16, n, table_load_factor(), true, t);
+    if (rc != KG_OK) {
+        kg_table_free(t);
+        return rc;
+    }
+    *table = t;
+    return KG_OK;
+}
+
+extern "C" int kg_table_get_info(const kg_table* table, kg_table_info* info) {
+    if (!table || !info) KG_FAIL(KG_EINVAL, "kg_table_get_info: null argument");
+    *info = table->info;
+    return KG_OK;
+}
+
+extern "C" void kg_table_free(kg_table* t) {
+    if (!t) return;
+    if (t->d_buckets) cudaFree(t->d_buckets);
+    if (t->d_payload) cudaFree(t->d_payload);
+    delete t;
+}

@@ -1,0 +1,190 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI against the CPU oracle, bit-exact for
+hit positions, function/OTU ids, calls and (because the fp32 sum keeps the reference's order) weighted scores."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.parity import assert_same
+from tools import kg_synth as synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FLAGS = [dict(), dict(order_constraint=1), dict(min_hits=3, max_gap=50, min_weighted_hits=2), dict(min_hits=2, max_gap=5)]
+
+
+@pytest.fixture(scope="module")
+def kg():
+    import kmergutsjava_b200 as kg
+    return kg
+
+
+@pytest.fixture(scope="module")
+def ctx(kg):
+    c = kg.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def universe():
+    u = synth.Universe(n_families=300, seed=0x4B470003)
+    keys, otu, avg, fi, wt = u.signatures()
+    return u, synth.build_table_image(keys, otu, avg, fi, wt), len(keys)
+
+
+def test_table_build(kg, ctx, universe):
+    u, img, nsig = universe
+    t = ctx.table_from_image(img)
+    ti = t.info
+    assert ti.num_signatures == nsig and ti.num_unreachable == 0 and ti.tail_run == 0
+    assert ti.entry_size == 24 and ti.num_slots == int(np.frombuffer(img[:8], "<i8")[0])
+    assert ti.flagged_buckets < ti.num_buckets * 0.2
+    t.free()
+
+
+@pytest.mark.parametrize("flags", FLAGS)
+def test_aa_parity(kg, ctx, oracle, universe, flags):
+    u, img, _ = universe
+    seqs = u.proteins(500, seed=21) + [b"", b"A", b"ACDEFGHI", b"ACDEFGHIK", b"acdefghiklmnp", b"ACDEFGHIKXLMNPQRSTVWY", b""]
+    sb, off = oracle.concat(seqs)
+    t = ctx.table_from_image(img)
+    res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1, **flags))
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True, **flags), sb, off, oracle.STREAM_JOIN)
+    assert len(ref.calls) > 20
+    assert_same(res, ref, what=f"aa {flags}")
+    res.free()
+    t.free()
+
+
+@pytest.mark.parametrize("flags", FLAGS[:3])
+def test_dna_parity(kg, ctx, oracle, universe, flags):
+    u, img, _ = universe
+    seqs = [synth.genome(u, 30000, seed=31, index=i) for i in range(3)] + [
+        b"", b"AC", b"ATG", b"ATGAAACCCGGGTTTACGTACGTAGCTAGCTAGCATCGATCGAT", synth.genome(u, 3001, seed=32),
+        synth.genome(u, 3002, seed=33), synth.genome(u, 4097 * 3, seed=34), b"acgtnACGTNryk" * 40]
+    sb, off = oracle.concat(seqs)
+    t = ctx.table_from_image(img)
+    res = ctx.run(t, kg.MODE_DNA, sb, off, kg.default_params(emit_hits=1, **flags))
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=False, **flags), sb, off, oracle.STREAM_JOIN)
+    assert len(ref.calls) > 10 and set(ref.hits["sf"]) == set(range(6))
+    assert_same(res, ref, what=f"dna {flags}")
+    res.free()
+    t.free()
+
+
+KATS = json.load(open(os.path.join(GOLD, "fsm_kats.json")))
+
+
+@pytest.mark.parametrize("kat", KATS, ids=[k["name"] for k in KATS])
+def test_fsm_kats_on_gpu(kg, ctx, kat):
+    """The hand-traced FSM vectors, driven through the whole GPU path: a random protein whose windows at the KAT's
+    positions are the only table entries, carrying the KAT's (fI, oI, wt, avg)."""
+    rng = np.random.default_rng(1234)
+    L = max(h[0] for h in kat["hits"]) + 40
+    prot = bytes(rng.choice(np.frombuffer(synth.PROT_ALPHA.encode(), np.uint8), L))
+    wk = synth.window_keys(synth.aa_codes(prot))
+    assert len(np.unique(wk)) == len(wk)
+    pos = [h[0] for h in kat["hits"]]
+    img = synth.build_table_image(wk[pos], [h[2] for h in kat["hits"]], [h[4] for h in kat["hits"]],
+                                  [h[1] for h in kat["hits"]], np.array([h[3] for h in kat["hits"]], np.float32))
+    t = ctx.table_from_image(img)
+    p = kat["params"]
+    sb = np.frombuffer(prot, np.uint8)
+    off = np.array([0, L], np.uint64)
+    res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1, **p))
+    assert list(res.hits["pos"]) == sorted(pos)
+    got = [[int(c["start"]), int(c["end"]), int(c["count"]), int(c["fI"]), float(c["weighted"])] for c in res.calls]
+    assert got == [[a, b, c, d, float(np.float32(w))] for a, b, c, d, w in kat["calls"]]
+    o = res.otus[0]
+    assert [[int(o["count"][j]), int(o["oI"][j])] for j in range(int(o["n"]))] == kat["otu"]
+    res.free()
+    t.free()
+
+
+def test_hit_cap_40000(kg, ctx, oracle):
+    """Q9 (KGJ:496-504): an open run never holds more than 39998 hits; later hits of the run are dropped."""
+    rng = np.random.default_rng(99)
+    L = 41000
+    prot = bytes(rng.choice(np.frombuffer(synth.PROT_ALPHA.encode(), np.uint8), L))
+    wk = synth.window_keys(synth.aa_codes(prot))
+    keys, first = np.unique(wk, return_index=True)
+    n = len(keys)
+    img = synth.build_table_image(keys, np.full(n, 3), np.full(n, 1), np.full(n, 7), np.full(n, 0.5, np.float32))
+    t = ctx.table_from_image(img)
+    sb, off = oracle.concat([prot])
+    res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1))
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True), sb, off, oracle.DIRECT_PROBE)
+    assert int(ref.calls["count"][0]) == 39998
+    assert_same(res, ref, what="cap")
+    res.free()
+    t.free()
+
+
+def test_malformed_table_reachability(kg, ctx, oracle):
+    """A key stored where the reference's no-wrap probe chain cannot reach it is never returned; a repeated key
+    returns the first copy on the chain; unmatchable keys (>= 20^8 or < 0) only extend chains."""
+    prot = b"MKVLAAGIVGLCAHHHWYYRRDDEEFFGGHHIIKKLLMMNNPPQQ"
+    wk = synth.window_keys(synth.aa_codes(prot))
+    n = len(wk)
+    img = bytearray(synth.build_table_image(wk, np.arange(n), np.arange(n) + 100, np.full(n, 5), np.ones(n, np.float32), num_slots=211))
+    ent = np.frombuffer(img, dtype=synth.ENTRY_DTYPE, offset=24)
+    occ = np.flatnonzero(ent["which"] <= synth.MAX_ENCODED)
+    empty = np.flatnonzero(ent["which"] > synth.MAX_ENCODED)
+    # 1. move one key to an isolated empty slot far from its home: unreachable
+    victim = occ[3]
+    far = [e for e in empty if e > 0 and e + 1 < 211 and ent["which"][e - 1] > synth.MAX_ENCODED and ent["which"][e + 1] > synth.MAX_ENCODED
+           and e != ent["which"][victim] % 211][0]
+    ent[far] = ent[victim]
+    ent["which"][victim] = synth.EMPTY_KEY
+    # 2. duplicate another key right after itself with a different payload: the first copy must win
+    dup = [s for s in occ if s != victim and s + 1 < 210 and ent["which"][s + 1] > synth.MAX_ENCODED and s + 1 != far][0]
+    ent[dup + 1] = ent[dup]
+    ent["fi"][dup + 1] = 99
+    # 3. an unmatchable key
+    um = [e for e in empty if e not in (far, dup + 1) and e + 1 < 211][-1]
+    ent["which"][um] = synth.MAX_ENCODED  # == 20^8: occupied (not > MAX_ENCODED) but no 8-mer encodes to it
+    t = ctx.table_from_image(bytes(img))
+    sb, off = oracle.concat([prot])
+    res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1, min_hits=2))
+    for variant in (oracle.STREAM_JOIN, oracle.DIRECT_PROBE):
+        ref = oracle.run(oracle.Table(data=bytes(img)), oracle.make_params(aa=True, min_hits=2), sb, off, variant)
+        assert len(ref.hits) == n - 1 - 1 and 99 not in ref.hits["fI"]
+        assert_same(res, ref, what="malformed")
+    assert t.info.num_unreachable >= 2
+    res.free()
+    t.free()
+
+
+def test_errors(kg, ctx, universe):
+    u, img, _ = universe
+    t = ctx.table_from_image(img)
+    sb = np.frombuffer(b"ACDEFGHIKLMNP", np.uint8)
+    off = np.array([0, 13], np.uint64)
+    with pytest.raises(kg.KgError) as e:
+        ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(min_hits=1))
+    assert e.value.code == -1
+    bad = bytearray(img)
+    bad[8:16] = (32).to_bytes(8, "little")
+    with pytest.raises(kg.KgError) as e:
+        ctx.table_from_image(bytes(bad))
+    assert e.value.code == -5
+    with pytest.raises(kg.KgError):
+        ctx.load_table("/nonexistent/dir")
+    t.free()
+
+
+def test_batch_rerun_is_idempotent(kg, ctx, oracle, universe):
+    u, img, _ = universe
+    seqs = u.proteins(200, seed=41)
+    sb, off = oracle.concat(seqs)
+    t = ctx.table_from_image(img)
+    b = ctx.upload(kg.MODE_AA, sb, off)
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True), sb, off, oracle.DIRECT_PROBE)
+    for _ in range(3):
+        res = ctx.run_batch(t, b, kg.default_params(emit_hits=1))
+        assert_same(res, ref, what="rerun")
+        res.free()
+    b.free()
+    t.free()

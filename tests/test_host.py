@@ -1,0 +1,97 @@
+"""Host-side mirror of run()'s CPU parts (FASTA, function.index, %f) -- no GPU needed.  The reference's behaviours
+under test are cited from KmerGutsJava.java (KGJ)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import kmergutsjava_b200 as kg
+
+
+def _write(tmp_path, name, data: bytes):
+    p = tmp_path / name
+    with (gzip.open(p, "wb") if name.endswith(".gz") else open(p, "wb")) as f:
+        f.write(data)
+    return str(p)
+
+
+def test_fasta_basic_and_gz(tmp_path):
+    body = b">id1 some description here\nACDE\nFGHI\n\n>id2\tx\nKLMN\n"
+    for name in ("a.fa", "a.fa.gz"):
+        f = kg.Fasta(_write(tmp_path, name, body))
+        assert f.ids == ["id1", "id2"]
+        assert bytes(f.bytes) == b"ACDEFGHIKLMN" and list(f.offsets) == [0, 8, 12]
+        f.free()
+
+
+def test_fasta_lines_are_not_trimmed(tmp_path):
+    # KGJ:1176 appends the raw line: inner and trailing blanks become (invalid) residues; \r\n is a line end
+    f = kg.Fasta(_write(tmp_path, "b.fa", b">x\r\nAC DE \r\n  \r\nFG\r\n>y\nAA\n"))
+    assert f.ids == ["x", "y"]
+    assert bytes(f.bytes[: int(f.offsets[1])]) == b"AC DE   FG"
+    f.free()
+
+
+def test_fasta_short_lines_before_caption_are_skipped(tmp_path):
+    # KGJ:1145: only lines whose trimmed length is > 1 are examined while looking for a caption
+    f = kg.Fasta(_write(tmp_path, "c.fa", b"\n \nA\n>s1\nACD\n"))
+    assert f.ids == ["s1"] and bytes(f.bytes) == b"ACD"
+    f.free()
+
+
+def test_fasta_errors(tmp_path):
+    with pytest.raises(kg.KgError, match="Wrong caption line: ACDEF"):     # KGJ:1158
+        kg.Fasta(_write(tmp_path, "d.fa", b"ACDEF\n>s\nAA\n"))
+    with pytest.raises(kg.KgError, match="No sequence for caption: s1"):   # KGJ:1170
+        kg.Fasta(_write(tmp_path, "e.fa", b">s1\n>s2\nAA\n"))
+    with pytest.raises(kg.KgError, match="No sequence for caption: s2"):
+        kg.Fasta(_write(tmp_path, "f.fa", b">s1\nAA\n>s2\n\n"))
+    with pytest.raises(kg.KgError):
+        kg.Fasta(str(tmp_path / "missing.fa"))
+
+
+def test_fasta_matches_oracle_reader_on_ecoli(oracle):
+    import ctypes as C
+    path = os.path.join(os.path.dirname(__file__), "data", "Ecoli_K12_W3110.faa.gz")
+    f = kg.Fasta(path)
+    assert f.n == 13645 and int(f.offsets[-1]) == 4147102
+    L = oracle.lib()
+    L.kgo_fasta_read.restype = C.c_void_p
+    L.kgo_fasta_read.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+
+    class KF(C.Structure):
+        _fields_ = [("n", C.c_size_t), ("id", C.POINTER(C.c_char_p)), ("seq", C.POINTER(C.c_uint8)), ("off", C.POINTER(C.c_uint64))]
+    err = C.create_string_buffer(256)
+    h = L.kgo_fasta_read(path.encode(), err, 256)
+    o = C.cast(h, C.POINTER(KF)).contents
+    assert o.n == f.n
+    assert [o.id[i].decode() for i in range(0, f.n, 997)] == f.ids[::997]
+    assert np.array_equal(np.ctypeslib.as_array(o.off, (f.n + 1,)), f.offsets)
+    assert np.array_equal(np.ctypeslib.as_array(o.seq, (int(f.offsets[-1]),)), f.bytes)
+    f.free()
+
+
+def test_function_index(tmp_path):
+    import ctypes as C
+    L = kg.lib()
+    p = _write(tmp_path, "function.index", b"0\thypothetical protein\n1\tDNA polymerase (EC 2.7.7.7)\n2\t\n")
+    h = C.c_void_p()
+    assert L.kg_functions_load(str(tmp_path).encode(), C.byref(h)) == 0
+    assert L.kg_functions_count(h) == 3
+    assert L.kg_functions_name(h, 1) == b"DNA polymerase (EC 2.7.7.7)" and L.kg_functions_name(h, 2) == b""
+    L.kg_functions_free(h)
+    bad = _write(tmp_path, "bad.index", b"0\ta\n2\tb\n")
+    assert L.kg_functions_read(bad.encode(), C.byref(h)) == -5
+    assert b"dense and in order (see line 1)" in L.kg_last_error()     # KGJ:361-364
+
+
+def test_java_format_matches_oracle(oracle):
+    rng = np.random.default_rng(3)
+    vals = [0.0, 1 / 128, 3 / 128, 2.5, 0.1, 1.0000001, 123456.0, 0.9999999403953552, 1e-7, 5e-7, 4.9999997e-7]
+    vals += list(rng.integers(0, 1 << 16, 300) / 256.0) + list(rng.random(300) * 100) + list(rng.integers(0, 4096, 200) / 128.0)
+    for v in vals:
+        v = float(np.float32(v))
+        for prec in (6, 3):
+            assert kg.java_format_f(v, prec) == oracle.java_format_f(v, prec), (v, prec)
+    assert kg.java_format_f(1 / 128) == "0.007813"
