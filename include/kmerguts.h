@@ -109,6 +109,7 @@ typedef struct kg_run_stats {
     uint64_t num_calls;
     uint32_t num_launches;    /* kernels of this library launched for the run */
     float ms_h2d, ms_device, ms_d2h; /* CUDA-event times of the last run (0 when not applicable) */
+    float ms_prepare, ms_probe, ms_group; /* inside ms_device: translate/patch, encode+probe kernel, gather+FSM */
 } kg_run_stats;
 
 /* ---- context ---- */

@@ -58,7 +58,8 @@ class TableInfo(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [("num_sequences", C.c_uint64), ("num_positions", C.c_uint64), ("num_kmers", C.c_uint64),
                 ("num_hits", C.c_uint64), ("num_calls", C.c_uint64), ("num_launches", C.c_uint32),
-                ("ms_h2d", C.c_float), ("ms_device", C.c_float), ("ms_d2h", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_device", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_prepare", C.c_float), ("ms_probe", C.c_float), ("ms_group", C.c_float)]
 
 
 class UniverseStruct(C.Structure):

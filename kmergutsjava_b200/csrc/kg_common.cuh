@@ -91,7 +91,7 @@ struct kg_context {
     int device = 0;
     cudaStream_t stream = nullptr;      // compute
     cudaStream_t copy_stream = nullptr; // H2D staging for the pipelined end-to-end call
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[12] = {};           // 0-5: run / fetch / upload brackets, 6-9: pipeline stages
     int sm_count = 0;
     size_t l2_bytes = 0;
     DevBuf scan_tmp;                    // CUB temp storage

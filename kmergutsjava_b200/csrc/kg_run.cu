@@ -538,6 +538,7 @@ static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, con
     cudaStream_t st = ctx->stream;
     RunScratch& sc = scratch_of(ctx);
     uint32_t launches = 0;
+    cudaEventRecord(ctx->ev[6], st);
     KG_TRY(kg_batch_prepare(b, st, &launches));
     const uint64_t nv = b->nv, vtotal = b->vtotal;
     const int per_seq = b->mode == KG_MODE_AA ? 1 : 6;
@@ -563,11 +564,13 @@ static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, con
         KG_TRY(sc.chunk.ensure(std::max<uint64_t>(hit_cap, 1) * sizeof(uint2)));
         CU(cudaMemsetAsync(d_ctr, 0, KG_CTR_COUNT * 8, st));
         CU(cudaMemsetAsync(sc.tile_cnt.p, 0, ((size_t)ntiles + 1) * 4, st));
+        cudaEventRecord(ctx->ev[7], st);
         if (ntiles) {
             k_probe<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sc.chunk.as<uint2>(),
                                                   (uint32_t)hit_cap, sc.tile_base.as<uint32_t>(), sc.tile_cnt.as<uint32_t>(), d_ctr);
             launches++;
         }
+        cudaEventRecord(ctx->ev[8], st);
         KG_TRY(exclusive_sum_u32(ctx, sc.tile_cnt.as<uint32_t>(), sc.tile_out.as<uint32_t>(), (size_t)ntiles + 1, st));
         launches++;
         CU(cudaMemcpyAsync(ctx->h_counters, d_ctr, KG_CTR_COUNT * 8, cudaMemcpyDeviceToHost, st));
@@ -620,7 +623,11 @@ static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, con
     }
     uint32_t ncalls32 = 0;
     CU(cudaMemcpyAsync(&ctx->h_counters[KG_CTR_CALLS], sc.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(ctx->ev[9], st);
     CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&r->stats.ms_prepare, ctx->ev[6], ctx->ev[7]);
+    cudaEventElapsedTime(&r->stats.ms_probe, ctx->ev[7], ctx->ev[8]);
+    cudaEventElapsedTime(&r->stats.ms_group, ctx->ev[8], ctx->ev[9]);
     CU(cudaGetLastError());
     ncalls32 = *(uint32_t*)&ctx->h_counters[KG_CTR_CALLS];
     r->stats.num_sequences = b->n;

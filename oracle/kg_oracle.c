@@ -189,6 +189,7 @@ void kgo_translate(const uint8_t* seq, size_t L, int off, uint8_t* pseq, uint8_t
 struct kgo_table {
     uint8_t* bytes;     /* whole decompressed file, header included */
     size_t nbytes;
+    int borrowed;
     int64_t num_sigs, entry_size, version; /* KGJ:933-935 */
 };
 
@@ -212,6 +213,7 @@ static kgo_table* table_adopt(uint8_t* bytes, size_t nbytes) {
     kgo_table* t = xmalloc(sizeof *t);
     t->bytes = bytes;
     t->nbytes = nbytes;
+    t->borrowed = 0;
     t->num_sigs = t->entry_size = t->version = 0;
     if (nbytes >= 24) { /* KGJ:933-935 */
         t->num_sigs = le64(bytes);
@@ -232,9 +234,14 @@ kgo_table* kgo_table_from_memory(const void* bytes, size_t nbytes) {
     memcpy(b, bytes, nbytes);
     return table_adopt(b, nbytes);
 }
+kgo_table* kgo_table_borrow(const void* bytes, size_t nbytes) {
+    kgo_table* t = table_adopt((uint8_t*)bytes, nbytes);
+    t->borrowed = 1;
+    return t;
+}
 void kgo_table_free(kgo_table* t) {
     if (!t) return;
-    free(t->bytes);
+    if (!t->borrowed) free(t->bytes);
     free(t);
 }
 int64_t kgo_table_num_sigs(const kgo_table* t) { return t->num_sigs; }
@@ -717,6 +724,67 @@ kgo_result* kgo_run(const kgo_table* t, const kgo_params* p, const uint8_t* seq_
         }
     }
     free(tmp);
+    return r;
+}
+
+/* ------------------------------------------------------------------ */
+/* T independent runs of the reference algorithm on T contiguous       */
+/* shards of the sequences (what running T JVMs on T FASTA shards      */
+/* would do); records are concatenated in sequence order.  The         */
+/* reference itself is single-threaded.                                */
+/* ------------------------------------------------------------------ */
+#include <pthread.h>
+typedef struct {
+    const kgo_table* t; const kgo_params* p; const uint8_t* seq; const uint64_t* off;
+    size_t first, n; int variant; kgo_result* r;
+} shard_job;
+static void* shard_main(void* a) {
+    shard_job* j = a;
+    uint64_t* off = xmalloc((j->n + 1) * sizeof *off);
+    for (size_t i = 0; i <= j->n; i++) off[i] = j->off[j->first + i] - j->off[j->first];
+    j->r = kgo_run(j->t, j->p, j->seq + j->off[j->first], off, j->n, j->variant);
+    free(off);
+    return NULL;
+}
+kgo_result* kgo_run_parallel(const kgo_table* t, const kgo_params* p, const uint8_t* seq_bytes, const uint64_t* offsets,
+                             size_t n, int variant, int threads) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    shard_job* jobs = xmalloc((size_t)threads * sizeof *jobs);
+    pthread_t* th = xmalloc((size_t)threads * sizeof *th);
+    size_t s = 0;
+    for (int k = 0; k < threads; k++) { /* shards balanced by residues */
+        uint64_t target = offsets[n] / (uint64_t)threads * (uint64_t)(k + 1);
+        size_t e = s;
+        if (k == threads - 1) e = n;
+        else while (e < n && offsets[e] < target) e++;
+        shard_job j = {t, p, seq_bytes, offsets, s, e - s, variant, NULL};
+        jobs[k] = j;
+        s = e;
+        pthread_create(&th[k], NULL, shard_main, &jobs[k]);
+    }
+    kgo_result* r = xmalloc(sizeof *r);
+    memset(r, 0, sizeof *r);
+    r->nseq = n;
+    r->per_seq = p->aa ? 1 : 6;
+    for (int k = 0; k < threads; k++) pthread_join(th[k], NULL);
+    size_t nh = 0, nc = 0;
+    for (int k = 0; k < threads; k++) { nh += jobs[k].r->nhits; nc += jobs[k].r->ncalls; }
+    r->hits = xmalloc(nh * sizeof *r->hits);
+    r->calls = xmalloc(nc * sizeof *r->calls);
+    r->calls_cap = nc;
+    r->otus = xmalloc(n * sizeof *r->otus);
+    for (int k = 0; k < threads; k++) {
+        kgo_result* q = jobs[k].r;
+        for (size_t i = 0; i < q->nhits; i++) { r->hits[r->nhits] = q->hits[i]; r->hits[r->nhits++].seq += (int32_t)jobs[k].first; }
+        for (size_t i = 0; i < q->ncalls; i++) { r->calls[r->ncalls] = q->calls[i]; r->calls[r->ncalls++].seq += (int32_t)jobs[k].first; }
+        memcpy(r->otus + jobs[k].first, q->otus, q->nseq * sizeof *q->otus);
+        r->num_kmers += q->num_kmers; r->kmers_found += q->kmers_found; r->pos_count += q->pos_count;
+        r->lookup_error |= q->lookup_error;
+        kgo_result_free(q);
+    }
+    free(jobs);
+    free(th);
     return r;
 }
 

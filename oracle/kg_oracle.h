@@ -99,6 +99,11 @@ int64_t kgo_table_version(const kgo_table* t);
 /* ---- the path: prepareQuery -> sort -> lookup -> gatherHits (KGJ:778-818) ---- */
 kgo_result* kgo_run(const kgo_table* t, const kgo_params* p, const uint8_t* seq_bytes,
                     const uint64_t* offsets /* n+1 */, size_t n, int variant);
+/* `threads` independent runs of the (single-threaded) reference algorithm on contiguous shards of the sequences. */
+kgo_result* kgo_run_parallel(const kgo_table* t, const kgo_params* p, const uint8_t* seq_bytes,
+                             const uint64_t* offsets, size_t n, int variant, int threads);
+/* Adopt (no copy) a file image the caller keeps alive: for the 10 GB tables of the large configurations. */
+kgo_table* kgo_table_borrow(const void* bytes, size_t nbytes);
 void kgo_result_free(kgo_result* r);
 size_t kgo_result_num_hits(const kgo_result* r);
 const kgo_hit_rec* kgo_result_hits(const kgo_result* r);

@@ -61,6 +61,10 @@ def lib() -> C.CDLL:
             getattr(L, f).argtypes = [C.c_void_p]
         L.kgo_run.restype = C.c_void_p
         L.kgo_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        L.kgo_run_parallel.restype = C.c_void_p
+        L.kgo_run_parallel.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        L.kgo_table_borrow.restype = C.c_void_p
+        L.kgo_table_borrow.argtypes = [C.c_void_p, C.c_size_t]
         L.kgo_result_free.argtypes = [C.c_void_p]
         for f in ("kgo_result_num_hits", "kgo_result_num_calls", "kgo_result_num_otus"):
             getattr(L, f).restype = C.c_size_t
@@ -93,9 +97,12 @@ def _copy(ptr, n, dtype):
 
 
 class Table:
-    def __init__(self, path: Optional[str] = None, data: Optional[bytes] = None):
+    def __init__(self, path: Optional[str] = None, data: Optional[bytes] = None, borrow: Optional[np.ndarray] = None):
         L = lib()
-        if path is not None:
+        if borrow is not None:      # numpy uint8 image kept alive by this object (no copy: 10 GB tables)
+            self._keep = borrow
+            self._h = L.kgo_table_borrow(borrow.ctypes.data, borrow.nbytes)
+        elif path is not None:
             err = C.create_string_buffer(512)
             self._h = L.kgo_table_open(path.encode(), err, 512)
             if not self._h:
@@ -131,10 +138,15 @@ def concat(seqs: Sequence[bytes]):
     return np.frombuffer(b"".join(seqs), dtype=np.uint8), off
 
 
-def run(table: Table, params: Params, seq_bytes: np.ndarray, offsets: np.ndarray, variant: int = STREAM_JOIN) -> Result:
+def run(table: Table, params: Params, seq_bytes: np.ndarray, offsets: np.ndarray, variant: int = STREAM_JOIN,
+        threads: int = 1) -> Result:
     seq_bytes = np.ascontiguousarray(seq_bytes, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-    h = lib().kgo_run(table._h, C.byref(params), seq_bytes.ctypes.data, offsets.ctypes.data, len(offsets) - 1, variant)
+    if threads > 1:
+        h = lib().kgo_run_parallel(table._h, C.byref(params), seq_bytes.ctypes.data, offsets.ctypes.data,
+                                   len(offsets) - 1, variant, threads)
+    else:
+        h = lib().kgo_run(table._h, C.byref(params), seq_bytes.ctypes.data, offsets.ctypes.data, len(offsets) - 1, variant)
     return Result(h)
 
 
