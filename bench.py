@@ -29,6 +29,13 @@ from tools import kg_synth as synth  # noqa: E402
 BYTES_PER_LOOKUP_AA = 33.0  # one 32-byte table sector + 1 residue byte
 
 
+T_START = time.time()
+
+
+def log(msg):
+    print(f"[bench {time.time() - T_START:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -124,10 +131,13 @@ def build_inputs(kg, ctx, args, rank):
     t0 = time.time()
     dk, dp, nsig = kg.synth_signatures(ctx, u, args.sigs)
     t1 = time.time()
+    log(f"signatures generated: {nsig}")
     table = ctx.table_from_device_entries(dk, dp, nsig)
     t2 = time.time()
+    log("table built")
     ds, do, total = kg.synth_proteins(ctx, u, rank * args.proteins, args.proteins, seed=1)
     t3 = time.time()
+    log(f"proteins generated: {total} residues")
     timing = {"gen_signatures_s": round(t1 - t0, 2), "build_table_s": round(t2 - t1, 2), "gen_proteins_s": round(t3 - t2, 2)}
     return u, (dk, dp, nsig), table, (ds, do, total), timing
 
@@ -156,6 +166,7 @@ def run_ours(args):
     # ---- device-resident throughput ----
     for _ in range(max(args.warmup, 3)):
         ctx.run_batch(table, batch, params).free()
+        log("warm-up step done")
     clocks = ClockSampler(local)
     clocks.start()
     barrier(torch, dist, local)
@@ -175,6 +186,7 @@ def run_ours(args):
     total_lookups = all_sum(torch, dist, float(lookups), local)
     total_proteins = float(args.proteins * args.steps * world)
     value = total_lookups / dt
+    log(f"device-resident: {value:.3e} lookups/s")
 
     # ---- end to end through kg_run with pinned host buffers ----
     e2e = None
@@ -201,6 +213,7 @@ def run_ours(args):
                "h2d_bytes_per_step": int(total + 8 * (args.proteins + 1)), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * edt / args.steps}
 
+    log("e2e done")
     # ---- rooflines ----
     hbm_peak, peak_src = measured_peaks()
     probe_s = float(np.mean(probe_ms)) * 1e-3
@@ -225,14 +238,18 @@ def run_ours(args):
         from oracle import kgo
         kgo.build()
         threads = os.cpu_count() or 1
-        num_slots = synth.next_prime(2 * nsig + 1)
+        num_slots = 3 * nsig + 1  # load 1/3: at 1/2 the reference hash (key % numSigs) clusters so badly that no prime near 2n avoids running off the end
         t0 = time.time()
+        log("roofline done; building the reference-format image for the CPU baseline")
         img = kg.synth_reference_image(ctx, dk, dp, nsig, num_slots)
+        num_slots = int(img[:8].view(np.int64)[0])
         otable = kgo.Table(borrow=img)
+        log("image on host")
         t_img = time.time() - t0
         nsample = args.cpu_sample or min(args.proteins, 16000 * threads)
         sb, off = sample_host(kg, ctx, ds, do, nsample)
         ref, secs = cpu_reference_run(kgo, otable, sb, off, threads)
+        log(f"cpu baseline done in {secs:.1f}s")
         cpu = {"value": ref.num_kmers / secs, "unit": "lookups/s", "cores": threads, "kind": "port",
                "sample": f"first {nsample} proteins of the step ({ref.num_kmers} lookups) against the full table in the "
                          f"reference's own 24-byte-slot format ({num_slots} slots); reference algorithm (comparator sort + "
@@ -286,8 +303,9 @@ def run_reference(args):
     ctx = kg.Context(int(os.environ.get("LOCAL_RANK", "0")))
     u = synth.Universe(n_families=args.families)
     dk, dp, nsig = kg.synth_signatures(ctx, u, args.sigs)
-    num_slots = synth.next_prime(2 * nsig + 1)
+    num_slots = 3 * nsig + 1  # load 1/3: at 1/2 the reference hash (key % numSigs) clusters so badly that no prime near 2n avoids running off the end
     img = kg.synth_reference_image(ctx, dk, dp, nsig, num_slots)
+    num_slots = int(img[:8].view(np.int64)[0])
     kg.device_free(dk)
     kg.device_free(dp)
     otable = kgo.Table(borrow=img)

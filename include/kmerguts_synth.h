@@ -39,10 +39,13 @@ int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64_t max_sigs
 int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t first, uint64_t n, uint64_t seed,
                       uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes);
 
-/* kmer.table.mem_map image (24-byte header + num_slots 24-byte LE entries, linear probing without wrap, last slot
- * empty) built on the device from (keys, payload) and copied into host_image (24 + 24*num_slots bytes). */
+/* kmer.table.mem_map image (24-byte header + num_slots 24-byte LE entries, linear probing WITHOUT wrap-around, last
+ * slot empty) built on the device from (keys, payload).  num_slots = the first prime >= min_slots for which no probe
+ * chain runs off the end.  *d_image is a device buffer of 24 + 24 * *num_slots bytes owned by the caller.
+ * *mean_displacement (optional) = average distance of a key from its home slot key % numSigs: the extra 24-byte slots
+ * the reference reads per hit, a property of the reference's own hash on skewed residue composition. */
 int kg_synth_reference_image(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, uint64_t n,
-                             uint64_t num_slots, void* host_image);
+                             uint64_t min_slots, uint64_t* num_slots, void** d_image, double* mean_displacement);
 
 void kg_device_free(void* d_ptr);
 int kg_device_to_host(kg_context* ctx, void* host, const void* dev, uint64_t bytes);

@@ -105,7 +105,7 @@ def lib() -> C.CDLL:
         "kg_main": (i32, [i32, C.POINTER(C.c_char_p)]),
         "kg_synth_signatures": (i32, [vp, C.POINTER(UniverseStruct), u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_proteins": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
-        "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, vp]),
+        "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, C.POINTER(u64), pp, C.POINTER(C.c_double)]),
         "kg_device_free": (None, [vp]), "kg_device_to_host": (i32, [vp, vp, vp, u64]),
         "kg_probe_roofline": (i32, [vp, u64, u64, i32, i32, C.POINTER(C.c_double)]),
         "kg_probe_roofline_table": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_double)]),
@@ -337,10 +337,15 @@ def synth_proteins(ctx: Context, u, first: int, n: int, seed: int):
     return ds.value, do.value, total.value
 
 
-def synth_reference_image(ctx: Context, d_keys: int, d_payload: int, n: int, num_slots: int) -> np.ndarray:
-    img = np.empty(24 + 24 * num_slots, dtype=np.uint8)
-    _check(lib().kg_synth_reference_image(ctx._h, d_keys, d_payload, n, num_slots, img.ctypes.data))
-    return img
+def synth_reference_image(ctx: Context, d_keys: int, d_payload: int, n: int, min_slots: int) -> np.ndarray:
+    """kmer.table.mem_map image written on the device (reference format, no wrap-around), copied to the host."""
+    ns, dimg, disp = C.c_uint64(), C.c_void_p(), C.c_double()
+    _check(lib().kg_synth_reference_image(ctx._h, d_keys, d_payload, n, min_slots, C.byref(ns), C.byref(dimg), C.byref(disp)))
+    synth_reference_image.mean_displacement = disp.value
+    try:
+        return ctx.to_host(dimg.value, 24 + 24 * ns.value)
+    finally:
+        device_free(dimg.value)
 
 
 def device_free(ptr):

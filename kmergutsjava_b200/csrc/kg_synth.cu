@@ -134,7 +134,11 @@ __global__ void k_prot_fill(DevUniverse u, uint64_t first, uint64_t n, uint64_t 
     }
 }
 
-// ---- reference-format image: linear probing without wrap over 24-byte slots (3 x uint64 words each) ----
+// ---- reference-format image: linear probing without wrap over 24-byte slots (3 x uint64 words each).
+// Keys taken in home-slot order get the first free slot at or after their home:
+//   slot_r = max(slot_{r-1} + 1, home_r) = r + max_{q<=r}(home_q - q)   -- the layout sequential insertion in that order
+// produces.  (key % numSigs of real 8-mers is far from uniform, so a CAS-per-probe insert would crawl through runs that
+// are thousands of slots long; the scan places every key in O(1).)
 __global__ void k_image_init(unsigned long long* __restrict__ w, uint64_t num_slots) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= num_slots) return;
@@ -142,23 +146,48 @@ __global__ void k_image_init(unsigned long long* __restrict__ w, uint64_t num_sl
     w[3 * s + 1] = 0;
     w[3 * s + 2] = 0;
 }
-__global__ void k_image_insert(unsigned long long* __restrict__ w, uint64_t num_slots, const uint64_t* __restrict__ keys,
-                               const int4* __restrict__ payload, uint64_t n, unsigned long long* __restrict__ err) {
+__global__ void k_image_home(const uint64_t* __restrict__ keys, uint64_t n, uint64_t num_slots, uint32_t* __restrict__ home,
+                             uint32_t* __restrict__ idx) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned long long key = keys[i], empty = (unsigned long long)(KG_MAX_ENCODED + 1);
-    const int4 p = payload[i];
-    for (uint64_t s = key % num_slots;; s++) {
+    home[i] = (uint32_t)(keys[i] % num_slots); // the reference's hash, KGJ:969
+    idx[i] = (uint32_t)i;
+}
+__global__ void k_image_bias(const uint32_t* __restrict__ home, uint64_t n, long long* __restrict__ t) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) t[r] = (long long)home[r] - (long long)r;
+}
+struct MaxLL {
+    __host__ __device__ __forceinline__ long long operator()(long long a, long long b) const { return a > b ? a : b; }
+};
+// ctr[0] = keys that would run off the end, ctr[1] = sum of (slot - home), ctr[2] = max of (slot - home)
+__global__ void k_image_place(const uint32_t* __restrict__ home, const uint32_t* __restrict__ idx, const long long* __restrict__ tmax,
+                              uint64_t n, const uint64_t* __restrict__ keys, const int4* __restrict__ payload,
+                              unsigned long long* __restrict__ w, uint64_t num_slots, unsigned long long* __restrict__ ctr) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long disp = 0;
+    if (r < n) {
+        const uint64_t s = (uint64_t)((long long)r + tmax[r]);
+        disp = s - home[r];
         if (s + 1 >= num_slots) { // the last slot stays empty so that no chain can run off the end
-            atomicAdd(err, 1ull);
-            return;
-        }
-        unsigned long long old = atomicCAS(&w[3 * s], empty, key);
-        if (old == empty) {
+            atomicAdd(&ctr[0], 1ull);
+        } else {
+            const int4 p = payload[idx[r]];
+            w[3 * s] = keys[idx[r]];
             w[3 * s + 1] = (unsigned long long)(uint32_t)p.x | ((unsigned long long)(uint32_t)p.y << 32); // otu, avgFromEnd
             w[3 * s + 2] = (unsigned long long)(uint32_t)p.z | ((unsigned long long)(uint32_t)p.w << 32); // fI, wt bits
-            return;
         }
+    }
+    unsigned long long sum = disp, mx = disp;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
+        mx = o > mx ? o : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&ctr[1], sum);
+        atomicMax(&ctr[2], mx);
     }
 }
 
@@ -306,28 +335,77 @@ extern "C" int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t
     return KG_OK;
 }
 
+static bool is_prime_u64(uint64_t n) {
+    if (n < 2) return false;
+    if (n % 2 == 0) return n == 2;
+    for (uint64_t i = 3; i * i <= n; i += 2)
+        if (n % i == 0) return false;
+    return true;
+}
+
 extern "C" int kg_synth_reference_image(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, uint64_t n,
-                                        uint64_t num_slots, void* host_image) {
-    if (!ctx || !host_image || num_slots < 2) KG_FAIL(KG_EINVAL, "kg_synth_reference_image: bad argument");
+                                        uint64_t min_slots, uint64_t* num_slots_out, void** d_image,
+                                        double* mean_displacement) {
+    if (!ctx || !num_slots_out || !d_image || min_slots < 2) KG_FAIL(KG_EINVAL, "kg_synth_reference_image: bad argument");
+    if (n >= (1ull << 32) || min_slots >= (1ull << 32) - 4096) KG_FAIL(KG_ERANGE, "kg_synth_reference_image: 32-bit slot index");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    unsigned long long *w = nullptr, *err = nullptr;
-    CU(cudaMalloc(&w, num_slots * 24));
-    CU(cudaMalloc(&err, 8));
-    CU(cudaMemsetAsync(err, 0, 8, st));
-    k_image_init<<<blocks_for(num_slots, 256), 256, 0, st>>>(w, num_slots);
-    if (n) k_image_insert<<<blocks_for(n, 256), 256, 0, st>>>(w, num_slots, d_keys, (const int4*)d_payload16, n, err);
-    unsigned long long herr = 0;
-    CU(cudaMemcpyAsync(&herr, err, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    int64_t hdr[3] = {(int64_t)num_slots, 24, 1}; // numSigs, entrySize, version (KGJ:933-935)
-    memcpy(host_image, hdr, 24);
-    cudaError_t e = cudaMemcpy((uint8_t*)host_image + 24, w, num_slots * 24, cudaMemcpyDeviceToHost);
-    cudaFree(w);
-    cudaFree(err);
-    if (e != cudaSuccess) KG_FAIL(KG_ECUDA, "image copy failed: %s", cudaGetErrorString(e));
-    if (herr) KG_FAIL(KG_ERANGE, "reference image: %llu keys would run off the end of %llu slots", herr, (unsigned long long)num_slots);
-    return KG_OK;
+    unsigned long long* ctr = nullptr;
+    uint32_t *home_a = nullptr, *home_b = nullptr, *idx_a = nullptr, *idx_b = nullptr;
+    long long* tb = nullptr;
+    const uint64_t n1 = std::max<uint64_t>(n, 1);
+    CU(cudaMalloc(&ctr, 32));
+    CU(cudaMalloc(&home_a, n1 * 4));
+    CU(cudaMalloc(&home_b, n1 * 4));
+    CU(cudaMalloc(&idx_a, n1 * 4));
+    CU(cudaMalloc(&idx_b, n1 * 4));
+    CU(cudaMalloc(&tb, n1 * 8));
+    uint64_t num_slots = min_slots;
+    int rc = KG_ERANGE;
+    // The reference never wraps around (KGJ:959-1026): a slot count for which some probe chain would run off the end
+    // is unusable.  Try successive primes until one fits.
+    for (int attempt = 0; attempt < 100; attempt++) {
+        while (!is_prime_u64(num_slots)) num_slots++;
+        unsigned long long* w = nullptr;
+        CU(cudaMalloc(&w, 24 + num_slots * 24));
+        CU(cudaMemsetAsync(ctr, 0, 32, st));
+        const int64_t hdr[3] = {(int64_t)num_slots, 24, 1}; // numSigs, entrySize, version (KGJ:933-935)
+        CU(cudaMemcpyAsync(w, hdr, 24, cudaMemcpyHostToDevice, st));
+        k_image_init<<<blocks_for(num_slots, 256), 256, 0, st>>>(w + 3, num_slots);
+        if (n) {
+            k_image_home<<<blocks_for(n, 256), 256, 0, st>>>(d_keys, n, num_slots, home_a, idx_a);
+            cub::DoubleBuffer<uint32_t> dk(home_a, home_b), dv(idx_a, idx_b);
+            size_t tmp = 0;
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, 32, st)); // stable: ties keep input order
+            KG_TRY(ctx->scan_tmp.ensure(tmp));
+            CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, dk, dv, n, 0, 32, st));
+            k_image_bias<<<blocks_for(n, 256), 256, 0, st>>>(dk.Current(), n, tb);
+            CU(cub::DeviceScan::InclusiveScan(nullptr, tmp, tb, tb, MaxLL(), n, st));
+            KG_TRY(ctx->scan_tmp.ensure(tmp));
+            CU(cub::DeviceScan::InclusiveScan(ctx->scan_tmp.p, tmp, tb, tb, MaxLL(), n, st));
+            k_image_place<<<blocks_for(n, 256), 256, 0, st>>>(dk.Current(), dv.Current(), tb, n, d_keys, (const int4*)d_payload16,
+                                                             w + 3, num_slots, ctr);
+        }
+        unsigned long long h[4] = {0, 0, 0, 0};
+        CU(cudaMemcpyAsync(h, ctr, 32, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        if (getenv("KG_DEBUG"))
+            fprintf(stderr, "[kg] reference image: attempt %d, %llu slots, %llu keys off the end, mean displacement %.2f, max %llu\n",
+                    attempt, (unsigned long long)num_slots, h[0], n ? (double)h[1] / (double)n : 0.0, h[2]);
+        if (!h[0]) {
+            *num_slots_out = num_slots;
+            *d_image = w;
+            if (mean_displacement) *mean_displacement = n ? (double)h[1] / (double)n : 0.0;
+            rc = KG_OK;
+            break;
+        }
+        cudaFree(w);
+        num_slots++;
+    }
+    for (void* p : {(void*)ctr, (void*)home_a, (void*)home_b, (void*)idx_a, (void*)idx_b, (void*)tb}) cudaFree(p);
+    if (rc != KG_OK) kg_set_error("reference image: no usable slot count found from %llu upwards", (unsigned long long)min_slots);
+    return rc;
 }
 
 static int roofline_run(kg_context* ctx, const uint4* buf, uint64_t n_sectors, uint64_t n_loads, int tpb, int inflight, double* out) {

@@ -607,7 +607,8 @@ static void hit_merge_sort(hit_t* a, hit_t* tmp, size_t n) { /* stable, like Col
 /* KGJ:457-514.  all_hits must already be sorted by pos (the sort is done once, right after lookup). */
 static void gather_hits(fsm_ctx* c, const hit_t* all_hits, size_t nall) {
     const kgo_params* p = c->p;
-    hit_t* hits = xmalloc((KGO_MAX_HITS_PER_SEQ) * sizeof *hits);
+    /* the open run never holds more than min(nall, MAX_HITS_PER_SEQ - 2) hits (KGJ:496) */
+    hit_t* hits = xmalloc(((nall < KGO_MAX_HITS_PER_SEQ ? nall : KGO_MAX_HITS_PER_SEQ) + 2) * sizeof *hits);
     size_t n = 0;
     int32_t current_fI = 0;
     c->hits_printed = 0;

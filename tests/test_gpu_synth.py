@@ -55,8 +55,7 @@ def test_device_pipeline_on_device_generated_inputs(kg, ctx, oracle):
     u = synth.Universe(n_families=400, seed=0x4B47000A)
     dk, dp, n = kg.synth_signatures(ctx, u, 0)
     table = ctx.table_from_device_entries(dk, dp, n)
-    num_slots = synth.next_prime(2 * n + 1)
-    img = kg.synth_reference_image(ctx, dk, dp, n, num_slots)
+    img = kg.synth_reference_image(ctx, dk, dp, n, 3 * n + 1)
     ent = np.frombuffer(img, dtype=synth.ENTRY_DTYPE, offset=24)
     assert int((ent["which"] <= synth.MAX_ENCODED).sum()) == n and ent["which"][-1] > synth.MAX_ENCODED
     ds, do, total = kg.synth_proteins(ctx, u, 0, 2000, 3)
