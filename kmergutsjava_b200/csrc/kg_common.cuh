@@ -87,6 +87,11 @@ struct DevBuf {
     T* as() const { return (T*)p; }
 };
 
+struct HostBuf { // pinned host memory
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
 struct kg_context {
     int device = 0;
     cudaStream_t stream = nullptr;      // compute
@@ -98,6 +103,9 @@ struct kg_context {
     // pinned staging for small device->host counters
     uint64_t* h_counters = nullptr;
     void* scratch = nullptr;            // RunScratch (kg_run.cu)
+    // result buffers are recycled through these pools: cudaMalloc / cudaMallocHost cost more than a whole run
+    std::vector<DevBuf> dev_pool;
+    std::vector<HostBuf> host_pool;
 };
 
 // counters written by the pipeline, one block of 8 x uint64 per run

@@ -25,6 +25,7 @@ struct kg_batch {
     uint8_t* d_seq = nullptr; // input bytes (+ 64 bytes of zero padding)
     uint64_t* d_off = nullptr; // n+1
     bool owns_input = true;
+    DevBuf seq_buf, off_buf;  // pooled storage behind d_seq / d_off when owns_input
     // derived by prepare(): virtual sequences
     uint64_t nv = 0;          // n (aa) or 6n (dna)
     uint64_t vtotal = 0;      // residue-stream length
@@ -46,9 +47,7 @@ struct kg_result {
     DevBuf d_otus;    // kg_otu[n]
     DevBuf d_hits;    // kg_hit[num_hits] when params.emit_hits
     // host
-    std::vector<kg_call> calls;
-    std::vector<kg_otu> otus;
-    std::vector<kg_hit> hits;
+    HostBuf h_calls, h_otus, h_hits; // pinned, from the context's pool
     bool fetched = false;
 };
 

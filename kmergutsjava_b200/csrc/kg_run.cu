@@ -347,6 +347,64 @@ RunScratch& scratch_of(kg_context* ctx) {
     return *static_cast<RunScratch*>(ctx->scratch);
 }
 
+// ---- recycled result buffers ----
+int pool_take_dev(kg_context* ctx, size_t bytes, DevBuf* out) {
+    int best = -1;
+    for (int i = 0; i < (int)ctx->dev_pool.size(); i++)
+        if (ctx->dev_pool[i].cap >= bytes && (best < 0 || ctx->dev_pool[i].cap < ctx->dev_pool[best].cap)) best = i;
+    if (best >= 0) {
+        *out = ctx->dev_pool[best];
+        ctx->dev_pool.erase(ctx->dev_pool.begin() + best);
+        return KG_OK;
+    }
+    *out = DevBuf();
+    return out->ensure(std::max<size_t>(bytes, 256));
+}
+void pool_give_dev(kg_context* ctx, DevBuf* b) {
+    if (!b->p) return;
+    if (ctx->dev_pool.size() >= 12) { // keep the pool bounded: drop the smallest
+        size_t k = 0;
+        for (size_t i = 1; i < ctx->dev_pool.size(); i++)
+            if (ctx->dev_pool[i].cap < ctx->dev_pool[k].cap) k = i;
+        ctx->dev_pool[k].release();
+        ctx->dev_pool.erase(ctx->dev_pool.begin() + k);
+    }
+    ctx->dev_pool.push_back(*b);
+    *b = DevBuf();
+}
+int pool_take_host(kg_context* ctx, size_t bytes, HostBuf* out) {
+    int best = -1;
+    for (int i = 0; i < (int)ctx->host_pool.size(); i++)
+        if (ctx->host_pool[i].cap >= bytes && (best < 0 || ctx->host_pool[i].cap < ctx->host_pool[best].cap)) best = i;
+    if (best >= 0) {
+        *out = ctx->host_pool[best];
+        ctx->host_pool.erase(ctx->host_pool.begin() + best);
+        return KG_OK;
+    }
+    size_t want = std::max<size_t>(bytes + bytes / 8, 4096);
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        KG_FAIL(KG_ENOMEM, "cudaMallocHost(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    }
+    out->p = p;
+    out->cap = want;
+    return KG_OK;
+}
+void pool_give_host(kg_context* ctx, HostBuf* b) {
+    if (!b->p) return;
+    if (ctx->host_pool.size() >= 12) {
+        size_t k = 0;
+        for (size_t i = 1; i < ctx->host_pool.size(); i++)
+            if (ctx->host_pool[i].cap < ctx->host_pool[k].cap) k = i;
+        cudaFreeHost(ctx->host_pool[k].p);
+        ctx->host_pool.erase(ctx->host_pool.begin() + k);
+    }
+    ctx->host_pool.push_back(*b);
+    *b = HostBuf();
+}
+
 int exclusive_sum_u32(kg_context* ctx, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
     size_t bytes = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, st));
@@ -380,6 +438,14 @@ extern "C" int kg_init(int device, kg_context** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) KG_FAIL(KG_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    // Every probe wants ONE 32-byte sector of a multi-GB table.  With the default L2 fetch granularity the memory system
+    // brings in the whole 128-byte line per miss (ncu: 124 B of DRAM reads per lookup); ask for sector-sized fetches.
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("KG_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     kg_context* ctx = new kg_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
@@ -401,6 +467,8 @@ extern "C" void kg_shutdown(kg_context* ctx) {
                       &sc.call_cnt, &sc.call_off, &sc.ctr})
         b->release();
     delete static_cast<RunScratch*>(ctx->scratch);
+    for (auto& b : ctx->dev_pool) b.release();
+    for (auto& h : ctx->host_pool) cudaFreeHost(h.p);
     ctx->scan_tmp.release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
@@ -442,12 +510,12 @@ extern "C" int kg_batch_upload(kg_context* ctx, int mode, const uint8_t* seq_byt
     cudaStream_t st = ctx->stream;
     int rc = KG_OK;
     do {
-        if (cudaMalloc(&b->d_seq, total + 64) != cudaSuccess || cudaMalloc(&b->d_off, (n + 1) * 8) != cudaSuccess) {
-            cudaGetLastError();
-            kg_set_error("kg_batch_upload: device allocation of %llu bytes failed", (unsigned long long)total);
+        if (pool_take_dev(ctx, total + 64, &b->seq_buf) != KG_OK || pool_take_dev(ctx, (n + 1) * 8, &b->off_buf) != KG_OK) {
             rc = KG_ENOMEM;
             break;
         }
+        b->d_seq = b->seq_buf.as<uint8_t>();
+        b->d_off = b->off_buf.as<uint64_t>();
         cudaMemsetAsync(b->d_seq + total, 0, 64, st);
         if (total) cudaMemcpyAsync(b->d_seq, seq_bytes, total, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(b->d_off, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st);
@@ -485,8 +553,8 @@ extern "C" int kg_batch_from_device(kg_context* ctx, int mode, uint8_t* d_seq_by
 extern "C" void kg_batch_free(kg_batch* b) {
     if (!b) return;
     if (b->owns_input) {
-        if (b->d_seq) cudaFree(b->d_seq);
-        if (b->d_off) cudaFree(b->d_off);
+        pool_give_dev(b->ctx, &b->seq_buf);
+        pool_give_dev(b->ctx, &b->off_buf);
     }
     b->vseq.release();
     b->voff.release();
@@ -597,8 +665,8 @@ static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, con
 
     const uint64_t max_calls = nhits / (uint64_t)prm->min_hits + 1;
     KG_TRY(sc.sparse.ensure(max_calls * sizeof(KgDevCall)));
-    KG_TRY(r->d_otus.ensure(std::max<uint64_t>(b->n, 1) * sizeof(kg_otu)));
-    KG_TRY(r->d_calls.ensure(max_calls * sizeof(kg_call)));
+    KG_TRY(pool_take_dev(ctx, std::max<uint64_t>(b->n, 1) * sizeof(kg_otu), &r->d_otus));
+    KG_TRY(pool_take_dev(ctx, max_calls * sizeof(kg_call), &r->d_calls));
     KgFsmParams fp = {prm->min_hits, prm->max_gap, prm->order_constraint, (float)prm->min_weighted_hits};
     if (b->n) {
         k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sc.lo.as<uint32_t>(), sc.hit_pos.as<uint32_t>(),
@@ -616,7 +684,7 @@ static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, con
         launches++;
     }
     if (prm->emit_hits && nhits) {
-        KG_TRY(r->d_hits.ensure(nhits * sizeof(kg_hit)));
+        KG_TRY(pool_take_dev(ctx, nhits * sizeof(kg_hit), &r->d_hits));
         k_emit_hits<<<blocks_for(nhits, 256), 256, 0, st>>>(b->voffsets(), nv, per_seq, sc.hit_pos.as<uint32_t>(),
                                                            sc.hit_payload.as<int4>(), (uint32_t)nhits, r->d_hits.as<kg_hit>());
         launches++;
@@ -674,13 +742,13 @@ extern "C" int kg_result_fetch(kg_result* r) {
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     cudaEventRecord(ctx->ev[2], st);
-    r->calls.resize(r->stats.num_calls);
-    r->otus.resize(r->n);
-    if (r->stats.num_calls) CU(cudaMemcpyAsync(r->calls.data(), r->d_calls.p, r->stats.num_calls * sizeof(kg_call), cudaMemcpyDeviceToHost, st));
-    if (r->n) CU(cudaMemcpyAsync(r->otus.data(), r->d_otus.p, r->n * sizeof(kg_otu), cudaMemcpyDeviceToHost, st));
+    KG_TRY(pool_take_host(ctx, r->stats.num_calls * sizeof(kg_call), &r->h_calls));
+    KG_TRY(pool_take_host(ctx, r->n * sizeof(kg_otu), &r->h_otus));
+    if (r->stats.num_calls) CU(cudaMemcpyAsync(r->h_calls.p, r->d_calls.p, r->stats.num_calls * sizeof(kg_call), cudaMemcpyDeviceToHost, st));
+    if (r->n) CU(cudaMemcpyAsync(r->h_otus.p, r->d_otus.p, r->n * sizeof(kg_otu), cudaMemcpyDeviceToHost, st));
     if (r->params.emit_hits) {
-        r->hits.resize(r->stats.num_hits);
-        if (r->stats.num_hits) CU(cudaMemcpyAsync(r->hits.data(), r->d_hits.p, r->stats.num_hits * sizeof(kg_hit), cudaMemcpyDeviceToHost, st));
+        KG_TRY(pool_take_host(ctx, r->stats.num_hits * sizeof(kg_hit), &r->h_hits));
+        if (r->stats.num_hits) CU(cudaMemcpyAsync(r->h_hits.p, r->d_hits.p, r->stats.num_hits * sizeof(kg_hit), cudaMemcpyDeviceToHost, st));
     }
     cudaEventRecord(ctx->ev[3], st);
     CU(cudaStreamSynchronize(st));
@@ -719,29 +787,33 @@ extern "C" int kg_result_stats(const kg_result* r, kg_run_stats* s) {
 extern "C" int kg_result_calls(kg_result* r, const kg_call** calls, size_t* n) {
     if (!r || !calls || !n) KG_FAIL(KG_EINVAL, "kg_result_calls: null argument");
     KG_TRY(kg_result_fetch(r));
-    *calls = r->calls.data();
-    *n = r->calls.size();
+    *calls = (const kg_call*)r->h_calls.p;
+    *n = r->stats.num_calls;
     return KG_OK;
 }
 extern "C" int kg_result_otus(kg_result* r, const kg_otu** otus, size_t* n) {
     if (!r || !otus || !n) KG_FAIL(KG_EINVAL, "kg_result_otus: null argument");
     KG_TRY(kg_result_fetch(r));
-    *otus = r->otus.data();
-    *n = r->otus.size();
+    *otus = (const kg_otu*)r->h_otus.p;
+    *n = r->n;
     return KG_OK;
 }
 extern "C" int kg_result_hits(kg_result* r, const kg_hit** hits, size_t* n) {
     if (!r || !hits || !n) KG_FAIL(KG_EINVAL, "kg_result_hits: null argument");
     if (!r->params.emit_hits) KG_FAIL(KG_EINVAL, "kg_result_hits: run was made without params.emit_hits");
     KG_TRY(kg_result_fetch(r));
-    *hits = r->hits.data();
-    *n = r->hits.size();
+    *hits = (const kg_hit*)r->h_hits.p;
+    *n = r->stats.num_hits;
     return KG_OK;
 }
 extern "C" void kg_result_free(kg_result* r) {
     if (!r) return;
-    r->d_calls.release();
-    r->d_otus.release();
-    r->d_hits.release();
+    // buffers go back to the context's pools (results must be freed before kg_shutdown)
+    pool_give_dev(r->ctx, &r->d_calls);
+    pool_give_dev(r->ctx, &r->d_otus);
+    pool_give_dev(r->ctx, &r->d_hits);
+    pool_give_host(r->ctx, &r->h_calls);
+    pool_give_host(r->ctx, &r->h_otus);
+    pool_give_host(r->ctx, &r->h_hits);
     delete r;
 }
