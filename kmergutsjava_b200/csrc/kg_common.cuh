@@ -59,7 +59,18 @@ struct KgTableView {
     const uint4* buckets;   // 2 x uint4 per bucket
     const int4* payload;    // {oI, avgFromEnd, fI, float bits of wt} per slot
     uint32_t num_buckets;   // home buckets (hash range); KG_TAIL_BUCKETS more follow
+    // L2-resident prefilter (kg_device.cuh): one 64-bit word per probe, two bits per key.  0 words = no filter.
+    const unsigned long long* filter;
+    uint32_t filter_words;
 };
+
+// On B200 an L2 miss always brings in the whole 128-byte line (ncu: ~124 B of DRAM reads per random 32-byte sector
+// load, whatever the load flavour or cudaLimitMaxL2FetchGranularity), so the DRAM roofline of a miss-dominant probe
+// stream is (HBM bandwidth / 128 B) lookups/s.  About 85-90 % of all lookups are misses.  A blocked Bloom filter small
+// enough to stay in the 126 MB L2 answers most of them without touching DRAM: random sector reads that hit L2 run at
+// 2.9e11/s against 5.2e10/s from DRAM (tools/probe_bench).
+constexpr uint64_t KG_FILTER_MAX_BYTES = 96ull << 20; // leave L2 room for the residue stream and the outputs
+constexpr double KG_FILTER_BITS_PER_KEY = 4.0;
 
 __host__ __device__ __forceinline__ uint64_t kg_mix(uint64_t k) {
     // murmur3 finaliser; the k-mer code is a base-20 number with very regular low digits
@@ -70,9 +81,19 @@ __host__ __device__ __forceinline__ uint64_t kg_mix(uint64_t k) {
     k ^= k >> 33;
     return k;
 }
+__host__ __device__ __forceinline__ uint32_t kg_bucket_of_hash(uint64_t h, uint32_t num_buckets) {
+    return (uint32_t)(((h >> 32) * (uint64_t)num_buckets) >> 32);
+}
 __host__ __device__ __forceinline__ uint32_t kg_home_bucket(uint64_t key, uint32_t num_buckets) {
-    uint32_t h = (uint32_t)(kg_mix(key) >> 32);
-    return (uint32_t)(((uint64_t)h * (uint64_t)num_buckets) >> 32);
+    return kg_bucket_of_hash(kg_mix(key), num_buckets);
+}
+// filter word and the two bits of a key, from the low half of the same hash (the bucket uses the high half)
+__host__ __device__ __forceinline__ uint32_t kg_filter_word(uint64_t h, uint32_t filter_words) {
+    return (uint32_t)(((h & 0xFFFFFFFFull) * (uint64_t)filter_words) >> 32);
+}
+__host__ __device__ __forceinline__ unsigned long long kg_filter_mask(uint64_t h) {
+    const uint64_t g = h * 0x9E3779B97F4A7C15ull;
+    return (1ull << (g >> 58)) | (1ull << ((g >> 52) & 63));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

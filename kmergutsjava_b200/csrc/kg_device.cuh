@@ -19,6 +19,33 @@ __device__ __forceinline__ KgBucket kg_load_bucket(const uint4* buckets, uint32_
     return r;
 }
 
+// L2 eviction policies: the prefilter must stay resident in L2 (evict_last) while the bucket array, the residue
+// stream and the outputs merely pass through it (evict_first).
+__device__ __forceinline__ uint64_t kg_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t kg_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ KgBucket kg_load_bucket_hint(const uint4* buckets, uint32_t b, uint64_t policy) {
+    KgBucket r;
+    const uint4* p = buckets + 2ull * b;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ unsigned long long kg_load_filter_word(const unsigned long long* filter, uint32_t w, uint64_t policy) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(filter + w), "l"(policy));
+    return v;
+}
+
 // Bit i of the result is set when slot i of the bucket holds `key`.
 __device__ __forceinline__ uint32_t kg_bucket_match(const KgBucket& bk, uint64_t key) {
     const uint32_t lo = (uint32_t)key;

@@ -8,6 +8,8 @@ struct kg_table {
     uint4* d_buckets = nullptr;
     int4* d_payload = nullptr;
     uint32_t num_buckets = 0;
+    unsigned long long* d_filter = nullptr;
+    uint32_t filter_words = 0;
     kg_table_info info = {};
     KgTableView view() const;
 };

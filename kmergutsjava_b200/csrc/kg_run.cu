@@ -138,26 +138,53 @@ __global__ __launch_bounds__(PROBE_BLK) void k_probe(const uint8_t* __restrict__
 #pragma unroll
         for (int i = 0; i < 20; i++) q[i] = ((c[i] * 20u + c[i + 1]) * 20u + c[i + 2]) * 20u + c[i + 3];
 
+        uint32_t valid = 0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) valid |= (uint32_t)(((bad >> i) & 0xFFu) == 0u) << i;
+        nk = __popc(valid);
+
+        // phase 1 -- L2-resident prefilter: one 8-byte word per window, eight loads in flight per thread.  Only the
+        // windows whose two bits are both set (all true signatures + ~17 % of the rest) go on to DRAM.
+        const uint64_t pol_keep = kg_policy_evict_last(), pol_stream = kg_policy_evict_first();
+        uint32_t pass = valid;
+        if (tab.filter_words) {
+            pass = 0;
+#pragma unroll
+            for (int half = 0; half < PT; half += 8) {
+                unsigned long long fw[8], fm[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int i = half + j;
+                    const uint64_t h = kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]);
+                    fm[j] = kg_filter_mask(h);
+                    fw[j] = 0;
+                    if ((valid >> i) & 1u) fw[j] = kg_load_filter_word(tab.filter, kg_filter_word(h, tab.filter_words), pol_keep);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) pass |= (uint32_t)((fw[j] & fm[j]) == fm[j]) << (half + j);
+            }
+            pass &= valid;
+        }
+
+        // phase 2 -- the surviving windows probe their bucket: one 256-bit sector load each, PROBE_G in flight
 #pragma unroll
         for (int g = 0; g < PT; g += PROBE_G) {
+            if (((pass >> g) & ((1u << PROBE_G) - 1u)) == 0u) continue;
             uint64_t key[PROBE_G];
             uint32_t bkt[PROBE_G];
-            bool valid[PROBE_G];
             KgBucket bk[PROBE_G];
 #pragma unroll
             for (int j = 0; j < PROBE_G; j++) {
                 const int i = g + j;
-                valid[j] = ((bad >> i) & 0xFFu) == 0u;
                 key[j] = (uint64_t)q[i] * 160000ull + q[i + 4];
                 bkt[j] = kg_home_bucket(key[j], tab.num_buckets);
             }
 #pragma unroll
             for (int j = 0; j < PROBE_G; j++)
-                if (valid[j]) bk[j] = kg_load_bucket(tab.buckets, bkt[j]);
+                if ((pass >> (g + j)) & 1u) bk[j] = kg_load_bucket_hint(tab.buckets, bkt[j], pol_stream);
 #pragma unroll
             for (int j = 0; j < PROBE_G; j++) {
-                if (!valid[j]) continue;
-                nk++;
+                if (!((pass >> (g + j)) & 1u)) continue;
                 uint32_t m = kg_bucket_match(bk[j], key[j]);
                 uint32_t slot = 0xFFFFFFFFu;
                 if (m) slot = bkt[j] * KG_BUCKET_KEYS + (__ffs(m) - 1);

@@ -54,6 +54,8 @@ void DevBuf::release() {
     cap = 0;
 }
 
+static double filter_bits_per_key();
+
 // ---------------------------------------------------------------------------------------------------------------
 // reference-format image parser (streaming, so a 10-100 GB file never has to sit in host memory twice)
 // ---------------------------------------------------------------------------------------------------------------
@@ -213,6 +215,14 @@ __global__ void k_scatter(const uint64_t* __restrict__ comp, const uint32_t* __r
     payload_out[slot] = payload_in[idx[r]];
 }
 
+__global__ void k_filter_build(const uint64_t* __restrict__ comp, size_t n, unsigned long long* __restrict__ filter,
+                               uint32_t filter_words) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t h = kg_mix(comp[r] & 0x7FFFFFFFFull);
+    atomicOr(&filter[kg_filter_word(h, filter_words)], kg_filter_mask(h));
+}
+
 __global__ void k_count_flagged(const uint32_t* __restrict__ words, size_t nbuckets_total, unsigned long long* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool f = i < nbuckets_total && (words[i * 8 + 7] & KG_W7_FLAG);
@@ -243,6 +253,8 @@ KgTableView kg_table::view() const {
     v.buckets = d_buckets;
     v.payload = d_payload;
     v.num_buckets = num_buckets;
+    v.filter = d_filter;
+    v.filter_words = filter_words;
     return v;
 }
 
@@ -320,6 +332,15 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
         k_scatter<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, idx, tb, n_unique, d_payload, (uint32_t*)t->d_buckets,
                                                             t->d_payload, total_slots, d_ctr);
         k_count_flagged<<<blocks_for(nb_total, 256), 256, 0, st>>>((const uint32_t*)t->d_buckets, nb_total, d_ctr + 1);
+        if (filter_bits_per_key() > 0) { // L2-resident prefilter over the same keys
+            uint64_t bytes = (uint64_t)((double)n_unique * filter_bits_per_key() / 8.0);
+            if (bytes > KG_FILTER_MAX_BYTES) bytes = KG_FILTER_MAX_BYTES;
+            if (bytes < 4096) bytes = 4096;
+            t->filter_words = (uint32_t)(bytes / 8);
+            CU(cudaMalloc(&t->d_filter, (size_t)t->filter_words * 8));
+            CU(cudaMemsetAsync(t->d_filter, 0, (size_t)t->filter_words * 8, st));
+            k_filter_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter, t->filter_words);
+        }
         // Every stored key must be found again.  With repeated keys only the surviving copy's payload can match, so
         // the payload comparison is skipped for inputs that had duplicates.
         (void)verify_payload;
@@ -346,10 +367,14 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
     t->info.num_signatures = (int64_t)n_unique;
     t->info.num_buckets = (int64_t)nb_total;
     t->info.flagged_buckets = (int64_t)h_ctr[1];
-    t->info.device_bytes = (int64_t)(nb_total * 32 + total_slots * sizeof(int4));
+    t->info.device_bytes = (int64_t)(nb_total * 32 + total_slots * sizeof(int4) + (size_t)t->filter_words * 8);
     return KG_OK;
 }
 
+static double filter_bits_per_key() { // KG_FILTER_BITS=0 disables the prefilter
+    const char* e = getenv("KG_FILTER_BITS");
+    return e ? atof(e) : KG_FILTER_BITS_PER_KEY;
+}
 static double table_load_factor() {
     const char* e = getenv("KG_TABLE_LOAD");
     double v = e ? atof(e) : 0.0;
@@ -474,5 +499,6 @@ extern "C" void kg_table_free(kg_table* t) {
     if (!t) return;
     if (t->d_buckets) cudaFree(t->d_buckets);
     if (t->d_payload) cudaFree(t->d_payload);
+    if (t->d_filter) cudaFree(t->d_filter);
     delete t;
 }
