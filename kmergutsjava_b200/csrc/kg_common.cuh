@@ -38,26 +38,29 @@ void kg_set_error(const char* fmt, ...);
 //
 // The reference streams 24-byte {int64 key; int32 oI; int32 avgFromEnd; int32 fI; float wt} slots of an
 // open-addressing table with linear probing and no wrap-around (KGJ:944-1034, 995-999).  All a probe has to answer
-// is "is k-mer v stored, and with which payload"; the layout is ours.  A key is < 20^8 < 2^35, so a 32-byte sector
-// holds seven of them:
+// is "is k-mer v stored, and with which payload"; the layout is ours.  A key is < 20^8 < 2^35.
 //
-//   bucket = 8 x uint32:  w[0..6] = low 32 bits of keys 0..6
-//                         w[7]    = bits [3i, 3i+3): bits 32..34 of key i (i = 0..6)
-//                                   bit  31        : overflow flag -- some key whose probe sequence passes through
-//                                                    this bucket lives in a later one
+// One bucket = one 128-byte L2 line (B200 fetches the whole line from HBM on a miss, whatever the load asks for):
+//
+//   sector 0 (32 bytes) = 8 x uint32:  w[0..5] = low 32 bits of keys 0..5
+//                                      w[6]    = bits [3i, 3i+3): bits 32..34 of key i (i = 0..5)
+//                                                bit 31: overflow flag -- some key whose probe sequence passes through
+//                                                        this bucket lives in a later one
+//                                      w[7]    = unused (0)
+//   sectors 1..3 (96 bytes)         =  six 16-byte payloads {oI, avgFromEnd, fI, float bits of wt}, one per key
 //   empty slot = 35 one-bits (0x7FFFFFFFF > 20^8).
 //
-// A lookup reads exactly one sector unless the flag is set (a few % of buckets at load 0.6).  Payloads live in a
-// separate array of 16-byte records indexed by slot = bucket*7 + lane and are read only on a hit.
+// A lookup reads ONE sector (the key sector) unless the flag is set; on a hit the payload is 16 more bytes of the line
+// the probe has just pulled into L2, so a hit costs no second DRAM access.  slot = bucket*6 + lane.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int KG_BUCKET_KEYS = 7;
-constexpr uint32_t KG_W7_EMPTY = 0x001FFFFFu; // all seven 3-bit high fields = 7, flag clear
-constexpr uint32_t KG_W7_FLAG = 0x80000000u;
+constexpr int KG_BUCKET_KEYS = 6;
+constexpr int KG_LINE_UINT4 = 8;              // 128-byte line = 8 x uint4: [0..1] keys, [2..7] payloads
+constexpr uint32_t KG_W6_EMPTY = 0x0003FFFFu; // all six 3-bit high fields = 7, flag clear
+constexpr uint32_t KG_W6_FLAG = 0x80000000u;
 constexpr uint32_t KG_TAIL_BUCKETS = 4096;    // spill room past the last home bucket (no wrap-around in our layout either)
 
 struct KgTableView {
-    const uint4* buckets;   // 2 x uint4 per bucket
-    const int4* payload;    // {oI, avgFromEnd, fI, float bits of wt} per slot
+    const uint4* lines;     // KG_LINE_UINT4 x uint4 per bucket
     uint32_t num_buckets;   // home buckets (hash range); KG_TAIL_BUCKETS more follow
     // L2-resident prefilter (kg_device.cuh): one 64-bit word per probe, two bits per key.  0 words = no filter.
     const unsigned long long* filter;
@@ -69,8 +72,8 @@ struct KgTableView {
 // stream is (HBM bandwidth / 128 B) lookups/s.  About 85-90 % of all lookups are misses.  A blocked Bloom filter small
 // enough to stay in the 126 MB L2 answers most of them without touching DRAM: random sector reads that hit L2 run at
 // 2.9e11/s against 5.2e10/s from DRAM (tools/probe_bench).
-constexpr uint64_t KG_FILTER_MAX_BYTES = 96ull << 20; // leave L2 room for the residue stream and the outputs
-constexpr double KG_FILTER_BITS_PER_KEY = 4.0;
+constexpr uint64_t KG_FILTER_MAX_BYTES = 76ull << 20; // the persisting-L2 carve-out tops out at 79 MiB on B200
+constexpr double KG_FILTER_BITS_PER_KEY = 3.0;
 
 __host__ __device__ __forceinline__ uint64_t kg_mix(uint64_t k) {
     // murmur3 finaliser; the k-mer code is a base-20 number with very regular low digits
@@ -130,4 +133,4 @@ struct kg_context {
 };
 
 // counters written by the pipeline, one block of 8 x uint64 per run
-enum { KG_CTR_HITS = 0, KG_CTR_KMERS = 1, KG_CTR_CALLS = 2, KG_CTR_OVERFLOW = 3, KG_CTR_VPOS = 4, KG_CTR_COUNT = 8 };
+enum { KG_CTR_HITS = 0, KG_CTR_KMERS = 1, KG_CTR_CALLS = 2, KG_CTR_OVERFLOW = 3, KG_CTR_VPOS = 4, KG_CTR_COUNT = 8 }; // h_counters has KG_CTR_COUNT + 1 slots: the last receives the call total

@@ -5,8 +5,7 @@
 
 struct kg_table {
     kg_context* ctx = nullptr;
-    uint4* d_buckets = nullptr;
-    int4* d_payload = nullptr;
+    uint4* d_lines = nullptr;   // 128-byte bucket lines (kg_common.cuh)
     uint32_t num_buckets = 0;
     unsigned long long* d_filter = nullptr;
     uint32_t filter_words = 0;

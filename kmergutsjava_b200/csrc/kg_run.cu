@@ -20,7 +20,6 @@ constexpr int PROBE_BLK = 256;    // threads per block
 constexpr int TILE = PT * PROBE_BLK;
 constexpr int TILE_SHIFT = 12;
 static_assert(TILE == (1 << TILE_SHIFT), "tile size");
-constexpr int STAGE_STRIDE = PT + 1; // +1: conflict-free shared-memory stride
 
 inline unsigned blocks_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
@@ -96,30 +95,72 @@ __global__ void k_translate(const uint8_t* __restrict__ seq, const uint64_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// encode + probe.  One thread owns PT consecutive stream positions; a block owns a 4096-position tile.
-//   * 24 residue bytes per thread (16 + 8 halo) come in as one 16-byte and one 8-byte coalesced load
-//   * residue codes via a 256-byte shared-memory LUT; 4-mer partial products give each window in one 64-bit IMAD
-//   * PROBE_G independent 256-bit sector loads are in flight per thread before the first compare
-//   * hits are compacted in tile order: per-thread slots staged in shared memory, block-wide exclusive scan,
-//     ONE global atomic per tile to claim an output chunk; chunks are stitched into global order by k_gather.
+// encode + probe.  A block owns a 4096-position tile of the residue stream and works in four phases:
+//   A  encode   one thread owns PT = 16 consecutive positions: 24 residue bytes (16 + 8 halo) arrive as one 16-byte and
+//               one 8-byte coalesced load, codes come from a 256-byte shared-memory LUT, 4-mer partial products give
+//               every 8-mer in one 64-bit IMAD (first residue most significant, KGJ:274-282)
+//      filter   every valid window tests its two bits in the L2-resident Bloom prefilter: 16 independent 8-byte loads
+//               in flight per thread; ~70 % of the windows end here without touching DRAM
+//   B  compact  the surviving (key, position) pairs are packed into a shared-memory queue (block-wide scan)
+//   C  probe    the queue is probed DENSELY: every lane busy, PROBE_U independent 256-bit sector loads in flight per
+//               thread.  A hit's 16-byte payload is read at once -- it sits in the 128-byte line the probe has just
+//               pulled into L2 -- and parked in shared memory at the hit's position
+//   D  emit     hits leave in tile order: block-wide scan of per-thread hit counts, ONE global atomic per tile to claim
+//               an output chunk, (position, payload) records written by the owning threads.
+// The run FSM reads the chunks through (tile_base, tile_cnt); no global sort or re-ordering pass is needed.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PROBE_G = 4;
+constexpr int PROBE_U = 4;
+constexpr size_t PROBE_SMEM_PSTAGE = (size_t)TILE * sizeof(int4);                 // payload parked per position
+constexpr size_t PROBE_SMEM_QUEUE = (size_t)TILE * sizeof(unsigned long long);    // survivor queue
+constexpr size_t PROBE_SMEM = PROBE_SMEM_PSTAGE + PROBE_SMEM_QUEUE;               // 96 KiB: needs the opt-in limit
 
-__global__ __launch_bounds__(PROBE_BLK) void k_probe(const uint8_t* __restrict__ stream, uint32_t vtotal, KgTableView tab,
-                                                     uint2* __restrict__ chunk, uint32_t hit_cap,
-                                                     uint32_t* __restrict__ tile_base, uint32_t* __restrict__ tile_cnt,
-                                                     unsigned long long* __restrict__ ctr) {
+// exclusive scan of one value per thread across the block; returns the block total through *total
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t mine, uint32_t* warp_tot, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < PROBE_BLK / 32; w++) {
+        const uint32_t t = warp_tot[w];
+        if (w < wid) before += t;
+        tot += t;
+    }
+    *total = tot;
+    return before + incl - mine;
+}
+
+__global__ __launch_bounds__(PROBE_BLK, 2) void k_probe(const uint8_t* __restrict__ stream, uint32_t vtotal, KgTableView tab,
+                                                        uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload,
+                                                        uint32_t hit_cap, uint32_t* __restrict__ tile_base,
+                                                        uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr,
+                                                        uint32_t flags) {
+    extern __shared__ int4 smem_dyn[];
+    int4* pstage = smem_dyn;                                                        // [TILE]
+    unsigned long long* queue = reinterpret_cast<unsigned long long*>(smem_dyn + TILE); // [TILE]
     __shared__ uint8_t lut[256];
-    __shared__ uint32_t stage[PROBE_BLK * STAGE_STRIDE];
-    __shared__ uint32_t warp_hits[PROBE_BLK / 32], warp_kmers[PROBE_BLK / 32];
+    __shared__ uint32_t hitbits[TILE / 32];
+    __shared__ uint32_t warp_a[PROBE_BLK / 32], warp_b[PROBE_BLK / 32], warp_kmers[PROBE_BLK / 32];
     __shared__ uint32_t s_base;
 
     const int tid = threadIdx.x;
     lut[tid] = (tid >= 'A' && tid <= 'Z') ? c_aa_code[tid - 'A'] : 20;
+    if (tid < TILE / 32) hitbits[tid] = 0;
     __syncthreads();
 
+    const uint64_t pol_keep = kg_policy_evict_last();
+    const uint64_t pol_stream = (flags & 1u) ? kg_policy_evict_normal() : kg_policy_evict_first();
     const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
-    uint32_t hitmask = 0, nk = 0;
+
+    // ---- A: encode + prefilter ----
+    uint32_t pass = 0, nk = 0;
+    uint32_t q[20];
     if (p0 < vtotal) {
         const uint4 a = *reinterpret_cast<const uint4*>(stream + p0);
         const uint2 b = *reinterpret_cast<const uint2*>(stream + p0 + 16);
@@ -133,90 +174,87 @@ __global__ __launch_bounds__(PROBE_BLK) void k_probe(const uint8_t* __restrict__
         }
         const uint32_t left = vtotal - p0; // bytes of this thread's 24 that exist
         if (left < 24) bad |= ~0u << left;
-        // pairs -> 4-mers -> 8-mers (first residue most significant, KGJ:274-282)
-        uint32_t q[20];
 #pragma unroll
         for (int i = 0; i < 20; i++) q[i] = ((c[i] * 20u + c[i + 1]) * 20u + c[i + 2]) * 20u + c[i + 3];
-
         uint32_t valid = 0;
 #pragma unroll
         for (int i = 0; i < PT; i++) valid |= (uint32_t)(((bad >> i) & 0xFFu) == 0u) << i;
-        nk = __popc(valid);
-
-        // phase 1 -- L2-resident prefilter: one 8-byte word per window, eight loads in flight per thread.  Only the
-        // windows whose two bits are both set (all true signatures + ~17 % of the rest) go on to DRAM.
-        const uint64_t pol_keep = kg_policy_evict_last(), pol_stream = kg_policy_evict_first();
-        uint32_t pass = valid;
+        nk = __popc(valid); // lookups = windows the reference enumerates (KGJ:912-921)
+        pass = valid;
         if (tab.filter_words) {
+            unsigned long long fw[PT];
+#pragma unroll
+            for (int i = 0; i < PT; i++) {
+                fw[i] = 0;
+                if ((valid >> i) & 1u) {
+                    const uint64_t h = kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]);
+                    const uint32_t w = kg_filter_word(h, tab.filter_words);
+                    fw[i] = (flags & 2u) ? __ldg(tab.filter + w) : kg_load_filter_word(tab.filter, w, pol_keep);
+                }
+            }
             pass = 0;
 #pragma unroll
-            for (int half = 0; half < PT; half += 8) {
-                unsigned long long fw[8], fm[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int i = half + j;
-                    const uint64_t h = kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]);
-                    fm[j] = kg_filter_mask(h);
-                    fw[j] = 0;
-                    if ((valid >> i) & 1u) fw[j] = kg_load_filter_word(tab.filter, kg_filter_word(h, tab.filter_words), pol_keep);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++) pass |= (uint32_t)((fw[j] & fm[j]) == fm[j]) << (half + j);
+            for (int i = 0; i < PT; i++) {
+                const unsigned long long fm = kg_filter_mask(kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]));
+                pass |= (uint32_t)((fw[i] & fm) == fm) << i;
             }
             pass &= valid;
         }
-
-        // phase 2 -- the surviving windows probe their bucket: one 256-bit sector load each, PROBE_G in flight
-#pragma unroll
-        for (int g = 0; g < PT; g += PROBE_G) {
-            if (((pass >> g) & ((1u << PROBE_G) - 1u)) == 0u) continue;
-            uint64_t key[PROBE_G];
-            uint32_t bkt[PROBE_G];
-            KgBucket bk[PROBE_G];
-#pragma unroll
-            for (int j = 0; j < PROBE_G; j++) {
-                const int i = g + j;
-                key[j] = (uint64_t)q[i] * 160000ull + q[i + 4];
-                bkt[j] = kg_home_bucket(key[j], tab.num_buckets);
-            }
-#pragma unroll
-            for (int j = 0; j < PROBE_G; j++)
-                if ((pass >> (g + j)) & 1u) bk[j] = kg_load_bucket_hint(tab.buckets, bkt[j], pol_stream);
-#pragma unroll
-            for (int j = 0; j < PROBE_G; j++) {
-                if (!((pass >> (g + j)) & 1u)) continue;
-                uint32_t m = kg_bucket_match(bk[j], key[j]);
-                uint32_t slot = 0xFFFFFFFFu;
-                if (m) slot = bkt[j] * KG_BUCKET_KEYS + (__ffs(m) - 1);
-                else if (bk[j].w[7] & KG_W7_FLAG) slot = kg_lookup_from(tab, key[j], bkt[j] + 1); // rare second sector
-                if (slot != 0xFFFFFFFFu) {
-                    hitmask |= 1u << (g + j);
-                    stage[tid * STAGE_STRIDE + g + j] = slot;
-                }
-            }
-        }
     }
 
-    // block-wide exclusive scan of per-thread hit counts (tile order = thread order)
-    const int lane = tid & 31, wid = tid >> 5;
-    const uint32_t mine = __popc(hitmask);
-    uint32_t incl = mine;
+    // ---- B: survivors -> shared-memory queue, tile order ----
+    uint32_t nsurv;
+    uint32_t qo = block_excl_scan(__popc(pass), warp_a, &nsurv);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += t;
-    }
+    for (int i = 0; i < PT; i++)
+        if ((pass >> i) & 1u) queue[qo++] = ((uint64_t)q[i] * 160000ull + q[i + 4]) | ((unsigned long long)(tid * PT + i) << 35);
     const uint32_t wk = __reduce_add_sync(0xFFFFFFFFu, nk);
-    if (lane == 31) warp_hits[wid] = incl;
-    if (lane == 0) warp_kmers[wid] = wk;
+    if ((tid & 31) == 0) warp_kmers[tid >> 5] = wk;
     __syncthreads();
-    uint32_t before = 0, total = 0;
+
+    // ---- C: dense probing of the queue ----
+    for (uint32_t k0 = 0; k0 < nsurv; k0 += PROBE_BLK * PROBE_U) {
+        uint64_t key[PROBE_U];
+        uint32_t lp[PROBE_U], bkt[PROBE_U], slot[PROBE_U];
+        bool on[PROBE_U];
+        KgBucket bk[PROBE_U];
+        int4 pl[PROBE_U];
 #pragma unroll
-    for (int w = 0; w < PROBE_BLK / 32; w++) {
-        const uint32_t t = warp_hits[w];
-        if (w < wid) before += t;
-        total += t;
+        for (int u = 0; u < PROBE_U; u++) {
+            const uint32_t k = k0 + u * PROBE_BLK + tid;
+            on[u] = k < nsurv;
+            const unsigned long long e = on[u] ? queue[k] : 0ull;
+            key[u] = e & 0x7FFFFFFFFull;
+            lp[u] = (uint32_t)(e >> 35);
+            bkt[u] = kg_home_bucket(key[u], tab.num_buckets);
+        }
+#pragma unroll
+        for (int u = 0; u < PROBE_U; u++)
+            if (on[u]) bk[u] = kg_load_bucket_hint(tab.lines, bkt[u], pol_stream);
+#pragma unroll
+        for (int u = 0; u < PROBE_U; u++) {
+            slot[u] = 0xFFFFFFFFu;
+            if (!on[u]) continue;
+            const uint32_t m = kg_bucket_match(bk[u], key[u]);
+            if (m) slot[u] = bkt[u] * KG_BUCKET_KEYS + (__ffs(m) - 1);
+            else if (bk[u].w[6] & KG_W6_FLAG) slot[u] = kg_lookup_from(tab, key[u], bkt[u] + 1); // rare second line
+        }
+#pragma unroll
+        for (int u = 0; u < PROBE_U; u++)
+            if (slot[u] != 0xFFFFFFFFu) pl[u] = kg_load_payload(tab.lines, slot[u]);
+#pragma unroll
+        for (int u = 0; u < PROBE_U; u++)
+            if (slot[u] != 0xFFFFFFFFu) {
+                pstage[lp[u]] = pl[u];
+                atomicOr(&hitbits[lp[u] >> 5], 1u << (lp[u] & 31));
+            }
     }
+    __syncthreads();
+
+    // ---- D: hits out, tile order ----
+    const uint32_t hitmask = (hitbits[tid >> 1] >> ((tid & 1) * 16)) & 0xFFFFu;
+    uint32_t total;
+    const uint32_t ho = block_excl_scan(__popc(hitmask), warp_b, &total);
     if (tid == 0) {
         uint32_t kmers = 0;
 #pragma unroll
@@ -234,58 +272,41 @@ __global__ __launch_bounds__(PROBE_BLK) void k_probe(const uint8_t* __restrict__
     __syncthreads();
     const uint32_t base = s_base;
     if (base != 0xFFFFFFFFu && hitmask) {
-        uint32_t o = base + before + (incl - mine);
+        uint32_t o = base + ho;
         uint32_t m = hitmask;
         while (m) {
             const int i = __ffs(m) - 1;
             m &= m - 1;
-            chunk[o++] = make_uint2(p0 + (uint32_t)i, stage[tid * STAGE_STRIDE + i]);
+            chunk_pos[o] = p0 + (uint32_t)i;
+            chunk_payload[o] = pstage[tid * PT + i];
+            o++;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// stitch the per-tile chunks into one position-sorted hit list and attach the 16-byte payloads (one warp per tile)
+// "-d" only: stitch the per-tile chunks into one position-sorted hit list (one warp per tile)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_gather(const uint2* __restrict__ chunk, const uint32_t* __restrict__ tile_base,
-                         const uint32_t* __restrict__ tile_out, uint32_t ntiles, const int4* __restrict__ payload,
+__global__ void k_gather(const uint32_t* __restrict__ chunk_pos, const int4* __restrict__ chunk_payload,
+                         const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_out, uint32_t ntiles,
                          uint32_t* __restrict__ hit_pos, int4* __restrict__ hit_payload) {
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= ntiles) return;
     const uint32_t out = tile_out[t], cnt = tile_out[t + 1] - out, base = tile_base[t];
     for (uint32_t j = lane; j < cnt; j += 32) {
-        const uint2 h = chunk[base + j];
-        hit_pos[out + j] = h.x;
-        hit_payload[out + j] = __ldg(&payload[h.y]);
+        hit_pos[out + j] = chunk_pos[base + j];
+        hit_payload[out + j] = chunk_payload[base + j];
     }
-}
-
-// lo[v] = index of the first hit at or after the start of virtual sequence v (v = nv gives the total)
-__global__ void k_ranges(const uint64_t* __restrict__ voff, uint64_t nv, const uint32_t* __restrict__ tile_out,
-                         uint32_t ntiles, const uint32_t* __restrict__ hit_pos, uint32_t* __restrict__ lo) {
-    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v > nv) return;
-    const uint64_t x = voff[v];
-    const uint64_t t = x >> TILE_SHIFT;
-    if (t >= ntiles) {
-        lo[v] = tile_out[ntiles];
-        return;
-    }
-    uint32_t a = tile_out[t], b = tile_out[t + 1]; // first hit >= x lies in [a, b]
-    while (a < b) {
-        uint32_t mid = (a + b) >> 1;
-        if ((uint64_t)hit_pos[mid] < x) a = mid + 1;
-        else b = mid;
-    }
-    lo[v] = a;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // run FSM: one thread per sequence walks its containers in the reference's order (+0,+1,+2,-0,-1,-2) so that the
-// OTU buffer sees the calls in the same order (KGJ:540-557).  Calls of container v go to the sparse slots
-// [lo[v]/min_hits, lo[v+1]/min_hits): a call consumes >= min_hits counted hits and no hit is counted twice, so the
-// slots cannot overflow and no second pass is needed to size them.
+// OTU buffer sees the calls in the same order (KGJ:540-557).  The hits of a container are read straight from the
+// per-tile chunks k_probe wrote: tiles in order, each chunk already sorted by position.
+// lo[v] = rank of the container's first hit in the global position order (tile_out = exclusive scan of tile_cnt).
+// Calls of container v go to the sparse slots [lo[v]/min_hits, lo[v+1]/min_hits): a call consumes >= min_hits counted
+// hits and no hit is counted twice, so the slots cannot overflow and no second pass is needed to size them.
 // ---------------------------------------------------------------------------------------------------------------
 struct SparseEmit {
     KgDevCall* dst;
@@ -293,28 +314,68 @@ struct SparseEmit {
 };
 
 __global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, uint64_t nseq, int per_seq,
-                                             const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hit_pos,
-                                             const int4* __restrict__ hit_payload, KgFsmParams p,
-                                             KgDevCall* __restrict__ sparse, uint32_t* __restrict__ call_cnt,
-                                             kg_otu* __restrict__ otus) {
+                                             const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_out,
+                                             uint32_t ntiles, const uint32_t* __restrict__ chunk_pos,
+                                             const int4* __restrict__ chunk_payload, KgFsmParams p,
+                                             KgDevCall* __restrict__ sparse, uint32_t* __restrict__ lo,
+                                             uint32_t* __restrict__ call_cnt, kg_otu* __restrict__ otus,
+                                             const unsigned long long* __restrict__ ctr) {
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseq) return;
+    if (ctr[KG_CTR_OVERFLOW]) { // some tile could not claim its chunk: the host repeats the pass with larger buffers
+        for (int k = 0; k < per_seq; k++) call_cnt[s * per_seq + k] = 0;
+        return;
+    }
     KgFsm f;
     f.begin_sequence();
     for (int k = 0; k < per_seq; k++) {
         const uint64_t v = s * per_seq + k;
-        const uint32_t a = lo[v], b = lo[v + 1];
-        const uint32_t base = (uint32_t)voff[v];
+        const uint32_t x0 = (uint32_t)voff[v], x1 = (uint32_t)voff[v + 1];
+        uint32_t t = x0 >> TILE_SHIFT;
+        // first hit at or after x0 inside tile t
+        uint32_t e = 0, cnt = 0, base = 0, rank = tile_out[ntiles];
+        if (t < ntiles) {
+            const uint32_t o = tile_out[t];
+            cnt = tile_out[t + 1] - o;
+            base = tile_base[t];
+            uint32_t a = 0, b = cnt;
+            while (a < b) {
+                const uint32_t mid = (a + b) >> 1;
+                if (chunk_pos[base + mid] < x0) a = mid + 1;
+                else b = mid;
+            }
+            e = a;
+            rank = o + a;
+        }
+        lo[v] = rank;
         f.begin_container();
-        SparseEmit emit{sparse + a / (uint32_t)p.min_hits};
-        for (uint32_t i = a; i < b; i++) {
-            const int4 pl = hit_payload[i];
-            KgHitLite h = {(int)(hit_pos[i] - base), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
-            f.hit(p, h, emit);
+        SparseEmit emit{sparse + rank / (uint32_t)p.min_hits};
+        bool done = x1 <= x0;
+        while (!done && t < ntiles) {
+            for (; e < cnt; e++) {
+                const uint32_t g = chunk_pos[base + e];
+                if (g >= x1) {
+                    done = true;
+                    break;
+                }
+                const int4 pl = chunk_payload[base + e];
+                KgHitLite h = {(int)(g - x0), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
+                f.hit(p, h, emit);
+            }
+            if (done) break;
+            t++;
+            if (((uint64_t)t << TILE_SHIFT) >= x1) break;
+            if (t < ntiles) {
+                const uint32_t o = tile_out[t];
+                cnt = tile_out[t + 1] - o;
+                base = tile_base[t];
+                e = 0;
+            }
         }
         f.end_container(p, emit);
         call_cnt[v] = (uint32_t)f.ncalls;
     }
+    if (s == nseq - 1) lo[nseq * per_seq] = tile_out[ntiles];
     kg_otu o;
     o.n = f.otu_c.n;
 #pragma unroll
@@ -367,7 +428,8 @@ __global__ void k_emit_hits(const uint64_t* __restrict__ voff, uint64_t nv, int 
 }
 
 struct RunScratch { // grow-only device scratch kept per context (so repeated runs do not allocate)
-    DevBuf tile_base, tile_cnt, tile_out, chunk, hit_pos, hit_payload, lo, sparse, call_cnt, call_off, ctr;
+    DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, hit_pos, hit_payload, lo, sparse, call_cnt, call_off, ctr;
+    uint64_t hit_cap_seen = 0; // hits of the largest run so far (+ slack): sizes the next run's buffers
 };
 RunScratch& scratch_of(kg_context* ctx) {
     if (!ctx->scratch) ctx->scratch = new RunScratch();
@@ -480,7 +542,9 @@ extern "C" int kg_init(int device, kg_context** out) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) CU(cudaEventCreate(&ev));
-    CU(cudaMallocHost(&ctx->h_counters, KG_CTR_COUNT * sizeof(uint64_t)));
+    CU(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
+    CU(cudaMallocHost(&ctx->h_counters, (KG_CTR_COUNT + 1) * sizeof(uint64_t)));
+    memset(ctx->h_counters, 0, (KG_CTR_COUNT + 1) * sizeof(uint64_t));
     *out = ctx;
     return KG_OK;
 }
@@ -490,7 +554,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     RunScratch& sc = scratch_of(ctx);
-    for (DevBuf* b : {&sc.tile_base, &sc.tile_cnt, &sc.tile_out, &sc.chunk, &sc.hit_pos, &sc.hit_payload, &sc.lo, &sc.sparse,
+    for (DevBuf* b : {&sc.tile_base, &sc.tile_cnt, &sc.tile_out, &sc.chunk_pos, &sc.chunk_payload, &sc.hit_pos, &sc.hit_payload, &sc.lo, &sc.sparse,
                       &sc.call_cnt, &sc.call_off, &sc.ctr})
         b->release();
     delete static_cast<RunScratch*>(ctx->scratch);
@@ -628,6 +692,11 @@ int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches) {
 // ---------------------------------------------------------------------------------------------------------------
 // the device pipeline
 // ---------------------------------------------------------------------------------------------------------------
+static uint32_t probe_flags() { // experiment switches: bit 0 = no evict_first on bucket lines, bit 1 = unhinted filter loads
+    const char* e = getenv("KG_PROBE_FLAGS");
+    return e ? (uint32_t)atoi(e) : 0u;
+}
+
 static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result* r,
                         uint64_t hit_cap_hint) {
     cudaStream_t st = ctx->stream;
@@ -648,88 +717,89 @@ static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, con
     KG_TRY(sc.tile_base.ensure(((size_t)ntiles + 1) * 4));
     KG_TRY(sc.tile_cnt.ensure(((size_t)ntiles + 1) * 4));
     KG_TRY(sc.tile_out.ensure(((size_t)ntiles + 1) * 4));
-    KG_TRY(sc.lo.ensure((nv + 1) * 4));
+    KG_TRY(sc.lo.ensure((nv + 2) * 4));
     KG_TRY(sc.call_cnt.ensure((nv + 1) * 4));
     KG_TRY(sc.call_off.ensure((nv + 1) * 4));
 
+    // One pass, one synchronisation at the end.  The hit buffers are sized from a guess (half the positions, or what an
+    // earlier run needed); if a tile could not claim its chunk the whole pass is repeated once with the exact size.
     uint64_t hit_cap = hit_cap_hint ? hit_cap_hint : std::max<uint64_t>(vtotal / 2, 1u << 16);
-    if (hit_cap > vtotal) hit_cap = vtotal;
+    if (hit_cap > vtotal) hit_cap = std::max<uint64_t>(vtotal, 1);
+    const KgFsmParams fp = {prm->min_hits, prm->max_gap, prm->order_constraint, (float)prm->min_weighted_hits};
+    KG_TRY(pool_take_dev(ctx, std::max<uint64_t>(b->n, 1) * sizeof(kg_otu), &r->d_otus));
     uint64_t nhits = 0, nkmers = 0;
     for (int attempt = 0;; attempt++) {
-        KG_TRY(sc.chunk.ensure(std::max<uint64_t>(hit_cap, 1) * sizeof(uint2)));
+        const uint64_t max_calls = hit_cap / (uint64_t)prm->min_hits + 1;
+        KG_TRY(sc.chunk_pos.ensure(hit_cap * 4));
+        KG_TRY(sc.chunk_payload.ensure(hit_cap * sizeof(int4)));
+        KG_TRY(sc.sparse.ensure(max_calls * sizeof(KgDevCall)));
+        if (r->d_calls.cap < max_calls * sizeof(kg_call)) {
+            pool_give_dev(ctx, &r->d_calls);
+            KG_TRY(pool_take_dev(ctx, max_calls * sizeof(kg_call), &r->d_calls));
+        }
         CU(cudaMemsetAsync(d_ctr, 0, KG_CTR_COUNT * 8, st));
         CU(cudaMemsetAsync(sc.tile_cnt.p, 0, ((size_t)ntiles + 1) * 4, st));
         cudaEventRecord(ctx->ev[7], st);
         if (ntiles) {
-            k_probe<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sc.chunk.as<uint2>(),
-                                                  (uint32_t)hit_cap, sc.tile_base.as<uint32_t>(), sc.tile_cnt.as<uint32_t>(), d_ctr);
+            k_probe<<<ntiles, PROBE_BLK, PROBE_SMEM, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sc.chunk_pos.as<uint32_t>(),
+                                                  sc.chunk_payload.as<int4>(), (uint32_t)hit_cap, sc.tile_base.as<uint32_t>(),
+                                                  sc.tile_cnt.as<uint32_t>(), d_ctr, probe_flags());
             launches++;
         }
         cudaEventRecord(ctx->ev[8], st);
         KG_TRY(exclusive_sum_u32(ctx, sc.tile_cnt.as<uint32_t>(), sc.tile_out.as<uint32_t>(), (size_t)ntiles + 1, st));
         launches++;
         CU(cudaMemcpyAsync(ctx->h_counters, d_ctr, KG_CTR_COUNT * 8, cudaMemcpyDeviceToHost, st));
+        if (b->n) {
+            k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sc.tile_base.as<uint32_t>(),
+                                                        sc.tile_out.as<uint32_t>(), ntiles, sc.chunk_pos.as<uint32_t>(),
+                                                        sc.chunk_payload.as<int4>(), fp, sc.sparse.as<KgDevCall>(),
+                                                        sc.lo.as<uint32_t>(), sc.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+            launches++;
+        }
+        CU(cudaMemsetAsync(sc.call_cnt.as<uint32_t>() + nv, 0, 4, st));
+        KG_TRY(exclusive_sum_u32(ctx, sc.call_cnt.as<uint32_t>(), sc.call_off.as<uint32_t>(), nv + 1, st));
+        launches++;
+        if (nv) {
+            k_compact_calls<<<blocks_for(nv, 256), 256, 0, st>>>(sc.sparse.as<KgDevCall>(), sc.lo.as<uint32_t>(),
+                                                                sc.call_off.as<uint32_t>(), nv, per_seq, prm->min_hits,
+                                                                r->d_calls.as<kg_call>());
+            launches++;
+        }
+        CU(cudaMemcpyAsync(&ctx->h_counters[KG_CTR_COUNT], sc.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(ctx->ev[9], st);
         CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
         nhits = ctx->h_counters[KG_CTR_HITS];
         nkmers = ctx->h_counters[KG_CTR_KMERS];
         if (!ctx->h_counters[KG_CTR_OVERFLOW]) break;
         if (attempt) KG_FAIL(KG_ECUDA, "hit buffer overflow persisted after resizing to %llu", (unsigned long long)hit_cap);
         hit_cap = nhits; // exact
     }
+    sc.hit_cap_seen = std::max<uint64_t>(sc.hit_cap_seen, nhits + nhits / 16 + 1024);
     if (nhits > 0xFFFFFFF0ull) KG_FAIL(KG_ERANGE, "%llu hits in one batch", (unsigned long long)nhits);
-
-    KG_TRY(sc.hit_pos.ensure(std::max<uint64_t>(nhits, 1) * 4));
-    KG_TRY(sc.hit_payload.ensure(std::max<uint64_t>(nhits, 1) * sizeof(int4)));
-    if (ntiles && nhits) {
-        k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sc.chunk.as<uint2>(), sc.tile_base.as<uint32_t>(),
-                                                                      sc.tile_out.as<uint32_t>(), ntiles, table->d_payload,
-                                                                      sc.hit_pos.as<uint32_t>(), sc.hit_payload.as<int4>());
-        launches++;
-    }
-    k_ranges<<<blocks_for(nv + 1, 256), 256, 0, st>>>(b->voffsets(), nv, sc.tile_out.as<uint32_t>(), ntiles,
-                                                     sc.hit_pos.as<uint32_t>(), sc.lo.as<uint32_t>());
-    launches++;
-
-    const uint64_t max_calls = nhits / (uint64_t)prm->min_hits + 1;
-    KG_TRY(sc.sparse.ensure(max_calls * sizeof(KgDevCall)));
-    KG_TRY(pool_take_dev(ctx, std::max<uint64_t>(b->n, 1) * sizeof(kg_otu), &r->d_otus));
-    KG_TRY(pool_take_dev(ctx, max_calls * sizeof(kg_call), &r->d_calls));
-    KgFsmParams fp = {prm->min_hits, prm->max_gap, prm->order_constraint, (float)prm->min_weighted_hits};
-    if (b->n) {
-        k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sc.lo.as<uint32_t>(), sc.hit_pos.as<uint32_t>(),
-                                                    sc.hit_payload.as<int4>(), fp, sc.sparse.as<KgDevCall>(),
-                                                    sc.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>());
-        launches++;
-    }
-    CU(cudaMemsetAsync(sc.call_cnt.as<uint32_t>() + nv, 0, 4, st));
-    KG_TRY(exclusive_sum_u32(ctx, sc.call_cnt.as<uint32_t>(), sc.call_off.as<uint32_t>(), nv + 1, st));
-    launches++;
-    if (nv) {
-        k_compact_calls<<<blocks_for(nv, 256), 256, 0, st>>>(sc.sparse.as<KgDevCall>(), sc.lo.as<uint32_t>(),
-                                                            sc.call_off.as<uint32_t>(), nv, per_seq, prm->min_hits,
-                                                            r->d_calls.as<kg_call>());
-        launches++;
-    }
-    if (prm->emit_hits && nhits) {
-        KG_TRY(pool_take_dev(ctx, nhits * sizeof(kg_hit), &r->d_hits));
-        k_emit_hits<<<blocks_for(nhits, 256), 256, 0, st>>>(b->voffsets(), nv, per_seq, sc.hit_pos.as<uint32_t>(),
-                                                           sc.hit_payload.as<int4>(), (uint32_t)nhits, r->d_hits.as<kg_hit>());
-        launches++;
-    }
-    uint32_t ncalls32 = 0;
-    CU(cudaMemcpyAsync(&ctx->h_counters[KG_CTR_CALLS], sc.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
-    cudaEventRecord(ctx->ev[9], st);
-    CU(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&r->stats.ms_prepare, ctx->ev[6], ctx->ev[7]);
     cudaEventElapsedTime(&r->stats.ms_probe, ctx->ev[7], ctx->ev[8]);
     cudaEventElapsedTime(&r->stats.ms_group, ctx->ev[8], ctx->ev[9]);
-    CU(cudaGetLastError());
-    ncalls32 = *(uint32_t*)&ctx->h_counters[KG_CTR_CALLS];
+
+    if (prm->emit_hits && nhits) { // "-d": position-ordered HIT records
+        KG_TRY(sc.hit_pos.ensure(nhits * 4));
+        KG_TRY(sc.hit_payload.ensure(nhits * sizeof(int4)));
+        KG_TRY(pool_take_dev(ctx, nhits * sizeof(kg_hit), &r->d_hits));
+        k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sc.chunk_pos.as<uint32_t>(), sc.chunk_payload.as<int4>(),
+                                                                      sc.tile_base.as<uint32_t>(), sc.tile_out.as<uint32_t>(), ntiles,
+                                                                      sc.hit_pos.as<uint32_t>(), sc.hit_payload.as<int4>());
+        k_emit_hits<<<blocks_for(nhits, 256), 256, 0, st>>>(b->voffsets(), nv, per_seq, sc.hit_pos.as<uint32_t>(),
+                                                           sc.hit_payload.as<int4>(), (uint32_t)nhits, r->d_hits.as<kg_hit>());
+        launches += 2;
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+    }
     r->stats.num_sequences = b->n;
     r->stats.num_positions = vtotal;
     r->stats.num_kmers = nkmers;
     r->stats.num_hits = nhits;
-    r->stats.num_calls = ncalls32;
+    r->stats.num_calls = *(uint32_t*)&ctx->h_counters[KG_CTR_COUNT];
     r->stats.num_launches = launches;
     return KG_OK;
 }
@@ -750,7 +820,7 @@ extern "C" int kg_batch_run(kg_context* ctx, const kg_table* table, kg_batch* ba
     kg_result* r = new kg_result();
     r->ctx = ctx;
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    int rc = run_pipeline(ctx, table, batch, params, r, 0);
+    int rc = run_pipeline(ctx, table, batch, params, r, scratch_of(ctx).hit_cap_seen);
     if (rc != KG_OK) {
         kg_result_free(r);
         return rc;

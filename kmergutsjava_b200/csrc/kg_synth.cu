@@ -202,7 +202,7 @@ __global__ void k_random_sectors(const uint4* __restrict__ buf, uint64_t n_secto
         for (int k = 0; k < U; k++) {
             uint64_t h = smix64(tid * 0x100000001B3ull + it + k);
             uint32_t idx = (uint32_t)(((h >> 32) * n_sectors) >> 32);
-            b[k] = kg_load_bucket(buf, idx);
+            b[k] = kg_load_sector(buf + 2ull * idx);
         }
 #pragma unroll
         for (int k = 0; k < U; k++) acc ^= b[k].w[0] ^ b[k].w[3] ^ b[k].w[7];
@@ -451,5 +451,5 @@ extern "C" int kg_probe_roofline(kg_context* ctx, uint64_t bytes, uint64_t n_loa
 extern "C" int kg_probe_roofline_table(kg_context* ctx, const kg_table* table, uint64_t n_loads, int tpb, int inflight, double* out) {
     if (!ctx || !table || !out) KG_FAIL(KG_EINVAL, "kg_probe_roofline_table: null argument");
     CU(cudaSetDevice(ctx->device));
-    return roofline_run(ctx, table->d_buckets, (uint64_t)table->num_buckets + KG_TAIL_BUCKETS, n_loads, tpb, inflight, out);
+    return roofline_run(ctx, table->d_lines, ((uint64_t)table->num_buckets + KG_TAIL_BUCKETS) * 4, n_loads, tpb, inflight, out);
 }

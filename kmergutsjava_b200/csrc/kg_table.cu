@@ -182,20 +182,22 @@ __global__ void k_slot_bias(const uint64_t* __restrict__ comp, size_t n, long lo
     t[i] = (long long)(comp[i] >> 35) * KG_BUCKET_KEYS - (long long)i;
 }
 
-__global__ void k_init_buckets(uint4* __restrict__ buckets, size_t nbuckets_total) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nbuckets_total) return;
-    buckets[2 * i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    buckets[2 * i + 1] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, KG_W7_EMPTY);
+__global__ void k_init_buckets(uint4* __restrict__ lines, size_t nbuckets_total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // one thread per uint4 of the table
+    if (i >= nbuckets_total * KG_LINE_UINT4) return;
+    const uint32_t q = (uint32_t)(i % KG_LINE_UINT4);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);                                       // payload sectors
+    if (q == 0) v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); // keys 0..3
+    if (q == 1) v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, KG_W6_EMPTY, 0u);          // keys 4..5, high bits + flag, unused
+    lines[i] = v;
 }
 
 // Keys sorted by home bucket take the first free slot at or after their bucket's first slot:
-//   slot_r = max(slot_{r-1} + 1, 7*home_r)  <=>  slot_r = r + max_{q<=r}(7*home_q - q)     (an inclusive max-scan)
+//   slot_r = max(slot_{r-1} + 1, 6*home_r)  <=>  slot_r = r + max_{q<=r}(6*home_q - q)     (an inclusive max-scan)
 // Bucket b gets the overflow flag iff the key in the first slot of bucket b+1 has its home at or before b.
 __global__ void k_scatter(const uint64_t* __restrict__ comp, const uint32_t* __restrict__ idx,
                           const long long* __restrict__ tmax, size_t n, const int4* __restrict__ payload_in,
-                          uint32_t* __restrict__ words, int4* __restrict__ payload_out, uint64_t total_slots,
-                          unsigned long long* __restrict__ err) {
+                          uint4* __restrict__ lines, uint64_t total_slots, unsigned long long* __restrict__ err) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     uint64_t c = comp[r];
@@ -208,11 +210,12 @@ __global__ void k_scatter(const uint64_t* __restrict__ comp, const uint32_t* __r
     }
     uint64_t b = slot / KG_BUCKET_KEYS;
     uint32_t lane = (uint32_t)(slot - b * KG_BUCKET_KEYS);
-    words[b * 8 + lane] = (uint32_t)key;
+    uint32_t* words = reinterpret_cast<uint32_t*>(lines + b * KG_LINE_UINT4); // the key sector
+    words[lane] = (uint32_t)key;
     uint32_t hi = (uint32_t)(key >> 32);
-    atomicAnd(&words[b * 8 + 7], ~(7u << (3 * lane)) | (hi << (3 * lane)));
-    if (lane == 0 && home < b) atomicOr(&words[(b - 1) * 8 + 7], KG_W7_FLAG);
-    payload_out[slot] = payload_in[idx[r]];
+    atomicAnd(&words[6], ~(7u << (3 * lane)) | (hi << (3 * lane)));
+    if (lane == 0 && home < b) atomicOr(reinterpret_cast<uint32_t*>(lines + (b - 1) * KG_LINE_UINT4) + 6, KG_W6_FLAG);
+    reinterpret_cast<int4*>(lines + b * KG_LINE_UINT4 + 2)[lane] = payload_in[idx[r]];
 }
 
 __global__ void k_filter_build(const uint64_t* __restrict__ comp, size_t n, unsigned long long* __restrict__ filter,
@@ -225,7 +228,7 @@ __global__ void k_filter_build(const uint64_t* __restrict__ comp, size_t n, unsi
 
 __global__ void k_count_flagged(const uint32_t* __restrict__ words, size_t nbuckets_total, unsigned long long* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool f = i < nbuckets_total && (words[i * 8 + 7] & KG_W7_FLAG);
+    bool f = i < nbuckets_total && (words[i * (KG_LINE_UINT4 * 4) + 6] & KG_W6_FLAG);
     unsigned m = __ballot_sync(0xFFFFFFFFu, f);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
@@ -238,7 +241,7 @@ __global__ void k_verify(KgTableView t, const uint64_t* __restrict__ keys, const
     uint32_t s = kg_lookup(t, keys[i]);
     bool ok = s != 0xFFFFFFFFu;
     if (ok) {
-        int4 a = t.payload[s], b = payload[i];
+        int4 a = kg_load_payload(t.lines, s), b = payload[i];
         ok = a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
     }
     if (!ok) atomicAdd(bad, 1ull);
@@ -250,8 +253,7 @@ inline unsigned blocks_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 
 
 KgTableView kg_table::view() const {
     KgTableView v;
-    v.buckets = d_buckets;
-    v.payload = d_payload;
+    v.lines = d_lines;
     v.num_buckets = num_buckets;
     v.filter = d_filter;
     v.filter_words = filter_words;
@@ -271,11 +273,9 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
     const uint64_t total_slots = (uint64_t)nb_total * KG_BUCKET_KEYS;
     if (total_slots >= (1ull << 32)) KG_FAIL(KG_ERANGE, "table: %llu slots exceed the 32-bit slot index", (unsigned long long)total_slots);
 
-    CU(cudaMalloc(&t->d_buckets, nb_total * 32));
-    CU(cudaMalloc(&t->d_payload, total_slots * sizeof(int4)));
+    CU(cudaMalloc(&t->d_lines, nb_total * 128));
     t->num_buckets = nb;
-    k_init_buckets<<<blocks_for(nb_total, 256), 256, 0, st>>>(t->d_buckets, nb_total);
-    CU(cudaMemsetAsync(t->d_payload, 0, total_slots * sizeof(int4), st));
+    k_init_buckets<<<blocks_for(nb_total * KG_LINE_UINT4, 256), 256, 0, st>>>(t->d_lines, nb_total);
 
     unsigned long long* d_ctr = nullptr; // [0] scatter overflow, [1] flagged buckets, [2] verify failures
     CU(cudaMalloc(&d_ctr, 4 * sizeof(unsigned long long)));
@@ -329,9 +329,8 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
         CU(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, tb, tb, MaxI64(), n_unique, st));
         KG_TRY(ctx->scan_tmp.ensure(scan_bytes));
         CU(cub::DeviceScan::InclusiveScan(ctx->scan_tmp.p, scan_bytes, tb, tb, MaxI64(), n_unique, st));
-        k_scatter<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, idx, tb, n_unique, d_payload, (uint32_t*)t->d_buckets,
-                                                            t->d_payload, total_slots, d_ctr);
-        k_count_flagged<<<blocks_for(nb_total, 256), 256, 0, st>>>((const uint32_t*)t->d_buckets, nb_total, d_ctr + 1);
+        k_scatter<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, idx, tb, n_unique, d_payload, t->d_lines, total_slots, d_ctr);
+        k_count_flagged<<<blocks_for(nb_total, 256), 256, 0, st>>>((const uint32_t*)t->d_lines, nb_total, d_ctr + 1);
         if (filter_bits_per_key() > 0) { // L2-resident prefilter over the same keys
             uint64_t bytes = (uint64_t)((double)n_unique * filter_bits_per_key() / 8.0);
             if (bytes > KG_FILTER_MAX_BYTES) bytes = KG_FILTER_MAX_BYTES;
@@ -340,6 +339,24 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
             CU(cudaMalloc(&t->d_filter, (size_t)t->filter_words * 8));
             CU(cudaMemsetAsync(t->d_filter, 0, (size_t)t->filter_words * 8, st));
             k_filter_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter, t->filter_words);
+            // Pin the filter in L2: a persisting carve-out (<= 79 MiB on B200) plus an access-policy window on the
+            // context's stream, so that the 128-byte lines streaming through for the probes cannot push it out.
+            // (One table per context benefits; a later table takes the window over.)
+            if (!getenv("KG_NO_L2_PERSIST")) {
+                cudaDeviceProp prop;
+                if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                    const size_t fbytes = (size_t)t->filter_words * 8;
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize));
+                    cudaStreamAttrValue av = {};
+                    av.accessPolicyWindow.base_ptr = t->d_filter;
+                    av.accessPolicyWindow.num_bytes = std::min<size_t>(fbytes, (size_t)prop.accessPolicyMaxWindowSize);
+                    av.accessPolicyWindow.hitRatio = 1.0f;
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+                    cudaGetLastError();
+                }
+            }
         }
         // Every stored key must be found again.  With repeated keys only the surviving copy's payload can match, so
         // the payload comparison is skipped for inputs that had duplicates.
@@ -367,7 +384,7 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
     t->info.num_signatures = (int64_t)n_unique;
     t->info.num_buckets = (int64_t)nb_total;
     t->info.flagged_buckets = (int64_t)h_ctr[1];
-    t->info.device_bytes = (int64_t)(nb_total * 32 + total_slots * sizeof(int4) + (size_t)t->filter_words * 8);
+    t->info.device_bytes = (int64_t)(nb_total * 128 + (size_t)t->filter_words * 8);
     return KG_OK;
 }
 
@@ -378,7 +395,7 @@ static double filter_bits_per_key() { // KG_FILTER_BITS=0 disables the prefilter
 static double table_load_factor() {
     const char* e = getenv("KG_TABLE_LOAD");
     double v = e ? atof(e) : 0.0;
-    return (v > 0.05 && v < 0.95) ? v : 0.60;
+    return (v > 0.05 && v < 0.95) ? v : 0.50; // 3 keys per 6-key bucket on average: ~3 % of buckets overflow
 }
 
 static int table_from_parser(kg_context* ctx, ImageParser& ps, kg_table** out) {
@@ -497,8 +514,7 @@ extern "C" int kg_table_get_info(const kg_table* table, kg_table_info* info) {
 
 extern "C" void kg_table_free(kg_table* t) {
     if (!t) return;
-    if (t->d_buckets) cudaFree(t->d_buckets);
-    if (t->d_payload) cudaFree(t->d_payload);
+    if (t->d_lines) cudaFree(t->d_lines);
     if (t->d_filter) cudaFree(t->d_filter);
     delete t;
 }
