@@ -1,0 +1,122 @@
+"""configs[0]: the reference's own CPU-runnable case.  The repo ships no kmer table, so the table is
+derived from the E. coli protein FASTA the reference ships as test data (tools/kg_synth.build_c0_fixture); then the
+reference's two fixtures are run in protein mode (.faa.gz) and 6-frame mode (.fna.gz) under the flag sets of
+SURVEY.md section 8(d), through the command lines, and the text reports are compared byte for byte."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.parity import assert_same
+from tools import kg_synth as synth
+
+pytestmark = pytest.mark.gpu
+DATA = os.path.join(os.path.dirname(__file__), "data")
+FAA = os.path.join(DATA, "Ecoli_K12_W3110.faa.gz")
+FNA = os.path.join(DATA, "Ecoli_K12_W3110.fna.gz")
+
+
+@pytest.fixture(scope="module")
+def c0(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("c0") / "KmerData")
+    info = synth.build_c0_fixture(FAA, d)
+    assert info["num_signatures"] > 300_000
+    return d
+
+
+@pytest.fixture(scope="module")
+def kg():
+    import kmergutsjava_b200 as kg
+    return kg
+
+
+FLAGSETS = [[], ["-d"], ["-O"], ["-m", "3", "-g", "50", "-M", "2"]]
+
+
+def _strip(text, debug):
+    """Drop what is wall-clock or deliberately not reproduced: timer lines everywhere; in -d output also the oracle's
+    list dumps (after-hit / after-call) and its 'Kmers found' counter (divergences)."""
+    out = []
+    for line in text.splitlines():
+        if line.startswith(("Temp. directory:", "Preparation time:", "Lookup time:", "Grouping time:", "Processed:", "Table load time:")):
+            continue
+        if debug and line.startswith(("after-hit:", "after-call:", "Kmers found:")):
+            continue
+        out.append(line)
+    return out
+
+
+@pytest.mark.parametrize("flags", FLAGSETS, ids=["default", "debug", "order", "m3g50M2"])
+@pytest.mark.parametrize("mode", ["aa", "dna"])
+def test_c0_reports_identical(kg, oracle, c0, tmp_path, mode, flags):
+    query = FAA if mode == "aa" else FNA
+    small = "-d" in flags   # the reference's -d output dumps the whole open run after every hit (quadratic): use a slice
+    if small:
+        ids, descr, seqs = synth.read_fasta_simple(query)
+        query = str(tmp_path / ("q.faa" if mode == "aa" else "q.fna"))
+        if mode == "aa":
+            synth.write_fasta(query, ids[:400], seqs[:400])
+        else:
+            synth.write_fasta(query, ["slice1", "slice2"], [seqs[0][100000:160000], seqs[0][2000000:2030001]])
+    base = (["-a"] if mode == "aa" else []) + flags + ["-D", c0, "-q", query]
+    o_out, g_out = str(tmp_path / "oracle.txt"), str(tmp_path / "gpu.txt")
+    oracle.run_cli(base + ["-o", o_out])
+    r = subprocess.run([kg.CLI_PATH, *base, "-o", g_out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a = _strip(open(o_out).read(), "-d" in flags)
+    b = _strip(open(g_out).read(), "-d" in flags)
+    assert len(a) == len(b)
+    ncall = sum(1 for x in a if x.startswith("CALL\t"))
+    assert ncall > ((5000 if mode == "aa" else 3000) if not small else 30), ncall
+    if small:
+        assert sum(1 for x in a if x.startswith("HIT\t")) > 1000
+    if a != b:
+        bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:5]
+        raise AssertionError(f"{len(bad)}+ differing lines, first: {bad}")
+
+
+def test_c0_library_level(kg, oracle, c0):
+    ctx = kg.Context(0)
+    table = ctx.load_table(c0)
+    otab = oracle.Table(path=os.path.join(c0, "kmer.table.mem_map"))
+    ti = table.info
+    assert ti.num_unreachable == 0 and ti.tail_run == 0 and ti.num_slots == otab.num_sigs
+    fa = kg.Fasta(FAA)
+    assert fa.n == 13645
+    res = ctx.run(table, kg.MODE_AA, fa.bytes, fa.offsets, kg.default_params(emit_hits=1))
+    ref = oracle.run(otab, oracle.make_params(aa=True), fa.bytes, fa.offsets, oracle.STREAM_JOIN)
+    assert ref.num_kmers == 4037833          # windows the reference enumerates from this file
+    assert_same(res, ref, what="C0 aa")
+    res.free()
+    fn = kg.Fasta(FNA)
+    res = ctx.run(table, kg.MODE_DNA, fn.bytes, fn.offsets, kg.default_params(emit_hits=1))
+    ref = oracle.run(otab, oracle.make_params(aa=False), fn.bytes, fn.offsets, oracle.STREAM_JOIN)
+    assert_same(res, ref, what="C0 dna")
+    assert len(ref.calls) > 3000 and set(ref.calls["sf"]) == set(range(6))
+    res.free()
+    table.free()
+    ctx.close()
+
+
+def test_c0_gz_table_and_duplicate_ids(kg, oracle, c0, tmp_path):
+    """kmer.table.mem_map.gz wins over the plain file (KGJ:749-753); repeated FASTA ids collapse as in the reference's
+    LinkedHashMap bookkeeping (KGJ:772, 805-809): first position, last length, last record's hits."""
+    import gzip
+    import shutil
+    d = tmp_path / "KmerDataGz"
+    d.mkdir()
+    with open(os.path.join(c0, "kmer.table.mem_map"), "rb") as f, gzip.open(d / "kmer.table.mem_map.gz", "wb", compresslevel=1) as g:
+        shutil.copyfileobj(f, g)
+    shutil.copy(os.path.join(c0, "function.index"), d / "function.index")
+    ids, descr, seqs = synth.read_fasta_simple(FAA)
+    pick = [0, 1, 2, 3, 1, 4, 0]
+    q = str(tmp_path / "dup.faa")
+    synth.write_fasta(q, [ids[i] if k != 4 else ids[1] for k, i in enumerate(pick)], [seqs[i] if k != 4 else seqs[5] for k, i in enumerate(pick)])
+    o_out, g_out = str(tmp_path / "o.txt"), str(tmp_path / "g.txt")
+    oracle.run_cli(["-a", "-D", str(d), "-q", q, "-o", o_out])
+    r = subprocess.run([kg.CLI_PATH, "-a", "-D", str(d), "-q", q, "-o", g_out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = _strip(open(o_out).read(), False), _strip(open(g_out).read(), False)
+    assert a == b
+    assert sum(1 for x in a if x.startswith("PROTEIN-ID")) == 5
