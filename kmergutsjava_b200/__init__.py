@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkmerguts_b200.so")
+LIB_PATH = os.environ.get("KG_LIB") or os.path.join(HERE, "libkmerguts_b200.so")  # KG_LIB: kernel-variant experiments
 CLI_PATH = os.path.join(HERE, "bin", "kmer_guts_b200")
 
 MODE_DNA, MODE_AA = 0, 1

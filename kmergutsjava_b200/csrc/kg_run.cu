@@ -15,10 +15,13 @@
 
 namespace {
 
-constexpr int PT = 16;            // positions per thread
-constexpr int PROBE_BLK = 256;    // threads per block
+constexpr int PT = 8;             // positions per thread
+#ifndef KG_PROBE_BLK
+#define KG_PROBE_BLK 128
+#endif
+constexpr int PROBE_BLK = KG_PROBE_BLK; // threads per block
 constexpr int TILE = PT * PROBE_BLK;
-constexpr int TILE_SHIFT = 12;
+constexpr int TILE_SHIFT = TILE == 4096 ? 12 : TILE == 2048 ? 11 : TILE == 1024 ? 10 : 9;
 static_assert(TILE == (1 << TILE_SHIFT), "tile size");
 
 inline unsigned blocks_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -95,11 +98,11 @@ __global__ void k_translate(const uint8_t* __restrict__ seq, const uint64_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// encode + probe.  A block owns a 4096-position tile of the residue stream and works in four phases:
-//   A  encode   one thread owns PT = 16 consecutive positions: 24 residue bytes (16 + 8 halo) arrive as one 16-byte and
-//               one 8-byte coalesced load, codes come from a 256-byte shared-memory LUT, 4-mer partial products give
+// encode + probe.  A block (128 threads, 6 resident per SM) owns a 1024-position tile of the residue stream and works in four phases:
+//   A  encode   one thread owns PT = 8 consecutive positions: 16 residue bytes (8 + 7 halo + 1) arrive as two coalesced
+//               8-byte loads, codes come from a 256-byte shared-memory LUT, 4-mer partial products give
 //               every 8-mer in one 64-bit IMAD (first residue most significant, KGJ:274-282)
-//      filter   every valid window tests its two bits in the L2-resident Bloom prefilter: 16 independent 8-byte loads
+//      filter   every valid window tests its two bits in the L2-resident Bloom prefilter: 8 independent 8-byte loads
 //               in flight per thread; ~70 % of the windows end here without touching DRAM
 //   B  compact  the surviving (key, position) pairs are packed into a shared-memory queue (block-wide scan)
 //   C  probe    the queue is probed DENSELY: every lane busy, PROBE_U independent 256-bit sector loads in flight per
@@ -109,7 +112,13 @@ __global__ void k_translate(const uint8_t* __restrict__ seq, const uint64_t* __r
 //               an output chunk, (position, payload) records written by the owning threads.
 // The run FSM reads the chunks through (tile_base, tile_cnt); no global sort or re-ordering pass is needed.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PROBE_U = 4;
+#ifndef KG_PROBE_OCC
+#define KG_PROBE_OCC 6
+#endif
+#ifndef KG_PROBE_U
+#define KG_PROBE_U 4
+#endif
+constexpr int PROBE_U = KG_PROBE_U;
 constexpr size_t PROBE_SMEM_PSTAGE = (size_t)TILE * sizeof(int4);                 // payload parked per position
 constexpr size_t PROBE_SMEM_QUEUE = (size_t)TILE * sizeof(unsigned long long);    // survivor queue
 constexpr size_t PROBE_SMEM = PROBE_SMEM_PSTAGE + PROBE_SMEM_QUEUE;               // 96 KiB: needs the opt-in limit
@@ -136,7 +145,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t mine, uint32_t* war
     return before + incl - mine;
 }
 
-__global__ __launch_bounds__(PROBE_BLK, 2) void k_probe(const uint8_t* __restrict__ stream, uint32_t vtotal, KgTableView tab,
+__global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe(const uint8_t* __restrict__ stream, uint32_t vtotal, KgTableView tab,
                                                         uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload,
                                                         uint32_t hit_cap, uint32_t* __restrict__ tile_base,
                                                         uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr,
@@ -150,7 +159,7 @@ __global__ __launch_bounds__(PROBE_BLK, 2) void k_probe(const uint8_t* __restric
     __shared__ uint32_t s_base;
 
     const int tid = threadIdx.x;
-    lut[tid] = (tid >= 'A' && tid <= 'Z') ? c_aa_code[tid - 'A'] : 20;
+    for (int i = tid; i < 256; i += PROBE_BLK) lut[i] = (i >= 'A' && i <= 'Z') ? c_aa_code[i - 'A'] : 20;
     if (tid < TILE / 32) hitbits[tid] = 0;
     __syncthreads();
 
@@ -160,22 +169,27 @@ __global__ __launch_bounds__(PROBE_BLK, 2) void k_probe(const uint8_t* __restric
 
     // ---- A: encode + prefilter ----
     uint32_t pass = 0, nk = 0;
-    uint32_t q[20];
+    constexpr int NB = PT + 8; // residue bytes a thread reads: its PT positions + 7 bytes of halo (+1 unused)
+    uint32_t q[PT + 4];
     if (p0 < vtotal) {
-        const uint4 a = *reinterpret_cast<const uint4*>(stream + p0);
-        const uint2 b = *reinterpret_cast<const uint2*>(stream + p0 + 16);
-        const uint32_t wv[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
-        uint32_t c[24];
+        uint32_t wv[NB / 4];
+#pragma unroll
+        for (int i = 0; i < NB / 8; i++) {
+            const uint2 t = *reinterpret_cast<const uint2*>(stream + p0 + 8 * i);
+            wv[2 * i] = t.x;
+            wv[2 * i + 1] = t.y;
+        }
+        uint32_t c[NB];
         uint32_t bad = 0;
 #pragma unroll
-        for (int i = 0; i < 24; i++) {
+        for (int i = 0; i < NB; i++) {
             c[i] = lut[(wv[i >> 2] >> (8 * (i & 3))) & 0xFFu];
             bad |= (uint32_t)(c[i] >= 20u) << i;
         }
-        const uint32_t left = vtotal - p0; // bytes of this thread's 24 that exist
-        if (left < 24) bad |= ~0u << left;
+        const uint32_t left = vtotal - p0; // bytes of this thread's NB that exist
+        if (left < NB) bad |= ~0u << left;
 #pragma unroll
-        for (int i = 0; i < 20; i++) q[i] = ((c[i] * 20u + c[i + 1]) * 20u + c[i + 2]) * 20u + c[i + 3];
+        for (int i = 0; i < PT + 4; i++) q[i] = ((c[i] * 20u + c[i + 1]) * 20u + c[i + 2]) * 20u + c[i + 3];
         uint32_t valid = 0;
 #pragma unroll
         for (int i = 0; i < PT; i++) valid |= (uint32_t)(((bad >> i) & 0xFFu) == 0u) << i;
@@ -252,7 +266,7 @@ __global__ __launch_bounds__(PROBE_BLK, 2) void k_probe(const uint8_t* __restric
     __syncthreads();
 
     // ---- D: hits out, tile order ----
-    const uint32_t hitmask = (hitbits[tid >> 1] >> ((tid & 1) * 16)) & 0xFFFFu;
+    const uint32_t hitmask = (hitbits[(tid * PT) >> 5] >> ((tid * PT) & 31)) & ((1u << PT) - 1u);
     uint32_t total;
     const uint32_t ho = block_excl_scan(__popc(hitmask), warp_b, &total);
     if (tid == 0) {
