@@ -119,8 +119,10 @@ struct HostBuf { // pinned host memory
 struct kg_context {
     int device = 0;
     cudaStream_t stream = nullptr;      // compute
-    cudaStream_t copy_stream = nullptr; // H2D staging for the pipelined end-to-end call
-    cudaEvent_t ev[12] = {};           // 0-5: run / fetch / upload brackets, 6-9: pipeline stages
+    cudaStream_t copy_stream = nullptr; // H2D of the next slice in the pipelined end-to-end call (kg_run)
+    cudaStream_t d2h_stream = nullptr;  // D2H of the previous slice's records
+    cudaEvent_t ev[12] = {};           // 0-5: run / fetch / upload brackets, 6-9: pipeline stages, 10-11: slice uploaded
+    cudaEvent_t d2h_ev[3] = {};        // kg_run: records of slice s%3 have reached the host
     int sm_count = 0;
     size_t l2_bytes = 0;
     DevBuf scan_tmp;                    // CUB temp storage

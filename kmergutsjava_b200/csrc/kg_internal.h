@@ -35,6 +35,7 @@ struct kg_batch {
     const uint8_t* stream() const { return mode == KG_MODE_AA ? d_seq : vseq.as<uint8_t>(); }
     const uint64_t* voffsets() const { return mode == KG_MODE_AA ? d_off : voff.as<uint64_t>(); }
     bool prepared = false;
+    bool vtotal_known = false; // dna: vtotal already computed on the host (kg_run / kg_batch_upload)
 };
 
 struct kg_result {

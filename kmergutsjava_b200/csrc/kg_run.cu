@@ -8,6 +8,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 
 #include "kg_device.cuh"
 #include "kg_fsm.cuh"
@@ -62,6 +63,12 @@ __global__ void k_patch_aa(uint8_t* __restrict__ seq, const uint64_t* __restrict
     if (s >= n) return;
     uint64_t a = off[s], b = off[s + 1];
     if (b > a) seq[b - 1] = 0;
+}
+
+// offsets of a slice of a larger batch -> offsets relative to the slice
+__global__ void k_rebase(uint64_t* __restrict__ off, uint64_t n1, uint64_t base) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n1) off[i] -= base;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -402,7 +409,7 @@ __global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, 
 
 __global__ void k_compact_calls(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ lo,
                                 const uint32_t* __restrict__ call_off, uint64_t nv, int per_seq, int min_hits,
-                                kg_call* __restrict__ out) {
+                                uint32_t seq_base, kg_call* __restrict__ out) {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     const uint32_t o = call_off[v], c = call_off[v + 1] - o;
@@ -410,7 +417,7 @@ __global__ void k_compact_calls(const KgDevCall* __restrict__ sparse, const uint
     for (uint32_t j = 0; j < c; j++) {
         KgDevCall d = src[j];
         kg_call r;
-        r.seq = (uint32_t)(v / per_seq);
+        r.seq = seq_base + (uint32_t)(v / per_seq);
         r.strand_frame = (int32_t)(v % per_seq);
         r.start = d.start;
         r.end = d.end;
@@ -424,14 +431,14 @@ __global__ void k_compact_calls(const KgDevCall* __restrict__ sparse, const uint
 
 // "-d" HIT records: one thread per hit finds its container by binary search over the virtual offsets
 __global__ void k_emit_hits(const uint64_t* __restrict__ voff, uint64_t nv, int per_seq, const uint32_t* __restrict__ hit_pos,
-                            const int4* __restrict__ hit_payload, uint32_t nhits, kg_hit* __restrict__ out) {
+                            const int4* __restrict__ hit_payload, uint32_t nhits, uint32_t seq_base, kg_hit* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nhits) return;
     const uint64_t g = hit_pos[i];
     const uint64_t v = seq_of(voff, nv, g);
     const int4 pl = hit_payload[i];
     kg_hit h;
-    h.seq = (uint32_t)(v / per_seq);
+    h.seq = seq_base + (uint32_t)(v / per_seq);
     h.strand_frame = (int32_t)(v % per_seq);
     h.pos = (int32_t)(g - voff[v]);
     h.oI = pl.x;
@@ -441,12 +448,28 @@ __global__ void k_emit_hits(const uint64_t* __restrict__ voff, uint64_t nv, int 
     out[i] = h;
 }
 
+struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them let slice s+1 queue up behind slice s
+    DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
+    uint64_t* h_ctr = nullptr; // pinned, KG_CTR_COUNT + 1 (the last slot receives the call total)
+    cudaEvent_t ev[4] = {};    // begin, probe begin, probe end, end
+    uint64_t hit_cap = 0;
+    uint32_t launches = 0;
+};
 struct RunScratch { // grow-only device scratch kept per context (so repeated runs do not allocate)
-    DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, hit_pos, hit_payload, lo, sparse, call_cnt, call_off, ctr;
-    uint64_t hit_cap_seen = 0; // hits of the largest run so far (+ slack): sizes the next run's buffers
+    PipeSlot slot[2];
+    DevBuf hit_pos, hit_payload; // "-d" only
+    uint64_t hit_cap_seen = 0;   // hits of the largest run so far (+ slack): sizes the next run's buffers
+    uint64_t calls_seen = 0;     // calls of the largest kg_run so far: sizes the pinned result buffer
 };
 RunScratch& scratch_of(kg_context* ctx) {
-    if (!ctx->scratch) ctx->scratch = new RunScratch();
+    if (!ctx->scratch) {
+        RunScratch* sc = new RunScratch();
+        for (auto& sl : sc->slot) {
+            cudaMallocHost(&sl.h_ctr, (KG_CTR_COUNT + 1) * sizeof(uint64_t));
+            for (auto& e : sl.ev) cudaEventCreate(&e);
+        }
+        ctx->scratch = sc;
+    }
     return *static_cast<RunScratch*>(ctx->scratch);
 }
 
@@ -555,7 +578,9 @@ extern "C" int kg_init(int device, kg_context** out) {
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) CU(cudaEventCreate(&ev));
+    for (auto& ev : ctx->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
     CU(cudaMallocHost(&ctx->h_counters, (KG_CTR_COUNT + 1) * sizeof(uint64_t)));
     memset(ctx->h_counters, 0, (KG_CTR_COUNT + 1) * sizeof(uint64_t));
@@ -568,17 +593,27 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     RunScratch& sc = scratch_of(ctx);
-    for (DevBuf* b : {&sc.tile_base, &sc.tile_cnt, &sc.tile_out, &sc.chunk_pos, &sc.chunk_payload, &sc.hit_pos, &sc.hit_payload, &sc.lo, &sc.sparse,
-                      &sc.call_cnt, &sc.call_off, &sc.ctr})
-        b->release();
+    for (auto& sl : sc.slot) {
+        for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
+                          &sl.call_off, &sl.ctr})
+            b->release();
+        if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
+        for (auto& e : sl.ev)
+            if (e) cudaEventDestroy(e);
+    }
+    sc.hit_pos.release();
+    sc.hit_payload.release();
     delete static_cast<RunScratch*>(ctx->scratch);
     for (auto& b : ctx->dev_pool) b.release();
     for (auto& h : ctx->host_pool) cudaFreeHost(h.p);
     ctx->scan_tmp.release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->d2h_ev)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     delete ctx;
 }
@@ -661,8 +696,8 @@ extern "C" void kg_batch_free(kg_batch* b) {
         pool_give_dev(b->ctx, &b->seq_buf);
         pool_give_dev(b->ctx, &b->off_buf);
     }
-    b->vseq.release();
-    b->voff.release();
+    pool_give_dev(b->ctx, &b->vseq);
+    pool_give_dev(b->ctx, &b->voff);
     delete b;
 }
 
@@ -680,18 +715,26 @@ int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches) {
         return KG_OK;
     }
     b->nv = 6 * b->n;
+    auto need = [&](DevBuf* buf, size_t bytes) -> int { // pooled: slices of a kg_run come and go
+        if (buf->cap >= bytes) return KG_OK;
+        pool_give_dev(ctx, buf);
+        return pool_take_dev(ctx, bytes, buf);
+    };
     if (!b->prepared) { // the layout depends only on the lengths: computed once per batch
-        KG_TRY(b->voff.ensure((b->nv + 2) * 8 * 2));
+        KG_TRY(need(&b->voff, (b->nv + 2) * 8 * 2));
         uint64_t* vlen = b->voff.as<uint64_t>() + (b->nv + 2);
         k_vlen<<<blocks_for(b->nv + 1, 256), 256, 0, st>>>(b->d_off, b->n, vlen);
         (*launches)++;
         KG_TRY(exclusive_sum_u64(ctx, vlen, b->voff.as<uint64_t>(), b->nv + 1, st));
         (*launches)++;
-        CU(cudaMemcpyAsync(&ctx->h_counters[KG_CTR_VPOS], b->voff.as<uint64_t>() + b->nv, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        b->vtotal = ctx->h_counters[KG_CTR_VPOS];
+        if (!b->vtotal_known) { // sequences adopted from device memory: the total has to come back
+            CU(cudaMemcpyAsync(&ctx->h_counters[KG_CTR_VPOS], b->voff.as<uint64_t>() + b->nv, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            b->vtotal = ctx->h_counters[KG_CTR_VPOS];
+            b->vtotal_known = true;
+        }
         if (b->vtotal > KG_MAX_STREAM) KG_FAIL(KG_ERANGE, "dna batch: %llu translated residues in one batch", (unsigned long long)b->vtotal);
-        KG_TRY(b->vseq.ensure(b->vtotal + 64));
+        KG_TRY(need(&b->vseq, b->vtotal + 64));
         b->prepared = true;
     }
     CU(cudaMemsetAsync(b->vseq.p, 0, b->vtotal + 64, st));
@@ -711,13 +754,15 @@ static uint32_t probe_flags() { // experiment switches: bit 0 = no evict_first o
     return e ? (uint32_t)atoi(e) : 0u;
 }
 
-static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result* r,
-                        uint64_t hit_cap_hint) {
+// Enqueue one whole pass (prepare -> probe -> scan -> FSM -> scan -> compact) on the compute stream; no host
+// synchronisation.  The hit buffers are sized from a guess (half the positions, or what an earlier run needed); if a
+// tile cannot claim its chunk the kernels downstream skip their work and pipe_finish repeats the pass with the exact size.
+static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result* r,
+                        uint64_t hit_cap_hint, uint32_t seq_base) {
     cudaStream_t st = ctx->stream;
-    RunScratch& sc = scratch_of(ctx);
-    uint32_t launches = 0;
-    cudaEventRecord(ctx->ev[6], st);
-    KG_TRY(kg_batch_prepare(b, st, &launches));
+    sl.launches = 0;
+    cudaEventRecord(sl.ev[0], st);
+    KG_TRY(kg_batch_prepare(b, st, &sl.launches));
     const uint64_t nv = b->nv, vtotal = b->vtotal;
     const int per_seq = b->mode == KG_MODE_AA ? 1 : 6;
     const uint32_t ntiles = (uint32_t)((vtotal + TILE - 1) >> TILE_SHIFT);
@@ -726,94 +771,109 @@ static int run_pipeline(kg_context* ctx, const kg_table* table, kg_batch* b, con
     r->mode = b->mode;
     r->params = *prm;
 
-    KG_TRY(sc.ctr.ensure(KG_CTR_COUNT * 8));
-    unsigned long long* d_ctr = sc.ctr.as<unsigned long long>();
-    KG_TRY(sc.tile_base.ensure(((size_t)ntiles + 1) * 4));
-    KG_TRY(sc.tile_cnt.ensure(((size_t)ntiles + 1) * 4));
-    KG_TRY(sc.tile_out.ensure(((size_t)ntiles + 1) * 4));
-    KG_TRY(sc.lo.ensure((nv + 2) * 4));
-    KG_TRY(sc.call_cnt.ensure((nv + 1) * 4));
-    KG_TRY(sc.call_off.ensure((nv + 1) * 4));
-
-    // One pass, one synchronisation at the end.  The hit buffers are sized from a guess (half the positions, or what an
-    // earlier run needed); if a tile could not claim its chunk the whole pass is repeated once with the exact size.
+    KG_TRY(sl.ctr.ensure(KG_CTR_COUNT * 8));
+    unsigned long long* d_ctr = sl.ctr.as<unsigned long long>();
+    KG_TRY(sl.tile_base.ensure(((size_t)ntiles + 1) * 4));
+    KG_TRY(sl.tile_cnt.ensure(((size_t)ntiles + 1) * 4));
+    KG_TRY(sl.tile_out.ensure(((size_t)ntiles + 1) * 4));
+    KG_TRY(sl.lo.ensure((nv + 2) * 4));
+    KG_TRY(sl.call_cnt.ensure((nv + 1) * 4));
+    KG_TRY(sl.call_off.ensure((nv + 1) * 4));
     uint64_t hit_cap = hit_cap_hint ? hit_cap_hint : std::max<uint64_t>(vtotal / 2, 1u << 16);
     if (hit_cap > vtotal) hit_cap = std::max<uint64_t>(vtotal, 1);
-    const KgFsmParams fp = {prm->min_hits, prm->max_gap, prm->order_constraint, (float)prm->min_weighted_hits};
-    KG_TRY(pool_take_dev(ctx, std::max<uint64_t>(b->n, 1) * sizeof(kg_otu), &r->d_otus));
-    uint64_t nhits = 0, nkmers = 0;
-    for (int attempt = 0;; attempt++) {
-        const uint64_t max_calls = hit_cap / (uint64_t)prm->min_hits + 1;
-        KG_TRY(sc.chunk_pos.ensure(hit_cap * 4));
-        KG_TRY(sc.chunk_payload.ensure(hit_cap * sizeof(int4)));
-        KG_TRY(sc.sparse.ensure(max_calls * sizeof(KgDevCall)));
-        if (r->d_calls.cap < max_calls * sizeof(kg_call)) {
-            pool_give_dev(ctx, &r->d_calls);
-            KG_TRY(pool_take_dev(ctx, max_calls * sizeof(kg_call), &r->d_calls));
-        }
-        CU(cudaMemsetAsync(d_ctr, 0, KG_CTR_COUNT * 8, st));
-        CU(cudaMemsetAsync(sc.tile_cnt.p, 0, ((size_t)ntiles + 1) * 4, st));
-        cudaEventRecord(ctx->ev[7], st);
-        if (ntiles) {
-            k_probe<<<ntiles, PROBE_BLK, PROBE_SMEM, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sc.chunk_pos.as<uint32_t>(),
-                                                  sc.chunk_payload.as<int4>(), (uint32_t)hit_cap, sc.tile_base.as<uint32_t>(),
-                                                  sc.tile_cnt.as<uint32_t>(), d_ctr, probe_flags());
-            launches++;
-        }
-        cudaEventRecord(ctx->ev[8], st);
-        KG_TRY(exclusive_sum_u32(ctx, sc.tile_cnt.as<uint32_t>(), sc.tile_out.as<uint32_t>(), (size_t)ntiles + 1, st));
-        launches++;
-        CU(cudaMemcpyAsync(ctx->h_counters, d_ctr, KG_CTR_COUNT * 8, cudaMemcpyDeviceToHost, st));
-        if (b->n) {
-            k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sc.tile_base.as<uint32_t>(),
-                                                        sc.tile_out.as<uint32_t>(), ntiles, sc.chunk_pos.as<uint32_t>(),
-                                                        sc.chunk_payload.as<int4>(), fp, sc.sparse.as<KgDevCall>(),
-                                                        sc.lo.as<uint32_t>(), sc.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
-            launches++;
-        }
-        CU(cudaMemsetAsync(sc.call_cnt.as<uint32_t>() + nv, 0, 4, st));
-        KG_TRY(exclusive_sum_u32(ctx, sc.call_cnt.as<uint32_t>(), sc.call_off.as<uint32_t>(), nv + 1, st));
-        launches++;
-        if (nv) {
-            k_compact_calls<<<blocks_for(nv, 256), 256, 0, st>>>(sc.sparse.as<KgDevCall>(), sc.lo.as<uint32_t>(),
-                                                                sc.call_off.as<uint32_t>(), nv, per_seq, prm->min_hits,
-                                                                r->d_calls.as<kg_call>());
-            launches++;
-        }
-        CU(cudaMemcpyAsync(&ctx->h_counters[KG_CTR_COUNT], sc.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
-        cudaEventRecord(ctx->ev[9], st);
-        CU(cudaStreamSynchronize(st));
-        CU(cudaGetLastError());
-        nhits = ctx->h_counters[KG_CTR_HITS];
-        nkmers = ctx->h_counters[KG_CTR_KMERS];
-        if (!ctx->h_counters[KG_CTR_OVERFLOW]) break;
-        if (attempt) KG_FAIL(KG_ECUDA, "hit buffer overflow persisted after resizing to %llu", (unsigned long long)hit_cap);
-        hit_cap = nhits; // exact
+    sl.hit_cap = hit_cap;
+    const uint64_t max_calls = hit_cap / (uint64_t)prm->min_hits + 1;
+    KG_TRY(sl.chunk_pos.ensure(hit_cap * 4));
+    KG_TRY(sl.chunk_payload.ensure(hit_cap * sizeof(int4)));
+    KG_TRY(sl.sparse.ensure(max_calls * sizeof(KgDevCall)));
+    if (r->d_otus.cap < std::max<uint64_t>(b->n, 1) * sizeof(kg_otu)) {
+        pool_give_dev(ctx, &r->d_otus);
+        KG_TRY(pool_take_dev(ctx, std::max<uint64_t>(b->n, 1) * sizeof(kg_otu), &r->d_otus));
     }
+    if (r->d_calls.cap < max_calls * sizeof(kg_call)) {
+        pool_give_dev(ctx, &r->d_calls);
+        KG_TRY(pool_take_dev(ctx, max_calls * sizeof(kg_call), &r->d_calls));
+    }
+    const KgFsmParams fp = {prm->min_hits, prm->max_gap, prm->order_constraint, (float)prm->min_weighted_hits};
+    CU(cudaMemsetAsync(d_ctr, 0, KG_CTR_COUNT * 8, st));
+    CU(cudaMemsetAsync(sl.tile_cnt.p, 0, ((size_t)ntiles + 1) * 4, st));
+    cudaEventRecord(sl.ev[1], st);
+    if (ntiles) {
+        k_probe<<<ntiles, PROBE_BLK, PROBE_SMEM, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sl.chunk_pos.as<uint32_t>(),
+                                                      sl.chunk_payload.as<int4>(), (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
+                                                      sl.tile_cnt.as<uint32_t>(), d_ctr, probe_flags());
+        sl.launches++;
+    }
+    cudaEventRecord(sl.ev[2], st);
+    KG_TRY(exclusive_sum_u32(ctx, sl.tile_cnt.as<uint32_t>(), sl.tile_out.as<uint32_t>(), (size_t)ntiles + 1, st));
+    sl.launches++;
+    CU(cudaMemcpyAsync(sl.h_ctr, d_ctr, KG_CTR_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    if (b->n) {
+        k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sl.tile_base.as<uint32_t>(),
+                                                    sl.tile_out.as<uint32_t>(), ntiles, sl.chunk_pos.as<uint32_t>(),
+                                                    sl.chunk_payload.as<int4>(), fp, sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(),
+                                                    sl.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+        sl.launches++;
+    }
+    CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + nv, 0, 4, st));
+    KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), nv + 1, st));
+    sl.launches++;
+    if (nv) {
+        k_compact_calls<<<blocks_for(nv, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(), sl.call_off.as<uint32_t>(),
+                                                            nv, per_seq, prm->min_hits, seq_base, r->d_calls.as<kg_call>());
+        sl.launches++;
+    }
+    CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(sl.ev[3], st);
+    return KG_OK;
+}
+
+// Wait for the pass, repeat it once if the hit buffers were too small, fill in the statistics, and (for "-d") build the
+// position-ordered HIT records.
+static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result* r,
+                       uint32_t seq_base) {
+    cudaStream_t st = ctx->stream;
+    RunScratch& sc = scratch_of(ctx);
+    uint32_t launches = 0;
+    for (int attempt = 0;; attempt++) {
+        CU(cudaEventSynchronize(sl.ev[3]));
+        CU(cudaGetLastError());
+        launches += sl.launches;
+        if (!sl.h_ctr[KG_CTR_OVERFLOW]) break;
+        if (attempt) KG_FAIL(KG_ECUDA, "hit buffer overflow persisted after resizing to %llu", (unsigned long long)sl.hit_cap);
+        KG_TRY(pipe_enqueue(ctx, sl, table, b, prm, r, sl.h_ctr[KG_CTR_HITS], seq_base)); // exact size
+    }
+    const uint64_t nhits = sl.h_ctr[KG_CTR_HITS], nkmers = sl.h_ctr[KG_CTR_KMERS];
     sc.hit_cap_seen = std::max<uint64_t>(sc.hit_cap_seen, nhits + nhits / 16 + 1024);
     if (nhits > 0xFFFFFFF0ull) KG_FAIL(KG_ERANGE, "%llu hits in one batch", (unsigned long long)nhits);
-    cudaEventElapsedTime(&r->stats.ms_prepare, ctx->ev[6], ctx->ev[7]);
-    cudaEventElapsedTime(&r->stats.ms_probe, ctx->ev[7], ctx->ev[8]);
-    cudaEventElapsedTime(&r->stats.ms_group, ctx->ev[8], ctx->ev[9]);
-
+    cudaEventElapsedTime(&r->stats.ms_prepare, sl.ev[0], sl.ev[1]);
+    cudaEventElapsedTime(&r->stats.ms_probe, sl.ev[1], sl.ev[2]);
+    cudaEventElapsedTime(&r->stats.ms_group, sl.ev[2], sl.ev[3]);
+    cudaEventElapsedTime(&r->stats.ms_device, sl.ev[0], sl.ev[3]);
+    const uint64_t nv = b->nv;
+    const int per_seq = b->mode == KG_MODE_AA ? 1 : 6;
+    const uint32_t ntiles = (uint32_t)((b->vtotal + TILE - 1) >> TILE_SHIFT);
     if (prm->emit_hits && nhits) { // "-d": position-ordered HIT records
         KG_TRY(sc.hit_pos.ensure(nhits * 4));
         KG_TRY(sc.hit_payload.ensure(nhits * sizeof(int4)));
-        KG_TRY(pool_take_dev(ctx, nhits * sizeof(kg_hit), &r->d_hits));
-        k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sc.chunk_pos.as<uint32_t>(), sc.chunk_payload.as<int4>(),
-                                                                      sc.tile_base.as<uint32_t>(), sc.tile_out.as<uint32_t>(), ntiles,
+        if (r->d_hits.cap < nhits * sizeof(kg_hit)) {
+            pool_give_dev(ctx, &r->d_hits);
+            KG_TRY(pool_take_dev(ctx, nhits * sizeof(kg_hit), &r->d_hits));
+        }
+        k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
+                                                                      sl.tile_base.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
                                                                       sc.hit_pos.as<uint32_t>(), sc.hit_payload.as<int4>());
         k_emit_hits<<<blocks_for(nhits, 256), 256, 0, st>>>(b->voffsets(), nv, per_seq, sc.hit_pos.as<uint32_t>(),
-                                                           sc.hit_payload.as<int4>(), (uint32_t)nhits, r->d_hits.as<kg_hit>());
+                                                           sc.hit_payload.as<int4>(), (uint32_t)nhits, seq_base, r->d_hits.as<kg_hit>());
         launches += 2;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
     }
     r->stats.num_sequences = b->n;
-    r->stats.num_positions = vtotal;
+    r->stats.num_positions = b->vtotal;
     r->stats.num_kmers = nkmers;
     r->stats.num_hits = nhits;
-    r->stats.num_calls = *(uint32_t*)&ctx->h_counters[KG_CTR_COUNT];
+    r->stats.num_calls = *(uint32_t*)&sl.h_ctr[KG_CTR_COUNT];
     r->stats.num_launches = launches;
     return KG_OK;
 }
@@ -833,15 +893,13 @@ extern "C" int kg_batch_run(kg_context* ctx, const kg_table* table, kg_batch* ba
     CU(cudaSetDevice(ctx->device));
     kg_result* r = new kg_result();
     r->ctx = ctx;
-    cudaEventRecord(ctx->ev[0], ctx->stream);
-    int rc = run_pipeline(ctx, table, batch, params, r, scratch_of(ctx).hit_cap_seen);
+    RunScratch& sc = scratch_of(ctx);
+    int rc = pipe_enqueue(ctx, sc.slot[0], table, batch, params, r, sc.hit_cap_seen, 0);
+    if (rc == KG_OK) rc = pipe_finish(ctx, sc.slot[0], table, batch, params, r, 0);
     if (rc != KG_OK) {
         kg_result_free(r);
         return rc;
     }
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    cudaEventSynchronize(ctx->ev[1]);
-    cudaEventElapsedTime(&r->stats.ms_device, ctx->ev[0], ctx->ev[1]);
     *out = r;
     return KG_OK;
 }
@@ -868,25 +926,191 @@ extern "C" int kg_result_fetch(kg_result* r) {
     return KG_OK;
 }
 
+// Host buffers in, host results out.  The batch is cut into slices of a few tens of MB at sequence boundaries (sequences
+// are independent, KGJ:528/540); slice i+1 is copied to the device (copy stream) while slice i runs (compute stream) and
+// the records of slice i-1 travel back (third stream), so the end-to-end time approaches max(H2D, device) instead of
+// their sum.  Pinned caller buffers make the copies truly asynchronous; pageable ones still work.
 extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const uint8_t* seq_bytes, const uint64_t* offsets,
                       size_t n, const kg_params* params, kg_result** out) {
-    if (!ctx || !table || !out) KG_FAIL(KG_EINVAL, "kg_run: null argument");
+    if (!ctx || !table || !out || !offsets || (mode != KG_MODE_AA && mode != KG_MODE_DNA)) KG_FAIL(KG_EINVAL, "kg_run: bad argument");
     KG_TRY(check_params(params));
-    kg_batch* b = nullptr;
-    cudaEventRecord(ctx->ev[4], ctx->stream);
-    KG_TRY(kg_batch_upload(ctx, mode, seq_bytes, offsets, n, &b));
-    cudaEventRecord(ctx->ev[5], ctx->stream);
-    kg_result* r = nullptr;
-    int rc = kg_batch_run(ctx, table, b, params, &r);
-    kg_batch_free(b);
-    if (rc != KG_OK) return rc;
-    cudaEventElapsedTime(&r->stats.ms_h2d, ctx->ev[4], ctx->ev[5]);
-    rc = kg_result_fetch(r);
-    if (rc != KG_OK) {
-        kg_result_free(r);
-        return rc;
+    if (offsets[0] != 0) KG_FAIL(KG_EINVAL, "kg_run: offsets[0] must be 0");
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) KG_FAIL(KG_EINVAL, "kg_run: offsets must be non-decreasing (at %zu)", i);
+    if (offsets[n] && !seq_bytes) KG_FAIL(KG_EINVAL, "kg_run: null sequence bytes");
+    if (n >= 0xFFFFFFF0ull) KG_FAIL(KG_ERANGE, "kg_run: %zu sequences in one call", n);
+    CU(cudaSetDevice(ctx->device));
+    RunScratch& sc = scratch_of(ctx);
+
+    // slice plan
+    // about six slices per call, 24..96 MB of residues each (a slice costs ~0.4 ms of host-side API calls, so many
+    // small slices would make the host the bottleneck; few large ones expose the first upload)
+    uint64_t target = std::min<uint64_t>(std::max<uint64_t>(offsets[n] / 6, 24ull << 20), 96ull << 20);
+    if (mode == KG_MODE_DNA) target /= 2; // six translations: two residues per nucleotide
+    if (const char* e = getenv("KG_SLICE_MB")) target = (uint64_t)atoll(e) << 20;
+    if (target < 65536) target = 65536;
+    const uint64_t hard = mode == KG_MODE_AA ? KG_MAX_STREAM : KG_MAX_STREAM / 2 - 64 * (uint64_t)n; // dna: 2 residues per nucleotide
+    std::vector<size_t> cut{0};
+    for (size_t i = 0; i < n;) {
+        size_t j = i;
+        while (j < n && (j == i || offsets[j + 1] - offsets[i] <= target)) j++;
+        if (offsets[j] - offsets[i] > hard) KG_FAIL(KG_ERANGE, "kg_run: sequence %zu alone exceeds the per-call limit", i);
+        cut.push_back(j);
+        i = j;
     }
-    *out = r;
+    if (n == 0) cut.push_back(0);
+    const size_t nslices = cut.size() - 1;
+
+    kg_result* R = new kg_result();
+    R->ctx = ctx;
+    R->n = n;
+    R->mode = mode;
+    R->params = *params;
+    R->nv = (uint64_t)n * (mode == KG_MODE_AA ? 1 : 6);
+    // device records of finished slices stay alive until their D2H copies are done: a ring of KEEP slices, each fenced
+    // by an event on the D2H stream, so that the buffers return to the pool (no cudaMalloc in steady state)
+    constexpr int KEEP = 3;
+    DevBuf keep[KEEP][3];
+    bool keep_used[KEEP] = {false, false, false};
+    kg_batch* slot[2] = {nullptr, nullptr};
+    int rc = KG_OK;
+    uint64_t ncalls = 0, nhits = 0;
+    auto fail = [&](int code) {
+        cudaDeviceSynchronize();
+        for (auto& k3 : keep)
+            for (auto& d : k3) pool_give_dev(ctx, &d);
+        for (auto*& b : slot)
+            if (b) { kg_batch_free(b); b = nullptr; }
+        kg_result_free(R);
+        return code;
+    };
+    auto upload = [&](size_t s) -> int { // slice s -> slot[s & 1], asynchronously on the copy stream
+        const size_t a = cut[s], b = cut[s + 1], cnt = b - a;
+        const uint64_t bytes = offsets[b] - offsets[a];
+        kg_batch* bt = new kg_batch();
+        bt->ctx = ctx;
+        bt->mode = mode;
+        bt->n = cnt;
+        bt->total = bytes;
+        slot[s & 1] = bt;
+        KG_TRY(pool_take_dev(ctx, bytes + 64, &bt->seq_buf));
+        KG_TRY(pool_take_dev(ctx, (cnt + 1) * 8, &bt->off_buf));
+        bt->d_seq = bt->seq_buf.as<uint8_t>();
+        bt->d_off = bt->off_buf.as<uint64_t>();
+        if (mode == KG_MODE_DNA) { // residue-stream length of the six translations, as k_vlen lays them out
+            uint64_t vt = 0;
+            for (size_t i = a; i < b; i++) {
+                const uint64_t L = offsets[i + 1] - offsets[i];
+                for (uint64_t f = 0; f < 3; f++) vt += 2 * (((L >= f + 3 ? (L - f) / 3 : 0) + 1 + 3) & ~3ull);
+            }
+            bt->vtotal = vt;
+            bt->vtotal_known = true;
+        }
+        cudaStream_t cs = ctx->copy_stream;
+        CU(cudaMemsetAsync(bt->d_seq + bytes, 0, 64, cs));
+        if (bytes) CU(cudaMemcpyAsync(bt->d_seq, seq_bytes + offsets[a], bytes, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(bt->d_off, offsets + a, (cnt + 1) * 8, cudaMemcpyHostToDevice, cs));
+        if (offsets[a]) k_rebase<<<blocks_for(cnt + 1, 256), 256, 0, cs>>>(bt->d_off, cnt + 1, offsets[a]);
+        CU(cudaEventRecord(ctx->ev[10 + (s & 1)], cs));
+        return KG_OK;
+    };
+
+    if ((rc = pool_take_host(ctx, std::max<size_t>(n, 1) * sizeof(kg_otu), &R->h_otus)) != KG_OK) return fail(rc);
+    if ((rc = pool_take_host(ctx, std::max<uint64_t>(sc.calls_seen + sc.calls_seen / 4, 1u << 16) * sizeof(kg_call), &R->h_calls)) != KG_OK) return fail(rc);
+    if (params->emit_hits && (rc = pool_take_host(ctx, std::max<uint64_t>(sc.hit_cap_seen, 1u << 16) * sizeof(kg_hit), &R->h_hits)) != KG_OK) return fail(rc);
+    auto grow = [&](HostBuf* hb, uint64_t need_bytes, uint64_t used_bytes) -> int { // rare: first run, or a batch unlike the last
+        if (need_bytes <= hb->cap) return KG_OK;
+        CU(cudaStreamSynchronize(ctx->d2h_stream));
+        HostBuf nb;
+        KG_TRY(pool_take_host(ctx, need_bytes + need_bytes / 2, &nb));
+        if (used_bytes) memcpy(nb.p, hb->p, used_bytes);
+        pool_give_host(ctx, hb);
+        *hb = nb;
+        return KG_OK;
+    };
+
+    const bool dbg = getenv("KG_DEBUG") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now_ms();
+    kg_result part[2];
+    part[0].ctx = part[1].ctx = ctx;
+    auto drop_parts = [&]() {
+        for (auto& pt : part) {
+            pool_give_dev(ctx, &pt.d_calls);
+            pool_give_dev(ctx, &pt.d_otus);
+            pool_give_dev(ctx, &pt.d_hits);
+        }
+    };
+    auto enqueue = [&](size_t s) -> int { // slice s runs as soon as its bytes have landed; nothing here waits for the GPU
+        cudaStreamWaitEvent(ctx->stream, ctx->ev[10 + (s & 1)], 0);
+        return pipe_enqueue(ctx, sc.slot[s & 1], table, slot[s & 1], params, &part[s & 1], sc.hit_cap_seen, (uint32_t)cut[s]);
+    };
+    if (nslices && ((rc = upload(0)) != KG_OK || (rc = enqueue(0)) != KG_OK)) {
+        drop_parts();
+        return fail(rc);
+    }
+    for (size_t s = 0; s < nslices; s++) {
+        const double t0 = now_ms();
+        if (keep_used[s % KEEP]) { // the ring slot this slice will take: its copies are long done
+            cudaEventSynchronize(ctx->d2h_ev[s % KEEP]);
+            for (auto& d : keep[s % KEEP]) pool_give_dev(ctx, &d);
+            keep_used[s % KEEP] = false;
+        }
+        // queue slice s+1 behind slice s BEFORE waiting for slice s: the GPU never idles between slices
+        if (s + 1 < nslices && ((rc = upload(s + 1)) != KG_OK || (rc = enqueue(s + 1)) != KG_OK)) {
+            drop_parts();
+            return fail(rc);
+        }
+        kg_batch* bt = slot[s & 1];
+        kg_result& pr = part[s & 1];
+        rc = pipe_finish(ctx, sc.slot[s & 1], table, bt, params, &pr, (uint32_t)cut[s]);
+        if (rc != KG_OK) {
+            drop_parts();
+            return fail(rc);
+        }
+        const float ms = pr.stats.ms_device;
+        // records of this slice go home on the third stream while the next slice computes
+        const kg_run_stats ps = pr.stats;
+        cudaStream_t ds = ctx->d2h_stream;
+        if ((rc = grow(&R->h_calls, (ncalls + ps.num_calls) * sizeof(kg_call), ncalls * sizeof(kg_call))) != KG_OK) { drop_parts(); return fail(rc); }
+        if (ps.num_calls) cudaMemcpyAsync((kg_call*)R->h_calls.p + ncalls, pr.d_calls.p, ps.num_calls * sizeof(kg_call), cudaMemcpyDeviceToHost, ds);
+        if (bt->n) cudaMemcpyAsync((kg_otu*)R->h_otus.p + cut[s], pr.d_otus.p, bt->n * sizeof(kg_otu), cudaMemcpyDeviceToHost, ds);
+        if (params->emit_hits) {
+            if ((rc = grow(&R->h_hits, (nhits + ps.num_hits) * sizeof(kg_hit), nhits * sizeof(kg_hit))) != KG_OK) { drop_parts(); return fail(rc); }
+            if (ps.num_hits) cudaMemcpyAsync((kg_hit*)R->h_hits.p + nhits, pr.d_hits.p, ps.num_hits * sizeof(kg_hit), cudaMemcpyDeviceToHost, ds);
+        }
+        {
+            const int k = (int)(s % KEEP);
+            keep[k][0] = pr.d_calls;
+            keep[k][1] = pr.d_otus;
+            keep[k][2] = pr.d_hits;
+            keep_used[k] = true;
+            cudaEventRecord(ctx->d2h_ev[k], ds);
+            pr.d_calls = pr.d_otus = pr.d_hits = DevBuf();
+        }
+        ncalls += ps.num_calls;
+        nhits += ps.num_hits;
+        R->stats.num_positions += ps.num_positions;
+        R->stats.num_kmers += ps.num_kmers;
+        R->stats.num_launches += ps.num_launches;
+        R->stats.ms_device += ms;
+        R->stats.ms_prepare += ps.ms_prepare;
+        R->stats.ms_probe += ps.ms_probe;
+        R->stats.ms_group += ps.ms_group;
+        kg_batch_free(bt);
+        slot[s & 1] = nullptr;
+        if (dbg) fprintf(stderr, "[kg] slice %zu: %zu seqs, host %.3f ms (device %.3f ms), since start %.3f ms\n", s, (size_t)(cut[s + 1] - cut[s]), now_ms() - t0, ms, now_ms() - t_begin);
+    }
+    CU(cudaStreamSynchronize(ctx->d2h_stream));
+    if (dbg) fprintf(stderr, "[kg] kg_run total %.3f ms\n", now_ms() - t_begin);
+    for (auto& k3 : keep)
+        for (auto& d : k3) pool_give_dev(ctx, &d);
+    R->stats.num_sequences = n;
+    R->stats.num_calls = ncalls;
+    R->stats.num_hits = nhits;
+    sc.calls_seen = std::max<uint64_t>(sc.calls_seen, ncalls);
+    R->fetched = true;
+    *out = R;
     return KG_OK;
 }
 
