@@ -39,6 +39,11 @@ int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64_t max_sigs
 int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t first, uint64_t n, uint64_t seed,
                       uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes);
 
+/* configs[2]-style genomes: n_genomes contigs of `length` bases; genes are family consensus proteins back-translated with
+ * uniformly chosen synonymous codons on a random strand, separated by random spacers of uniform ACGT; ~1e-5 N. */
+int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t n_genomes, uint64_t length, uint64_t seed,
+                     uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes);
+
 /* kmer.table.mem_map image (24-byte header + num_slots 24-byte LE entries, linear probing WITHOUT wrap-around, last
  * slot empty) built on the device from (keys, payload).  num_slots = the first prime >= min_slots for which no probe
  * chain runs off the end.  *d_image is a device buffer of 24 + 24 * *num_slots bytes owned by the caller.

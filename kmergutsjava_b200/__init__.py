@@ -34,7 +34,7 @@ EXPORTS = [
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
     "kg_functions_load", "kg_functions_read", "kg_functions_count", "kg_functions_name", "kg_functions_free",
     "kg_format_java_f", "kg_report_write", "kg_main",
-    "kg_synth_signatures", "kg_synth_proteins", "kg_synth_reference_image", "kg_device_free", "kg_device_to_host",
+    "kg_synth_signatures", "kg_synth_proteins", "kg_synth_genomes", "kg_synth_reference_image", "kg_device_free", "kg_device_to_host",
     "kg_probe_roofline", "kg_probe_roofline_table",
 ]
 
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "kg_main": (i32, [i32, C.POINTER(C.c_char_p)]),
         "kg_synth_signatures": (i32, [vp, C.POINTER(UniverseStruct), u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_proteins": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
+        "kg_synth_genomes": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, C.POINTER(u64), pp, C.POINTER(C.c_double)]),
         "kg_device_free": (None, [vp]), "kg_device_to_host": (i32, [vp, vp, vp, u64]),
         "kg_probe_roofline": (i32, [vp, u64, u64, i32, i32, C.POINTER(C.c_double)]),
@@ -334,6 +335,13 @@ def synth_proteins(ctx: Context, u, first: int, n: int, seed: int):
     ds, do, total = C.c_void_p(), C.c_void_p(), C.c_uint64()
     us = make_universe(u)
     _check(lib().kg_synth_proteins(ctx._h, C.byref(us), first, n, seed, C.byref(ds), C.byref(do), C.byref(total)))
+    return ds.value, do.value, total.value
+
+
+def synth_genomes(ctx: Context, u, n_genomes: int, length: int, seed: int):
+    ds, do, total = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    us = make_universe(u)
+    _check(lib().kg_synth_genomes(ctx._h, C.byref(us), n_genomes, length, seed, C.byref(ds), C.byref(do), C.byref(total)))
     return ds.value, do.value, total.value
 
 

@@ -166,3 +166,135 @@ struct KgFsm {
         if (n >= p.min_hits) process(p, emit); // KGJ:511-513
     }
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Segment variant (long contigs).  After a gap larger than max_gap the open run is always empty: at the gap test
+// processSetOfHits either clears the list or is entered with a list whose last two entries do NOT form a foreign pair
+// (the pair-switch test of KGJ:503-507 has fired on every append, so "l2.fI == l1.fI != cur" never survives a step),
+// hence its retained-pair branch (KGJ:442-449) cannot be taken there.  A container's hits can therefore be cut at gaps
+// > max_gap into independent segments, one thread each.  The OTU buffer is order-dependent across calls (KGJ:413-438),
+// so this FSM only MARKS the hits each call counts (flag 1) and a per-sequence replay applies them in order afterwards.
+// flag[i]: 0 = not counted, 2 = counted by the still-open run (tentative), 1 = counted by an emitted CALL.
+// ---------------------------------------------------------------------------------------------------------------
+struct KgFsmSeg {
+    int n, cur, first_pos, cnt, last_match;
+    float w;
+    KgHitLite l1, l2;
+    uint32_t i1, i2;          // global hit indices of l1 / l2
+    uint32_t first_idx, last_match_idx;
+    int consumed, ncalls;
+
+    __device__ __forceinline__ void begin(int consumed0) {
+        n = 0;
+        cur = 0;
+        consumed = consumed0;
+        ncalls = 0;
+        cnt = 0;
+        w = 0.f;
+        first_pos = last_match = 0;
+        l1 = KgHitLite{0, 0, 0, 0, 0.f};
+        l2 = l1;
+        i1 = i2 = first_idx = last_match_idx = 0;
+    }
+    __device__ __forceinline__ void append(const KgHitLite& h, uint32_t idx, uint8_t* flag) {
+        if (n == 0) {
+            first_pos = h.pos;
+            first_idx = idx;
+            cnt = 0;
+            w = 0.f;
+        }
+        n++;
+        l2 = l1;
+        i2 = i1;
+        l1 = h;
+        i1 = idx;
+        if (h.fI == cur) {
+            cnt++;
+            w = __fadd_rn(w, h.wt);
+            last_match = h.pos;
+            last_match_idx = idx;
+            flag[idx] = 2;
+        }
+    }
+    template <class Emit>
+    __device__ __forceinline__ void process(const KgFsmParams& p, Emit& emit, uint8_t* flag) {
+        if (cnt >= p.min_hits && w >= p.min_weighted) {
+            KgDevCall c = {first_pos, last_match + (KG_K - 1), cnt, cur, w, consumed};
+            emit(ncalls, c);
+            ncalls++;
+            for (uint32_t i = first_idx; i <= last_match_idx; i++) // the hits KGJ:413-439 replays into the OTU buffer
+                if (flag[i] == 2) flag[i] = 1;
+        } // tentative marks of an uncalled run stay 2: they lie outside every later run's index range and are never read
+        if (n >= 2 && l2.fI != cur && l2.fI == l1.fI) {
+            cur = l1.fI;
+            n = 2;
+            first_pos = l2.pos;
+            first_idx = i2;
+            cnt = 2;
+            w = __fadd_rn(__fadd_rn(0.f, l2.wt), l1.wt);
+            last_match = l1.pos;
+            last_match_idx = i1;
+            flag[i2] = 2;
+            flag[i1] = 2;
+        } else {
+            n = 0;
+        }
+    }
+    template <class Emit>
+    __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, uint32_t idx, Emit& emit, uint8_t* flag) {
+        consumed++;
+        if (n > 0 && (int)((unsigned)l1.pos + (unsigned)p.max_gap) < h.pos) {
+            if (n >= p.min_hits) process(p, emit, flag);
+            else n = 0;
+        }
+        if (n == 0) cur = h.fI;
+        bool accept = !p.order_constraint || n == 0;
+        if (!accept) {
+            int d = (int)((unsigned)(h.pos - l1.pos) - (unsigned)(l1.avg - h.avg));
+            int ad = d < 0 ? (int)(0u - (unsigned)d) : d;
+            accept = (h.fI == l1.fI) && ad <= 20;
+        }
+        if (accept) {
+            if (n < KG_MAX_HITS_PER_SEQ - 2) append(h, idx, flag);
+            if (n > 1 && cur != h.fI && l2.fI == l1.fI) process(p, emit, flag);
+        }
+    }
+    template <class Emit>
+    __device__ __forceinline__ void end(const KgFsmParams& p, Emit& emit, uint8_t* flag) {
+        if (n >= p.min_hits) process(p, emit, flag);
+    }
+};
+
+// count += m for oI (m >= 1 consecutive updates of the same OTU index collapse exactly: the entry ends up in front of
+// the maximal block of entries ahead of it whose count is <= its final count, whether it got there in one step or m)
+__device__ __forceinline__ void kg_otu_update_n(KgOtuBuf& u, int oI, int m) {
+    int j = u.n;
+#pragma unroll
+    for (int i = KG_OI_BUFSZ - 1; i >= 0; i--)
+        if (i < u.n && u.o[i] == oI) j = i;
+    if (j == u.n) {
+        if (u.n == KG_OI_BUFSZ) j = KG_OI_BUFSZ - 1;
+        else u.n++;
+#pragma unroll
+        for (int i = 0; i < KG_OI_BUFSZ; i++)
+            if (i == j) {
+                u.o[i] = oI;
+                u.c[i] = m;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < KG_OI_BUFSZ; i++)
+            if (i == j) u.c[i] += m;
+    }
+#pragma unroll
+    for (int i = KG_OI_BUFSZ - 1; i >= 1; i--) {
+        if (i == j && u.c[i - 1] <= u.c[i]) {
+            int tc = u.c[i - 1], to = u.o[i - 1];
+            u.c[i - 1] = u.c[i];
+            u.o[i - 1] = u.o[i];
+            u.c[i] = tc;
+            u.o[i] = to;
+            j = i - 1;
+        }
+    }
+}

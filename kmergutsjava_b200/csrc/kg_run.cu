@@ -7,6 +7,8 @@
 //   gatherHits / processSetOfHits KGJ:457-514, 385-455 (k_fsm)
 #include <cub/device/device_scan.cuh>
 
+#include <string.h>
+
 #include <algorithm>
 #include <chrono>
 
@@ -310,10 +312,11 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe(const uint8_t
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_gather(const uint32_t* __restrict__ chunk_pos, const int4* __restrict__ chunk_payload,
                          const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_out, uint32_t ntiles,
-                         uint32_t* __restrict__ hit_pos, int4* __restrict__ hit_payload) {
+                         uint32_t* __restrict__ hit_pos, int4* __restrict__ hit_payload,
+                         const unsigned long long* __restrict__ ctr) {
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (t >= ntiles) return;
+    if (t >= ntiles || ctr[KG_CTR_OVERFLOW]) return;
     const uint32_t out = tile_out[t], cnt = tile_out[t + 1] - out, base = tile_base[t];
     for (uint32_t j = lane; j < cnt; j += 32) {
         hit_pos[out + j] = chunk_pos[base + j];
@@ -407,6 +410,164 @@ __global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, 
     otus[s] = o;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// segment path (long contigs; kg_fsm.cuh explains why a container can be cut at gaps > max_gap)
+// ---------------------------------------------------------------------------------------------------------------
+// container of every position-ordered hit + "a segment starts here"
+__global__ void k_seg_flags(const uint64_t* __restrict__ voff, uint64_t nv, const uint32_t* __restrict__ hit_pos,
+                            const uint32_t* __restrict__ tile_out, uint32_t ntiles, uint32_t cap, int max_gap,
+                            uint32_t* __restrict__ hit_v, uint32_t* __restrict__ seg_flag,
+                            const unsigned long long* __restrict__ ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const uint32_t nhits = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
+    if (i >= nhits) {
+        seg_flag[i] = 0;
+        return;
+    }
+    const uint32_t g = hit_pos[i];
+    const uint64_t v = seq_of(voff, nv, g);
+    hit_v[i] = (uint32_t)v;
+    bool start = i == 0;
+    if (!start) {
+        const uint32_t gp = hit_pos[i - 1];
+        start = (uint64_t)gp < voff[v] || g - gp > (uint32_t)max_gap;
+    }
+    seg_flag[i] = start;
+}
+__global__ void k_seg_begin(const uint32_t* __restrict__ seg_flag, const uint32_t* __restrict__ seg_id,
+                            const uint32_t* __restrict__ tile_out, uint32_t ntiles, uint32_t cap,
+                            uint32_t* __restrict__ seg_begin, uint32_t* __restrict__ nseg_out,
+                            const unsigned long long* __restrict__ ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const uint32_t nhits = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
+    if (i < nhits && seg_flag[i]) seg_begin[seg_id[i] - 1] = i;
+    if (i == 0) {
+        const uint32_t ns = nhits ? seg_id[nhits - 1] : 0u;
+        nseg_out[0] = ns;
+        seg_begin[ns] = nhits;
+    }
+}
+// lo[v] = rank of the first hit at or after the start of container v (v = nv gives the number of hits)
+__global__ void k_lo(const uint64_t* __restrict__ voff, uint64_t nv, const uint32_t* __restrict__ hit_pos,
+                     const uint32_t* __restrict__ tile_out, uint32_t ntiles, uint32_t* __restrict__ lo,
+                     const unsigned long long* __restrict__ ctr) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > nv) return;
+    const uint32_t nhits = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
+    const uint64_t x = voff[v];
+    uint32_t a = 0, b = nhits;
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if ((uint64_t)hit_pos[mid] < x) a = mid + 1;
+        else b = mid;
+    }
+    lo[v] = a;
+}
+__global__ __launch_bounds__(128) void k_fsm_seg(const uint64_t* __restrict__ voff, const uint32_t* __restrict__ hit_pos,
+                                                 const int4* __restrict__ hit_payload, const uint32_t* __restrict__ hit_v,
+                                                 const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg,
+                                                 const uint32_t* __restrict__ lo, uint32_t cap, KgFsmParams p,
+                                                 KgDevCall* __restrict__ sparse, uint32_t* __restrict__ seg_calls,
+                                                 uint8_t* __restrict__ flag) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cap) return;
+    if (j >= nseg[0]) {
+        seg_calls[j] = 0;
+        return;
+    }
+    const uint32_t a = seg_begin[j], b = seg_begin[j + 1];
+    const uint32_t v = hit_v[a];
+    const uint32_t base = (uint32_t)voff[v];
+    KgFsmSeg f;
+    f.begin((int)(a - lo[v])); // HIT lines of this container printed before the segment
+    SparseEmit emit{sparse + a / (uint32_t)p.min_hits};
+    for (uint32_t i = a; i < b; i++) {
+        const int4 pl = hit_payload[i];
+        KgHitLite h = {(int)(hit_pos[i] - base), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
+        f.hit(p, h, i, emit, flag);
+    }
+    // In the reference the run that ends at a gap is processed when the NEXT hit of the container arrives, after that
+    // hit's HIT line (KGJ:472-480); only the container's last run is processed after the loop (KGJ:511-513).
+    if (j + 1 < nseg[0] && hit_v[b] == v) f.consumed++;
+    f.end(p, emit, flag);
+    seg_calls[j] = (uint32_t)f.ncalls;
+}
+__global__ void k_compact_calls_seg(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ seg_begin,
+                                    const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ hit_v,
+                                    const uint32_t* __restrict__ call_off, uint32_t cap, int per_seq, int min_hits,
+                                    uint32_t seq_base, kg_call* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cap || j >= nseg[0]) return;
+    const uint32_t o = call_off[j], c = call_off[j + 1] - o, a = seg_begin[j], v = hit_v[a];
+    const KgDevCall* src = sparse + a / (uint32_t)min_hits;
+    for (uint32_t k = 0; k < c; k++) {
+        const KgDevCall d = src[k];
+        kg_call r;
+        r.seq = seq_base + v / (uint32_t)per_seq;
+        r.strand_frame = (int32_t)(v % (uint32_t)per_seq);
+        r.start = d.start;
+        r.end = d.end;
+        r.count = d.count;
+        r.fI = d.fI;
+        r.weighted = d.weighted;
+        r.hits_before = d.hits_before;
+        out[o + k] = r;
+    }
+}
+// OTU-COUNTS of one sequence: replay, in order, the OTU index of every hit a CALL counted (KGJ:413-438).  One warp
+// per sequence reads 32 hits at a time; runs of equal OTU indices are collapsed (kg_otu_update_n), so the sequential
+// part of the work is one update per run, not per hit.
+__global__ void k_otu_replay(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const int4* __restrict__ hit_payload,
+                             const uint8_t* __restrict__ flag, kg_otu* __restrict__ otus,
+                             const unsigned long long* __restrict__ ctr) {
+    const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nseq || ctr[KG_CTR_OVERFLOW]) return;
+    const uint32_t a = lo[s * per_seq], b = lo[(s + 1) * per_seq];
+    KgOtuBuf u;
+    kg_otu_clear(u);
+    int cur_oI = 0, cur_cnt = 0;
+    for (uint32_t i0 = a; i0 < b; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool f = i < b && flag[i] == 1;
+        const int oI = f ? hit_payload[i].x : 0;
+        const uint32_t M = __ballot_sync(0xFFFFFFFFu, f);
+        if (M == 0) continue;
+        const uint32_t lower = M & ((1u << lane) - 1u);
+        const int prev_lane = lower ? 31 - __clz(lower) : -1;
+        const int prev_oI = __shfl_sync(0xFFFFFFFFu, oI, prev_lane < 0 ? 0 : prev_lane);
+        const bool head = f && (prev_lane < 0 ? (cur_cnt == 0 || oI != cur_oI) : (oI != prev_oI));
+        uint32_t H = __ballot_sync(0xFFFFFFFFu, head);
+        if (H == 0) {
+            cur_cnt += __popc(M);
+            continue;
+        }
+        const int first_head = __ffs(H) - 1;
+        cur_cnt += __popc(M & ((1u << first_head) - 1u));
+        while (H) {
+            const int h = __ffs(H) - 1;
+            H &= H - 1;
+            const uint32_t upto = H ? ((1u << (__ffs(H) - 1)) - 1u) : 0xFFFFFFFFu;
+            if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
+            cur_oI = __shfl_sync(0xFFFFFFFFu, oI, h);
+            cur_cnt = __popc(M & upto & ~((1u << h) - 1u));
+        }
+    }
+    if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
+    if (lane == 0) {
+        kg_otu o;
+        o.n = u.n;
+#pragma unroll
+        for (int k = 0; k < KG_OI_BUFSZ; k++) {
+            o.count[k] = u.c[k];
+            o.oI[k] = u.o[k];
+        }
+        otus[s] = o;
+    }
+}
+
 __global__ void k_compact_calls(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ lo,
                                 const uint32_t* __restrict__ call_off, uint64_t nv, int per_seq, int min_hits,
                                 uint32_t seq_base, kg_call* __restrict__ out) {
@@ -450,6 +611,9 @@ __global__ void k_emit_hits(const uint64_t* __restrict__ voff, uint64_t nv, int 
 
 struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them let slice s+1 queue up behind slice s
     DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
+    DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
+    DevBuf hit_v, seg_flag, seg_id, seg_begin, hit_flag, nseg;    // segment path
+    bool seg = false;                                            // which FSM path the enqueued run uses
     uint64_t* h_ctr = nullptr; // pinned, KG_CTR_COUNT + 1 (the last slot receives the call total)
     cudaEvent_t ev[4] = {};    // begin, probe begin, probe end, end
     uint64_t hit_cap = 0;
@@ -457,7 +621,6 @@ struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them le
 };
 struct RunScratch { // grow-only device scratch kept per context (so repeated runs do not allocate)
     PipeSlot slot[2];
-    DevBuf hit_pos, hit_payload; // "-d" only
     uint64_t hit_cap_seen = 0;   // hits of the largest run so far (+ slack): sizes the next run's buffers
     uint64_t calls_seen = 0;     // calls of the largest kg_run so far: sizes the pinned result buffer
 };
@@ -538,6 +701,13 @@ int exclusive_sum_u32(kg_context* ctx, const uint32_t* in, uint32_t* out, size_t
     CU(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, bytes, in, out, n, st));
     return KG_OK;
 }
+int inclusive_sum_u32(kg_context* ctx, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
+    size_t bytes = 0;
+    CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, n, st));
+    KG_TRY(ctx->scan_tmp.ensure(bytes));
+    CU(cub::DeviceScan::InclusiveSum(ctx->scan_tmp.p, bytes, in, out, n, st));
+    return KG_OK;
+}
 int exclusive_sum_u64(kg_context* ctx, const uint64_t* in, uint64_t* out, size_t n, cudaStream_t st) {
     size_t bytes = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, st));
@@ -595,14 +765,13 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     RunScratch& sc = scratch_of(ctx);
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
-                          &sl.call_off, &sl.ctr})
+                          &sl.call_off, &sl.ctr, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
+                          &sl.hit_flag, &sl.nseg})
             b->release();
         if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
         for (auto& e : sl.ev)
             if (e) cudaEventDestroy(e);
     }
-    sc.hit_pos.release();
-    sc.hit_payload.release();
     delete static_cast<RunScratch*>(ctx->scratch);
     for (auto& b : ctx->dev_pool) b.release();
     for (auto& h : ctx->host_pool) cudaFreeHost(h.p);
@@ -749,6 +918,13 @@ int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches) {
 // ---------------------------------------------------------------------------------------------------------------
 // the device pipeline
 // ---------------------------------------------------------------------------------------------------------------
+// Which run FSM: one thread per sequence (many short sequences: proteins) or one thread per gap-delimited segment plus an
+// OTU replay (long contigs: 6-frame mode).  KG_FSM=seq|seg overrides (tests drive both paths through the same cases).
+static bool use_segment_path(int mode) {
+    if (const char* e = getenv("KG_FSM")) return strcmp(e, "seg") == 0;
+    return mode == KG_MODE_DNA;
+}
+
 static uint32_t probe_flags() { // experiment switches: bit 0 = no evict_first on bucket lines, bit 1 = unhinted filter loads
     const char* e = getenv("KG_PROBE_FLAGS");
     return e ? (uint32_t)atoi(e) : 0u;
@@ -808,22 +984,64 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
     KG_TRY(exclusive_sum_u32(ctx, sl.tile_cnt.as<uint32_t>(), sl.tile_out.as<uint32_t>(), (size_t)ntiles + 1, st));
     sl.launches++;
     CU(cudaMemcpyAsync(sl.h_ctr, d_ctr, KG_CTR_COUNT * 8, cudaMemcpyDeviceToHost, st));
-    if (b->n) {
-        k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sl.tile_base.as<uint32_t>(),
-                                                    sl.tile_out.as<uint32_t>(), ntiles, sl.chunk_pos.as<uint32_t>(),
-                                                    sl.chunk_payload.as<int4>(), fp, sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(),
-                                                    sl.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+    sl.seg = use_segment_path(b->mode);
+    if (!sl.seg) { // many short sequences: one thread per sequence straight off the per-tile chunks
+        if (b->n) {
+            k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sl.tile_base.as<uint32_t>(),
+                                                        sl.tile_out.as<uint32_t>(), ntiles, sl.chunk_pos.as<uint32_t>(),
+                                                        sl.chunk_payload.as<int4>(), fp, sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(),
+                                                        sl.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+            sl.launches++;
+        }
+        CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + nv, 0, 4, st));
+        KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), nv + 1, st));
         sl.launches++;
+        if (nv) {
+            k_compact_calls<<<blocks_for(nv, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(), sl.call_off.as<uint32_t>(),
+                                                                nv, per_seq, prm->min_hits, seq_base, r->d_calls.as<kg_call>());
+            sl.launches++;
+        }
+        CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
+    } else { // long contigs: position-ordered hits -> segments at gaps > max_gap -> one thread per segment -> OTU replay
+        const uint32_t cap = (uint32_t)hit_cap;
+        KG_TRY(sl.hit_pos.ensure((size_t)cap * 4));
+        KG_TRY(sl.hit_payload.ensure((size_t)cap * sizeof(int4)));
+        KG_TRY(sl.hit_v.ensure((size_t)cap * 4));
+        KG_TRY(sl.seg_flag.ensure((size_t)cap * 4));
+        KG_TRY(sl.seg_id.ensure((size_t)cap * 4));
+        KG_TRY(sl.seg_begin.ensure(((size_t)cap + 1) * 4));
+        KG_TRY(sl.hit_flag.ensure(cap));
+        KG_TRY(sl.nseg.ensure(16));
+        KG_TRY(sl.call_cnt.ensure(((size_t)cap + 1) * 4)); // per segment here
+        KG_TRY(sl.call_off.ensure(((size_t)cap + 1) * 4));
+        CU(cudaMemsetAsync(sl.hit_flag.p, 0, cap, st));
+        if (ntiles) {
+            k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
+                                                                          sl.tile_base.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
+                                                                          sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), d_ctr);
+            sl.launches++;
+        }
+        k_seg_flags<<<blocks_for(cap, 256), 256, 0, st>>>(b->voffsets(), nv, sl.hit_pos.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles, cap,
+                                                         prm->max_gap, sl.hit_v.as<uint32_t>(), sl.seg_flag.as<uint32_t>(), d_ctr);
+        KG_TRY(inclusive_sum_u32(ctx, sl.seg_flag.as<uint32_t>(), sl.seg_id.as<uint32_t>(), cap, st));
+        k_seg_begin<<<blocks_for(cap, 256), 256, 0, st>>>(sl.seg_flag.as<uint32_t>(), sl.seg_id.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
+                                                         cap, sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), d_ctr);
+        k_lo<<<blocks_for(nv + 1, 256), 256, 0, st>>>(b->voffsets(), nv, sl.hit_pos.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
+                                                     sl.lo.as<uint32_t>(), d_ctr);
+        k_fsm_seg<<<blocks_for(cap, 128), 128, 0, st>>>(b->voffsets(), sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), sl.hit_v.as<uint32_t>(),
+                                                       sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), sl.lo.as<uint32_t>(), cap, fp,
+                                                       sl.sparse.as<KgDevCall>(), sl.call_cnt.as<uint32_t>(), sl.hit_flag.as<uint8_t>());
+        CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + cap, 0, 4, st));
+        KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), (size_t)cap + 1, st));
+        k_compact_calls_seg<<<blocks_for(cap, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(),
+                                                                 sl.hit_v.as<uint32_t>(), sl.call_off.as<uint32_t>(), cap, per_seq, prm->min_hits,
+                                                                 seq_base, r->d_calls.as<kg_call>());
+        if (b->n)
+            k_otu_replay<<<blocks_for(b->n * 32, 256), 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.hit_payload.as<int4>(),
+                                                                    sl.hit_flag.as<uint8_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+        sl.launches += 8;
+        CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + cap, 4, cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + nv, 0, 4, st));
-    KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), nv + 1, st));
-    sl.launches++;
-    if (nv) {
-        k_compact_calls<<<blocks_for(nv, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(), sl.call_off.as<uint32_t>(),
-                                                            nv, per_seq, prm->min_hits, seq_base, r->d_calls.as<kg_call>());
-        sl.launches++;
-    }
-    CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
     cudaEventRecord(sl.ev[3], st);
     return KG_OK;
 }
@@ -854,17 +1072,19 @@ static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_
     const int per_seq = b->mode == KG_MODE_AA ? 1 : 6;
     const uint32_t ntiles = (uint32_t)((b->vtotal + TILE - 1) >> TILE_SHIFT);
     if (prm->emit_hits && nhits) { // "-d": position-ordered HIT records
-        KG_TRY(sc.hit_pos.ensure(nhits * 4));
-        KG_TRY(sc.hit_payload.ensure(nhits * sizeof(int4)));
         if (r->d_hits.cap < nhits * sizeof(kg_hit)) {
             pool_give_dev(ctx, &r->d_hits);
             KG_TRY(pool_take_dev(ctx, nhits * sizeof(kg_hit), &r->d_hits));
         }
-        k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
-                                                                      sl.tile_base.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
-                                                                      sc.hit_pos.as<uint32_t>(), sc.hit_payload.as<int4>());
-        k_emit_hits<<<blocks_for(nhits, 256), 256, 0, st>>>(b->voffsets(), nv, per_seq, sc.hit_pos.as<uint32_t>(),
-                                                           sc.hit_payload.as<int4>(), (uint32_t)nhits, seq_base, r->d_hits.as<kg_hit>());
+        if (!sl.seg) { // the segment path has the position-ordered arrays already
+            KG_TRY(sl.hit_pos.ensure(nhits * 4));
+            KG_TRY(sl.hit_payload.ensure(nhits * sizeof(int4)));
+            k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
+                                                                          sl.tile_base.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
+                                                                          sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), sl.ctr.as<unsigned long long>());
+        }
+        k_emit_hits<<<blocks_for(nhits, 256), 256, 0, st>>>(b->voffsets(), nv, per_seq, sl.hit_pos.as<uint32_t>(),
+                                                           sl.hit_payload.as<int4>(), (uint32_t)nhits, seq_base, r->d_hits.as<kg_hit>());
         launches += 2;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());

@@ -134,6 +134,49 @@ __global__ void k_prot_fill(DevUniverse u, uint64_t first, uint64_t n, uint64_t 
     }
 }
 
+// ---- genomes (configs[2]): genes = family consensus proteins back-translated with a uniformly chosen synonymous codon,
+// random strand, separated by random spacers; spacer bases are uniform ACGT; ~1e-5 of all bases become N ----
+__device__ __constant__ char c_gcode[65] = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
+__global__ void k_genome_background(uint8_t* __restrict__ out, uint64_t total, uint64_t seed) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint64_t h = hash3(seed ^ 0x77, i, 0);
+    out[i] = ((h >> 8) % 100000ull == 0) ? (uint8_t)'N' : (uint8_t)"ACGT"[h & 3];
+}
+struct GenePlan { // one gene: where it starts in the concatenated genome stream, which family, which strand
+    uint64_t start;
+    uint32_t family;
+    uint32_t minus;
+};
+__global__ void k_genome_genes(DevUniverse u, const GenePlan* __restrict__ plan, uint64_t ngenes, uint64_t seed,
+                               uint8_t* __restrict__ out) {
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per gene
+    const int lane = threadIdx.x & 31;
+    if (g >= ngenes) return;
+    const GenePlan gp = plan[g];
+    const uint32_t L = family_len(u, gp.family);
+    const char* alpha = "ACDEFGHIKLMNPQRSTVWY";
+    for (uint32_t c = lane; c < L; c += 32) {
+        const char aa = alpha[residue_code(u, gp.family, c)];
+        // the k-th codon (k uniform) among the codons of this residue in GENETIC_CODE order
+        uint32_t ncod = 0;
+        for (int i = 0; i < 64; i++) ncod += (c_gcode[i] == aa);
+        uint32_t k = (uint32_t)(hash3(seed ^ 0x88, g, c) % ncod), idx = 0;
+        for (int i = 0; i < 64; i++)
+            if (c_gcode[i] == aa) {
+                if (k == 0) { idx = i; break; }
+                k--;
+            }
+        const char nt[3] = {"ACGT"[idx >> 4], "ACGT"[(idx >> 2) & 3], "ACGT"[idx & 3]};
+        if (!gp.minus) {
+            for (int j = 0; j < 3; j++) out[gp.start + 3ull * c + j] = (uint8_t)nt[j];
+        } else { // reverse complement of the whole gene
+            const uint64_t end = gp.start + 3ull * L - 1;
+            for (int j = 0; j < 3; j++) out[end - (3ull * c + j)] = (uint8_t)"TGCA"[(nt[j] == 'A') ? 0 : (nt[j] == 'C') ? 1 : (nt[j] == 'G') ? 2 : 3];
+        }
+    }
+}
+
 // ---- reference-format image: linear probing without wrap over 24-byte slots (3 x uint64 words each).
 // Keys taken in home-slot order get the first free slot at or after their home:
 //   slot_r = max(slot_{r-1} + 1, home_r) = r + max_{q<=r}(home_q - q)   -- the layout sequential insertion in that order
@@ -331,6 +374,56 @@ extern "C" int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t
     cudaFree(d_lenq);
     *d_seq = seq;
     *d_off = off;
+    *total_bytes = total;
+    return KG_OK;
+}
+
+extern "C" int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t n_genomes, uint64_t length, uint64_t seed,
+                                uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes) {
+    if (!ctx || !u || !d_seq || !d_off || !total_bytes || length < 64) KG_FAIL(KG_EINVAL, "kg_synth_genomes: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevUniverse du;
+    uint32_t* d_lenq = nullptr;
+    KG_TRY(upload_universe(ctx, u, &du, &d_lenq));
+    // gene plan on the host (a few thousand genes per genome): spacer ~ 1 + geometric(mean 120), family uniform
+    std::vector<GenePlan> plan;
+    std::vector<uint64_t> off(n_genomes + 1);
+    uint64_t ctr = 0;
+    for (uint64_t gi = 0; gi < n_genomes; gi++) {
+        off[gi] = gi * length;
+        uint64_t pos = 0;
+        for (;;) {
+            const uint64_t h = hash3(seed ^ 0x99, gi, ctr++);
+            uint64_t gap = 1;
+            for (uint64_t r = h >> 20; gap < 2000 && (r % 120) != 0; r = smix64(r)) gap++;
+            const uint32_t fam = (uint32_t)((h >> 1) % u->n_families);
+            const uint32_t L = u->lenq[hash3(u->seed, fam, 0xFFFFFFFFull) & 4095];
+            pos += gap;
+            if (pos + 3ull * L > length) break;
+            plan.push_back(GenePlan{gi * length + pos, fam, (uint32_t)(h & 1)});
+            pos += 3ull * L;
+        }
+    }
+    off[n_genomes] = n_genomes * length;
+    const uint64_t total = n_genomes * length;
+    uint8_t* seq = nullptr;
+    uint64_t* doff = nullptr;
+    GenePlan* dplan = nullptr;
+    CU(cudaMalloc(&seq, total + 64));
+    CU(cudaMalloc(&doff, (n_genomes + 1) * 8));
+    CU(cudaMalloc(&dplan, std::max<size_t>(plan.size(), 1) * sizeof(GenePlan)));
+    CU(cudaMemsetAsync(seq + total, 0, 64, st));
+    CU(cudaMemcpyAsync(doff, off.data(), (n_genomes + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dplan, plan.data(), plan.size() * sizeof(GenePlan), cudaMemcpyHostToDevice, st));
+    k_genome_background<<<blocks_for(total, 256), 256, 0, st>>>(seq, total, seed);
+    if (!plan.empty()) k_genome_genes<<<blocks_for(plan.size() * 32, 256), 256, 0, st>>>(du, dplan, plan.size(), seed, seq);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaFree(dplan);
+    cudaFree(d_lenq);
+    *d_seq = seq;
+    *d_off = doff;
     *total_bytes = total;
     return KG_OK;
 }

@@ -211,3 +211,59 @@ def test_sliced_pipeline_matches_oracle(kg, ctx, oracle, universe, mode, monkeyp
     assert res.stats.num_launches > 30
     res.free()
     t.free()
+
+
+@pytest.mark.parametrize("fsm", ["seg", "seq"])
+@pytest.mark.parametrize("kat", KATS, ids=[k["name"] for k in KATS])
+def test_fsm_kats_both_paths(kg, ctx, kat, fsm, monkeypatch):
+    """Both run-FSM implementations (thread per sequence / thread per gap-delimited segment + OTU replay) against the
+    hand-traced vectors."""
+    monkeypatch.setenv("KG_FSM", fsm)
+    test_fsm_kats_on_gpu(kg, ctx, kat)
+
+
+@pytest.mark.parametrize("fsm", ["seg", "seq"])
+@pytest.mark.parametrize("flags", FLAGS)
+def test_parity_both_fsm_paths(kg, ctx, oracle, universe, flags, fsm, monkeypatch):
+    monkeypatch.setenv("KG_FSM", fsm)
+    u, img, _ = universe
+    t = ctx.table_from_image(img)
+    aa = u.proteins(300, seed=61) + [b"", b"ACDEFGHIK"]
+    sb, off = oracle.concat(aa)
+    res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1, **flags))
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True, **flags), sb, off, oracle.DIRECT_PROBE)
+    assert_same(res, ref, what=f"aa {fsm} {flags}")
+    res.free()
+    dna = [synth.genome(u, 40000, seed=62, index=i) for i in range(3)] + [b"", b"ACGT"]
+    sb, off = oracle.concat(dna)
+    res = ctx.run(t, kg.MODE_DNA, sb, off, kg.default_params(emit_hits=1, **flags))
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=False, **flags), sb, off, oracle.DIRECT_PROBE)
+    assert_same(res, ref, what=f"dna {fsm} {flags}")
+    res.free()
+    t.free()
+
+
+def test_otu_replay_many_otus(kg, ctx, oracle, monkeypatch):
+    """OTU top-5 buffer with more than five OTU indices in alternating and repeated order (overwrite + bubbling), through
+    the run-length replay of the segment path and through the per-sequence FSM."""
+    rng = np.random.default_rng(5)
+    L = 3000
+    prot = bytes(rng.choice(np.frombuffer(synth.PROT_ALPHA.encode(), np.uint8), L))
+    wk = synth.window_keys(synth.aa_codes(prot))
+    keys, first = np.unique(wk, return_index=True)
+    pos = np.sort(first)
+    n = len(pos)
+    otu = rng.integers(0, 9, size=n)
+    otu[::7] = otu[1::7][: len(otu[::7])]          # some immediate repeats
+    fI = np.where((pos // 400) % 2 == 0, 7, 9)      # function switches every 400 residues
+    img = synth.build_table_image(wk[pos], otu, np.full(n, 3), fI, np.full(n, 0.25, np.float32))
+    t = ctx.table_from_image(img)
+    sb, off = oracle.concat([prot, prot[100:2500], prot[::-1]])
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True), sb, off, oracle.DIRECT_PROBE)
+    assert int(ref.otus["n"][0]) == 5 and len(ref.calls) >= 8
+    for fsm in ("seg", "seq"):
+        monkeypatch.setenv("KG_FSM", fsm)
+        res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1))
+        assert_same(res, ref, what=f"otu {fsm}")
+        res.free()
+    t.free()
