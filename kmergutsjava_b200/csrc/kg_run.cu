@@ -87,23 +87,56 @@ __global__ void k_vlen(const uint64_t* __restrict__ off, uint64_t n, uint64_t* _
     vlen[v] = (nk + 1 + 3) & ~3ull; // residues + terminator, rounded up to 4 (all padding bytes are 0 = separator)
 }
 
-__global__ void k_translate(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off, uint64_t n, uint64_t total,
-                            const uint64_t* __restrict__ voff, uint8_t* __restrict__ vseq) {
-    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    uint64_t s = seq_of(off, n, g);
-    uint64_t p = g - off[s], L = off[s + 1] - off[s];
-    if (p + 3 > L) return;
-    int c1 = dna_code(seq[g]), c2 = dna_code(seq[g + 1]), c3 = dna_code(seq[g + 2]);
-    bool ok = (c1 | c2 | c3) < 4;
-    // forward strand: codon at p belongs to frame p%3, residue p/3 (KGJ:323-338)
-    uint8_t fw = ok ? (uint8_t)c_genetic_code[c1 * 16 + c2 * 4 + c3] : (uint8_t)'x';
-    vseq[voff[6 * s + p % 3] + p / 3] = fw;
-    // reverse strand: revComp (KGJ:263-272) puts compl(seq[p+2]), compl(seq[p+1]), compl(seq[p]) at q = L-3-p.
-    // compl() maps ACGTU (either case) to the complementary base and never maps anything else onto ACGTU.
-    uint64_t q = L - 3 - p;
-    uint8_t rv = ok ? (uint8_t)c_genetic_code[(3 - c3) * 16 + (3 - c2) * 4 + (3 - c1)] : (uint8_t)'x';
-    vseq[voff[6 * s + 3 + q % 3] + q / 3] = rv;
+// One thread per 4-byte word of the translated stream: it finds its virtual protein (binary search over the nv+1
+// offsets, which are multiples of 4), translates four consecutive codons of that frame and writes one aligned word --
+// residues, then the terminator / padding zeros (so the stream needs no memset).  Codon and amino-acid tables sit in
+// shared memory.  Forward frame f: codon j starts at nucleotide f+3j (KGJ:323-338).  Reverse frames are frames of the
+// reverse complement (KGJ:1068-1071): its base q is compl(seq[L-1-q]), and compl() maps ACGTU (either case) onto the
+// complementary base and never maps anything else onto ACGTU, so the complemented code is simply 3 - code.
+__global__ __launch_bounds__(256) void k_translate(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off, uint64_t n,
+                                                   const uint64_t* __restrict__ voff, uint64_t nv, uint64_t vwords,
+                                                   uint32_t* __restrict__ vseq_words) {
+    __shared__ uint8_t s_nt[256];   // dnaChar, KGJ:294-318
+    __shared__ char s_code[64];     // GENETIC_CODE, KGJ:88-93
+    s_nt[threadIdx.x] = (uint8_t)dna_code((uint8_t)threadIdx.x);
+    if (threadIdx.x < 64) s_code[threadIdx.x] = c_genetic_code[threadIdx.x];
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= vwords) return;
+    const uint64_t g = 4 * t;
+    const uint64_t v = seq_of(voff, nv, g);
+    const uint64_t sidx = v / 6;
+    const uint32_t k = (uint32_t)(v % 6), f = k % 3;
+    const bool rev = k >= 3;
+    const uint64_t base = off[sidx], L = off[sidx + 1] - base;
+    const uint64_t nk = L >= f + 3 ? (L - f) / 3 : 0;
+    const uint64_t j0 = g - voff[v];
+    uint32_t word = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint64_t j = j0 + r;
+        if (j < nk) {
+            const uint64_t p = f + 3 * j; // codon start in strand coordinates
+            int c1, c2, c3;
+            if (!rev) {
+                c1 = s_nt[seq[base + p]];
+                c2 = s_nt[seq[base + p + 1]];
+                c3 = s_nt[seq[base + p + 2]];
+            } else {
+                c1 = s_nt[seq[base + L - 1 - p]];
+                c2 = s_nt[seq[base + L - 2 - p]];
+                c3 = s_nt[seq[base + L - 3 - p]];
+                if ((c1 | c2 | c3) < 4) {
+                    c1 = 3 - c1;
+                    c2 = 3 - c2;
+                    c3 = 3 - c3;
+                }
+            }
+            const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[c1 * 16 + c2 * 4 + c3] : (uint32_t)'x';
+            word |= aa << (8 * r);
+        }
+    }
+    vseq_words[t] = word;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -529,34 +562,147 @@ __global__ void k_otu_replay(const uint32_t* __restrict__ lo, uint64_t nseq, int
     KgOtuBuf u;
     kg_otu_clear(u);
     int cur_oI = 0, cur_cnt = 0;
-    for (uint32_t i0 = a; i0 < b; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool f = i < b && flag[i] == 1;
-        const int oI = f ? hit_payload[i].x : 0;
-        const uint32_t M = __ballot_sync(0xFFFFFFFFu, f);
-        if (M == 0) continue;
-        const uint32_t lower = M & ((1u << lane) - 1u);
-        const int prev_lane = lower ? 31 - __clz(lower) : -1;
-        const int prev_oI = __shfl_sync(0xFFFFFFFFu, oI, prev_lane < 0 ? 0 : prev_lane);
-        const bool head = f && (prev_lane < 0 ? (cur_cnt == 0 || oI != cur_oI) : (oI != prev_oI));
-        uint32_t H = __ballot_sync(0xFFFFFFFFu, head);
-        if (H == 0) {
-            cur_cnt += __popc(M);
-            continue;
+    constexpr int DEPTH = 8; // batches of 32 hits whose loads are issued together (the walk is latency-bound otherwise)
+    for (uint32_t j0 = a; j0 < b; j0 += 32 * DEPTH) {
+        bool fk[DEPTH];
+        int ok[DEPTH];
+#pragma unroll
+        for (int k = 0; k < DEPTH; k++) {
+            const uint32_t i = j0 + 32 * k + lane;
+            fk[k] = i < b && flag[i] == 1;
         }
-        const int first_head = __ffs(H) - 1;
-        cur_cnt += __popc(M & ((1u << first_head) - 1u));
-        while (H) {
-            const int h = __ffs(H) - 1;
-            H &= H - 1;
-            const uint32_t upto = H ? ((1u << (__ffs(H) - 1)) - 1u) : 0xFFFFFFFFu;
-            if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
-            cur_oI = __shfl_sync(0xFFFFFFFFu, oI, h);
-            cur_cnt = __popc(M & upto & ~((1u << h) - 1u));
+#pragma unroll
+        for (int k = 0; k < DEPTH; k++) {
+            const uint32_t i = j0 + 32 * k + lane;
+            ok[k] = fk[k] ? reinterpret_cast<const int*>(hit_payload + i)[0] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < DEPTH; k++) {
+            const bool f = fk[k];
+            const int oI = ok[k];
+            const uint32_t M = __ballot_sync(0xFFFFFFFFu, f);
+            if (M == 0) continue;
+            const uint32_t lower = M & ((1u << lane) - 1u);
+            const int prev_lane = lower ? 31 - __clz(lower) : -1;
+            const int prev_oI = __shfl_sync(0xFFFFFFFFu, oI, prev_lane < 0 ? 0 : prev_lane);
+            const bool head = f && (prev_lane < 0 ? (cur_cnt == 0 || oI != cur_oI) : (oI != prev_oI));
+            uint32_t H = __ballot_sync(0xFFFFFFFFu, head);
+            if (H == 0) {
+                cur_cnt += __popc(M);
+                continue;
+            }
+            const int first_head = __ffs(H) - 1;
+            cur_cnt += __popc(M & ((1u << first_head) - 1u));
+            while (H) {
+                const int h = __ffs(H) - 1;
+                H &= H - 1;
+                const uint32_t upto = H ? ((1u << (__ffs(H) - 1)) - 1u) : 0xFFFFFFFFu;
+                if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
+                cur_oI = __shfl_sync(0xFFFFFFFFu, oI, h);
+                cur_cnt = __popc(M & upto & ~((1u << h) - 1u));
+            }
         }
     }
     if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
     if (lane == 0) {
+        kg_otu o;
+        o.n = u.n;
+#pragma unroll
+        for (int k = 0; k < KG_OI_BUFSZ; k++) {
+            o.count[k] = u.c[k];
+            o.oI[k] = u.o[k];
+        }
+        otus[s] = o;
+    }
+}
+
+// Same replay for FEW, LONG sequences (genomes): one block per sequence.  All 256 threads stream 2048 (counted?, OTU
+// index) pairs at a time into shared memory -- plenty of loads in flight -- and warp 0 folds them exactly as above.
+__global__ __launch_bounds__(256) void k_otu_replay_block(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq,
+                                                          const int4* __restrict__ hit_payload, const uint8_t* __restrict__ flag,
+                                                          kg_otu* __restrict__ otus, const unsigned long long* __restrict__ ctr) {
+    constexpr int CH = 2048, PER = CH / 256;
+    __shared__ int s_oi[CH];
+    __shared__ uint32_t s_mask[CH / 32];
+    __shared__ int s_first[CH / 32]; // OTU index of the first counted hit of the batch
+    __shared__ uint8_t s_uni[CH / 32]; // every counted hit of the batch has that same OTU index
+    const uint64_t s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (s >= nseq || ctr[KG_CTR_OVERFLOW]) return;
+    const uint32_t a = lo[s * per_seq], b = lo[(s + 1) * per_seq];
+    KgOtuBuf u;
+    kg_otu_clear(u);
+    int cur_oI = 0, cur_cnt = 0;
+    for (uint32_t c0 = a; c0 < b; c0 += CH) {
+        bool fk[PER];
+        int ok[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const uint32_t i = c0 + k * 256 + tid;
+            fk[k] = i < b && flag[i] == 1;
+        }
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const uint32_t i = c0 + k * 256 + tid;
+            ok[k] = fk[k] ? reinterpret_cast<const int*>(hit_payload + i)[0] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < PER; k++) { // every warp summarises its own batches; warp 0 then only walks the summaries
+            const int bt = (k * 256 + tid) >> 5;
+            s_oi[k * 256 + tid] = ok[k];
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, fk[k]);
+            const int first = __shfl_sync(0xFFFFFFFFu, ok[k], m ? __ffs(m) - 1 : 0);
+            const bool uni = __all_sync(0xFFFFFFFFu, !fk[k] || ok[k] == first);
+            if (lane == 0) {
+                s_mask[bt] = m;
+                s_first[bt] = first;
+                s_uni[bt] = uni;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t nb = min((uint32_t)(CH / 32), (b - c0 + 31) / 32);
+            for (uint32_t bt = 0; bt < nb; bt++) {
+                const uint32_t M = s_mask[bt];
+                if (M == 0) continue;
+                if (s_uni[bt]) { // the common case: one run (or part of one) per batch
+                    const int o = s_first[bt];
+                    if (cur_cnt && o == cur_oI) {
+                        cur_cnt += __popc(M);
+                    } else {
+                        if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
+                        cur_oI = o;
+                        cur_cnt = __popc(M);
+                    }
+                    continue;
+                }
+                const int oI = s_oi[bt * 32 + lane];
+                const bool f = (M >> lane) & 1u;
+                const uint32_t lower = M & ((1u << lane) - 1u);
+                const int prev_lane = lower ? 31 - __clz(lower) : -1;
+                const int prev_oI = __shfl_sync(0xFFFFFFFFu, oI, prev_lane < 0 ? 0 : prev_lane);
+                const bool head = f && (prev_lane < 0 ? (cur_cnt == 0 || oI != cur_oI) : (oI != prev_oI));
+                uint32_t H = __ballot_sync(0xFFFFFFFFu, head);
+                if (H == 0) {
+                    cur_cnt += __popc(M);
+                    continue;
+                }
+                const int first_head = __ffs(H) - 1;
+                cur_cnt += __popc(M & ((1u << first_head) - 1u));
+                while (H) {
+                    const int h = __ffs(H) - 1;
+                    H &= H - 1;
+                    const uint32_t upto = H ? ((1u << (__ffs(H) - 1)) - 1u) : 0xFFFFFFFFu;
+                    if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
+                    cur_oI = __shfl_sync(0xFFFFFFFFu, oI, h);
+                    cur_cnt = __popc(M & upto & ~((1u << h) - 1u));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
         kg_otu o;
         o.n = u.n;
 #pragma unroll
@@ -906,10 +1052,10 @@ int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches) {
         KG_TRY(need(&b->vseq, b->vtotal + 64));
         b->prepared = true;
     }
-    CU(cudaMemsetAsync(b->vseq.p, 0, b->vtotal + 64, st));
-    if (b->total) {
-        k_translate<<<blocks_for(b->total, 256), 256, 0, st>>>(b->d_seq, b->d_off, b->n, b->total, b->voff.as<uint64_t>(),
-                                                              b->vseq.as<uint8_t>());
+    CU(cudaMemsetAsync(b->vseq.as<uint8_t>() + b->vtotal, 0, 64, st)); // tail padding; every stream word is written below
+    if (b->vtotal) {
+        k_translate<<<blocks_for(b->vtotal / 4, 256), 256, 0, st>>>(b->d_seq, b->d_off, b->n, b->voff.as<uint64_t>(), b->nv,
+                                                                   b->vtotal / 4, b->vseq.as<uint32_t>());
         (*launches)++;
     }
     return KG_OK;
@@ -1036,7 +1182,12 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
         k_compact_calls_seg<<<blocks_for(cap, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(),
                                                                  sl.hit_v.as<uint32_t>(), sl.call_off.as<uint32_t>(), cap, per_seq, prm->min_hits,
                                                                  seq_base, r->d_calls.as<kg_call>());
-        if (b->n)
+        const char* otu_env = getenv("KG_OTU"); // tests force either replay kernel
+        const bool otu_block = otu_env ? strcmp(otu_env, "block") == 0 : b->n <= 4096;
+        if (b->n && otu_block) // few sequences: a block each; many: a warp each
+            k_otu_replay_block<<<(unsigned)b->n, 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.hit_payload.as<int4>(),
+                                                              sl.hit_flag.as<uint8_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+        else if (b->n)
             k_otu_replay<<<blocks_for(b->n * 32, 256), 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.hit_payload.as<int4>(),
                                                                     sl.hit_flag.as<uint8_t>(), r->d_otus.as<kg_otu>(), d_ctr);
         sl.launches += 8;
