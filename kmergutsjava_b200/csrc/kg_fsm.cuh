@@ -9,7 +9,9 @@
 //   last_match   hits.get(lastHit).from0InProt
 //   l1, l2       the last two list entries (gap test, order constraint, pair-switch test, retained pair)
 //   otu_t        the OTU buffer as it would be after replaying every counted hit of the open run (KGJ:413-438);
-//                committed to otu_c when the run is called, dropped otherwise
+//                committed to otu_c when the run is called, dropped otherwise.  Consecutive counted hits with the same
+//                OTU index are held back as (pend_oI, pend_cnt) and applied in one step (kg_otu_update_n: m updates of
+//                one index collapse exactly), which is what keeps this FSM off the instruction-issue limit
 // No list, no second pass, identical results (bit-exact, including the fp32 sum).
 #pragma once
 
@@ -60,6 +62,40 @@ __device__ __forceinline__ void kg_otu_update(KgOtuBuf& u, int oI) {
     }
 }
 
+// count += m for oI (m >= 1 consecutive updates of the same OTU index collapse exactly: the entry ends up in front of
+// the maximal block of entries ahead of it whose count is <= its final count, whether it got there in one step or m)
+__device__ __forceinline__ void kg_otu_update_n(KgOtuBuf& u, int oI, int m) {
+    int j = u.n;
+#pragma unroll
+    for (int i = KG_OI_BUFSZ - 1; i >= 0; i--)
+        if (i < u.n && u.o[i] == oI) j = i;
+    if (j == u.n) {
+        if (u.n == KG_OI_BUFSZ) j = KG_OI_BUFSZ - 1;
+        else u.n++;
+#pragma unroll
+        for (int i = 0; i < KG_OI_BUFSZ; i++)
+            if (i == j) {
+                u.o[i] = oI;
+                u.c[i] = m;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < KG_OI_BUFSZ; i++)
+            if (i == j) u.c[i] += m;
+    }
+#pragma unroll
+    for (int i = KG_OI_BUFSZ - 1; i >= 1; i--) {
+        if (i == j && u.c[i - 1] <= u.c[i]) {
+            int tc = u.c[i - 1], to = u.o[i - 1];
+            u.c[i - 1] = u.c[i];
+            u.o[i - 1] = u.o[i];
+            u.c[i] = tc;
+            u.o[i] = to;
+            j = i - 1;
+        }
+    }
+}
+
 struct KgFsmParams {
     int min_hits, max_gap, order_constraint;
     float min_weighted;
@@ -82,6 +118,7 @@ struct KgFsm {
     float w;
     KgHitLite l1, l2;
     KgOtuBuf otu_c, otu_t;
+    int pend_oI, pend_cnt;
     int consumed;       // HIT lines so far in this container
     int ncalls;
 
@@ -96,6 +133,16 @@ struct KgFsm {
         first_pos = last_match = 0;
         l1 = KgHitLite{0, 0, 0, 0, 0.f};
         l2 = l1;
+        pend_oI = pend_cnt = 0;
+    }
+    __device__ __forceinline__ void count_otu(int oI) {
+        if (pend_cnt && oI == pend_oI) {
+            pend_cnt++;
+        } else {
+            if (pend_cnt) kg_otu_update_n(otu_t, pend_oI, pend_cnt);
+            pend_oI = oI;
+            pend_cnt = 1;
+        }
     }
 
     __device__ __forceinline__ void append(const KgHitLite& h) {
@@ -104,6 +151,7 @@ struct KgFsm {
             cnt = 0;
             w = 0.f;
             otu_t = otu_c;
+            pend_cnt = 0;
         }
         n++;
         l2 = l1;
@@ -112,7 +160,7 @@ struct KgFsm {
             cnt++;
             w = __fadd_rn(w, h.wt);
             last_match = h.pos;
-            kg_otu_update(otu_t, h.oI);
+            count_otu(h.oI);
         }
     }
 
@@ -123,8 +171,10 @@ struct KgFsm {
             KgDevCall c = {first_pos, last_match + (KG_K - 1), cnt, cur, w, consumed};
             emit(ncalls, c);
             ncalls++;
+            if (pend_cnt) kg_otu_update_n(otu_t, pend_oI, pend_cnt);
             otu_c = otu_t; // the replay of KGJ:413-439 has already been done incrementally
         }
+        pend_cnt = 0;
         if (n >= 2 && l2.fI != cur && l2.fI == l1.fI) { // KGJ:442-449: the pair seeds the next run
             cur = l1.fI;
             n = 2;
@@ -133,8 +183,8 @@ struct KgFsm {
             w = __fadd_rn(__fadd_rn(0.f, l2.wt), l1.wt);
             last_match = l1.pos;
             otu_t = otu_c;
-            kg_otu_update(otu_t, l2.oI);
-            kg_otu_update(otu_t, l1.oI);
+            count_otu(l2.oI);
+            count_otu(l1.oI);
         } else {
             n = 0; // KGJ:452
         }
@@ -264,37 +314,3 @@ struct KgFsmSeg {
         if (n >= p.min_hits) process(p, emit, flag);
     }
 };
-
-// count += m for oI (m >= 1 consecutive updates of the same OTU index collapse exactly: the entry ends up in front of
-// the maximal block of entries ahead of it whose count is <= its final count, whether it got there in one step or m)
-__device__ __forceinline__ void kg_otu_update_n(KgOtuBuf& u, int oI, int m) {
-    int j = u.n;
-#pragma unroll
-    for (int i = KG_OI_BUFSZ - 1; i >= 0; i--)
-        if (i < u.n && u.o[i] == oI) j = i;
-    if (j == u.n) {
-        if (u.n == KG_OI_BUFSZ) j = KG_OI_BUFSZ - 1;
-        else u.n++;
-#pragma unroll
-        for (int i = 0; i < KG_OI_BUFSZ; i++)
-            if (i == j) {
-                u.o[i] = oI;
-                u.c[i] = m;
-            }
-    } else {
-#pragma unroll
-        for (int i = 0; i < KG_OI_BUFSZ; i++)
-            if (i == j) u.c[i] += m;
-    }
-#pragma unroll
-    for (int i = KG_OI_BUFSZ - 1; i >= 1; i--) {
-        if (i == j && u.c[i - 1] <= u.c[i]) {
-            int tc = u.c[i - 1], to = u.o[i - 1];
-            u.c[i - 1] = u.c[i];
-            u.o[i - 1] = u.o[i];
-            u.c[i] = tc;
-            u.o[i] = to;
-            j = i - 1;
-        }
-    }
-}
