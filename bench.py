@@ -39,7 +39,7 @@ def log(msg):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--families", type=int, default=2_000_000)
@@ -57,29 +57,38 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
+
+    def window(self, t0, t1):
+        """A timed region (wall-clock): only samples taken inside such windows are reported."""
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc:
+            time.sleep(0.06)
             self.proc.terminate()
-        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        rows = [r[1:] for r in self.rows if len(r) >= 7 and any(a - 0.05 <= r[0] <= b + 0.05 for a, b in self.windows)]
+        scope = "timed regions"
+        if len(rows) < 2:   # very short runs: fall back to everything sampled while the GPU was busy (warm-up included)
+            rows, scope = [r[1:] for r in self.rows if len(r) >= 7], "whole run incl. warm-up"
+        sm = [int(r[0]) for r in rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "scope": scope}
 
 
 def measured_peaks():
@@ -164,12 +173,13 @@ def run_ours(args):
     batch = ctx.batch_from_device(kg.MODE_AA, ds, do, args.proteins, total)
 
     # ---- device-resident throughput ----
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         ctx.run_batch(table, batch, params).free()
         log("warm-up step done")
-    clocks = ClockSampler(local)
-    clocks.start()
     barrier(torch, dist, local)
+    w0 = time.time()
     t0 = time.perf_counter()
     probe_ms, dev_ms, lookups, launches, st = [], [], 0, 0, None
     for _ in range(args.steps):
@@ -182,7 +192,7 @@ def run_ours(args):
         r.free()
     barrier(torch, dist, local)
     dt = all_max(torch, dist, time.perf_counter() - t0, local)
-    clk = clocks.stop()
+    clocks.window(w0, time.time())
     total_lookups = all_sum(torch, dist, float(lookups), local)
     total_proteins = float(args.proteins * args.steps * world)
     value = total_lookups / dt
@@ -199,6 +209,7 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):
             ctx.run_ptr(table, kg.MODE_AA, h_seq.data_ptr(), h_off.data_ptr(), args.proteins, params).free()
         barrier(torch, dist, local)
+        w0 = time.time()
         t0 = time.perf_counter()
         e_lookups = 0
         for _ in range(args.steps):
@@ -209,10 +220,12 @@ def run_ours(args):
             r.free()
         barrier(torch, dist, local)
         edt = all_max(torch, dist, time.perf_counter() - t0, local)
+        clocks.window(w0, time.time())
         e2e = {"value": all_sum(torch, dist, float(e_lookups), local) / edt, "unit": "lookups/s",
                "h2d_bytes_per_step": int(total + 8 * (args.proteins + 1)), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * edt / args.steps}
 
+    clk = clocks.stop()
     log("e2e done")
     # ---- rooflines ----
     hbm_peak, peak_src = measured_peaks()
@@ -223,8 +236,16 @@ def run_ours(args):
     if rank == 0:
         for tpb, infl in ((256, 4), (256, 8), (512, 4), (1024, 2), (128, 8)):
             r_probe = max(r_probe, ctx.probe_roofline_table(table, 1 << 28, tpb, infl))
+    traffic, traffic_src = None, None
+    try:    # dram__bytes_read.sum + dram__bytes_write.sum of k_probe from the committed `ncu --set full` capture of this workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj["signatures"] == int(nsig) and tj["proteins"] == args.proteins:
+            traffic, traffic_src = tj["k_probe_dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": round(achieved_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved_gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved_gbs / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": lookups_per_step * BYTES_PER_LOOKUP_AA, "peak_source": peak_src,
                 "kernel": "k_probe", "kernel_ms": round(probe_s * 1e3, 4),
                 "bytes_per_lookup": BYTES_PER_LOOKUP_AA, "lookups_per_launch": lookups_per_step,
                 "probe_roofline_sectors_per_s": r_probe,
