@@ -52,6 +52,15 @@ int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t n_genomes, 
 int kg_synth_reference_image(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, uint64_t n,
                              uint64_t min_slots, uint64_t* num_slots, void** d_image, double* mean_displacement);
 
+/* Size-independent cross-check of the probe path in protein mode: the most naive kernel possible (one thread per stream
+ * position, residues read byte by byte, unfiltered full table lookup).  out3 = {valid windows, hits, order-independent
+ * checksum over (stream position, payload) of all hits}.  d_seq must be the UNPATCHED protein bytes or the patched ones:
+ * the kernel applies the reference's aa-mode window rule (i < len - 8) from the offsets itself. */
+int kg_synth_naive_scan_aa(kg_context* ctx, const kg_table* table, const uint8_t* d_seq, const uint64_t* d_off, uint64_t n,
+                           uint64_t total, uint64_t* out3);
+/* The same checksum over kg_hit records (host array) of a run on those sequences. */
+int kg_synth_hits_checksum(kg_context* ctx, const kg_hit* host_hits, uint64_t nhits, const uint64_t* d_off, uint64_t* out);
+
 void kg_device_free(void* d_ptr);
 int kg_device_to_host(kg_context* ctx, void* host, const void* dev, uint64_t bytes);
 

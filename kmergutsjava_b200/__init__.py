@@ -34,7 +34,7 @@ EXPORTS = [
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
     "kg_functions_load", "kg_functions_read", "kg_functions_count", "kg_functions_name", "kg_functions_free",
     "kg_format_java_f", "kg_report_write", "kg_main",
-    "kg_synth_signatures", "kg_synth_proteins", "kg_synth_genomes", "kg_synth_reference_image", "kg_device_free", "kg_device_to_host",
+    "kg_synth_signatures", "kg_synth_proteins", "kg_synth_genomes", "kg_synth_reference_image", "kg_synth_naive_scan_aa", "kg_synth_hits_checksum", "kg_device_free", "kg_device_to_host",
     "kg_probe_roofline", "kg_probe_roofline_table",
 ]
 
@@ -107,6 +107,8 @@ def lib() -> C.CDLL:
         "kg_synth_proteins": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_genomes": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, C.POINTER(u64), pp, C.POINTER(C.c_double)]),
+        "kg_synth_naive_scan_aa": (i32, [vp, vp, vp, vp, u64, u64, vp]),
+        "kg_synth_hits_checksum": (i32, [vp, vp, u64, vp, C.POINTER(u64)]),
         "kg_device_free": (None, [vp]), "kg_device_to_host": (i32, [vp, vp, vp, u64]),
         "kg_probe_roofline": (i32, [vp, u64, u64, i32, i32, C.POINTER(C.c_double)]),
         "kg_probe_roofline_table": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_double)]),
@@ -354,6 +356,20 @@ def synth_reference_image(ctx: Context, d_keys: int, d_payload: int, n: int, min
         return ctx.to_host(dimg.value, 24 + 24 * ns.value)
     finally:
         device_free(dimg.value)
+
+
+def naive_scan_aa(ctx: Context, table: Table, d_seq: int, d_off: int, n: int, total: int):
+    """(valid windows, hits, checksum) by the naive one-thread-per-position kernel."""
+    out = (C.c_uint64 * 3)()
+    _check(lib().kg_synth_naive_scan_aa(ctx._h, table._h, d_seq, d_off, n, total, out))
+    return int(out[0]), int(out[1]), int(out[2])
+
+
+def hits_checksum(ctx: Context, hits: np.ndarray, d_off: int) -> int:
+    hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
+    out = C.c_uint64()
+    _check(lib().kg_synth_hits_checksum(ctx._h, hits.ctypes.data, len(hits), d_off, C.byref(out)))
+    return int(out.value)
 
 
 def device_free(ptr):

@@ -234,6 +234,73 @@ __global__ void k_image_place(const uint32_t* __restrict__ home, const uint32_t*
     }
 }
 
+// ---- size-independent cross-check of the probe path (tests / bench): the most naive kernel possible -- one thread per
+// protein-stream position, residues re-read byte by byte, full unfiltered table lookup -- counts the valid windows, the
+// hits, and a checksum over (position, payload) that the pipeline's hit records must reproduce ----
+__global__ void k_naive_scan(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off, uint64_t n, uint64_t total,
+                             KgTableView tab, unsigned long long* __restrict__ out) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long valid = 0, hit = 0, sum = 0;
+    if (g < total) {
+        // sequence of g by binary search; aa-mode rule of the reference: windows i with i < len - 8 (KGJ:912, 1055)
+        uint64_t lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (off[mid] <= g) lo = mid;
+            else hi = mid;
+        }
+        const uint64_t i = g - off[lo], len = off[lo + 1] - off[lo];
+        if (len > 8 && i < len - 8) {
+            uint64_t key = 0;
+            bool ok = true;
+            for (int k = 0; k < 8; k++) {
+                const uint8_t ch = seq[g + k];
+                int code = 20;
+                const char* alpha = "ACDEFGHIKLMNPQRSTVWY";
+                for (int a = 0; a < 20; a++)
+                    if (alpha[a] == (char)ch) code = a;
+                if (code >= 20) ok = false;
+                key = key * 20 + (uint64_t)code;
+            }
+            if (ok) {
+                valid = 1;
+                const uint32_t slot = kg_lookup(tab, key);
+                if (slot != 0xFFFFFFFFu) {
+                    const int4 p = kg_load_payload(tab.lines, slot);
+                    hit = 1;
+                    sum = smix64(g * 0x9E3779B97F4A7C15ull ^ (uint64_t)(uint32_t)p.x ^ ((uint64_t)(uint32_t)p.z << 32)) ^
+                          smix64(((uint64_t)(uint32_t)p.y << 32) | (uint32_t)p.w);
+                }
+            }
+        }
+    }
+    // block reduction: sums of valid / hit, XOR... use wrapping sum for the checksum so order does not matter
+    for (int d = 16; d; d >>= 1) {
+        valid += __shfl_xor_sync(0xFFFFFFFFu, valid, d);
+        hit += __shfl_xor_sync(0xFFFFFFFFu, hit, d);
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (valid) atomicAdd(&out[0], valid);
+        if (hit) atomicAdd(&out[1], hit);
+        if (sum) atomicAdd(&out[2], sum);
+    }
+}
+// the same checksum over hit records (seq-relative positions are turned back into stream positions with the offsets)
+__global__ void k_hits_checksum(const kg_hit* __restrict__ hits, uint64_t nhits, const uint64_t* __restrict__ off,
+                                unsigned long long* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sum = 0;
+    if (i < nhits) {
+        const kg_hit h = hits[i];
+        const uint64_t g = off[h.seq] + (uint64_t)h.pos;
+        sum = smix64(g * 0x9E3779B97F4A7C15ull ^ (uint64_t)(uint32_t)h.oI ^ ((uint64_t)(uint32_t)h.fI << 32)) ^
+              smix64(((uint64_t)(uint32_t)h.avg_off_from_end << 32) | (uint32_t)__float_as_int(h.function_wt));
+    }
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&out[0], sum);
+}
+
 // ---- R_probe ----
 template <int U>
 __global__ void k_random_sectors(const uint4* __restrict__ buf, uint64_t n_sectors, uint32_t per_thread, uint32_t* __restrict__ sink) {
@@ -425,6 +492,39 @@ extern "C" int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t 
     *d_seq = seq;
     *d_off = doff;
     *total_bytes = total;
+    return KG_OK;
+}
+
+extern "C" int kg_synth_naive_scan_aa(kg_context* ctx, const kg_table* table, const uint8_t* d_seq, const uint64_t* d_off, uint64_t n,
+                                      uint64_t total, uint64_t* out3) {
+    if (!ctx || !table || !d_off || !out3) KG_FAIL(KG_EINVAL, "kg_synth_naive_scan_aa: null argument");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, 24));
+    CU(cudaMemsetAsync(d, 0, 24, ctx->stream));
+    if (total) k_naive_scan<<<blocks_for(total, 256), 256, 0, ctx->stream>>>(d_seq, d_off, n, total, table->view(), d);
+    CU(cudaMemcpyAsync(out3, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    cudaFree(d);
+    return KG_OK;
+}
+
+extern "C" int kg_synth_hits_checksum(kg_context* ctx, const kg_hit* host_hits, uint64_t nhits, const uint64_t* d_off, uint64_t* out) {
+    if (!ctx || !out || (nhits && !host_hits)) KG_FAIL(KG_EINVAL, "kg_synth_hits_checksum: null argument");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    kg_hit* dh = nullptr;
+    CU(cudaMalloc(&d, 8));
+    CU(cudaMalloc(&dh, std::max<uint64_t>(nhits, 1) * sizeof(kg_hit)));
+    CU(cudaMemsetAsync(d, 0, 8, ctx->stream));
+    CU(cudaMemcpyAsync(dh, host_hits, nhits * sizeof(kg_hit), cudaMemcpyHostToDevice, ctx->stream));
+    if (nhits) k_hits_checksum<<<blocks_for(nhits, 256), 256, 0, ctx->stream>>>(dh, nhits, d_off, d);
+    CU(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    cudaFree(d);
+    cudaFree(dh);
     return KG_OK;
 }
 

@@ -80,3 +80,40 @@ def test_device_pipeline_on_device_generated_inputs(kg, ctx, oracle):
 def test_probe_roofline_runs(kg, ctx):
     r = ctx.probe_roofline(256 << 20, 1 << 24, 256, 4)
     assert r > 1e9
+
+
+def test_full_size_properties_against_naive_kernel(kg, ctx):
+    """Size-independent parity at a size the CPU oracle would take minutes for: the pipeline's lookup count, hit count and
+    an order-independent checksum over (position, payload) of every hit must equal those of the naive one-thread-per-
+    position kernel (byte-wise residue reads, no prefilter, no queue, full table lookup).  Also: running twice changes nothing."""
+    u = synth.Universe(n_families=40000, seed=0x4B47000C)
+    dk, dp, n = kg.synth_signatures(ctx, u, 0)
+    table = ctx.table_from_device_entries(dk, dp, n)
+    nprot = 100000
+    ds, do, total = kg.synth_proteins(ctx, u, 0, nprot, 5)
+    valid, hits, chk = kg.naive_scan_aa(ctx, table, ds, do, nprot, total)
+    assert valid > 0.9 * total - 9 * nprot and hits > 0.05 * valid
+    batch = ctx.batch_from_device(kg.MODE_AA, ds, do, nprot, total)
+    first = None
+    for _ in range(2):
+        res = ctx.run_batch(table, batch, kg.default_params(emit_hits=1))
+        st = res.stats
+        assert (st.num_kmers, st.num_hits) == (valid, hits)
+        h = res.hits
+        assert len(h) == hits
+        assert kg.hits_checksum(ctx, h, do) == chk
+        key = (h["seq"].astype(np.int64) << 32) | h["pos"].astype(np.int64)
+        assert np.all(np.diff(key) > 0)                       # sorted by (sequence, position), no duplicates
+        calls = res.calls
+        ck = (calls["seq"].astype(np.int64) << 32) | calls["start"].astype(np.int64)
+        assert np.all(np.diff(ck) > 0) and np.all(calls["count"] >= 5) and np.all(calls["end"] >= calls["start"] + 7)
+        sig = (len(calls), int(calls["count"].sum()), float(calls["weighted"].astype(np.float64).sum()), int(res.otus["n"].sum()))
+        assert first is None or sig == first                  # idempotent
+        first = sig
+        res.free()
+    # the naive scan does not care whether the batch has been patched (last residue -> 0) or not
+    assert kg.naive_scan_aa(ctx, table, ds, do, nprot, total) == (valid, hits, chk)
+    batch.free()
+    table.free()
+    for p in (dk, dp, ds, do):
+        kg.device_free(p)
