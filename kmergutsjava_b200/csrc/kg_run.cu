@@ -792,12 +792,20 @@ int pool_take_dev(kg_context* ctx, size_t bytes, DevBuf* out) {
         ctx->dev_pool.erase(ctx->dev_pool.begin() + best);
         return KG_OK;
     }
+    // size classes (next power of two, refined to eighths) so that slices of slightly different sizes reuse each other's
+    // buffers: a cudaMalloc / cudaFree inside a run synchronises the device
+    size_t cls = 256;
+    while (cls < bytes) cls <<= 1;
+    if (cls >= 2048) {
+        const size_t eighth = cls >> 4; // refine within [cls/2, cls] in steps of cls/16
+        cls = (bytes + eighth - 1) / eighth * eighth;
+    }
     *out = DevBuf();
-    return out->ensure(std::max<size_t>(bytes, 256));
+    return out->ensure(cls);
 }
 void pool_give_dev(kg_context* ctx, DevBuf* b) {
     if (!b->p) return;
-    if (ctx->dev_pool.size() >= 12) { // keep the pool bounded: drop the smallest
+    if (ctx->dev_pool.size() >= 64) { // keep the pool bounded: drop the smallest
         size_t k = 0;
         for (size_t i = 1; i < ctx->dev_pool.size(); i++)
             if (ctx->dev_pool[i].cap < ctx->dev_pool[k].cap) k = i;
@@ -829,7 +837,7 @@ int pool_take_host(kg_context* ctx, size_t bytes, HostBuf* out) {
 }
 void pool_give_host(kg_context* ctx, HostBuf* b) {
     if (!b->p) return;
-    if (ctx->host_pool.size() >= 12) {
+    if (ctx->host_pool.size() >= 32) {
         size_t k = 0;
         for (size_t i = 1; i < ctx->host_pool.size(); i++)
             if (ctx->host_pool[i].cap < ctx->host_pool[k].cap) k = i;
@@ -1321,10 +1329,13 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     if (const char* e = getenv("KG_SLICE_MB")) target = (uint64_t)atoll(e) << 20;
     if (target < 65536) target = 65536;
     const uint64_t hard = mode == KG_MODE_AA ? KG_MAX_STREAM : KG_MAX_STREAM / 2 - 64 * (uint64_t)n; // dna: 2 residues per nucleotide
+    // the first slices are small (target/8, /4, /2): nothing can overlap the very first upload, so keep it short
     std::vector<size_t> cut{0};
+    uint64_t step = std::max<uint64_t>(target / 8, std::min<uint64_t>(target, 2ull << 20));
     for (size_t i = 0; i < n;) {
         size_t j = i;
-        while (j < n && (j == i || offsets[j + 1] - offsets[i] <= target)) j++;
+        while (j < n && (j == i || offsets[j + 1] - offsets[i] <= step)) j++;
+        step = std::min<uint64_t>(step * 2, target);
         if (offsets[j] - offsets[i] > hard) KG_FAIL(KG_ERANGE, "kg_run: sequence %zu alone exceeds the per-call limit", i);
         cut.push_back(j);
         i = j;
