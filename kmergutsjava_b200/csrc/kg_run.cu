@@ -549,169 +549,79 @@ __global__ void k_compact_calls_seg(const KgDevCall* __restrict__ sparse, const 
         out[o + k] = r;
     }
 }
-// OTU-COUNTS of one sequence: replay, in order, the OTU index of every hit a CALL counted (KGJ:413-438).  One warp
-// per sequence reads 32 hits at a time; runs of equal OTU indices are collapsed (kg_otu_update_n), so the sequential
-// part of the work is one update per run, not per hit.
-__global__ void k_otu_replay(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const int4* __restrict__ hit_payload,
-                             const uint8_t* __restrict__ flag, kg_otu* __restrict__ otus,
-                             const unsigned long long* __restrict__ ctr) {
-    const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (s >= nseq || ctr[KG_CTR_OVERFLOW]) return;
-    const uint32_t a = lo[s * per_seq], b = lo[(s + 1) * per_seq];
-    KgOtuBuf u;
-    kg_otu_clear(u);
-    int cur_oI = 0, cur_cnt = 0;
-    constexpr int DEPTH = 8; // batches of 32 hits whose loads are issued together (the walk is latency-bound otherwise)
-    for (uint32_t j0 = a; j0 < b; j0 += 32 * DEPTH) {
-        bool fk[DEPTH];
-        int ok[DEPTH];
-#pragma unroll
-        for (int k = 0; k < DEPTH; k++) {
-            const uint32_t i = j0 + 32 * k + lane;
-            fk[k] = i < b && flag[i] == 1;
-        }
-#pragma unroll
-        for (int k = 0; k < DEPTH; k++) {
-            const uint32_t i = j0 + 32 * k + lane;
-            ok[k] = fk[k] ? reinterpret_cast<const int*>(hit_payload + i)[0] : 0;
-        }
-#pragma unroll
-        for (int k = 0; k < DEPTH; k++) {
-            const bool f = fk[k];
-            const int oI = ok[k];
-            const uint32_t M = __ballot_sync(0xFFFFFFFFu, f);
-            if (M == 0) continue;
-            const uint32_t lower = M & ((1u << lane) - 1u);
-            const int prev_lane = lower ? 31 - __clz(lower) : -1;
-            const int prev_oI = __shfl_sync(0xFFFFFFFFu, oI, prev_lane < 0 ? 0 : prev_lane);
-            const bool head = f && (prev_lane < 0 ? (cur_cnt == 0 || oI != cur_oI) : (oI != prev_oI));
-            uint32_t H = __ballot_sync(0xFFFFFFFFu, head);
-            if (H == 0) {
-                cur_cnt += __popc(M);
-                continue;
-            }
-            const int first_head = __ffs(H) - 1;
-            cur_cnt += __popc(M & ((1u << first_head) - 1u));
-            while (H) {
-                const int h = __ffs(H) - 1;
-                H &= H - 1;
-                const uint32_t upto = H ? ((1u << (__ffs(H) - 1)) - 1u) : 0xFFFFFFFFu;
-                if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
-                cur_oI = __shfl_sync(0xFFFFFFFFu, oI, h);
-                cur_cnt = __popc(M & upto & ~((1u << h) - 1u));
-            }
-        }
-    }
-    if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
-    if (lane == 0) {
-        kg_otu o;
-        o.n = u.n;
-#pragma unroll
-        for (int k = 0; k < KG_OI_BUFSZ; k++) {
-            o.count[k] = u.c[k];
-            o.oI[k] = u.o[k];
-        }
-        otus[s] = o;
-    }
+// OTU-COUNTS (KGJ:413-438, 516-524): replay, in order, the OTU index of every hit a CALL counted.  Only the fold of the
+// five-entry buffer is inherently sequential, so everything else is done grid-wide first: the counted hits are run-length
+// encoded in parallel (a run = consecutive counted hits of one sequence with the same OTU index; m updates of one index
+// collapse exactly, kg_otu_update_n), and one thread per sequence then folds its runs -- one update per run, typically
+// one per gene, instead of one per hit.
+//   k_otu_prep   per hit: counted?, OTU index, (index+1 if counted)           -> max-scan = previous counted hit,
+//                                                                                sum-scan = rank among the counted hits
+//   k_otu_heads  per counted hit: does it start a run?                         -> sum-scan = run index
+//   k_otu_runs   per run head: (OTU index, counted-rank at the run start)
+//   k_otu_fold   per sequence: runs [hrank[a], hrank[b]) with lengths from the counted-ranks
+__global__ void k_otu_prep(const uint8_t* __restrict__ flag, const int4* __restrict__ hit_payload, const uint32_t* __restrict__ tile_out,
+                           uint32_t ntiles, uint32_t cap1, int* __restrict__ oi, uint32_t* __restrict__ cidx, uint32_t* __restrict__ c01,
+                           const unsigned long long* __restrict__ ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap1) return;
+    const uint32_t nhits = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
+    const bool c = i < nhits && flag[i] == 1;
+    oi[i] = c ? reinterpret_cast<const int*>(hit_payload + i)[0] : 0;
+    cidx[i] = c ? i + 1 : 0;
+    c01[i] = c;
 }
-
-// Same replay for FEW, LONG sequences (genomes): one block per sequence.  All 256 threads stream 2048 (counted?, OTU
-// index) pairs at a time into shared memory -- plenty of loads in flight -- and warp 0 folds them exactly as above.
-__global__ __launch_bounds__(256) void k_otu_replay_block(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq,
-                                                          const int4* __restrict__ hit_payload, const uint8_t* __restrict__ flag,
-                                                          kg_otu* __restrict__ otus, const unsigned long long* __restrict__ ctr) {
-    constexpr int CH = 2048, PER = CH / 256;
-    __shared__ int s_oi[CH];
-    __shared__ uint32_t s_mask[CH / 32];
-    __shared__ int s_first[CH / 32]; // OTU index of the first counted hit of the batch
-    __shared__ uint8_t s_uni[CH / 32]; // every counted hit of the batch has that same OTU index
-    const uint64_t s = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31;
+struct MaxU32 {
+    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+__global__ void k_otu_heads(const uint32_t* __restrict__ c01, const uint32_t* __restrict__ prevc, const int* __restrict__ oi,
+                            const uint32_t* __restrict__ hit_v, const uint32_t* __restrict__ lo, int per_seq, uint32_t cap1,
+                            uint32_t* __restrict__ head01) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap1) return;
+    uint32_t head = 0;
+    if (c01[i]) {
+        const uint32_t p = prevc[i]; // index + 1 of the previous counted hit, 0 = none
+        const uint32_t a = lo[(hit_v[i] / (uint32_t)per_seq) * (uint32_t)per_seq]; // first hit of this sequence
+        head = p == 0 || p - 1 < a || oi[p - 1] != oi[i];
+    }
+    head01[i] = head;
+}
+__global__ void k_otu_runs(const uint32_t* __restrict__ head01, const uint32_t* __restrict__ hrank, const uint32_t* __restrict__ crank,
+                           const int* __restrict__ oi, uint32_t cap1, int* __restrict__ run_oi, uint32_t* __restrict__ run_crank) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap1 || !head01[i]) return;
+    const uint32_t r = hrank[i];
+    run_oi[r] = oi[i];
+    run_crank[r] = crank[i];
+}
+__global__ void k_otu_fold(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const uint32_t* __restrict__ hrank,
+                           const uint32_t* __restrict__ crank, const int* __restrict__ run_oi, const uint32_t* __restrict__ run_crank,
+                           kg_otu* __restrict__ otus, const unsigned long long* __restrict__ ctr) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseq || ctr[KG_CTR_OVERFLOW]) return;
     const uint32_t a = lo[s * per_seq], b = lo[(s + 1) * per_seq];
+    const uint32_t r0 = hrank[a], r1 = hrank[b], cend = crank[b]; // exclusive scans: "before index"
     KgOtuBuf u;
     kg_otu_clear(u);
-    int cur_oI = 0, cur_cnt = 0;
-    for (uint32_t c0 = a; c0 < b; c0 += CH) {
-        bool fk[PER];
-        int ok[PER];
+    for (uint32_t r = r0; r < r1; r += 8) { // eight runs per memory round trip: the loads do not depend on the buffer state
+        int o8[8];
+        uint32_t c9[9];
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const uint32_t i = c0 + k * 256 + tid;
-            fk[k] = i < b && flag[i] == 1;
-        }
+        for (int k = 0; k < 8; k++) o8[k] = run_oi[min(r + k, r1 - 1)];
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const uint32_t i = c0 + k * 256 + tid;
-            ok[k] = fk[k] ? reinterpret_cast<const int*>(hit_payload + i)[0] : 0;
-        }
+        for (int k = 0; k < 9; k++) c9[k] = r + k < r1 ? run_crank[r + k] : cend;
 #pragma unroll
-        for (int k = 0; k < PER; k++) { // every warp summarises its own batches; warp 0 then only walks the summaries
-            const int bt = (k * 256 + tid) >> 5;
-            s_oi[k * 256 + tid] = ok[k];
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, fk[k]);
-            const int first = __shfl_sync(0xFFFFFFFFu, ok[k], m ? __ffs(m) - 1 : 0);
-            const bool uni = __all_sync(0xFFFFFFFFu, !fk[k] || ok[k] == first);
-            if (lane == 0) {
-                s_mask[bt] = m;
-                s_first[bt] = first;
-                s_uni[bt] = uni;
-            }
-        }
-        __syncthreads();
-        if (tid < 32) {
-            const uint32_t nb = min((uint32_t)(CH / 32), (b - c0 + 31) / 32);
-            for (uint32_t bt = 0; bt < nb; bt++) {
-                const uint32_t M = s_mask[bt];
-                if (M == 0) continue;
-                if (s_uni[bt]) { // the common case: one run (or part of one) per batch
-                    const int o = s_first[bt];
-                    if (cur_cnt && o == cur_oI) {
-                        cur_cnt += __popc(M);
-                    } else {
-                        if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
-                        cur_oI = o;
-                        cur_cnt = __popc(M);
-                    }
-                    continue;
-                }
-                const int oI = s_oi[bt * 32 + lane];
-                const bool f = (M >> lane) & 1u;
-                const uint32_t lower = M & ((1u << lane) - 1u);
-                const int prev_lane = lower ? 31 - __clz(lower) : -1;
-                const int prev_oI = __shfl_sync(0xFFFFFFFFu, oI, prev_lane < 0 ? 0 : prev_lane);
-                const bool head = f && (prev_lane < 0 ? (cur_cnt == 0 || oI != cur_oI) : (oI != prev_oI));
-                uint32_t H = __ballot_sync(0xFFFFFFFFu, head);
-                if (H == 0) {
-                    cur_cnt += __popc(M);
-                    continue;
-                }
-                const int first_head = __ffs(H) - 1;
-                cur_cnt += __popc(M & ((1u << first_head) - 1u));
-                while (H) {
-                    const int h = __ffs(H) - 1;
-                    H &= H - 1;
-                    const uint32_t upto = H ? ((1u << (__ffs(H) - 1)) - 1u) : 0xFFFFFFFFu;
-                    if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
-                    cur_oI = __shfl_sync(0xFFFFFFFFu, oI, h);
-                    cur_cnt = __popc(M & upto & ~((1u << h) - 1u));
-                }
-            }
-        }
-        __syncthreads();
+        for (int k = 0; k < 8; k++)
+            if (r + k < r1) kg_otu_update_n(u, o8[k], (int)(c9[k + 1] - c9[k]));
     }
-    if (tid == 0) {
-        if (cur_cnt) kg_otu_update_n(u, cur_oI, cur_cnt);
-        kg_otu o;
-        o.n = u.n;
+    kg_otu o;
+    o.n = u.n;
 #pragma unroll
-        for (int k = 0; k < KG_OI_BUFSZ; k++) {
-            o.count[k] = u.c[k];
-            o.oI[k] = u.o[k];
-        }
-        otus[s] = o;
+    for (int k = 0; k < KG_OI_BUFSZ; k++) {
+        o.count[k] = u.c[k];
+        o.oI[k] = u.o[k];
     }
+    otus[s] = o;
 }
 
 __global__ void k_compact_calls(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ lo,
@@ -759,6 +669,7 @@ struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them le
     DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
     DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
     DevBuf hit_v, seg_flag, seg_id, seg_begin, hit_flag, nseg;    // segment path
+    DevBuf o_oi, o_cidx, o_c01, o_prevc, o_crank, o_head, o_hrank, o_run_oi, o_run_crank; // segment path: OTU run-length encoding
     bool seg = false;                                            // which FSM path the enqueued run uses
     uint64_t* h_ctr = nullptr; // pinned, KG_CTR_COUNT + 1 (the last slot receives the call total)
     cudaEvent_t ev[4] = {};    // begin, probe begin, probe end, end
@@ -920,7 +831,8 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
                           &sl.call_off, &sl.ctr, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
-                          &sl.hit_flag, &sl.nseg})
+                          &sl.hit_flag, &sl.nseg, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_prevc, &sl.o_crank, &sl.o_head, &sl.o_hrank,
+                          &sl.o_run_oi, &sl.o_run_crank})
             b->release();
         if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
         for (auto& e : sl.ev)
@@ -1190,15 +1102,27 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
         k_compact_calls_seg<<<blocks_for(cap, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(),
                                                                  sl.hit_v.as<uint32_t>(), sl.call_off.as<uint32_t>(), cap, per_seq, prm->min_hits,
                                                                  seq_base, r->d_calls.as<kg_call>());
-        const char* otu_env = getenv("KG_OTU"); // tests force either replay kernel
-        const bool otu_block = otu_env ? strcmp(otu_env, "block") == 0 : b->n <= 4096;
-        if (b->n && otu_block) // few sequences: a block each; many: a warp each
-            k_otu_replay_block<<<(unsigned)b->n, 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.hit_payload.as<int4>(),
-                                                              sl.hit_flag.as<uint8_t>(), r->d_otus.as<kg_otu>(), d_ctr);
-        else if (b->n)
-            k_otu_replay<<<blocks_for(b->n * 32, 256), 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.hit_payload.as<int4>(),
-                                                                    sl.hit_flag.as<uint8_t>(), r->d_otus.as<kg_otu>(), d_ctr);
-        sl.launches += 8;
+        { // OTU-COUNTS: parallel run-length encoding of the counted hits, then one thread per sequence folds its runs
+            const uint32_t cap1 = cap + 1; // index cap = "one past the last hit": the exclusive scans are read there too
+            for (DevBuf* d : {&sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_prevc, &sl.o_crank, &sl.o_head, &sl.o_hrank, &sl.o_run_oi, &sl.o_run_crank})
+                KG_TRY(d->ensure((size_t)cap1 * 4));
+            k_otu_prep<<<blocks_for(cap1, 256), 256, 0, st>>>(sl.hit_flag.as<uint8_t>(), sl.hit_payload.as<int4>(), sl.tile_out.as<uint32_t>(), ntiles,
+                                                             cap1, sl.o_oi.as<int>(), sl.o_cidx.as<uint32_t>(), sl.o_c01.as<uint32_t>(), d_ctr);
+            size_t tb = 0;
+            CU(cub::DeviceScan::ExclusiveScan(nullptr, tb, sl.o_cidx.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), MaxU32(), 0u, (size_t)cap1, st));
+            KG_TRY(ctx->scan_tmp.ensure(tb));
+            CU(cub::DeviceScan::ExclusiveScan(ctx->scan_tmp.p, tb, sl.o_cidx.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), MaxU32(), 0u, (size_t)cap1, st));
+            KG_TRY(exclusive_sum_u32(ctx, sl.o_c01.as<uint32_t>(), sl.o_crank.as<uint32_t>(), cap1, st));
+            k_otu_heads<<<blocks_for(cap1, 256), 256, 0, st>>>(sl.o_c01.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), sl.o_oi.as<int>(), sl.hit_v.as<uint32_t>(),
+                                                              sl.lo.as<uint32_t>(), per_seq, cap1, sl.o_head.as<uint32_t>());
+            KG_TRY(exclusive_sum_u32(ctx, sl.o_head.as<uint32_t>(), sl.o_hrank.as<uint32_t>(), cap1, st));
+            k_otu_runs<<<blocks_for(cap1, 256), 256, 0, st>>>(sl.o_head.as<uint32_t>(), sl.o_hrank.as<uint32_t>(), sl.o_crank.as<uint32_t>(),
+                                                             sl.o_oi.as<int>(), cap1, sl.o_run_oi.as<int>(), sl.o_run_crank.as<uint32_t>());
+            if (b->n)
+                k_otu_fold<<<blocks_for(b->n, 64), 64, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.o_hrank.as<uint32_t>(), sl.o_crank.as<uint32_t>(),
+                                                               sl.o_run_oi.as<int>(), sl.o_run_crank.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+        }
+        sl.launches += 14;
         CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + cap, 4, cudaMemcpyDeviceToHost, st));
     }
     cudaEventRecord(sl.ev[3], st);
