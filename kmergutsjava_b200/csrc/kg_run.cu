@@ -101,10 +101,15 @@ __global__ __launch_bounds__(256) void k_translate(const uint8_t* __restrict__ s
     s_nt[threadIdx.x] = (uint8_t)dna_code((uint8_t)threadIdx.x);
     if (threadIdx.x < 64) s_code[threadIdx.x] = c_genetic_code[threadIdx.x];
     __syncthreads();
+    // the block's 256 words almost always lie in one virtual protein: search once per block, then step forward
+    __shared__ uint64_t s_v0;
+    if (threadIdx.x == 0) s_v0 = seq_of(voff, nv, 4ull * blockIdx.x * blockDim.x);
+    __syncthreads();
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= vwords) return;
     const uint64_t g = 4 * t;
-    const uint64_t v = seq_of(voff, nv, g);
+    uint64_t v = s_v0;
+    while (v + 1 < nv && voff[v + 1] <= g) v++;
     const uint64_t sidx = v / 6;
     const uint32_t k = (uint32_t)(v % 6), f = k % 3;
     const bool rev = k >= 3;
