@@ -269,3 +269,52 @@ def test_otu_replay_many_otus(kg, ctx, oracle, monkeypatch):
         assert_same(res, ref, what=f"otu {fsm} {otu}")
         res.free()
     t.free()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fsm_fuzz(kg, ctx, oracle, seed, monkeypatch):
+    """Adversarial hit streams for the run FSM: sticky-but-switching function indices, OTU churn over more than five
+    indices, clustered positions with gaps around max_gap, odd weights and offsets -- several proteins per case, every flag
+    set, both FSM implementations, against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    alpha = np.frombuffer(synth.PROT_ALPHA.encode(), np.uint8)
+    prots, keys, otu, avg, fI, wt = [], [], [], [], [], []
+    used = set()
+    for _ in range(12):
+        L = int(rng.integers(200, 6000))
+        prot = bytes(rng.choice(alpha, L))
+        wk = synth.window_keys(synth.aa_codes(prot))
+        # clustered positions: bursts of hits separated by gaps of 150..260 (around the default max_gap of 200)
+        pos, p = [], int(rng.integers(0, 50))
+        while p < len(wk) - 1:
+            for _ in range(int(rng.integers(1, 40))):
+                if p >= len(wk) - 1:
+                    break
+                pos.append(p)
+                p += int(rng.choice([1, 1, 1, 2, 3, 7, 30]))
+            p += int(rng.integers(150, 260))
+        f = int(rng.integers(1, 5))
+        for q in pos:
+            k = int(wk[q])
+            if k in used:
+                continue
+            used.add(k)
+            if rng.random() < 0.25:
+                f = int(rng.integers(1, 5))
+            keys.append(k)
+            fI.append(f if rng.random() > 0.1 else int(rng.integers(1, 5)))
+            otu.append(int(rng.integers(0, 9)) if rng.random() < 0.5 else 3)
+            avg.append(int(L - q + rng.integers(-30, 30)))
+            wt.append(float(rng.integers(1, 700)) / 256.0)
+        prots.append(prot)
+    img = synth.build_table_image(np.array(keys), otu, avg, fI, np.array(wt, np.float32))
+    t = ctx.table_from_image(img)
+    sb, off = oracle.concat(prots)
+    for flags in FLAGS + [dict(min_hits=2, max_gap=0), dict(min_hits=7, max_gap=1000, min_weighted_hits=9)]:
+        ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True, **flags), sb, off, oracle.DIRECT_PROBE)
+        for fsm in ("seq", "seg"):
+            monkeypatch.setenv("KG_FSM", fsm)
+            res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1, **flags))
+            assert_same(res, ref, what=f"fuzz seed {seed} {fsm} {flags}")
+            res.free()
+    t.free()

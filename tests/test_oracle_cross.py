@@ -127,3 +127,33 @@ def test_duplicate_positions_of_one_kmer(oracle):
     assert _as_lists(a) == _as_lists(b)
     assert len(a.hits) == (len(rep) - 8) + (len(rep) - 3 - 8)
     assert len(a.calls) == 2 and int(a.calls["count"][0]) == len(rep) - 8
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fsm_fuzz_c_vs_python(oracle, seed):
+    """The two independently written FSMs (C, pure Python) on random adversarial hit lists, all flag combinations."""
+    rng = np.random.default_rng(500 + seed)
+    for case in range(25):
+        n = int(rng.integers(0, 120))
+        pos = np.sort(rng.choice(3000, size=n, replace=False)) if n else np.zeros(0, int)
+        if case % 3 == 0 and n:      # clustered
+            pos = np.unique(np.cumsum(rng.choice([1, 1, 2, 5, 190, 200, 201, 230], size=n)))
+            n = len(pos)
+        fI = rng.integers(1, 4, size=n)
+        for i in range(1, n):
+            if rng.random() < 0.7:
+                fI[i] = fI[i - 1]
+        oI = rng.integers(0, 8, size=n)
+        avg = (3000 - pos + rng.integers(-25, 25, size=n)) if n else np.zeros(0, int)
+        wt = (rng.integers(1, 600, size=n) / 256.0).astype(np.float32)
+        flags = dict(order_constraint=bool(rng.integers(2)), min_hits=int(rng.integers(2, 7)), min_weighted_hits=int(rng.integers(0, 4)),
+                     max_gap=int(rng.choice([0, 5, 50, 200, 1000])))
+        hits = np.zeros(n, dtype=oracle.HIT_DTYPE)
+        hits["pos"], hits["fI"], hits["oI"], hits["avg"], hits["wt"] = pos, fI, oI, avg, wt
+        calls, otu = oracle.gather_hits(oracle.make_params(aa=True, **flags), hits)
+        fsm = pyo.Fsm(pyo.Params(aa=True, **flags))
+        fsm.gather(0, [pyo.Hit(int(o), int(p), int(a), int(f), np.float32(w)) for p, f, o, a, w in zip(pos, fI, oI, avg, wt)])
+        got = [(int(c["start"]), int(c["end"]), int(c["count"]), int(c["fI"]), float(c["weighted"])) for c in calls]
+        assert got == [(s, e, c, f, float(w)) for _, s, e, c, f, w in fsm.calls], (seed, case, flags)
+        k = int(otu["n"][0])
+        assert [[int(otu["count"][0][j]), int(otu["oI"][0][j])] for j in range(k)] == [list(x) for x in fsm.otu], (seed, case, flags)
