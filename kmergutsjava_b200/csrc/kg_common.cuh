@@ -121,11 +121,12 @@ struct kg_context {
     cudaStream_t stream = nullptr;      // compute
     cudaStream_t copy_stream = nullptr; // H2D of the next slice in the pipelined end-to-end call (kg_run)
     cudaStream_t d2h_stream = nullptr;  // D2H of the previous slice's records
+    cudaStream_t fsm_stream = nullptr;  // run FSM + call compaction of slice s while the compute stream probes slice s+1
     cudaEvent_t ev[12] = {};           // 0-5: run / fetch / upload brackets, 6-9: pipeline stages, 10-11: slice uploaded
     cudaEvent_t d2h_ev[3] = {};        // kg_run: records of slice s%3 have reached the host
     int sm_count = 0;
     size_t l2_bytes = 0;
-    DevBuf scan_tmp;                    // CUB temp storage
+    DevBuf scan_tmp, scan_tmp2;         // CUB temp storage (compute stream / fsm stream)
     // pinned staging for small device->host counters
     uint64_t* h_counters = nullptr;
     void* scratch = nullptr;            // RunScratch (kg_run.cu)

@@ -5,6 +5,7 @@
 //   addKmers      KGJ:900-922     (k_probe: window enumeration, base-20 encoding)
 //   sort + lookup KGJ:1076-1095, 944-1034 (k_probe: one 32-byte sector per k-mer instead of a sort-merge join)
 //   gatherHits / processSetOfHits KGJ:457-514, 385-455 (k_fsm)
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <string.h>
@@ -375,15 +376,101 @@ struct SparseEmit {
     __device__ __forceinline__ void operator()(int i, const KgDevCall& c) { dst[i] = c; }
 };
 
+// lo[v] = rank (in the global position order) of the first hit at or after the start of container v, found by a binary
+// search inside the one tile chunk that holds that position; lo[nv] = number of hits.
+__global__ void k_lo_tiles(const uint64_t* __restrict__ voff, uint64_t nv, const uint32_t* __restrict__ tile_base,
+                           const uint32_t* __restrict__ tile_out, uint32_t ntiles, const uint32_t* __restrict__ chunk_pos,
+                           uint32_t* __restrict__ lo, const unsigned long long* __restrict__ ctr) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > nv) return;
+    if (ctr[KG_CTR_OVERFLOW]) {
+        lo[v] = 0;
+        return;
+    }
+    const uint32_t x0 = (uint32_t)voff[v];
+    const uint32_t t = x0 >> TILE_SHIFT;
+    uint32_t rank = tile_out[ntiles];
+    if (v < nv && t < ntiles) {
+        const uint32_t o = tile_out[t], cnt = tile_out[t + 1] - o, base = tile_base[t];
+        uint32_t a = 0, b = cnt;
+        while (a < b) {
+            const uint32_t mid = (a + b) >> 1;
+            if (chunk_pos[base + mid] < x0) a = mid + 1;
+            else b = mid;
+        }
+        rank = o + a;
+    }
+    lo[v] = rank;
+}
+// Sequences are handed to the FSM threads grouped by hit count (64 classes, largest first), so that the 32 lanes of a
+// warp walk about the same number of hits (ungrouped, the average lane was active in 18 % of the issued instructions:
+// ncu, r01).  A counting sort by class: histogram, then scatter with one cursor per class; the order inside a class is
+// arbitrary, which is fine -- every sequence writes to places fixed by its own ranks, not by the thread that runs it.
+constexpr int FSM_CLASSES = 64;
+constexpr int FSM_LONG_CLASSES = 4;  // classes 0..3 = 256 hits or more
+__device__ __forceinline__ uint32_t fsm_class(uint32_t hits) { // 0 = most hits
+    const uint32_t c = hits < 32 ? hits : 32 + min(31u, (hits - 32) >> 3); // 0..31 exact, then steps of 8 up to 280+
+    return (FSM_CLASSES - 1) - c;
+}
+__global__ void k_fsm_hist(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[FSM_CLASSES];
+    if (threadIdx.x < FSM_CLASSES) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nseq) atomicAdd(&sh[fsm_class(lo[(s + 1) * per_seq] - lo[s * per_seq])], 1u);
+    __syncthreads();
+    if (threadIdx.x < FSM_CLASSES && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void k_fsm_scatter(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const uint32_t* __restrict__ hist,
+                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
+    __shared__ uint32_t start[FSM_CLASSES], sh_cnt[FSM_CLASSES], sh_base[FSM_CLASSES];
+    __shared__ uint32_t s_nlong;
+    if (threadIdx.x < FSM_CLASSES) sh_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0, nl = 0;
+        for (int c = 0; c < FSM_CLASSES; c++) {
+            start[c] = acc;
+            acc += hist[c];
+            if (c < FSM_LONG_CLASSES) nl = acc;
+        }
+        s_nlong = min(nl, (uint32_t)(nseq / 32)); // long sequences that get a warp's lane 0 to themselves
+    }
+    __syncthreads();
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cls = 0, mine = 0;
+    if (s < nseq) {
+        cls = fsm_class(lo[(s + 1) * per_seq] - lo[s * per_seq]);
+        mine = atomicAdd(&sh_cnt[cls], 1u); // rank inside this block's share of the class
+    }
+    __syncthreads();
+    if (threadIdx.x < FSM_CLASSES && sh_cnt[threadIdx.x]) sh_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], sh_cnt[threadIdx.x]);
+    __syncthreads();
+    if (s < nseq) {
+        // Ordinal j in class order (most hits first).  A warp full of long sequences would execute the union of 32
+        // divergent paths on every hit and stretch the kernel's critical path; so the nl longest sequences are dealt one
+        // per warp (lane 0) and the others fill lanes 1..31 and then the remaining warps, still grouped by class.
+        const uint32_t j = start[cls] + sh_base[cls] + mine, nl = s_nlong;
+        uint32_t slot;
+        if (j < nl) {
+            slot = 32 * j;
+        } else {
+            const uint32_t q = j - nl;
+            slot = q < 31 * nl ? (q / 31) * 32 + 1 + q % 31 : 32 * nl + (q - 31 * nl);
+        }
+        perm[slot] = (uint32_t)s;
+    }
+}
+
 __global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, uint64_t nseq, int per_seq,
                                              const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_out,
                                              uint32_t ntiles, const uint32_t* __restrict__ chunk_pos,
                                              const int4* __restrict__ chunk_payload, KgFsmParams p,
-                                             KgDevCall* __restrict__ sparse, uint32_t* __restrict__ lo,
-                                             uint32_t* __restrict__ call_cnt, kg_otu* __restrict__ otus,
-                                             const unsigned long long* __restrict__ ctr) {
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseq) return;
+                                             KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ lo,
+                                             const uint32_t* __restrict__ perm, uint32_t* __restrict__ call_cnt,
+                                             kg_otu* __restrict__ otus, const unsigned long long* __restrict__ ctr) {
+    const uint64_t tix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= nseq) return;
+    const uint64_t s = perm[tix];
     if (ctr[KG_CTR_OVERFLOW]) { // some tile could not claim its chunk: the host repeats the pass with larger buffers
         for (int k = 0; k < per_seq; k++) call_cnt[s * per_seq + k] = 0;
         return;
@@ -394,33 +481,38 @@ __global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, 
         const uint64_t v = s * per_seq + k;
         const uint32_t x0 = (uint32_t)voff[v], x1 = (uint32_t)voff[v + 1];
         uint32_t t = x0 >> TILE_SHIFT;
-        // first hit at or after x0 inside tile t
-        uint32_t e = 0, cnt = 0, base = 0, rank = tile_out[ntiles];
+        const uint32_t rank = lo[v]; // k_lo_tiles
+        uint32_t e = 0, cnt = 0, base = 0;
         if (t < ntiles) {
             const uint32_t o = tile_out[t];
             cnt = tile_out[t + 1] - o;
             base = tile_base[t];
-            uint32_t a = 0, b = cnt;
-            while (a < b) {
-                const uint32_t mid = (a + b) >> 1;
-                if (chunk_pos[base + mid] < x0) a = mid + 1;
-                else b = mid;
-            }
-            e = a;
-            rank = o + a;
+            e = rank - o;
         }
-        lo[v] = rank;
         f.begin_container();
         SparseEmit emit{sparse + rank / (uint32_t)p.min_hits};
         bool done = x1 <= x0;
         while (!done && t < ntiles) {
-            for (; e < cnt; e++) {
-                const uint32_t g = chunk_pos[base + e];
+            // software-pipelined by one hit: the loads of hit e+1 are in flight while hit e goes through the FSM (a long
+            // protein is a chain of ~10^3 dependent steps on one thread; this halves its latency per step)
+            uint32_t g_n = 0;
+            int4 pl_n = make_int4(0, 0, 0, 0);
+            if (e < cnt) {
+                g_n = chunk_pos[base + e];
+                pl_n = chunk_payload[base + e];
+            }
+            while (e < cnt) {
+                const uint32_t g = g_n;
+                const int4 pl = pl_n;
+                e++;
+                if (e < cnt) {
+                    g_n = chunk_pos[base + e];
+                    pl_n = chunk_payload[base + e];
+                }
                 if (g >= x1) {
                     done = true;
                     break;
                 }
-                const int4 pl = chunk_payload[base + e];
                 KgHitLite h = {(int)(g - x0), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
                 f.hit(p, h, emit);
             }
@@ -437,7 +529,6 @@ __global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, 
         f.end_container(p, emit);
         call_cnt[v] = (uint32_t)f.ncalls;
     }
-    if (s == nseq - 1) lo[nseq * per_seq] = tile_out[ntiles];
     kg_otu o;
     o.n = f.otu_c.n;
 #pragma unroll
@@ -673,6 +764,7 @@ __global__ void k_emit_hits(const uint64_t* __restrict__ voff, uint64_t nv, int 
 struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them let slice s+1 queue up behind slice s
     DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
     DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
+    DevBuf fk_a, fi_a;                                           // per-sequence path: class histogram / cursors, sequence permutation
     DevBuf hit_v, seg_flag, seg_id, seg_begin, hit_flag, nseg;    // segment path
     DevBuf o_oi, o_cidx, o_c01, o_prevc, o_crank, o_head, o_hrank, o_run_oi, o_run_crank; // segment path: OTU run-length encoding
     bool seg = false;                                            // which FSM path the enqueued run uses
@@ -764,18 +856,20 @@ void pool_give_host(kg_context* ctx, HostBuf* b) {
     *b = HostBuf();
 }
 
+// CUB temporary storage: one buffer per stream, because work on the two streams overlaps
+DevBuf& scan_tmp_of(kg_context* ctx, cudaStream_t st) { return st == ctx->fsm_stream ? ctx->scan_tmp2 : ctx->scan_tmp; }
 int exclusive_sum_u32(kg_context* ctx, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
     size_t bytes = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, st));
-    KG_TRY(ctx->scan_tmp.ensure(bytes));
-    CU(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, bytes, in, out, n, st));
+    KG_TRY(scan_tmp_of(ctx, st).ensure(bytes));
+    CU(cub::DeviceScan::ExclusiveSum(scan_tmp_of(ctx, st).p, bytes, in, out, n, st));
     return KG_OK;
 }
 int inclusive_sum_u32(kg_context* ctx, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
     size_t bytes = 0;
     CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, n, st));
-    KG_TRY(ctx->scan_tmp.ensure(bytes));
-    CU(cub::DeviceScan::InclusiveSum(ctx->scan_tmp.p, bytes, in, out, n, st));
+    KG_TRY(scan_tmp_of(ctx, st).ensure(bytes));
+    CU(cub::DeviceScan::InclusiveSum(scan_tmp_of(ctx, st).p, bytes, in, out, n, st));
     return KG_OK;
 }
 int exclusive_sum_u64(kg_context* ctx, const uint64_t* in, uint64_t* out, size_t n, cudaStream_t st) {
@@ -819,6 +913,7 @@ extern "C" int kg_init(int device, kg_context** out) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->fsm_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) CU(cudaEventCreate(&ev));
     for (auto& ev : ctx->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
@@ -836,7 +931,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
                           &sl.call_off, &sl.ctr, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
-                          &sl.hit_flag, &sl.nseg, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_prevc, &sl.o_crank, &sl.o_head, &sl.o_hrank,
+                          &sl.hit_flag, &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_prevc, &sl.o_crank, &sl.o_head, &sl.o_hrank,
                           &sl.o_run_oi, &sl.o_run_crank})
             b->release();
         if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
@@ -847,6 +942,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     for (auto& b : ctx->dev_pool) b.release();
     for (auto& h : ctx->host_pool) cudaFreeHost(h.p);
     ctx->scan_tmp.release();
+    ctx->scan_tmp2.release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->d2h_ev)
@@ -854,6 +950,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->fsm_stream) cudaStreamDestroy(ctx->fsm_stream);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     delete ctx;
 }
@@ -1052,17 +1149,30 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
         sl.launches++;
     }
     cudaEventRecord(sl.ev[2], st);
+    // Everything downstream of the probe runs on a second stream: in kg_run the run FSM of slice s (whose tail is a few
+    // long sequences on a mostly idle GPU) then overlaps the probe of slice s+1, which is queued on the compute stream.
+    st = ctx->fsm_stream;
+    cudaStreamWaitEvent(st, sl.ev[2], 0);
     KG_TRY(exclusive_sum_u32(ctx, sl.tile_cnt.as<uint32_t>(), sl.tile_out.as<uint32_t>(), (size_t)ntiles + 1, st));
     sl.launches++;
     CU(cudaMemcpyAsync(sl.h_ctr, d_ctr, KG_CTR_COUNT * 8, cudaMemcpyDeviceToHost, st));
     sl.seg = use_segment_path(b->mode);
     if (!sl.seg) { // many short sequences: one thread per sequence straight off the per-tile chunks
+        k_lo_tiles<<<blocks_for(nv + 1, 256), 256, 0, st>>>(b->voffsets(), nv, sl.tile_base.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
+                                                           sl.chunk_pos.as<uint32_t>(), sl.lo.as<uint32_t>(), d_ctr);
+        sl.launches++;
         if (b->n) {
+            KG_TRY(sl.fi_a.ensure(b->n * 4));
+            KG_TRY(sl.fk_a.ensure(2 * FSM_CLASSES * 4));
+            uint32_t* hist = sl.fk_a.as<uint32_t>();
+            CU(cudaMemsetAsync(hist, 0, 2 * FSM_CLASSES * 4, st));
+            k_fsm_hist<<<blocks_for(b->n, 256), 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, hist);
+            k_fsm_scatter<<<blocks_for(b->n, 256), 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, hist, hist + FSM_CLASSES, sl.fi_a.as<uint32_t>());
             k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sl.tile_base.as<uint32_t>(),
                                                         sl.tile_out.as<uint32_t>(), ntiles, sl.chunk_pos.as<uint32_t>(),
                                                         sl.chunk_payload.as<int4>(), fp, sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(),
-                                                        sl.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
-            sl.launches++;
+                                                        sl.fi_a.as<uint32_t>(), sl.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
+            sl.launches += 3;
         }
         CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + nv, 0, 4, st));
         KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), nv + 1, st));
@@ -1115,8 +1225,8 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
                                                              cap1, sl.o_oi.as<int>(), sl.o_cidx.as<uint32_t>(), sl.o_c01.as<uint32_t>(), d_ctr);
             size_t tb = 0;
             CU(cub::DeviceScan::ExclusiveScan(nullptr, tb, sl.o_cidx.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), MaxU32(), 0u, (size_t)cap1, st));
-            KG_TRY(ctx->scan_tmp.ensure(tb));
-            CU(cub::DeviceScan::ExclusiveScan(ctx->scan_tmp.p, tb, sl.o_cidx.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), MaxU32(), 0u, (size_t)cap1, st));
+            KG_TRY(scan_tmp_of(ctx, st).ensure(tb));
+            CU(cub::DeviceScan::ExclusiveScan(scan_tmp_of(ctx, st).p, tb, sl.o_cidx.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), MaxU32(), 0u, (size_t)cap1, st));
             KG_TRY(exclusive_sum_u32(ctx, sl.o_c01.as<uint32_t>(), sl.o_crank.as<uint32_t>(), cap1, st));
             k_otu_heads<<<blocks_for(cap1, 256), 256, 0, st>>>(sl.o_c01.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), sl.o_oi.as<int>(), sl.hit_v.as<uint32_t>(),
                                                               sl.lo.as<uint32_t>(), per_seq, cap1, sl.o_head.as<uint32_t>());
@@ -1410,7 +1520,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         R->stats.ms_group += ps.ms_group;
         kg_batch_free(bt);
         slot[s & 1] = nullptr;
-        if (dbg) fprintf(stderr, "[kg] slice %zu: %zu seqs, host %.3f ms (device %.3f ms), since start %.3f ms\n", s, (size_t)(cut[s + 1] - cut[s]), now_ms() - t0, ms, now_ms() - t_begin);
+        if (dbg) fprintf(stderr, "[kg] slice %zu: %zu seqs, host %.3f ms (device %.3f = prepare %.3f + probe %.3f + group %.3f ms), since start %.3f ms\n", s, (size_t)(cut[s + 1] - cut[s]), now_ms() - t0, ms, ps.ms_prepare, ps.ms_probe, ps.ms_group, now_ms() - t_begin);
     }
     CU(cudaStreamSynchronize(ctx->d2h_stream));
     if (dbg) fprintf(stderr, "[kg] kg_run total %.3f ms\n", now_ms() - t_begin);
