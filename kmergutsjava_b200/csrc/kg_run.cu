@@ -913,7 +913,11 @@ extern "C" int kg_init(int device, kg_context** out) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->fsm_stream, cudaStreamNonBlocking));
+    {   // the FSM's critical path is one long sequence on one thread: let its blocks jump the queue of probe blocks
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        CU(cudaStreamCreateWithPriority(&ctx->fsm_stream, cudaStreamNonBlocking, hi_p));
+    }
     for (auto& ev : ctx->ev) CU(cudaEventCreate(&ev));
     for (auto& ev : ctx->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
@@ -1353,8 +1357,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     if (!ctx || !table || !out || !offsets || (mode != KG_MODE_AA && mode != KG_MODE_DNA)) KG_FAIL(KG_EINVAL, "kg_run: bad argument");
     KG_TRY(check_params(params));
     if (offsets[0] != 0) KG_FAIL(KG_EINVAL, "kg_run: offsets[0] must be 0");
-    for (size_t i = 0; i < n; i++)
-        if (offsets[i + 1] < offsets[i]) KG_FAIL(KG_EINVAL, "kg_run: offsets must be non-decreasing (at %zu)", i);
+    // offsets are checked slice by slice (validate, below) while the GPU already works on the slices before
     if (offsets[n] && !seq_bytes) KG_FAIL(KG_EINVAL, "kg_run: null sequence bytes");
     if (n >= 0xFFFFFFF0ull) KG_FAIL(KG_ERANGE, "kg_run: %zu sequences in one call", n);
     CU(cudaSetDevice(ctx->device));
@@ -1372,9 +1375,12 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     std::vector<size_t> cut{0};
     uint64_t step = std::max<uint64_t>(target / 8, std::min<uint64_t>(target, 2ull << 20));
     for (size_t i = 0; i < n;) {
-        size_t j = i;
-        while (j < n && (j == i || offsets[j + 1] - offsets[i] <= step)) j++;
+        // last j with offsets[j] - offsets[i] <= step (binary search: a linear walk over a million offsets costs ~1 ms)
+        size_t j = (size_t)(std::upper_bound(offsets + i, offsets + n + 1, offsets[i] + step) - offsets) - 1;
+        if (j <= i) j = i + 1;
+        if (offsets[n] - offsets[j] < step / 2 && offsets[n] - offsets[i] <= hard) j = n; // no tiny last slice: its FSM tail would be exposed
         step = std::min<uint64_t>(step * 2, target);
+        if (offsets[j] < offsets[i]) KG_FAIL(KG_EINVAL, "kg_run: offsets must be non-decreasing (between %zu and %zu)", i, j);
         if (offsets[j] - offsets[i] > hard) KG_FAIL(KG_ERANGE, "kg_run: sequence %zu alone exceeds the per-call limit", i);
         cut.push_back(j);
         i = j;
@@ -1407,7 +1413,10 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     };
     auto upload = [&](size_t s) -> int { // slice s -> slot[s & 1], asynchronously on the copy stream
         const size_t a = cut[s], b = cut[s + 1], cnt = b - a;
+        for (size_t i = a; i < b; i++)
+            if (offsets[i + 1] < offsets[i]) KG_FAIL(KG_EINVAL, "kg_run: offsets must be non-decreasing (at %zu)", i);
         const uint64_t bytes = offsets[b] - offsets[a];
+        if (bytes > hard) KG_FAIL(KG_ERANGE, "kg_run: sequence %zu alone exceeds the per-call limit", a);
         kg_batch* bt = new kg_batch();
         bt->ctx = ctx;
         bt->mode = mode;
