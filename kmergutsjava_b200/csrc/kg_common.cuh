@@ -122,7 +122,8 @@ struct kg_context {
     cudaStream_t copy_stream = nullptr; // H2D of the next slice in the pipelined end-to-end call (kg_run)
     cudaStream_t d2h_stream = nullptr;  // D2H of the previous slice's records
     cudaStream_t fsm_stream = nullptr;  // run FSM + call compaction of slice s while the compute stream probes slice s+1
-    cudaEvent_t ev[12] = {};           // 0-5: run / fetch / upload brackets, 6-9: pipeline stages, 10-11: slice uploaded
+    cudaEvent_t ev[12] = {};           // 0-5: run / fetch / upload brackets, 6-9: pipeline stages
+    cudaEvent_t up_ev[4] = {};         // kg_run: slice s%4 has been uploaded
     cudaEvent_t d2h_ev[3] = {};        // kg_run: records of slice s%3 have reached the host
     int sm_count = 0;
     size_t l2_bytes = 0;

@@ -920,6 +920,7 @@ extern "C" int kg_init(int device, kg_context** out) {
     }
     for (auto& ev : ctx->ev) CU(cudaEventCreate(&ev));
     for (auto& ev : ctx->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : ctx->up_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
     CU(cudaMallocHost(&ctx->h_counters, (KG_CTR_COUNT + 1) * sizeof(uint64_t)));
     memset(ctx->h_counters, 0, (KG_CTR_COUNT + 1) * sizeof(uint64_t));
@@ -950,6 +951,8 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->d2h_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->up_ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1399,7 +1402,9 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     constexpr int KEEP = 3;
     DevBuf keep[KEEP][3];
     bool keep_used[KEEP] = {false, false, false};
-    kg_batch* slot[2] = {nullptr, nullptr};
+    // uploads run UP-1 slices ahead of the compute stream: the copy engine never waits for a slice to finish
+    constexpr size_t UP = 4;
+    kg_batch* slot[UP] = {nullptr, nullptr, nullptr, nullptr};
     int rc = KG_OK;
     uint64_t ncalls = 0, nhits = 0;
     auto fail = [&](int code) {
@@ -1411,7 +1416,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         kg_result_free(R);
         return code;
     };
-    auto upload = [&](size_t s) -> int { // slice s -> slot[s & 1], asynchronously on the copy stream
+    auto upload = [&](size_t s) -> int { // slice s -> slot[s % UP], asynchronously on the copy stream
         const size_t a = cut[s], b = cut[s + 1], cnt = b - a;
         for (size_t i = a; i < b; i++)
             if (offsets[i + 1] < offsets[i]) KG_FAIL(KG_EINVAL, "kg_run: offsets must be non-decreasing (at %zu)", i);
@@ -1422,7 +1427,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         bt->mode = mode;
         bt->n = cnt;
         bt->total = bytes;
-        slot[s & 1] = bt;
+        slot[s % UP] = bt;
         KG_TRY(pool_take_dev(ctx, bytes + 64, &bt->seq_buf));
         KG_TRY(pool_take_dev(ctx, (cnt + 1) * 8, &bt->off_buf));
         bt->d_seq = bt->seq_buf.as<uint8_t>();
@@ -1441,7 +1446,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         if (bytes) CU(cudaMemcpyAsync(bt->d_seq, seq_bytes + offsets[a], bytes, cudaMemcpyHostToDevice, cs));
         CU(cudaMemcpyAsync(bt->d_off, offsets + a, (cnt + 1) * 8, cudaMemcpyHostToDevice, cs));
         if (offsets[a]) k_rebase<<<blocks_for(cnt + 1, 256), 256, 0, cs>>>(bt->d_off, cnt + 1, offsets[a]);
-        CU(cudaEventRecord(ctx->ev[10 + (s & 1)], cs));
+        CU(cudaEventRecord(ctx->up_ev[s % UP], cs));
         return KG_OK;
     };
 
@@ -1472,10 +1477,12 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         }
     };
     auto enqueue = [&](size_t s) -> int { // slice s runs as soon as its bytes have landed; nothing here waits for the GPU
-        cudaStreamWaitEvent(ctx->stream, ctx->ev[10 + (s & 1)], 0);
-        return pipe_enqueue(ctx, sc.slot[s & 1], table, slot[s & 1], params, &part[s & 1], sc.hit_cap_seen, (uint32_t)cut[s]);
+        cudaStreamWaitEvent(ctx->stream, ctx->up_ev[s % UP], 0);
+        return pipe_enqueue(ctx, sc.slot[s & 1], table, slot[s % UP], params, &part[s & 1], sc.hit_cap_seen, (uint32_t)cut[s]);
     };
-    if (nslices && ((rc = upload(0)) != KG_OK || (rc = enqueue(0)) != KG_OK)) {
+    for (size_t s = 0; s < std::min(nslices, UP - 1); s++)
+        if ((rc = upload(s)) != KG_OK) return fail(rc);
+    if (nslices && (rc = enqueue(0)) != KG_OK) {
         drop_parts();
         return fail(rc);
     }
@@ -1487,11 +1494,11 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
             keep_used[s % KEEP] = false;
         }
         // queue slice s+1 behind slice s BEFORE waiting for slice s: the GPU never idles between slices
-        if (s + 1 < nslices && ((rc = upload(s + 1)) != KG_OK || (rc = enqueue(s + 1)) != KG_OK)) {
+        if ((s + UP - 1 < nslices && (rc = upload(s + UP - 1)) != KG_OK) || (s + 1 < nslices && (rc = enqueue(s + 1)) != KG_OK)) {
             drop_parts();
             return fail(rc);
         }
-        kg_batch* bt = slot[s & 1];
+        kg_batch* bt = slot[s % UP];
         kg_result& pr = part[s & 1];
         rc = pipe_finish(ctx, sc.slot[s & 1], table, bt, params, &pr, (uint32_t)cut[s]);
         if (rc != KG_OK) {
@@ -1528,7 +1535,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         R->stats.ms_probe += ps.ms_probe;
         R->stats.ms_group += ps.ms_group;
         kg_batch_free(bt);
-        slot[s & 1] = nullptr;
+        slot[s % UP] = nullptr;
         if (dbg) fprintf(stderr, "[kg] slice %zu: %zu seqs, host %.3f ms (device %.3f = prepare %.3f + probe %.3f + group %.3f ms), since start %.3f ms\n", s, (size_t)(cut[s + 1] - cut[s]), now_ms() - t0, ms, ps.ms_prepare, ps.ms_probe, ps.ms_group, now_ms() - t_begin);
     }
     CU(cudaStreamSynchronize(ctx->d2h_stream));
