@@ -36,6 +36,9 @@ EXPORTS = [
     "kg_format_java_f", "kg_report_write", "kg_main",
     "kg_synth_signatures", "kg_synth_proteins", "kg_synth_genomes", "kg_synth_reference_image", "kg_synth_naive_scan_aa", "kg_synth_hits_checksum", "kg_device_free", "kg_device_to_host",
     "kg_probe_roofline", "kg_probe_roofline_table",
+    "kg_shard_owner", "kg_comm_unique_id", "kg_comm_init", "kg_comm_init_local", "kg_comm_free", "kg_comm_last_stats",
+    "kg_table_load_sharded", "kg_table_from_image_sharded", "kg_table_from_device_entries_sharded",
+    "kg_batch_run_sharded", "kg_batch_run_sharded_local",
 ]
 
 
@@ -60,6 +63,12 @@ class RunStats(C.Structure):
                 ("num_hits", C.c_uint64), ("num_calls", C.c_uint64), ("num_launches", C.c_uint32),
                 ("ms_h2d", C.c_float), ("ms_device", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_prepare", C.c_float), ("ms_probe", C.c_float), ("ms_group", C.c_float)]
+
+
+class ShardStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("keys_sent", "keys_remote", "keys_received", "replies_sent", "replies_received",
+                                          "bytes_sent")] + \
+               [(n, C.c_float) for n in ("ms_route", "ms_keys", "ms_answer", "ms_replies", "ms_merge", "ms_total")]
 
 
 class UniverseStruct(C.Structure):
@@ -112,6 +121,14 @@ def lib() -> C.CDLL:
         "kg_device_free": (None, [vp]), "kg_device_to_host": (i32, [vp, vp, vp, u64]),
         "kg_probe_roofline": (i32, [vp, u64, u64, i32, i32, C.POINTER(C.c_double)]),
         "kg_probe_roofline_table": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_double)]),
+        "kg_shard_owner": (i32, [u64, i32]), "kg_comm_unique_id": (i32, [vp]),
+        "kg_comm_init": (i32, [vp, i32, i32, vp, pp]), "kg_comm_init_local": (i32, [pp, i32, pp]),
+        "kg_comm_free": (None, [vp]), "kg_comm_last_stats": (i32, [vp, C.POINTER(ShardStats)]),
+        "kg_table_load_sharded": (i32, [vp, C.c_char_p, i32, i32, pp]),
+        "kg_table_from_image_sharded": (i32, [vp, vp, sz, i32, i32, pp]),
+        "kg_table_from_device_entries_sharded": (i32, [vp, vp, vp, sz, i32, i32, pp]),
+        "kg_batch_run_sharded": (i32, [vp, vp, vp, C.POINTER(Params), pp]),
+        "kg_batch_run_sharded_local": (i32, [pp, pp, pp, i32, C.POINTER(Params), pp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -176,6 +193,23 @@ class Context:
         return Table(self, h)
 
     # -- the path --
+    # ---- hash-sharded table (include/kmerguts_shard.h) ----
+    def load_table_sharded(self, data_dir: str, rank: int, nranks: int) -> "Table":
+        h = C.c_void_p()
+        _check(lib().kg_table_load_sharded(self._h, data_dir.encode(), rank, nranks, C.byref(h)))
+        return Table(self, h)
+
+    def table_from_image_sharded(self, image: bytes, rank: int, nranks: int) -> "Table":
+        h = C.c_void_p()
+        buf = np.frombuffer(image, dtype=np.uint8)
+        _check(lib().kg_table_from_image_sharded(self._h, buf.ctypes.data, buf.size, rank, nranks, C.byref(h)))
+        return Table(self, h)
+
+    def table_from_device_entries_sharded(self, d_keys: int, d_payload: int, n: int, rank: int, nranks: int) -> "Table":
+        h = C.c_void_p()
+        _check(lib().kg_table_from_device_entries_sharded(self._h, d_keys, d_payload, n, rank, nranks, C.byref(h)))
+        return Table(self, h)
+
     def run(self, table: "Table", mode: int, seq_bytes: np.ndarray, offsets: np.ndarray, params: Params) -> "Result":
         """Host buffers in, host results out (kg_run): the end-to-end call."""
         seq_bytes = np.ascontiguousarray(seq_bytes, dtype=np.uint8)
@@ -222,6 +256,65 @@ class Context:
         out = np.empty(nbytes, dtype=np.uint8)
         _check(lib().kg_device_to_host(self._h, out.ctypes.data, d_ptr, nbytes))
         return out
+
+
+def shard_owner(key: int, nranks: int) -> int:
+    return int(lib().kg_shard_owner(int(key), int(nranks)))
+
+
+class Comm:
+    """One rank of a sharded-table communicator.  `Comm.unique_id()` on rank 0, pass the 128 bytes to every rank, then
+    `Comm(ctx, rank, nranks, id)` on all of them (collective).  `Comm.local(ctxs)` puts all ranks in this process."""
+
+    def __init__(self, ctx: Context, rank: int = 0, nranks: int = 1, uid: Optional[bytes] = None, _h=None):
+        self.ctx, self.rank, self.nranks = ctx, rank, nranks
+        if _h is not None:
+            self._h = _h
+            return
+        h = C.c_void_p()
+        buf = C.create_string_buffer(uid, 128) if uid is not None else None
+        _check(lib().kg_comm_init(ctx._h, rank, nranks, C.cast(buf, C.c_void_p) if buf is not None else None, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().kg_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    @staticmethod
+    def local(ctxs: Sequence[Context]) -> list["Comm"]:
+        n = len(ctxs)
+        arr = (C.c_void_p * n)(*[c._h for c in ctxs])
+        out = (C.c_void_p * n)()
+        _check(lib().kg_comm_init_local(arr, n, out))
+        return [Comm(ctxs[r], r, n, _h=C.c_void_p(out[r])) for r in range(n)]
+
+    def run(self, table: "Table", batch: "Batch", params: Params) -> "Result":
+        h = C.c_void_p()
+        _check(lib().kg_batch_run_sharded(self._h, table._h, batch._h, C.byref(params), C.byref(h)))
+        return Result(h)
+
+    @property
+    def stats(self) -> ShardStats:
+        s = ShardStats()
+        _check(lib().kg_comm_last_stats(self._h, C.byref(s)))
+        return s
+
+    def free(self):
+        if self._h:
+            lib().kg_comm_free(self._h)
+            self._h = None
+
+
+def run_sharded_local(comms: Sequence[Comm], tables: Sequence["Table"], batches: Sequence["Batch"], params: Params) -> list["Result"]:
+    n = len(comms)
+    ca = (C.c_void_p * n)(*[c._h for c in comms])
+    ta = (C.c_void_p * n)(*[t._h for t in tables])
+    ba = (C.c_void_p * n)(*[b._h for b in batches])
+    out = (C.c_void_p * n)()
+    _check(lib().kg_batch_run_sharded_local(ca, ta, ba, n, C.byref(params), out))
+    return [Result(C.c_void_p(out[r])) for r in range(n)]
 
 
 class Table:

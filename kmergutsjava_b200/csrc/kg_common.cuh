@@ -99,6 +99,15 @@ __host__ __device__ __forceinline__ unsigned long long kg_filter_mask(uint64_t h
     return (1ull << (g >> 58)) | (1ull << ((g >> 52) & 63));
 }
 
+// hash-sharded table (configs[4]): the rank that owns a key.  A second, independent mix: the bucket and the filter
+// already use both halves of kg_mix(key), and an owner derived from the same bits would leave every shard using 1/R of
+// its bucket range.
+constexpr int KG_MAX_RANKS = 16;
+__host__ __device__ __forceinline__ uint32_t kg_owner_of(uint64_t key, uint32_t nranks) {
+    const uint64_t h = kg_mix(key ^ 0x5851F42D4C957F2Dull);
+    return (uint32_t)(((h >> 32) * (uint64_t)nranks) >> 32);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // device memory helpers (host side)
 // ---------------------------------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@ struct kg_table {
     unsigned long long* d_filter = nullptr;
     uint32_t filter_words = 0;
     kg_table_info info = {};
+    int shard_rank = 0, shard_count = 1; // hash-sharded table: this handle holds the keys kg_owner_of() gives shard_rank
     KgTableView view() const;
 };
 

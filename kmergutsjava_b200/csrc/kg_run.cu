@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <chrono>
 
 #include "kg_device.cuh"
@@ -193,88 +194,63 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t mine, uint32_t* war
     return before + incl - mine;
 }
 
-__global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe(const uint8_t* __restrict__ stream, uint32_t vtotal, KgTableView tab,
-                                                        uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload,
-                                                        uint32_t hit_cap, uint32_t* __restrict__ tile_base,
-                                                        uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr,
-                                                        uint32_t flags) {
-    extern __shared__ int4 smem_dyn[];
-    int4* pstage = smem_dyn;                                                        // [TILE]
-    unsigned long long* queue = reinterpret_cast<unsigned long long*>(smem_dyn + TILE); // [TILE]
-    __shared__ uint8_t lut[256];
-    __shared__ uint32_t hitbits[TILE / 32];
-    __shared__ uint32_t warp_a[PROBE_BLK / 32], warp_b[PROBE_BLK / 32], warp_kmers[PROBE_BLK / 32];
-    __shared__ uint32_t s_base;
-
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += PROBE_BLK) lut[i] = (i >= 'A' && i <= 'Z') ? c_aa_code[i - 'A'] : 20;
-    if (tid < TILE / 32) hitbits[tid] = 0;
-    __syncthreads();
-
-    const uint64_t pol_keep = kg_policy_evict_last();
-    const uint64_t pol_stream = (flags & 1u) ? kg_policy_evict_normal() : kg_policy_evict_first();
-    const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
-
-    // ---- A: encode + prefilter ----
-    uint32_t pass = 0, nk = 0;
+// Windows of one thread: PT consecutive positions from p0 (+ 7 bytes of halo).  q[i] = base-20 value of residues
+// i..i+3, so the key of window i is q[i] * 20^4 + q[i+4] (first residue most significant, KGJ:274-292); bit i of the
+// result is set when all eight residues of window i are amino-acid letters (KGJ:111-175, 283-289).
+__device__ __forceinline__ uint32_t encode_windows(const uint8_t* __restrict__ stream, uint32_t p0, uint32_t vtotal,
+                                                   const uint8_t* lut, uint32_t (&q)[PT + 4]) {
     constexpr int NB = PT + 8; // residue bytes a thread reads: its PT positions + 7 bytes of halo (+1 unused)
-    uint32_t q[PT + 4];
-    if (p0 < vtotal) {
-        uint32_t wv[NB / 4];
+    uint32_t wv[NB / 4];
 #pragma unroll
-        for (int i = 0; i < NB / 8; i++) {
-            const uint2 t = *reinterpret_cast<const uint2*>(stream + p0 + 8 * i);
-            wv[2 * i] = t.x;
-            wv[2 * i + 1] = t.y;
-        }
-        uint32_t c[NB];
-        uint32_t bad = 0;
+    for (int i = 0; i < NB / 8; i++) {
+        const uint2 t = *reinterpret_cast<const uint2*>(stream + p0 + 8 * i);
+        wv[2 * i] = t.x;
+        wv[2 * i + 1] = t.y;
+    }
+    uint32_t c[NB];
+    uint32_t bad = 0;
 #pragma unroll
-        for (int i = 0; i < NB; i++) {
-            c[i] = lut[(wv[i >> 2] >> (8 * (i & 3))) & 0xFFu];
-            bad |= (uint32_t)(c[i] >= 20u) << i;
-        }
-        const uint32_t left = vtotal - p0; // bytes of this thread's NB that exist
-        if (left < NB) bad |= ~0u << left;
+    for (int i = 0; i < NB; i++) {
+        c[i] = lut[(wv[i >> 2] >> (8 * (i & 3))) & 0xFFu];
+        bad |= (uint32_t)(c[i] >= 20u) << i;
+    }
+    const uint32_t left = vtotal - p0; // bytes of this thread's NB that exist
+    if (left < NB) bad |= ~0u << left;
 #pragma unroll
-        for (int i = 0; i < PT + 4; i++) q[i] = ((c[i] * 20u + c[i + 1]) * 20u + c[i + 2]) * 20u + c[i + 3];
-        uint32_t valid = 0;
+    for (int i = 0; i < PT + 4; i++) q[i] = ((c[i] * 20u + c[i + 1]) * 20u + c[i + 2]) * 20u + c[i + 3];
+    uint32_t valid = 0;
 #pragma unroll
-        for (int i = 0; i < PT; i++) valid |= (uint32_t)(((bad >> i) & 0xFFu) == 0u) << i;
-        nk = __popc(valid); // lookups = windows the reference enumerates (KGJ:912-921)
-        pass = valid;
-        if (tab.filter_words) {
-            unsigned long long fw[PT];
+    for (int i = 0; i < PT; i++) valid |= (uint32_t)(((bad >> i) & 0xFFu) == 0u) << i;
+    return valid;
+}
+
+// Prefilter: which of the valid windows may be in the table (all PT filter words are in flight together).
+__device__ __forceinline__ uint32_t filter_windows(const KgTableView& tab, const uint32_t (&q)[PT + 4], uint32_t valid,
+                                                   uint32_t flags, uint64_t pol_keep) {
+    unsigned long long fw[PT];
 #pragma unroll
-            for (int i = 0; i < PT; i++) {
-                fw[i] = 0;
-                if ((valid >> i) & 1u) {
-                    const uint64_t h = kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]);
-                    const uint32_t w = kg_filter_word(h, tab.filter_words);
-                    fw[i] = (flags & 2u) ? __ldg(tab.filter + w) : kg_load_filter_word(tab.filter, w, pol_keep);
-                }
-            }
-            pass = 0;
-#pragma unroll
-            for (int i = 0; i < PT; i++) {
-                const unsigned long long fm = kg_filter_mask(kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]));
-                pass |= (uint32_t)((fw[i] & fm) == fm) << i;
-            }
-            pass &= valid;
+    for (int i = 0; i < PT; i++) {
+        fw[i] = 0;
+        if ((valid >> i) & 1u) {
+            const uint64_t h = kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]);
+            const uint32_t w = kg_filter_word(h, tab.filter_words);
+            fw[i] = (flags & 2u) ? __ldg(tab.filter + w) : kg_load_filter_word(tab.filter, w, pol_keep);
         }
     }
-
-    // ---- B: survivors -> shared-memory queue, tile order ----
-    uint32_t nsurv;
-    uint32_t qo = block_excl_scan(__popc(pass), warp_a, &nsurv);
+    uint32_t pass = 0;
 #pragma unroll
-    for (int i = 0; i < PT; i++)
-        if ((pass >> i) & 1u) queue[qo++] = ((uint64_t)q[i] * 160000ull + q[i + 4]) | ((unsigned long long)(tid * PT + i) << 35);
-    const uint32_t wk = __reduce_add_sync(0xFFFFFFFFu, nk);
-    if ((tid & 31) == 0) warp_kmers[tid >> 5] = wk;
-    __syncthreads();
+    for (int i = 0; i < PT; i++) {
+        const unsigned long long fm = kg_filter_mask(kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]));
+        pass |= (uint32_t)((fw[i] & fm) == fm) << i;
+    }
+    return pass & valid;
+}
 
-    // ---- C: dense probing of the queue ----
+// Dense probing of a block's survivor queue (entries: key | local position << 35): every thread keeps PROBE_U bucket
+// lines in flight; a hit parks its payload at the local position and sets the position's bit.
+__device__ __forceinline__ void probe_queue(const KgTableView& tab, const unsigned long long* queue, uint32_t nsurv, int4* pstage,
+                                            uint32_t* hitbits, uint64_t pol_stream) {
+    const int tid = threadIdx.x;
     for (uint32_t k0 = 0; k0 < nsurv; k0 += PROBE_BLK * PROBE_U) {
         uint64_t key[PROBE_U];
         uint32_t lp[PROBE_U], bkt[PROBE_U], slot[PROBE_U];
@@ -311,6 +287,52 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe(const uint8_t
                 atomicOr(&hitbits[lp[u] >> 5], 1u << (lp[u] & 31));
             }
     }
+}
+
+__global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe(const uint8_t* __restrict__ stream, uint32_t vtotal, KgTableView tab,
+                                                        uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload,
+                                                        uint32_t hit_cap, uint32_t* __restrict__ tile_base,
+                                                        uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr,
+                                                        uint32_t flags) {
+    extern __shared__ int4 smem_dyn[];
+    int4* pstage = smem_dyn;                                                        // [TILE]
+    unsigned long long* queue = reinterpret_cast<unsigned long long*>(smem_dyn + TILE); // [TILE]
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t hitbits[TILE / 32];
+    __shared__ uint32_t warp_a[PROBE_BLK / 32], warp_b[PROBE_BLK / 32], warp_kmers[PROBE_BLK / 32];
+    __shared__ uint32_t s_base;
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += PROBE_BLK) lut[i] = (i >= 'A' && i <= 'Z') ? c_aa_code[i - 'A'] : 20;
+    if (tid < TILE / 32) hitbits[tid] = 0;
+    __syncthreads();
+
+    const uint64_t pol_keep = kg_policy_evict_last();
+    const uint64_t pol_stream = (flags & 1u) ? kg_policy_evict_normal() : kg_policy_evict_first();
+    const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
+
+    // ---- A: encode + prefilter ----
+    uint32_t pass = 0, nk = 0;
+    uint32_t q[PT + 4];
+    if (p0 < vtotal) {
+        const uint32_t valid = encode_windows(stream, p0, vtotal, lut, q);
+        nk = __popc(valid); // lookups = windows the reference enumerates (KGJ:912-921)
+        pass = valid;
+        if (tab.filter_words) pass = filter_windows(tab, q, valid, flags, pol_keep);
+    }
+
+    // ---- B: survivors -> shared-memory queue, tile order ----
+    uint32_t nsurv;
+    uint32_t qo = block_excl_scan(__popc(pass), warp_a, &nsurv);
+#pragma unroll
+    for (int i = 0; i < PT; i++)
+        if ((pass >> i) & 1u) queue[qo++] = ((uint64_t)q[i] * 160000ull + q[i + 4]) | ((unsigned long long)(tid * PT + i) << 35);
+    const uint32_t wk = __reduce_add_sync(0xFFFFFFFFu, nk);
+    if ((tid & 31) == 0) warp_kmers[tid >> 5] = wk;
+    __syncthreads();
+
+    // ---- C: dense probing of the queue ----
+    probe_queue(tab, queue, nsurv, pstage, hitbits, pol_stream);
     __syncthreads();
 
     // ---- D: hits out, tile order ----
@@ -1108,12 +1130,16 @@ static uint32_t probe_flags() { // experiment switches: bit 0 = no evict_first o
 // Enqueue one whole pass (prepare -> probe -> scan -> FSM -> scan -> compact) on the compute stream; no host
 // synchronisation.  The hit buffers are sized from a guess (half the positions, or what an earlier run needed); if a
 // tile cannot claim its chunk the kernels downstream skip their work and pipe_finish repeats the pass with the exact size.
+// A custom probe stage (the hash-sharded table, kg_shard.cuh) stands in for k_probe: it must fill chunk_pos /
+// chunk_payload / tile_base / tile_cnt and the HITS and KMERS counters on the given stream; the batch is then already prepared.
+using ProbeStage = std::function<int(PipeSlot& sl, unsigned long long* d_ctr, uint64_t hit_cap, cudaStream_t st)>;
+
 static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result* r,
-                        uint64_t hit_cap_hint, uint32_t seq_base) {
+                        uint64_t hit_cap_hint, uint32_t seq_base, const ProbeStage* custom = nullptr) {
     cudaStream_t st = ctx->stream;
     sl.launches = 0;
     cudaEventRecord(sl.ev[0], st);
-    KG_TRY(kg_batch_prepare(b, st, &sl.launches));
+    if (!custom) KG_TRY(kg_batch_prepare(b, st, &sl.launches));
     const uint64_t nv = b->nv, vtotal = b->vtotal;
     const int per_seq = b->mode == KG_MODE_AA ? 1 : 6;
     const uint32_t ntiles = (uint32_t)((vtotal + TILE - 1) >> TILE_SHIFT);
@@ -1149,7 +1175,9 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
     CU(cudaMemsetAsync(d_ctr, 0, KG_CTR_COUNT * 8, st));
     CU(cudaMemsetAsync(sl.tile_cnt.p, 0, ((size_t)ntiles + 1) * 4, st));
     cudaEventRecord(sl.ev[1], st);
-    if (ntiles) {
+    if (custom) {
+        KG_TRY((*custom)(sl, d_ctr, hit_cap, st));
+    } else if (ntiles) {
         k_probe<<<ntiles, PROBE_BLK, PROBE_SMEM, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sl.chunk_pos.as<uint32_t>(),
                                                       sl.chunk_payload.as<int4>(), (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
                                                       sl.tile_cnt.as<uint32_t>(), d_ctr, probe_flags());
@@ -1254,7 +1282,7 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
 // Wait for the pass, repeat it once if the hit buffers were too small, fill in the statistics, and (for "-d") build the
 // position-ordered HIT records.
 static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result* r,
-                       uint32_t seq_base) {
+                       uint32_t seq_base, const ProbeStage* custom = nullptr) {
     cudaStream_t st = ctx->stream;
     RunScratch& sc = scratch_of(ctx);
     uint32_t launches = 0;
@@ -1264,7 +1292,7 @@ static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_
         launches += sl.launches;
         if (!sl.h_ctr[KG_CTR_OVERFLOW]) break;
         if (attempt) KG_FAIL(KG_ECUDA, "hit buffer overflow persisted after resizing to %llu", (unsigned long long)sl.hit_cap);
-        KG_TRY(pipe_enqueue(ctx, sl, table, b, prm, r, sl.h_ctr[KG_CTR_HITS], seq_base)); // exact size
+        KG_TRY(pipe_enqueue(ctx, sl, table, b, prm, r, sl.h_ctr[KG_CTR_HITS], seq_base, custom)); // exact size
     }
     const uint64_t nhits = sl.h_ctr[KG_CTR_HITS], nkmers = sl.h_ctr[KG_CTR_KMERS];
     sc.hit_cap_seen = std::max<uint64_t>(sc.hit_cap_seen, nhits + nhits / 16 + 1024);
@@ -1314,6 +1342,7 @@ static int check_params(const kg_params* p) {
 extern "C" int kg_batch_run(kg_context* ctx, const kg_table* table, kg_batch* batch, const kg_params* params,
                             kg_result** out) {
     if (!ctx || !table || !batch || !out) KG_FAIL(KG_EINVAL, "kg_batch_run: null argument");
+    if (table->shard_count > 1) KG_FAIL(KG_EINVAL, "kg_batch_run: the table is shard %d of %d; use kg_batch_run_sharded", table->shard_rank, table->shard_count);
     KG_TRY(check_params(params));
     CU(cudaSetDevice(ctx->device));
     kg_result* r = new kg_result();
@@ -1358,6 +1387,7 @@ extern "C" int kg_result_fetch(kg_result* r) {
 extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const uint8_t* seq_bytes, const uint64_t* offsets,
                       size_t n, const kg_params* params, kg_result** out) {
     if (!ctx || !table || !out || !offsets || (mode != KG_MODE_AA && mode != KG_MODE_DNA)) KG_FAIL(KG_EINVAL, "kg_run: bad argument");
+    if (table->shard_count > 1) KG_FAIL(KG_EINVAL, "kg_run: the table is shard %d of %d; use kg_batch_run_sharded", table->shard_rank, table->shard_count);
     KG_TRY(check_params(params));
     if (offsets[0] != 0) KG_FAIL(KG_EINVAL, "kg_run: offsets[0] must be 0");
     // offsets are checked slice by slice (validate, below) while the GPU already works on the slices before
@@ -1589,3 +1619,5 @@ extern "C" void kg_result_free(kg_result* r) {
     pool_give_host(r->ctx, &r->h_hits);
     delete r;
 }
+
+#include "kg_shard.cuh" // hash-sharded table (same translation unit: it reuses the probe helpers and the pipeline)

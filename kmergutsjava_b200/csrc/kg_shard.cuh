@@ -1,0 +1,713 @@
+// kg_shard.cuh -- the hash-sharded signature table (include/kmerguts_shard.h; BASELINE.json configs[4]).
+// Included at the end of kg_run.cu: it reuses that file's window encoder, prefilter, probe loop and the whole pipeline
+// downstream of the probe.
+//
+//   k_route              addKmers (KGJ:900-922) + "which GPU holds this key": valid windows binned by kg_owner_of()
+//   keys exchange        NCCL send/recv (one process per GPU) or peer copies (all ranks in one process)
+//   k_answer             lookup (KGJ:944-1034) of the received keys against this rank's shard -> replies for the hits
+//   replies exchange     {index of the query in the asker's bin, payload}
+//   k_scatter_replies    replies -> bit + payload at the residue position they belong to
+//   k_tiles_from_bitmap  the per-tile hit chunks k_probe would have written; from here on the pipeline is unchanged
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/kmerguts_shard.h"
+
+namespace {
+
+// ---- NCCL, loaded on first use: a single-GPU deployment needs no libnccl ----
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!api.h) return api;
+    bool all = true;
+    auto sym = [&](const char* name) {
+        void* p = dlsym(api.h, name);
+        if (!p) all = false;
+        return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.ok = all;
+    return api;
+}
+#define NC(call)                                                                                                      \
+    do {                                                                                                              \
+        ncclResult_t e_ = (call);                                                                                     \
+        if (e_ != ncclSuccess) KG_FAIL(KG_ECUDA, "%s failed: %s", #call, nccl_api().GetErrorString(e_));              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SHARD_CNT_SLOTS = 2 * KG_MAX_RANKS; // [0, R): keys per owner; [KG_MAX_RANKS]: valid windows of the batch
+
+// One tile of TILE positions per block, PT per thread, like k_probe.  The valid windows go to the bin of their owner:
+// send_keys[owner * cap + i] = key, send_pos[owner * cap + i] = residue position (stays here; the reply names i).
+// Slots inside a bin are claimed per tile (one global atomic per owner and tile), warp-aggregated inside the tile.
+__global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__ stream, uint32_t vtotal, uint32_t nranks, unsigned long long cap,
+                                                     unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ send_pos,
+                                                     unsigned long long* __restrict__ send_cnt) {
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t cnt[KG_MAX_RANKS];
+    __shared__ unsigned long long base[KG_MAX_RANKS];
+    __shared__ uint32_t warp_kmers[PROBE_BLK / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 256; i += PROBE_BLK) lut[i] = (i >= 'A' && i <= 'Z') ? c_aa_code[i - 'A'] : 20;
+    if (tid < KG_MAX_RANKS) cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
+    uint32_t q[PT + 4];
+    uint32_t valid = 0;
+    if (p0 < vtotal) valid = encode_windows(stream, p0, vtotal, lut, q);
+    uint32_t own[PT], lr[PT];
+#pragma unroll
+    for (int i = 0; i < PT; i++) {
+        const bool ok = (valid >> i) & 1u;
+        own[i] = ok ? kg_owner_of((uint64_t)q[i] * 160000ull + q[i + 4], nranks) : nranks; // nranks = "nobody"
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, own[i]);
+        const int leader = __ffs(peers) - 1;
+        uint32_t b = 0;
+        if (lane == leader && ok) b = atomicAdd(&cnt[own[i]], (uint32_t)__popc(peers));
+        b = __shfl_sync(0xFFFFFFFFu, b, leader);
+        lr[i] = b + __popc(peers & ((1u << lane) - 1u));
+    }
+    const uint32_t wk = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(valid));
+    if (lane == 0) warp_kmers[tid >> 5] = wk;
+    __syncthreads();
+    if (tid < (int)nranks) base[tid] = cnt[tid] ? atomicAdd(&send_cnt[tid], (unsigned long long)cnt[tid]) : 0ull;
+    if (tid == PROBE_BLK - 1) {
+        uint32_t kmers = 0;
+#pragma unroll
+        for (int w = 0; w < PROBE_BLK / 32; w++) kmers += warp_kmers[w];
+        if (kmers) atomicAdd(&send_cnt[KG_MAX_RANKS], (unsigned long long)kmers);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PT; i++) {
+        if (!((valid >> i) & 1u)) continue;
+        const unsigned long long o = base[own[i]] + lr[i];
+        if (o < cap) { // a bin that overflows is only counted: the host repeats the pass with the exact capacity
+            send_keys[own[i] * cap + o] = (uint64_t)q[i] * 160000ull + q[i + 4];
+            send_pos[own[i] * cap + o] = p0 + (uint32_t)i;
+        }
+    }
+}
+
+// The keys received from rank s are segment s of recv_keys; its tiles are blocks [tile_first[s], tile_first[s + 1]).
+struct AnswerPlan {
+    uint32_t nseg;
+    uint32_t tile_first[KG_MAX_RANKS + 1];
+    unsigned long long seg_off[KG_MAX_RANKS + 1];
+};
+
+// k_probe with the encoder replaced by "read the key": prefilter -> survivor queue -> dense probing -> hits out.  A hit
+// becomes a reply {index of the query inside its segment, payload} appended to the segment's reply region (which
+// starts at the segment's own offset: there are never more replies than queries).
+__global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const unsigned long long* __restrict__ recv_keys, AnswerPlan plan, KgTableView tab,
+                                                                    uint32_t* __restrict__ reply_idx, int4* __restrict__ reply_payload,
+                                                                    unsigned long long* __restrict__ reply_cnt, uint32_t flags) {
+    extern __shared__ int4 smem_dyn[];
+    int4* pstage = smem_dyn;
+    unsigned long long* queue = reinterpret_cast<unsigned long long*>(smem_dyn + TILE);
+    __shared__ uint32_t hitbits[TILE / 32];
+    __shared__ uint32_t warp_a[PROBE_BLK / 32], warp_b[PROBE_BLK / 32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+    if (tid < TILE / 32) hitbits[tid] = 0;
+    __syncthreads();
+    uint32_t s = 0;
+    while (s + 1 < plan.nseg && blockIdx.x >= plan.tile_first[s + 1]) s++;
+    const unsigned long long n_s = plan.seg_off[s + 1] - plan.seg_off[s];
+    const unsigned long long* keys = recv_keys + plan.seg_off[s];
+    const unsigned long long k0 = (unsigned long long)(blockIdx.x - plan.tile_first[s]) * TILE + (unsigned long long)tid * PT;
+    const uint64_t pol_keep = kg_policy_evict_last();
+    const uint64_t pol_stream = (flags & 1u) ? kg_policy_evict_normal() : kg_policy_evict_first();
+
+    uint64_t key[PT];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int i = 0; i < PT; i++) {
+        key[i] = 0;
+        if (k0 + i < n_s) {
+            key[i] = keys[k0 + i];
+            valid |= 1u << i;
+        }
+    }
+    uint32_t pass = valid;
+    if (tab.filter_words) {
+        unsigned long long fw[PT];
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            fw[i] = 0;
+            if ((valid >> i) & 1u) fw[i] = kg_load_filter_word(tab.filter, kg_filter_word(kg_mix(key[i]), tab.filter_words), pol_keep);
+        }
+        pass = 0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            const unsigned long long fm = kg_filter_mask(kg_mix(key[i]));
+            pass |= (uint32_t)((fw[i] & fm) == fm) << i;
+        }
+        pass &= valid;
+    }
+    uint32_t nsurv;
+    uint32_t qo = block_excl_scan(__popc(pass), warp_a, &nsurv);
+#pragma unroll
+    for (int i = 0; i < PT; i++)
+        if ((pass >> i) & 1u) queue[qo++] = key[i] | ((unsigned long long)(tid * PT + i) << 35);
+    __syncthreads();
+    probe_queue(tab, queue, nsurv, pstage, hitbits, pol_stream);
+    __syncthreads();
+    const uint32_t hitmask = (hitbits[(tid * PT) >> 5] >> ((tid * PT) & 31)) & ((1u << PT) - 1u);
+    uint32_t total;
+    const uint32_t ho = block_excl_scan(__popc(hitmask), warp_b, &total);
+    if (tid == 0) s_base = total ? atomicAdd(&reply_cnt[s], (unsigned long long)total) : 0ull;
+    __syncthreads();
+    if (hitmask) {
+        unsigned long long o = plan.seg_off[s] + s_base + ho;
+        uint32_t m = hitmask;
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            reply_idx[o] = (uint32_t)(k0 + i);
+            reply_payload[o] = pstage[tid * PT + i];
+            o++;
+        }
+    }
+}
+
+// replies of owner o: entries [o * cap, o * cap + (first[o + 1] - first[o])) of rr_idx / rr_payload
+struct ScatterPlan {
+    uint32_t nseg;
+    unsigned long long first[KG_MAX_RANKS + 1];
+};
+__global__ void k_scatter_replies(const uint32_t* __restrict__ rr_idx, const int4* __restrict__ rr_payload, ScatterPlan plan, unsigned long long cap,
+                                  const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
+                                  uint32_t* __restrict__ bitmap, int4* __restrict__ payload_at, unsigned long long* __restrict__ ctr) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= plan.first[plan.nseg]) return;
+    uint32_t o = 0;
+    while (g >= plan.first[o + 1]) o++;
+    const unsigned long long j = g - plan.first[o];
+    const uint32_t idx = rr_idx[o * cap + j];
+    if (idx >= send_cnt[o]) { // a reply that names no query of ours: the peer's answer is corrupt
+        ctr[KG_CTR_OVERFLOW] = 2ull;
+        return;
+    }
+    const uint32_t pos = send_pos[o * cap + idx];
+    payload_at[pos] = rr_payload[o * cap + j];
+    atomicOr(&bitmap[pos >> 5], 1u << (pos & 31));
+}
+
+// phase D of k_probe, fed from the bitmap: per-tile hit chunks in position order
+__global__ __launch_bounds__(PROBE_BLK) void k_tiles_from_bitmap(const uint32_t* __restrict__ bitmap, const int4* __restrict__ payload_at,
+                                                                 uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload, uint32_t hit_cap,
+                                                                 uint32_t* __restrict__ tile_base, uint32_t* __restrict__ tile_cnt,
+                                                                 unsigned long long* __restrict__ ctr, unsigned long long kmers) {
+    __shared__ uint32_t warp_b[PROBE_BLK / 32];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x;
+    const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
+    const uint32_t hitmask = (bitmap[p0 >> 5] >> (p0 & 31)) & ((1u << PT) - 1u);
+    uint32_t total;
+    const uint32_t ho = block_excl_scan(__popc(hitmask), warp_b, &total);
+    if (tid == 0) {
+        if (blockIdx.x == 0 && kmers) atomicAdd(&ctr[KG_CTR_KMERS], kmers);
+        unsigned long long base = 0;
+        if (total) base = atomicAdd(&ctr[KG_CTR_HITS], (unsigned long long)total);
+        uint32_t b32 = 0xFFFFFFFFu;
+        if (base + total <= (unsigned long long)hit_cap) b32 = (uint32_t)base;
+        else ctr[KG_CTR_OVERFLOW] = 1ull;
+        s_base = b32;
+        tile_base[blockIdx.x] = b32;
+        tile_cnt[blockIdx.x] = total;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (base != 0xFFFFFFFFu && hitmask) {
+        uint32_t o = base + ho;
+        uint32_t m = hitmask;
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            chunk_pos[o] = p0 + (uint32_t)i;
+            chunk_payload[o] = payload_at[p0 + i];
+            o++;
+        }
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// communicator
+// ---------------------------------------------------------------------------------------------------------------
+struct KgLocalGroup {
+    std::vector<kg_comm*> members;
+    int alive = 0;
+};
+
+struct kg_comm {
+    kg_context* ctx = nullptr;
+    int rank = 0, nranks = 1;
+    ncclComm_t nccl = nullptr;
+    KgLocalGroup* group = nullptr;
+    // device scratch, grow-only
+    DevBuf send_keys, send_pos, send_cnt, recv_keys, reply_idx, reply_payload, reply_cnt, rr_idx, rr_payload, bitmap, payload_at, matrix;
+    uint64_t* h = nullptr; // pinned: [0, 32) route counters, [32, 64) reply counters, [64, 64 + 32 * 16) gathered counters
+    cudaEvent_t ev[5] = {};
+    kg_shard_stats stats = {};
+    // state of the run in flight
+    uint64_t cap = 0, cap_seen = 0, kmers = 0;
+    uint64_t send_n[KG_MAX_RANKS] = {}, recv_n[KG_MAX_RANKS] = {}, recv_off[KG_MAX_RANKS + 1] = {};
+    uint64_t reply_n[KG_MAX_RANKS] = {}, rr_n[KG_MAX_RANKS] = {};
+};
+
+namespace {
+
+int comm_alloc(kg_context* ctx, int rank, int nranks, kg_comm** out) {
+    CU(cudaSetDevice(ctx->device));
+    kg_comm* c = new kg_comm();
+    c->ctx = ctx;
+    c->rank = rank;
+    c->nranks = nranks;
+    if (cudaMallocHost(&c->h, (64 + SHARD_CNT_SLOTS * KG_MAX_RANKS) * sizeof(uint64_t)) != cudaSuccess) {
+        delete c;
+        KG_FAIL(KG_ENOMEM, "kg_comm: pinned counters");
+    }
+    for (auto& e : c->ev) cudaEventCreate(&e);
+    *out = c;
+    return KG_OK;
+}
+
+// ---- phase 1: encode + bin by owner; ends with the bin sizes on the host ----
+int shard_route(kg_comm* c, kg_batch* b) {
+    kg_context* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t R = (uint32_t)c->nranks;
+    c->stats = kg_shard_stats();
+    cudaEventRecord(c->ev[0], st);
+    uint32_t launches = 0;
+    KG_TRY(kg_batch_prepare(b, st, &launches));
+    const uint64_t vtotal = b->vtotal;
+    const uint32_t ntiles = (uint32_t)((vtotal + TILE - 1) >> TILE_SHIFT);
+    // bins: an even split plus an eighth, or what an earlier run needed; exact on the second attempt
+    uint64_t cap = R == 1 ? vtotal : std::max<uint64_t>(vtotal / R + vtotal / (8 * R) + 4096, c->cap_seen);
+    cap = std::max<uint64_t>(std::min<uint64_t>(cap, std::max<uint64_t>(vtotal, 1)), 1);
+    KG_TRY(c->send_cnt.ensure(SHARD_CNT_SLOTS * 8));
+    for (int attempt = 0;; attempt++) {
+        KG_TRY(c->send_keys.ensure(R * cap * 8));
+        KG_TRY(c->send_pos.ensure(R * cap * 4));
+        CU(cudaMemsetAsync(c->send_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
+        if (ntiles)
+            k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, R, cap, c->send_keys.as<unsigned long long>(),
+                                                  c->send_pos.as<uint32_t>(), c->send_cnt.as<unsigned long long>());
+        CU(cudaMemcpyAsync(c->h, c->send_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        uint64_t mx = 0;
+        for (uint32_t r = 0; r < R; r++) mx = std::max(mx, c->h[r]);
+        if (mx <= cap) break;
+        if (attempt) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: bin overflow persisted at capacity %llu", (unsigned long long)cap);
+        cap = mx; // a skewed batch (e.g. low-complexity repeats all hashing to one owner)
+    }
+    c->cap = cap;
+    c->cap_seen = std::max(c->cap_seen, cap);
+    c->kmers = c->h[KG_MAX_RANKS];
+    for (uint32_t r = 0; r < R; r++) {
+        c->send_n[r] = c->h[r];
+        c->stats.keys_sent += c->send_n[r];
+        if ((int)r != c->rank) c->stats.keys_remote += c->send_n[r];
+    }
+    cudaEventRecord(c->ev[1], st);
+    return KG_OK;
+}
+
+// every rank's counter block -> every rank (NCCL transport); returns the row of `from` in the pinned matrix
+int gather_counters(kg_comm* c, const DevBuf& mine) {
+    NcclApi& nc = nccl_api();
+    cudaStream_t st = c->ctx->stream;
+    KG_TRY(c->matrix.ensure((size_t)SHARD_CNT_SLOTS * 8 * c->nranks));
+    NC(nc.AllGather(mine.p, c->matrix.p, SHARD_CNT_SLOTS, ncclUint64, c->nccl, st));
+    CU(cudaMemcpyAsync(c->h + 64, c->matrix.p, (size_t)SHARD_CNT_SLOTS * 8 * c->nranks, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return KG_OK;
+}
+
+// ---- keys: learn what arrives, make room, move the bins ----
+int shard_exchange_keys(kg_comm* c) {
+    kg_context* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int R = c->nranks;
+    if (c->nccl) {
+        KG_TRY(gather_counters(c, c->send_cnt));
+        for (int s = 0; s < R; s++) c->recv_n[s] = c->h[64 + (size_t)s * SHARD_CNT_SLOTS + c->rank];
+    } else if (c->group) {
+        for (int s = 0; s < R; s++) c->recv_n[s] = c->group->members[s]->send_n[c->rank];
+    } else {
+        c->recv_n[0] = c->send_n[0];
+    }
+    c->recv_off[0] = 0;
+    for (int s = 0; s < R; s++) c->recv_off[s + 1] = c->recv_off[s] + c->recv_n[s];
+    const uint64_t nrecv = c->recv_off[R];
+    c->stats.keys_received = nrecv;
+    KG_TRY(c->recv_keys.ensure(std::max<uint64_t>(nrecv, 1) * 8));
+    KG_TRY(c->reply_idx.ensure(std::max<uint64_t>(nrecv, 1) * 4));
+    KG_TRY(c->reply_payload.ensure(std::max<uint64_t>(nrecv, 1) * sizeof(int4)));
+    KG_TRY(c->reply_cnt.ensure(SHARD_CNT_SLOTS * 8));
+    unsigned long long* sk = c->send_keys.as<unsigned long long>();
+    unsigned long long* rk = c->recv_keys.as<unsigned long long>();
+    if (c->nccl) {
+        NcclApi& nc = nccl_api();
+        NC(nc.GroupStart());
+        for (int p = 0; p < R; p++) {
+            if (p == c->rank) continue;
+            if (c->send_n[p]) NC(nc.Send(sk + p * c->cap, c->send_n[p], ncclUint64, p, c->nccl, st));
+            if (c->recv_n[p]) NC(nc.Recv(rk + c->recv_off[p], c->recv_n[p], ncclUint64, p, c->nccl, st));
+            c->stats.bytes_sent += c->send_n[p] * 8;
+        }
+        NC(nc.GroupEnd());
+        if (c->send_n[c->rank]) CU(cudaMemcpyAsync(rk + c->recv_off[c->rank], sk + c->rank * c->cap, c->send_n[c->rank] * 8, cudaMemcpyDeviceToDevice, st));
+    } else if (c->group) { // every member has finished its route phase (host-synchronised): pull the bins
+        for (int s = 0; s < R; s++) {
+            kg_comm* src = c->group->members[s];
+            if (!c->recv_n[s]) continue;
+            CU(cudaMemcpyPeerAsync(rk + c->recv_off[s], ctx->device, src->send_keys.as<unsigned long long>() + c->rank * src->cap, src->ctx->device,
+                                   c->recv_n[s] * 8, st));
+            if (s != c->rank) src->stats.bytes_sent += c->recv_n[s] * 8;
+        }
+    } else if (nrecv) {
+        CU(cudaMemcpyAsync(rk, sk, nrecv * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    cudaEventRecord(c->ev[2], st);
+    return KG_OK;
+}
+
+// ---- phase 2: probe the received keys; ends with the reply counts on the host ----
+int shard_answer(kg_comm* c, const kg_table* table) {
+    kg_context* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int R = c->nranks;
+    AnswerPlan plan = {};
+    plan.nseg = (uint32_t)R;
+    uint64_t tiles = 0;
+    for (int s = 0; s < R; s++) {
+        plan.tile_first[s] = (uint32_t)tiles;
+        plan.seg_off[s] = c->recv_off[s];
+        tiles += (c->recv_n[s] + TILE - 1) >> TILE_SHIFT;
+    }
+    plan.tile_first[R] = (uint32_t)tiles;
+    plan.seg_off[R] = c->recv_off[R];
+    if (tiles > 0x7FFFFFFFull) KG_FAIL(KG_ERANGE, "kg_batch_run_sharded: %llu keys received in one step", (unsigned long long)c->recv_off[R]);
+    CU(cudaMemsetAsync(c->reply_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
+    if (tiles)
+        k_answer<<<(unsigned)tiles, PROBE_BLK, PROBE_SMEM, st>>>(c->recv_keys.as<unsigned long long>(), plan, table->view(), c->reply_idx.as<uint32_t>(),
+                                                                 c->reply_payload.as<int4>(), c->reply_cnt.as<unsigned long long>(), probe_flags());
+    cudaEventRecord(c->ev[3], st);
+    CU(cudaMemcpyAsync(c->h + 32, c->reply_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (int s = 0; s < R; s++) {
+        c->reply_n[s] = c->h[32 + s];
+        if (c->reply_n[s] > c->recv_n[s]) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: more replies than queries for rank %d", s);
+        c->stats.replies_sent += c->reply_n[s];
+    }
+    return KG_OK;
+}
+
+// ---- replies: back to the ranks that asked ----
+int shard_exchange_replies(kg_comm* c) {
+    kg_context* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int R = c->nranks;
+    if (c->nccl) {
+        KG_TRY(gather_counters(c, c->reply_cnt));
+        for (int o = 0; o < R; o++) c->rr_n[o] = c->h[64 + (size_t)o * SHARD_CNT_SLOTS + c->rank];
+    } else if (c->group) {
+        for (int o = 0; o < R; o++) c->rr_n[o] = c->group->members[o]->reply_n[c->rank];
+    } else {
+        c->rr_n[0] = c->reply_n[0];
+    }
+    for (int o = 0; o < R; o++) {
+        if (c->rr_n[o] > c->send_n[o]) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: rank %d answers %llu of %llu queries", o, (unsigned long long)c->rr_n[o], (unsigned long long)c->send_n[o]);
+        c->stats.replies_received += c->rr_n[o];
+    }
+    KG_TRY(c->rr_idx.ensure((size_t)R * c->cap * 4));
+    KG_TRY(c->rr_payload.ensure((size_t)R * c->cap * sizeof(int4)));
+    uint32_t* ri = c->rr_idx.as<uint32_t>();
+    int4* rp = c->rr_payload.as<int4>();
+    if (c->nccl) {
+        NcclApi& nc = nccl_api();
+        NC(nc.GroupStart());
+        for (int p = 0; p < R; p++) {
+            if (p == c->rank) continue;
+            if (c->reply_n[p]) {
+                NC(nc.Send(c->reply_idx.as<uint32_t>() + c->recv_off[p], c->reply_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Send(c->reply_payload.as<int4>() + c->recv_off[p], c->reply_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
+                c->stats.bytes_sent += c->reply_n[p] * (4 + sizeof(int4));
+            }
+            if (c->rr_n[p]) {
+                NC(nc.Recv(ri + p * c->cap, c->rr_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Recv(rp + p * c->cap, c->rr_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
+            }
+        }
+        NC(nc.GroupEnd());
+        const int me = c->rank;
+        if (c->reply_n[me]) {
+            CU(cudaMemcpyAsync(ri + me * c->cap, c->reply_idx.as<uint32_t>() + c->recv_off[me], c->reply_n[me] * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(rp + me * c->cap, c->reply_payload.as<int4>() + c->recv_off[me], c->reply_n[me] * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+        }
+    } else if (c->group) {
+        for (int o = 0; o < R; o++) {
+            kg_comm* src = c->group->members[o];
+            if (!c->rr_n[o]) continue;
+            CU(cudaMemcpyPeerAsync(ri + o * c->cap, ctx->device, src->reply_idx.as<uint32_t>() + src->recv_off[c->rank], src->ctx->device, c->rr_n[o] * 4, st));
+            CU(cudaMemcpyPeerAsync(rp + o * c->cap, ctx->device, src->reply_payload.as<int4>() + src->recv_off[c->rank], src->ctx->device,
+                                   c->rr_n[o] * sizeof(int4), st));
+            if (o != c->rank) src->stats.bytes_sent += c->rr_n[o] * (4 + sizeof(int4));
+        }
+    } else if (c->rr_n[0]) {
+        CU(cudaMemcpyAsync(ri, c->reply_idx.p, c->rr_n[0] * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(rp, c->reply_payload.p, c->rr_n[0] * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+    }
+    cudaEventRecord(c->ev[4], st);
+    return KG_OK;
+}
+
+// ---- phase 3: replies -> per-tile hit chunks -> the unchanged rest of the pipeline ----
+int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result** out) {
+    kg_context* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int R = c->nranks;
+    const uint64_t vtotal = b->vtotal;
+    const uint32_t ntiles = (uint32_t)((vtotal + TILE - 1) >> TILE_SHIFT);
+    ScatterPlan sp = {};
+    sp.nseg = (uint32_t)R;
+    for (int o = 0; o < R; o++) sp.first[o + 1] = sp.first[o] + c->rr_n[o];
+    const uint64_t nhits = sp.first[R];
+    const size_t bitmap_bytes = ((size_t)ntiles * TILE) / 8 + 4;
+    KG_TRY(c->bitmap.ensure(bitmap_bytes));
+    KG_TRY(c->payload_at.ensure(std::max<uint64_t>(vtotal, 1) * sizeof(int4)));
+    ProbeStage stage = [&](PipeSlot& sl, unsigned long long* d_ctr, uint64_t hit_cap, cudaStream_t st) -> int {
+        CU(cudaMemsetAsync(c->bitmap.p, 0, bitmap_bytes, st));
+        if (nhits) {
+            k_scatter_replies<<<blocks_for(nhits, 256), 256, 0, st>>>(c->rr_idx.as<uint32_t>(), c->rr_payload.as<int4>(), sp, c->cap,
+                                                                     c->send_cnt.as<unsigned long long>(), c->send_pos.as<uint32_t>(),
+                                                                     c->bitmap.as<uint32_t>(), c->payload_at.as<int4>(), d_ctr);
+            sl.launches++;
+        }
+        if (ntiles) {
+            k_tiles_from_bitmap<<<ntiles, PROBE_BLK, 0, st>>>(c->bitmap.as<uint32_t>(), c->payload_at.as<int4>(), sl.chunk_pos.as<uint32_t>(),
+                                                             sl.chunk_payload.as<int4>(), (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
+                                                             sl.tile_cnt.as<uint32_t>(), d_ctr, c->kmers);
+            sl.launches++;
+        }
+        return KG_OK;
+    };
+    kg_result* r = new kg_result();
+    r->ctx = ctx;
+    RunScratch& sc = scratch_of(ctx);
+    int rc = pipe_enqueue(ctx, sc.slot[0], table, b, prm, r, std::max<uint64_t>(nhits, 1), 0, &stage);
+    if (rc == KG_OK) rc = pipe_finish(ctx, sc.slot[0], table, b, prm, r, 0, &stage);
+    if (rc == KG_OK && r->stats.num_hits != nhits) {
+        // distinct replies always land on distinct positions; fewer bits than replies means a peer answered a query twice
+        kg_set_error("kg_batch_run_sharded: %llu replies but %llu hit positions", (unsigned long long)nhits, (unsigned long long)r->stats.num_hits);
+        rc = KG_ECUDA;
+    }
+    if (rc != KG_OK) {
+        kg_result_free(r);
+        return rc;
+    }
+    r->stats.num_launches += 2 + 1; // k_route, k_answer (+ patch/translate counted by prepare)
+    cudaEventElapsedTime(&c->stats.ms_route, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->stats.ms_keys, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->stats.ms_answer, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->stats.ms_replies, c->ev[3], c->ev[4]);
+    c->stats.ms_merge = r->stats.ms_device;
+    *out = r;
+    return KG_OK;
+}
+
+int shard_check(const kg_comm* c, const kg_table* t, const kg_batch* b, const kg_params* prm) {
+    if (!c || !t || !b) KG_FAIL(KG_EINVAL, "kg_batch_run_sharded: null argument");
+    KG_TRY(check_params(prm));
+    if (t->shard_count != c->nranks || t->shard_rank != c->rank)
+        KG_FAIL(KG_EINVAL, "kg_batch_run_sharded: the table is shard %d of %d, the communicator is rank %d of %d", t->shard_rank, t->shard_count,
+                c->rank, c->nranks);
+    if (b->ctx != c->ctx || t->ctx != c->ctx) KG_FAIL(KG_EINVAL, "kg_batch_run_sharded: table, batch and communicator must share one context");
+    return KG_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int kg_comm_unique_id(uint8_t id[KG_COMM_ID_BYTES]) {
+    if (!id) KG_FAIL(KG_EINVAL, "kg_comm_unique_id: null argument");
+    static_assert(sizeof(ncclUniqueId) == KG_COMM_ID_BYTES, "ncclUniqueId size");
+    NcclApi& nc = nccl_api();
+    if (!nc.ok) KG_FAIL(KG_EIO, "kg_comm_unique_id: libnccl.so.2 not loadable: %s", dlerror());
+    ncclUniqueId u;
+    NC(nc.GetUniqueId(&u));
+    memcpy(id, &u, KG_COMM_ID_BYTES);
+    return KG_OK;
+}
+
+extern "C" int kg_comm_init(kg_context* ctx, int rank, int nranks, const uint8_t id[KG_COMM_ID_BYTES], kg_comm** comm) {
+    if (!ctx || !comm) KG_FAIL(KG_EINVAL, "kg_comm_init: null argument");
+    if (nranks < 1 || nranks > KG_MAX_RANKS || rank < 0 || rank >= nranks) KG_FAIL(KG_EINVAL, "kg_comm_init: rank %d of %d (at most %d ranks)", rank, nranks, KG_MAX_RANKS);
+    kg_comm* c = nullptr;
+    KG_TRY(comm_alloc(ctx, rank, nranks, &c));
+    if (nranks > 1) {
+        NcclApi& nc = nccl_api();
+        if (!id || !nc.ok) {
+            kg_comm_free(c);
+            KG_FAIL(KG_EINVAL, "kg_comm_init: %s", id ? "libnccl.so.2 not loadable" : "null id");
+        }
+        ncclUniqueId u;
+        memcpy(&u, id, KG_COMM_ID_BYTES);
+        ncclResult_t e = nc.CommInitRank(&c->nccl, nranks, u, rank);
+        if (e != ncclSuccess) {
+            c->nccl = nullptr;
+            kg_comm_free(c);
+            KG_FAIL(KG_ECUDA, "ncclCommInitRank failed: %s", nc.GetErrorString(e));
+        }
+    }
+    *comm = c;
+    return KG_OK;
+}
+
+extern "C" int kg_comm_init_local(kg_context* const* ctxs, int nranks, kg_comm** comms) {
+    if (!ctxs || !comms) KG_FAIL(KG_EINVAL, "kg_comm_init_local: null argument");
+    if (nranks < 1 || nranks > KG_MAX_RANKS) KG_FAIL(KG_EINVAL, "kg_comm_init_local: %d ranks (at most %d)", nranks, KG_MAX_RANKS);
+    KgLocalGroup* g = new KgLocalGroup();
+    for (int r = 0; r < nranks; r++) {
+        kg_comm* c = nullptr;
+        int rc = ctxs[r] ? comm_alloc(ctxs[r], r, nranks, &c) : KG_EINVAL;
+        if (rc != KG_OK) {
+            for (kg_comm* m : g->members) {
+                m->group = nullptr;
+                kg_comm_free(m);
+            }
+            delete g;
+            return rc;
+        }
+        c->group = g;
+        g->members.push_back(c);
+    }
+    g->alive = nranks;
+    for (int r = 0; r < nranks; r++) {
+        comms[r] = g->members[r];
+        for (int p = 0; p < nranks; p++) { // peer copies between two devices of this process go direct when they can
+            const int a = ctxs[r]->device, b = ctxs[p]->device;
+            int can = 0;
+            if (a != b && cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+                cudaSetDevice(a);
+                if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError(); // already enabled
+            }
+        }
+    }
+    return KG_OK;
+}
+
+extern "C" void kg_comm_free(kg_comm* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaDeviceSynchronize();
+    if (c->nccl) nccl_api().CommDestroy(c->nccl);
+    for (DevBuf* d : {&c->send_keys, &c->send_pos, &c->send_cnt, &c->recv_keys, &c->reply_idx, &c->reply_payload, &c->reply_cnt, &c->rr_idx,
+                      &c->rr_payload, &c->bitmap, &c->payload_at, &c->matrix})
+        d->release();
+    if (c->h) cudaFreeHost(c->h);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->group && --c->group->alive == 0) delete c->group;
+    delete c;
+}
+
+extern "C" int kg_comm_last_stats(const kg_comm* c, kg_shard_stats* s) {
+    if (!c || !s) KG_FAIL(KG_EINVAL, "kg_comm_last_stats: null argument");
+    *s = c->stats;
+    return KG_OK;
+}
+
+extern "C" int kg_batch_run_sharded(kg_comm* c, const kg_table* shard, kg_batch* batch, const kg_params* params, kg_result** result) {
+    if (!result) KG_FAIL(KG_EINVAL, "kg_batch_run_sharded: null argument");
+    KG_TRY(shard_check(c, shard, batch, params));
+    if (c->group && c->nranks > 1) KG_FAIL(KG_EINVAL, "kg_batch_run_sharded: local communicators run through kg_batch_run_sharded_local");
+    const auto t0 = std::chrono::steady_clock::now();
+    KG_TRY(shard_route(c, batch));
+    KG_TRY(shard_exchange_keys(c));
+    KG_TRY(shard_answer(c, shard));
+    KG_TRY(shard_exchange_replies(c));
+    KG_TRY(shard_merge(c, shard, batch, params, result));
+    c->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return KG_OK;
+}
+
+extern "C" int kg_batch_run_sharded_local(kg_comm* const* comms, const kg_table* const* shards, kg_batch* const* batches, int nranks,
+                                          const kg_params* params, kg_result** results) {
+    if (!comms || !shards || !batches || !results || nranks < 1) KG_FAIL(KG_EINVAL, "kg_batch_run_sharded_local: null argument");
+    for (int r = 0; r < nranks; r++) {
+        KG_TRY(shard_check(comms[r], shards[r], batches[r], params));
+        if (!comms[r]->group || comms[r]->nranks != nranks || comms[r]->group != comms[0]->group || comms[r]->rank != r)
+            KG_FAIL(KG_EINVAL, "kg_batch_run_sharded_local: comms must be the %d members of one local group, in rank order", nranks);
+        results[r] = nullptr;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = KG_OK;
+    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_route(comms[r], batches[r]);
+    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_exchange_keys(comms[r]);
+    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_answer(comms[r], shards[r]);
+    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_exchange_replies(comms[r]);
+    for (int r = 0; r < nranks && rc == KG_OK; r++) { // the reply copies read the owners' buffers: finish them before anyone merges
+        cudaSetDevice(comms[r]->ctx->device);
+        if (cudaStreamSynchronize(comms[r]->ctx->stream) != cudaSuccess) {
+            kg_set_error("kg_batch_run_sharded_local: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = KG_ECUDA;
+        }
+    }
+    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_merge(comms[r], shards[r], batches[r], params, &results[r]);
+    if (rc != KG_OK) {
+        for (int r = 0; r < nranks; r++) {
+            kg_result_free(results[r]);
+            results[r] = nullptr;
+        }
+        return rc;
+    }
+    const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (int r = 0; r < nranks; r++) comms[r]->stats.ms_total = ms;
+    return KG_OK;
+}

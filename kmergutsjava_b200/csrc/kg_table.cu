@@ -69,6 +69,8 @@ struct ImageParser {
     int64_t slot = 0, run_start = 0;
     bool in_run = false;
     int64_t unreachable = 0, unmatchable = 0;
+    int shard_rank = 0, shard_count = 1; // hash-sharded table: keep the keys this rank owns
+    int64_t not_owned = 0;
     std::vector<uint64_t> keys;
     std::vector<int4> payload;
     std::string error;
@@ -106,6 +108,11 @@ struct ImageParser {
                 // (KGJ:959-1026).  It can therefore return this slot iff h lies inside the occupied run that ends here.
                 int64_t h = k % num_slots;
                 if (h >= run_start && h <= slot) {
+                    if (shard_count > 1 && (int)kg_owner_of((uint64_t)k, (uint32_t)shard_count) != shard_rank) {
+                        not_owned++;
+                        slot++;
+                        return;
+                    }
                     int4 p;
                     memcpy(&p, e + 8, 16); // otuIndex, avgFromEnd, functionIndex, functionWt bits (KGJ:996-999)
                     keys.push_back((uint64_t)k);
@@ -408,6 +415,8 @@ static int table_from_parser(kg_context* ctx, ImageParser& ps, kg_table** out) {
     t->info.version = ps.version;
     t->info.num_unreachable = ps.unreachable + ps.unmatchable;
     t->info.tail_run = ps.tail_run();
+    t->shard_rank = ps.shard_rank;
+    t->shard_count = ps.shard_count;
     size_t n = ps.keys.size();
     uint64_t* d_keys = nullptr;
     int4* d_payload = nullptr;
@@ -434,6 +443,26 @@ static int table_from_parser(kg_context* ctx, ImageParser& ps, kg_table** out) {
     return KG_OK;
 }
 
+static int check_shard(int rank, int nranks) {
+    if (nranks < 1 || nranks > KG_MAX_RANKS || rank < 0 || rank >= nranks) KG_FAIL(KG_EINVAL, "shard %d of %d: need 0 <= rank < nranks <= %d", rank, nranks, KG_MAX_RANKS);
+    return KG_OK;
+}
+
+extern "C" int kg_shard_owner(uint64_t key, int nranks) {
+    if (nranks < 1) return -1;
+    return (int)kg_owner_of(key, (uint32_t)nranks);
+}
+
+extern "C" int kg_table_from_image_sharded(kg_context* ctx, const void* image, size_t nbytes, int rank, int nranks, kg_table** table) {
+    if (!ctx || !image || !table) KG_FAIL(KG_EINVAL, "kg_table_from_image: null argument");
+    KG_TRY(check_shard(rank, nranks));
+    ImageParser ps;
+    ps.shard_rank = rank;
+    ps.shard_count = nranks;
+    if (!ps.feed((const uint8_t*)image, nbytes)) KG_FAIL(KG_EFORMAT, "%s", ps.error.c_str());
+    return table_from_parser(ctx, ps, table);
+}
+
 extern "C" int kg_table_from_image(kg_context* ctx, const void* image, size_t nbytes, kg_table** table) {
     if (!ctx || !image || !table) KG_FAIL(KG_EINVAL, "kg_table_from_image: null argument");
     ImageParser ps;
@@ -441,9 +470,11 @@ extern "C" int kg_table_from_image(kg_context* ctx, const void* image, size_t nb
     return table_from_parser(ctx, ps, table);
 }
 
-extern "C" int kg_table_load_file(kg_context* ctx, const char* path, kg_table** table) {
+static int load_file_impl(kg_context* ctx, const char* path, int rank, int nranks, kg_table** table) {
     if (!ctx || !path || !table) KG_FAIL(KG_EINVAL, "kg_table_load_file: null argument");
     ImageParser ps;
+    ps.shard_rank = rank;
+    ps.shard_count = nranks;
     std::vector<uint8_t> buf(8u << 20);
     size_t len = strlen(path);
     bool gz = len > 3 && strcmp(path + len - 3, ".gz") == 0; // the reference keys on the suffix (KGJ:927)
@@ -480,14 +511,19 @@ extern "C" int kg_table_load_file(kg_context* ctx, const char* path, kg_table** 
     return table_from_parser(ctx, ps, table);
 }
 
-extern "C" int kg_table_load(kg_context* ctx, const char* data_dir, kg_table** table) {
+extern "C" int kg_table_load_file(kg_context* ctx, const char* path, kg_table** table) { return load_file_impl(ctx, path, 0, 1, table); }
+
+extern "C" int kg_table_load_sharded(kg_context* ctx, const char* data_dir, int rank, int nranks, kg_table** table) {
     if (!ctx || !data_dir || !table) KG_FAIL(KG_EINVAL, "kg_table_load: null argument");
+    KG_TRY(check_shard(rank, nranks));
     std::string base = std::string(data_dir) + "/kmer.table.mem_map";
     std::string gz = base + ".gz";
     struct stat st;
-    if (stat(gz.c_str(), &st) == 0) return kg_table_load_file(ctx, gz.c_str(), table); // KGJ:750-753
-    return kg_table_load_file(ctx, base.c_str(), table);
+    if (stat(gz.c_str(), &st) == 0) return load_file_impl(ctx, gz.c_str(), rank, nranks, table); // KGJ:750-753
+    return load_file_impl(ctx, base.c_str(), rank, nranks, table);
 }
+
+extern "C" int kg_table_load(kg_context* ctx, const char* data_dir, kg_table** table) { return kg_table_load_sharded(ctx, data_dir, 0, 1, table); }
 
 extern "C" int kg_table_from_device_entries(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, size_t n,
                                             kg_table** table) {
@@ -502,6 +538,59 @@ extern "C" int kg_table_from_device_entries(kg_context* ctx, const uint64_t* d_k
         kg_table_free(t);
         return rc;
     }
+    *table = t;
+    return KG_OK;
+}
+
+namespace {
+__global__ void k_owner_flag(const uint64_t* __restrict__ keys, size_t n, uint32_t rank, uint32_t nranks, uint8_t* __restrict__ flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = kg_owner_of(keys[i], nranks) == rank;
+}
+} // namespace
+
+extern "C" int kg_table_from_device_entries_sharded(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, size_t n,
+                                                    int rank, int nranks, kg_table** table) {
+    if (!ctx || !table || (n && (!d_keys || !d_payload16))) KG_FAIL(KG_EINVAL, "kg_table_from_device_entries_sharded: null argument");
+    KG_TRY(check_shard(rank, nranks));
+    if (nranks == 1) return kg_table_from_device_entries(ctx, d_keys, d_payload16, n, table);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf flag, keys, payload, count, tmp;
+    int rc = KG_OK;
+    kg_table* t = nullptr;
+    do {
+        // entries this rank owns, compacted in their original order (the builder wants distinct keys, not an order)
+        if ((rc = flag.ensure(std::max<size_t>(n, 1))) != KG_OK || (rc = keys.ensure(std::max<size_t>(n, 1) * 8)) != KG_OK ||
+            (rc = payload.ensure(std::max<size_t>(n, 1) * sizeof(int4))) != KG_OK || (rc = count.ensure(16)) != KG_OK)
+            break;
+        size_t owned = 0;
+        if (n) {
+            k_owner_flag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_keys, n, (uint32_t)rank, (uint32_t)nranks, flag.as<uint8_t>());
+            size_t tb1 = 0, tb2 = 0;
+            cub::DeviceSelect::Flagged(nullptr, tb1, d_keys, flag.as<uint8_t>(), keys.as<uint64_t>(), count.as<size_t>(), n, st);
+            cub::DeviceSelect::Flagged(nullptr, tb2, (const int4*)d_payload16, flag.as<uint8_t>(), payload.as<int4>(), count.as<size_t>(), n, st);
+            if ((rc = tmp.ensure(std::max(tb1, tb2))) != KG_OK) break;
+            cub::DeviceSelect::Flagged(tmp.p, tb1, d_keys, flag.as<uint8_t>(), keys.as<uint64_t>(), count.as<size_t>(), n, st);
+            cub::DeviceSelect::Flagged(tmp.p, tb2, (const int4*)d_payload16, flag.as<uint8_t>(), payload.as<int4>(), count.as<size_t>(), n, st);
+            if (cudaMemcpyAsync(&owned, count.p, sizeof(size_t), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+                kg_set_error("kg_table_from_device_entries_sharded: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = KG_ECUDA;
+                break;
+            }
+        }
+        flag.release();
+        tmp.release();
+        rc = kg_table_from_device_entries(ctx, keys.as<uint64_t>(), payload.p, owned, &t);
+    } while (0);
+    flag.release();
+    keys.release();
+    payload.release();
+    count.release();
+    tmp.release();
+    if (rc != KG_OK) return rc;
+    t->shard_rank = rank;
+    t->shard_count = nranks;
     *table = t;
     return KG_OK;
 }

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     names = set()
-    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_synth.h"):
+    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_synth.h", "kmerguts_shard.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(kg_[a-z0-9_]+)\s*\(", src))
@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_no_torch_types_in_signatures():
-    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_synth.h"):
+    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_synth.h", "kmerguts_shard.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         assert "torch" not in src and "at::" not in src and "std::" not in src
 
@@ -42,6 +42,28 @@ def test_no_torch_types_in_signatures():
 def test_struct_layouts_match_numpy_views():
     assert kg.CALL_DTYPE.itemsize == 32 and kg.OTU_DTYPE.itemsize == 44 and kg.HIT_DTYPE.itemsize == 28
     assert C.sizeof(kg.Params) == 20 and C.sizeof(kg.TableInfo) == 72
+
+
+def test_shard_owner_partitions_keys():
+    """kg_shard_owner (include/kmerguts_shard.h): every key has exactly one owner, the split is even, and it is not
+    correlated with the bucket hash (a python restatement of the two murmur mixes)."""
+    M = (1 << 64) - 1
+
+    def mix(k):
+        k ^= k >> 33
+        k = (k * 0xff51afd7ed558ccd) & M
+        k ^= k >> 33
+        k = (k * 0xc4ceb9fe1a85ec53) & M
+        return k ^ (k >> 33)
+
+    rng = np.random.default_rng(5)
+    keys = [int(k) for k in rng.integers(0, 20 ** 8, 4000)] + [0, 1, 20 ** 8 - 1]
+    for R in (1, 2, 3, 8, 16):
+        own = [kg.shard_owner(k, R) for k in keys]
+        assert own == [((mix(k ^ 0x5851F42D4C957F2D) >> 32) * R) >> 32 for k in keys]
+        cnt = np.bincount(own, minlength=R)
+        assert cnt.min() > 0.8 * len(keys) / R and cnt.max() < 1.2 * len(keys) / R
+    assert C.sizeof(kg.ShardStats) == 6 * 8 + 6 * 4
 
 
 def test_defaults_match_reference():
