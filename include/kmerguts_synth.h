@@ -34,6 +34,10 @@ typedef struct kg_universe {
  * the caller (kg_device_free). */
 int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64_t max_sigs, uint64_t** d_keys, void** d_payload16,
                         uint64_t* n);
+/* One shard of the same table (kmerguts_shard.h): only the signatures kg_shard_owner gives to `rank`; the union over the
+ * ranks is exactly what kg_synth_signatures(max_sigs = 0) generates.  max_sigs must be 0 when nranks > 1. */
+int kg_synth_signatures_sharded(kg_context* ctx, const kg_universe* u, uint64_t max_sigs, int rank, int nranks,
+                                uint64_t** d_keys, void** d_payload16, uint64_t* n);
 
 /* Query proteins first..first+n-1 of tools/kg_synth.py::Universe.proteins(seed): device byte stream + offsets. */
 int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t first, uint64_t n, uint64_t seed,

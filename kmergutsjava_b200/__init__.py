@@ -34,7 +34,7 @@ EXPORTS = [
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
     "kg_functions_load", "kg_functions_read", "kg_functions_count", "kg_functions_name", "kg_functions_free",
     "kg_format_java_f", "kg_report_write", "kg_main",
-    "kg_synth_signatures", "kg_synth_proteins", "kg_synth_genomes", "kg_synth_reference_image", "kg_synth_naive_scan_aa", "kg_synth_hits_checksum", "kg_device_free", "kg_device_to_host",
+    "kg_synth_signatures", "kg_synth_signatures_sharded", "kg_synth_proteins", "kg_synth_genomes", "kg_synth_reference_image", "kg_synth_naive_scan_aa", "kg_synth_hits_checksum", "kg_device_free", "kg_device_to_host",
     "kg_probe_roofline", "kg_probe_roofline_table",
     "kg_shard_owner", "kg_comm_unique_id", "kg_comm_init", "kg_comm_init_local", "kg_comm_free", "kg_comm_last_stats",
     "kg_table_load_sharded", "kg_table_from_image_sharded", "kg_table_from_device_entries_sharded",
@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "kg_report_write": (i32, [C.c_char_p, i32, i32, vp, vp, vp, vp]),
         "kg_main": (i32, [i32, C.POINTER(C.c_char_p)]),
         "kg_synth_signatures": (i32, [vp, C.POINTER(UniverseStruct), u64, pp, pp, C.POINTER(u64)]),
+        "kg_synth_signatures_sharded": (i32, [vp, C.POINTER(UniverseStruct), u64, i32, i32, pp, pp, C.POINTER(u64)]),
         "kg_synth_proteins": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_genomes": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, C.POINTER(u64), pp, C.POINTER(C.c_double)]),
@@ -423,6 +424,14 @@ def synth_signatures(ctx: Context, u, max_sigs: int = 0):
     dk, dp, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
     us = make_universe(u)
     _check(lib().kg_synth_signatures(ctx._h, C.byref(us), max_sigs, C.byref(dk), C.byref(dp), C.byref(n)))
+    return dk.value, dp.value, n.value
+
+
+def synth_signatures_sharded(ctx: Context, u, rank: int, nranks: int):
+    """The signatures of the universe that `rank` owns (device arrays); the union over ranks = synth_signatures(u, 0)."""
+    dk, dp, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    us = make_universe(u)
+    _check(lib().kg_synth_signatures_sharded(ctx._h, C.byref(us), 0, rank, nranks, C.byref(dk), C.byref(dp), C.byref(n)))
     return dk.value, dp.value, n.value
 
 

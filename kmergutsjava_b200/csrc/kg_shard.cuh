@@ -6,8 +6,9 @@
 //   keys exchange        NCCL send/recv (one process per GPU) or peer copies (all ranks in one process)
 //   k_answer             lookup (KGJ:944-1034) of the received keys against this rank's shard -> replies for the hits
 //   replies exchange     {index of the query in the asker's bin, payload}
-//   k_scatter_replies    replies -> bit + payload at the residue position they belong to
-//   k_tiles_from_bitmap  the per-tile hit chunks k_probe would have written; from here on the pipeline is unchanged
+//   k_mark_replies, k_word_popc + scan, k_place_replies, k_tile_meta
+//                        replies -> the position-ordered hit list and per-tile view k_probe would have written; from
+//                        here on the pipeline is unchanged
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -208,9 +209,10 @@ struct ScatterPlan {
     uint32_t nseg;
     unsigned long long first[KG_MAX_RANKS + 1];
 };
-__global__ void k_scatter_replies(const uint32_t* __restrict__ rr_idx, const int4* __restrict__ rr_payload, ScatterPlan plan, unsigned long long cap,
-                                  const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
-                                  uint32_t* __restrict__ bitmap, int4* __restrict__ payload_at, unsigned long long* __restrict__ ctr) {
+// Merge, step 1: one bit per residue position that has a hit (the bitmap stays in L2: one bit per position).
+__global__ void k_mark_replies(const uint32_t* __restrict__ rr_idx, ScatterPlan plan, unsigned long long cap,
+                               const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
+                               uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ ctr) {
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= plan.first[plan.nseg]) return;
     uint32_t o = 0;
@@ -222,45 +224,48 @@ __global__ void k_scatter_replies(const uint32_t* __restrict__ rr_idx, const int
         return;
     }
     const uint32_t pos = send_pos[o * cap + idx];
-    payload_at[pos] = rr_payload[o * cap + j];
     atomicOr(&bitmap[pos >> 5], 1u << (pos & 31));
 }
 
-// phase D of k_probe, fed from the bitmap: per-tile hit chunks in position order
-__global__ __launch_bounds__(PROBE_BLK) void k_tiles_from_bitmap(const uint32_t* __restrict__ bitmap, const int4* __restrict__ payload_at,
-                                                                 uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload, uint32_t hit_cap,
-                                                                 uint32_t* __restrict__ tile_base, uint32_t* __restrict__ tile_cnt,
-                                                                 unsigned long long* __restrict__ ctr, unsigned long long kmers) {
-    __shared__ uint32_t warp_b[PROBE_BLK / 32];
-    __shared__ uint32_t s_base;
-    const int tid = threadIdx.x;
-    const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
-    const uint32_t hitmask = (bitmap[p0 >> 5] >> (p0 & 31)) & ((1u << PT) - 1u);
-    uint32_t total;
-    const uint32_t ho = block_excl_scan(__popc(hitmask), warp_b, &total);
-    if (tid == 0) {
-        if (blockIdx.x == 0 && kmers) atomicAdd(&ctr[KG_CTR_KMERS], kmers);
-        unsigned long long base = 0;
-        if (total) base = atomicAdd(&ctr[KG_CTR_HITS], (unsigned long long)total);
-        uint32_t b32 = 0xFFFFFFFFu;
-        if (base + total <= (unsigned long long)hit_cap) b32 = (uint32_t)base;
-        else ctr[KG_CTR_OVERFLOW] = 1ull;
-        s_base = b32;
-        tile_base[blockIdx.x] = b32;
-        tile_cnt[blockIdx.x] = total;
+// step 2: hits per 32-position word (an exclusive scan of these gives every hit its rank in position order)
+__global__ void k_word_popc(const uint32_t* __restrict__ bitmap, uint32_t nwords, uint32_t* __restrict__ cnt) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w <= nwords) cnt[w] = w < nwords ? __popc(bitmap[w]) : 0u;
+}
+
+// step 3: every reply goes straight to its final place in the position-ordered hit list
+__global__ void k_place_replies(const uint32_t* __restrict__ rr_idx, const int4* __restrict__ rr_payload, ScatterPlan plan, unsigned long long cap,
+                                const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
+                                const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank, uint32_t hit_cap,
+                                uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= plan.first[plan.nseg]) return;
+    uint32_t o = 0;
+    while (g >= plan.first[o + 1]) o++;
+    const unsigned long long j = g - plan.first[o];
+    const uint32_t idx = rr_idx[o * cap + j];
+    if (idx >= send_cnt[o]) return;
+    const uint32_t pos = send_pos[o * cap + idx];
+    const uint32_t slot = word_rank[pos >> 5] + __popc(bitmap[pos >> 5] & ((1u << (pos & 31)) - 1u));
+    if (slot < hit_cap) {
+        chunk_pos[slot] = pos;
+        chunk_payload[slot] = rr_payload[o * cap + j];
     }
-    __syncthreads();
-    const uint32_t base = s_base;
-    if (base != 0xFFFFFFFFu && hitmask) {
-        uint32_t o = base + ho;
-        uint32_t m = hitmask;
-        while (m) {
-            const int i = __ffs(m) - 1;
-            m &= m - 1;
-            chunk_pos[o] = p0 + (uint32_t)i;
-            chunk_payload[o] = payload_at[p0 + i];
-            o++;
-        }
+}
+
+// step 4: the per-tile view of that list (what k_probe's phase D publishes), and the run's counters
+__global__ void k_tile_meta(const uint32_t* __restrict__ word_rank, uint32_t ntiles, uint32_t hit_cap, uint32_t* __restrict__ tile_base,
+                            uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr, unsigned long long kmers) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    constexpr uint32_t WPT = TILE / 32;
+    const uint32_t b = word_rank[t * WPT], e = word_rank[(t + 1) * WPT];
+    tile_base[t] = b;
+    tile_cnt[t] = e - b;
+    if (t == ntiles - 1) {
+        ctr[KG_CTR_HITS] = e;
+        ctr[KG_CTR_KMERS] = kmers;
+        if (e > hit_cap) ctr[KG_CTR_OVERFLOW] = 1ull;
     }
 }
 
@@ -280,7 +285,7 @@ struct kg_comm {
     ncclComm_t nccl = nullptr;
     KgLocalGroup* group = nullptr;
     // device scratch, grow-only
-    DevBuf send_keys, send_pos, send_cnt, recv_keys, reply_idx, reply_payload, reply_cnt, rr_idx, rr_payload, bitmap, payload_at, matrix;
+    DevBuf send_keys, send_pos, send_cnt, recv_keys, reply_idx, reply_payload, reply_cnt, rr_idx, rr_payload, bitmap, word_cnt, word_rank, matrix;
     uint64_t* h = nullptr; // pinned: [0, 32) route counters, [32, 64) reply counters, [64, 64 + 32 * 16) gathered counters
     cudaEvent_t ev[5] = {};
     kg_shard_stats stats = {};
@@ -516,23 +521,27 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
     sp.nseg = (uint32_t)R;
     for (int o = 0; o < R; o++) sp.first[o + 1] = sp.first[o] + c->rr_n[o];
     const uint64_t nhits = sp.first[R];
-    const size_t bitmap_bytes = ((size_t)ntiles * TILE) / 8 + 4;
+    const uint32_t nwords = ntiles * (uint32_t)(TILE / 32);
+    const size_t bitmap_bytes = ((size_t)nwords + 1) * 4;
     KG_TRY(c->bitmap.ensure(bitmap_bytes));
-    KG_TRY(c->payload_at.ensure(std::max<uint64_t>(vtotal, 1) * sizeof(int4)));
+    KG_TRY(c->word_cnt.ensure(bitmap_bytes));
+    KG_TRY(c->word_rank.ensure(bitmap_bytes));
     ProbeStage stage = [&](PipeSlot& sl, unsigned long long* d_ctr, uint64_t hit_cap, cudaStream_t st) -> int {
+        if (!ntiles) return KG_OK;
         CU(cudaMemsetAsync(c->bitmap.p, 0, bitmap_bytes, st));
-        if (nhits) {
-            k_scatter_replies<<<blocks_for(nhits, 256), 256, 0, st>>>(c->rr_idx.as<uint32_t>(), c->rr_payload.as<int4>(), sp, c->cap,
-                                                                     c->send_cnt.as<unsigned long long>(), c->send_pos.as<uint32_t>(),
-                                                                     c->bitmap.as<uint32_t>(), c->payload_at.as<int4>(), d_ctr);
-            sl.launches++;
-        }
-        if (ntiles) {
-            k_tiles_from_bitmap<<<ntiles, PROBE_BLK, 0, st>>>(c->bitmap.as<uint32_t>(), c->payload_at.as<int4>(), sl.chunk_pos.as<uint32_t>(),
-                                                             sl.chunk_payload.as<int4>(), (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
-                                                             sl.tile_cnt.as<uint32_t>(), d_ctr, c->kmers);
-            sl.launches++;
-        }
+        if (nhits)
+            k_mark_replies<<<blocks_for(nhits, 256), 256, 0, st>>>(c->rr_idx.as<uint32_t>(), sp, c->cap, c->send_cnt.as<unsigned long long>(),
+                                                                  c->send_pos.as<uint32_t>(), c->bitmap.as<uint32_t>(), d_ctr);
+        k_word_popc<<<blocks_for((size_t)nwords + 1, 256), 256, 0, st>>>(c->bitmap.as<uint32_t>(), nwords, c->word_cnt.as<uint32_t>());
+        KG_TRY(exclusive_sum_u32(ctx, c->word_cnt.as<uint32_t>(), c->word_rank.as<uint32_t>(), (size_t)nwords + 1, st));
+        if (nhits)
+            k_place_replies<<<blocks_for(nhits, 256), 256, 0, st>>>(c->rr_idx.as<uint32_t>(), c->rr_payload.as<int4>(), sp, c->cap,
+                                                                   c->send_cnt.as<unsigned long long>(), c->send_pos.as<uint32_t>(),
+                                                                   c->bitmap.as<uint32_t>(), c->word_rank.as<uint32_t>(), (uint32_t)hit_cap,
+                                                                   sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>());
+        k_tile_meta<<<blocks_for(ntiles, 256), 256, 0, st>>>(c->word_rank.as<uint32_t>(), ntiles, (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
+                                                           sl.tile_cnt.as<uint32_t>(), d_ctr, c->kmers);
+        sl.launches += 3 + (nhits ? 2 : 0);
         return KG_OK;
     };
     kg_result* r = new kg_result();
@@ -648,7 +657,7 @@ extern "C" void kg_comm_free(kg_comm* c) {
     cudaDeviceSynchronize();
     if (c->nccl) nccl_api().CommDestroy(c->nccl);
     for (DevBuf* d : {&c->send_keys, &c->send_pos, &c->send_cnt, &c->recv_keys, &c->reply_idx, &c->reply_payload, &c->reply_cnt, &c->rr_idx,
-                      &c->rr_payload, &c->bitmap, &c->payload_at, &c->matrix})
+                      &c->rr_payload, &c->bitmap, &c->word_cnt, &c->word_rank, &c->matrix})
         d->release();
     if (c->h) cudaFreeHost(c->h);
     for (auto& e : c->ev)

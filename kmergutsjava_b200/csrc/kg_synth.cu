@@ -56,17 +56,26 @@ __device__ __forceinline__ float weight_of_key(uint64_t key) { // 0.5 + b/256, e
     return 0.5f + (float)b * (1.0f / 256.0f);
 }
 
-__global__ void k_sig_count(DevUniverse u, uint32_t* __restrict__ cnt) {
+__global__ void k_sig_count(DevUniverse u, uint32_t* __restrict__ cnt, uint32_t rank, uint32_t nranks) {
     uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f > u.n_families) return;
     uint32_t c = 0;
     if (f < u.n_families) {
         uint32_t L = family_len(u, f);
-        for (uint32_t i = 0; i + KG_K <= L; i++) c += is_signature(u, f, i);
+        if (nranks <= 1) {
+            for (uint32_t i = 0; i + KG_K <= L; i++) c += is_signature(u, f, i);
+        } else { // one shard of the table: only the candidates whose key this rank owns
+            uint64_t enc = 0;
+            for (uint32_t i = 0; i < L; i++) {
+                enc = (enc % 1280000000ull) * 20ull + residue_code(u, f, i);
+                if (i + 1 >= KG_K && is_signature(u, f, i + 1 - KG_K) && kg_owner_of(enc, nranks) == rank) c++;
+            }
+        }
     }
     cnt[f] = c;
 }
-__global__ void k_sig_fill(DevUniverse u, const uint64_t* __restrict__ off, uint64_t* __restrict__ keys, int4* __restrict__ payload) {
+__global__ void k_sig_fill(DevUniverse u, const uint64_t* __restrict__ off, uint64_t* __restrict__ keys, int4* __restrict__ payload,
+                           uint32_t rank, uint32_t nranks) {
     uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= u.n_families) return;
     uint32_t L = family_len(u, f);
@@ -76,7 +85,7 @@ __global__ void k_sig_fill(DevUniverse u, const uint64_t* __restrict__ off, uint
         enc = (enc % 1280000000ull) * 20ull + residue_code(u, f, i);
         if (i + 1 >= KG_K) {
             uint32_t w = i + 1 - KG_K; // window start
-            if (is_signature(u, f, w)) {
+            if (is_signature(u, f, w) && (nranks <= 1 || kg_owner_of(enc, nranks) == rank)) {
                 keys[o] = enc;
                 payload[o] = make_int4((int)(f % u.n_otus), (int)(L - w), (int)(f % u.n_functions), __float_as_int(weight_of_key(enc)));
                 o++;
@@ -348,7 +357,14 @@ extern "C" int kg_device_to_host(kg_context* ctx, void* host, const void* dev, u
 
 extern "C" int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64_t max_sigs, uint64_t** out_keys,
                                    void** out_payload, uint64_t* out_n) {
+    return kg_synth_signatures_sharded(ctx, u, max_sigs, 0, 1, out_keys, out_payload, out_n);
+}
+
+extern "C" int kg_synth_signatures_sharded(kg_context* ctx, const kg_universe* u, uint64_t max_sigs, int rank, int nranks,
+                                           uint64_t** out_keys, void** out_payload, uint64_t* out_n) {
     if (!ctx || !u || !out_keys || !out_payload || !out_n) KG_FAIL(KG_EINVAL, "kg_synth_signatures: null argument");
+    if (nranks < 1 || nranks > KG_MAX_RANKS || rank < 0 || rank >= nranks) KG_FAIL(KG_EINVAL, "kg_synth_signatures_sharded: rank %d of %d", rank, nranks);
+    if (nranks > 1 && max_sigs) KG_FAIL(KG_EINVAL, "kg_synth_signatures_sharded: max_sigs truncates in family order and needs the whole set; pass 0");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DevUniverse du;
@@ -359,7 +375,7 @@ extern "C" int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64
     uint64_t* off = nullptr;
     CU(cudaMalloc(&cnt, (F + 1) * 4));
     CU(cudaMalloc(&off, (F + 1) * 8));
-    k_sig_count<<<blocks_for(F + 1, 128), 128, 0, st>>>(du, cnt);
+    k_sig_count<<<blocks_for(F + 1, 128), 128, 0, st>>>(du, cnt, (uint32_t)rank, (uint32_t)nranks);
     size_t tmp = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, off, F + 1, st));
     KG_TRY(ctx->scan_tmp.ensure(tmp));
@@ -380,7 +396,7 @@ extern "C" int kg_synth_signatures(kg_context* ctx, const kg_universe* u, uint64
     CU(cudaMalloc(&r2, std::max<uint64_t>(C, 1) * 4));
     CU(cudaMalloc(&flag, std::max<uint64_t>(C, 1)));
     CU(cudaMalloc(&d_nsel, sizeof(size_t)));
-    k_sig_fill<<<blocks_for(F, 128), 128, 0, st>>>(du, off, ck, cp);
+    k_sig_fill<<<blocks_for(F, 128), 128, 0, st>>>(du, off, ck, cp, (uint32_t)rank, (uint32_t)nranks);
     k_iota<<<blocks_for(C, 256), 256, 0, st>>>(r1, C);
     // first occurrence (lowest candidate rank) of every key: stable sort by key, keep the head of each run
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ck, ck2, r1, r2, C, 0, 35, st));

@@ -71,6 +71,33 @@ def test_shards_partition_the_table(kg, ctx, universe, nranks):
     free_all(tables)
 
 
+def test_sharded_generator_is_a_partition(kg, ctx):
+    """kg_synth_signatures_sharded: the shards' signatures are disjoint, owned by their rank, and their union is the
+    unsharded generator's output (same payloads)."""
+    u = synth.Universe(n_families=2000, seed=0x4B470009)
+    dk, dp, n = kg.synth_signatures(ctx, u, 0)
+    keys = ctx.to_host(dk, 8 * n).view(np.uint64).copy()
+    pay = ctx.to_host(dp, 16 * n).view(np.uint32).reshape(n, 4).copy()
+    whole = {int(k): tuple(p) for k, p in zip(keys, pay)}
+    kg.device_free(dk)
+    kg.device_free(dp)
+    nranks, seen = 3, {}
+    for r in range(nranks):
+        dk, dp, m = kg.synth_signatures_sharded(ctx, u, r, nranks)
+        ks = ctx.to_host(dk, 8 * m).view(np.uint64).copy()
+        ps = ctx.to_host(dp, 16 * m).view(np.uint32).reshape(m, 4).copy()
+        assert all(kg.shard_owner(int(k), nranks) == r for k in ks[:500])
+        for k, p in zip(ks, ps):
+            assert int(k) not in seen
+            seen[int(k)] = tuple(p)
+        t = ctx.table_from_device_entries_sharded(dk, dp, m, r, nranks)
+        assert t.info.num_signatures == m
+        t.free()
+        kg.device_free(dk)
+        kg.device_free(dp)
+    assert seen == whole and len(whole) > 100000
+
+
 @pytest.mark.parametrize("nranks", [1, 2, 3, 5])
 @pytest.mark.parametrize("flags", [dict(), dict(order_constraint=1), dict(min_hits=3, max_gap=50, min_weighted_hits=2)])
 def test_aa_parity_sharded(kg, ctx, oracle, universe, nranks, flags):
