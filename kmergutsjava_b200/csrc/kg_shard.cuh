@@ -71,10 +71,11 @@ NcclApi& nccl_api() {
 constexpr int SHARD_CNT_SLOTS = 2 * KG_MAX_RANKS; // [0, R): keys per owner; [KG_MAX_RANKS]: valid windows of the batch
 
 // One tile of TILE positions per block, PT per thread, like k_probe.  The valid windows go to the bin of their owner:
-// send_keys[owner * cap + i] = key, send_pos[owner * cap + i] = residue position (stays here; the reply names i).
+// send_lo / send_hi[owner * cap + i] = the key (35 bits: low word + 3 high bits in a byte, 5 bytes per lookup on the
+// wire), send_pos[owner * cap + i] = residue position (stays here; the reply names i).
 // Slots inside a bin are claimed per tile (one global atomic per owner and tile), warp-aggregated inside the tile.
 __global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__ stream, uint32_t vtotal, uint32_t nranks, unsigned long long cap,
-                                                     unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ send_pos,
+                                                     uint32_t* __restrict__ send_lo, uint8_t* __restrict__ send_hi, uint32_t* __restrict__ send_pos,
                                                      unsigned long long* __restrict__ send_cnt) {
     __shared__ uint8_t lut[256];
     __shared__ uint32_t cnt[KG_MAX_RANKS];
@@ -116,13 +117,15 @@ __global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__
         if (!((valid >> i) & 1u)) continue;
         const unsigned long long o = base[own[i]] + lr[i];
         if (o < cap) { // a bin that overflows is only counted: the host repeats the pass with the exact capacity
-            send_keys[own[i] * cap + o] = (uint64_t)q[i] * 160000ull + q[i + 4];
+            const uint64_t key = (uint64_t)q[i] * 160000ull + q[i + 4];
+            send_lo[own[i] * cap + o] = (uint32_t)key;
+            send_hi[own[i] * cap + o] = (uint8_t)(key >> 32);
             send_pos[own[i] * cap + o] = p0 + (uint32_t)i;
         }
     }
 }
 
-// The keys received from rank s are segment s of recv_keys; its tiles are blocks [tile_first[s], tile_first[s + 1]).
+// The keys received from rank s are segment s of recv_lo / recv_hi; its tiles are blocks [tile_first[s], tile_first[s + 1]).
 struct AnswerPlan {
     uint32_t nseg;
     uint32_t tile_first[KG_MAX_RANKS + 1];
@@ -132,7 +135,7 @@ struct AnswerPlan {
 // k_probe with the encoder replaced by "read the key": prefilter -> survivor queue -> dense probing -> hits out.  A hit
 // becomes a reply {index of the query inside its segment, payload} appended to the segment's reply region (which
 // starts at the segment's own offset: there are never more replies than queries).
-__global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const unsigned long long* __restrict__ recv_keys, AnswerPlan plan, KgTableView tab,
+__global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32_t* __restrict__ recv_lo, const uint8_t* __restrict__ recv_hi, AnswerPlan plan, KgTableView tab,
                                                                     uint32_t* __restrict__ reply_idx, int4* __restrict__ reply_payload,
                                                                     unsigned long long* __restrict__ reply_cnt, uint32_t flags) {
     extern __shared__ int4 smem_dyn[];
@@ -147,7 +150,8 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const unsign
     uint32_t s = 0;
     while (s + 1 < plan.nseg && blockIdx.x >= plan.tile_first[s + 1]) s++;
     const unsigned long long n_s = plan.seg_off[s + 1] - plan.seg_off[s];
-    const unsigned long long* keys = recv_keys + plan.seg_off[s];
+    const uint32_t* klo = recv_lo + plan.seg_off[s];
+    const uint8_t* khi = recv_hi + plan.seg_off[s];
     const unsigned long long k0 = (unsigned long long)(blockIdx.x - plan.tile_first[s]) * TILE + (unsigned long long)tid * PT;
     const uint64_t pol_keep = kg_policy_evict_last();
     const uint64_t pol_stream = (flags & 1u) ? kg_policy_evict_normal() : kg_policy_evict_first();
@@ -158,7 +162,7 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const unsign
     for (int i = 0; i < PT; i++) {
         key[i] = 0;
         if (k0 + i < n_s) {
-            key[i] = keys[k0 + i];
+            key[i] = (uint64_t)klo[k0 + i] | ((uint64_t)khi[k0 + i] << 32);
             valid |= 1u << i;
         }
     }
@@ -204,7 +208,10 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const unsign
     }
 }
 
-// replies of owner o: entries [o * cap, o * cap + (first[o + 1] - first[o])) of rr_idx / rr_payload
+// replies of owner o: entries [o * cap, o * cap + (first[o + 1] - first[o])) of rr_idx / rr_payload.  Every owner's
+// replies arrive roughly in position order and cover the whole batch, so the kernels below walk all owners' lists at
+// the same pace (block b works on owner b % nseg): neighbours in the output are then written at about the same time and
+// their half-sector writes merge in L2 instead of becoming read-modify-writes in DRAM.
 struct ScatterPlan {
     uint32_t nseg;
     unsigned long long first[KG_MAX_RANKS + 1];
@@ -213,11 +220,9 @@ struct ScatterPlan {
 __global__ void k_mark_replies(const uint32_t* __restrict__ rr_idx, ScatterPlan plan, unsigned long long cap,
                                const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
                                uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ ctr) {
-    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= plan.first[plan.nseg]) return;
-    uint32_t o = 0;
-    while (g >= plan.first[o + 1]) o++;
-    const unsigned long long j = g - plan.first[o];
+    const uint32_t o = blockIdx.x % plan.nseg; // owners interleaved block by block (see ScatterPlan)
+    const unsigned long long j = (unsigned long long)(blockIdx.x / plan.nseg) * blockDim.x + threadIdx.x;
+    if (j >= plan.first[o + 1] - plan.first[o]) return;
     const uint32_t idx = rr_idx[o * cap + j];
     if (idx >= send_cnt[o]) { // a reply that names no query of ours: the peer's answer is corrupt
         ctr[KG_CTR_OVERFLOW] = 2ull;
@@ -238,11 +243,9 @@ __global__ void k_place_replies(const uint32_t* __restrict__ rr_idx, const int4*
                                 const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
                                 const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank, uint32_t hit_cap,
                                 uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload) {
-    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= plan.first[plan.nseg]) return;
-    uint32_t o = 0;
-    while (g >= plan.first[o + 1]) o++;
-    const unsigned long long j = g - plan.first[o];
+    const uint32_t o = blockIdx.x % plan.nseg; // owners interleaved block by block (see ScatterPlan)
+    const unsigned long long j = (unsigned long long)(blockIdx.x / plan.nseg) * blockDim.x + threadIdx.x;
+    if (j >= plan.first[o + 1] - plan.first[o]) return;
     const uint32_t idx = rr_idx[o * cap + j];
     if (idx >= send_cnt[o]) return;
     const uint32_t pos = send_pos[o * cap + idx];
@@ -285,7 +288,7 @@ struct kg_comm {
     ncclComm_t nccl = nullptr;
     KgLocalGroup* group = nullptr;
     // device scratch, grow-only
-    DevBuf send_keys, send_pos, send_cnt, recv_keys, reply_idx, reply_payload, reply_cnt, rr_idx, rr_payload, bitmap, word_cnt, word_rank, matrix;
+    DevBuf send_lo, send_hi, send_pos, send_cnt, recv_lo, recv_hi, reply_idx, reply_payload, reply_cnt, rr_idx, rr_payload, bitmap, word_cnt, word_rank, matrix;
     uint64_t* h = nullptr; // pinned: [0, 32) route counters, [32, 64) reply counters, [64, 64 + 32 * 16) gathered counters
     cudaEvent_t ev[5] = {};
     kg_shard_stats stats = {};
@@ -329,11 +332,12 @@ int shard_route(kg_comm* c, kg_batch* b) {
     cap = std::max<uint64_t>(std::min<uint64_t>(cap, std::max<uint64_t>(vtotal, 1)), 1);
     KG_TRY(c->send_cnt.ensure(SHARD_CNT_SLOTS * 8));
     for (int attempt = 0;; attempt++) {
-        KG_TRY(c->send_keys.ensure(R * cap * 8));
+        KG_TRY(c->send_lo.ensure(R * cap * 4));
+        KG_TRY(c->send_hi.ensure(R * cap));
         KG_TRY(c->send_pos.ensure(R * cap * 4));
         CU(cudaMemsetAsync(c->send_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
         if (ntiles)
-            k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, R, cap, c->send_keys.as<unsigned long long>(),
+            k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, R, cap, c->send_lo.as<uint32_t>(), c->send_hi.as<uint8_t>(),
                                                   c->send_pos.as<uint32_t>(), c->send_cnt.as<unsigned long long>());
         CU(cudaMemcpyAsync(c->h, c->send_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -385,33 +389,44 @@ int shard_exchange_keys(kg_comm* c) {
     for (int s = 0; s < R; s++) c->recv_off[s + 1] = c->recv_off[s] + c->recv_n[s];
     const uint64_t nrecv = c->recv_off[R];
     c->stats.keys_received = nrecv;
-    KG_TRY(c->recv_keys.ensure(std::max<uint64_t>(nrecv, 1) * 8));
+    KG_TRY(c->recv_lo.ensure(std::max<uint64_t>(nrecv, 1) * 4));
+    KG_TRY(c->recv_hi.ensure(std::max<uint64_t>(nrecv, 1)));
     KG_TRY(c->reply_idx.ensure(std::max<uint64_t>(nrecv, 1) * 4));
     KG_TRY(c->reply_payload.ensure(std::max<uint64_t>(nrecv, 1) * sizeof(int4)));
     KG_TRY(c->reply_cnt.ensure(SHARD_CNT_SLOTS * 8));
-    unsigned long long* sk = c->send_keys.as<unsigned long long>();
-    unsigned long long* rk = c->recv_keys.as<unsigned long long>();
+    uint32_t *sl = c->send_lo.as<uint32_t>(), *rl = c->recv_lo.as<uint32_t>();
+    uint8_t *sh = c->send_hi.as<uint8_t>(), *rh = c->recv_hi.as<uint8_t>();
     if (c->nccl) {
         NcclApi& nc = nccl_api();
         NC(nc.GroupStart());
         for (int p = 0; p < R; p++) {
             if (p == c->rank) continue;
-            if (c->send_n[p]) NC(nc.Send(sk + p * c->cap, c->send_n[p], ncclUint64, p, c->nccl, st));
-            if (c->recv_n[p]) NC(nc.Recv(rk + c->recv_off[p], c->recv_n[p], ncclUint64, p, c->nccl, st));
-            c->stats.bytes_sent += c->send_n[p] * 8;
+            if (c->send_n[p]) {
+                NC(nc.Send(sl + p * c->cap, c->send_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Send(sh + p * c->cap, c->send_n[p], ncclUint8, p, c->nccl, st));
+            }
+            if (c->recv_n[p]) {
+                NC(nc.Recv(rl + c->recv_off[p], c->recv_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Recv(rh + c->recv_off[p], c->recv_n[p], ncclUint8, p, c->nccl, st));
+            }
+            c->stats.bytes_sent += c->send_n[p] * 5;
         }
         NC(nc.GroupEnd());
-        if (c->send_n[c->rank]) CU(cudaMemcpyAsync(rk + c->recv_off[c->rank], sk + c->rank * c->cap, c->send_n[c->rank] * 8, cudaMemcpyDeviceToDevice, st));
+        if (c->send_n[c->rank]) {
+            CU(cudaMemcpyAsync(rl + c->recv_off[c->rank], sl + c->rank * c->cap, c->send_n[c->rank] * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(rh + c->recv_off[c->rank], sh + c->rank * c->cap, c->send_n[c->rank], cudaMemcpyDeviceToDevice, st));
+        }
     } else if (c->group) { // every member has finished its route phase (host-synchronised): pull the bins
         for (int s = 0; s < R; s++) {
             kg_comm* src = c->group->members[s];
             if (!c->recv_n[s]) continue;
-            CU(cudaMemcpyPeerAsync(rk + c->recv_off[s], ctx->device, src->send_keys.as<unsigned long long>() + c->rank * src->cap, src->ctx->device,
-                                   c->recv_n[s] * 8, st));
-            if (s != c->rank) src->stats.bytes_sent += c->recv_n[s] * 8;
+            CU(cudaMemcpyPeerAsync(rl + c->recv_off[s], ctx->device, src->send_lo.as<uint32_t>() + c->rank * src->cap, src->ctx->device, c->recv_n[s] * 4, st));
+            CU(cudaMemcpyPeerAsync(rh + c->recv_off[s], ctx->device, src->send_hi.as<uint8_t>() + c->rank * src->cap, src->ctx->device, c->recv_n[s], st));
+            if (s != c->rank) src->stats.bytes_sent += c->recv_n[s] * 5;
         }
     } else if (nrecv) {
-        CU(cudaMemcpyAsync(rk, sk, nrecv * 8, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(rl, sl, nrecv * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(rh, sh, nrecv, cudaMemcpyDeviceToDevice, st));
     }
     cudaEventRecord(c->ev[2], st);
     return KG_OK;
@@ -436,7 +451,7 @@ int shard_answer(kg_comm* c, const kg_table* table) {
     if (tiles > 0x7FFFFFFFull) KG_FAIL(KG_ERANGE, "kg_batch_run_sharded: %llu keys received in one step", (unsigned long long)c->recv_off[R]);
     CU(cudaMemsetAsync(c->reply_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
     if (tiles)
-        k_answer<<<(unsigned)tiles, PROBE_BLK, PROBE_SMEM, st>>>(c->recv_keys.as<unsigned long long>(), plan, table->view(), c->reply_idx.as<uint32_t>(),
+        k_answer<<<(unsigned)tiles, PROBE_BLK, PROBE_SMEM, st>>>(c->recv_lo.as<uint32_t>(), c->recv_hi.as<uint8_t>(), plan, table->view(), c->reply_idx.as<uint32_t>(),
                                                                  c->reply_payload.as<int4>(), c->reply_cnt.as<unsigned long long>(), probe_flags());
     cudaEventRecord(c->ev[3], st);
     CU(cudaMemcpyAsync(c->h + 32, c->reply_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
@@ -521,6 +536,9 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
     sp.nseg = (uint32_t)R;
     for (int o = 0; o < R; o++) sp.first[o + 1] = sp.first[o] + c->rr_n[o];
     const uint64_t nhits = sp.first[R];
+    uint64_t longest = 0;
+    for (int o = 0; o < R; o++) longest = std::max(longest, c->rr_n[o]);
+    const unsigned merge_grid = (unsigned)(blocks_for(longest, 256) * (uint64_t)R);
     const uint32_t nwords = ntiles * (uint32_t)(TILE / 32);
     const size_t bitmap_bytes = ((size_t)nwords + 1) * 4;
     KG_TRY(c->bitmap.ensure(bitmap_bytes));
@@ -530,12 +548,12 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
         if (!ntiles) return KG_OK;
         CU(cudaMemsetAsync(c->bitmap.p, 0, bitmap_bytes, st));
         if (nhits)
-            k_mark_replies<<<blocks_for(nhits, 256), 256, 0, st>>>(c->rr_idx.as<uint32_t>(), sp, c->cap, c->send_cnt.as<unsigned long long>(),
+            k_mark_replies<<<merge_grid, 256, 0, st>>>(c->rr_idx.as<uint32_t>(), sp, c->cap, c->send_cnt.as<unsigned long long>(),
                                                                   c->send_pos.as<uint32_t>(), c->bitmap.as<uint32_t>(), d_ctr);
         k_word_popc<<<blocks_for((size_t)nwords + 1, 256), 256, 0, st>>>(c->bitmap.as<uint32_t>(), nwords, c->word_cnt.as<uint32_t>());
         KG_TRY(exclusive_sum_u32(ctx, c->word_cnt.as<uint32_t>(), c->word_rank.as<uint32_t>(), (size_t)nwords + 1, st));
         if (nhits)
-            k_place_replies<<<blocks_for(nhits, 256), 256, 0, st>>>(c->rr_idx.as<uint32_t>(), c->rr_payload.as<int4>(), sp, c->cap,
+            k_place_replies<<<merge_grid, 256, 0, st>>>(c->rr_idx.as<uint32_t>(), c->rr_payload.as<int4>(), sp, c->cap,
                                                                    c->send_cnt.as<unsigned long long>(), c->send_pos.as<uint32_t>(),
                                                                    c->bitmap.as<uint32_t>(), c->word_rank.as<uint32_t>(), (uint32_t)hit_cap,
                                                                    sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>());
@@ -656,7 +674,7 @@ extern "C" void kg_comm_free(kg_comm* c) {
     cudaSetDevice(c->ctx->device);
     cudaDeviceSynchronize();
     if (c->nccl) nccl_api().CommDestroy(c->nccl);
-    for (DevBuf* d : {&c->send_keys, &c->send_pos, &c->send_cnt, &c->recv_keys, &c->reply_idx, &c->reply_payload, &c->reply_cnt, &c->rr_idx,
+    for (DevBuf* d : {&c->send_lo, &c->send_hi, &c->send_pos, &c->send_cnt, &c->recv_lo, &c->recv_hi, &c->reply_idx, &c->reply_payload, &c->reply_cnt, &c->rr_idx,
                       &c->rr_payload, &c->bitmap, &c->word_cnt, &c->word_rank, &c->matrix})
         d->release();
     if (c->h) cudaFreeHost(c->h);
