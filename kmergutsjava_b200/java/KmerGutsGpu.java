@@ -56,8 +56,11 @@ public final class KmerGutsGpu implements AutoCloseable {
     private final SymbolLookup lib;
     private final MethodHandle kgInit, kgShutdown, kgLastError, kgTableLoad, kgTableFree, kgRun, kgResultCalls, kgResultOtus,
             kgResultHits, kgResultFree;
+    // hash-sharded table across GPUs (include/kmerguts_shard.h); the reference has no counterpart
+    private final MethodHandle kgCommUniqueId, kgCommInit, kgCommFree, kgTableLoadSharded, kgBatchUpload, kgBatchFree, kgBatchRunSharded;
     private final MemorySegment ctx;
     private MemorySegment table = MemorySegment.NULL;
+    private MemorySegment comm = MemorySegment.NULL;
 
     public KmerGutsGpu(String libraryPath, int device) throws Throwable {
         lib = SymbolLookup.libraryLookup(libraryPath, arena);
@@ -71,6 +74,13 @@ public final class KmerGutsGpu implements AutoCloseable {
         kgResultOtus = h("kg_result_otus", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
         kgResultHits = h("kg_result_hits", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
         kgResultFree = h("kg_result_free", FunctionDescriptor.ofVoid(ADDRESS));
+        kgCommUniqueId = h("kg_comm_unique_id", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+        kgCommInit = h("kg_comm_init", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+        kgCommFree = h("kg_comm_free", FunctionDescriptor.ofVoid(ADDRESS));
+        kgTableLoadSharded = h("kg_table_load_sharded", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
+        kgBatchUpload = h("kg_batch_upload", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+        kgBatchFree = h("kg_batch_free", FunctionDescriptor.ofVoid(ADDRESS));
+        kgBatchRunSharded = h("kg_batch_run_sharded", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
         MemorySegment out = arena.allocate(ADDRESS);
         check((int) kgInit.invokeExact(device, out));
         ctx = out.get(ADDRESS, 0);
@@ -103,63 +113,113 @@ public final class KmerGutsGpu implements AutoCloseable {
     public Result run(List<String> seqs, boolean aa, int minHits, int minWeightedHits, int maxGap, boolean orderConstraint,
                       boolean debug) throws Throwable {
         try (Arena a = Arena.ofConfined()) {
-            long total = 0;
-            for (String s : seqs) total += s.length();
-            MemorySegment bytes = a.allocate(Math.max(total, 1));
-            MemorySegment offs = a.allocate(JAVA_LONG, seqs.size() + 1L);
-            long at = 0;
-            for (int i = 0; i < seqs.size(); i++) {
-                // ISO_8859_1 keeps one byte per Java char, as toAminoAcidOff / dnaChar see them (KGJ:1057, 324)
-                byte[] b = seqs.get(i).getBytes(StandardCharsets.ISO_8859_1);
-                MemorySegment.copy(b, 0, bytes, ValueLayout.JAVA_BYTE, at, b.length);
-                offs.setAtIndex(JAVA_LONG, i, at);
-                at += b.length;
-            }
-            offs.setAtIndex(JAVA_LONG, seqs.size(), at);
-            MemorySegment p = a.allocate(PARAMS);
-            p.set(JAVA_INT, 0, minHits);
-            p.set(JAVA_INT, 4, minWeightedHits);
-            p.set(JAVA_INT, 8, maxGap);
-            p.set(JAVA_INT, 12, orderConstraint ? 1 : 0);
-            p.set(JAVA_INT, 16, debug ? 1 : 0);
+            MemorySegment[] in = pack(a, seqs, minHits, minWeightedHits, maxGap, orderConstraint, debug);
             MemorySegment out = a.allocate(ADDRESS);
-            check((int) kgRun.invokeExact(ctx, table, aa ? MODE_AA : MODE_DNA, bytes, offs, (long) seqs.size(), p, out));
-            MemorySegment res = out.get(ADDRESS, 0);
+            check((int) kgRun.invokeExact(ctx, table, aa ? MODE_AA : MODE_DNA, in[0], in[1], (long) seqs.size(), in[2], out));
+            return readAndFree(a, out.get(ADDRESS, 0));
+        }
+    }
+
+    /** Rank 0 of a multi-GPU job makes the communicator id; the application hands the 128 bytes to every rank. */
+    public byte[] commUniqueId() throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment id = a.allocate(128);
+            check((int) kgCommUniqueId.invokeExact(id));
+            return id.toArray(ValueLayout.JAVA_BYTE);
+        }
+    }
+
+    /** Collective over the ranks: join the communicator and load this rank's shard of kmer.table.mem_map[.gz]. */
+    public void joinSharded(int rank, int nranks, byte[] id, String kmerTableDir) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(ADDRESS);
+            MemorySegment idSeg = a.allocate(128);
+            MemorySegment.copy(id, 0, idSeg, ValueLayout.JAVA_BYTE, 0, 128);
+            check((int) kgCommInit.invokeExact(ctx, rank, nranks, idSeg, out));
+            comm = out.get(ADDRESS, 0);
+            check((int) kgTableLoadSharded.invokeExact(ctx, a.allocateFrom(kmerTableDir), rank, nranks, out));
+            table = out.get(ADDRESS, 0);
+        }
+    }
+
+    /** run() against the sharded table: collective, every rank calls it the same number of times with its own sequences. */
+    public Result runSharded(List<String> seqs, boolean aa, int minHits, int minWeightedHits, int maxGap, boolean orderConstraint,
+                             boolean debug) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment[] in = pack(a, seqs, minHits, minWeightedHits, maxGap, orderConstraint, debug);
+            MemorySegment out = a.allocate(ADDRESS);
+            check((int) kgBatchUpload.invokeExact(ctx, aa ? MODE_AA : MODE_DNA, in[0], in[1], (long) seqs.size(), out));
+            MemorySegment batch = out.get(ADDRESS, 0);
             try {
-                MemorySegment ptr = a.allocate(ADDRESS), cnt = a.allocate(JAVA_LONG);
-                check((int) kgResultCalls.invokeExact(res, ptr, cnt));
-                long n = cnt.get(JAVA_LONG, 0);
-                MemorySegment cs = ptr.get(ADDRESS, 0).reinterpret(n * CALL.byteSize());
-                List<Call> calls = new ArrayList<>((int) n);
-                for (long i = 0; i < n; i++) {
-                    long o = i * CALL.byteSize();
-                    calls.add(new Call(cs.get(JAVA_INT, o), cs.get(JAVA_INT, o + 4), cs.get(JAVA_INT, o + 8), cs.get(JAVA_INT, o + 12),
-                            cs.get(JAVA_INT, o + 16), cs.get(JAVA_INT, o + 20), cs.get(JAVA_FLOAT, o + 24), cs.get(JAVA_INT, o + 28)));
-                }
-                check((int) kgResultOtus.invokeExact(res, ptr, cnt));
-                n = cnt.get(JAVA_LONG, 0);
-                MemorySegment os = ptr.get(ADDRESS, 0).reinterpret(n * OTU.byteSize());
-                List<Otu> otus = new ArrayList<>((int) n);
-                for (long i = 0; i < n; i++) {
-                    long o = i * OTU.byteSize();
-                    int k = os.get(JAVA_INT, o);
-                    int[] c = new int[k], oi = new int[k];
-                    for (int j = 0; j < k; j++) {
-                        c[j] = os.get(JAVA_INT, o + 4 + 4L * j);
-                        oi[j] = os.get(JAVA_INT, o + 24 + 4L * j);
-                    }
-                    otus.add(new Otu(c, oi));
-                }
-                return new Result(calls, otus, null); // "-d": kg_result_hits is read the same way (HIT layout above)
+                check((int) kgBatchRunSharded.invokeExact(comm, table, batch, in[2], out));
+                return readAndFree(a, out.get(ADDRESS, 0));
             } finally {
-                kgResultFree.invokeExact(res);
+                kgBatchFree.invokeExact(batch);
             }
+        }
+    }
+
+    /** {sequence bytes, offsets[n+1], kg_params} in native memory. */
+    private MemorySegment[] pack(Arena a, List<String> seqs, int minHits, int minWeightedHits, int maxGap, boolean orderConstraint,
+                                 boolean debug) {
+        long total = 0;
+        for (String s : seqs) total += s.length();
+        MemorySegment bytes = a.allocate(Math.max(total, 1));
+        MemorySegment offs = a.allocate(JAVA_LONG, seqs.size() + 1L);
+        long at = 0;
+        for (int i = 0; i < seqs.size(); i++) {
+            // ISO_8859_1 keeps one byte per Java char, as toAminoAcidOff / dnaChar see them (KGJ:1057, 324)
+            byte[] b = seqs.get(i).getBytes(StandardCharsets.ISO_8859_1);
+            MemorySegment.copy(b, 0, bytes, ValueLayout.JAVA_BYTE, at, b.length);
+            offs.setAtIndex(JAVA_LONG, i, at);
+            at += b.length;
+        }
+        offs.setAtIndex(JAVA_LONG, seqs.size(), at);
+        MemorySegment p = a.allocate(PARAMS);
+        p.set(JAVA_INT, 0, minHits);
+        p.set(JAVA_INT, 4, minWeightedHits);
+        p.set(JAVA_INT, 8, maxGap);
+        p.set(JAVA_INT, 12, orderConstraint ? 1 : 0);
+        p.set(JAVA_INT, 16, debug ? 1 : 0);
+        return new MemorySegment[] {bytes, offs, p};
+    }
+
+    private Result readAndFree(Arena a, MemorySegment res) throws Throwable {
+        try {
+            MemorySegment ptr = a.allocate(ADDRESS), cnt = a.allocate(JAVA_LONG);
+            check((int) kgResultCalls.invokeExact(res, ptr, cnt));
+            long n = cnt.get(JAVA_LONG, 0);
+            MemorySegment cs = ptr.get(ADDRESS, 0).reinterpret(n * CALL.byteSize());
+            List<Call> calls = new ArrayList<>((int) n);
+            for (long i = 0; i < n; i++) {
+                long o = i * CALL.byteSize();
+                calls.add(new Call(cs.get(JAVA_INT, o), cs.get(JAVA_INT, o + 4), cs.get(JAVA_INT, o + 8), cs.get(JAVA_INT, o + 12),
+                        cs.get(JAVA_INT, o + 16), cs.get(JAVA_INT, o + 20), cs.get(JAVA_FLOAT, o + 24), cs.get(JAVA_INT, o + 28)));
+            }
+            check((int) kgResultOtus.invokeExact(res, ptr, cnt));
+            n = cnt.get(JAVA_LONG, 0);
+            MemorySegment os = ptr.get(ADDRESS, 0).reinterpret(n * OTU.byteSize());
+            List<Otu> otus = new ArrayList<>((int) n);
+            for (long i = 0; i < n; i++) {
+                long o = i * OTU.byteSize();
+                int k = os.get(JAVA_INT, o);
+                int[] c = new int[k], oi = new int[k];
+                for (int j = 0; j < k; j++) {
+                    c[j] = os.get(JAVA_INT, o + 4 + 4L * j);
+                    oi[j] = os.get(JAVA_INT, o + 24 + 4L * j);
+                }
+                otus.add(new Otu(c, oi));
+            }
+            return new Result(calls, otus, null); // "-d": kg_result_hits is read the same way (HIT layout above)
+        } finally {
+            kgResultFree.invokeExact(res);
         }
     }
 
     @Override
     public void close() {
         try {
+            if (!comm.equals(MemorySegment.NULL)) kgCommFree.invokeExact(comm);
             if (!table.equals(MemorySegment.NULL)) kgTableFree.invokeExact(table);
             kgShutdown.invokeExact(ctx);
         } catch (Throwable t) {
