@@ -10,6 +10,7 @@
 //                        replies -> the position-ordered hit list and per-tile view k_probe would have written; from
 //                        here on the pipeline is unchanged
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <nccl.h>
 
 #include <string>
@@ -623,6 +624,11 @@ extern "C" int kg_comm_init(kg_context* ctx, int rank, int nranks, const uint8_t
             kg_comm_free(c);
             KG_FAIL(KG_EINVAL, "kg_comm_init: %s", id ? "libnccl.so.2 not loadable" : "null id");
         }
+        // The exchanges are a few large point-to-point messages per peer: more channels than NCCL's default move them faster
+        // (2 GPUs, 1.25 GB each way: 8 channels 10.0 ms, default 3.6 ms, 64 channels 2.8 ms).  The caller's environment wins;
+        // NCCL reads it once per process, so a host that creates its own communicators first should set it itself.
+        setenv("NCCL_MIN_P2P_NCHANNELS", "64", 0);
+        setenv("NCCL_MAX_P2P_NCHANNELS", "64", 0);
         ncclUniqueId u;
         memcpy(&u, id, KG_COMM_ID_BYTES);
         ncclResult_t e = nc.CommInitRank(&c->nccl, nranks, u, rank);

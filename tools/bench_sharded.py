@@ -25,6 +25,40 @@ sys.path.insert(0, ROOT)
 from tools import kg_synth as synth  # noqa: E402
 
 
+def local_main(a):
+    """R virtual ranks on one GPU: the kernels see the same bin / owner structure as an R-GPU run (for ncu)."""
+    import kmergutsjava_b200 as kg
+    R = a.local_ranks
+    ctx = kg.Context(0)
+    u = synth.Universe(n_families=a.families or 1_250_000, sig_keep_per_1024=a.keep)
+    tables = []
+    for r in range(R):
+        dk, dp, n = kg.synth_signatures_sharded(ctx, u, r, R)
+        tables.append(ctx.table_from_device_entries_sharded(dk, dp, n, r, R))
+        kg.device_free(dk)
+        kg.device_free(dp)
+    comms = kg.Comm.local([ctx] * R)
+    batches = []
+    for r in range(R):
+        ds, do, total = kg.synth_proteins(ctx, u, r * a.proteins, a.proteins, seed=1)
+        batches.append(ctx.batch_from_device(kg.MODE_AA, ds, do, a.proteins, total))
+    params = kg.default_params()
+    for _ in range(a.warmup):
+        for res in kg.run_sharded_local(comms, tables, batches, params):
+            res.free()
+    t0 = time.perf_counter()
+    lookups = 0
+    for _ in range(a.steps):
+        for res in kg.run_sharded_local(comms, tables, batches, params):
+            lookups += res.stats.num_kmers
+            res.free()
+    dt = time.perf_counter() - t0
+    st = comms[0].stats
+    print(json.dumps({"workload": f"{R} virtual ranks on one GPU, {a.proteins} proteins each", "ms_per_step_all_ranks": 1e3 * dt / a.steps,
+                      "lookups_per_s": lookups / dt,
+                      "rank0_phase_ms": {k: round(getattr(st, "ms_" + k), 3) for k in ("route", "keys", "answer", "replies", "merge", "total")}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -35,11 +69,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sample", type=int, default=2000)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--local-ranks", type=int, default=0,
+                    help="profiling aid: R virtual ranks in ONE process on one GPU (peer copies instead of NCCL); prints phase times only")
     a = ap.parse_args()
+    if a.local_ranks:
+        return local_main(a)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     families = a.families or 1_250_000 * world
+    # more point-to-point channels for the library's exchanges (NCCL reads this once per process, before torch's communicator)
+    os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "64")
+    os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "64")
     import torch
     dist = None
     if world > 1:
