@@ -340,7 +340,9 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
         k_count_flagged<<<blocks_for(nb_total, 256), 256, 0, st>>>((const uint32_t*)t->d_lines, nb_total, d_ctr + 1);
         if (filter_bits_per_key() > 0) { // L2-resident prefilter over the same keys
             uint64_t bytes = (uint64_t)((double)n_unique * filter_bits_per_key() / 8.0);
-            if (bytes > KG_FILTER_MAX_BYTES) bytes = KG_FILTER_MAX_BYTES;
+            uint64_t max_bytes = KG_FILTER_MAX_BYTES;
+            if (const char* e = getenv("KG_FILTER_MAX_MB")) max_bytes = (uint64_t)atoll(e) << 20; // experiments
+            if (bytes > max_bytes) bytes = max_bytes;
             if (bytes < 4096) bytes = 4096;
             t->filter_words = (uint32_t)(bytes / 8);
             CU(cudaMalloc(&t->d_filter, (size_t)t->filter_words * 8));
@@ -353,13 +355,15 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
                 cudaDeviceProp prop;
                 if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
                     const size_t fbytes = (size_t)t->filter_words * 8;
-                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize));
+                    const size_t carve = std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize);
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
                     cudaStreamAttrValue av = {};
                     av.accessPolicyWindow.base_ptr = t->d_filter;
                     av.accessPolicyWindow.num_bytes = std::min<size_t>(fbytes, (size_t)prop.accessPolicyMaxWindowSize);
-                    av.accessPolicyWindow.hitRatio = 1.0f;
+                    // a filter larger than the carve-out: that fraction of its lines persists, the rest competes normally
+                    av.accessPolicyWindow.hitRatio = fbytes > carve ? (float)((double)carve / (double)fbytes) : 1.0f;
                     av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    av.accessPolicyWindow.missProp = fbytes > carve ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
                     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
                     cudaGetLastError();
                 }
