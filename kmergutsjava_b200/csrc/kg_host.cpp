@@ -61,9 +61,16 @@ bool read_all(const std::string& path, std::string& out) {
     }
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) return false;
-    std::vector<char> buf(4u << 20);
-    size_t got;
-    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) out.append(buf.data(), got);
+    struct stat st;
+    size_t have = 0, cap = (fstat(fileno(f), &st) == 0 && st.st_size > 0) ? (size_t)st.st_size + 1 : (4u << 20);
+    for (;;) { // straight into the string: no staging buffer, no regrowth when the size is known
+        out.resize(cap);
+        const size_t got = fread(&out[have], 1, cap - have, f);
+        have += got;
+        if (have < cap) break;
+        cap *= 2;
+    }
+    out.resize(have);
     fclose(f);
     return true;
 }
@@ -74,9 +81,13 @@ struct Lines {
     size_t pos = 0;
     bool next(std::string_view& line) {
         if (pos >= text.size()) return false;
-        size_t e = pos;
-        while (e < text.size() && text[e] != '\n' && text[e] != '\r') e++;
-        line = text.substr(pos, e - pos);
+        const char* b = text.data() + pos;
+        const size_t left = text.size() - pos;
+        const char* nl = (const char*)memchr(b, '\n', left);
+        size_t e = nl ? (size_t)(nl - b) : left;            // up to the next \n ...
+        if (const char* cr = (const char*)memchr(b, '\r', e)) e = (size_t)(cr - b); // ... or an earlier \r
+        line = text.substr(pos, e);
+        e += pos;
         if (e < text.size()) e += (text[e] == '\r' && e + 1 < text.size() && text[e + 1] == '\n') ? 2 : 1;
         pos = e;
         return true;
@@ -105,6 +116,7 @@ extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
         return KG_EIO;
     }
     kg_fasta* fa = new kg_fasta();
+    fa->bytes.reserve(text.size());
     Lines in{text};
     std::string_view cur;
     bool have = in.next(cur); // str1
@@ -311,28 +323,54 @@ extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_f
     }
     // queryIdToLen is a LinkedHashMap<String,Integer>: iteration in FIRST-insertion order with the LAST length;
     // hitCnts.put() keeps the LAST container of a repeated (id, strand, frame).  KGJ:772, 782, 805-809.
-    std::unordered_map<std::string, size_t> last;
-    last.reserve(n * 2);
-    for (size_t i = 0; i < n; i++) last[fa->ids[i]] = i;
-    std::unordered_map<std::string, bool> seen;
-    seen.reserve(n * 2);
+    struct FirstLast {
+        size_t first, last;
+    };
+    std::unordered_map<std::string_view, FirstLast> occ;
+    occ.reserve(n * 2);
+    for (size_t i = 0; i < n; i++) {
+        auto r = occ.emplace(std::string_view(fa->ids[i]), FirstLast{i, i});
+        if (!r.second) r.first->second.last = i;
+    }
     const int per_seq = mode == KG_MODE_AA ? 1 : 6;
+    // Lines are assembled in a buffer and written a megabyte at a time (fprintf per line was the slowest part of a run).
+    std::string buf;
+    buf.reserve((1u << 20) + 4096);
+    auto put = [&](std::string_view t) { buf.append(t.data(), t.size()); };
+    auto num = [&](long long v) {
+        char tmp[24];
+        auto r = std::to_chars(tmp, tmp + sizeof tmp, v);
+        buf.append(tmp, (size_t)(r.ptr - tmp));
+    };
+    auto flush = [&](bool force) {
+        if (buf.size() >= (1u << 20) || (force && !buf.empty())) {
+            fwrite(buf.data(), 1, buf.size(), out);
+            buf.clear();
+        }
+    };
     char wbuf[96];
     for (size_t i = 0; i < n; i++) {
-        if (!seen.emplace(fa->ids[i], true).second) continue;
-        const size_t s = last[fa->ids[i]];
+        const std::string& ids = fa->ids[i];
+        const FirstLast& fl = occ.find(std::string_view(ids))->second;
+        if (fl.first != i) continue;
+        const size_t s = fl.last;
         const long long len = (long long)(fa->off[s + 1] - fa->off[s]);
-        const char* id = fa->ids[i].c_str();
-        if (mode == KG_MODE_AA) fprintf(out, "PROTEIN-ID\t%s\t%lld\n", id, len);       // KGJ:529
-        else fprintf(out, "processing %s[%lld]\n", id, len);                             // KGJ:541
+        if (mode == KG_MODE_AA) { // KGJ:529
+            put("PROTEIN-ID\t"); put(ids); put("\t"); num(len); put("\n");
+        } else { // KGJ:541
+            put("processing "); put(ids); put("["); num(len); put("]\n");
+        }
         size_t c = call_lo[s], h = hit_lo[s];
         for (int k = 0; k < per_seq; k++) {
-            if (mode != KG_MODE_AA) fprintf(out, "TRANSLATION\t%s\t%lld\t%c\t%d\n", id, len, k < 3 ? '+' : '-', k % 3); // KGJ:545-548
+            if (mode != KG_MODE_AA) { // KGJ:545-548
+                put("TRANSLATION\t"); put(ids); put("\t"); num(len); put(k < 3 ? "\t+\t" : "\t-\t"); num(k % 3); put("\n");
+            }
             int printed = 0;
             auto flush_hits = [&](int upto) { // HIT lines precede the CALL they trigger (KGJ:472-475 before 477-508)
                 while (debug && h < hit_lo[s + 1] && hits[h].strand_frame == k && printed < upto) {
                     kg_format_java_f(hits[h].function_wt, 3, wbuf, sizeof wbuf);
-                    fprintf(out, "HIT\t%d\t%d\t%d\t%d\t%s\t%d\n", hits[h].pos, 0, hits[h].avg_off_from_end, hits[h].fI, wbuf, hits[h].oI);
+                    put("HIT\t"); num(hits[h].pos); put("\t0\t"); num(hits[h].avg_off_from_end); put("\t"); num(hits[h].fI); put("\t");
+                    put(wbuf); put("\t"); num(hits[h].oI); put("\n");
                     h++;
                     printed++;
                 }
@@ -341,15 +379,21 @@ extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_f
                 flush_hits(calls[c].hits_before);
                 const kg_call& cl = calls[c];
                 kg_format_java_f(cl.weighted, 6, wbuf, sizeof wbuf);
-                const char* fname = (cl.fI >= 0 && (size_t)cl.fI < fn->names.size()) ? fn->names[(size_t)cl.fI].c_str() : "";
-                fprintf(out, "CALL\t%d\t%d\t%d\t%d\t%s\t%s\n", cl.start, cl.end, cl.count, cl.fI, fname, wbuf); // KGJ:398-404
+                put("CALL\t"); num(cl.start); put("\t"); num(cl.end); put("\t"); num(cl.count); put("\t"); num(cl.fI); put("\t"); // KGJ:398-404
+                if (cl.fI >= 0 && (size_t)cl.fI < fn->names.size()) put(fn->names[(size_t)cl.fI]);
+                put("\t"); put(wbuf); put("\n");
             }
             flush_hits(0x7FFFFFFF);
+            flush(false);
         }
-        fprintf(out, "OTU-COUNTS\t%s[%lld]", id, len); // KGJ:518-522
-        for (int j = 0; j < otus[s].n; j++) fprintf(out, "\t%d-%d", otus[s].count[j], otus[s].oI[j]);
-        fputc('\n', out);
+        put("OTU-COUNTS\t"); put(ids); put("["); num(len); put("]"); // KGJ:518-522
+        for (int j = 0; j < otus[s].n; j++) {
+            put("\t"); num(otus[s].count[j]); put("-"); num(otus[s].oI[j]);
+        }
+        put("\n");
+        flush(false);
     }
+    flush(true);
     if (path) fclose(out);
     else fflush(out);
     return KG_OK;
