@@ -223,9 +223,21 @@ struct KgFsm {
 // (the pair-switch test of KGJ:503-507 has fired on every append, so "l2.fI == l1.fI != cur" never survives a step),
 // hence its retained-pair branch (KGJ:442-449) cannot be taken there.  A container's hits can therefore be cut at gaps
 // > max_gap into independent segments, one thread each.  The OTU buffer is order-dependent across calls (KGJ:413-438),
-// so this FSM only MARKS the hits each call counts (flag 1) and a per-sequence replay applies them in order afterwards.
-// flag[i]: 0 = not counted, 2 = counted by the still-open run (tentative), 1 = counted by an emitted CALL.
+// so this FSM only LISTS, per call, the OTU indices of the hits it counts (run-length encoded) and a per-sequence fold
+// applies them in order afterwards.  flag[i]: 0 = not counted, 2 = counted by the run that is open (or was open last).
 // ---------------------------------------------------------------------------------------------------------------
+struct KgSegRuns { // where a segment's OTU runs go: sparse slots starting at the segment's first hit index
+    const int4* payload;
+    int* run_oi;
+    uint32_t* run_m;
+    uint32_t n;
+    __device__ __forceinline__ void out(int oi, uint32_t m) {
+        run_oi[n] = oi;
+        run_m[n] = m;
+        n++;
+    }
+};
+
 struct KgFsmSeg {
     int n, cur, first_pos, cnt, last_match;
     float w;
@@ -267,14 +279,30 @@ struct KgFsmSeg {
         }
     }
     template <class Emit>
-    __device__ __forceinline__ void process(const KgFsmParams& p, Emit& emit, uint8_t* flag) {
+    __device__ __forceinline__ void process(const KgFsmParams& p, Emit& emit, uint8_t* flag, KgSegRuns& runs) {
         if (cnt >= p.min_hits && w >= p.min_weighted) {
             KgDevCall c = {first_pos, last_match + (KG_K - 1), cnt, cur, w, consumed};
             emit(ncalls, c);
             ncalls++;
-            for (uint32_t i = first_idx; i <= last_match_idx; i++) // the hits KGJ:413-439 replays into the OTU buffer
-                if (flag[i] == 2) flag[i] = 1;
-        } // tentative marks of an uncalled run stay 2: they lie outside every later run's index range and are never read
+            // The hits KGJ:413-439 replays into the OTU buffer = the marked hits of this run, in order.  They leave as
+            // runs of equal OTU index (m updates of one index collapse exactly, kg_otu_update_n); a hit is counted by at
+            // most one call, so a segment never emits more runs than it has hits.
+            int ro = 0;
+            uint32_t rm = 0;
+            for (uint32_t i = first_idx; i <= last_match_idx; i++) {
+                if (flag[i] != 2) continue;
+                const int o = reinterpret_cast<const int*>(runs.payload + i)[0];
+                if (rm && o == ro) {
+                    rm++;
+                } else {
+                    if (rm) runs.out(ro, rm);
+                    ro = o;
+                    rm = 1;
+                }
+            }
+            if (rm) runs.out(ro, rm);
+        } // marks of a finished run are never read again: every later run starts at the retained pair or behind it, and
+          // the hits from there on were either re-marked by that run or never marked (rejected or foreign hits)
         if (n >= 2 && l2.fI != cur && l2.fI == l1.fI) {
             cur = l1.fI;
             n = 2;
@@ -291,10 +319,10 @@ struct KgFsmSeg {
         }
     }
     template <class Emit>
-    __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, uint32_t idx, Emit& emit, uint8_t* flag) {
+    __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, uint32_t idx, Emit& emit, uint8_t* flag, KgSegRuns& runs) {
         consumed++;
         if (n > 0 && (int)((unsigned)l1.pos + (unsigned)p.max_gap) < h.pos) {
-            if (n >= p.min_hits) process(p, emit, flag);
+            if (n >= p.min_hits) process(p, emit, flag, runs);
             else n = 0;
         }
         if (n == 0) cur = h.fI;
@@ -306,11 +334,11 @@ struct KgFsmSeg {
         }
         if (accept) {
             if (n < KG_MAX_HITS_PER_SEQ - 2) append(h, idx, flag);
-            if (n > 1 && cur != h.fI && l2.fI == l1.fI) process(p, emit, flag);
+            if (n > 1 && cur != h.fI && l2.fI == l1.fI) process(p, emit, flag, runs);
         }
     }
     template <class Emit>
-    __device__ __forceinline__ void end(const KgFsmParams& p, Emit& emit, uint8_t* flag) {
-        if (n >= p.min_hits) process(p, emit, flag);
+    __device__ __forceinline__ void end(const KgFsmParams& p, Emit& emit, uint8_t* flag, KgSegRuns& runs) {
+        if (n >= p.min_hits) process(p, emit, flag, runs);
     }
 };

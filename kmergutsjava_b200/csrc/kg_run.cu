@@ -621,11 +621,13 @@ __global__ __launch_bounds__(128) void k_fsm_seg(const uint64_t* __restrict__ vo
                                                  const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg,
                                                  const uint32_t* __restrict__ lo, uint32_t cap, KgFsmParams p,
                                                  KgDevCall* __restrict__ sparse, uint32_t* __restrict__ seg_calls,
-                                                 uint8_t* __restrict__ flag) {
+                                                 uint8_t* __restrict__ flag, int* __restrict__ run_oi, uint32_t* __restrict__ run_m,
+                                                 uint32_t* __restrict__ seg_runs) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cap) return;
     if (j >= nseg[0]) {
         seg_calls[j] = 0;
+        seg_runs[j] = 0;
         return;
     }
     const uint32_t a = seg_begin[j], b = seg_begin[j + 1];
@@ -634,16 +636,25 @@ __global__ __launch_bounds__(128) void k_fsm_seg(const uint64_t* __restrict__ vo
     KgFsmSeg f;
     f.begin((int)(a - lo[v])); // HIT lines of this container printed before the segment
     SparseEmit emit{sparse + a / (uint32_t)p.min_hits};
+    KgSegRuns runs{hit_payload, run_oi + a, run_m + a, 0u};
+    uint32_t npos = hit_pos[a]; // hit i+1 is loaded while hit i goes through the FSM
+    int4 npl = hit_payload[a];
     for (uint32_t i = a; i < b; i++) {
-        const int4 pl = hit_payload[i];
-        KgHitLite h = {(int)(hit_pos[i] - base), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
-        f.hit(p, h, i, emit, flag);
+        const uint32_t pos = npos;
+        const int4 pl = npl;
+        if (i + 1 < b) {
+            npos = hit_pos[i + 1];
+            npl = hit_payload[i + 1];
+        }
+        KgHitLite h = {(int)(pos - base), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
+        f.hit(p, h, i, emit, flag, runs);
     }
     // In the reference the run that ends at a gap is processed when the NEXT hit of the container arrives, after that
     // hit's HIT line (KGJ:472-480); only the container's last run is processed after the loop (KGJ:511-513).
     if (j + 1 < nseg[0] && hit_v[b] == v) f.consumed++;
-    f.end(p, emit, flag);
+    f.end(p, emit, flag, runs);
     seg_calls[j] = (uint32_t)f.ncalls;
+    seg_runs[j] = runs.n;
 }
 __global__ void k_compact_calls_seg(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ seg_begin,
                                     const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ hit_v,
@@ -668,78 +679,54 @@ __global__ void k_compact_calls_seg(const KgDevCall* __restrict__ sparse, const 
     }
 }
 // OTU-COUNTS (KGJ:413-438, 516-524): replay, in order, the OTU index of every hit a CALL counted.  Only the fold of the
-// five-entry buffer is inherently sequential, so everything else is done grid-wide first: the counted hits are run-length
-// encoded in parallel (a run = consecutive counted hits of one sequence with the same OTU index; m updates of one index
-// collapse exactly, kg_otu_update_n), and one thread per sequence then folds its runs -- one update per run, typically
-// one per gene, instead of one per hit.
-//   k_otu_prep   per hit: counted?, OTU index, (index+1 if counted)           -> max-scan = previous counted hit,
-//                                                                                sum-scan = rank among the counted hits
-//   k_otu_heads  per counted hit: does it start a run?                         -> sum-scan = run index
-//   k_otu_runs   per run head: (OTU index, counted-rank at the run start)
-//   k_otu_fold   per sequence: runs [hrank[a], hrank[b]) with lengths from the counted-ranks
-__global__ void k_otu_prep(const uint8_t* __restrict__ flag, const int4* __restrict__ hit_payload, const uint32_t* __restrict__ tile_out,
-                           uint32_t ntiles, uint32_t cap1, int* __restrict__ oi, uint32_t* __restrict__ cidx, uint32_t* __restrict__ c01,
-                           const unsigned long long* __restrict__ ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cap1) return;
-    const uint32_t nhits = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
-    const bool c = i < nhits && flag[i] == 1;
-    oi[i] = c ? reinterpret_cast<const int*>(hit_payload + i)[0] : 0;
-    cidx[i] = c ? i + 1 : 0;
-    c01[i] = c;
-}
-struct MaxU32 {
-    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
-};
-__global__ void k_otu_heads(const uint32_t* __restrict__ c01, const uint32_t* __restrict__ prevc, const int* __restrict__ oi,
-                            const uint32_t* __restrict__ hit_v, const uint32_t* __restrict__ lo, int per_seq, uint32_t cap1,
-                            uint32_t* __restrict__ head01) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cap1) return;
-    uint32_t head = 0;
-    if (c01[i]) {
-        const uint32_t p = prevc[i]; // index + 1 of the previous counted hit, 0 = none
-        const uint32_t a = lo[(hit_v[i] / (uint32_t)per_seq) * (uint32_t)per_seq]; // first hit of this sequence
-        head = p == 0 || p - 1 < a || oi[p - 1] != oi[i];
+// five-entry buffer is inherently sequential per sequence.  k_fsm_seg leaves, per segment, the run-length encoded OTU
+// indices of its calls (sparse slots from the segment's first hit index); k_compact_runs packs them in segment order
+// (= print order: +0,+1,+2,-0,-1,-2 and ascending positions, KGJ:540-557) and k_otu_fold folds one sequence per warp.
+__global__ void k_compact_runs(const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ run_off,
+                               const int* __restrict__ run_oi, const uint32_t* __restrict__ run_m, uint32_t cap,
+                               int* __restrict__ dense_oi, uint32_t* __restrict__ dense_m) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cap || j >= nseg[0]) return;
+    const uint32_t o = run_off[j], c = run_off[j + 1] - o, a = seg_begin[j];
+    for (uint32_t k = 0; k < c; k++) {
+        dense_oi[o + k] = run_oi[a + k];
+        dense_m[o + k] = run_m[a + k];
     }
-    head01[i] = head;
 }
-__global__ void k_otu_runs(const uint32_t* __restrict__ head01, const uint32_t* __restrict__ hrank, const uint32_t* __restrict__ crank,
-                           const int* __restrict__ oi, uint32_t cap1, int* __restrict__ run_oi, uint32_t* __restrict__ run_crank) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cap1 || !head01[i]) return;
-    const uint32_t r = hrank[i];
-    run_oi[r] = oi[i];
-    run_crank[r] = crank[i];
-}
-__global__ void k_otu_fold(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const uint32_t* __restrict__ hrank,
-                           const uint32_t* __restrict__ crank, const int* __restrict__ run_oi, const uint32_t* __restrict__ run_crank,
-                           kg_otu* __restrict__ otus, const unsigned long long* __restrict__ ctr) {
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per sequence: 32 runs arrive per coalesced load, every lane then applies them in order (all lanes hold the
+// same buffer; the updates depend on each other, the loads do not).
+__global__ __launch_bounds__(128) void k_otu_fold(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const uint32_t* __restrict__ seg_id,
+                                                  const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ run_off,
+                                                  const int* __restrict__ dense_oi, const uint32_t* __restrict__ dense_m,
+                                                  const uint32_t* __restrict__ tile_out, uint32_t ntiles, kg_otu* __restrict__ otus,
+                                                  const unsigned long long* __restrict__ ctr) {
+    const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (s >= nseq || ctr[KG_CTR_OVERFLOW]) return;
+    const uint32_t nhits = tile_out[ntiles];
     const uint32_t a = lo[s * per_seq], b = lo[(s + 1) * per_seq];
-    const uint32_t r0 = hrank[a], r1 = hrank[b], cend = crank[b]; // exclusive scans: "before index"
+    // the first hit of a container always starts a segment, so these are segment numbers (seg_id = inclusive scan of starts)
+    const uint32_t sa = a < nhits ? seg_id[a] - 1 : nseg[0], sb = b < nhits ? seg_id[b] - 1 : nseg[0];
+    const uint32_t r0 = run_off[sa], r1 = run_off[sb];
     KgOtuBuf u;
     kg_otu_clear(u);
-    for (uint32_t r = r0; r < r1; r += 8) { // eight runs per memory round trip: the loads do not depend on the buffer state
-        int o8[8];
-        uint32_t c9[9];
-#pragma unroll
-        for (int k = 0; k < 8; k++) o8[k] = run_oi[min(r + k, r1 - 1)];
-#pragma unroll
-        for (int k = 0; k < 9; k++) c9[k] = r + k < r1 ? run_crank[r + k] : cend;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (r + k < r1) kg_otu_update_n(u, o8[k], (int)(c9[k + 1] - c9[k]));
+    for (uint32_t r = r0; r < r1; r += 32) {
+        const uint32_t idx = r + (uint32_t)lane;
+        const int o = idx < r1 ? dense_oi[idx] : 0;
+        const uint32_t m = idx < r1 ? dense_m[idx] : 0u;
+        const int cnt = (int)min(32u, r1 - r);
+        for (int k = 0; k < cnt; k++) kg_otu_update_n(u, __shfl_sync(0xFFFFFFFFu, o, k), (int)__shfl_sync(0xFFFFFFFFu, m, k));
     }
-    kg_otu o;
-    o.n = u.n;
+    if (lane == 0) {
+        kg_otu o;
+        o.n = u.n;
 #pragma unroll
-    for (int k = 0; k < KG_OI_BUFSZ; k++) {
-        o.count[k] = u.c[k];
-        o.oI[k] = u.o[k];
+        for (int k = 0; k < KG_OI_BUFSZ; k++) {
+            o.count[k] = u.c[k];
+            o.oI[k] = u.o[k];
+        }
+        otus[s] = o;
     }
-    otus[s] = o;
 }
 
 __global__ void k_compact_calls(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ lo,
@@ -1244,35 +1231,27 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
                                                          cap, sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), d_ctr);
         k_lo<<<blocks_for(nv + 1, 256), 256, 0, st>>>(b->voffsets(), nv, sl.hit_pos.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
                                                      sl.lo.as<uint32_t>(), d_ctr);
+        for (DevBuf* d : {&sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_crank, &sl.o_run_oi, &sl.o_run_crank}) KG_TRY(d->ensure(((size_t)cap + 1) * 4));
         k_fsm_seg<<<blocks_for(cap, 128), 128, 0, st>>>(b->voffsets(), sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), sl.hit_v.as<uint32_t>(),
                                                        sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), sl.lo.as<uint32_t>(), cap, fp,
-                                                       sl.sparse.as<KgDevCall>(), sl.call_cnt.as<uint32_t>(), sl.hit_flag.as<uint8_t>());
+                                                       sl.sparse.as<KgDevCall>(), sl.call_cnt.as<uint32_t>(), sl.hit_flag.as<uint8_t>(),
+                                                       sl.o_oi.as<int>(), sl.o_cidx.as<uint32_t>(), sl.o_c01.as<uint32_t>());
         CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + cap, 0, 4, st));
         KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), (size_t)cap + 1, st));
         k_compact_calls_seg<<<blocks_for(cap, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(),
                                                                  sl.hit_v.as<uint32_t>(), sl.call_off.as<uint32_t>(), cap, per_seq, prm->min_hits,
                                                                  seq_base, r->d_calls.as<kg_call>());
-        { // OTU-COUNTS: parallel run-length encoding of the counted hits, then one thread per sequence folds its runs
-            const uint32_t cap1 = cap + 1; // index cap = "one past the last hit": the exclusive scans are read there too
-            for (DevBuf* d : {&sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_prevc, &sl.o_crank, &sl.o_head, &sl.o_hrank, &sl.o_run_oi, &sl.o_run_crank})
-                KG_TRY(d->ensure((size_t)cap1 * 4));
-            k_otu_prep<<<blocks_for(cap1, 256), 256, 0, st>>>(sl.hit_flag.as<uint8_t>(), sl.hit_payload.as<int4>(), sl.tile_out.as<uint32_t>(), ntiles,
-                                                             cap1, sl.o_oi.as<int>(), sl.o_cidx.as<uint32_t>(), sl.o_c01.as<uint32_t>(), d_ctr);
-            size_t tb = 0;
-            CU(cub::DeviceScan::ExclusiveScan(nullptr, tb, sl.o_cidx.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), MaxU32(), 0u, (size_t)cap1, st));
-            KG_TRY(scan_tmp_of(ctx, st).ensure(tb));
-            CU(cub::DeviceScan::ExclusiveScan(scan_tmp_of(ctx, st).p, tb, sl.o_cidx.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), MaxU32(), 0u, (size_t)cap1, st));
-            KG_TRY(exclusive_sum_u32(ctx, sl.o_c01.as<uint32_t>(), sl.o_crank.as<uint32_t>(), cap1, st));
-            k_otu_heads<<<blocks_for(cap1, 256), 256, 0, st>>>(sl.o_c01.as<uint32_t>(), sl.o_prevc.as<uint32_t>(), sl.o_oi.as<int>(), sl.hit_v.as<uint32_t>(),
-                                                              sl.lo.as<uint32_t>(), per_seq, cap1, sl.o_head.as<uint32_t>());
-            KG_TRY(exclusive_sum_u32(ctx, sl.o_head.as<uint32_t>(), sl.o_hrank.as<uint32_t>(), cap1, st));
-            k_otu_runs<<<blocks_for(cap1, 256), 256, 0, st>>>(sl.o_head.as<uint32_t>(), sl.o_hrank.as<uint32_t>(), sl.o_crank.as<uint32_t>(),
-                                                             sl.o_oi.as<int>(), cap1, sl.o_run_oi.as<int>(), sl.o_run_crank.as<uint32_t>());
-            if (b->n)
-                k_otu_fold<<<blocks_for(b->n, 64), 64, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.o_hrank.as<uint32_t>(), sl.o_crank.as<uint32_t>(),
-                                                               sl.o_run_oi.as<int>(), sl.o_run_crank.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
-        }
-        sl.launches += 14;
+        // OTU-COUNTS: the runs k_fsm_seg listed per segment, packed in print order, folded one sequence per warp
+        CU(cudaMemsetAsync(sl.o_c01.as<uint32_t>() + cap, 0, 4, st));
+        KG_TRY(exclusive_sum_u32(ctx, sl.o_c01.as<uint32_t>(), sl.o_crank.as<uint32_t>(), (size_t)cap + 1, st));
+        k_compact_runs<<<blocks_for(cap, 256), 256, 0, st>>>(sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), sl.o_crank.as<uint32_t>(),
+                                                            sl.o_oi.as<int>(), sl.o_cidx.as<uint32_t>(), cap, sl.o_run_oi.as<int>(),
+                                                            sl.o_run_crank.as<uint32_t>());
+        if (b->n)
+            k_otu_fold<<<blocks_for(b->n * 32, 128), 128, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.seg_id.as<uint32_t>(), sl.nseg.as<uint32_t>(),
+                                                                  sl.o_crank.as<uint32_t>(), sl.o_run_oi.as<int>(), sl.o_run_crank.as<uint32_t>(),
+                                                                  sl.tile_out.as<uint32_t>(), ntiles, r->d_otus.as<kg_otu>(), d_ctr);
+        sl.launches += 10;
         CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + cap, 4, cudaMemcpyDeviceToHost, st));
     }
     cudaEventRecord(sl.ev[3], st);
