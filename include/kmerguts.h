@@ -143,7 +143,8 @@ int kg_run(kg_context* ctx, const kg_table* table, int mode, const uint8_t* seq_
 int kg_batch_upload(kg_context* ctx, int mode, const uint8_t* seq_bytes, const uint64_t* offsets, size_t n,
                     kg_batch** batch);
 /* Adopt sequences that are ALREADY in device memory (d_seq_bytes is modified in place in aa mode; d_offsets is a
- * device array of n+1 uint64).  The batch does not own the two buffers. */
+ * device array of n+1 uint64).  d_seq_bytes must be 16-byte aligned and followed by at least 64 readable bytes (the
+ * kernels read whole 16-byte words).  The batch does not own the two buffers. */
 int kg_batch_from_device(kg_context* ctx, int mode, uint8_t* d_seq_bytes, const uint64_t* d_offsets, size_t n,
                          uint64_t total_bytes, kg_batch** batch);
 void kg_batch_free(kg_batch* batch);

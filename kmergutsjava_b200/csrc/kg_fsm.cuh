@@ -224,17 +224,15 @@ struct KgFsm {
 // hence its retained-pair branch (KGJ:442-449) cannot be taken there.  A container's hits can therefore be cut at gaps
 // > max_gap into independent segments, one thread each.  The OTU buffer is order-dependent across calls (KGJ:413-438),
 // so this FSM only LISTS, per call, the OTU indices of the hits it counts (run-length encoded) and a per-sequence fold
-// applies them in order afterwards.  flag[i]: 0 = not counted, 2 = counted by the run that is open (or was open last).
+// applies them in order afterwards.
 // ---------------------------------------------------------------------------------------------------------------
 struct KgSegRuns { // where a segment's OTU runs go: sparse slots starting at the segment's first hit index
-    const int4* payload;
     int* run_oi;
     uint32_t* run_m;
-    uint32_t n;
-    __device__ __forceinline__ void out(int oi, uint32_t m) {
-        run_oi[n] = oi;
-        run_m[n] = m;
-        n++;
+    uint32_t n; // runs of emitted calls
+    __device__ __forceinline__ void put(uint32_t at, int oi, uint32_t m) {
+        run_oi[at] = oi;
+        run_m[at] = m;
     }
 };
 
@@ -242,9 +240,15 @@ struct KgFsmSeg {
     int n, cur, first_pos, cnt, last_match;
     float w;
     KgHitLite l1, l2;
-    uint32_t i1, i2;          // global hit indices of l1 / l2
-    uint32_t first_idx, last_match_idx;
     int consumed, ncalls;
+    // The hits KGJ:413-439 would replay into the OTU buffer if the open run is called = its hits with fI == cur, in
+    // order.  They are run-length encoded as they arrive (m updates of one index collapse exactly, kg_otu_update_n):
+    // finished runs wait in the output slots behind the committed ones, (ro, rm) is the run still growing.  A call commits
+    // them; a run that is dropped just forgets them.  A hit is counted by at most one call, so committed + waiting runs
+    // never outnumber the hits seen so far and stay inside the segment's own slots.
+    uint32_t tent;
+    int ro;
+    uint32_t rm;
 
     __device__ __forceinline__ void begin(int consumed0) {
         n = 0;
@@ -256,73 +260,66 @@ struct KgFsmSeg {
         first_pos = last_match = 0;
         l1 = KgHitLite{0, 0, 0, 0, 0.f};
         l2 = l1;
-        i1 = i2 = first_idx = last_match_idx = 0;
+        tent = 0;
+        ro = 0;
+        rm = 0;
     }
-    __device__ __forceinline__ void append(const KgHitLite& h, uint32_t idx, uint8_t* flag) {
+    __device__ __forceinline__ void count_oi(int oI, KgSegRuns& runs) {
+        if (rm && oI == ro) {
+            rm++;
+        } else {
+            if (rm) runs.put(runs.n + tent++, ro, rm);
+            ro = oI;
+            rm = 1;
+        }
+    }
+    __device__ __forceinline__ void append(const KgHitLite& h, KgSegRuns& runs) {
         if (n == 0) {
             first_pos = h.pos;
-            first_idx = idx;
             cnt = 0;
             w = 0.f;
+            tent = 0;
+            rm = 0;
         }
         n++;
         l2 = l1;
-        i2 = i1;
         l1 = h;
-        i1 = idx;
         if (h.fI == cur) {
             cnt++;
             w = __fadd_rn(w, h.wt);
             last_match = h.pos;
-            last_match_idx = idx;
-            flag[idx] = 2;
+            count_oi(h.oI, runs);
         }
     }
     template <class Emit>
-    __device__ __forceinline__ void process(const KgFsmParams& p, Emit& emit, uint8_t* flag, KgSegRuns& runs) {
+    __device__ __forceinline__ void process(const KgFsmParams& p, Emit& emit, KgSegRuns& runs) {
         if (cnt >= p.min_hits && w >= p.min_weighted) {
             KgDevCall c = {first_pos, last_match + (KG_K - 1), cnt, cur, w, consumed};
             emit(ncalls, c);
             ncalls++;
-            // The hits KGJ:413-439 replays into the OTU buffer = the marked hits of this run, in order.  They leave as
-            // runs of equal OTU index (m updates of one index collapse exactly, kg_otu_update_n); a hit is counted by at
-            // most one call, so a segment never emits more runs than it has hits.
-            int ro = 0;
-            uint32_t rm = 0;
-            for (uint32_t i = first_idx; i <= last_match_idx; i++) {
-                if (flag[i] != 2) continue;
-                const int o = reinterpret_cast<const int*>(runs.payload + i)[0];
-                if (rm && o == ro) {
-                    rm++;
-                } else {
-                    if (rm) runs.out(ro, rm);
-                    ro = o;
-                    rm = 1;
-                }
-            }
-            if (rm) runs.out(ro, rm);
-        } // marks of a finished run are never read again: every later run starts at the retained pair or behind it, and
-          // the hits from there on were either re-marked by that run or never marked (rejected or foreign hits)
-        if (n >= 2 && l2.fI != cur && l2.fI == l1.fI) {
+            if (rm) runs.put(runs.n + tent++, ro, rm);
+            runs.n += tent;
+        }
+        tent = 0;
+        rm = 0;
+        if (n >= 2 && l2.fI != cur && l2.fI == l1.fI) { // the retained pair seeds the next run (KGJ:442-449)
             cur = l1.fI;
             n = 2;
             first_pos = l2.pos;
-            first_idx = i2;
             cnt = 2;
             w = __fadd_rn(__fadd_rn(0.f, l2.wt), l1.wt);
             last_match = l1.pos;
-            last_match_idx = i1;
-            flag[i2] = 2;
-            flag[i1] = 2;
+            count_oi(l2.oI, runs);
+            count_oi(l1.oI, runs);
         } else {
             n = 0;
         }
     }
     template <class Emit>
-    __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, uint32_t idx, Emit& emit, uint8_t* flag, KgSegRuns& runs) {
+    __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, Emit& emit, KgSegRuns& runs) {
         consumed++;
         if (n > 0 && (int)((unsigned)l1.pos + (unsigned)p.max_gap) < h.pos) {
-            if (n >= p.min_hits) process(p, emit, flag, runs);
+            if (n >= p.min_hits) process(p, emit, runs);
             else n = 0;
         }
         if (n == 0) cur = h.fI;
@@ -333,12 +330,12 @@ struct KgFsmSeg {
             accept = (h.fI == l1.fI) && ad <= 20;
         }
         if (accept) {
-            if (n < KG_MAX_HITS_PER_SEQ - 2) append(h, idx, flag);
-            if (n > 1 && cur != h.fI && l2.fI == l1.fI) process(p, emit, flag, runs);
+            if (n < KG_MAX_HITS_PER_SEQ - 2) append(h, runs);
+            if (n > 1 && cur != h.fI && l2.fI == l1.fI) process(p, emit, runs);
         }
     }
     template <class Emit>
-    __device__ __forceinline__ void end(const KgFsmParams& p, Emit& emit, uint8_t* flag, KgSegRuns& runs) {
-        if (n >= p.min_hits) process(p, emit, flag, runs);
+    __device__ __forceinline__ void end(const KgFsmParams& p, Emit& emit, KgSegRuns& runs) {
+        if (n >= p.min_hits) process(p, emit, runs);
     }
 };

@@ -89,28 +89,21 @@ __global__ void k_vlen(const uint64_t* __restrict__ off, uint64_t n, uint64_t* _
     vlen[v] = (nk + 1 + 3) & ~3ull; // residues + terminator, rounded up to 4 (all padding bytes are 0 = separator)
 }
 
-// One thread per 4-byte word of the translated stream: it finds its virtual protein (binary search over the nv+1
-// offsets, which are multiples of 4), translates four consecutive codons of that frame and writes one aligned word --
-// residues, then the terminator / padding zeros (so the stream needs no memset).  Codon and amino-acid tables sit in
-// shared memory.  Forward frame f: codon j starts at nucleotide f+3j (KGJ:323-338).  Reverse frames are frames of the
-// reverse complement (KGJ:1068-1071): its base q is compl(seq[L-1-q]), and compl() maps ACGTU (either case) onto the
-// complementary base and never maps anything else onto ACGTU, so the complemented code is simply 3 - code.
-__global__ __launch_bounds__(256) void k_translate(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off, uint64_t n,
-                                                   const uint64_t* __restrict__ voff, uint64_t nv, uint64_t vwords,
-                                                   uint32_t* __restrict__ vseq_words) {
-    __shared__ uint8_t s_nt[256];   // dnaChar, KGJ:294-318
-    __shared__ char s_code[64];     // GENETIC_CODE, KGJ:88-93
-    s_nt[threadIdx.x] = (uint8_t)dna_code((uint8_t)threadIdx.x);
-    if (threadIdx.x < 64) s_code[threadIdx.x] = c_genetic_code[threadIdx.x];
-    __syncthreads();
-    // the block's 256 words almost always lie in one virtual protein: search once per block, then step forward
-    __shared__ uint64_t s_v0;
-    if (threadIdx.x == 0) s_v0 = seq_of(voff, nv, 4ull * blockIdx.x * blockDim.x);
-    __syncthreads();
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= vwords) return;
-    const uint64_t g = 4 * t;
-    uint64_t v = s_v0;
+// One thread per 4-byte word of the translated stream (four codons of one frame in, one aligned word out: residues, then
+// the terminator / padding zeros, so the stream needs no memset); a block makes 1024 consecutive residues.  Codon and
+// amino-acid tables sit in shared memory.  Forward frame f: codon j starts at nucleotide f+3j (KGJ:323-338).  Reverse
+// frames are frames of the reverse complement (KGJ:1068-1071): its base q is compl(seq[L-1-q]), and compl() maps ACGTU
+// (either case) onto the complementary base and never maps anything else onto ACGTU, so the complemented code is simply
+// 3 - code.
+// Fast path (all but a few hundred blocks): the block's residues lie in ONE virtual protein, so thread 0 resolves
+// (protein, contig, frame, strand) once, the 3072 nucleotides the block needs -- one contiguous span of the contig for
+// either strand -- arrive as coalesced 16-byte loads and are turned into 2-bit codes in shared memory, and every thread
+// builds its four codons from twelve shared-memory bytes with 32-bit arithmetic only.
+constexpr int TR_BLK = 256;                    // threads = words per block
+constexpr int TR_SPAN = TR_BLK * 4 * 3;        // nucleotides behind one block's residues
+__device__ __forceinline__ uint32_t translate_word_slow(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off,
+                                                        const uint64_t* __restrict__ voff, uint64_t nv, uint64_t v, uint64_t g,
+                                                        const uint8_t* s_nt, const char* s_code) {
     while (v + 1 < nv && voff[v + 1] <= g) v++;
     const uint64_t sidx = v / 6;
     const uint32_t k = (uint32_t)(v % 6), f = k % 3;
@@ -141,6 +134,98 @@ __global__ __launch_bounds__(256) void k_translate(const uint8_t* __restrict__ s
             }
             const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[c1 * 16 + c2 * 4 + c3] : (uint32_t)'x';
             word |= aa << (8 * r);
+        }
+    }
+    return word;
+}
+
+__global__ __launch_bounds__(TR_BLK) void k_translate(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off, uint64_t n,
+                                                      const uint64_t* __restrict__ voff, uint64_t nv, uint64_t vwords,
+                                                      uint32_t* __restrict__ vseq_words) {
+    __shared__ uint8_t s_nt[256];   // dnaChar, KGJ:294-318
+    __shared__ char s_code[64];     // GENETIC_CODE, KGJ:88-93
+    __shared__ __align__(16) uint8_t s_span[TR_SPAN + 32]; // nucleotide codes of the block's span (16-byte aligned chunks)
+    __shared__ uint64_t s_v0, s_lo;      // first virtual protein of the block; byte address of s_span[0] in seq
+    __shared__ uint32_t s_fast, s_first, s_j0, s_nk, s_rev, s_nch; // s_first: index in s_span of the block's first nucleotide; s_nch: chunks to stage
+    const int tid = threadIdx.x;
+    s_nt[tid] = (uint8_t)dna_code((uint8_t)tid);
+    if (tid < 64) s_code[tid] = c_genetic_code[tid];
+    const uint64_t t0 = (uint64_t)blockIdx.x * TR_BLK;
+    if (tid == 0) {
+        const uint64_t g0 = 4 * t0;
+        const uint64_t v = seq_of(voff, nv, g0);
+        s_v0 = v;
+        const uint64_t gend = 4 * min((uint64_t)(t0 + TR_BLK), vwords); // one past the block's last residue
+        uint32_t fast = v < nv && voff[v + 1] >= gend;
+        if (fast) {
+            const uint64_t sidx = v / 6;
+            const uint32_t k = (uint32_t)(v % 6), f = k % 3;
+            const uint64_t base = off[sidx], L = off[sidx + 1] - base;
+            const uint64_t nk = L >= f + 3 ? (L - f) / 3 : 0;
+            const uint64_t j0 = g0 - voff[v];
+            // strand coordinates [p0, p1) of the block's codons, clipped to the frame's last whole codon
+            const uint64_t p0 = f + 3 * j0, p1 = min((uint64_t)(f + 3 * (j0 + 4ull * TR_BLK)), (uint64_t)(f + 3 * nk));
+            uint64_t lo_addr = 0;
+            uint32_t first = 0, nch = 0;
+            if (p1 > p0) {
+                // forward: seq[base+p0 .. base+p1); reverse: seq[base+L-p1 .. base+L-p0), read downwards
+                const uint64_t a = k < 3 ? base + p0 : base + L - p1;
+                lo_addr = a & ~15ull;
+                first = k < 3 ? (uint32_t)(a - lo_addr) : (uint32_t)(base + L - 1 - p0 - lo_addr);
+                nch = (uint32_t)((a - lo_addr + (p1 - p0) + 15) / 16); // whole chunks: at most 15 bytes past the contig, inside the padding
+            }
+            s_nch = nch;
+            s_lo = lo_addr;
+            s_first = first;
+            s_j0 = (uint32_t)min(j0, (uint64_t)0xFFFFFFFFu);
+            s_nk = (uint32_t)min(nk, (uint64_t)0xFFFFFFFFu);
+            s_rev = k >= 3;
+            if (j0 > 0xFFFF0000ull || nk > 0xFFFF0000ull) fast = 0;
+        }
+        s_fast = fast;
+    }
+    __syncthreads();
+    const uint64_t t = t0 + tid;
+    if (!s_fast) {
+        if (t < vwords) vseq_words[t] = translate_word_slow(seq, off, voff, nv, s_v0, 4 * t, s_nt, s_code);
+        return;
+    }
+    // stage: TR_SPAN + 15 bytes at most (the span starts up to 15 bytes into its first chunk); the sequence buffer is
+    // 16-byte aligned and padded by 64 bytes, so whole chunks can be read
+    for (int c = tid; c < (int)s_nch; c += TR_BLK) {
+        const uint4 w = *reinterpret_cast<const uint4*>(seq + s_lo + 16ull * c);
+        const uint32_t in[4] = {w.x, w.y, w.z, w.w};
+        uint32_t out[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            out[q] = (uint32_t)s_nt[in[q] & 0xFFu] | ((uint32_t)s_nt[(in[q] >> 8) & 0xFFu] << 8) | ((uint32_t)s_nt[(in[q] >> 16) & 0xFFu] << 16) |
+                     ((uint32_t)s_nt[in[q] >> 24] << 24);
+        *reinterpret_cast<uint4*>(s_span + 16 * c) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    __syncthreads();
+    if (t >= vwords) return;
+    const uint32_t jl = 4u * (uint32_t)tid; // first residue of this thread, relative to the block
+    const uint32_t j0 = s_j0 + jl, nk = s_nk;
+    uint32_t word = 0;
+    if (!s_rev) {
+        const uint8_t* p = s_span + s_first + 3u * jl;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (j0 + r < nk) {
+                const int c1 = p[3 * r], c2 = p[3 * r + 1], c3 = p[3 * r + 2];
+                const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[c1 * 16 + c2 * 4 + c3] : (uint32_t)'x';
+                word |= aa << (8 * r);
+            }
+        }
+    } else {
+        const uint8_t* p = s_span + s_first - 3u * jl; // codon r: p[-3r], p[-3r-1], p[-3r-2]
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (j0 + r < nk) {
+                const int c1 = *(p - 3 * r), c2 = *(p - 3 * r - 1), c3 = *(p - 3 * r - 2);
+                const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[(3 - c1) * 16 + (3 - c2) * 4 + (3 - c3)] : (uint32_t)'x';
+                word |= aa << (8 * r);
+            }
         }
     }
     vseq_words[t] = word;
@@ -621,8 +706,7 @@ __global__ __launch_bounds__(128) void k_fsm_seg(const uint64_t* __restrict__ vo
                                                  const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg,
                                                  const uint32_t* __restrict__ lo, uint32_t cap, KgFsmParams p,
                                                  KgDevCall* __restrict__ sparse, uint32_t* __restrict__ seg_calls,
-                                                 uint8_t* __restrict__ flag, int* __restrict__ run_oi, uint32_t* __restrict__ run_m,
-                                                 uint32_t* __restrict__ seg_runs) {
+                                                 int* __restrict__ run_oi, uint32_t* __restrict__ run_m, uint32_t* __restrict__ seg_runs) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cap) return;
     if (j >= nseg[0]) {
@@ -636,7 +720,7 @@ __global__ __launch_bounds__(128) void k_fsm_seg(const uint64_t* __restrict__ vo
     KgFsmSeg f;
     f.begin((int)(a - lo[v])); // HIT lines of this container printed before the segment
     SparseEmit emit{sparse + a / (uint32_t)p.min_hits};
-    KgSegRuns runs{hit_payload, run_oi + a, run_m + a, 0u};
+    KgSegRuns runs{run_oi + a, run_m + a, 0u};
     uint32_t npos = hit_pos[a]; // hit i+1 is loaded while hit i goes through the FSM
     int4 npl = hit_payload[a];
     for (uint32_t i = a; i < b; i++) {
@@ -647,12 +731,12 @@ __global__ __launch_bounds__(128) void k_fsm_seg(const uint64_t* __restrict__ vo
             npl = hit_payload[i + 1];
         }
         KgHitLite h = {(int)(pos - base), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
-        f.hit(p, h, i, emit, flag, runs);
+        f.hit(p, h, emit, runs);
     }
     // In the reference the run that ends at a gap is processed when the NEXT hit of the container arrives, after that
     // hit's HIT line (KGJ:472-480); only the container's last run is processed after the loop (KGJ:511-513).
     if (j + 1 < nseg[0] && hit_v[b] == v) f.consumed++;
-    f.end(p, emit, flag, runs);
+    f.end(p, emit, runs);
     seg_calls[j] = (uint32_t)f.ncalls;
     seg_runs[j] = runs.n;
 }
@@ -1213,11 +1297,9 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
         KG_TRY(sl.seg_flag.ensure((size_t)cap * 4));
         KG_TRY(sl.seg_id.ensure((size_t)cap * 4));
         KG_TRY(sl.seg_begin.ensure(((size_t)cap + 1) * 4));
-        KG_TRY(sl.hit_flag.ensure(cap));
         KG_TRY(sl.nseg.ensure(16));
         KG_TRY(sl.call_cnt.ensure(((size_t)cap + 1) * 4)); // per segment here
         KG_TRY(sl.call_off.ensure(((size_t)cap + 1) * 4));
-        CU(cudaMemsetAsync(sl.hit_flag.p, 0, cap, st));
         if (ntiles) {
             k_gather<<<blocks_for((size_t)ntiles * 32, 256), 256, 0, st>>>(sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
                                                                           sl.tile_base.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
@@ -1234,8 +1316,8 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
         for (DevBuf* d : {&sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_crank, &sl.o_run_oi, &sl.o_run_crank}) KG_TRY(d->ensure(((size_t)cap + 1) * 4));
         k_fsm_seg<<<blocks_for(cap, 128), 128, 0, st>>>(b->voffsets(), sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), sl.hit_v.as<uint32_t>(),
                                                        sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), sl.lo.as<uint32_t>(), cap, fp,
-                                                       sl.sparse.as<KgDevCall>(), sl.call_cnt.as<uint32_t>(), sl.hit_flag.as<uint8_t>(),
-                                                       sl.o_oi.as<int>(), sl.o_cidx.as<uint32_t>(), sl.o_c01.as<uint32_t>());
+                                                       sl.sparse.as<KgDevCall>(), sl.call_cnt.as<uint32_t>(), sl.o_oi.as<int>(),
+                                                       sl.o_cidx.as<uint32_t>(), sl.o_c01.as<uint32_t>());
         CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + cap, 0, 4, st));
         KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), (size_t)cap + 1, st));
         k_compact_calls_seg<<<blocks_for(cap, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(),
