@@ -90,7 +90,7 @@ __global__ void k_vlen(const uint64_t* __restrict__ off, uint64_t n, uint64_t* _
 }
 
 // One thread per 4-byte word of the translated stream (four codons of one frame in, one aligned word out: residues, then
-// the terminator / padding zeros, so the stream needs no memset); a block makes 1024 consecutive residues.  Codon and
+// the terminator / padding zeros, so the stream needs no memset); a block makes TR_PASSES x 1024 consecutive residues.  Codon and
 // amino-acid tables sit in shared memory.  Forward frame f: codon j starts at nucleotide f+3j (KGJ:323-338).  Reverse
 // frames are frames of the reverse complement (KGJ:1068-1071): its base q is compl(seq[L-1-q]), and compl() maps ACGTU
 // (either case) onto the complementary base and never maps anything else onto ACGTU, so the complemented code is simply
@@ -100,7 +100,8 @@ __global__ void k_vlen(const uint64_t* __restrict__ off, uint64_t n, uint64_t* _
 // either strand -- arrive as coalesced 16-byte loads and are turned into 2-bit codes in shared memory, and every thread
 // builds its four codons from twelve shared-memory bytes with 32-bit arithmetic only.
 constexpr int TR_BLK = 256;                    // threads = words per block
-constexpr int TR_SPAN = TR_BLK * 4 * 3;        // nucleotides behind one block's residues
+constexpr int TR_SPAN = TR_BLK * 4 * 3;        // nucleotides behind the residues of one pass
+constexpr int TR_PASSES = 8;                   // passes per block: the block's set-up (a binary search, divisions) is paid once
 __device__ __forceinline__ uint32_t translate_word_slow(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off,
                                                         const uint64_t* __restrict__ voff, uint64_t nv, uint64_t v, uint64_t g,
                                                         const uint8_t* s_nt, const char* s_code) {
@@ -144,18 +145,18 @@ __global__ __launch_bounds__(TR_BLK) void k_translate(const uint8_t* __restrict_
                                                       uint32_t* __restrict__ vseq_words) {
     __shared__ uint8_t s_nt[256];   // dnaChar, KGJ:294-318
     __shared__ char s_code[64];     // GENETIC_CODE, KGJ:88-93
-    __shared__ __align__(16) uint8_t s_span[TR_SPAN + 32]; // nucleotide codes of the block's span (16-byte aligned chunks)
-    __shared__ uint64_t s_v0, s_lo;      // first virtual protein of the block; byte address of s_span[0] in seq
-    __shared__ uint32_t s_fast, s_first, s_j0, s_nk, s_rev, s_nch; // s_first: index in s_span of the block's first nucleotide; s_nch: chunks to stage
+    __shared__ __align__(16) uint8_t s_span[TR_SPAN + 32]; // nucleotide codes of one pass (16-byte aligned chunks)
+    __shared__ uint64_t s_v0, s_base, s_L, s_p0; // first virtual protein of the block; its contig; strand coordinate of the block's first codon
+    __shared__ uint32_t s_fast, s_j0, s_nk, s_rev, s_f;
     const int tid = threadIdx.x;
     s_nt[tid] = (uint8_t)dna_code((uint8_t)tid);
     if (tid < 64) s_code[tid] = c_genetic_code[tid];
-    const uint64_t t0 = (uint64_t)blockIdx.x * TR_BLK;
-    if (tid == 0) {
+    const uint64_t t0 = (uint64_t)blockIdx.x * (TR_BLK * TR_PASSES);
+    if (tid == 0) { // the only binary search, divisions and dependent offset loads of the block
         const uint64_t g0 = 4 * t0;
         const uint64_t v = seq_of(voff, nv, g0);
         s_v0 = v;
-        const uint64_t gend = 4 * min((uint64_t)(t0 + TR_BLK), vwords); // one past the block's last residue
+        const uint64_t gend = 4 * min((uint64_t)(t0 + TR_BLK * TR_PASSES), vwords); // one past the block's last residue
         uint32_t fast = v < nv && voff[v + 1] >= gend;
         if (fast) {
             const uint64_t sidx = v / 6;
@@ -163,72 +164,81 @@ __global__ __launch_bounds__(TR_BLK) void k_translate(const uint8_t* __restrict_
             const uint64_t base = off[sidx], L = off[sidx + 1] - base;
             const uint64_t nk = L >= f + 3 ? (L - f) / 3 : 0;
             const uint64_t j0 = g0 - voff[v];
-            // strand coordinates [p0, p1) of the block's codons, clipped to the frame's last whole codon
-            const uint64_t p0 = f + 3 * j0, p1 = min((uint64_t)(f + 3 * (j0 + 4ull * TR_BLK)), (uint64_t)(f + 3 * nk));
-            uint64_t lo_addr = 0;
-            uint32_t first = 0, nch = 0;
-            if (p1 > p0) {
-                // forward: seq[base+p0 .. base+p1); reverse: seq[base+L-p1 .. base+L-p0), read downwards
-                const uint64_t a = k < 3 ? base + p0 : base + L - p1;
-                lo_addr = a & ~15ull;
-                first = k < 3 ? (uint32_t)(a - lo_addr) : (uint32_t)(base + L - 1 - p0 - lo_addr);
-                nch = (uint32_t)((a - lo_addr + (p1 - p0) + 15) / 16); // whole chunks: at most 15 bytes past the contig, inside the padding
-            }
-            s_nch = nch;
-            s_lo = lo_addr;
-            s_first = first;
+            s_base = base;
+            s_L = L;
+            s_f = f;
+            s_p0 = f + 3 * j0;
             s_j0 = (uint32_t)min(j0, (uint64_t)0xFFFFFFFFu);
             s_nk = (uint32_t)min(nk, (uint64_t)0xFFFFFFFFu);
             s_rev = k >= 3;
-            if (j0 > 0xFFFF0000ull || nk > 0xFFFF0000ull) fast = 0;
+            if (j0 > 0xFFF00000ull || nk > 0xFFF00000ull) fast = 0;
         }
         s_fast = fast;
     }
     __syncthreads();
-    const uint64_t t = t0 + tid;
     if (!s_fast) {
-        if (t < vwords) vseq_words[t] = translate_word_slow(seq, off, voff, nv, s_v0, 4 * t, s_nt, s_code);
+        for (int pass = 0; pass < TR_PASSES; pass++) {
+            const uint64_t t = t0 + (uint64_t)pass * TR_BLK + tid;
+            if (t < vwords) vseq_words[t] = translate_word_slow(seq, off, voff, nv, s_v0, 4 * t, s_nt, s_code);
+        }
         return;
     }
-    // stage: TR_SPAN + 15 bytes at most (the span starts up to 15 bytes into its first chunk); the sequence buffer is
-    // 16-byte aligned and padded by 64 bytes, so whole chunks can be read
-    for (int c = tid; c < (int)s_nch; c += TR_BLK) {
-        const uint4 w = *reinterpret_cast<const uint4*>(seq + s_lo + 16ull * c);
-        const uint32_t in[4] = {w.x, w.y, w.z, w.w};
-        uint32_t out[4];
+    const uint64_t base = s_base, L = s_L;
+    const uint32_t nk = s_nk;
+    const bool rev = s_rev;
+    const uint64_t pend = (uint64_t)s_f + 3ull * nk; // one past the frame's last whole codon, strand coordinates
+    for (int pass = 0; pass < TR_PASSES; pass++) {
+        // strand coordinates [p0, p1) of this pass's codons
+        const uint64_t p0 = s_p0 + (uint64_t)pass * TR_SPAN, p1 = min((uint64_t)(p0 + TR_SPAN), pend);
+        uint32_t first = 0, nch = 0;
+        uint64_t lo_addr = 0;
+        if (p1 > p0) {
+            // forward: seq[base+p0 .. base+p1); reverse: seq[base+L-p1 .. base+L-p0), read downwards
+            const uint64_t a = !rev ? base + p0 : base + L - p1;
+            lo_addr = a & ~15ull;
+            first = !rev ? (uint32_t)(a - lo_addr) : (uint32_t)(base + L - 1 - p0 - lo_addr);
+            nch = (uint32_t)((a - lo_addr + (p1 - p0) + 15) / 16); // whole chunks: at most 15 bytes past the contig, inside the padding
+        }
+        if (pass) __syncthreads(); // the previous pass has finished reading s_span
+        for (int c = tid; c < (int)nch; c += TR_BLK) {
+            const uint4 w = *reinterpret_cast<const uint4*>(seq + lo_addr + 16ull * c);
+            const uint32_t in[4] = {w.x, w.y, w.z, w.w};
+            uint32_t out[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-            out[q] = (uint32_t)s_nt[in[q] & 0xFFu] | ((uint32_t)s_nt[(in[q] >> 8) & 0xFFu] << 8) | ((uint32_t)s_nt[(in[q] >> 16) & 0xFFu] << 16) |
-                     ((uint32_t)s_nt[in[q] >> 24] << 24);
-        *reinterpret_cast<uint4*>(s_span + 16 * c) = make_uint4(out[0], out[1], out[2], out[3]);
-    }
-    __syncthreads();
-    if (t >= vwords) return;
-    const uint32_t jl = 4u * (uint32_t)tid; // first residue of this thread, relative to the block
-    const uint32_t j0 = s_j0 + jl, nk = s_nk;
-    uint32_t word = 0;
-    if (!s_rev) {
-        const uint8_t* p = s_span + s_first + 3u * jl;
+            for (int q = 0; q < 4; q++)
+                out[q] = (uint32_t)s_nt[in[q] & 0xFFu] | ((uint32_t)s_nt[(in[q] >> 8) & 0xFFu] << 8) | ((uint32_t)s_nt[(in[q] >> 16) & 0xFFu] << 16) |
+                         ((uint32_t)s_nt[in[q] >> 24] << 24);
+            *reinterpret_cast<uint4*>(s_span + 16 * c) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+        __syncthreads();
+        const uint64_t t = t0 + (uint64_t)pass * TR_BLK + tid;
+        if (t >= vwords) continue;
+        const uint32_t jl = 4u * (uint32_t)tid; // first residue of this thread, relative to the pass
+        const uint32_t j0 = s_j0 + (uint32_t)pass * (4u * TR_BLK) + jl;
+        uint32_t word = 0;
+        if (!rev) {
+            const uint8_t* p = s_span + first + 3u * jl;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if (j0 + r < nk) {
-                const int c1 = p[3 * r], c2 = p[3 * r + 1], c3 = p[3 * r + 2];
-                const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[c1 * 16 + c2 * 4 + c3] : (uint32_t)'x';
-                word |= aa << (8 * r);
+            for (int r = 0; r < 4; r++) {
+                if (j0 + r < nk) {
+                    const int c1 = p[3 * r], c2 = p[3 * r + 1], c3 = p[3 * r + 2];
+                    const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[c1 * 16 + c2 * 4 + c3] : (uint32_t)'x';
+                    word |= aa << (8 * r);
+                }
+            }
+        } else {
+            const uint8_t* p = s_span + first - 3u * jl; // codon r: p[-3r], p[-3r-1], p[-3r-2]
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                if (j0 + r < nk) {
+                    const int c1 = *(p - 3 * r), c2 = *(p - 3 * r - 1), c3 = *(p - 3 * r - 2);
+                    const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[(3 - c1) * 16 + (3 - c2) * 4 + (3 - c3)] : (uint32_t)'x';
+                    word |= aa << (8 * r);
+                }
             }
         }
-    } else {
-        const uint8_t* p = s_span + s_first - 3u * jl; // codon r: p[-3r], p[-3r-1], p[-3r-2]
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if (j0 + r < nk) {
-                const int c1 = *(p - 3 * r), c2 = *(p - 3 * r - 1), c3 = *(p - 3 * r - 2);
-                const uint32_t aa = ((c1 | c2 | c3) < 4) ? (uint32_t)(uint8_t)s_code[(3 - c1) * 16 + (3 - c2) * 4 + (3 - c3)] : (uint32_t)'x';
-                word |= aa << (8 * r);
-            }
-        }
+        vseq_words[t] = word;
     }
-    vseq_words[t] = word;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1176,7 +1186,7 @@ int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches) {
     }
     CU(cudaMemsetAsync(b->vseq.as<uint8_t>() + b->vtotal, 0, 64, st)); // tail padding; every stream word is written below
     if (b->vtotal) {
-        k_translate<<<blocks_for(b->vtotal / 4, 256), 256, 0, st>>>(b->d_seq, b->d_off, b->n, b->voff.as<uint64_t>(), b->nv,
+        k_translate<<<blocks_for(b->vtotal / 4, TR_BLK * TR_PASSES), TR_BLK, 0, st>>>(b->d_seq, b->d_off, b->n, b->voff.as<uint64_t>(), b->nv,
                                                                    b->vtotal / 4, b->vseq.as<uint32_t>());
         (*launches)++;
     }
