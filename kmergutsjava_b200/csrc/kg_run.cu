@@ -1471,13 +1471,20 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     // about six slices per call, 24..96 MB of residues each (a slice costs ~0.4 ms of host-side API calls, so many
     // small slices would make the host the bottleneck; few large ones expose the first upload)
     uint64_t target = std::min<uint64_t>(std::max<uint64_t>(offsets[n] / 6, 24ull << 20), 96ull << 20);
-    if (mode == KG_MODE_DNA) target /= 2; // six translations: two residues per nucleotide
+    uint64_t ramp = 8;
+    if (mode == KG_MODE_DNA) {
+        // Long contigs: every slice pays ~1.5 ms of latency-bound tails (the longest segment in k_fsm_seg, the OTU fold
+        // of the largest contig), whatever its size, so few big slices win (configs[2]: 14 slices 32 ms, 3 slices 12 ms).
+        target = std::min<uint64_t>(std::max<uint64_t>(offsets[n] * 2 / 5, 32ull << 20), 128ull << 20);
+        ramp = 2;
+    }
     if (const char* e = getenv("KG_SLICE_MB")) target = (uint64_t)atoll(e) << 20;
     if (target < 65536) target = 65536;
     const uint64_t hard = mode == KG_MODE_AA ? KG_MAX_STREAM : KG_MAX_STREAM / 2 - 64 * (uint64_t)n; // dna: 2 residues per nucleotide
-    // the first slices are small (target/8, /4, /2): nothing can overlap the very first upload, so keep it short
+    // the first slices are small (target/ramp, doubling): nothing can overlap the very first upload, so keep it short
     std::vector<size_t> cut{0};
-    uint64_t step = std::max<uint64_t>(target / 8, std::min<uint64_t>(target, 2ull << 20));
+    if (const char* e = getenv("KG_SLICE_RAMP")) ramp = std::max(1, atoi(e));
+    uint64_t step = std::max<uint64_t>(target / ramp, std::min<uint64_t>(target, 2ull << 20));
     for (size_t i = 0; i < n;) {
         // last j with offsets[j] - offsets[i] <= step (binary search: a linear walk over a million offsets costs ~1 ms)
         size_t j = (size_t)(std::upper_bound(offsets + i, offsets + n + 1, offsets[i] + step) - offsets) - 1;

@@ -45,6 +45,22 @@ def main():
            "lookups": int(st.num_kmers), "hits": int(st.num_hits), "calls": int(st.num_calls),
            "stage_ms": {"prepare(translate)": round(st.ms_prepare, 3), "probe": round(st.ms_probe, 3), "group(fsm)": round(st.ms_group, 3),
                         "device": round(st.ms_device, 3)}}
+    # end to end through kg_run: pinned host buffers in, host records out (H2D + six-frame pipeline + D2H, sliced)
+    try:
+        import torch
+        h_seq = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
+        h_off = torch.empty(a.genomes + 1, dtype=torch.int64, pin_memory=True)
+        kg._check(kg.lib().kg_device_to_host(ctx._h, h_seq.data_ptr(), ds, total))
+        kg._check(kg.lib().kg_device_to_host(ctx._h, h_off.data_ptr(), do, 8 * (a.genomes + 1)))
+        for _ in range(3):
+            ctx.run_ptr(table, kg.MODE_DNA, h_seq.data_ptr(), h_off.data_ptr(), a.genomes, params).free()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            ctx.run_ptr(table, kg.MODE_DNA, h_seq.data_ptr(), h_off.data_ptr(), a.genomes, params).free()
+        edt = (time.perf_counter() - t0) / a.steps
+        out["e2e"] = {"ms_per_step": edt * 1e3, "mbp_per_s": total / edt / 1e6, "h2d_bytes_per_step": int(total + 8 * (a.genomes + 1))}
+    except ImportError:
+        pass
     if a.parity_genomes:
         from oracle import kgo
         from tests.parity import assert_same
