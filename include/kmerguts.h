@@ -14,6 +14,11 @@
  * from kg_last_error(); the library owns every buffer it returns until the
  * matching *_free; inputs are borrowed only for the duration of the call.
  * There is NO CPU fallback: without a CUDA device kg_init fails with KG_ENODEV.
+ *
+ * Threading (the reference path is single-threaded, KGJ has no Thread/executor): a
+ * context runs one call at a time -- it owns the streams, scratch and buffer pools --
+ * so a multi-threaded host uses one context per thread (and one per GPU).  A table
+ * handle is immutable after loading; kg_last_error() is thread-local.
  */
 #ifndef KMERGUTS_H
 #define KMERGUTS_H
@@ -96,8 +101,8 @@ typedef struct kg_table_info {
     int64_t num_unreachable;  /* occupied slots the reference could never return (dropped) */
     int64_t tail_run;         /* occupied slots at the very end of the file: probes into them can run off
                                  the end in the reference (EOFException, KGJ:799-802); 0 for well-formed tables */
-    int64_t num_buckets;      /* 32-byte buckets of the GPU layout */
-    int64_t flagged_buckets;  /* buckets whose overflow flag is set (a miss there costs a second sector) */
+    int64_t num_buckets;      /* 128-byte buckets (six keys + six payloads) of the GPU layout, incl. the spill tail */
+    int64_t flagged_buckets;  /* buckets whose overflow flag is set (a miss there costs a second line) */
     int64_t device_bytes;     /* HBM used by the table */
 } kg_table_info;
 
@@ -127,6 +132,11 @@ int kg_table_from_image(kg_context* ctx, const void* image, size_t nbytes, kg_ta
 /* From DEVICE arrays of n distinct keys (< 20^8) and 16-byte payloads {oI, avgFromEnd, fI, wt-bits}. */
 int kg_table_from_device_entries(kg_context* ctx, const uint64_t* d_keys, const void* d_payload16, size_t n,
                                  kg_table** table);
+/* Cache of the built GPU layout (bucket lines + prefilter): written once, read back at file speed instead of parsing --
+ * and, for .gz, inflating -- the reference-format file on every run (the reference re-streams it on every run,
+ * KGJ:944-1034).  kg_table_load_cached fails with KG_EFORMAT on a file of another build / layout; fall back to kg_table_load. */
+int kg_table_save(kg_context* ctx, const kg_table* table, const char* path);
+int kg_table_load_cached(kg_context* ctx, const char* path, kg_table** table);
 int kg_table_get_info(const kg_table* table, kg_table_info* info);
 void kg_table_free(kg_table* table);
 

@@ -417,13 +417,14 @@ static void usage() { // KGJ:618-635
     puts(" -t - (optional) temporary directory (system one is used by default)");
     puts(" -l - (optional) limit for input Kmer array (long, default = 20,000,000)");
     puts(" -G - (extension) CUDA device index (default 0)");
+    puts(" -C - (extension) cache file of the GPU table layout: read if present and valid, else written after loading -D");
 }
 
 extern "C" int kg_main(int argc, char** argv) {
     kg_params prm;
     kg_params_default(&prm);
     bool aa = false, debug = false;
-    const char *dir = nullptr, *query = nullptr, *outp = nullptr;
+    const char *dir = nullptr, *query = nullptr, *outp = nullptr, *cache = nullptr;
     int device = 0;
     std::string err;
     for (int i = 1; i < argc && err.empty(); i++) {
@@ -448,6 +449,7 @@ extern "C" int kg_main(int argc, char** argv) {
             // disk here, so they are accepted and ignored.
             case 't': case 'l': value(); break;
             case 'G': device = atoi(value()); break;
+            case 'C': cache = value(); break;
             default: err = "Unknown parameter: " + a;
         }
     }
@@ -476,7 +478,10 @@ extern "C" int kg_main(int argc, char** argv) {
         if (kg_init(device, &ctx) != KG_OK) break;
         if (kg_functions_load(dir, &fn) != KG_OK) break; // KGJ:759
         auto t0 = now();
-        if (kg_table_load(ctx, dir, &table) != KG_OK) break; // KGJ:774
+        if (!cache || kg_table_load_cached(ctx, cache, &table) != KG_OK) {
+            if (kg_table_load(ctx, dir, &table) != KG_OK) break; // KGJ:774
+            if (cache && kg_table_save(ctx, table, cache) != KG_OK) fprintf(stderr, "Warning: %s\n", kg_last_error());
+        }
         info("Table load time: " + std::to_string(ms(t0, now())) + " ms.");
         auto t1 = now();
         if (kg_fasta_read(query, &fa) != KG_OK) break; // KGJ:778

@@ -7,6 +7,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <stdarg.h>
+#include <stddef.h>
+#include <stdio.h>
 #include <string.h>
 #include <sys/stat.h>
 #include <zlib.h>
@@ -268,6 +270,27 @@ KgTableView kg_table::view() const {
 }
 
 // d_keys / d_payload: device arrays in the reference's SLOT order (so that of two equal keys the earlier slot wins).
+// Pin the prefilter in L2: a persisting carve-out (<= 79 MiB on B200) plus an access-policy window on the context's
+// stream, so that the 128-byte lines streaming through for the probes cannot push it out.  (One table per context
+// benefits; a later table takes the window over.)
+static void pin_filter(kg_context* ctx, const kg_table* t) {
+    if (!t->d_filter || !t->filter_words || getenv("KG_NO_L2_PERSIST")) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
+    const size_t fbytes = (size_t)t->filter_words * 8;
+    const size_t carve = std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    cudaStreamAttrValue av = {};
+    av.accessPolicyWindow.base_ptr = t->d_filter;
+    av.accessPolicyWindow.num_bytes = std::min<size_t>(fbytes, (size_t)prop.accessPolicyMaxWindowSize);
+    // a filter larger than the carve-out: that fraction of its lines persists, the rest competes normally
+    av.accessPolicyWindow.hitRatio = fbytes > carve ? (float)((double)carve / (double)fbytes) : 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = fbytes > carve ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaGetLastError();
+}
+
 static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* d_payload, size_t n, double load,
                            bool verify_payload, kg_table* t) {
     if (n >= (1ull << 32)) KG_FAIL(KG_ERANGE, "table: %zu signatures do not fit the 32-bit slot index", n);
@@ -348,26 +371,7 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
             CU(cudaMalloc(&t->d_filter, (size_t)t->filter_words * 8));
             CU(cudaMemsetAsync(t->d_filter, 0, (size_t)t->filter_words * 8, st));
             k_filter_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter, t->filter_words);
-            // Pin the filter in L2: a persisting carve-out (<= 79 MiB on B200) plus an access-policy window on the
-            // context's stream, so that the 128-byte lines streaming through for the probes cannot push it out.
-            // (One table per context benefits; a later table takes the window over.)
-            if (!getenv("KG_NO_L2_PERSIST")) {
-                cudaDeviceProp prop;
-                if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-                    const size_t fbytes = (size_t)t->filter_words * 8;
-                    const size_t carve = std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize);
-                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-                    cudaStreamAttrValue av = {};
-                    av.accessPolicyWindow.base_ptr = t->d_filter;
-                    av.accessPolicyWindow.num_bytes = std::min<size_t>(fbytes, (size_t)prop.accessPolicyMaxWindowSize);
-                    // a filter larger than the carve-out: that fraction of its lines persists, the rest competes normally
-                    av.accessPolicyWindow.hitRatio = fbytes > carve ? (float)((double)carve / (double)fbytes) : 1.0f;
-                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                    av.accessPolicyWindow.missProp = fbytes > carve ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
-                    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-                    cudaGetLastError();
-                }
-            }
+            pin_filter(ctx, t);
         }
         // Every stored key must be found again.  With repeated keys only the surviving copy's payload can match, so
         // the payload comparison is skipped for inputs that had duplicates.
@@ -595,6 +599,151 @@ extern "C" int kg_table_from_device_entries_sharded(kg_context* ctx, const uint6
     if (rc != KG_OK) return rc;
     t->shard_rank = rank;
     t->shard_count = nranks;
+    *table = t;
+    return KG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cache file of the GPU layout: parsing a 10-100 GB reference-format file -- and inflating it when it
+// is .gz -- dominates a short run; the built bucket lines + prefilter are written once and read back at file speed.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct CacheHeader {
+    char magic[8];           // "KGB200T\0"
+    uint32_t format;         // bumped whenever the bucket / filter layout or the hashes change
+    uint32_t bucket_keys, line_bytes, tail_buckets;
+    uint32_t num_buckets, filter_words;
+    int32_t shard_rank, shard_count;
+    kg_table_info info;
+    uint64_t lines_bytes, filter_bytes;
+    uint64_t check;          // kg_mix over the fields above (catches truncation / foreign files, not bit rot in the body)
+};
+constexpr uint32_t KG_CACHE_FORMAT = 1;
+uint64_t header_check(const CacheHeader& h) {
+    uint64_t x = 0x4B47423230305431ull;
+    const unsigned char* p = (const unsigned char*)&h;
+    for (size_t i = 0; i + 8 <= offsetof(CacheHeader, check); i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        x = kg_mix(x ^ w);
+    }
+    return x;
+}
+} // namespace
+
+extern "C" int kg_table_save(kg_context* ctx, const kg_table* t, const char* path) {
+    if (!ctx || !t || !path) KG_FAIL(KG_EINVAL, "kg_table_save: null argument");
+    CU(cudaSetDevice(ctx->device));
+    CacheHeader h = {};
+    memcpy(h.magic, "KGB200T", 8);
+    h.format = KG_CACHE_FORMAT;
+    h.bucket_keys = KG_BUCKET_KEYS;
+    h.line_bytes = 128;
+    h.tail_buckets = KG_TAIL_BUCKETS;
+    h.num_buckets = t->num_buckets;
+    h.filter_words = t->filter_words;
+    h.shard_rank = t->shard_rank;
+    h.shard_count = t->shard_count;
+    h.info = t->info;
+    h.lines_bytes = ((uint64_t)t->num_buckets + KG_TAIL_BUCKETS) * 128;
+    h.filter_bytes = (uint64_t)t->filter_words * 8;
+    h.check = header_check(h);
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) KG_FAIL(KG_EIO, "cannot write %s", tmp.c_str());
+    const size_t CH = 64u << 20;
+    void* stage = nullptr;
+    if (cudaMallocHost(&stage, CH) != cudaSuccess) {
+        fclose(f);
+        cudaGetLastError();
+        KG_FAIL(KG_ENOMEM, "kg_table_save: pinned staging buffer");
+    }
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    auto dump = [&](const void* dev, uint64_t bytes) {
+        for (uint64_t o = 0; ok && o < bytes; o += CH) {
+            const size_t n = (size_t)std::min<uint64_t>(CH, bytes - o);
+            ok = cudaMemcpy(stage, (const char*)dev + o, n, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(stage, 1, n, f) == n;
+        }
+    };
+    dump(t->d_lines, h.lines_bytes);
+    dump(t->d_filter, h.filter_bytes);
+    cudaFreeHost(stage);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        cudaGetLastError();
+        KG_FAIL(KG_EIO, "kg_table_save: writing %s failed", path);
+    }
+    return KG_OK;
+}
+
+extern "C" int kg_table_load_cached(kg_context* ctx, const char* path, kg_table** table) {
+    if (!ctx || !path || !table) KG_FAIL(KG_EINVAL, "kg_table_load_cached: null argument");
+    CU(cudaSetDevice(ctx->device));
+    FILE* f = fopen(path, "rb");
+    if (!f) KG_FAIL(KG_EIO, "cannot open %s", path);
+    CacheHeader h;
+    struct stat st;
+    bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "KGB200T", 8) == 0 && h.check == header_check(h);
+    if (ok && (h.format != KG_CACHE_FORMAT || h.bucket_keys != KG_BUCKET_KEYS || h.line_bytes != 128 || h.tail_buckets != KG_TAIL_BUCKETS))
+        ok = false; // written by a build with another layout: rebuild from the reference file
+    if (ok) ok = h.lines_bytes == ((uint64_t)h.num_buckets + KG_TAIL_BUCKETS) * 128 && h.filter_bytes == (uint64_t)h.filter_words * 8 &&
+                 fstat(fileno(f), &st) == 0 && (uint64_t)st.st_size == sizeof h + h.lines_bytes + h.filter_bytes;
+    if (!ok) {
+        fclose(f);
+        KG_FAIL(KG_EFORMAT, "%s is not a table cache of this build (bad magic, layout, checksum or size)", path);
+    }
+    kg_table* t = new kg_table();
+    t->ctx = ctx;
+    t->num_buckets = h.num_buckets;
+    t->filter_words = h.filter_words;
+    t->shard_rank = h.shard_rank;
+    t->shard_count = h.shard_count;
+    t->info = h.info;
+    const size_t CH = 64u << 20;
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = KG_OK;
+    do {
+        if (cudaMalloc(&t->d_lines, h.lines_bytes) != cudaSuccess || (h.filter_bytes && cudaMalloc(&t->d_filter, h.filter_bytes) != cudaSuccess) ||
+            cudaMallocHost(&stage[0], CH) != cudaSuccess || cudaMallocHost(&stage[1], CH) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            kg_set_error("kg_table_load_cached: allocation of %llu bytes failed", (unsigned long long)(h.lines_bytes + h.filter_bytes));
+            rc = KG_ENOMEM;
+            break;
+        }
+        int k = 0;
+        auto fill = [&](void* dev, uint64_t bytes) { // fread into one pinned buffer while the other one is in flight
+            for (uint64_t o = 0; rc == KG_OK && o < bytes; o += CH, k ^= 1) {
+                const size_t n = (size_t)std::min<uint64_t>(CH, bytes - o);
+                cudaEventSynchronize(ev[k]);
+                if (fread(stage[k], 1, n, f) != n) {
+                    kg_set_error("%s: short read", path);
+                    rc = KG_EIO;
+                    break;
+                }
+                cudaMemcpyAsync((char*)dev + o, stage[k], n, cudaMemcpyHostToDevice, ctx->stream);
+                cudaEventRecord(ev[k], ctx->stream);
+            }
+        };
+        fill(t->d_lines, h.lines_bytes);
+        fill(t->d_filter, h.filter_bytes);
+        if (rc == KG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            kg_set_error("kg_table_load_cached: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = KG_ECUDA;
+        }
+    } while (0);
+    fclose(f);
+    for (int i = 0; i < 2; i++) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (rc != KG_OK) {
+        kg_table_free(t);
+        return rc;
+    }
+    pin_filter(ctx, t);
     *table = t;
     return KG_OK;
 }

@@ -120,3 +120,26 @@ def test_c0_gz_table_and_duplicate_ids(kg, oracle, c0, tmp_path):
     a, b = _strip(open(o_out).read(), False), _strip(open(g_out).read(), False)
     assert a == b
     assert sum(1 for x in a if x.startswith("PROTEIN-ID")) == 5
+
+
+def test_c0_cli_table_cache(kg, oracle, c0, tmp_path):
+    """-C: the first run builds the table from -D and writes the cache, the second run reads the cache (the reference
+    table may be gone by then); both reports equal the oracle's."""
+    import shutil
+    d = tmp_path / "KmerData"
+    shutil.copytree(c0, d)
+    cache = str(tmp_path / "table.kgcache")
+    ids, descr, seqs = synth.read_fasta_simple(FAA)
+    q = str(tmp_path / "q.faa")
+    synth.write_fasta(q, ids[:300], seqs[:300])
+    o_out = str(tmp_path / "o.txt")
+    oracle.run_cli(["-a", "-D", str(d), "-q", q, "-o", o_out])
+    want = _strip(open(o_out).read(), False)
+    for attempt in range(2):
+        g_out = str(tmp_path / f"g{attempt}.txt")
+        r = subprocess.run([kg.CLI_PATH, "-a", "-D", str(d), "-C", cache, "-q", q, "-o", g_out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert _strip(open(g_out).read(), False) == want
+        assert os.path.getsize(cache) > 1 << 20
+        if attempt == 0:
+            os.remove(d / "kmer.table.mem_map")  # only the cache can serve the second run

@@ -318,3 +318,40 @@ def test_fsm_fuzz(kg, ctx, oracle, seed, monkeypatch):
             assert_same(res, ref, what=f"fuzz seed {seed} {fsm} {flags}")
             res.free()
     t.free()
+
+
+def test_table_cache_roundtrip(kg, ctx, oracle, universe, tmp_path):
+    """kg_table_save / kg_table_load_cached: the cached GPU layout answers exactly like the table it was saved from;
+    foreign, truncated or corrupted files are refused (KG_EFORMAT / KG_EIO), never half-loaded."""
+    u, img, nsig = universe
+    t = ctx.table_from_image(img)
+    path = str(tmp_path / "table.kgcache")
+    t.save(path)
+    c = ctx.load_table_cached(path)
+    for f in ("num_slots", "entry_size", "version", "num_signatures", "num_unreachable", "tail_run", "num_buckets", "flagged_buckets", "device_bytes"):
+        assert getattr(c.info, f) == getattr(t.info, f), f
+    sb, off = oracle.concat(u.proteins(400, seed=3))
+    p = kg.default_params(emit_hits=1)
+    a, b = ctx.run(t, kg.MODE_AA, sb, off, p), ctx.run(c, kg.MODE_AA, sb, off, p)
+    assert len(a.hits) > 1000
+    for name in ("hits", "calls", "otus"):
+        assert getattr(a, name).tobytes() == getattr(b, name).tobytes(), name
+    a.free()
+    b.free()
+    # a shard keeps its identity through the cache
+    s = ctx.table_from_image_sharded(img, 1, 3)
+    s.save(path + ".shard")
+    s2 = ctx.load_table_cached(path + ".shard")
+    with pytest.raises(kg.KgError, match="shard 1 of 3"):
+        ctx.run(s2, kg.MODE_AA, sb, off, p)
+    raw = open(path, "rb").read()
+    for bad in (raw[:len(raw) - 128], b"XXXXXXXX" + raw[8:], raw[:40] + bytes([raw[40] ^ 1]) + raw[41:], raw + b"\0" * 8, b""):
+        with open(path + ".bad", "wb") as f:
+            f.write(bad)
+        with pytest.raises(kg.KgError) as e:
+            ctx.load_table_cached(path + ".bad")
+        assert e.value.code in (-5, -4)
+    with pytest.raises(kg.KgError):
+        ctx.load_table_cached(path + ".missing")
+    for x in (t, c, s, s2):
+        x.free()
