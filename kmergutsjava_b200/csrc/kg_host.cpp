@@ -10,10 +10,12 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <charconv>
 #include <chrono>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -102,22 +104,14 @@ std::string_view jtrim(std::string_view s) {
 
 } // namespace
 
-// ---------------------------------------------------------------------------------------------------------------
-// readFasta, KGJ:1132-1192
-// ---------------------------------------------------------------------------------------------------------------
-extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
-    if (!path || !out) {
-        kg_set_error("kg_fasta_read: null argument");
-        return KG_EINVAL;
-    }
-    std::string text;
-    if (!read_all(path, text)) {
-        kg_set_error("cannot read %s", path);
-        return KG_EIO;
-    }
-    kg_fasta* fa = new kg_fasta();
-    fa->bytes.reserve(text.size());
-    Lines in{text};
+namespace {
+
+// The reference's reader (KGJ:1132-1192) over text[begin, end).  `begin` is 0 or the start of a caption line and `end` is
+// the start of a caption line or the end of the text, so that the state machine enters every range in the state the
+// sequential reader would be in.  Returns false with the reference's message in err.
+bool parse_fasta_range(std::string_view whole, size_t begin, size_t end, kg_fasta& fa, std::string& err, int* code) {
+    Lines in{whole.substr(0, end), begin};
+    fa.bytes.reserve(end - begin);
     std::string_view cur;
     bool have = in.next(cur); // str1
     for (;;) {
@@ -137,9 +131,9 @@ extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
                     got_caption = true;
                     break;
                 }
-                kg_set_error("Wrong caption line: %.*s", (int)std::min<size_t>(t.size(), 400), t.data()); // KGJ:1158
-                delete fa;
-                return KG_EFORMAT;
+                err = "Wrong caption line: " + std::string(t.substr(0, std::min<size_t>(t.size(), 400))); // KGJ:1158
+                *code = KG_EFORMAT;
+                return false;
             }
             have = in.next(cur);
         }
@@ -147,22 +141,123 @@ extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
         for (;;) {               // first non-blank line after the caption, KGJ:1167-1174
             have = in.next(cur);
             std::string_view t = have ? jtrim(cur) : std::string_view();
-            if (!have || (!t.empty() && t[0] == '>')) {
-                kg_set_error("No sequence for caption: %s", name.c_str()); // KGJ:1170
-                delete fa;
-                return KG_EFORMAT;
+            if (!have && end < whole.size()) t = std::string_view(">"); // the next range starts with a caption line
+            if ((!have && end >= whole.size()) || (!t.empty() && t[0] == '>')) {
+                err = "No sequence for caption: " + name; // KGJ:1170
+                *code = KG_EFORMAT;
+                return false;
             }
             if (!t.empty()) break;
         }
         for (;;) { // KGJ:1175-1180: lines are appended as they are, blanks and inner spaces included
-            fa->bytes.insert(fa->bytes.end(), cur.begin(), cur.end());
+            fa.bytes.insert(fa.bytes.end(), cur.begin(), cur.end());
             have = in.next(cur);
             if (!have) break;
             std::string_view t = jtrim(cur);
             if (!t.empty() && t[0] == '>') break;
         }
-        fa->ids.push_back(std::move(name));
-        fa->off.push_back(fa->bytes.size());
+        fa.ids.push_back(std::move(name));
+        fa.off.push_back(fa.bytes.size());
+    }
+    return true;
+}
+
+// start of the first line at or after `from` whose first character after leading blanks is '>' (a caption line in either
+// state of the reader), or text.size()
+size_t next_caption_line(std::string_view text, size_t from) {
+    size_t p = from;
+    if (p == 0) return 0;
+    for (;;) {
+        // move to the start of the next line: a line ends at \n, \r or \r\n
+        const char* b = text.data() + p;
+        const size_t left = text.size() - p;
+        const char* nl = (const char*)memchr(b, '\n', left);
+        size_t e = nl ? (size_t)(nl - b) : left;
+        if (const char* cr = (const char*)memchr(b, '\r', e)) e = (size_t)(cr - b);
+        p += e;
+        if (p >= text.size()) return text.size();
+        p += (text[p] == '\r' && p + 1 < text.size() && text[p + 1] == '\n') ? 2 : 1;
+        if (p >= text.size()) return text.size();
+        size_t q = p;
+        while (q < text.size() && (unsigned char)text[q] <= ' ' && text[q] != '\n' && text[q] != '\r') q++;
+        if (q < text.size() && text[q] == '>') return p;
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// readFasta, KGJ:1132-1192.  The text is cut at caption lines into one range per thread; a caption line puts the
+// reference's reader into the same state wherever it comes from, so the ranges parse independently and concatenate.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
+    if (!path || !out) {
+        kg_set_error("kg_fasta_read: null argument");
+        return KG_EINVAL;
+    }
+    std::string text;
+    if (!read_all(path, text)) {
+        kg_set_error("cannot read %s", path);
+        return KG_EIO;
+    }
+    size_t min_chunk = 4u << 20;
+    if (const char* e = getenv("KG_FASTA_CHUNK")) min_chunk = std::max<size_t>(1, (size_t)atoll(e)); // tests: many tiny ranges
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t want = std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, text.size() / min_chunk + 1});
+    std::vector<size_t> cut{0};
+    for (size_t k = 1; k < want; k++) {
+        size_t p = next_caption_line(text, std::max(cut.back() + 1, text.size() / want * k));
+        if (p >= text.size()) break;
+        if (p > cut.back()) cut.push_back(p);
+    }
+    cut.push_back(text.size());
+    const size_t parts = cut.size() - 1;
+    std::vector<kg_fasta> part(parts);
+    std::vector<std::string> errs(parts);
+    std::vector<int> codes(parts, KG_OK);
+    auto work = [&](size_t k) {
+        if (!parse_fasta_range(text, cut[k], cut[k + 1], part[k], errs[k], &codes[k]) && codes[k] == KG_OK) codes[k] = KG_EFORMAT;
+    };
+    if (parts == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t k = 1; k < parts; k++) th.emplace_back(work, k);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    for (size_t k = 0; k < parts; k++)
+        if (codes[k] != KG_OK) { // the first failing range holds the error the sequential reader would have met first
+            kg_set_error("%s", errs[k].c_str());
+            return codes[k];
+        }
+    kg_fasta* fa = new kg_fasta();
+    if (parts == 1) {
+        *fa = std::move(part[0]);
+    } else {
+        size_t nseq = 0, nbytes = 0;
+        std::vector<size_t> seq0(parts), byte0(parts);
+        for (size_t k = 0; k < parts; k++) {
+            seq0[k] = nseq;
+            byte0[k] = nbytes;
+            nseq += part[k].ids.size();
+            nbytes += part[k].bytes.size();
+        }
+        fa->ids.resize(nseq);
+        fa->bytes.resize(nbytes);
+        fa->off.resize(nseq + 1);
+        fa->off[0] = 0;
+        auto merge = [&](size_t k) {
+            if (!part[k].bytes.empty()) memcpy(fa->bytes.data() + byte0[k], part[k].bytes.data(), part[k].bytes.size());
+            for (size_t i = 0; i < part[k].ids.size(); i++) {
+                fa->ids[seq0[k] + i] = std::move(part[k].ids[i]);
+                fa->off[seq0[k] + i + 1] = byte0[k] + part[k].off[i + 1];
+            }
+        };
+        std::vector<std::thread> th;
+        for (size_t k = 1; k < parts; k++) th.emplace_back(merge, k);
+        merge(0);
+        for (auto& t : th) t.join();
     }
     *out = fa;
     return KG_OK;
@@ -333,67 +428,88 @@ extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_f
         if (!r.second) r.first->second.last = i;
     }
     const int per_seq = mode == KG_MODE_AA ? 1 : 6;
-    // Lines are assembled in a buffer and written a megabyte at a time (fprintf per line was the slowest part of a run).
-    std::string buf;
-    buf.reserve((1u << 20) + 4096);
-    auto put = [&](std::string_view t) { buf.append(t.data(), t.size()); };
-    auto num = [&](long long v) {
-        char tmp[24];
-        auto r = std::to_chars(tmp, tmp + sizeof tmp, v);
-        buf.append(tmp, (size_t)(r.ptr - tmp));
-    };
-    auto flush = [&](bool force) {
-        if (buf.size() >= (1u << 20) || (force && !buf.empty())) {
-            fwrite(buf.data(), 1, buf.size(), out);
-            buf.clear();
-        }
-    };
-    char wbuf[96];
-    for (size_t i = 0; i < n; i++) {
-        const std::string& ids = fa->ids[i];
-        const FirstLast& fl = occ.find(std::string_view(ids))->second;
-        if (fl.first != i) continue;
-        const size_t s = fl.last;
-        const long long len = (long long)(fa->off[s + 1] - fa->off[s]);
-        if (mode == KG_MODE_AA) { // KGJ:529
-            put("PROTEIN-ID\t"); put(ids); put("\t"); num(len); put("\n");
-        } else { // KGJ:541
-            put("processing "); put(ids); put("["); num(len); put("]\n");
-        }
-        size_t c = call_lo[s], h = hit_lo[s];
-        for (int k = 0; k < per_seq; k++) {
-            if (mode != KG_MODE_AA) { // KGJ:545-548
-                put("TRANSLATION\t"); put(ids); put("\t"); num(len); put(k < 3 ? "\t+\t" : "\t-\t"); num(k % 3); put("\n");
+    // Sequences are formatted in waves: every thread turns a contiguous block of sequences into text in its own buffer,
+    // then the buffers are written in order (fprintf per line was the slowest part of a run; one thread formats ~6 M lines/s).
+    auto format_range = [&](size_t i0, size_t i1, std::string& buf) {
+        auto put = [&](std::string_view t) { buf.append(t.data(), t.size()); };
+        auto num = [&](long long v) {
+            char tmp[24];
+            auto r = std::to_chars(tmp, tmp + sizeof tmp, v);
+            buf.append(tmp, (size_t)(r.ptr - tmp));
+        };
+        char wbuf[96];
+        for (size_t i = i0; i < i1; i++) {
+            const std::string& ids = fa->ids[i];
+            const FirstLast& fl = occ.find(std::string_view(ids))->second;
+            if (fl.first != i) continue;
+            const size_t s = fl.last;
+            const long long len = (long long)(fa->off[s + 1] - fa->off[s]);
+            if (mode == KG_MODE_AA) { // KGJ:529
+                put("PROTEIN-ID\t"); put(ids); put("\t"); num(len); put("\n");
+            } else { // KGJ:541
+                put("processing "); put(ids); put("["); num(len); put("]\n");
             }
-            int printed = 0;
-            auto flush_hits = [&](int upto) { // HIT lines precede the CALL they trigger (KGJ:472-475 before 477-508)
-                while (debug && h < hit_lo[s + 1] && hits[h].strand_frame == k && printed < upto) {
-                    kg_format_java_f(hits[h].function_wt, 3, wbuf, sizeof wbuf);
-                    put("HIT\t"); num(hits[h].pos); put("\t0\t"); num(hits[h].avg_off_from_end); put("\t"); num(hits[h].fI); put("\t");
-                    put(wbuf); put("\t"); num(hits[h].oI); put("\n");
-                    h++;
-                    printed++;
+            size_t c = call_lo[s], h = hit_lo[s];
+            for (int k = 0; k < per_seq; k++) {
+                if (mode != KG_MODE_AA) { // KGJ:545-548
+                    put("TRANSLATION\t"); put(ids); put("\t"); num(len); put(k < 3 ? "\t+\t" : "\t-\t"); num(k % 3); put("\n");
                 }
-            };
-            for (; c < call_lo[s + 1] && calls[c].strand_frame == k; c++) {
-                flush_hits(calls[c].hits_before);
-                const kg_call& cl = calls[c];
-                kg_format_java_f(cl.weighted, 6, wbuf, sizeof wbuf);
-                put("CALL\t"); num(cl.start); put("\t"); num(cl.end); put("\t"); num(cl.count); put("\t"); num(cl.fI); put("\t"); // KGJ:398-404
-                if (cl.fI >= 0 && (size_t)cl.fI < fn->names.size()) put(fn->names[(size_t)cl.fI]);
-                put("\t"); put(wbuf); put("\n");
+                int printed = 0;
+                auto flush_hits = [&](int upto) { // HIT lines precede the CALL they trigger (KGJ:472-475 before 477-508)
+                    while (debug && h < hit_lo[s + 1] && hits[h].strand_frame == k && printed < upto) {
+                        kg_format_java_f(hits[h].function_wt, 3, wbuf, sizeof wbuf);
+                        put("HIT\t"); num(hits[h].pos); put("\t0\t"); num(hits[h].avg_off_from_end); put("\t"); num(hits[h].fI); put("\t");
+                        put(wbuf); put("\t"); num(hits[h].oI); put("\n");
+                        h++;
+                        printed++;
+                    }
+                };
+                for (; c < call_lo[s + 1] && calls[c].strand_frame == k; c++) {
+                    flush_hits(calls[c].hits_before);
+                    const kg_call& cl = calls[c];
+                    kg_format_java_f(cl.weighted, 6, wbuf, sizeof wbuf);
+                    put("CALL\t"); num(cl.start); put("\t"); num(cl.end); put("\t"); num(cl.count); put("\t"); num(cl.fI); put("\t"); // KGJ:398-404
+                    if (cl.fI >= 0 && (size_t)cl.fI < fn->names.size()) put(fn->names[(size_t)cl.fI]);
+                    put("\t"); put(wbuf); put("\n");
+                }
+                flush_hits(0x7FFFFFFF);
             }
-            flush_hits(0x7FFFFFFF);
-            flush(false);
+            put("OTU-COUNTS\t"); put(ids); put("["); num(len); put("]"); // KGJ:518-522
+            for (int j = 0; j < otus[s].n; j++) {
+                put("\t"); num(otus[s].count[j]); put("-"); num(otus[s].oI[j]);
+            }
+            put("\n");
         }
-        put("OTU-COUNTS\t"); put(ids); put("["); num(len); put("]"); // KGJ:518-522
-        for (int j = 0; j < otus[s].n; j++) {
-            put("\t"); num(otus[s].count[j]); put("-"); num(otus[s].oI[j]);
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, n / 4096 + 1}));
+    // a block = about 1/8 of what a thread gets in total, bounded so that a wave's text stays in the tens of megabytes
+    const size_t block_cap = mode == KG_MODE_AA ? 65536 : 16; // a contig can carry 10^5 lines
+    const size_t block = std::max<size_t>(1, std::min<size_t>((n + nthreads * 8 - 1) / (nthreads * 8), block_cap));
+    std::vector<std::string> bufs(nthreads);
+    bool io_ok = true;
+    for (size_t w0 = 0; w0 < n && io_ok; w0 += block * nthreads) {
+        auto work = [&](size_t t) {
+            bufs[t].clear();
+            const size_t i0 = std::min(n, w0 + t * block), i1 = std::min(n, i0 + block);
+            if (i0 < i1) format_range(i0, i1, bufs[t]);
+        };
+        if (nthreads == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (size_t t = 1; t < nthreads; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto& t : th) t.join();
         }
-        put("\n");
-        flush(false);
+        for (size_t t = 0; t < nthreads && io_ok; t++)
+            if (!bufs[t].empty()) io_ok = fwrite(bufs[t].data(), 1, bufs[t].size(), out) == bufs[t].size();
     }
-    flush(true);
+    if (!io_ok) {
+        if (path) fclose(out);
+        kg_set_error("kg_report_write: write to %s failed", path ? path : "stdout");
+        return KG_EIO;
+    }
     if (path) fclose(out);
     else fflush(out);
     return KG_OK;

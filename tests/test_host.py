@@ -72,6 +72,70 @@ def test_fasta_matches_oracle_reader_on_ecoli(oracle):
     f.free()
 
 
+def _oracle_fasta(oracle, path):
+    """(ids, bytes, offsets) from the oracle's reader, or its error message."""
+    import ctypes as C
+    L = oracle.lib()
+    L.kgo_fasta_read.restype = C.c_void_p
+    L.kgo_fasta_read.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+
+    class KF(C.Structure):
+        _fields_ = [("n", C.c_size_t), ("id", C.POINTER(C.c_char_p)), ("seq", C.POINTER(C.c_uint8)), ("off", C.POINTER(C.c_uint64))]
+    err = C.create_string_buffer(512)
+    h = L.kgo_fasta_read(path.encode(), err, 512)
+    if not h:
+        return err.value.decode()
+    o = C.cast(h, C.POINTER(KF)).contents
+    off = np.ctypeslib.as_array(o.off, (o.n + 1,)).copy()
+    seq = np.ctypeslib.as_array(o.seq, (max(int(off[-1]), 1),))[: int(off[-1])].copy()
+    return [o.id[i].decode("latin1") for i in range(o.n)], seq, off
+
+
+def test_fasta_parallel_reader_fuzz(oracle, tmp_path, monkeypatch):
+    """The reader cuts the text at caption lines and parses the ranges on several threads (KG_FASTA_CHUNK forces many tiny
+    ranges here).  Whatever the text looks like -- blank lines, lines of blanks, leading blanks before '>', lone '>', \r and
+    \r\n line ends, captions without a sequence -- it must return exactly what the oracle's sequential reader returns,
+    including which error comes first."""
+    rng = np.random.default_rng(11)
+    caps = [b">id%d desc\n", b"  >sp%d\tx y\n", b">dup\n", b">id%d\r\n"]
+    seqs = [b"ACDEFGHIK\n", b"LMNP QRST \r\n", b"VWY\r", b"A\n", b"XX>notcaption\n", b"ACGT" * 30 + b"\n"]
+    blanks = [b" \n", b"\n", b"  \t \n", b">\n", b"\r\n"]
+    n_err = n_ok = 0
+    for trial in range(120):
+        parts = []
+        for r in range(int(rng.integers(1, 25))):
+            c = caps[int(rng.integers(0, len(caps)))]
+            parts.append(c % (100 * trial + r) if b"%d" in c else c)
+            while rng.random() < 0.3:
+                parts.append(blanks[int(rng.integers(0, len(blanks)))])
+            if rng.random() < 0.97:  # now and then a caption without a sequence: an error, and it must be the FIRST one reported
+                for _ in range(int(rng.integers(1, 5))):
+                    parts.append(seqs[int(rng.integers(0, len(seqs)))])
+                    if rng.random() < 0.2:
+                        parts.append(blanks[int(rng.integers(0, 3))])
+        body = b"".join(parts)
+        if trial % 10 == 0:
+            body = b"garbage before the first caption\n" + body
+        if trial % 7 == 0:
+            body = b"\n \nA\n" + body
+        path = _write(tmp_path, f"fz{trial}.fa", body)
+        want = _oracle_fasta(oracle, path)
+        for chunk in ("1", "37", "100000000"):
+            monkeypatch.setenv("KG_FASTA_CHUNK", chunk)
+            if isinstance(want, str):
+                with pytest.raises(kg.KgError) as e:
+                    kg.Fasta(path)
+                assert want in str(e.value), (trial, chunk, body)
+                n_err += 1
+            else:
+                f = kg.Fasta(path)
+                assert f.ids == want[0], (trial, chunk, body)
+                assert np.array_equal(f.offsets, want[2]) and bytes(f.bytes) == bytes(want[1]), (trial, chunk, body)
+                f.free()
+                n_ok += 1
+    assert n_err > 20 and n_ok > 60
+
+
 def test_function_index(tmp_path):
     import ctypes as C
     L = kg.lib()
