@@ -29,70 +29,51 @@ __device__ __forceinline__ void kg_otu_clear(KgOtuBuf& u) {
     for (int i = 0; i < KG_OI_BUFSZ; i++) u.c[i] = u.o[i] = 0;
 }
 
-// KGJ:415-437.  Fully unrolled so the five entries stay in registers.
-__device__ __forceinline__ void kg_otu_update(KgOtuBuf& u, int oI) {
-    int j = u.n;
-#pragma unroll
-    for (int i = KG_OI_BUFSZ - 1; i >= 0; i--)
-        if (i < u.n && u.o[i] == oI) j = i;
-    if (j == u.n) {
-        if (u.n == KG_OI_BUFSZ) j = KG_OI_BUFSZ - 1; // overwrite the last entry (KGJ:419-421)
-        else u.n++;
-#pragma unroll
-        for (int i = 0; i < KG_OI_BUFSZ; i++)
-            if (i == j) {
-                u.o[i] = oI;
-                u.c[i] = 1;
-            }
-    } else {
-#pragma unroll
-        for (int i = 0; i < KG_OI_BUFSZ; i++)
-            if (i == j) u.c[i]++;
-    }
-#pragma unroll
-    for (int i = KG_OI_BUFSZ - 1; i >= 1; i--) { // bubble toward the front while prev.count <= cur.count (KGJ:432-437)
-        if (i == j && u.c[i - 1] <= u.c[i]) {
-            int tc = u.c[i - 1], to = u.o[i - 1];
-            u.c[i - 1] = u.c[i];
-            u.o[i - 1] = u.o[i];
-            u.c[i] = tc;
-            u.o[i] = to;
-            j = i - 1;
-        }
-    }
-}
+__device__ __forceinline__ void kg_otu_update_n(KgOtuBuf& u, int oI, int m);
+// KGJ:415-437: one update.
+__device__ __forceinline__ void kg_otu_update(KgOtuBuf& u, int oI) { kg_otu_update_n(u, oI, 1); }
 
 // count += m for oI (m >= 1 consecutive updates of the same OTU index collapse exactly: the entry ends up in front of
-// the maximal block of entries ahead of it whose count is <= its final count, whether it got there in one step or m)
+// the maximal block of entries ahead of it whose count is <= its final count, whether it got there in one step or m).
+//
+// The list is always sorted by count, non-increasing: a new or overwritten entry starts at the end and bubbles past every
+// entry with a count <= its own (KGJ:432-437), and an incremented entry only ever moves forward.  So the bubbling has a
+// closed form -- the entry lands behind the entries ahead of it whose count is LARGER, the ones in between shift back by
+// one -- and the whole update is a handful of independent compares and selects instead of a chain of dependent swaps
+// (the OTU fold of a long contig is one such update after the other: its latency is what counts).
 __device__ __forceinline__ void kg_otu_update_n(KgOtuBuf& u, int oI, int m) {
-    int j = u.n;
+    unsigned eq = 0;
 #pragma unroll
-    for (int i = KG_OI_BUFSZ - 1; i >= 0; i--)
-        if (i < u.n && u.o[i] == oI) j = i;
-    if (j == u.n) {
-        if (u.n == KG_OI_BUFSZ) j = KG_OI_BUFSZ - 1;
-        else u.n++;
+    for (int i = 0; i < KG_OI_BUFSZ; i++) eq |= (unsigned)(i < u.n && u.o[i] == oI) << i;
+    int j, C;
+    if (eq) { // KGJ:415-418 found
+        j = __ffs(eq) - 1;
+        C = m;
 #pragma unroll
-        for (int i = 0; i < KG_OI_BUFSZ; i++)
-            if (i == j) {
-                u.o[i] = oI;
-                u.c[i] = m;
-            }
-    } else {
+        for (int i = 0; i < KG_OI_BUFSZ; i++) C += (i == j) ? u.c[i] : 0;
+    } else if (u.n == KG_OI_BUFSZ) { // overwrite the last entry (KGJ:419-421)
+        j = KG_OI_BUFSZ - 1;
+        C = m;
+    } else { // append (KGJ:422-426)
+        j = u.n;
+        u.n++;
+        C = m;
+    }
+    int p = 0; // entries ahead of j with a larger count stay in front (KGJ:432-437 stops at the first prev.count > cur.count)
 #pragma unroll
-        for (int i = 0; i < KG_OI_BUFSZ; i++)
-            if (i == j) u.c[i] += m;
+    for (int i = 0; i < KG_OI_BUFSZ - 1; i++) p += (i < j && u.c[i] > C);
+    int nc[KG_OI_BUFSZ], no[KG_OI_BUFSZ];
+#pragma unroll
+    for (int i = 0; i < KG_OI_BUFSZ; i++) {
+        const bool shifted = i > p && i <= j; // entries p..j-1 move back by one
+        const int pc = i > 0 ? u.c[i - 1] : 0, po = i > 0 ? u.o[i - 1] : 0;
+        nc[i] = i == p ? C : (shifted ? pc : u.c[i]);
+        no[i] = i == p ? oI : (shifted ? po : u.o[i]);
     }
 #pragma unroll
-    for (int i = KG_OI_BUFSZ - 1; i >= 1; i--) {
-        if (i == j && u.c[i - 1] <= u.c[i]) {
-            int tc = u.c[i - 1], to = u.o[i - 1];
-            u.c[i - 1] = u.c[i];
-            u.o[i - 1] = u.o[i];
-            u.c[i] = tc;
-            u.o[i] = to;
-            j = i - 1;
-        }
+    for (int i = 0; i < KG_OI_BUFSZ; i++) {
+        u.c[i] = nc[i];
+        u.o[i] = no[i];
     }
 }
 
