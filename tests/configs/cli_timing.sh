@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/cli_timing.sh -- where the wall-clock time of the command line goes on a FASTA of ~270k proteins (host parts vs GPU)
+# tests/configs/cli_timing.sh -- where the wall-clock time of the command line goes on a FASTA of ~270k proteins (host parts vs GPU)
 set -e
 D=/tmp/kg_cli_timing; mkdir -p $D
 python - <<PY

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/bench_dna.py -- configs[2]: 6-frame contig mode, N synthetic G-Mbp genomes against the 200M-signature table.
+"""tests/configs/config2_dna.py -- configs[2]: 6-frame contig mode, N synthetic G-Mbp genomes against the 200M-signature table.
 Not the driver's bench line (that is bench.py / configs[1]); prints one JSON line with stage times, Mbp/s, lookups/s and a
 bit-exact parity check of the first genomes against the CPU oracle."""
 import argparse
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tools import kg_synth as synth  # noqa: E402
 

@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""tools/bench_orfs.py -- configs[3]: a metagenome-scale batch of synthetic ORFs (default 1e8 proteins, ~3.2e10 residues)
+"""tests/configs/config3_orfs.py -- configs[3]: a metagenome-scale batch of synthetic ORFs (default 1e8 proteins, ~3.2e10 residues)
 sharded across the ranks with the signature table replicated.  Each rank generates its shard ON THE DEVICE, one million
 proteins at a time (the 30 GB of residues never cross PCIe), and runs every batch through the C ABI (`kg_batch_run`).  Not
 the driver's bench line; prints one JSON line on rank 0: proteins/s and lookups/s over the whole job (max over ranks), and a
 bit-exact parity check of deterministic samples (the first proteins of the shard and a random batch) against the CPU oracle.
 
-    python tools/bench_orfs.py --orfs 100000000
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_orfs.py --gpus 8
+    python tests/configs/config3_orfs.py --orfs 100000000
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tests/configs/config3_orfs.py --gpus 8
 """
 import argparse
 import json
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tools import kg_synth as synth  # noqa: E402
 

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""tools/bench_sharded.py -- configs[4]: hash-sharded signature table across N B200 (default: 10 M families, ~2 B
+"""tests/configs/config4_sharded.py -- configs[4]: hash-sharded signature table across N B200 (default: 10 M families, ~2 B
 signatures over 8 GPUs, 250 M per shard), 1 M synthetic proteins per rank, k-mers exchanged over NVLink (NCCL send/recv
 inside the C-ABI library; torch.distributed is only the launcher's plumbing: communicator id, barriers, reductions).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_sharded.py --gpus 8
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tests/configs/config4_sharded.py --gpus 8
 
 Not the driver's bench line.  Prints one JSON line on rank 0: whole-job lookups/s (max over ranks), the phase times of
 rank 0, interconnect bytes, and two full-size parity properties:
@@ -20,7 +20,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tools import kg_synth as synth  # noqa: E402
 
@@ -91,7 +91,7 @@ def main():
 
     def log(msg):
         if rank == 0:
-            print(f"[bench_sharded +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+            print(f"[config4 +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
     def barrier():
         torch.cuda.synchronize()
