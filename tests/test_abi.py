@@ -90,3 +90,11 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".java", "Makefile")):
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert "oracle" not in src.lower() or f == "__init__.py" and "oracle" not in src.replace("# oracle", ""), (dp, f)
+    # tools/ is neutral tooling: nothing there imports, runs or links the oracle either
+    for dp, _, files in os.walk(os.path.join(ROOT, "tools")):
+        for f in files:
+            if f.endswith((".py", ".sh", ".cu")):
+                src = open(os.path.join(dp, f), errors="replace").read()
+                assert not re.search(r"(from|import)\s+oracle|oracle/build|kgo\.", src), (dp, f)
+    so = subprocess.run(["ldd", kg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in so
