@@ -137,6 +137,10 @@ int kg_table_from_device_entries(kg_context* ctx, const uint64_t* d_keys, const 
  * KGJ:944-1034).  kg_table_load_cached fails with KG_EFORMAT on a file of another build / layout; fall back to kg_table_load. */
 int kg_table_save(kg_context* ctx, const kg_table* table, const char* path);
 int kg_table_load_cached(kg_context* ctx, const char* path, kg_table** table);
+/* A table may serve several contexts of ITS device (one context per host thread: two threads that alternate batches
+ * overlap one call's copies with the other's kernels).  Attach it to every additional context once, so that the
+ * context's stream keeps the table's prefilter resident in L2 as well. */
+int kg_table_attach(kg_context* ctx, const kg_table* table);
 int kg_table_get_info(const kg_table* table, kg_table_info* info);
 void kg_table_free(kg_table* table);
 

@@ -28,7 +28,7 @@ HIT_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("pos", "<i4"), ("oI", "<i4
 EXPORTS = [
     "kg_init", "kg_shutdown", "kg_last_error", "kg_version",
     "kg_table_load", "kg_table_load_file", "kg_table_from_image", "kg_table_from_device_entries", "kg_table_get_info",
-    "kg_table_save", "kg_table_load_cached", "kg_table_free", "kg_params_default", "kg_run", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
+    "kg_table_save", "kg_table_load_cached", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
     "kg_batch_run", "kg_result_fetch", "kg_result_stats", "kg_result_calls", "kg_result_otus", "kg_result_hits",
     "kg_result_free",
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
         "kg_table_load": (i32, [vp, C.c_char_p, pp]), "kg_table_load_file": (i32, [vp, C.c_char_p, pp]),
         "kg_table_from_image": (i32, [vp, vp, sz, pp]), "kg_table_from_device_entries": (i32, [vp, vp, vp, sz, pp]),
         "kg_table_get_info": (i32, [vp, C.POINTER(TableInfo)]), "kg_table_free": (None, [vp]),
+        "kg_table_attach": (i32, [vp, vp]),
         "kg_table_save": (i32, [vp, vp, C.c_char_p]), "kg_table_load_cached": (i32, [vp, C.c_char_p, pp]),
         "kg_params_default": (None, [C.POINTER(Params)]),
         "kg_run": (i32, [vp, vp, i32, vp, vp, sz, C.POINTER(Params), pp]),
@@ -333,6 +334,10 @@ class Table:
         ti = TableInfo()
         _check(lib().kg_table_get_info(self._h, C.byref(ti)))
         return ti
+
+    def attach(self, ctx: "Context"):
+        """Use this table from another context of the same device (one context per host thread)."""
+        _check(lib().kg_table_attach(ctx._h, self._h))
 
     def save(self, path: str):
         _check(lib().kg_table_save(self.ctx._h, self._h, path.encode()))

@@ -748,6 +748,14 @@ extern "C" int kg_table_load_cached(kg_context* ctx, const char* path, kg_table*
     return KG_OK;
 }
 
+extern "C" int kg_table_attach(kg_context* ctx, const kg_table* table) {
+    if (!ctx || !table) KG_FAIL(KG_EINVAL, "kg_table_attach: null argument");
+    if (ctx->device != table->ctx->device) KG_FAIL(KG_EINVAL, "kg_table_attach: the table lives on device %d, the context on device %d", table->ctx->device, ctx->device);
+    CU(cudaSetDevice(ctx->device));
+    pin_filter(ctx, table); // the persisting-L2 window is a per-stream attribute
+    return KG_OK;
+}
+
 extern "C" int kg_table_get_info(const kg_table* table, kg_table_info* info) {
     if (!table || !info) KG_FAIL(KG_EINVAL, "kg_table_get_info: null argument");
     *info = table->info;
