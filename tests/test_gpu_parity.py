@@ -355,3 +355,38 @@ def test_table_cache_roundtrip(kg, ctx, oracle, universe, tmp_path):
         ctx.load_table_cached(path + ".missing")
     for x in (t, c, s, s2):
         x.free()
+
+
+def test_two_contexts_share_a_table(kg, ctx, oracle, universe):
+    """One context per host thread (include/kmerguts.h, threading): a second context attaches to the table and both run
+    different batches at the same time; each result equals the oracle's."""
+    import threading
+    u, img, _ = universe
+    t = ctx.table_from_image(img)
+    ctx2 = kg.Context(0)
+    t.attach(ctx2)
+    otable = oracle.Table(data=img)
+    jobs = []
+    for k, c in enumerate((ctx, ctx2)):
+        sb, off = oracle.concat(u.proteins(3000, seed=50 + k))
+        jobs.append((c, sb, off))
+    out = [[None] * 4, [None] * 4]
+
+    def lane(k):
+        c, sb, off = jobs[k]
+        for rep in range(4):
+            out[k][rep] = c.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1))
+
+    th = [threading.Thread(target=lane, args=(k,)) for k in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for k in range(2):
+        _, sb, off = jobs[k]
+        ref = oracle.run(otable, oracle.make_params(aa=True), sb, off, oracle.DIRECT_PROBE)
+        for rep in range(4):
+            assert_same(out[k][rep], ref, what=f"context {k}, run {rep}")
+            out[k][rep].free()
+    ctx2.close()
+    t.free()
