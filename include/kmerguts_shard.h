@@ -6,7 +6,7 @@
  * exchange step each way stands where the reference's table stream stands:
  *
  *     route   : encode every valid 8-mer, bin it by owner                           (k_route)
- *     keys    : all-to-all of the binned keys                                       (NCCL send/recv, or peer copies)
+ *     keys    : all-to-all of the binned keys, 5 bytes each                         (NCCL send/recv, or peer copies)
  *     answer  : each owner probes the keys it received against its shard            (k_answer; same bucket layout,
  *                                                                                    prefilter and probe loop as k_probe)
  *     replies : all-to-all of {index of the query, 16-byte payload} for the HITS only
@@ -42,7 +42,11 @@ typedef struct kg_shard_stats {        /* of the last kg_batch_run_sharded on th
     uint64_t replies_sent;             /* hits found in this rank's shard */
     uint64_t replies_received;         /* hits of this rank's sequences */
     uint64_t bytes_sent;               /* over the interconnect (keys + replies, excluding the self segment) */
-    float ms_route, ms_keys, ms_answer, ms_replies, ms_merge, ms_total; /* CUDA events on the compute stream */
+    float ms_route, ms_keys, ms_answer, ms_replies, ms_merge, ms_total; /* CUDA events; ms_total: host clock around the call */
+    int32_t chunks;                    /* pieces the step was cut into (NCCL transport: the exchange of one piece overlaps
+                                          the kernels of the others).  1: ms_route .. ms_replies are phase durations;
+                                          > 1: the phases overlap and the four values are the times from the start of the
+                                          call to the END of that phase for the last piece.  ms_merge is always a duration */
 } kg_shard_stats;
 
 /* Rank (0 <= r < nranks) that owns an encoded 8-mer; table builders and loaders partition with it. */

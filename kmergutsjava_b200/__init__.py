@@ -68,7 +68,8 @@ class RunStats(C.Structure):
 class ShardStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("keys_sent", "keys_remote", "keys_received", "replies_sent", "replies_received",
                                           "bytes_sent")] + \
-               [(n, C.c_float) for n in ("ms_route", "ms_keys", "ms_answer", "ms_replies", "ms_merge", "ms_total")]
+               [(n, C.c_float) for n in ("ms_route", "ms_keys", "ms_answer", "ms_replies", "ms_merge", "ms_total")] + \
+               [("chunks", C.c_int32)]
 
 
 class UniverseStruct(C.Structure):

@@ -78,7 +78,7 @@ constexpr int SHARD_CNT_SLOTS = 2 * KG_MAX_RANKS; // [0, R): keys per owner; [KG
 // tile's entries are first sorted by owner in shared memory and then copied out run by run, so that every bin receives
 // one contiguous, coalesced burst per tile whatever the number of owners (scattered 4-byte stores made the kernel
 // 1.9x slower with eight bins than with two).
-__global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__ stream, uint32_t vtotal, uint32_t nranks, unsigned long long cap,
+__global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__ stream, uint32_t vtotal, uint32_t tile0, uint32_t nranks, unsigned long long cap,
                                                      uint32_t* __restrict__ send_lo, uint8_t* __restrict__ send_hi, uint32_t* __restrict__ send_pos,
                                                      unsigned long long* __restrict__ send_cnt) {
     __shared__ uint8_t lut[256];
@@ -92,7 +92,7 @@ __global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__
     for (int i = tid; i < 256; i += PROBE_BLK) lut[i] = (i >= 'A' && i <= 'Z') ? c_aa_code[i - 'A'] : 20;
     if (tid < KG_MAX_RANKS) cnt[tid] = 0;
     __syncthreads();
-    const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
+    const uint32_t p0 = (blockIdx.x + tile0) * (uint32_t)TILE + (uint32_t)tid * PT; // this launch routes tiles tile0, tile0 + 1, ...
     uint32_t q[PT + 4];
     uint32_t valid = 0;
     if (p0 < vtotal) valid = encode_windows(stream, p0, vtotal, lut, q);
@@ -304,23 +304,36 @@ struct KgLocalGroup {
     int alive = 0;
 };
 
-struct kg_comm {
-    kg_context* ctx = nullptr;
-    int rank = 0, nranks = 1;
-    ncclComm_t nccl = nullptr;
-    KgLocalGroup* group = nullptr;
-    // device scratch, grow-only
-    DevBuf send_lo, send_hi, send_pos, send_cnt, recv_lo, recv_hi, reply_idx, reply_payload, reply_cnt, rr_idx, rr_payload, bitmap, word_cnt, word_rank, matrix;
+// One chunk of a step: a contiguous range of the batch's tiles with its own bins, receive / reply buffers and counters.
+// A step over NCCL is cut into several chunks so that the exchange of one chunk overlaps the kernels of the others; the
+// other transports use a single chunk.
+constexpr int KG_MAX_CHUNKS = 4;
+struct ShardChunk {
+    DevBuf send_lo, send_hi, send_pos, send_cnt, recv_lo, recv_hi, reply_idx, reply_payload, reply_cnt, rr_idx, rr_payload, matrix;
     uint64_t* h = nullptr; // pinned: [0, 32) route counters, [32, 64) reply counters, [64, 64 + 32 * 16) gathered counters
-    cudaEvent_t ev[5] = {};
-    kg_shard_stats stats = {};
-    // state of the run in flight
+    cudaEvent_t ev_route = nullptr, ev_keys = nullptr, ev_answer = nullptr, ev_replies = nullptr;
+    uint32_t tile0 = 0, tile1 = 0; // tiles of the batch this chunk routes
     uint64_t cap = 0, cap_seen = 0, kmers = 0;
     uint64_t send_n[KG_MAX_RANKS] = {}, recv_n[KG_MAX_RANKS] = {}, recv_off[KG_MAX_RANKS + 1] = {};
     uint64_t reply_n[KG_MAX_RANKS] = {}, rr_n[KG_MAX_RANKS] = {};
 };
 
+struct kg_comm {
+    kg_context* ctx = nullptr;
+    int rank = 0, nranks = 1;
+    ncclComm_t nccl = nullptr;
+    KgLocalGroup* group = nullptr;
+    cudaStream_t comm_stream = nullptr; // NCCL transport: the exchanges run here, next to the kernels on the compute stream
+    ShardChunk ch[KG_MAX_CHUNKS];
+    int nchunks = 1;                    // of the run in flight
+    DevBuf bitmap, word_cnt, word_rank; // merge
+    cudaEvent_t ev_begin = nullptr;
+    kg_shard_stats stats = {};
+};
+
 namespace {
+
+constexpr int CAP_SLOT = KG_MAX_RANKS + 1; // counter block: [0, R) keys per owner, [KG_MAX_RANKS] valid windows, [CAP_SLOT] bin capacity
 
 int comm_alloc(kg_context* ctx, int rank, int nranks, kg_comm** out) {
     CU(cudaSetDevice(ctx->device));
@@ -328,136 +341,174 @@ int comm_alloc(kg_context* ctx, int rank, int nranks, kg_comm** out) {
     c->ctx = ctx;
     c->rank = rank;
     c->nranks = nranks;
-    if (cudaMallocHost(&c->h, (64 + SHARD_CNT_SLOTS * KG_MAX_RANKS) * sizeof(uint64_t)) != cudaSuccess) {
-        delete c;
-        KG_FAIL(KG_ENOMEM, "kg_comm: pinned counters");
+    bool ok = cudaEventCreate(&c->ev_begin) == cudaSuccess;
+    for (auto& k : c->ch) {
+        ok = ok && cudaMallocHost(&k.h, (64 + SHARD_CNT_SLOTS * KG_MAX_RANKS) * sizeof(uint64_t)) == cudaSuccess;
+        for (cudaEvent_t* e : {&k.ev_route, &k.ev_keys, &k.ev_answer, &k.ev_replies}) ok = ok && cudaEventCreate(e) == cudaSuccess;
     }
-    for (auto& e : c->ev) cudaEventCreate(&e);
+    if (!ok) {
+        cudaGetLastError();
+        kg_comm_free(c);
+        KG_FAIL(KG_ENOMEM, "kg_comm: events / pinned counters");
+    }
     *out = c;
     return KG_OK;
 }
 
-// ---- phase 1: encode + bin by owner; ends with the bin sizes on the host ----
-int shard_route(kg_comm* c, kg_batch* b) {
-    kg_context* ctx = c->ctx;
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+// ---- route: encode + bin by owner.  Enqueues only; the bin sizes are still on the device ----
+int shard_route(kg_comm* c, ShardChunk& k, kg_batch* b, cudaStream_t st) {
     const uint32_t R = (uint32_t)c->nranks;
-    c->stats = kg_shard_stats();
-    cudaEventRecord(c->ev[0], st);
-    uint32_t launches = 0;
-    KG_TRY(kg_batch_prepare(b, st, &launches));
     const uint64_t vtotal = b->vtotal;
-    const uint32_t ntiles = (uint32_t)((vtotal + TILE - 1) >> TILE_SHIFT);
-    // bins: an even split plus an eighth, or what an earlier run needed; exact on the second attempt
-    uint64_t cap = R == 1 ? vtotal : std::max<uint64_t>(vtotal / R + vtotal / (8 * R) + 4096, c->cap_seen);
-    cap = std::max<uint64_t>(std::min<uint64_t>(cap, std::max<uint64_t>(vtotal, 1)), 1);
-    KG_TRY(c->send_cnt.ensure(SHARD_CNT_SLOTS * 8));
+    const uint32_t ntiles = k.tile1 - k.tile0;
+    KG_TRY(k.send_cnt.ensure(SHARD_CNT_SLOTS * 8));
+    KG_TRY(k.send_lo.ensure(R * k.cap * 4));
+    KG_TRY(k.send_hi.ensure(R * k.cap));
+    KG_TRY(k.send_pos.ensure(R * k.cap * 4));
+    CU(cudaMemsetAsync(k.send_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
+    k.h[CAP_SLOT] = k.cap; // travels with the counters: every rank can see who overflowed
+    CU(cudaMemcpyAsync(k.send_cnt.as<unsigned long long>() + CAP_SLOT, &k.h[CAP_SLOT], 8, cudaMemcpyHostToDevice, st));
+    if (ntiles)
+        k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, k.tile0, R, k.cap, k.send_lo.as<uint32_t>(), k.send_hi.as<uint8_t>(),
+                                              k.send_pos.as<uint32_t>(), k.send_cnt.as<unsigned long long>());
+    cudaEventRecord(k.ev_route, st);
+    return KG_OK;
+}
+
+// first guess of a chunk's bin capacity: an even split plus an eighth, or what an earlier run needed
+uint64_t shard_cap_guess(const kg_comm* c, const ShardChunk& k) {
+    const uint64_t R = (uint64_t)c->nranks, positions = (uint64_t)(k.tile1 - k.tile0) * TILE;
+    uint64_t cap = R == 1 ? positions : std::max<uint64_t>(positions / R + positions / (8 * R) + 4096, k.cap_seen);
+    return std::max<uint64_t>(std::min<uint64_t>(cap, std::max<uint64_t>(positions, 1)), 1);
+}
+
+// host-synchronous transports: bring the bin sizes back, repeat the pass with the exact capacity if a bin overflowed
+int shard_route_sync(kg_comm* c, ShardChunk& k, kg_batch* b, cudaStream_t st) {
+    const uint32_t R = (uint32_t)c->nranks;
+    k.cap = shard_cap_guess(c, k);
     for (int attempt = 0;; attempt++) {
-        KG_TRY(c->send_lo.ensure(R * cap * 4));
-        KG_TRY(c->send_hi.ensure(R * cap));
-        KG_TRY(c->send_pos.ensure(R * cap * 4));
-        CU(cudaMemsetAsync(c->send_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
-        if (ntiles)
-            k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, R, cap, c->send_lo.as<uint32_t>(), c->send_hi.as<uint8_t>(),
-                                                  c->send_pos.as<uint32_t>(), c->send_cnt.as<unsigned long long>());
-        CU(cudaMemcpyAsync(c->h, c->send_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
+        KG_TRY(shard_route(c, k, b, st));
+        CU(cudaMemcpyAsync(k.h, k.send_cnt.p, (KG_MAX_RANKS + 1) * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         uint64_t mx = 0;
-        for (uint32_t r = 0; r < R; r++) mx = std::max(mx, c->h[r]);
-        if (mx <= cap) break;
-        if (attempt) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: bin overflow persisted at capacity %llu", (unsigned long long)cap);
-        cap = mx; // a skewed batch (e.g. low-complexity repeats all hashing to one owner)
+        for (uint32_t r = 0; r < R; r++) mx = std::max(mx, k.h[r]);
+        if (mx <= k.cap) break;
+        if (attempt) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: bin overflow persisted at capacity %llu", (unsigned long long)k.cap);
+        k.cap = mx; // a skewed batch (e.g. low-complexity repeats all hashing to one owner)
     }
-    c->cap = cap;
-    c->cap_seen = std::max(c->cap_seen, cap);
-    c->kmers = c->h[KG_MAX_RANKS];
-    for (uint32_t r = 0; r < R; r++) {
-        c->send_n[r] = c->h[r];
-        c->stats.keys_sent += c->send_n[r];
-        if ((int)r != c->rank) c->stats.keys_remote += c->send_n[r];
-    }
-    cudaEventRecord(c->ev[1], st);
     return KG_OK;
 }
 
-// every rank's counter block -> every rank (NCCL transport); returns the row of `from` in the pinned matrix
-int gather_counters(kg_comm* c, const DevBuf& mine) {
+void shard_take_counts(kg_comm* c, ShardChunk& k, const uint64_t* row) {
+    k.cap_seen = std::max(k.cap_seen, k.cap);
+    k.kmers = row[KG_MAX_RANKS];
+    for (int r = 0; r < c->nranks; r++) {
+        k.send_n[r] = row[r];
+        c->stats.keys_sent += k.send_n[r];
+        if (r != c->rank) c->stats.keys_remote += k.send_n[r];
+    }
+}
+
+// every rank's counter block -> every rank (NCCL transport), on the communication stream; ends host-synchronised
+int gather_counters(kg_comm* c, ShardChunk& k, const DevBuf& mine) {
     NcclApi& nc = nccl_api();
-    cudaStream_t st = c->ctx->stream;
-    KG_TRY(c->matrix.ensure((size_t)SHARD_CNT_SLOTS * 8 * c->nranks));
-    NC(nc.AllGather(mine.p, c->matrix.p, SHARD_CNT_SLOTS, ncclUint64, c->nccl, st));
-    CU(cudaMemcpyAsync(c->h + 64, c->matrix.p, (size_t)SHARD_CNT_SLOTS * 8 * c->nranks, cudaMemcpyDeviceToHost, st));
+    cudaStream_t st = c->comm_stream;
+    KG_TRY(k.matrix.ensure((size_t)SHARD_CNT_SLOTS * 8 * c->nranks));
+    NC(nc.AllGather(mine.p, k.matrix.p, SHARD_CNT_SLOTS, ncclUint64, c->nccl, st));
+    CU(cudaMemcpyAsync(k.h + 64, k.matrix.p, (size_t)SHARD_CNT_SLOTS * 8 * c->nranks, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
     return KG_OK;
 }
 
-// ---- keys: learn what arrives, make room, move the bins ----
-int shard_exchange_keys(kg_comm* c) {
+// ---- keys: learn what arrives, make room, move the bins.  `st` = the stream the exchange runs on ----
+int shard_exchange_keys(kg_comm* c, ShardChunk& k, int ci, kg_batch* b, cudaStream_t st) {
     kg_context* ctx = c->ctx;
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     const int R = c->nranks;
     if (c->nccl) {
-        KG_TRY(gather_counters(c, c->send_cnt));
-        for (int s = 0; s < R; s++) c->recv_n[s] = c->h[64 + (size_t)s * SHARD_CNT_SLOTS + c->rank];
-    } else if (c->group) {
-        for (int s = 0; s < R; s++) c->recv_n[s] = c->group->members[s]->send_n[c->rank];
+        // The gathered counters carry every rank's bin capacity, so all ranks agree on whether somebody overflowed; those
+        // ranks route the chunk again with the exact capacity and everybody gathers once more.
+        for (int attempt = 0;; attempt++) {
+            CU(cudaStreamWaitEvent(st, k.ev_route, 0));
+            KG_TRY(gather_counters(c, k, k.send_cnt));
+            bool any = false, mine = false;
+            for (int s = 0; s < R; s++) {
+                const uint64_t* row = k.h + 64 + (size_t)s * SHARD_CNT_SLOTS;
+                uint64_t mx = 0;
+                for (int d = 0; d < R; d++) mx = std::max(mx, row[d]);
+                if (mx > row[CAP_SLOT]) {
+                    any = true;
+                    if (s == c->rank) {
+                        mine = true;
+                        k.cap = mx;
+                    }
+                }
+            }
+            if (!any) break;
+            if (attempt) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: bin overflow persisted");
+            if (mine) KG_TRY(shard_route(c, k, b, ctx->stream));
+        }
+        shard_take_counts(c, k, k.h + 64 + (size_t)c->rank * SHARD_CNT_SLOTS);
+        for (int s = 0; s < R; s++) k.recv_n[s] = k.h[64 + (size_t)s * SHARD_CNT_SLOTS + c->rank];
     } else {
-        c->recv_n[0] = c->send_n[0];
+        shard_take_counts(c, k, k.h);
+        if (c->group) {
+            for (int s = 0; s < R; s++) k.recv_n[s] = c->group->members[s]->ch[ci].h[c->rank];
+        } else {
+            k.recv_n[0] = k.send_n[0];
+        }
     }
-    c->recv_off[0] = 0;
-    for (int s = 0; s < R; s++) c->recv_off[s + 1] = c->recv_off[s] + c->recv_n[s];
-    const uint64_t nrecv = c->recv_off[R];
-    c->stats.keys_received = nrecv;
-    KG_TRY(c->recv_lo.ensure(std::max<uint64_t>(nrecv, 1) * 4));
-    KG_TRY(c->recv_hi.ensure(std::max<uint64_t>(nrecv, 1)));
-    KG_TRY(c->reply_idx.ensure(std::max<uint64_t>(nrecv, 1) * 4));
-    KG_TRY(c->reply_payload.ensure(std::max<uint64_t>(nrecv, 1) * sizeof(int4)));
-    KG_TRY(c->reply_cnt.ensure(SHARD_CNT_SLOTS * 8));
-    uint32_t *sl = c->send_lo.as<uint32_t>(), *rl = c->recv_lo.as<uint32_t>();
-    uint8_t *sh = c->send_hi.as<uint8_t>(), *rh = c->recv_hi.as<uint8_t>();
+    k.recv_off[0] = 0;
+    for (int s = 0; s < R; s++) k.recv_off[s + 1] = k.recv_off[s] + k.recv_n[s];
+    const uint64_t nrecv = k.recv_off[R];
+    c->stats.keys_received += nrecv;
+    KG_TRY(k.recv_lo.ensure(std::max<uint64_t>(nrecv, 1) * 4));
+    KG_TRY(k.recv_hi.ensure(std::max<uint64_t>(nrecv, 1)));
+    KG_TRY(k.reply_idx.ensure(std::max<uint64_t>(nrecv, 1) * 4));
+    KG_TRY(k.reply_payload.ensure(std::max<uint64_t>(nrecv, 1) * sizeof(int4)));
+    KG_TRY(k.reply_cnt.ensure(SHARD_CNT_SLOTS * 8));
+    uint32_t *sl = k.send_lo.as<uint32_t>(), *rl = k.recv_lo.as<uint32_t>();
+    uint8_t *sh = k.send_hi.as<uint8_t>(), *rh = k.recv_hi.as<uint8_t>();
     if (c->nccl) {
         NcclApi& nc = nccl_api();
         NC(nc.GroupStart());
         for (int p = 0; p < R; p++) {
             if (p == c->rank) continue;
-            if (c->send_n[p]) {
-                NC(nc.Send(sl + p * c->cap, c->send_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Send(sh + p * c->cap, c->send_n[p], ncclUint8, p, c->nccl, st));
+            if (k.send_n[p]) {
+                NC(nc.Send(sl + p * k.cap, k.send_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Send(sh + p * k.cap, k.send_n[p], ncclUint8, p, c->nccl, st));
             }
-            if (c->recv_n[p]) {
-                NC(nc.Recv(rl + c->recv_off[p], c->recv_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Recv(rh + c->recv_off[p], c->recv_n[p], ncclUint8, p, c->nccl, st));
+            if (k.recv_n[p]) {
+                NC(nc.Recv(rl + k.recv_off[p], k.recv_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Recv(rh + k.recv_off[p], k.recv_n[p], ncclUint8, p, c->nccl, st));
             }
-            c->stats.bytes_sent += c->send_n[p] * 5;
+            c->stats.bytes_sent += k.send_n[p] * 5;
         }
         NC(nc.GroupEnd());
-        if (c->send_n[c->rank]) {
-            CU(cudaMemcpyAsync(rl + c->recv_off[c->rank], sl + c->rank * c->cap, c->send_n[c->rank] * 4, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(rh + c->recv_off[c->rank], sh + c->rank * c->cap, c->send_n[c->rank], cudaMemcpyDeviceToDevice, st));
+        if (k.send_n[c->rank]) {
+            CU(cudaMemcpyAsync(rl + k.recv_off[c->rank], sl + c->rank * k.cap, k.send_n[c->rank] * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(rh + k.recv_off[c->rank], sh + c->rank * k.cap, k.send_n[c->rank], cudaMemcpyDeviceToDevice, st));
         }
     } else if (c->group) { // every member has finished its route phase (host-synchronised): pull the bins
         for (int s = 0; s < R; s++) {
             kg_comm* src = c->group->members[s];
-            if (!c->recv_n[s]) continue;
-            CU(cudaMemcpyPeerAsync(rl + c->recv_off[s], ctx->device, src->send_lo.as<uint32_t>() + c->rank * src->cap, src->ctx->device, c->recv_n[s] * 4, st));
-            CU(cudaMemcpyPeerAsync(rh + c->recv_off[s], ctx->device, src->send_hi.as<uint8_t>() + c->rank * src->cap, src->ctx->device, c->recv_n[s], st));
-            if (s != c->rank) src->stats.bytes_sent += c->recv_n[s] * 5;
+            const ShardChunk& sk = src->ch[ci];
+            if (!k.recv_n[s]) continue;
+            CU(cudaMemcpyPeerAsync(rl + k.recv_off[s], ctx->device, sk.send_lo.as<uint32_t>() + c->rank * sk.cap, src->ctx->device, k.recv_n[s] * 4, st));
+            CU(cudaMemcpyPeerAsync(rh + k.recv_off[s], ctx->device, sk.send_hi.as<uint8_t>() + c->rank * sk.cap, src->ctx->device, k.recv_n[s], st));
+            if (s != c->rank) src->stats.bytes_sent += k.recv_n[s] * 5;
         }
     } else if (nrecv) {
         CU(cudaMemcpyAsync(rl, sl, nrecv * 4, cudaMemcpyDeviceToDevice, st));
         CU(cudaMemcpyAsync(rh, sh, nrecv, cudaMemcpyDeviceToDevice, st));
     }
-    cudaEventRecord(c->ev[2], st);
+    cudaEventRecord(k.ev_keys, st);
     return KG_OK;
 }
 
-// ---- phase 2: probe the received keys; ends with the reply counts on the host ----
-int shard_answer(kg_comm* c, const kg_table* table) {
+// ---- answer: probe the received keys (compute stream).  With `sync` the reply counts come back to the host ----
+int shard_answer(kg_comm* c, ShardChunk& k, const kg_table* table, bool sync) {
     kg_context* ctx = c->ctx;
-    CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int R = c->nranks;
     AnswerPlan plan = {};
@@ -465,102 +516,115 @@ int shard_answer(kg_comm* c, const kg_table* table) {
     uint64_t tiles = 0;
     for (int s = 0; s < R; s++) {
         plan.tile_first[s] = (uint32_t)tiles;
-        plan.seg_off[s] = c->recv_off[s];
-        tiles += (c->recv_n[s] + TILE - 1) >> TILE_SHIFT;
+        plan.seg_off[s] = k.recv_off[s];
+        tiles += (k.recv_n[s] + TILE - 1) >> TILE_SHIFT;
     }
     plan.tile_first[R] = (uint32_t)tiles;
-    plan.seg_off[R] = c->recv_off[R];
-    if (tiles > 0x7FFFFFFFull) KG_FAIL(KG_ERANGE, "kg_batch_run_sharded: %llu keys received in one step", (unsigned long long)c->recv_off[R]);
-    CU(cudaMemsetAsync(c->reply_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
+    plan.seg_off[R] = k.recv_off[R];
+    if (tiles > 0x7FFFFFFFull) KG_FAIL(KG_ERANGE, "kg_batch_run_sharded: %llu keys received in one step", (unsigned long long)k.recv_off[R]);
+    CU(cudaStreamWaitEvent(st, k.ev_keys, 0));
+    CU(cudaMemsetAsync(k.reply_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
     if (tiles)
-        k_answer<<<(unsigned)tiles, PROBE_BLK, PROBE_SMEM, st>>>(c->recv_lo.as<uint32_t>(), c->recv_hi.as<uint8_t>(), plan, table->view(), c->reply_idx.as<uint32_t>(),
-                                                                 c->reply_payload.as<int4>(), c->reply_cnt.as<unsigned long long>(), probe_flags());
-    cudaEventRecord(c->ev[3], st);
-    CU(cudaMemcpyAsync(c->h + 32, c->reply_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    for (int s = 0; s < R; s++) {
-        c->reply_n[s] = c->h[32 + s];
-        if (c->reply_n[s] > c->recv_n[s]) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: more replies than queries for rank %d", s);
-        c->stats.replies_sent += c->reply_n[s];
+        k_answer<<<(unsigned)tiles, PROBE_BLK, PROBE_SMEM, st>>>(k.recv_lo.as<uint32_t>(), k.recv_hi.as<uint8_t>(), plan, table->view(), k.reply_idx.as<uint32_t>(),
+                                                                 k.reply_payload.as<int4>(), k.reply_cnt.as<unsigned long long>(), probe_flags());
+    cudaEventRecord(k.ev_answer, st);
+    if (sync) {
+        CU(cudaMemcpyAsync(k.h + 32, k.reply_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
     }
     return KG_OK;
 }
 
 // ---- replies: back to the ranks that asked ----
-int shard_exchange_replies(kg_comm* c) {
+int shard_exchange_replies(kg_comm* c, ShardChunk& k, int ci, cudaStream_t st) {
     kg_context* ctx = c->ctx;
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     const int R = c->nranks;
     if (c->nccl) {
-        KG_TRY(gather_counters(c, c->reply_cnt));
-        for (int o = 0; o < R; o++) c->rr_n[o] = c->h[64 + (size_t)o * SHARD_CNT_SLOTS + c->rank];
-    } else if (c->group) {
-        for (int o = 0; o < R; o++) c->rr_n[o] = c->group->members[o]->reply_n[c->rank];
+        CU(cudaStreamWaitEvent(st, k.ev_answer, 0));
+        KG_TRY(gather_counters(c, k, k.reply_cnt));
+        for (int s = 0; s < R; s++) k.reply_n[s] = k.h[64 + (size_t)c->rank * SHARD_CNT_SLOTS + s];
+        for (int o = 0; o < R; o++) k.rr_n[o] = k.h[64 + (size_t)o * SHARD_CNT_SLOTS + c->rank];
     } else {
-        c->rr_n[0] = c->reply_n[0];
+        for (int s = 0; s < R; s++) k.reply_n[s] = k.h[32 + s];
+        if (c->group) {
+            for (int o = 0; o < R; o++) k.rr_n[o] = c->group->members[o]->ch[ci].h[32 + c->rank];
+        } else {
+            k.rr_n[0] = k.reply_n[0];
+        }
+    }
+    for (int s = 0; s < R; s++) {
+        if (k.reply_n[s] > k.recv_n[s]) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: more replies than queries for rank %d", s);
+        c->stats.replies_sent += k.reply_n[s];
     }
     for (int o = 0; o < R; o++) {
-        if (c->rr_n[o] > c->send_n[o]) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: rank %d answers %llu of %llu queries", o, (unsigned long long)c->rr_n[o], (unsigned long long)c->send_n[o]);
-        c->stats.replies_received += c->rr_n[o];
+        if (k.rr_n[o] > k.send_n[o]) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: rank %d answers %llu of %llu queries", o, (unsigned long long)k.rr_n[o], (unsigned long long)k.send_n[o]);
+        c->stats.replies_received += k.rr_n[o];
     }
-    KG_TRY(c->rr_idx.ensure((size_t)R * c->cap * 4));
-    KG_TRY(c->rr_payload.ensure((size_t)R * c->cap * sizeof(int4)));
-    uint32_t* ri = c->rr_idx.as<uint32_t>();
-    int4* rp = c->rr_payload.as<int4>();
+    KG_TRY(k.rr_idx.ensure((size_t)R * k.cap * 4));
+    KG_TRY(k.rr_payload.ensure((size_t)R * k.cap * sizeof(int4)));
+    uint32_t* ri = k.rr_idx.as<uint32_t>();
+    int4* rp = k.rr_payload.as<int4>();
     if (c->nccl) {
         NcclApi& nc = nccl_api();
         NC(nc.GroupStart());
         for (int p = 0; p < R; p++) {
             if (p == c->rank) continue;
-            if (c->reply_n[p]) {
-                NC(nc.Send(c->reply_idx.as<uint32_t>() + c->recv_off[p], c->reply_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Send(c->reply_payload.as<int4>() + c->recv_off[p], c->reply_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
-                c->stats.bytes_sent += c->reply_n[p] * (4 + sizeof(int4));
+            if (k.reply_n[p]) {
+                NC(nc.Send(k.reply_idx.as<uint32_t>() + k.recv_off[p], k.reply_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Send(k.reply_payload.as<int4>() + k.recv_off[p], k.reply_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
+                c->stats.bytes_sent += k.reply_n[p] * (4 + sizeof(int4));
             }
-            if (c->rr_n[p]) {
-                NC(nc.Recv(ri + p * c->cap, c->rr_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Recv(rp + p * c->cap, c->rr_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
+            if (k.rr_n[p]) {
+                NC(nc.Recv(ri + p * k.cap, k.rr_n[p], ncclUint32, p, c->nccl, st));
+                NC(nc.Recv(rp + p * k.cap, k.rr_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
             }
         }
         NC(nc.GroupEnd());
         const int me = c->rank;
-        if (c->reply_n[me]) {
-            CU(cudaMemcpyAsync(ri + me * c->cap, c->reply_idx.as<uint32_t>() + c->recv_off[me], c->reply_n[me] * 4, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(rp + me * c->cap, c->reply_payload.as<int4>() + c->recv_off[me], c->reply_n[me] * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+        if (k.reply_n[me]) {
+            CU(cudaMemcpyAsync(ri + me * k.cap, k.reply_idx.as<uint32_t>() + k.recv_off[me], k.reply_n[me] * 4, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(rp + me * k.cap, k.reply_payload.as<int4>() + k.recv_off[me], k.reply_n[me] * sizeof(int4), cudaMemcpyDeviceToDevice, st));
         }
     } else if (c->group) {
         for (int o = 0; o < R; o++) {
             kg_comm* src = c->group->members[o];
-            if (!c->rr_n[o]) continue;
-            CU(cudaMemcpyPeerAsync(ri + o * c->cap, ctx->device, src->reply_idx.as<uint32_t>() + src->recv_off[c->rank], src->ctx->device, c->rr_n[o] * 4, st));
-            CU(cudaMemcpyPeerAsync(rp + o * c->cap, ctx->device, src->reply_payload.as<int4>() + src->recv_off[c->rank], src->ctx->device,
-                                   c->rr_n[o] * sizeof(int4), st));
-            if (o != c->rank) src->stats.bytes_sent += c->rr_n[o] * (4 + sizeof(int4));
+            const ShardChunk& sk = src->ch[ci];
+            if (!k.rr_n[o]) continue;
+            CU(cudaMemcpyPeerAsync(ri + o * k.cap, ctx->device, sk.reply_idx.as<uint32_t>() + sk.recv_off[c->rank], src->ctx->device, k.rr_n[o] * 4, st));
+            CU(cudaMemcpyPeerAsync(rp + o * k.cap, ctx->device, sk.reply_payload.as<int4>() + sk.recv_off[c->rank], src->ctx->device,
+                                   k.rr_n[o] * sizeof(int4), st));
+            if (o != c->rank) src->stats.bytes_sent += k.rr_n[o] * (4 + sizeof(int4));
         }
-    } else if (c->rr_n[0]) {
-        CU(cudaMemcpyAsync(ri, c->reply_idx.p, c->rr_n[0] * 4, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(rp, c->reply_payload.p, c->rr_n[0] * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+    } else if (k.rr_n[0]) {
+        CU(cudaMemcpyAsync(ri, k.reply_idx.p, k.rr_n[0] * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(rp, k.reply_payload.p, k.rr_n[0] * sizeof(int4), cudaMemcpyDeviceToDevice, st));
     }
-    cudaEventRecord(c->ev[4], st);
+    cudaEventRecord(k.ev_replies, st);
     return KG_OK;
 }
 
-// ---- phase 3: replies -> per-tile hit chunks -> the unchanged rest of the pipeline ----
+// ---- merge: replies of all chunks -> per-tile hit chunks -> the unchanged rest of the pipeline ----
 int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result** out) {
     kg_context* ctx = c->ctx;
-    CU(cudaSetDevice(ctx->device));
-    const int R = c->nranks;
+    const int R = c->nranks, H = c->nchunks;
     const uint64_t vtotal = b->vtotal;
     const uint32_t ntiles = (uint32_t)((vtotal + TILE - 1) >> TILE_SHIFT);
-    ScatterPlan sp = {};
-    sp.nseg = (uint32_t)R;
-    for (int o = 0; o < R; o++) sp.first[o + 1] = sp.first[o] + c->rr_n[o];
-    const uint64_t nhits = sp.first[R];
-    uint64_t longest = 0;
-    for (int o = 0; o < R; o++) longest = std::max(longest, c->rr_n[o]);
-    const unsigned merge_grid = (unsigned)(blocks_for(longest, 256) * (uint64_t)R);
+    ScatterPlan sp[KG_MAX_CHUNKS] = {};
+    unsigned grid[KG_MAX_CHUNKS] = {};
+    uint64_t nhits = 0, kmers = 0;
+    for (int h = 0; h < H; h++) {
+        const ShardChunk& k = c->ch[h];
+        sp[h].nseg = (uint32_t)R;
+        uint64_t longest = 0;
+        for (int o = 0; o < R; o++) {
+            sp[h].first[o + 1] = sp[h].first[o] + k.rr_n[o];
+            longest = std::max(longest, k.rr_n[o]);
+        }
+        grid[h] = (unsigned)(blocks_for(longest, 256) * (uint64_t)R);
+        nhits += sp[h].first[R];
+        kmers += k.kmers;
+    }
     const uint32_t nwords = ntiles * (uint32_t)(TILE / 32);
     const size_t bitmap_bytes = ((size_t)nwords + 1) * 4;
     KG_TRY(c->bitmap.ensure(bitmap_bytes));
@@ -569,19 +633,25 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
     ProbeStage stage = [&](PipeSlot& sl, unsigned long long* d_ctr, uint64_t hit_cap, cudaStream_t st) -> int {
         if (!ntiles) return KG_OK;
         CU(cudaMemsetAsync(c->bitmap.p, 0, bitmap_bytes, st));
-        if (nhits)
-            k_mark_replies<<<merge_grid, 256, 0, st>>>(c->rr_idx.as<uint32_t>(), sp, c->cap, c->send_cnt.as<unsigned long long>(),
-                                                                  c->send_pos.as<uint32_t>(), c->bitmap.as<uint32_t>(), d_ctr);
+        for (int h = 0; h < H; h++) {
+            const ShardChunk& k = c->ch[h];
+            CU(cudaStreamWaitEvent(st, k.ev_replies, 0));
+            if (grid[h])
+                k_mark_replies<<<grid[h], 256, 0, st>>>(k.rr_idx.as<uint32_t>(), sp[h], k.cap, k.send_cnt.as<unsigned long long>(), k.send_pos.as<uint32_t>(),
+                                                        c->bitmap.as<uint32_t>(), d_ctr);
+        }
         k_word_popc<<<blocks_for((size_t)nwords + 1, 256), 256, 0, st>>>(c->bitmap.as<uint32_t>(), nwords, c->word_cnt.as<uint32_t>());
         KG_TRY(exclusive_sum_u32(ctx, c->word_cnt.as<uint32_t>(), c->word_rank.as<uint32_t>(), (size_t)nwords + 1, st));
-        if (nhits)
-            k_place_replies<<<merge_grid, 256, 0, st>>>(c->rr_idx.as<uint32_t>(), c->rr_payload.as<int4>(), sp, c->cap,
-                                                                   c->send_cnt.as<unsigned long long>(), c->send_pos.as<uint32_t>(),
-                                                                   c->bitmap.as<uint32_t>(), c->word_rank.as<uint32_t>(), (uint32_t)hit_cap,
-                                                                   sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>());
+        for (int h = 0; h < H; h++) {
+            const ShardChunk& k = c->ch[h];
+            if (grid[h])
+                k_place_replies<<<grid[h], 256, 0, st>>>(k.rr_idx.as<uint32_t>(), k.rr_payload.as<int4>(), sp[h], k.cap, k.send_cnt.as<unsigned long long>(),
+                                                         k.send_pos.as<uint32_t>(), c->bitmap.as<uint32_t>(), c->word_rank.as<uint32_t>(), (uint32_t)hit_cap,
+                                                         sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>());
+        }
         k_tile_meta<<<blocks_for(ntiles, 256), 256, 0, st>>>(c->word_rank.as<uint32_t>(), ntiles, (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
-                                                           sl.tile_cnt.as<uint32_t>(), d_ctr, c->kmers);
-        sl.launches += 3 + (nhits ? 2 : 0);
+                                                           sl.tile_cnt.as<uint32_t>(), d_ctr, kmers);
+        sl.launches += 3 + 2 * (uint32_t)H;
         return KG_OK;
     };
     kg_result* r = new kg_result();
@@ -598,13 +668,47 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
         kg_result_free(r);
         return rc;
     }
-    r->stats.num_launches += 2 + 1; // k_route, k_answer (+ patch/translate counted by prepare)
-    cudaEventElapsedTime(&c->stats.ms_route, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&c->stats.ms_keys, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&c->stats.ms_answer, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&c->stats.ms_replies, c->ev[3], c->ev[4]);
+    r->stats.num_launches += 2 * (uint32_t)H; // k_route, k_answer per chunk (patch / translate are counted by prepare)
+    // phase END times of the last chunk since the start of the call (with several chunks the phases overlap)
+    const ShardChunk& last = c->ch[H - 1];
+    float t_route = 0, t_keys = 0, t_answer = 0, t_replies = 0;
+    cudaEventElapsedTime(&t_route, c->ev_begin, last.ev_route);
+    cudaEventElapsedTime(&t_keys, c->ev_begin, last.ev_keys);
+    cudaEventElapsedTime(&t_answer, c->ev_begin, last.ev_answer);
+    cudaEventElapsedTime(&t_replies, c->ev_begin, last.ev_replies);
+    cudaGetLastError();
+    c->stats.chunks = H;
+    if (H == 1) { // one chunk: the phases run back to back, report their durations
+        c->stats.ms_route = t_route;
+        c->stats.ms_keys = t_keys - t_route;
+        c->stats.ms_answer = t_answer - t_keys;
+        c->stats.ms_replies = t_replies - t_answer;
+    } else {
+        c->stats.ms_route = t_route;
+        c->stats.ms_keys = t_keys;
+        c->stats.ms_answer = t_answer;
+        c->stats.ms_replies = t_replies;
+    }
     c->stats.ms_merge = r->stats.ms_device;
     *out = r;
+    return KG_OK;
+}
+
+// the chunks of a run: contiguous tile ranges of the prepared batch
+int shard_begin(kg_comm* c, kg_batch* b, int want_chunks) {
+    kg_context* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    c->stats = kg_shard_stats();
+    cudaEventRecord(c->ev_begin, ctx->stream);
+    uint32_t launches = 0;
+    KG_TRY(kg_batch_prepare(b, ctx->stream, &launches));
+    const uint32_t ntiles = (uint32_t)((b->vtotal + TILE - 1) >> TILE_SHIFT);
+    int H = std::max(1, std::min(want_chunks, KG_MAX_CHUNKS));
+    c->nchunks = H;
+    for (int h = 0; h < H; h++) {
+        c->ch[h].tile0 = (uint32_t)((uint64_t)ntiles * h / H);
+        c->ch[h].tile1 = (uint32_t)((uint64_t)ntiles * (h + 1) / H);
+    }
     return KG_OK;
 }
 
@@ -658,6 +762,13 @@ extern "C" int kg_comm_init(kg_context* ctx, int rank, int nranks, const uint8_t
             kg_comm_free(c);
             KG_FAIL(KG_ECUDA, "ncclCommInitRank failed: %s", nc.GetErrorString(e));
         }
+        int lo_p = 0, hi_p = 0; // the exchange kernels must not queue behind a grid of probe blocks that fills every SM
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        if (cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi_p) != cudaSuccess) {
+            cudaGetLastError();
+            kg_comm_free(c);
+            KG_FAIL(KG_ECUDA, "kg_comm_init: communication stream");
+        }
     }
     *comm = c;
     return KG_OK;
@@ -701,12 +812,17 @@ extern "C" void kg_comm_free(kg_comm* c) {
     cudaSetDevice(c->ctx->device);
     cudaDeviceSynchronize();
     if (c->nccl) nccl_api().CommDestroy(c->nccl);
-    for (DevBuf* d : {&c->send_lo, &c->send_hi, &c->send_pos, &c->send_cnt, &c->recv_lo, &c->recv_hi, &c->reply_idx, &c->reply_payload, &c->reply_cnt, &c->rr_idx,
-                      &c->rr_payload, &c->bitmap, &c->word_cnt, &c->word_rank, &c->matrix})
-        d->release();
-    if (c->h) cudaFreeHost(c->h);
-    for (auto& e : c->ev)
-        if (e) cudaEventDestroy(e);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    for (auto& k : c->ch) {
+        for (DevBuf* d : {&k.send_lo, &k.send_hi, &k.send_pos, &k.send_cnt, &k.recv_lo, &k.recv_hi, &k.reply_idx, &k.reply_payload, &k.reply_cnt,
+                          &k.rr_idx, &k.rr_payload, &k.matrix})
+            d->release();
+        if (k.h) cudaFreeHost(k.h);
+        for (cudaEvent_t e : {k.ev_route, k.ev_keys, k.ev_answer, k.ev_replies})
+            if (e) cudaEventDestroy(e);
+    }
+    for (DevBuf* d : {&c->bitmap, &c->word_cnt, &c->word_rank}) d->release();
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->group && --c->group->alive == 0) delete c->group;
     delete c;
 }
@@ -717,15 +833,46 @@ extern "C" int kg_comm_last_stats(const kg_comm* c, kg_shard_stats* s) {
     return KG_OK;
 }
 
+// Chunks of a step over NCCL (KG_SHARD_CHUNKS, default 4).  The number must not depend on the rank's own batch: every rank
+// has to issue the same sequence of collectives, whatever it holds itself (an empty chunk still takes part).
+static int shard_chunks_wanted(const kg_comm* c, const kg_batch*) {
+    if (!c->nccl) return 1;
+    int want = KG_MAX_CHUNKS;
+    if (const char* e = getenv("KG_SHARD_CHUNKS")) want = atoi(e);
+    return std::max(1, std::min(want, KG_MAX_CHUNKS));
+}
+
 extern "C" int kg_batch_run_sharded(kg_comm* c, const kg_table* shard, kg_batch* batch, const kg_params* params, kg_result** result) {
     if (!result) KG_FAIL(KG_EINVAL, "kg_batch_run_sharded: null argument");
     KG_TRY(shard_check(c, shard, batch, params));
     if (c->group && c->nranks > 1) KG_FAIL(KG_EINVAL, "kg_batch_run_sharded: local communicators run through kg_batch_run_sharded_local");
     const auto t0 = std::chrono::steady_clock::now();
-    KG_TRY(shard_route(c, batch));
-    KG_TRY(shard_exchange_keys(c));
-    KG_TRY(shard_answer(c, shard));
-    KG_TRY(shard_exchange_replies(c));
+    kg_context* ctx = c->ctx;
+    KG_TRY(shard_begin(c, batch, shard_chunks_wanted(c, batch)));
+    const int H = c->nchunks;
+    if (!c->nccl) { // a single rank: the whole path without an interconnect
+        ShardChunk& k = c->ch[0];
+        KG_TRY(shard_route_sync(c, k, batch, ctx->stream));
+        KG_TRY(shard_exchange_keys(c, k, 0, batch, ctx->stream));
+        KG_TRY(shard_answer(c, k, shard, true));
+        KG_TRY(shard_exchange_replies(c, k, 0, ctx->stream));
+    } else {
+        // Every rank issues the same sequence, so the collectives match up:
+        //   compute stream : route(0) .. route(H-1), answer(0), answer(1), ...
+        //   comm stream    : keys(0), keys(1), replies(0), keys(2), replies(1), ...
+        // The host only ever waits on the comm stream (for the counters that size the next send/recv), while the kernels
+        // queued on the compute stream keep the GPU busy: the exchange of a chunk overlaps the answer kernel of its neighbours.
+        for (int h = 0; h < H; h++) {
+            c->ch[h].cap = shard_cap_guess(c, c->ch[h]);
+            KG_TRY(shard_route(c, c->ch[h], batch, ctx->stream));
+        }
+        for (int h = 0; h < H; h++) {
+            KG_TRY(shard_exchange_keys(c, c->ch[h], h, batch, c->comm_stream));
+            KG_TRY(shard_answer(c, c->ch[h], shard, false));
+            if (h >= 1) KG_TRY(shard_exchange_replies(c, c->ch[h - 1], h - 1, c->comm_stream));
+        }
+        KG_TRY(shard_exchange_replies(c, c->ch[H - 1], H - 1, c->comm_stream));
+    }
     KG_TRY(shard_merge(c, shard, batch, params, result));
     c->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return KG_OK;
@@ -742,18 +889,25 @@ extern "C" int kg_batch_run_sharded_local(kg_comm* const* comms, const kg_table*
     }
     const auto t0 = std::chrono::steady_clock::now();
     int rc = KG_OK;
-    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_route(comms[r], batches[r]);
-    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_exchange_keys(comms[r]);
-    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_answer(comms[r], shards[r]);
-    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_exchange_replies(comms[r]);
-    for (int r = 0; r < nranks && rc == KG_OK; r++) { // the reply copies read the owners' buffers: finish them before anyone merges
-        cudaSetDevice(comms[r]->ctx->device);
+    auto each = [&](auto&& fn) {
+        for (int r = 0; r < nranks && rc == KG_OK; r++) {
+            cudaSetDevice(comms[r]->ctx->device);
+            rc = fn(r);
+        }
+    };
+    // every phase ends host-synchronised on every rank before the next one reads its neighbours' buffers
+    each([&](int r) { int e = shard_begin(comms[r], batches[r], 1); return e != KG_OK ? e : shard_route_sync(comms[r], comms[r]->ch[0], batches[r], comms[r]->ctx->stream); });
+    each([&](int r) { return shard_exchange_keys(comms[r], comms[r]->ch[0], 0, batches[r], comms[r]->ctx->stream); });
+    each([&](int r) { return shard_answer(comms[r], comms[r]->ch[0], shards[r], true); });
+    each([&](int r) { return shard_exchange_replies(comms[r], comms[r]->ch[0], 0, comms[r]->ctx->stream); });
+    each([&](int r) { // the reply copies read the owners' buffers: finish them before anyone merges
         if (cudaStreamSynchronize(comms[r]->ctx->stream) != cudaSuccess) {
             kg_set_error("kg_batch_run_sharded_local: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = KG_ECUDA;
+            return (int)KG_ECUDA;
         }
-    }
-    for (int r = 0; r < nranks && rc == KG_OK; r++) rc = shard_merge(comms[r], shards[r], batches[r], params, &results[r]);
+        return (int)KG_OK;
+    });
+    each([&](int r) { return shard_merge(comms[r], shards[r], batches[r], params, &results[r]); });
     if (rc != KG_OK) {
         for (int r = 0; r < nranks; r++) {
             kg_result_free(results[r]);

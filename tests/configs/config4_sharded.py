@@ -156,8 +156,11 @@ def main():
                                       [round(float(x), 3) for x in phases])),
            "interconnect_bytes_per_step": int(tot_sent / a.steps),
            "interconnect_GBps_per_gpu_during_exchange": None}
+    out["chunks"] = int(comm.stats.chunks)
+    if out["chunks"] > 1:
+        out["rank0_phase_ms_note"] = "the step runs in chunks whose exchanges overlap the kernels: route .. replies_exchange are END times since the start of the call"
     ex_ms = phases[1] + phases[3]
-    if world > 1 and ex_ms > 0:
+    if world > 1 and ex_ms > 0 and out["chunks"] == 1:
         out["interconnect_GBps_per_gpu_during_exchange"] = round(tot_sent / a.steps / world / (ex_ms * 1e-3) / 1e9, 1)
 
     if not a.no_check:

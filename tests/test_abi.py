@@ -63,7 +63,7 @@ def test_shard_owner_partitions_keys():
         assert own == [((mix(k ^ 0x5851F42D4C957F2D) >> 32) * R) >> 32 for k in keys]
         cnt = np.bincount(own, minlength=R)
         assert cnt.min() > 0.8 * len(keys) / R and cnt.max() < 1.2 * len(keys) / R
-    assert C.sizeof(kg.ShardStats) == 6 * 8 + 6 * 4
+    assert C.sizeof(kg.ShardStats) == 6 * 8 + 6 * 4 + 8  # + chunks, padded to 8
 
 
 def test_defaults_match_reference():
