@@ -868,8 +868,8 @@ struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them le
     DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
     DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
     DevBuf fk_a, fi_a;                                           // per-sequence path: class histogram / cursors, sequence permutation
-    DevBuf hit_v, seg_flag, seg_id, seg_begin, hit_flag, nseg;    // segment path
-    DevBuf o_oi, o_cidx, o_c01, o_prevc, o_crank, o_head, o_hrank, o_run_oi, o_run_crank; // segment path: OTU run-length encoding
+    DevBuf hit_v, seg_flag, seg_id, seg_begin, nseg;              // segment path
+    DevBuf o_oi, o_cidx, o_c01, o_crank, o_run_oi, o_run_crank;  // segment path: OTU runs (sparse oI / length, per-segment count, its scan, dense oI / length)
     bool seg = false;                                            // which FSM path the enqueued run uses
     uint64_t* h_ctr = nullptr; // pinned, KG_CTR_COUNT + 1 (the last slot receives the call total)
     cudaEvent_t ev[4] = {};    // begin, probe begin, probe end, end
@@ -1039,7 +1039,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
                           &sl.call_off, &sl.ctr, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
-                          &sl.hit_flag, &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_prevc, &sl.o_crank, &sl.o_head, &sl.o_hrank,
+                          &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_crank,
                           &sl.o_run_oi, &sl.o_run_crank})
             b->release();
         if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
