@@ -140,9 +140,9 @@ __global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__
         while (e >= first[o + 1]) o++;
         const unsigned long long slot = base[o] + (e - first[o]);
         if (slot < cap) { // a bin that overflows is only counted: the host repeats the pass with the exact capacity
-            send_lo[o * cap + slot] = st_lo[e];
-            send_hi[o * cap + slot] = st_hi[e];
-            send_pos[o * cap + slot] = st_pos[e];
+            __stcs(send_lo + o * cap + slot, st_lo[e]); // streamed: keep the L2 for the prefilter of the answer kernel
+            __stcs(send_hi + o * cap + slot, st_hi[e]);
+            __stcs(send_pos + o * cap + slot, st_pos[e]);
         }
     }
 }
@@ -184,7 +184,7 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32
     for (int i = 0; i < PT; i++) {
         key[i] = 0;
         if (k0 + i < n_s) {
-            key[i] = (uint64_t)klo[k0 + i] | ((uint64_t)khi[k0 + i] << 32);
+            key[i] = (uint64_t)__ldcs(klo + k0 + i) | ((uint64_t)__ldcs(khi + k0 + i) << 32); // read once: do not displace the prefilter
             valid |= 1u << i;
         }
     }
@@ -223,8 +223,8 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32
         while (m) {
             const int i = __ffs(m) - 1;
             m &= m - 1;
-            reply_idx[o] = (uint32_t)(k0 + i);
-            reply_payload[o] = pstage[tid * PT + i];
+            __stcs(reply_idx + o, (uint32_t)(k0 + i));
+            __stcs(reply_payload + o, pstage[tid * PT + i]);
             o++;
         }
     }
@@ -238,20 +238,32 @@ struct ScatterPlan {
     uint32_t nseg;
     unsigned long long first[KG_MAX_RANKS + 1];
 };
-// Merge, step 1: one bit per residue position that has a hit (the bitmap stays in L2: one bit per position).
-__global__ void k_mark_replies(const uint32_t* __restrict__ rr_idx, ScatterPlan plan, unsigned long long cap,
-                               const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
-                               uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ ctr) {
+// Merge, step 1: one bit per residue position that has a hit (the bitmap stays in L2: one bit per position).  Every
+// thread takes MERGE_U replies of one owner, a block apart, and issues their loads together: the kernels of the merge are
+// chains of dependent random accesses (reply -> bin slot -> position -> bitmap word) and live on memory-level parallelism.
+constexpr int MERGE_U = 4;
+__global__ __launch_bounds__(256) void k_mark_replies(const uint32_t* __restrict__ rr_idx, ScatterPlan plan, unsigned long long cap,
+                                                      const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
+                                                      uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ ctr) {
     const uint32_t o = blockIdx.x % plan.nseg; // owners interleaved block by block (see ScatterPlan)
-    const unsigned long long j = (unsigned long long)(blockIdx.x / plan.nseg) * blockDim.x + threadIdx.x;
-    if (j >= plan.first[o + 1] - plan.first[o]) return;
-    const uint32_t idx = rr_idx[o * cap + j];
-    if (idx >= send_cnt[o]) { // a reply that names no query of ours: the peer's answer is corrupt
-        ctr[KG_CTR_OVERFLOW] = 2ull;
-        return;
+    const unsigned long long n = plan.first[o + 1] - plan.first[o], j0 = (unsigned long long)(blockIdx.x / plan.nseg) * (256 * MERGE_U) + threadIdx.x;
+    const unsigned long long nsent = send_cnt[o];
+    uint32_t idx[MERGE_U], pos[MERGE_U];
+    bool on[MERGE_U];
+#pragma unroll
+    for (int u = 0; u < MERGE_U; u++) {
+        on[u] = j0 + 256ull * u < n;
+        idx[u] = on[u] ? __ldcs(rr_idx + o * cap + j0 + 256ull * u) : 0u;
+        if (on[u] && idx[u] >= nsent) { // a reply that names no query of ours: the peer's answer is corrupt
+            ctr[KG_CTR_OVERFLOW] = 2ull;
+            on[u] = false;
+        }
     }
-    const uint32_t pos = send_pos[o * cap + idx];
-    atomicOr(&bitmap[pos >> 5], 1u << (pos & 31));
+#pragma unroll
+    for (int u = 0; u < MERGE_U; u++) pos[u] = on[u] ? send_pos[o * cap + idx[u]] : 0u;
+#pragma unroll
+    for (int u = 0; u < MERGE_U; u++)
+        if (on[u]) atomicOr(&bitmap[pos[u] >> 5], 1u << (pos[u] & 31));
 }
 
 // step 2: hits per 32-position word (an exclusive scan of these gives every hit its rank in position order)
@@ -260,21 +272,42 @@ __global__ void k_word_popc(const uint32_t* __restrict__ bitmap, uint32_t nwords
     if (w <= nwords) cnt[w] = w < nwords ? __popc(bitmap[w]) : 0u;
 }
 
-// step 3: every reply goes straight to its final place in the position-ordered hit list
-__global__ void k_place_replies(const uint32_t* __restrict__ rr_idx, const int4* __restrict__ rr_payload, ScatterPlan plan, unsigned long long cap,
-                                const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
-                                const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank, uint32_t hit_cap,
-                                uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload) {
-    const uint32_t o = blockIdx.x % plan.nseg; // owners interleaved block by block (see ScatterPlan)
-    const unsigned long long j = (unsigned long long)(blockIdx.x / plan.nseg) * blockDim.x + threadIdx.x;
-    if (j >= plan.first[o + 1] - plan.first[o]) return;
-    const uint32_t idx = rr_idx[o * cap + j];
-    if (idx >= send_cnt[o]) return;
-    const uint32_t pos = send_pos[o * cap + idx];
-    const uint32_t slot = word_rank[pos >> 5] + __popc(bitmap[pos >> 5] & ((1u << (pos & 31)) - 1u));
-    if (slot < hit_cap) {
-        chunk_pos[slot] = pos;
-        chunk_payload[slot] = rr_payload[o * cap + j];
+// step 3: every reply goes straight to its final place in the position-ordered hit list.  (One reply per thread: four
+// per thread as in k_mark_replies measured 4.0 instead of 3.05 ms for 89 M replies.)
+constexpr int PLACE_U = 1;
+__global__ __launch_bounds__(256) void k_place_replies(const uint32_t* __restrict__ rr_idx, const int4* __restrict__ rr_payload, ScatterPlan plan,
+                                                       unsigned long long cap, const unsigned long long* __restrict__ send_cnt,
+                                                       const uint32_t* __restrict__ send_pos, const uint32_t* __restrict__ bitmap,
+                                                       const uint32_t* __restrict__ word_rank, uint32_t hit_cap, uint32_t* __restrict__ chunk_pos,
+                                                       int4* __restrict__ chunk_payload) {
+    const uint32_t o = blockIdx.x % plan.nseg;
+    const unsigned long long n = plan.first[o + 1] - plan.first[o], j0 = (unsigned long long)(blockIdx.x / plan.nseg) * (256 * PLACE_U) + threadIdx.x;
+    const unsigned long long nsent = send_cnt[o];
+    uint32_t idx[PLACE_U], pos[PLACE_U], bits[PLACE_U], rank[PLACE_U];
+    int4 pay[PLACE_U];
+    bool on[PLACE_U];
+#pragma unroll
+    for (int u = 0; u < PLACE_U; u++) {
+        on[u] = j0 + 256ull * u < n;
+        idx[u] = on[u] ? rr_idx[o * cap + j0 + 256ull * u] : 0u;
+        on[u] = on[u] && idx[u] < nsent;
+        if (on[u]) pay[u] = rr_payload[o * cap + j0 + 256ull * u];
+    }
+#pragma unroll
+    for (int u = 0; u < PLACE_U; u++) pos[u] = on[u] ? send_pos[o * cap + idx[u]] : 0u;
+#pragma unroll
+    for (int u = 0; u < PLACE_U; u++) {
+        bits[u] = on[u] ? bitmap[pos[u] >> 5] : 0u;
+        rank[u] = on[u] ? word_rank[pos[u] >> 5] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < PLACE_U; u++) {
+        if (!on[u]) continue;
+        const uint32_t slot = rank[u] + __popc(bits[u] & ((1u << (pos[u] & 31)) - 1u));
+        if (slot < hit_cap) {
+            chunk_pos[slot] = pos[u];
+            chunk_payload[slot] = pay[u];
+        }
     }
 }
 
@@ -611,7 +644,7 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
     const uint64_t vtotal = b->vtotal;
     const uint32_t ntiles = (uint32_t)((vtotal + TILE - 1) >> TILE_SHIFT);
     ScatterPlan sp[KG_MAX_CHUNKS] = {};
-    unsigned grid[KG_MAX_CHUNKS] = {};
+    unsigned grid[KG_MAX_CHUNKS] = {}, grid_place[KG_MAX_CHUNKS] = {};
     uint64_t nhits = 0, kmers = 0;
     for (int h = 0; h < H; h++) {
         const ShardChunk& k = c->ch[h];
@@ -621,7 +654,8 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
             sp[h].first[o + 1] = sp[h].first[o] + k.rr_n[o];
             longest = std::max(longest, k.rr_n[o]);
         }
-        grid[h] = (unsigned)(blocks_for(longest, 256) * (uint64_t)R);
+        grid[h] = (unsigned)(blocks_for(longest, 256 * MERGE_U) * (uint64_t)R);
+        grid_place[h] = (unsigned)(blocks_for(longest, 256 * PLACE_U) * (uint64_t)R);
         nhits += sp[h].first[R];
         kmers += k.kmers;
     }
@@ -644,8 +678,8 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
         KG_TRY(exclusive_sum_u32(ctx, c->word_cnt.as<uint32_t>(), c->word_rank.as<uint32_t>(), (size_t)nwords + 1, st));
         for (int h = 0; h < H; h++) {
             const ShardChunk& k = c->ch[h];
-            if (grid[h])
-                k_place_replies<<<grid[h], 256, 0, st>>>(k.rr_idx.as<uint32_t>(), k.rr_payload.as<int4>(), sp[h], k.cap, k.send_cnt.as<unsigned long long>(),
+            if (grid_place[h])
+                k_place_replies<<<grid_place[h], 256, 0, st>>>(k.rr_idx.as<uint32_t>(), k.rr_payload.as<int4>(), sp[h], k.cap, k.send_cnt.as<unsigned long long>(),
                                                          k.send_pos.as<uint32_t>(), c->bitmap.as<uint32_t>(), c->word_rank.as<uint32_t>(), (uint32_t)hit_cap,
                                                          sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>());
         }
