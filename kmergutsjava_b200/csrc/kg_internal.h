@@ -11,6 +11,7 @@ struct kg_table {
     uint32_t filter_words = 0;
     kg_table_info info = {};
     int shard_rank = 0, shard_count = 1; // hash-sharded table: this handle holds the keys kg_owner_of() gives shard_rank
+    mutable size_t l2_carve = 0;         // persisting-L2 set-aside the prefilter asked for (pin_filter)
     KgTableView view() const;
 };
 

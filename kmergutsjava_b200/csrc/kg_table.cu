@@ -280,6 +280,7 @@ static void pin_filter(kg_context* ctx, const kg_table* t) {
     const size_t fbytes = (size_t)t->filter_words * 8;
     const size_t carve = std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize);
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    t->l2_carve = carve;
     cudaStreamAttrValue av = {};
     av.accessPolicyWindow.base_ptr = t->d_filter;
     av.accessPolicyWindow.num_bytes = std::min<size_t>(fbytes, (size_t)prop.accessPolicyMaxWindowSize);
