@@ -72,7 +72,9 @@ struct KgTableView {
 // stream is (HBM bandwidth / 128 B) lookups/s.  About 85-90 % of all lookups are misses.  A blocked Bloom filter small
 // enough to stay in the 126 MB L2 answers most of them without touching DRAM: random sector reads that hit L2 run at
 // 2.9e11/s against 5.2e10/s from DRAM (tools/probe_bench).
-constexpr uint64_t KG_FILTER_MAX_BYTES = 76ull << 20; // the persisting-L2 carve-out tops out at 79 MiB on B200
+// The persisting-L2 carve-out tops out at 79 MiB on B200, but a filter that fills it leaves too little ordinary L2 for
+// everything else (and collides with itself): 64 MiB measured better than 76 on both the 2e8- and the 2.6e8-key tables.
+constexpr uint64_t KG_FILTER_MAX_BYTES = 64ull << 20;
 constexpr double KG_FILTER_BITS_PER_KEY = 3.0;
 
 __host__ __device__ __forceinline__ uint64_t kg_mix(uint64_t k) {
