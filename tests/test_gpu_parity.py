@@ -222,11 +222,10 @@ def test_fsm_kats_both_paths(kg, ctx, kat, fsm, monkeypatch):
     test_fsm_kats_on_gpu(kg, ctx, kat)
 
 
-@pytest.mark.parametrize("fsm", ["seg", "seg-warp", "seq"])
+@pytest.mark.parametrize("fsm", ["seg", "seq"])
 @pytest.mark.parametrize("flags", FLAGS)
 def test_parity_both_fsm_paths(kg, ctx, oracle, universe, flags, fsm, monkeypatch):
-    monkeypatch.setenv("KG_FSM", fsm.split("-")[0])
-    monkeypatch.setenv("KG_OTU", "warp" if fsm.endswith("warp") else "block")
+    monkeypatch.setenv("KG_FSM", fsm)
     u, img, _ = universe
     t = ctx.table_from_image(img)
     aa = u.proteins(300, seed=61) + [b"", b"ACDEFGHIK"]
@@ -262,11 +261,10 @@ def test_otu_replay_many_otus(kg, ctx, oracle, monkeypatch):
     sb, off = oracle.concat([prot, prot[100:2500], prot[::-1]])
     ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True), sb, off, oracle.DIRECT_PROBE)
     assert int(ref.otus["n"][0]) == 5 and len(ref.calls) >= 8
-    for fsm, otu in (("seg", "block"), ("seg", "warp"), ("seq", "warp")):
+    for fsm in ("seg", "seq"):
         monkeypatch.setenv("KG_FSM", fsm)
-        monkeypatch.setenv("KG_OTU", otu)
         res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1))
-        assert_same(res, ref, what=f"otu {fsm} {otu}")
+        assert_same(res, ref, what=f"otu {fsm}")
         res.free()
     t.free()
 
