@@ -18,6 +18,10 @@
  *
  * One process per GPU: kg_comm_init is collective (rank 0 makes an id with kg_comm_unique_id, the host application
  * hands it to every rank over whatever channel it has -- MPI, a file, a socket -- like ncclUniqueId).
+ * Environment: KG_SHARD_CHUNKS (1-4, default 4; must be the same on every rank) cuts a step into pieces whose exchanges
+ * overlap the kernels of the other pieces.  While a sharded step runs, the device's persisting-L2 set-aside is switched on
+ * for the answer phase only and restored when the call returns (it is a device-wide limit: another context probing a
+ * replicated table on the same GPU at that moment runs without it for a few milliseconds).
  * NCCL (libnccl.so.2) is loaded on first use and only when nranks > 1.  kg_comm_init_local puts all ranks into ONE
  * process (peer copies instead of NCCL): tests on a single GPU, or a single process that drives several devices.
  */
