@@ -308,7 +308,7 @@ def run_ours(args):
         otable = kgo.Table(borrow=img)
         log("image on host")
         t_img = time.time() - t0
-        nsample = args.cpu_sample or min(args.proteins, 16000 * threads)
+        nsample = args.cpu_sample or min(args.proteins, 64000 * threads)
         sb, off = sample_host(kg, ctx, ds, do, nsample)
         ref, secs = cpu_reference_run(kgo, otable, sb, off, threads)
         log(f"cpu baseline done in {secs:.1f}s")
