@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from tools import kg_synth as synth  # noqa: E402
+from tools import kg_benchlib as bl  # noqa: E402
 
 BYTES_PER_LOOKUP_AA = 33.0  # one 32-byte table sector + 1 residue byte
 
@@ -139,13 +140,13 @@ def build_inputs(kg, ctx, args, rank):
     """Synthetic universe -> GPU table + this rank's proteins (device resident)."""
     u = synth.Universe(n_families=args.families)
     t0 = time.time()
-    dk, dp, nsig = kg.synth_signatures(ctx, u, args.sigs)
+    dk, dp, nsig = bl.synth_signatures(ctx, u, args.sigs)
     t1 = time.time()
     log(f"signatures generated: {nsig}")
     table = ctx.table_from_device_entries(dk, dp, nsig)
     t2 = time.time()
     log("table built")
-    ds, do, total = kg.synth_proteins(ctx, u, rank * args.proteins, args.proteins, seed=1)
+    ds, do, total = bl.synth_proteins(ctx, u, rank * args.proteins, args.proteins, seed=1)
     t3 = time.time()
     log(f"proteins generated: {total} residues")
     timing = {"gen_signatures_s": round(t1 - t0, 2), "build_table_s": round(t2 - t1, 2), "gen_proteins_s": round(t3 - t2, 2)}
@@ -159,8 +160,8 @@ def cpu_reference_run(kgo, otable, sb, off, threads):
 
 
 def sample_host(kg, ctx, ds, do, nsample):
-    off = ctx.to_host(do, 8 * (nsample + 1)).view(np.uint64).copy()
-    sb = ctx.to_host(ds, int(off[-1]))
+    off = bl.to_host(ctx, do, 8 * (nsample + 1)).view(np.uint64).copy()
+    sb = bl.to_host(ctx, ds, int(off[-1]))
     return sb, off
 
 
@@ -204,8 +205,8 @@ def run_ours(args):
     if not args.no_e2e:
         h_seq = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
         h_off = torch.empty(args.proteins + 1, dtype=torch.int64, pin_memory=True)
-        kg._check(kg.lib().kg_device_to_host(ctx._h, h_seq.data_ptr(), ds, total))
-        kg._check(kg.lib().kg_device_to_host(ctx._h, h_off.data_ptr(), do, 8 * (args.proteins + 1)))
+        kg._check(bl.lib().kg_device_to_host(ctx._h, h_seq.data_ptr(), ds, total))
+        kg._check(bl.lib().kg_device_to_host(ctx._h, h_off.data_ptr(), do, 8 * (args.proteins + 1)))
         d2h = 0
         for _ in range(max(args.warmup, 3)):
             ctx.run_ptr(table, kg.MODE_AA, h_seq.data_ptr(), h_off.data_ptr(), args.proteins, params).free()
@@ -276,7 +277,7 @@ def run_ours(args):
     r_probe = 0.0
     if rank == 0:
         for tpb, infl in ((256, 4), (256, 8), (512, 4), (1024, 2), (128, 8)):
-            r_probe = max(r_probe, ctx.probe_roofline_table(table, 1 << 28, tpb, infl))
+            r_probe = max(r_probe, bl.probe_roofline_table(ctx, table, 1 << 28, tpb, infl))
     traffic, traffic_src = None, None
     try:    # dram__bytes_read.sum + dram__bytes_write.sum of k_probe from the committed `ncu --set full` capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
@@ -303,7 +304,7 @@ def run_ours(args):
         num_slots = 3 * nsig + 1  # load 1/3: at 1/2 the reference hash (key % numSigs) clusters so badly that no prime near 2n avoids running off the end
         t0 = time.time()
         log("roofline done; building the reference-format image for the CPU baseline")
-        img = kg.synth_reference_image(ctx, dk, dp, nsig, num_slots)
+        img = bl.synth_reference_image(ctx, dk, dp, nsig, num_slots)
         num_slots = int(img[:8].view(np.int64)[0])
         otable = kgo.Table(borrow=img)
         log("image on host")
@@ -330,10 +331,10 @@ def run_ours(args):
     # equal those of the naive one-thread-per-position kernel (no prefilter, no queue, byte-wise reads, full table lookup)
     full = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        valid, nh, chk = kg.naive_scan_aa(ctx, table, ds, do, args.proteins, total)
+        valid, nh, chk = bl.naive_scan_aa(ctx, table, ds, do, args.proteins, total)
         g = ctx.run_batch(table, batch, kg.default_params(emit_hits=1))
         gs = g.stats
-        ok = (gs.num_kmers, gs.num_hits) == (valid, nh) and kg.hits_checksum(ctx, g.hits, do) == chk
+        ok = (gs.num_kmers, gs.num_hits) == (valid, nh) and bl.hits_checksum(ctx, g.hits, do) == chk
         g.free()
         if not ok:
             raise SystemExit("full-size cross-check against the naive kernel FAILED")
@@ -355,13 +356,15 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity, "parity_full_size": full, "prep": prep,
             "stage_ms": {"prepare": round(st.ms_prepare, 4), "probe": round(st.ms_probe, 4), "group": round(st.ms_group, 4),
-                         "device_total": round(st.ms_device, 4)},
+                         "device_total": round(st.ms_device, 4), "probe_filter": round(st.ms_filter, 4),
+                         "probe_refilter": round(st.ms_refilter, 4), "probe_lines": round(st.ms_lines, 4),
+                         "survivors_filter1": int(st.num_survivors1), "survivors_filter2": int(st.num_survivors2)},
         }
         print(json.dumps(out))
     batch.free()
     table.free()
     for p in (dk, dp, ds, do):
-        kg.device_free(p)
+        bl.device_free(p)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -378,19 +381,19 @@ def run_reference(args):
     kgo.build()
     ctx = kg.Context(int(os.environ.get("LOCAL_RANK", "0")))
     u = synth.Universe(n_families=args.families)
-    dk, dp, nsig = kg.synth_signatures(ctx, u, args.sigs)
+    dk, dp, nsig = bl.synth_signatures(ctx, u, args.sigs)
     num_slots = 3 * nsig + 1  # load 1/3: at 1/2 the reference hash (key % numSigs) clusters so badly that no prime near 2n avoids running off the end
-    img = kg.synth_reference_image(ctx, dk, dp, nsig, num_slots)
+    img = bl.synth_reference_image(ctx, dk, dp, nsig, num_slots)
     num_slots = int(img[:8].view(np.int64)[0])
-    kg.device_free(dk)
-    kg.device_free(dp)
+    bl.device_free(dk)
+    bl.device_free(dp)
     otable = kgo.Table(borrow=img)
     threads = os.cpu_count() or 1
     nsample = args.cpu_sample or min(args.proteins, 16000 * threads)
-    ds, do, total = kg.synth_proteins(ctx, u, 0, nsample, seed=1)
+    ds, do, total = bl.synth_proteins(ctx, u, 0, nsample, seed=1)
     sb, off = sample_host(kg, ctx, ds, do, nsample)
-    kg.device_free(ds)
-    kg.device_free(do)
+    bl.device_free(ds)
+    bl.device_free(do)
     ctx.close()
     for _ in range(args.warmup):
         cpu_reference_run(kgo, otable, sb, off, threads)

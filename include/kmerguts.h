@@ -114,7 +114,10 @@ typedef struct kg_run_stats {
     uint64_t num_calls;
     uint32_t num_launches;    /* kernels of this library launched for the run */
     float ms_h2d, ms_device, ms_d2h; /* CUDA-event times of the last run (0 when not applicable) */
-    float ms_prepare, ms_probe, ms_group; /* inside ms_device: translate/patch, encode+probe kernel, gather+FSM */
+    float ms_prepare, ms_probe, ms_group; /* inside ms_device: translate/patch, encode+probe stage, gather+FSM */
+    float ms_filter, ms_refilter, ms_lines; /* inside ms_probe when the probe ran as the three-kernel cascade (else 0):
+                                               encode + first prefilter, second prefilter, bucket-line probe */
+    uint64_t num_survivors1, num_survivors2; /* cascade: lookups that passed the first / both prefilters (hits included) */
 } kg_run_stats;
 
 /* ---- context ---- */
@@ -137,6 +140,9 @@ int kg_table_from_device_entries(kg_context* ctx, const uint64_t* d_keys, const 
  * KGJ:944-1034).  kg_table_load_cached fails with KG_EFORMAT on a file of another build / layout; fall back to kg_table_load. */
 int kg_table_save(kg_context* ctx, const kg_table* table, const char* path);
 int kg_table_load_cached(kg_context* ctx, const char* path, kg_table** table);
+/* Same, but only if the cache was built from the kmer.table.mem_map[.gz] that data_dir holds NOW (its size and mtime are
+ * recorded in the cache header); KG_EFORMAT otherwise.  Both loaders verify a checksum over the whole body. */
+int kg_table_load_cached_checked(kg_context* ctx, const char* path, const char* data_dir, kg_table** table);
 /* A table may serve several contexts of ITS device (one context per host thread: two threads that alternate batches
  * overlap one call's copies with the other's kernels).  Attach it to every additional context once, so that the
  * context's stream keeps the table's prefilter resident in L2 as well. */

@@ -1,4 +1,4 @@
-"""kmergutsjava_b200 -- ctypes binding of libkmerguts_b200.so (include/kmerguts.h, kmerguts_host.h, kmerguts_synth.h).
+"""kmergutsjava_b200 -- ctypes binding of libkmerguts_b200.so (include/kmerguts.h, kmerguts_host.h, kmerguts_shard.h).
 
 The product is the CUDA library; this module only loads it and wraps handles in small Python classes so that the
 tests and bench.py read like the reference's own driver (KmerGutsJava.run: load table, feed sequences, print calls).
@@ -28,14 +28,12 @@ HIT_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("pos", "<i4"), ("oI", "<i4
 EXPORTS = [
     "kg_init", "kg_shutdown", "kg_last_error", "kg_version",
     "kg_table_load", "kg_table_load_file", "kg_table_from_image", "kg_table_from_device_entries", "kg_table_get_info",
-    "kg_table_save", "kg_table_load_cached", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
+    "kg_table_save", "kg_table_load_cached", "kg_table_load_cached_checked", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
     "kg_batch_run", "kg_result_fetch", "kg_result_stats", "kg_result_calls", "kg_result_otus", "kg_result_hits",
     "kg_result_free",
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
     "kg_functions_load", "kg_functions_read", "kg_functions_count", "kg_functions_name", "kg_functions_free",
     "kg_format_java_f", "kg_report_write", "kg_main",
-    "kg_synth_signatures", "kg_synth_signatures_sharded", "kg_synth_proteins", "kg_synth_genomes", "kg_synth_reference_image", "kg_synth_naive_scan_aa", "kg_synth_hits_checksum", "kg_device_free", "kg_device_to_host",
-    "kg_probe_roofline", "kg_probe_roofline_table",
     "kg_shard_owner", "kg_comm_unique_id", "kg_comm_init", "kg_comm_init_local", "kg_comm_free", "kg_comm_last_stats",
     "kg_table_load_sharded", "kg_table_from_image_sharded", "kg_table_from_device_entries_sharded",
     "kg_batch_run_sharded", "kg_batch_run_sharded_local",
@@ -62,7 +60,9 @@ class RunStats(C.Structure):
     _fields_ = [("num_sequences", C.c_uint64), ("num_positions", C.c_uint64), ("num_kmers", C.c_uint64),
                 ("num_hits", C.c_uint64), ("num_calls", C.c_uint64), ("num_launches", C.c_uint32),
                 ("ms_h2d", C.c_float), ("ms_device", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_prepare", C.c_float), ("ms_probe", C.c_float), ("ms_group", C.c_float)]
+                ("ms_prepare", C.c_float), ("ms_probe", C.c_float), ("ms_group", C.c_float),
+                ("ms_filter", C.c_float), ("ms_refilter", C.c_float), ("ms_lines", C.c_float),
+                ("num_survivors1", C.c_uint64), ("num_survivors2", C.c_uint64)]
 
 
 class ShardStats(C.Structure):
@@ -70,12 +70,6 @@ class ShardStats(C.Structure):
                                           "bytes_sent")] + \
                [(n, C.c_float) for n in ("ms_route", "ms_keys", "ms_answer", "ms_replies", "ms_merge", "ms_total")] + \
                [("chunks", C.c_int32)]
-
-
-class UniverseStruct(C.Structure):
-    _fields_ = [("n_families", C.c_uint64), ("seed", C.c_uint64), ("sig_keep_per_1024", C.c_uint32),
-                ("n_functions", C.c_uint32), ("n_otus", C.c_uint32), ("cdf16", C.c_uint32 * 20),
-                ("lenq", C.c_uint32 * 4096)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -100,6 +94,7 @@ def lib() -> C.CDLL:
         "kg_table_get_info": (i32, [vp, C.POINTER(TableInfo)]), "kg_table_free": (None, [vp]),
         "kg_table_attach": (i32, [vp, vp]),
         "kg_table_save": (i32, [vp, vp, C.c_char_p]), "kg_table_load_cached": (i32, [vp, C.c_char_p, pp]),
+        "kg_table_load_cached_checked": (i32, [vp, C.c_char_p, C.c_char_p, pp]),
         "kg_params_default": (None, [C.POINTER(Params)]),
         "kg_run": (i32, [vp, vp, i32, vp, vp, sz, C.POINTER(Params), pp]),
         "kg_batch_upload": (i32, [vp, i32, vp, vp, sz, pp]),
@@ -115,16 +110,6 @@ def lib() -> C.CDLL:
         "kg_format_java_f": (i32, [C.c_float, i32, C.c_char_p, sz]),
         "kg_report_write": (i32, [C.c_char_p, i32, i32, vp, vp, vp, vp]),
         "kg_main": (i32, [i32, C.POINTER(C.c_char_p)]),
-        "kg_synth_signatures": (i32, [vp, C.POINTER(UniverseStruct), u64, pp, pp, C.POINTER(u64)]),
-        "kg_synth_signatures_sharded": (i32, [vp, C.POINTER(UniverseStruct), u64, i32, i32, pp, pp, C.POINTER(u64)]),
-        "kg_synth_proteins": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
-        "kg_synth_genomes": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
-        "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, C.POINTER(u64), pp, C.POINTER(C.c_double)]),
-        "kg_synth_naive_scan_aa": (i32, [vp, vp, vp, vp, u64, u64, vp]),
-        "kg_synth_hits_checksum": (i32, [vp, vp, u64, vp, C.POINTER(u64)]),
-        "kg_device_free": (None, [vp]), "kg_device_to_host": (i32, [vp, vp, vp, u64]),
-        "kg_probe_roofline": (i32, [vp, u64, u64, i32, i32, C.POINTER(C.c_double)]),
-        "kg_probe_roofline_table": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_double)]),
         "kg_shard_owner": (i32, [u64, i32]), "kg_comm_unique_id": (i32, [vp]),
         "kg_comm_init": (i32, [vp, i32, i32, vp, pp]), "kg_comm_init_local": (i32, [pp, i32, pp]),
         "kg_comm_free": (None, [vp]), "kg_comm_last_stats": (i32, [vp, C.POINTER(ShardStats)]),
@@ -185,9 +170,13 @@ class Context:
         _check(lib().kg_table_load(self._h, data_dir.encode(), C.byref(h)))
         return Table(self, h)
 
-    def load_table_cached(self, path: str) -> "Table":
+    def load_table_cached(self, path: str, data_dir: Optional[str] = None) -> "Table":
+        """data_dir given: only if the cache was built from the kmer.table.mem_map[.gz] that directory holds now."""
         h = C.c_void_p()
-        _check(lib().kg_table_load_cached(self._h, path.encode(), C.byref(h)))
+        if data_dir is None:
+            _check(lib().kg_table_load_cached(self._h, path.encode(), C.byref(h)))
+        else:
+            _check(lib().kg_table_load_cached_checked(self._h, path.encode(), data_dir.encode(), C.byref(h)))
         return Table(self, h)
 
     def table_from_image(self, image: bytes) -> "Table":
@@ -249,22 +238,6 @@ class Context:
         h = C.c_void_p()
         _check(lib().kg_batch_run(self._h, table._h, batch._h, C.byref(params), C.byref(h)))
         return Result(h)
-
-    # -- tooling --
-    def probe_roofline(self, nbytes: int, n_loads: int, tpb: int = 256, inflight: int = 4) -> float:
-        out = C.c_double()
-        _check(lib().kg_probe_roofline(self._h, nbytes, n_loads, tpb, inflight, C.byref(out)))
-        return out.value
-
-    def probe_roofline_table(self, table: "Table", n_loads: int, tpb: int = 256, inflight: int = 4) -> float:
-        out = C.c_double()
-        _check(lib().kg_probe_roofline_table(self._h, table._h, n_loads, tpb, inflight, C.byref(out)))
-        return out.value
-
-    def to_host(self, d_ptr: int, nbytes: int) -> np.ndarray:
-        out = np.empty(nbytes, dtype=np.uint8)
-        _check(lib().kg_device_to_host(self._h, out.ctypes.data, d_ptr, nbytes))
-        return out
 
 
 def shard_owner(key: int, nranks: int) -> int:
@@ -421,74 +394,3 @@ class Fasta:
         if self._h:
             lib().kg_fasta_free(self._h)
             self._h = C.c_void_p()
-
-
-def make_universe(u) -> UniverseStruct:
-    """tools.kg_synth.Universe -> the C struct the CUDA generators take."""
-    s = UniverseStruct()
-    s.n_families, s.seed, s.sig_keep_per_1024 = u.n_families, u.seed, u.sig_keep_per_1024
-    s.n_functions, s.n_otus = u.n_functions, u.n_otus
-    for i, v in enumerate(u.cdf):
-        s.cdf16[i] = int(v)
-    for i, v in enumerate(u.lenq):
-        s.lenq[i] = int(v)
-    return s
-
-
-def synth_signatures(ctx: Context, u, max_sigs: int = 0):
-    dk, dp, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
-    us = make_universe(u)
-    _check(lib().kg_synth_signatures(ctx._h, C.byref(us), max_sigs, C.byref(dk), C.byref(dp), C.byref(n)))
-    return dk.value, dp.value, n.value
-
-
-def synth_signatures_sharded(ctx: Context, u, rank: int, nranks: int):
-    """The signatures of the universe that `rank` owns (device arrays); the union over ranks = synth_signatures(u, 0)."""
-    dk, dp, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
-    us = make_universe(u)
-    _check(lib().kg_synth_signatures_sharded(ctx._h, C.byref(us), 0, rank, nranks, C.byref(dk), C.byref(dp), C.byref(n)))
-    return dk.value, dp.value, n.value
-
-
-def synth_proteins(ctx: Context, u, first: int, n: int, seed: int):
-    ds, do, total = C.c_void_p(), C.c_void_p(), C.c_uint64()
-    us = make_universe(u)
-    _check(lib().kg_synth_proteins(ctx._h, C.byref(us), first, n, seed, C.byref(ds), C.byref(do), C.byref(total)))
-    return ds.value, do.value, total.value
-
-
-def synth_genomes(ctx: Context, u, n_genomes: int, length: int, seed: int):
-    ds, do, total = C.c_void_p(), C.c_void_p(), C.c_uint64()
-    us = make_universe(u)
-    _check(lib().kg_synth_genomes(ctx._h, C.byref(us), n_genomes, length, seed, C.byref(ds), C.byref(do), C.byref(total)))
-    return ds.value, do.value, total.value
-
-
-def synth_reference_image(ctx: Context, d_keys: int, d_payload: int, n: int, min_slots: int) -> np.ndarray:
-    """kmer.table.mem_map image written on the device (reference format, no wrap-around), copied to the host."""
-    ns, dimg, disp = C.c_uint64(), C.c_void_p(), C.c_double()
-    _check(lib().kg_synth_reference_image(ctx._h, d_keys, d_payload, n, min_slots, C.byref(ns), C.byref(dimg), C.byref(disp)))
-    synth_reference_image.mean_displacement = disp.value
-    try:
-        return ctx.to_host(dimg.value, 24 + 24 * ns.value)
-    finally:
-        device_free(dimg.value)
-
-
-def naive_scan_aa(ctx: Context, table: Table, d_seq: int, d_off: int, n: int, total: int):
-    """(valid windows, hits, checksum) by the naive one-thread-per-position kernel."""
-    out = (C.c_uint64 * 3)()
-    _check(lib().kg_synth_naive_scan_aa(ctx._h, table._h, d_seq, d_off, n, total, out))
-    return int(out[0]), int(out[1]), int(out[2])
-
-
-def hits_checksum(ctx: Context, hits: np.ndarray, d_off: int) -> int:
-    hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
-    out = C.c_uint64()
-    _check(lib().kg_synth_hits_checksum(ctx._h, hits.ctypes.data, len(hits), d_off, C.byref(out)))
-    return int(out.value)
-
-
-def device_free(ptr):
-    if ptr:
-        lib().kg_device_free(ptr)

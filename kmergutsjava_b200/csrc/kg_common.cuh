@@ -65,6 +65,10 @@ struct KgTableView {
     // L2-resident prefilter (kg_device.cuh): one 64-bit word per probe, two bits per key.  0 words = no filter.
     const unsigned long long* filter;
     uint32_t filter_words;
+    // second prefilter of the cascade (kg_run.cu: k_refilter), an independent hash of the same keys.  It takes its turn in
+    // L2 AFTER the first one: the two never have to be resident together.  0 words = no second stage.
+    const unsigned long long* filter2;
+    uint32_t filter2_words;
 };
 
 // On B200 an L2 miss always brings in the whole 128-byte line (ncu: ~124 B of DRAM reads per random 32-byte sector
@@ -92,13 +96,28 @@ __host__ __device__ __forceinline__ uint32_t kg_bucket_of_hash(uint64_t h, uint3
 __host__ __device__ __forceinline__ uint32_t kg_home_bucket(uint64_t key, uint32_t num_buckets) {
     return kg_bucket_of_hash(kg_mix(key), num_buckets);
 }
-// filter word and the two bits of a key, from the low half of the same hash (the bucket uses the high half)
-__host__ __device__ __forceinline__ uint32_t kg_filter_word(uint64_t h, uint32_t filter_words) {
-    return (uint32_t)(((h & 0xFFFFFFFFull) * (uint64_t)filter_words) >> 32);
+// Prefilter hashes.  The filter test runs once per LOOKUP (the bucket hash only once per survivor), and ncu showed the
+// encode + filter stage bound by instruction issue with murmur's two 64-bit multiplies per window (~125 instructions per
+// position), so the filters use ONE multiplicative hash each: m = key * odd constant (mod 2^64); the word comes from the
+// top 32 bits, the two bit positions from a second 32-bit multiply of bits 11..42.  On the synthetic universes this has
+// the same false-positive rate as the murmur mix (0.280 vs 0.279 at 2.68 bits/key; both stages together 0.078).
+__host__ __device__ __forceinline__ uint64_t kg_fhash1(uint64_t key) { return key * 0x9E3779B97F4A7C15ull; }
+__host__ __device__ __forceinline__ uint64_t kg_fhash2(uint64_t key) { return key * 0xC2B2AE3D27D4EB4Full; }
+__host__ __device__ __forceinline__ uint32_t kg_filter_word(uint64_t m, uint32_t filter_words) {
+    return (uint32_t)(((m >> 32) * (uint64_t)filter_words) >> 32);
 }
-__host__ __device__ __forceinline__ unsigned long long kg_filter_mask(uint64_t h) {
-    const uint64_t g = h * 0x9E3779B97F4A7C15ull;
-    return (1ull << (g >> 58)) | (1ull << ((g >> 52) & 63));
+__host__ __device__ __forceinline__ unsigned long long kg_filter_mask(uint64_t m) {
+    const uint32_t b = (uint32_t)(m >> 11) * 0x85EBCA77u;
+    return (1ull << (b >> 26)) | (1ull << ((b >> 20) & 63u));
+}
+// second-stage prefilter (the probe cascade, kg_run.cu): same construction on an independent multiplier, so that a false
+// positive of the first filter is an (almost) independent draw in the second
+__host__ __device__ __forceinline__ uint32_t kg_filter2_word(uint64_t m2, uint32_t filter2_words) {
+    return (uint32_t)(((m2 >> 32) * (uint64_t)filter2_words) >> 32);
+}
+__host__ __device__ __forceinline__ unsigned long long kg_filter2_mask(uint64_t m2) {
+    const uint32_t b = (uint32_t)(m2 >> 11) * 0x27D4EB2Fu;
+    return (1ull << (b >> 26)) | (1ull << ((b >> 20) & 63u));
 }
 
 // hash-sharded table (configs[4]): the rank that owns a key.  A second, independent mix: the bucket and the filter
@@ -133,6 +152,7 @@ struct kg_context {
     cudaStream_t copy_stream = nullptr; // H2D of the next slice in the pipelined end-to-end call (kg_run)
     cudaStream_t d2h_stream = nullptr;  // D2H of the previous slice's records
     cudaStream_t fsm_stream = nullptr;  // run FSM + call compaction of slice s while the compute stream probes slice s+1
+    cudaStream_t lines_stream = nullptr; // probe cascade run in parts: bucket-line stage of part p while the filters work on part p+1
     cudaEvent_t ev[12] = {};           // 0-5: run / fetch / upload brackets, 6-9: pipeline stages
     cudaEvent_t up_ev[4] = {};         // kg_run: slice s%4 has been uploaded
     cudaEvent_t d2h_ev[3] = {};        // kg_run: records of slice s%3 have reached the host
@@ -148,4 +168,4 @@ struct kg_context {
 };
 
 // counters written by the pipeline, one block of 8 x uint64 per run
-enum { KG_CTR_HITS = 0, KG_CTR_KMERS = 1, KG_CTR_CALLS = 2, KG_CTR_OVERFLOW = 3, KG_CTR_VPOS = 4, KG_CTR_COUNT = 8 }; // h_counters has KG_CTR_COUNT + 1 slots: the last receives the call total
+enum { KG_CTR_HITS = 0, KG_CTR_KMERS = 1, KG_CTR_CALLS = 2, KG_CTR_OVERFLOW = 3, KG_CTR_VPOS = 4, KG_CTR_CLAIM = 5 /* probe cascade: hit-chunk slots claimed = survivors of the second filter */, KG_CTR_SURV1 = 6 /* survivors of the first filter */, KG_CTR_COUNT = 8 }; // h_counters has KG_CTR_COUNT + 1 slots: the last receives the call total

@@ -53,6 +53,17 @@ __device__ __forceinline__ KgBucket kg_load_bucket_hint(const uint4* lines, uint
                  : "l"(p), "l"(policy));
     return r;
 }
+// Same, asking L2 to bring in the WHOLE 128-byte line (SASS LDG...LTC128B): the payload sectors are then L2 hits for the load
+// that follows a key match.
+__device__ __forceinline__ KgBucket kg_load_bucket_line(const uint4* lines, uint32_t b, uint64_t policy) {
+    KgBucket r;
+    const uint4* p = lines + (size_t)KG_LINE_UINT4 * b;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p), "l"(policy));
+    return r;
+}
 // payload of slot = bucket*6 + lane: same 128-byte line as the key sector
 __device__ __forceinline__ int4 kg_load_payload(const uint4* lines, uint32_t slot) {
     const uint32_t b = slot / KG_BUCKET_KEYS, lane = slot - b * KG_BUCKET_KEYS;

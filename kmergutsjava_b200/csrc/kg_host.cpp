@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -594,7 +595,18 @@ extern "C" int kg_main(int argc, char** argv) {
         if (kg_init(device, &ctx) != KG_OK) break;
         if (kg_functions_load(dir, &fn) != KG_OK) break; // KGJ:759
         auto t0 = now();
-        if (!cache || kg_table_load_cached(ctx, cache, &table) != KG_OK) {
+        // The cache is trusted only if it was built from the kmer.table.mem_map that is in -D now (size + mtime in its
+        // header) and its body checksum still holds; otherwise the table is rebuilt from the reference-format file.  A
+        // data directory that holds no table file at all (a deployment that ships only the cache) uses the cache as it is.
+        bool have = false;
+        if (cache) {
+            struct stat sst;
+            const std::string base = std::string(dir) + "/kmer.table.mem_map";
+            const bool source = stat((base + ".gz").c_str(), &sst) == 0 || stat(base.c_str(), &sst) == 0;
+            have = (source ? kg_table_load_cached_checked(ctx, cache, dir, &table) : kg_table_load_cached(ctx, cache, &table)) == KG_OK;
+            if (!have && access(cache, F_OK) == 0) fprintf(stderr, "Note: table cache not used: %s\n", kg_last_error());
+        }
+        if (!have) {
             if (kg_table_load(ctx, dir, &table) != KG_OK) break; // KGJ:774
             if (cache && kg_table_save(ctx, table, cache) != KG_OK) fprintf(stderr, "Warning: %s\n", kg_last_error());
         }

@@ -9,6 +9,9 @@ struct kg_table {
     uint32_t num_buckets = 0;
     unsigned long long* d_filter = nullptr;
     uint32_t filter_words = 0;
+    uint32_t filter2_words = 0;          // second-stage prefilter: stored right behind the first in d_filter
+    uint64_t src_size = 0;               // the reference-format file this table was parsed from (0 = not from a file):
+    int64_t src_mtime_ns = 0;            //   identity recorded in the cache file (kg_table_save)
     kg_table_info info = {};
     int shard_rank = 0, shard_count = 1; // hash-sharded table: this handle holds the keys kg_owner_of() gives shard_rank
     mutable size_t l2_carve = 0;         // persisting-L2 set-aside the prefilter asked for (pin_filter)
@@ -55,5 +58,8 @@ struct kg_result {
     bool fetched = false;
 };
 
+// kg_table.cu: persisting-L2 set-aside + stream window for the first prefilter (the fused probe / k_answer want it even for
+// tables whose default probe, the cascade, does not)
+void kg_table_pin_filter(kg_context* ctx, const kg_table* t);
 // kg_run.cu
 int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches);

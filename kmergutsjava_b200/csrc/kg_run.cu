@@ -327,7 +327,7 @@ __device__ __forceinline__ uint32_t filter_windows(const KgTableView& tab, const
     for (int i = 0; i < PT; i++) {
         fw[i] = 0;
         if ((valid >> i) & 1u) {
-            const uint64_t h = kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]);
+            const uint64_t h = kg_fhash1((uint64_t)q[i] * 160000ull + q[i + 4]);
             const uint32_t w = kg_filter_word(h, tab.filter_words);
             fw[i] = (flags & 2u) ? __ldg(tab.filter + w) : kg_load_filter_word(tab.filter, w, pol_keep);
         }
@@ -335,7 +335,7 @@ __device__ __forceinline__ uint32_t filter_windows(const KgTableView& tab, const
     uint32_t pass = 0;
 #pragma unroll
     for (int i = 0; i < PT; i++) {
-        const unsigned long long fm = kg_filter_mask(kg_mix((uint64_t)q[i] * 160000ull + q[i + 4]));
+        const unsigned long long fm = kg_filter_mask(kg_fhash1((uint64_t)q[i] * 160000ull + q[i + 4]));
         pass |= (uint32_t)((fw[i] & fm) == fm) << i;
     }
     return pass & valid;
@@ -460,6 +460,380 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe(const uint8_t
             chunk_payload[o] = pstage[tid * PT + i];
             o++;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// encode + probe as a CASCADE of three kernels (the default when the table carries a second prefilter).
+//
+// Why: the fused kernel above keeps one 64 MiB prefilter in L2 WHILE 15 GB of bucket lines stream through the same L2;
+// ncu (profiles/r01) shows 10 % of its filter loads missing L2 (4 GB of DRAM reads), 30 % false positives (9.5 GB of
+// bucket lines fetched for nothing) and more resident blocks evicting the filter.  L2 capacity bounds the bits per key
+// that can be resident AT ONE TIME -- so the stages take turns:
+//   k_filter    A  encode every window + first prefilter (L2-resident, nothing else competes)  -> survivors (key, local
+//                  position) of the tile, tile order, into the tile's own 8 KB slice of a global queue
+//   k_refilter  B  survivors re-tested against a SECOND, independently hashed prefilter that now has the L2 to itself;
+//                  compacted in place, order kept.  Two 2.7-bit filters in sequence: false positives 0.30 -> ~0.09
+//   k_probe2    C  what is left (hits + ~9 % of the misses) fetches its 128-byte bucket line: pure DRAM streaming of
+//                  random lines, no filter to protect, so occupancy is free; hits leave in tile order as before.
+// The queue costs 8 B per survivor written and read (3 GB per 3.1e8 lookups), the lines saved are ~7 GB and the filter
+// misses ~4 GB.  Every stage keeps tile order, so the run FSM downstream is unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CAS_BLK = 256;                 // threads of the two queue kernels (eight warps = eight tiles)
+
+template <int BLK>
+__device__ __forceinline__ uint32_t block_excl_scan_t(uint32_t mine, uint32_t* warp_tot, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < BLK / 32; w++) {
+        const uint32_t t = warp_tot[w];
+        if (w < wid) before += t;
+        tot += t;
+    }
+    *total = tot;
+    return before + incl - mine;
+}
+
+__device__ __forceinline__ void kg_store_stream_2xu64(unsigned long long* p, unsigned long long a, unsigned long long b, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(a), "l"(b), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void kg_store_stream_u64(unsigned long long* p, unsigned long long a, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(a), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long kg_load_stream_u64(const unsigned long long* p, uint64_t policy) {
+    unsigned long long v;
+    asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+#ifndef KG_FILTER_OCC
+#define KG_FILTER_OCC 8
+#endif
+__global__ __launch_bounds__(PROBE_BLK, KG_FILTER_OCC) void k_filter(const uint8_t* __restrict__ stream, uint32_t vtotal, uint32_t tile0, KgTableView tab,
+                                                          unsigned long long* __restrict__ queue, uint32_t* __restrict__ tile_qcnt,
+                                                          unsigned long long* __restrict__ ctr, uint32_t flags) {
+    const uint32_t tile = tile0 + blockIdx.x;
+    __shared__ __align__(16) unsigned long long sq[TILE];
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t warp_a[PROBE_BLK / 32], warp_kmers[PROBE_BLK / 32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += PROBE_BLK) lut[i] = (i >= 'A' && i <= 'Z') ? c_aa_code[i - 'A'] : 20;
+    __syncthreads();
+    const uint64_t pol_keep = kg_policy_evict_last();
+    const uint64_t pol_stream = kg_policy_evict_first();
+    const uint32_t p0 = tile * (uint32_t)TILE + (uint32_t)tid * PT;
+    uint32_t pass = 0, nk = 0;
+    uint32_t q[PT + 4];
+    if (p0 < vtotal) {
+        const uint32_t valid = encode_windows(stream, p0, vtotal, lut, q);
+        nk = __popc(valid);
+        pass = valid;
+        if (tab.filter_words) pass = filter_windows(tab, q, valid, flags, pol_keep);
+    }
+    uint32_t nsurv;
+    uint32_t qo = block_excl_scan(__popc(pass), warp_a, &nsurv);
+#pragma unroll
+    for (int i = 0; i < PT; i++)
+        if ((pass >> i) & 1u) sq[qo++] = ((uint64_t)q[i] * 160000ull + q[i + 4]) | ((unsigned long long)(tid * PT + i) << 35);
+    const uint32_t wk = __reduce_add_sync(0xFFFFFFFFu, nk);
+    if ((tid & 31) == 0) warp_kmers[tid >> 5] = wk;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t kmers = 0;
+#pragma unroll
+        for (int w = 0; w < PROBE_BLK / 32; w++) kmers += warp_kmers[w];
+        if (kmers) atomicAdd(&ctr[KG_CTR_KMERS], (unsigned long long)kmers);
+        if (nsurv) atomicAdd(&ctr[KG_CTR_SURV1], (unsigned long long)nsurv);
+        tile_qcnt[tile] = nsurv;
+    }
+    // the tile's survivors leave as whole 16-byte stores, streaming through L2 (they must not displace the filter)
+    unsigned long long* dst = queue + (size_t)tile * TILE;
+    for (uint32_t i = 2u * tid; i < nsurv; i += 2u * PROBE_BLK) {
+        if (i + 1 < nsurv) kg_store_stream_2xu64(dst + i, sq[i], sq[i + 1], pol_stream);
+        else kg_store_stream_u64(dst + i, sq[i], pol_stream);
+    }
+}
+
+// Stages B and C give every tile to ONE WARP (eight tiles per block): a tile holds only a few hundred survivors, and with a
+// block per tile the chain count -> entries -> filter word / bucket line -> scan -> store is five dependent round trips
+// for one load per thread (measured: 0.96 and 3.2 ms).  A lane owns CAS_U consecutive entries of a 32 x CAS_U round, so
+// CAS_U independent loads per lane are in flight, and order is kept by a shuffle scan of the lanes' counts: no barrier,
+// no shared memory.
+constexpr int CAS_U = 8;
+constexpr int CAS_ROUND = 32 * CAS_U;
+__device__ __forceinline__ void kg_load_entries8(const unsigned long long* p, unsigned long long (&e)[CAS_U], uint64_t policy) {
+    // 64 consecutive bytes (the slice is 8 KB aligned and a lane's offset a multiple of 64): two 256-bit loads
+    asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(p), "l"(policy));
+    asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(e[4]), "=l"(e[5]), "=l"(e[6]), "=l"(e[7]) : "l"(p + 4), "l"(policy));
+}
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t mine, uint32_t* total) {
+    const int lane = threadIdx.x & 31;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    *total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    return incl - mine;
+}
+
+__global__ __launch_bounds__(CAS_BLK) void k_refilter(unsigned long long* __restrict__ queue, uint32_t* __restrict__ tile_qcnt, uint32_t tile0,
+                                                      uint32_t tile_end, KgTableView tab) {
+    const uint32_t tile = tile0 + blockIdx.x * (CAS_BLK / 32) + (threadIdx.x >> 5);
+    if (tile >= tile_end) return;
+    const uint32_t cnt = tile_qcnt[tile];
+    if (cnt == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long* base = queue + (size_t)tile * TILE;
+    const uint64_t pol_keep = kg_policy_evict_last();
+    const uint64_t pol_stream = kg_policy_evict_first();
+    uint32_t out = 0;
+    for (uint32_t r0 = 0; r0 < cnt; r0 += CAS_ROUND) {
+        const uint32_t i0 = r0 + (uint32_t)lane * CAS_U;
+        unsigned long long e[CAS_U], fw[CAS_U];
+        kg_load_entries8(base + i0, e, pol_stream); // entries past cnt are stale but inside the tile's slice
+#pragma unroll
+        for (int u = 0; u < CAS_U; u++) {
+            const uint64_t m = kg_fhash2(e[u] & 0x7FFFFFFFFull);
+            fw[u] = i0 + u < cnt ? kg_load_filter_word(tab.filter2, kg_filter2_word(m, tab.filter2_words), pol_keep) : 0ull;
+        }
+        uint32_t pass = 0;
+#pragma unroll
+        for (int u = 0; u < CAS_U; u++) {
+            const unsigned long long fm = kg_filter2_mask(kg_fhash2(e[u] & 0x7FFFFFFFFull));
+            pass |= (uint32_t)(i0 + u < cnt && (fw[u] & fm) == fm) << u;
+        }
+        uint32_t total;
+        // The scan needs every lane's loaded entries, so all reads of this round are complete before the first store; the
+        // stores land at or below the positions already read (compaction in place, order kept).
+        uint32_t o = out + warp_excl_scan(__popc(pass), &total);
+#pragma unroll
+        for (int u = 0; u < CAS_U; u++)
+            if ((pass >> u) & 1u) kg_store_stream_u64(base + o++, e[u], pol_stream);
+        out += total;
+    }
+    if (lane == 0) tile_qcnt[tile] = out;
+}
+
+// Stage C.  Warp-cooperative probing: FOUR LANES fetch one 128-byte bucket line, one 32-byte sector each, in the same load
+// instruction -- lane 0 of the group gets the key sector, lanes 1-3 the payload sectors.  A hit's payload is then already
+// in a register of a sibling lane (four shuffles), not a second, dependent access to a line that L2 may have dropped in the
+// meantime (ncu, first version with a separate payload load: 14.3 GB of DRAM reads for 68 M survivors -- the 47 M payload
+// loads missed L2 and fetched their lines AGAIN; hit rate 9.7 %).  PR_U lines are in flight per group, 8 x PR_U per warp.
+// The tile's hit chunk is claimed UP FRONT for all its survivors (one atomic whose round trip overlaps the line fetches;
+// hits <= survivors), so hits can be written round by round in order (a ballot over the group leaders); tile_cnt gets the
+// real number, the gap behind it stays unused (downstream addresses chunks through tile_base / tile_cnt only).
+constexpr int PR_PASS = 8; // entries per lane and pass: 256 entries of the tile are fetched at once, then probed in rounds
+__device__ __forceinline__ KgBucket kg_load_line_sector(const uint4* lines, uint32_t b, uint32_t sector, uint64_t policy) {
+    KgBucket r;
+    const uint4* p = lines + (size_t)KG_LINE_UINT4 * b + 2u * sector;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p), "l"(policy));
+    return r;
+}
+// PR_U = bucket lines in flight per four-lane group (8 x PR_U per warp); a round covers 8 x PR_U consecutive entries
+template <int PR_U>
+__global__ __launch_bounds__(CAS_BLK) void k_probe2(const unsigned long long* __restrict__ queue, const uint32_t* __restrict__ tile_qcnt,
+                                                    uint32_t tile0, uint32_t tile_end, KgTableView tab, uint32_t* __restrict__ chunk_pos,
+                                                    int4* __restrict__ chunk_payload, uint32_t hit_cap, uint32_t* __restrict__ tile_base,
+                                                    uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr) {
+    constexpr int LPR = 32 / (8 * PR_U) ? 32 / (8 * PR_U) : 1; // (unused when a round needs more than one entry register)
+    constexpr int EPR = (8 * PR_U + 31) / 32;                   // entry registers a round consumes (1 for U <= 4, 2 for U = 8)
+    static_assert(PR_U == 2 || PR_U == 4 || PR_U == 8, "lines in flight per group");
+    (void)LPR;
+    const uint32_t tile = tile0 + blockIdx.x * (CAS_BLK / 32) + (threadIdx.x >> 5);
+    if (tile >= tile_end) return;
+    const uint32_t cnt = tile_qcnt[tile];
+    const int lane = threadIdx.x & 31;
+    if (cnt == 0) {
+        if (lane == 0) {
+            tile_base[tile] = 0;
+            tile_cnt[tile] = 0;
+        }
+        return;
+    }
+    unsigned long long claim = 0;
+    if (lane == 0) claim = atomicAdd(&ctr[KG_CTR_CLAIM], (unsigned long long)cnt);
+    const unsigned long long* base = queue + (size_t)tile * TILE;
+    const uint64_t pol_stream = kg_policy_evict_first();
+    const int grp = lane >> 2, sub = lane & 3, lead = lane & ~3;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t out = 0, cb = 0;
+    bool fits = true, have_claim = false;
+    for (uint32_t p0 = 0; p0 < cnt; p0 += 32 * PR_PASS) {
+        // the pass's entries, one coalesced 256-byte load per register: entry p0 + 32 j + lane sits in e[j] of `lane`
+        unsigned long long e[PR_PASS];
+#pragma unroll
+        for (int j = 0; j < PR_PASS; j++) {
+            e[j] = 0x7FFFFFFFFull; // the empty-slot pattern: matches nothing
+            if (p0 + 32 * j + lane < cnt) e[j] = kg_load_stream_u64(base + p0 + 32 * j + lane, pol_stream);
+        }
+        // rounds of 8 x PR_U entries, in order; the entry registers shift down as they are consumed
+        for (uint32_t r0 = p0; r0 < cnt && r0 < p0 + 32 * PR_PASS; r0 += 8 * PR_U) {
+            const uint32_t off = (r0 - p0) & 31u; // first lane of this round inside e[0] (always 0 unless PR_U < 4)
+            uint32_t mybkt[EPR];
+#pragma unroll
+            for (int q = 0; q < EPR; q++) mybkt[q] = kg_home_bucket(e[q] & 0x7FFFFFFFFull, tab.num_buckets);
+            KgBucket bk[PR_U];
+            bool valid[PR_U];
+#pragma unroll
+            for (int u = 0; u < PR_U; u++) {
+                const int idx = u * 8 + grp;               // entry r0 + idx of the round
+                const int src = (int)((off + idx) & 31u);
+                const uint32_t b = __shfl_sync(0xFFFFFFFFu, mybkt[idx >> 5], src);
+                valid[u] = r0 + idx < cnt;
+                if (valid[u]) bk[u] = kg_load_line_sector(tab.lines, b, (uint32_t)sub, pol_stream);
+            }
+#pragma unroll
+            for (int u = 0; u < PR_U; u++) {
+                const int idx = u * 8 + grp;
+                const int src = (int)((off + idx) & 31u);
+                const unsigned long long eu = __shfl_sync(0xFFFFFFFFu, e[idx >> 5], src);
+                const uint64_t key = eu & 0x7FFFFFFFFull;
+                int s = -1;
+                bool slow = false;
+                if (sub == 0 && valid[u]) {
+                    const uint32_t m = kg_bucket_match(bk[u], key);
+                    if (m) s = __ffs(m) - 1;
+                    else slow = (bk[u].w[6] & KG_W6_FLAG) != 0; // rare: the key may live in a later bucket
+                }
+                s = __shfl_sync(0xFFFFFFFFu, s, lead);
+                // payload s sits in sector 1 + s/2 (lane lead + 1 + s/2), words 4*(s&1) .. +3
+                const bool hi = (s & 1) != 0;
+                const uint32_t v0 = hi ? bk[u].w[4] : bk[u].w[0], v1 = hi ? bk[u].w[5] : bk[u].w[1];
+                const uint32_t v2 = hi ? bk[u].w[6] : bk[u].w[2], v3 = hi ? bk[u].w[7] : bk[u].w[3];
+                const int srcl = lead + 1 + (max(s, 0) >> 1);
+                int4 pl;
+                pl.x = (int)__shfl_sync(0xFFFFFFFFu, v0, srcl);
+                pl.y = (int)__shfl_sync(0xFFFFFFFFu, v1, srcl);
+                pl.z = (int)__shfl_sync(0xFFFFFFFFu, v2, srcl);
+                pl.w = (int)__shfl_sync(0xFFFFFFFFu, v3, srcl);
+                bool hit = sub == 0 && s >= 0;
+                if (slow) {
+                    const uint32_t slot = kg_lookup_from(tab, key, kg_home_bucket(key, tab.num_buckets) + 1);
+                    if (slot != 0xFFFFFFFFu) {
+                        pl = kg_load_payload(tab.lines, slot);
+                        hit = true;
+                    }
+                }
+                const uint32_t ball = __ballot_sync(0xFFFFFFFFu, hit);
+                if (!have_claim) { // the claim is needed only now: its latency ran under the line fetches
+                    claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+                    fits = claim + cnt <= (unsigned long long)hit_cap;
+                    cb = (uint32_t)claim;
+                    have_claim = true;
+                }
+                if (hit && fits) {
+                    const uint32_t o = cb + out + __popc(ball & lt_mask);
+                    chunk_pos[o] = tile * (uint32_t)TILE + (uint32_t)(eu >> 35);
+                    chunk_payload[o] = pl;
+                }
+                out += __popc(ball);
+            }
+            // consume: after a round has used up the 32 entries of e[0] (and e[1] for PR_U = 8), shift the registers down
+            if (((r0 - p0 + 8 * PR_U) & 31u) == 0 || PR_U == 8) {
+#pragma unroll
+                for (int j = 0; j + EPR < PR_PASS; j++) e[j] = e[j + EPR];
+            }
+        }
+    }
+    if (lane == 0) {
+        if (!fits) ctr[KG_CTR_OVERFLOW] = 1ull; // chunk array too small: the host re-runs with the exact size
+        tile_base[tile] = fits ? cb : 0xFFFFFFFFu;
+        tile_cnt[tile] = out;
+        if (out) atomicAdd(&ctr[KG_CTR_HITS], (unsigned long long)out);
+    }
+}
+
+// Variant of stage C without the four-lane cooperation: a lane owns PO_U consecutive entries of a 32 x PO_U round, loads
+// their key sectors (PO_U lines in flight per LANE, 32 x PO_U per warp) and reads a hit's payload with a second load from
+// the same line.  `pol` = L2 eviction policy of the key-sector load: with evict_first the line is gone again before the
+// payload load arrives (ncu: 80 % of the payload loads fetched their line a second time).
+template <int PO_U>
+__global__ __launch_bounds__(CAS_BLK) void k_probe2_own(const unsigned long long* __restrict__ queue, const uint32_t* __restrict__ tile_qcnt,
+                                                        uint32_t tile0, uint32_t tile_end, KgTableView tab, uint32_t* __restrict__ chunk_pos,
+                                                        int4* __restrict__ chunk_payload, uint32_t hit_cap, uint32_t* __restrict__ tile_base,
+                                                        uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr, uint32_t polsel) {
+    static_assert(PO_U == 4, "entries per lane");
+    const uint32_t tile = tile0 + blockIdx.x * (CAS_BLK / 32) + (threadIdx.x >> 5);
+    if (tile >= tile_end) return;
+    const uint32_t cnt = tile_qcnt[tile];
+    const int lane = threadIdx.x & 31;
+    if (cnt == 0) {
+        if (lane == 0) {
+            tile_base[tile] = 0;
+            tile_cnt[tile] = 0;
+        }
+        return;
+    }
+    unsigned long long claim = 0;
+    if (lane == 0) claim = atomicAdd(&ctr[KG_CTR_CLAIM], (unsigned long long)cnt);
+    const unsigned long long* base = queue + (size_t)tile * TILE;
+    const uint64_t pol_stream = kg_policy_evict_first();
+    const uint64_t pol_line = (polsel & 3u) == 1 ? kg_policy_evict_normal() : (polsel & 3u) == 2 ? kg_policy_evict_last() : kg_policy_evict_first();
+    const bool whole = (polsel & 4u) != 0;
+    uint32_t out = 0, cb = 0;
+    bool fits = true;
+    for (uint32_t r0 = 0; r0 < cnt; r0 += 32 * PO_U) {
+        const uint32_t i0 = r0 + (uint32_t)lane * PO_U;
+        unsigned long long e[PO_U];
+        asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(base + i0), "l"(pol_stream));
+        uint32_t bkt[PO_U], slot[PO_U];
+        KgBucket bk[PO_U];
+#pragma unroll
+        for (int u = 0; u < PO_U; u++) {
+            bkt[u] = kg_home_bucket(e[u] & 0x7FFFFFFFFull, tab.num_buckets);
+            if (i0 + u < cnt) bk[u] = whole ? kg_load_bucket_line(tab.lines, bkt[u], pol_line) : kg_load_bucket_hint(tab.lines, bkt[u], pol_line);
+        }
+        uint32_t hm = 0;
+#pragma unroll
+        for (int u = 0; u < PO_U; u++) {
+            slot[u] = 0xFFFFFFFFu;
+            if (i0 + u >= cnt) continue;
+            const uint64_t key = e[u] & 0x7FFFFFFFFull;
+            const uint32_t m = kg_bucket_match(bk[u], key);
+            if (m) slot[u] = bkt[u] * KG_BUCKET_KEYS + (__ffs(m) - 1);
+            else if (bk[u].w[6] & KG_W6_FLAG) slot[u] = kg_lookup_from(tab, key, bkt[u] + 1); // rare second line
+            hm |= (uint32_t)(slot[u] != 0xFFFFFFFFu) << u;
+        }
+        int4 pl[PO_U];
+#pragma unroll
+        for (int u = 0; u < PO_U; u++)
+            if ((hm >> u) & 1u) pl[u] = kg_load_payload(tab.lines, slot[u]);
+        if (r0 == 0) {
+            claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+            fits = claim + cnt <= (unsigned long long)hit_cap;
+            cb = (uint32_t)claim;
+        }
+        uint32_t total;
+        uint32_t o = cb + out + warp_excl_scan(__popc(hm), &total);
+        if (fits) {
+#pragma unroll
+            for (int u = 0; u < PO_U; u++)
+                if ((hm >> u) & 1u) {
+                    chunk_pos[o] = tile * (uint32_t)TILE + (uint32_t)(e[u] >> 35);
+                    chunk_payload[o] = pl[u];
+                    o++;
+                }
+        }
+        out += total;
+    }
+    if (lane == 0) {
+        if (!fits) ctr[KG_CTR_OVERFLOW] = 1ull;
+        tile_base[tile] = fits ? cb : 0xFFFFFFFFu;
+        tile_cnt[tile] = out;
+        if (out) atomicAdd(&ctr[KG_CTR_HITS], (unsigned long long)out);
     }
 }
 
@@ -880,15 +1254,20 @@ __global__ void k_emit_hits(const uint64_t* __restrict__ voff, uint64_t nv, int 
     out[i] = h;
 }
 
+constexpr int KG_MAX_PARTS = 16;
 struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them let slice s+1 queue up behind slice s
     DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
+    DevBuf queue, tile_qcnt;                                     // probe cascade: survivors (8 KB slice per tile) and their counts
     DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
     DevBuf fk_a, fi_a;                                           // per-sequence path: class histogram / cursors, sequence permutation
     DevBuf hit_v, seg_flag, seg_id, seg_begin, nseg;              // segment path
     DevBuf o_oi, o_cidx, o_c01, o_crank, o_run_oi, o_run_crank;  // segment path: OTU runs (sparse oI / length, per-segment count, its scan, dense oI / length)
     bool seg = false;                                            // which FSM path the enqueued run uses
     uint64_t* h_ctr = nullptr; // pinned, KG_CTR_COUNT + 1 (the last slot receives the call total)
-    cudaEvent_t ev[4] = {};    // begin, probe begin, probe end, end
+    cudaEvent_t ev[6] = {};    // begin, probe begin, probe end, end, cascade: first filter done, second filter done
+    cudaEvent_t part_ev[KG_MAX_PARTS + 1] = {}; // cascade in parts: filters of part p done; [KG_MAX_PARTS]: last line stage done
+    bool cascade = false;      // the enqueued run used the three-kernel probe
+    uint32_t cascade_parts = 1;
     uint64_t hit_cap = 0;
     uint32_t launches = 0;
 };
@@ -903,6 +1282,7 @@ RunScratch& scratch_of(kg_context* ctx) {
         for (auto& sl : sc->slot) {
             cudaMallocHost(&sl.h_ctr, (KG_CTR_COUNT + 1) * sizeof(uint64_t));
             for (auto& e : sl.ev) cudaEventCreate(&e);
+            for (auto& e : sl.part_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         }
         ctx->scratch = sc;
     }
@@ -1036,6 +1416,7 @@ extern "C" int kg_init(int device, kg_context** out) {
         int lo_p = 0, hi_p = 0;
         cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
         CU(cudaStreamCreateWithPriority(&ctx->fsm_stream, cudaStreamNonBlocking, hi_p));
+        CU(cudaStreamCreateWithPriority(&ctx->lines_stream, cudaStreamNonBlocking, hi_p)); // cascade in parts: the bucket-line stage
     }
     for (auto& ev : ctx->ev) CU(cudaEventCreate(&ev));
     for (auto& ev : ctx->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1054,12 +1435,14 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     RunScratch& sc = scratch_of(ctx);
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
-                          &sl.call_off, &sl.ctr, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
+                          &sl.call_off, &sl.ctr, &sl.queue, &sl.tile_qcnt, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
                           &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_crank,
                           &sl.o_run_oi, &sl.o_run_crank})
             b->release();
         if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
         for (auto& e : sl.ev)
+            if (e) cudaEventDestroy(e);
+        for (auto& e : sl.part_ev)
             if (e) cudaEventDestroy(e);
     }
     delete static_cast<RunScratch*>(ctx->scratch);
@@ -1077,6 +1460,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->fsm_stream) cudaStreamDestroy(ctx->fsm_stream);
+    if (ctx->lines_stream) cudaStreamDestroy(ctx->lines_stream);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     delete ctx;
 }
@@ -1224,6 +1608,46 @@ static uint32_t probe_flags() { // experiment switches: bit 0 = no evict_first o
     return e ? (uint32_t)atoi(e) : 0u;
 }
 
+// Which probe: the three-kernel cascade (tables with a second prefilter) or the fused kernel.  KG_PROBE=fused|cascade.
+static bool use_cascade(const kg_table* table) {
+    if (!table->filter_words || !table->filter2_words) return false;
+    if (const char* e = getenv("KG_PROBE")) return strcmp(e, "fused") != 0;
+    return true;
+}
+static int probe2_u() { // experiment switch: bucket lines in flight per four-lane group in the cascade's last stage
+    static const int u = [] { const char* e = getenv("KG_PROBE2_U"); return e ? atoi(e) : 4; }();
+    return u;
+}
+// In how many parts the cascade runs (KG_CASCADE_PARTS; 1 = the three stages one after the other over the whole batch).
+static uint32_t cascade_parts(uint32_t ntiles) {
+    uint32_t p = 1;
+    if (const char* e = getenv("KG_CASCADE_PARTS")) p = (uint32_t)atoi(e);
+    p = std::max(1u, std::min<uint32_t>(p, KG_MAX_PARTS));
+    while (p > 1 && ntiles / p < 4096) p--; // parts of less than ~4 M positions only add launches
+    return p;
+}
+// A kernel launch with its own persisting-L2 access-policy window (bytes = 0: no window): the cascade's filters take
+// turns in the set-aside part of L2, which a stream-wide window cannot express.
+template <class... KArgs, class... Args>
+static cudaError_t launch_windowed(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const void* win_base,
+                                   size_t win_bytes, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(win_base);
+    at[0].val.accessPolicyWindow.num_bytes = win_bytes;
+    at[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    at[0].val.accessPolicyWindow.hitProp = win_bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    at[0].val.accessPolicyWindow.missProp = win_bytes ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+    cfg.attrs = at;
+    cfg.numAttrs = getenv("KG_NO_L2_PERSIST") ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Enqueue one whole pass (prepare -> probe -> scan -> FSM -> scan -> compact) on the compute stream; no host
 // synchronisation.  The hit buffers are sized from a guess (half the positions, or what an earlier run needed); if a
 // tile cannot claim its chunk the kernels downstream skip their work and pipe_finish repeats the pass with the exact size.
@@ -1274,7 +1698,52 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
     cudaEventRecord(sl.ev[1], st);
     if (custom) {
         KG_TRY((*custom)(sl, d_ctr, hit_cap, st));
+    } else if (ntiles && use_cascade(table)) {
+        sl.cascade = true;
+        KG_TRY(sl.queue.ensure((size_t)ntiles * TILE * 8));
+        KG_TRY(sl.tile_qcnt.ensure((size_t)ntiles * 4));
+        const KgTableView tv = table->view();
+        const size_t carve = table->l2_carve; // 0 unless KG_CASCADE_PERSIST: the filters have L2 to themselves in their stages
+        // The stage that streams bucket lines (DRAM-bound) can overlap the filter stages of the NEXT part of the batch
+        // (bound by L1 wavefronts and L2 hits): parts > 1 puts it on a second, high-priority stream.
+        uint32_t parts = cascade_parts(ntiles);
+        sl.cascade_parts = parts;
+        const uint32_t per = (ntiles + parts - 1) / parts;
+        cudaStream_t ls = parts > 1 ? ctx->lines_stream : st;
+        for (uint32_t p = 0; p < parts; p++) {
+            const uint32_t t0 = p * per, t1 = std::min(ntiles, t0 + per);
+            if (t1 <= t0) break;
+            const unsigned wgrid = blocks_for(t1 - t0, CAS_BLK / 32);
+            CU(launch_windowed(k_filter, dim3(t1 - t0), dim3(PROBE_BLK), 0, st, tv.filter, std::min<size_t>((size_t)tv.filter_words * 8, carve),
+                               b->stream(), (uint32_t)vtotal, t0, tv, sl.queue.as<unsigned long long>(), sl.tile_qcnt.as<uint32_t>(), d_ctr, probe_flags()));
+            if (parts == 1) cudaEventRecord(sl.ev[4], st);
+            CU(launch_windowed(k_refilter, dim3(wgrid), dim3(CAS_BLK), 0, st, tv.filter2, std::min<size_t>((size_t)tv.filter2_words * 8, carve),
+                               sl.queue.as<unsigned long long>(), sl.tile_qcnt.as<uint32_t>(), t0, t1, tv));
+            if (parts == 1) cudaEventRecord(sl.ev[5], st);
+            if (parts > 1) {
+                cudaEventRecord(sl.part_ev[p], st);
+                cudaStreamWaitEvent(ls, sl.part_ev[p], 0);
+            }
+            if (const char* kind = getenv("KG_PROBE2_KIND"); !kind || strcmp(kind, "coop")) { // default: the faster of the two variants
+                const char* pe = getenv("KG_PROBE2_POLICY");
+                CU(launch_windowed(k_probe2_own<4>, dim3(wgrid), dim3(CAS_BLK), 0, ls, nullptr, 0, (const unsigned long long*)sl.queue.as<unsigned long long>(),
+                                   (const uint32_t*)sl.tile_qcnt.as<uint32_t>(), t0, t1, tv, sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
+                                   (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(), sl.tile_cnt.as<uint32_t>(), d_ctr, (uint32_t)(pe ? atoi(pe) : 1)));
+                sl.launches += 3;
+                continue;
+            }
+            auto kp2 = probe2_u() == 2 ? k_probe2<2> : k_probe2<4>;
+            CU(launch_windowed(kp2, dim3(wgrid), dim3(CAS_BLK), 0, ls, nullptr, 0, (const unsigned long long*)sl.queue.as<unsigned long long>(),
+                               (const uint32_t*)sl.tile_qcnt.as<uint32_t>(), t0, t1, tv, sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
+                               (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(), sl.tile_cnt.as<uint32_t>(), d_ctr));
+            sl.launches += 3;
+        }
+        if (parts > 1) {
+            cudaEventRecord(sl.part_ev[KG_MAX_PARTS], ls);
+            cudaStreamWaitEvent(st, sl.part_ev[KG_MAX_PARTS], 0);
+        }
     } else if (ntiles) {
+        sl.cascade = false;
         k_probe<<<ntiles, PROBE_BLK, PROBE_SMEM, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sl.chunk_pos.as<uint32_t>(),
                                                       sl.chunk_payload.as<int4>(), (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
                                                       sl.tile_cnt.as<uint32_t>(), d_ctr, probe_flags());
@@ -1366,6 +1835,8 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
     return KG_OK;
 }
 
+static uint32_t ntiles_of(const kg_batch* b) { return (uint32_t)((b->vtotal + TILE - 1) >> TILE_SHIFT); }
+
 // Wait for the pass, repeat it once if the hit buffers were too small, fill in the statistics, and (for "-d") build the
 // position-ordered HIT records.
 static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result* r,
@@ -1379,14 +1850,21 @@ static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_
         launches += sl.launches;
         if (!sl.h_ctr[KG_CTR_OVERFLOW]) break;
         if (attempt) KG_FAIL(KG_ECUDA, "hit buffer overflow persisted after resizing to %llu", (unsigned long long)sl.hit_cap);
-        KG_TRY(pipe_enqueue(ctx, sl, table, b, prm, r, sl.h_ctr[KG_CTR_HITS], seq_base, custom)); // exact size
+        KG_TRY(pipe_enqueue(ctx, sl, table, b, prm, r, std::max(sl.h_ctr[KG_CTR_HITS], sl.h_ctr[KG_CTR_CLAIM]), seq_base, custom)); // exact size
     }
     const uint64_t nhits = sl.h_ctr[KG_CTR_HITS], nkmers = sl.h_ctr[KG_CTR_KMERS];
-    sc.hit_cap_seen = std::max<uint64_t>(sc.hit_cap_seen, nhits + nhits / 16 + 1024);
+    const uint64_t nslots = std::max<uint64_t>(nhits, sl.h_ctr[KG_CTR_CLAIM]); // the cascade claims a slot per second-filter survivor
+    sc.hit_cap_seen = std::max<uint64_t>(sc.hit_cap_seen, nslots + nslots / 16 + 1024);
     if (nhits > 0xFFFFFFF0ull) KG_FAIL(KG_ERANGE, "%llu hits in one batch", (unsigned long long)nhits);
     cudaEventElapsedTime(&r->stats.ms_prepare, sl.ev[0], sl.ev[1]);
     cudaEventElapsedTime(&r->stats.ms_probe, sl.ev[1], sl.ev[2]);
     cudaEventElapsedTime(&r->stats.ms_group, sl.ev[2], sl.ev[3]);
+    r->stats.ms_filter = r->stats.ms_refilter = r->stats.ms_lines = 0.f;
+    if (sl.cascade && sl.cascade_parts == 1 && !custom && ntiles_of(b)) {
+        cudaEventElapsedTime(&r->stats.ms_filter, sl.ev[1], sl.ev[4]);
+        cudaEventElapsedTime(&r->stats.ms_refilter, sl.ev[4], sl.ev[5]);
+        cudaEventElapsedTime(&r->stats.ms_lines, sl.ev[5], sl.ev[2]);
+    }
     cudaEventElapsedTime(&r->stats.ms_device, sl.ev[0], sl.ev[3]);
     const uint64_t nv = b->nv;
     const int per_seq = b->mode == KG_MODE_AA ? 1 : 6;
@@ -1415,6 +1893,8 @@ static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_
     r->stats.num_hits = nhits;
     r->stats.num_calls = *(uint32_t*)&sl.h_ctr[KG_CTR_COUNT];
     r->stats.num_launches = launches;
+    r->stats.num_survivors1 = sl.h_ctr[KG_CTR_SURV1];
+    r->stats.num_survivors2 = sl.h_ctr[KG_CTR_CLAIM];
     return KG_OK;
 }
 
@@ -1654,10 +2134,15 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         R->stats.num_positions += ps.num_positions;
         R->stats.num_kmers += ps.num_kmers;
         R->stats.num_launches += ps.num_launches;
+        R->stats.num_survivors1 += ps.num_survivors1;
+        R->stats.num_survivors2 += ps.num_survivors2;
         R->stats.ms_device += ms;
         R->stats.ms_prepare += ps.ms_prepare;
         R->stats.ms_probe += ps.ms_probe;
         R->stats.ms_group += ps.ms_group;
+        R->stats.ms_filter += ps.ms_filter;
+        R->stats.ms_refilter += ps.ms_refilter;
+        R->stats.ms_lines += ps.ms_lines;
         kg_batch_free(bt);
         slot[s % UP] = nullptr;
         if (dbg) fprintf(stderr, "[kg] slice %zu: %zu seqs, host %.3f ms (device %.3f = prepare %.3f + probe %.3f + group %.3f ms), since start %.3f ms\n", s, (size_t)(cut[s + 1] - cut[s]), now_ms() - t0, ms, ps.ms_prepare, ps.ms_probe, ps.ms_group, now_ms() - t_begin);

@@ -194,12 +194,12 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32
 #pragma unroll
         for (int i = 0; i < PT; i++) {
             fw[i] = 0;
-            if ((valid >> i) & 1u) fw[i] = kg_load_filter_word(tab.filter, kg_filter_word(kg_mix(key[i]), tab.filter_words), pol_keep);
+            if ((valid >> i) & 1u) fw[i] = kg_load_filter_word(tab.filter, kg_filter_word(kg_fhash1(key[i]), tab.filter_words), pol_keep);
         }
         pass = 0;
 #pragma unroll
         for (int i = 0; i < PT; i++) {
-            const unsigned long long fm = kg_filter_mask(kg_mix(key[i]));
+            const unsigned long long fm = kg_filter_mask(kg_fhash1(key[i]));
             pass |= (uint32_t)((fw[i] & fm) == fm) << i;
         }
         pass &= valid;
@@ -393,6 +393,7 @@ int comm_alloc(kg_context* ctx, int rank, int nranks, kg_comm** out) {
 // batch), so the set-aside is switched on for the answer phase only and restored when the call returns (other runs on this
 // device expect it).  One rank, 311 M lookups: keys 1.13 -> 0.50 ms, merge 5.6 -> 3.4 ms, step 16.8 -> 13.8 ms.
 void shard_l2_setaside(const kg_table* table, bool on) {
+    if (on && !table->l2_carve) kg_table_pin_filter(table->ctx, table); // a table built for the cascade: k_answer wants the window
     if (!table->l2_carve || getenv("KG_SHARD_KEEP_CARVE")) return;
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, on ? table->l2_carve : 0);
     cudaGetLastError();

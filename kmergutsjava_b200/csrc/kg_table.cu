@@ -57,6 +57,8 @@ void DevBuf::release() {
 }
 
 static double filter_bits_per_key();
+static int filter_stages();
+static void pin_filter(kg_context* ctx, const kg_table* t, bool force);
 
 // ---------------------------------------------------------------------------------------------------------------
 // reference-format image parser (streaming, so a 10-100 GB file never has to sit in host memory twice)
@@ -231,8 +233,15 @@ __global__ void k_filter_build(const uint64_t* __restrict__ comp, size_t n, unsi
                                uint32_t filter_words) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const uint64_t h = kg_mix(comp[r] & 0x7FFFFFFFFull);
-    atomicOr(&filter[kg_filter_word(h, filter_words)], kg_filter_mask(h));
+    const uint64_t m = kg_fhash1(comp[r] & 0x7FFFFFFFFull);
+    atomicOr(&filter[kg_filter_word(m, filter_words)], kg_filter_mask(m));
+}
+__global__ void k_filter2_build(const uint64_t* __restrict__ comp, size_t n, unsigned long long* __restrict__ filter2,
+                                uint32_t filter2_words) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t m = kg_fhash2(comp[r] & 0x7FFFFFFFFull);
+    atomicOr(&filter2[kg_filter2_word(m, filter2_words)], kg_filter2_mask(m));
 }
 
 __global__ void k_count_flagged(const uint32_t* __restrict__ words, size_t nbuckets_total, unsigned long long* out) {
@@ -260,12 +269,16 @@ inline unsigned blocks_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 
 
 } // namespace
 
+void kg_table_pin_filter(kg_context* ctx, const kg_table* t) { pin_filter(ctx, t, true); }
+
 KgTableView kg_table::view() const {
     KgTableView v;
     v.lines = d_lines;
     v.num_buckets = num_buckets;
     v.filter = d_filter;
     v.filter_words = filter_words;
+    v.filter2 = filter2_words ? d_filter + filter_words : nullptr;
+    v.filter2_words = filter2_words;
     return v;
 }
 
@@ -273,8 +286,12 @@ KgTableView kg_table::view() const {
 // Pin the prefilter in L2: a persisting carve-out (<= 79 MiB on B200) plus an access-policy window on the context's
 // stream, so that the 128-byte lines streaming through for the probes cannot push it out.  (One table per context
 // benefits; a later table takes the window over.)
-static void pin_filter(kg_context* ctx, const kg_table* t) {
+static void pin_filter(kg_context* ctx, const kg_table* t, bool force) {
     if (!t->d_filter || !t->filter_words || getenv("KG_NO_L2_PERSIST")) return;
+    // A table with a second prefilter is probed by the cascade (kg_run.cu): each filter has the L2 to itself during its
+    // stage, and a persisting set-aside only takes L2 away from the bucket-line stage (measured: 3.5 vs 2.8 ms).  The fused
+    // kernel and the hash-sharded mode's k_answer (one filter against streaming lines) keep the window.
+    if (!force && t->filter2_words && t->shard_count == 1 && !getenv("KG_CASCADE_PERSIST")) return;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
     const size_t fbytes = (size_t)t->filter_words * 8;
@@ -368,11 +385,15 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
             if (const char* e = getenv("KG_FILTER_MAX_MB")) max_bytes = (uint64_t)atoll(e) << 20; // experiments
             if (bytes > max_bytes) bytes = max_bytes;
             if (bytes < 4096) bytes = 4096;
-            t->filter_words = (uint32_t)(bytes / 8);
-            CU(cudaMalloc(&t->d_filter, (size_t)t->filter_words * 8));
-            CU(cudaMemsetAsync(t->d_filter, 0, (size_t)t->filter_words * 8, st));
+            t->filter_words = (uint32_t)(bytes / 8) & ~15u; // whole 128-byte lines, so that the second filter starts on one
+            t->filter2_words = filter_stages() >= 2 ? t->filter_words : 0;
+            const size_t fwords = (size_t)t->filter_words + t->filter2_words;
+            CU(cudaMalloc(&t->d_filter, fwords * 8));
+            CU(cudaMemsetAsync(t->d_filter, 0, fwords * 8, st));
             k_filter_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter, t->filter_words);
-            pin_filter(ctx, t);
+            if (t->filter2_words)
+                k_filter2_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter + t->filter_words, t->filter2_words);
+            pin_filter(ctx, t, false);
         }
         // Every stored key must be found again.  With repeated keys only the surviving copy's payload can match, so
         // the payload comparison is skipped for inputs that had duplicates.
@@ -400,13 +421,17 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
     t->info.num_signatures = (int64_t)n_unique;
     t->info.num_buckets = (int64_t)nb_total;
     t->info.flagged_buckets = (int64_t)h_ctr[1];
-    t->info.device_bytes = (int64_t)(nb_total * 128 + (size_t)t->filter_words * 8);
+    t->info.device_bytes = (int64_t)(nb_total * 128 + ((size_t)t->filter_words + t->filter2_words) * 8);
     return KG_OK;
 }
 
 static double filter_bits_per_key() { // KG_FILTER_BITS=0 disables the prefilter
     const char* e = getenv("KG_FILTER_BITS");
     return e ? atof(e) : KG_FILTER_BITS_PER_KEY;
+}
+static int filter_stages() { // KG_FILTER_STAGES=2 also builds the second-stage prefilter; the probe then runs as the three-kernel
+    const char* e = getenv("KG_FILTER_STAGES"); // cascade (kg_run.cu), which moves 40 % less DRAM traffic but measured slower than the
+    return e ? atoi(e) : 1;                     // fused kernel (profiles/r02_probe_cascade.md), so one stage is the default
 }
 static double table_load_factor() {
     const char* e = getenv("KG_TABLE_LOAD");
@@ -517,7 +542,13 @@ static int load_file_impl(kg_context* ctx, const char* path, int rank, int nrank
         }
         fclose(f);
     }
-    return table_from_parser(ctx, ps, table);
+    KG_TRY(table_from_parser(ctx, ps, table));
+    struct stat sst;
+    if (stat(path, &sst) == 0) {
+        (*table)->src_size = (uint64_t)sst.st_size;
+        (*table)->src_mtime_ns = (int64_t)sst.st_mtim.tv_sec * 1000000000ll + sst.st_mtim.tv_nsec;
+    }
+    return KG_OK;
 }
 
 extern "C" int kg_table_load_file(kg_context* ctx, const char* path, kg_table** table) { return load_file_impl(ctx, path, 0, 1, table); }
@@ -613,13 +644,16 @@ struct CacheHeader {
     char magic[8];           // "KGB200T\0"
     uint32_t format;         // bumped whenever the bucket / filter layout or the hashes change
     uint32_t bucket_keys, line_bytes, tail_buckets;
-    uint32_t num_buckets, filter_words;
+    uint32_t num_buckets, filter_words, filter2_words, pad0;
     int32_t shard_rank, shard_count;
     kg_table_info info;
     uint64_t lines_bytes, filter_bytes;
-    uint64_t check;          // kg_mix over the fields above (catches truncation / foreign files, not bit rot in the body)
+    uint64_t src_size;       // size and mtime of the reference-format file the table was parsed from (0 = unknown):
+    int64_t src_mtime_ns;    //   kg_table_load_cached_checked refuses a cache made from another or an updated file
+    uint64_t body_check;     // order-independent checksum over every 8-byte word of lines + filters (computed on the device)
+    uint64_t check;          // kg_mix over the fields above (catches truncation / foreign files)
 };
-constexpr uint32_t KG_CACHE_FORMAT = 1;
+constexpr uint32_t KG_CACHE_FORMAT = 3;
 uint64_t header_check(const CacheHeader& h) {
     uint64_t x = 0x4B47423230305431ull;
     const unsigned char* p = (const unsigned char*)&h;
@@ -629,6 +663,48 @@ uint64_t header_check(const CacheHeader& h) {
         x = kg_mix(x ^ w);
     }
     return x;
+}
+// sum over kg_mix(word ^ index): any flipped bit, swapped or missing chunk changes it; runs at HBM speed
+__global__ void k_body_check(const unsigned long long* __restrict__ words, size_t n, uint64_t salt, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc += kg_mix(words[i] ^ (salt + i));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+int body_check_of(kg_context* ctx, const kg_table* t, uint64_t* out) {
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, 8));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(d, 0, 8, st));
+    const size_t nl = ((size_t)t->num_buckets + KG_TAIL_BUCKETS) * 16, nf = (size_t)t->filter_words + t->filter2_words;
+    k_body_check<<<148 * 8, 256, 0, st>>>((const unsigned long long*)t->d_lines, nl, 0x11ull << 56, d);
+    if (nf) k_body_check<<<148 * 8, 256, 0, st>>>(t->d_filter, nf, 0x22ull << 56, d);
+    cudaError_t e = cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    CU(e);
+    return KG_OK;
+}
+bool read_cache_header(FILE* f, CacheHeader* h) {
+    struct stat st;
+    bool ok = fread(h, sizeof *h, 1, f) == 1 && memcmp(h->magic, "KGB200T", 8) == 0 && h->check == header_check(*h);
+    if (ok && (h->format != KG_CACHE_FORMAT || h->bucket_keys != KG_BUCKET_KEYS || h->line_bytes != 128 || h->tail_buckets != KG_TAIL_BUCKETS))
+        ok = false; // written by a build with another layout: rebuild from the reference file
+    if (ok) ok = h->lines_bytes == ((uint64_t)h->num_buckets + KG_TAIL_BUCKETS) * 128 &&
+                 h->filter_bytes == ((uint64_t)h->filter_words + h->filter2_words) * 8 && fstat(fileno(f), &st) == 0 &&
+                 (uint64_t)st.st_size == sizeof *h + h->lines_bytes + h->filter_bytes;
+    return ok;
+}
+// the reference-format file a data directory resolves to (the .gz wins, KGJ:749-753)
+bool stat_source(const char* data_dir, uint64_t* size, int64_t* mtime_ns) {
+    const std::string base = std::string(data_dir) + "/kmer.table.mem_map", gz = base + ".gz";
+    struct stat st;
+    if (stat(gz.c_str(), &st) != 0 && stat(base.c_str(), &st) != 0) return false;
+    *size = (uint64_t)st.st_size;
+    *mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+    return true;
 }
 } // namespace
 
@@ -643,11 +719,15 @@ extern "C" int kg_table_save(kg_context* ctx, const kg_table* t, const char* pat
     h.tail_buckets = KG_TAIL_BUCKETS;
     h.num_buckets = t->num_buckets;
     h.filter_words = t->filter_words;
+    h.filter2_words = t->filter2_words;
+    h.src_size = t->src_size;
+    h.src_mtime_ns = t->src_mtime_ns;
+    KG_TRY(body_check_of(ctx, t, &h.body_check));
     h.shard_rank = t->shard_rank;
     h.shard_count = t->shard_count;
     h.info = t->info;
     h.lines_bytes = ((uint64_t)t->num_buckets + KG_TAIL_BUCKETS) * 128;
-    h.filter_bytes = (uint64_t)t->filter_words * 8;
+    h.filter_bytes = ((uint64_t)t->filter_words + t->filter2_words) * 8;
     h.check = header_check(h);
     std::string tmp = std::string(path) + ".tmp";
     FILE* f = fopen(tmp.c_str(), "wb");
@@ -684,13 +764,7 @@ extern "C" int kg_table_load_cached(kg_context* ctx, const char* path, kg_table*
     FILE* f = fopen(path, "rb");
     if (!f) KG_FAIL(KG_EIO, "cannot open %s", path);
     CacheHeader h;
-    struct stat st;
-    bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "KGB200T", 8) == 0 && h.check == header_check(h);
-    if (ok && (h.format != KG_CACHE_FORMAT || h.bucket_keys != KG_BUCKET_KEYS || h.line_bytes != 128 || h.tail_buckets != KG_TAIL_BUCKETS))
-        ok = false; // written by a build with another layout: rebuild from the reference file
-    if (ok) ok = h.lines_bytes == ((uint64_t)h.num_buckets + KG_TAIL_BUCKETS) * 128 && h.filter_bytes == (uint64_t)h.filter_words * 8 &&
-                 fstat(fileno(f), &st) == 0 && (uint64_t)st.st_size == sizeof h + h.lines_bytes + h.filter_bytes;
-    if (!ok) {
+    if (!read_cache_header(f, &h)) {
         fclose(f);
         KG_FAIL(KG_EFORMAT, "%s is not a table cache of this build (bad magic, layout, checksum or size)", path);
     }
@@ -698,6 +772,9 @@ extern "C" int kg_table_load_cached(kg_context* ctx, const char* path, kg_table*
     t->ctx = ctx;
     t->num_buckets = h.num_buckets;
     t->filter_words = h.filter_words;
+    t->filter2_words = h.filter2_words;
+    t->src_size = h.src_size;
+    t->src_mtime_ns = h.src_mtime_ns;
     t->shard_rank = h.shard_rank;
     t->shard_count = h.shard_count;
     t->info = h.info;
@@ -740,20 +817,44 @@ extern "C" int kg_table_load_cached(kg_context* ctx, const char* path, kg_table*
         if (stage[i]) cudaFreeHost(stage[i]);
         if (ev[i]) cudaEventDestroy(ev[i]);
     }
+    if (rc == KG_OK && !getenv("KG_CACHE_NO_VERIFY")) { // bit rot / a torn write in the 8 GB body would silently change CALL lines
+        uint64_t chk = 0;
+        rc = body_check_of(ctx, t, &chk);
+        if (rc == KG_OK && chk != h.body_check) {
+            kg_set_error("%s: body checksum mismatch (file damaged); rebuild it from the reference-format table", path);
+            rc = KG_EFORMAT;
+        }
+    }
     if (rc != KG_OK) {
         kg_table_free(t);
         return rc;
     }
-    pin_filter(ctx, t);
+    pin_filter(ctx, t, false);
     *table = t;
     return KG_OK;
+}
+
+extern "C" int kg_table_load_cached_checked(kg_context* ctx, const char* path, const char* data_dir, kg_table** table) {
+    if (!ctx || !path || !data_dir || !table) KG_FAIL(KG_EINVAL, "kg_table_load_cached_checked: null argument");
+    uint64_t size = 0;
+    int64_t mtime = 0;
+    if (!stat_source(data_dir, &size, &mtime)) KG_FAIL(KG_EIO, "no kmer.table.mem_map[.gz] in %s", data_dir);
+    FILE* f = fopen(path, "rb");
+    if (!f) KG_FAIL(KG_EIO, "cannot open %s", path);
+    CacheHeader h;
+    const bool ok = read_cache_header(f, &h);
+    fclose(f);
+    if (!ok) KG_FAIL(KG_EFORMAT, "%s is not a table cache of this build (bad magic, layout, checksum or size)", path);
+    if (h.src_size != size || h.src_mtime_ns != mtime)
+        KG_FAIL(KG_EFORMAT, "%s was built from another (or an older) kmer.table.mem_map than the one in %s", path, data_dir);
+    return kg_table_load_cached(ctx, path, table);
 }
 
 extern "C" int kg_table_attach(kg_context* ctx, const kg_table* table) {
     if (!ctx || !table) KG_FAIL(KG_EINVAL, "kg_table_attach: null argument");
     if (ctx->device != table->ctx->device) KG_FAIL(KG_EINVAL, "kg_table_attach: the table lives on device %d, the context on device %d", table->ctx->device, ctx->device);
     CU(cudaSetDevice(ctx->device));
-    pin_filter(ctx, table); // the persisting-L2 window is a per-stream attribute
+    pin_filter(ctx, table, false); // the persisting-L2 window is a per-stream attribute
     return KG_OK;
 }
 

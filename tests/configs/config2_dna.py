@@ -13,6 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tools import kg_synth as synth  # noqa: E402
+from tools import kg_benchlib as bl  # noqa: E402
 
 
 def main():
@@ -27,9 +28,9 @@ def main():
     import kmergutsjava_b200 as kg
     ctx = kg.Context(0)
     u = synth.Universe(n_families=a.families)
-    dk, dp, nsig = kg.synth_signatures(ctx, u, a.sigs)
+    dk, dp, nsig = bl.synth_signatures(ctx, u, a.sigs)
     table = ctx.table_from_device_entries(dk, dp, nsig)
-    ds, do, total = kg.synth_genomes(ctx, u, a.genomes, a.length, seed=2)
+    ds, do, total = bl.synth_genomes(ctx, u, a.genomes, a.length, seed=2)
     batch = ctx.batch_from_device(kg.MODE_DNA, ds, do, a.genomes, total)
     params = kg.default_params()
     for _ in range(3):
@@ -50,8 +51,8 @@ def main():
         import torch
         h_seq = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
         h_off = torch.empty(a.genomes + 1, dtype=torch.int64, pin_memory=True)
-        kg._check(kg.lib().kg_device_to_host(ctx._h, h_seq.data_ptr(), ds, total))
-        kg._check(kg.lib().kg_device_to_host(ctx._h, h_off.data_ptr(), do, 8 * (a.genomes + 1)))
+        kg._check(bl.lib().kg_device_to_host(ctx._h, h_seq.data_ptr(), ds, total))
+        kg._check(bl.lib().kg_device_to_host(ctx._h, h_off.data_ptr(), do, 8 * (a.genomes + 1)))
         for _ in range(3):
             ctx.run_ptr(table, kg.MODE_DNA, h_seq.data_ptr(), h_off.data_ptr(), a.genomes, params).free()
         t0 = time.perf_counter()
@@ -65,10 +66,10 @@ def main():
         from oracle import kgo
         from tests.parity import assert_same
         kgo.build()
-        img = kg.synth_reference_image(ctx, dk, dp, nsig, 3 * nsig + 1)
+        img = bl.synth_reference_image(ctx, dk, dp, nsig, 3 * nsig + 1)
         n = min(a.parity_genomes, a.genomes)
-        off = ctx.to_host(do, 8 * (n + 1)).view(np.uint64).copy()
-        sb = ctx.to_host(ds, int(off[-1]))
+        off = bl.to_host(ctx, do, 8 * (n + 1)).view(np.uint64).copy()
+        sb = bl.to_host(ctx, ds, int(off[-1]))
         t0 = time.time()
         ref = kgo.run(kgo.Table(borrow=img), kgo.make_params(aa=False), sb, off, kgo.STREAM_JOIN, threads=n)
         cpu_s = time.time() - t0

@@ -19,6 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tools import kg_synth as synth  # noqa: E402
+from tools import kg_benchlib as bl  # noqa: E402
 
 
 def main():
@@ -42,7 +43,7 @@ def main():
     import kmergutsjava_b200 as kg
     ctx = kg.Context(local)
     u = synth.Universe(n_families=a.families)
-    dk, dp, nsig = kg.synth_signatures(ctx, u, a.sigs)
+    dk, dp, nsig = bl.synth_signatures(ctx, u, a.sigs)
     table = ctx.table_from_device_entries(dk, dp, nsig)
     params = kg.default_params()
     per = (a.orfs + world - 1) // world  # this rank's slice of the job's protein indices
@@ -51,7 +52,7 @@ def main():
 
     def gen(b):
         n = min(a.batch, count - b * a.batch)
-        ds, do, total = kg.synth_proteins(ctx, u, first + b * a.batch, n, seed=3)
+        ds, do, total = bl.synth_proteins(ctx, u, first + b * a.batch, n, seed=3)
         return ds, do, total, n
 
     # warm-up (buffer pools, clocks)
@@ -60,8 +61,8 @@ def main():
     for _ in range(3):
         ctx.run_batch(table, bt, params).free()
     bt.free()
-    kg.device_free(ds)
-    kg.device_free(do)
+    bl.device_free(ds)
+    bl.device_free(do)
 
     def sync_all():
         if dist is not None:
@@ -88,8 +89,8 @@ def main():
         residues += total
         r.free()
         bt.free()
-        kg.device_free(ds)
-        kg.device_free(do)
+        bl.device_free(ds)
+        bl.device_free(do)
     sync_all()
     job_s = time.perf_counter() - t_job
 
@@ -116,23 +117,23 @@ def main():
         from oracle import kgo
         from tests.parity import assert_same
         kgo.build()
-        img = kg.synth_reference_image(ctx, dk, dp, nsig, 3 * nsig + 1)
+        img = bl.synth_reference_image(ctx, dk, dp, nsig, 3 * nsig + 1)
         otable = kgo.Table(borrow=img)
         rng = np.random.default_rng(3)
         picks = [("first of shard", first), ("random", first + int(rng.integers(0, max(count - a.parity, 1))))]
         notes = []
         for what, start in picks:
             n = min(a.parity, count)
-            ds, do, total = kg.synth_proteins(ctx, u, start, n, seed=3)
-            off = ctx.to_host(do, 8 * (n + 1)).view(np.uint64).copy()
-            sb = ctx.to_host(ds, int(off[-1]))
+            ds, do, total = bl.synth_proteins(ctx, u, start, n, seed=3)
+            off = bl.to_host(ctx, do, 8 * (n + 1)).view(np.uint64).copy()
+            sb = bl.to_host(ctx, ds, int(off[-1]))
             ref = kgo.run(otable, kgo.make_params(aa=True), sb, off, kgo.DIRECT_PROBE, threads=os.cpu_count() or 1)
             g = ctx.run(table, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1))
             assert_same(g, ref, what=f"configs[3] {what}")
             notes.append(f"{what} ({start}..+{n}): {len(ref.hits)} hits, {len(ref.calls)} calls")
             g.free()
-            kg.device_free(ds)
-            kg.device_free(do)
+            bl.device_free(ds)
+            bl.device_free(do)
         out["parity"] = "bit-exact vs the CPU oracle: " + "; ".join(notes)
     if rank == 0:
         print(json.dumps(out))

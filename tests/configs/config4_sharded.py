@@ -23,6 +23,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tools import kg_synth as synth  # noqa: E402
+from tools import kg_benchlib as bl  # noqa: E402
 
 
 def local_main(a):
@@ -33,14 +34,14 @@ def local_main(a):
     u = synth.Universe(n_families=a.families or 1_250_000, sig_keep_per_1024=a.keep)
     tables = []
     for r in range(R):
-        dk, dp, n = kg.synth_signatures_sharded(ctx, u, r, R)
+        dk, dp, n = bl.synth_signatures_sharded(ctx, u, r, R)
         tables.append(ctx.table_from_device_entries_sharded(dk, dp, n, r, R))
-        kg.device_free(dk)
-        kg.device_free(dp)
+        bl.device_free(dk)
+        bl.device_free(dp)
     comms = kg.Comm.local([ctx] * R)
     batches = []
     for r in range(R):
-        ds, do, total = kg.synth_proteins(ctx, u, r * a.proteins, a.proteins, seed=1)
+        ds, do, total = bl.synth_proteins(ctx, u, r * a.proteins, a.proteins, seed=1)
         batches.append(ctx.batch_from_device(kg.MODE_AA, ds, do, a.proteins, total))
     params = kg.default_params()
     for _ in range(a.warmup):
@@ -109,11 +110,11 @@ def main():
     ctx = kg.Context(local)
     u = synth.Universe(n_families=families, sig_keep_per_1024=a.keep)
     t0 = time.time()
-    dk, dp, nsig = kg.synth_signatures_sharded(ctx, u, rank, world)
+    dk, dp, nsig = bl.synth_signatures_sharded(ctx, u, rank, world)
     t1 = time.time()
     table = ctx.table_from_device_entries_sharded(dk, dp, nsig, rank, world)
-    kg.device_free(dk)
-    kg.device_free(dp)
+    bl.device_free(dk)
+    bl.device_free(dp)
     t2 = time.time()
     ti = table.info
     log(f"shard built: {nsig} signatures, {ti.device_bytes / 1e9:.2f} GB ({t1 - t0:.1f} s generate, {t2 - t1:.1f} s build)")
@@ -121,7 +122,7 @@ def main():
     if dist is not None:
         dist.broadcast_object_list(uid, src=0)
     comm = kg.Comm(ctx, rank, world, uid[0])
-    ds, do, total = kg.synth_proteins(ctx, u, rank * a.proteins, a.proteins, seed=1)
+    ds, do, total = bl.synth_proteins(ctx, u, rank * a.proteins, a.proteins, seed=1)
     batch = ctx.batch_from_device(kg.MODE_AA, ds, do, a.proteins, total)
     params = kg.default_params()
     for _ in range(max(a.warmup, 3)):
@@ -166,21 +167,21 @@ def main():
     if not a.no_check:
         res = comm.run(table, batch, kg.default_params(emit_hits=1))
         hits, calls, otus = res.hits, res.calls, res.otus
-        my = (len(hits), kg.hits_checksum(ctx, hits, do), int(res.stats.num_kmers))
+        my = (len(hits), bl.hits_checksum(ctx, hits, do), int(res.stats.num_kmers))
         contrib = np.zeros((world, 2), dtype=np.uint64)
         valid = 0
         for s in range(world):  # proteins of rank s against MY shard
             if s == rank:
                 ds2, do2, tot2 = ds, do, total
             else:
-                ds2, do2, tot2 = kg.synth_proteins(ctx, u, s * a.proteins, a.proteins, seed=1)
-            v, h, ck = kg.naive_scan_aa(ctx, table, ds2, do2, a.proteins, tot2)
+                ds2, do2, tot2 = bl.synth_proteins(ctx, u, s * a.proteins, a.proteins, seed=1)
+            v, h, ck = bl.naive_scan_aa(ctx, table, ds2, do2, a.proteins, tot2)
             contrib[s] = (h, ck)
             if s == rank:
                 valid = v
             else:
-                kg.device_free(ds2)
-                kg.device_free(do2)
+                bl.device_free(ds2)
+                bl.device_free(do2)
         tot = np.array(reduce(contrib.view(np.int64).tolist(), "SUM", torch.int64), dtype=np.int64).view(np.uint64) if dist is not None else contrib
         ok = int(tot[rank][0]) == my[0] and int(tot[rank][1]) == my[1] and valid == my[2]
         all_ok = reduce([1.0 if ok else 0.0], "MIN")[0] if dist is not None else float(ok)

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     names = set()
-    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_synth.h", "kmerguts_shard.h"):
+    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_shard.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(kg_[a-z0-9_]+)\s*\(", src))
@@ -34,9 +34,20 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_no_torch_types_in_signatures():
-    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_synth.h", "kmerguts_shard.h"):
+    for h in ("kmerguts.h", "kmerguts_host.h", "kmerguts_shard.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         assert "torch" not in src and "at::" not in src and "std::" not in src
+
+
+def test_product_library_carries_only_the_path():
+    """Generators, the naive cross-check scan and the roofline microbenchmark live in tools/benchlib/libkmerguts_bench.so;
+    the product library exports nothing of them."""
+    out = subprocess.run(["nm", "-D", "--defined-only", kg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("kg_")}
+    assert not [n for n in exported if "synth" in n or "roofline" in n or "naive" in n], exported
+    assert exported == _declared(), exported ^ _declared()
+    from tools import kg_benchlib as bl
+    bl.lib()  # the bench library loads (no GPU needed) and resolves against the product library
 
 
 def test_struct_layouts_match_numpy_views():

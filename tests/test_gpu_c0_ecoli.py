@@ -143,3 +143,32 @@ def test_c0_cli_table_cache(kg, oracle, c0, tmp_path):
         assert os.path.getsize(cache) > 1 << 20
         if attempt == 0:
             os.remove(d / "kmer.table.mem_map")  # only the cache can serve the second run
+
+
+def test_c0_cli_stale_table_cache(kg, oracle, c0, tmp_path):
+    """-C with a cache that was built from ANOTHER kmer.table.mem_map than the one in -D: the cache records the
+    source's size and mtime, the command line notices the mismatch, rebuilds from -D and reports what -D says."""
+    import shutil
+    d = tmp_path / "KmerData"
+    shutil.copytree(c0, d)
+    cache = str(tmp_path / "table.kgcache")
+    ids, descr, seqs = synth.read_fasta_simple(FAA)
+    q = str(tmp_path / "q.faa")
+    synth.write_fasta(q, ids[:200], seqs[:200])
+    g0 = str(tmp_path / "g0.txt")
+    r = subprocess.run([kg.CLI_PATH, "-a", "-D", str(d), "-C", cache, "-q", q, "-o", g0], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # a different table in -D: every payload's function index swapped to 0 (same size, new mtime)
+    img = bytearray(open(d / "kmer.table.mem_map", "rb").read())
+    a = np.frombuffer(img, dtype=np.uint8)[24:].reshape(-1, 24)
+    a[:, 16:20] = 0
+    with open(d / "kmer.table.mem_map", "wb") as f:
+        f.write(bytes(img))
+    os.utime(d / "kmer.table.mem_map", ns=(1, 1))
+    o_out, g1 = str(tmp_path / "o.txt"), str(tmp_path / "g1.txt")
+    oracle.run_cli(["-a", "-D", str(d), "-q", q, "-o", o_out])
+    r = subprocess.run([kg.CLI_PATH, "-a", "-D", str(d), "-C", cache, "-q", q, "-o", g1], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "table cache not used" in r.stderr
+    assert _strip(open(g1).read(), False) == _strip(open(o_out).read(), False)
+    assert _strip(open(g1).read(), False) != _strip(open(g0).read(), False)

@@ -74,6 +74,38 @@ def test_dna_parity(kg, ctx, oracle, universe, flags):
     t.free()
 
 
+@pytest.mark.parametrize("probe,stages", [("cascade", "2"), ("fused", "2"), ("fused", "1"), ("fused", "0")],
+                         ids=["cascade", "fused", "fused-one-filter", "fused-no-filter"])
+def test_probe_variants(kg, ctx, oracle, universe, monkeypatch, probe, stages):
+    """The probe stage exists as a three-kernel cascade (two prefilters that take turns in L2, the default) and as one
+    fused kernel (one prefilter, also what the hash-sharded mode's k_answer shares its code with): both must give the
+    oracle's hits, in aa mode and in 6-frame mode, with dense tiles (a protein of the table's own windows) included."""
+    u, img, _ = universe
+    monkeypatch.setenv("KG_PROBE", probe)
+    if stages == "0":
+        monkeypatch.setenv("KG_FILTER_BITS", "0")
+    else:
+        monkeypatch.setenv("KG_FILTER_STAGES", stages)
+    t = ctx.table_from_image(img)
+    alpha = np.frombuffer(synth.PROT_ALPHA.encode(), np.uint8)
+    fams = [alpha[u.consensus(f)].tobytes() for f in range(40)]  # unmutated consensus: tiles where a third of the windows hit
+    seqs = u.proteins(700, seed=77) + fams + [b"", b"ACDEFGHIK", b"A" * 3000]
+    sb, off = oracle.concat(seqs)
+    res = ctx.run(t, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1))
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True), sb, off, oracle.DIRECT_PROBE)
+    assert len(ref.hits) > 5000
+    assert_same(res, ref, what=f"aa {probe} {stages}")
+    st = res.stats
+    assert (st.ms_filter > 0) == (probe == "cascade"), (st.ms_filter, st.ms_refilter, st.ms_lines)
+    res.free()
+    sb, off = oracle.concat([synth.genome(u, 40000, seed=41, index=i) for i in range(2)])
+    res = ctx.run(t, kg.MODE_DNA, sb, off, kg.default_params(emit_hits=1))
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=False), sb, off, oracle.DIRECT_PROBE)
+    assert_same(res, ref, what=f"dna {probe} {stages}")
+    res.free()
+    t.free()
+
+
 KATS = json.load(open(os.path.join(GOLD, "fsm_kats.json")))
 
 
@@ -349,6 +381,13 @@ def test_table_cache_roundtrip(kg, ctx, oracle, universe, tmp_path):
         with pytest.raises(kg.KgError) as e:
             ctx.load_table_cached(path + ".bad")
         assert e.value.code in (-5, -4)
+    # bit rot inside the body (not the header): the body checksum refuses it (a damaged cache must not yield calls)
+    mid = len(raw) // 2
+    with open(path + ".rot", "wb") as f:
+        f.write(raw[:mid] + bytes([raw[mid] ^ 0x10]) + raw[mid + 1:])
+    with pytest.raises(kg.KgError, match="checksum") as e:
+        ctx.load_table_cached(path + ".rot")
+    assert e.value.code == -5
     with pytest.raises(kg.KgError):
         ctx.load_table_cached(path + ".missing")
     for x in (t, c, s, s2):

@@ -11,6 +11,7 @@ import pytest
 
 from tests.parity import assert_same
 from tools import kg_synth as synth
+from tools import kg_benchlib as bl  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -75,17 +76,17 @@ def test_sharded_generator_is_a_partition(kg, ctx):
     """kg_synth_signatures_sharded: the shards' signatures are disjoint, owned by their rank, and their union is the
     unsharded generator's output (same payloads)."""
     u = synth.Universe(n_families=2000, seed=0x4B470009)
-    dk, dp, n = kg.synth_signatures(ctx, u, 0)
-    keys = ctx.to_host(dk, 8 * n).view(np.uint64).copy()
-    pay = ctx.to_host(dp, 16 * n).view(np.uint32).reshape(n, 4).copy()
+    dk, dp, n = bl.synth_signatures(ctx, u, 0)
+    keys = bl.to_host(ctx, dk, 8 * n).view(np.uint64).copy()
+    pay = bl.to_host(ctx, dp, 16 * n).view(np.uint32).reshape(n, 4).copy()
     whole = {int(k): tuple(p) for k, p in zip(keys, pay)}
-    kg.device_free(dk)
-    kg.device_free(dp)
+    bl.device_free(dk)
+    bl.device_free(dp)
     nranks, seen = 3, {}
     for r in range(nranks):
-        dk, dp, m = kg.synth_signatures_sharded(ctx, u, r, nranks)
-        ks = ctx.to_host(dk, 8 * m).view(np.uint64).copy()
-        ps = ctx.to_host(dp, 16 * m).view(np.uint32).reshape(m, 4).copy()
+        dk, dp, m = bl.synth_signatures_sharded(ctx, u, r, nranks)
+        ks = bl.to_host(ctx, dk, 8 * m).view(np.uint64).copy()
+        ps = bl.to_host(ctx, dp, 16 * m).view(np.uint32).reshape(m, 4).copy()
         assert all(kg.shard_owner(int(k), nranks) == r for k in ks[:500])
         for k, p in zip(ks, ps):
             assert int(k) not in seen
@@ -93,8 +94,8 @@ def test_sharded_generator_is_a_partition(kg, ctx):
         t = ctx.table_from_device_entries_sharded(dk, dp, m, r, nranks)
         assert t.info.num_signatures == m
         t.free()
-        kg.device_free(dk)
-        kg.device_free(dp)
+        bl.device_free(dk)
+        bl.device_free(dp)
     assert seen == whole and len(whole) > 100000
 
 

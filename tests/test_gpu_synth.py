@@ -5,6 +5,7 @@ import pytest
 
 from tests.parity import assert_same
 from tools import kg_synth as synth
+from tools import kg_benchlib as bl  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -26,41 +27,41 @@ def ctx(kg):
 def test_signatures_match_numpy(kg, ctx, max_sigs):
     u = synth.Universe(n_families=150, seed=0x4B470009)
     keys, otu, avg, fi, wt = u.signatures(max_sigs or None)
-    dk, dp, n = kg.synth_signatures(ctx, u, max_sigs)
+    dk, dp, n = bl.synth_signatures(ctx, u, max_sigs)
     assert n == len(keys)
-    gk = ctx.to_host(dk, 8 * n).view(np.uint64)
-    gp = ctx.to_host(dp, 16 * n).view(np.int32).reshape(n, 4)
+    gk = bl.to_host(ctx, dk, 8 * n).view(np.uint64)
+    gp = bl.to_host(ctx, dp, 16 * n).view(np.int32).reshape(n, 4)
     assert np.array_equal(gk.astype(np.int64), keys)
     assert np.array_equal(gp[:, 0], otu) and np.array_equal(gp[:, 1], avg) and np.array_equal(gp[:, 2], fi)
     assert np.array_equal(gp[:, 3].view(np.float32), wt)
-    kg.device_free(dk)
-    kg.device_free(dp)
+    bl.device_free(dk)
+    bl.device_free(dp)
 
 
 def test_proteins_match_numpy(kg, ctx):
     u = synth.Universe(n_families=150, seed=0x4B470009)
     want = u.proteins(60, seed=7, first=1000)
-    ds, do, total = kg.synth_proteins(ctx, u, 1000, 60, 7)
-    off = ctx.to_host(do, 8 * 61).view(np.uint64)
-    sb = ctx.to_host(ds, total)
+    ds, do, total = bl.synth_proteins(ctx, u, 1000, 60, 7)
+    off = bl.to_host(ctx, do, 8 * 61).view(np.uint64)
+    sb = bl.to_host(ctx, ds, total)
     assert list(off) == list(np.concatenate([[0], np.cumsum([len(w) for w in want])]))
     assert sb.tobytes() == b"".join(want)
-    kg.device_free(ds)
-    kg.device_free(do)
+    bl.device_free(ds)
+    bl.device_free(do)
 
 
 def test_device_pipeline_on_device_generated_inputs(kg, ctx, oracle):
     """Generators -> kg_table_from_device_entries -> kg_batch_from_device -> kg_batch_run, checked against the oracle
     reading the device-written reference-format image."""
     u = synth.Universe(n_families=400, seed=0x4B47000A)
-    dk, dp, n = kg.synth_signatures(ctx, u, 0)
+    dk, dp, n = bl.synth_signatures(ctx, u, 0)
     table = ctx.table_from_device_entries(dk, dp, n)
-    img = kg.synth_reference_image(ctx, dk, dp, n, 3 * n + 1)
+    img = bl.synth_reference_image(ctx, dk, dp, n, 3 * n + 1)
     ent = np.frombuffer(img, dtype=synth.ENTRY_DTYPE, offset=24)
     assert int((ent["which"] <= synth.MAX_ENCODED).sum()) == n and ent["which"][-1] > synth.MAX_ENCODED
-    ds, do, total = kg.synth_proteins(ctx, u, 0, 2000, 3)
-    off = ctx.to_host(do, 8 * 2001).view(np.uint64).copy()
-    sb = ctx.to_host(ds, total).copy()
+    ds, do, total = bl.synth_proteins(ctx, u, 0, 2000, 3)
+    off = bl.to_host(ctx, do, 8 * 2001).view(np.uint64).copy()
+    sb = bl.to_host(ctx, ds, total).copy()
     batch = ctx.batch_from_device(kg.MODE_AA, ds, do, 2000, total)
     res = ctx.run_batch(table, batch, kg.default_params(emit_hits=1))
     ref = oracle.run(oracle.Table(borrow=img), oracle.make_params(aa=True), sb, off, oracle.STREAM_JOIN, threads=4)
@@ -74,11 +75,11 @@ def test_device_pipeline_on_device_generated_inputs(kg, ctx, oracle):
     for x in (res, res2, batch, table, t2):
         x.free()
     for p in (dk, dp, ds, do):
-        kg.device_free(p)
+        bl.device_free(p)
 
 
 def test_probe_roofline_runs(kg, ctx):
-    r = ctx.probe_roofline(256 << 20, 1 << 24, 256, 4)
+    r = bl.probe_roofline(ctx, 256 << 20, 1 << 24, 256, 4)
     assert r > 1e9
 
 
@@ -87,11 +88,11 @@ def test_full_size_properties_against_naive_kernel(kg, ctx):
     an order-independent checksum over (position, payload) of every hit must equal those of the naive one-thread-per-
     position kernel (byte-wise residue reads, no prefilter, no queue, full table lookup).  Also: running twice changes nothing."""
     u = synth.Universe(n_families=40000, seed=0x4B47000C)
-    dk, dp, n = kg.synth_signatures(ctx, u, 0)
+    dk, dp, n = bl.synth_signatures(ctx, u, 0)
     table = ctx.table_from_device_entries(dk, dp, n)
     nprot = 100000
-    ds, do, total = kg.synth_proteins(ctx, u, 0, nprot, 5)
-    valid, hits, chk = kg.naive_scan_aa(ctx, table, ds, do, nprot, total)
+    ds, do, total = bl.synth_proteins(ctx, u, 0, nprot, 5)
+    valid, hits, chk = bl.naive_scan_aa(ctx, table, ds, do, nprot, total)
     assert valid > 0.9 * total - 9 * nprot and hits > 0.05 * valid
     batch = ctx.batch_from_device(kg.MODE_AA, ds, do, nprot, total)
     first = None
@@ -101,7 +102,7 @@ def test_full_size_properties_against_naive_kernel(kg, ctx):
         assert (st.num_kmers, st.num_hits) == (valid, hits)
         h = res.hits
         assert len(h) == hits
-        assert kg.hits_checksum(ctx, h, do) == chk
+        assert bl.hits_checksum(ctx, h, do) == chk
         key = (h["seq"].astype(np.int64) << 32) | h["pos"].astype(np.int64)
         assert np.all(np.diff(key) > 0)                       # sorted by (sequence, position), no duplicates
         calls = res.calls
@@ -112,8 +113,8 @@ def test_full_size_properties_against_naive_kernel(kg, ctx):
         first = sig
         res.free()
     # the naive scan does not care whether the batch has been patched (last residue -> 0) or not
-    assert kg.naive_scan_aa(ctx, table, ds, do, nprot, total) == (valid, hits, chk)
+    assert bl.naive_scan_aa(ctx, table, ds, do, nprot, total) == (valid, hits, chk)
     batch.free()
     table.free()
     for p in (dk, dp, ds, do):
-        kg.device_free(p)
+        bl.device_free(p)

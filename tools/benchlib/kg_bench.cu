@@ -1,15 +1,16 @@
-// kg_synth.cu -- bench/test tooling (include/kmerguts_synth.h): probe-roofline microbenchmark, CUDA generators of
-// the synthetic universe of tools/kg_synth.py, and a device-side writer of the reference's table format.
-// Nothing here is on the product path.
+// kg_bench.cu -- bench/test tooling (tools/benchlib/kmerguts_bench.h), built as libkmerguts_bench.so, SEPARATE from the
+// product library: probe-roofline microbenchmark, CUDA generators of the synthetic universe of tools/kg_synth.py, a
+// device-side writer of the reference's table format, a naive cross-check scan.  Nothing here is on the product path;
+// it links against libkmerguts_b200.so only for the context / table handles it is handed.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
 
-#include "../../include/kmerguts_synth.h"
-#include "kg_device.cuh"
-#include "kg_internal.h"
+#include "kmerguts_bench.h"
+#include "../../kmergutsjava_b200/csrc/kg_device.cuh"
+#include "../../kmergutsjava_b200/csrc/kg_internal.h"
 
 namespace {
 

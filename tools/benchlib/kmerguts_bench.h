@@ -1,6 +1,7 @@
 /*
- * include/kmerguts_synth.h -- bench / test tooling shipped inside libkmerguts_b200.so.  NOT part of the drop-in
- * surface (that is include/kmerguts.h): the reference has no counterpart for any of this.
+ * tools/benchlib/kmerguts_bench.h -- bench / test tooling, built as tools/benchlib/libkmerguts_bench.so.  NOT part of the
+ * product library (libkmerguts_b200.so carries only the path) and not part of the drop-in surface (include/kmerguts.h):
+ * the reference has no counterpart for any of this.
  *
  *   - the random-sector probe roofline microbenchmark (R_probe)
  *   - CUDA generators of the synthetic universe defined in tools/kg_synth.py (same counter-based hashing, so the
@@ -8,10 +9,10 @@
  *   - a device-side writer of the REFERENCE's table format, so that the CPU oracle can be handed the very same
  *     200M-signature table the GPU probes
  */
-#ifndef KMERGUTS_SYNTH_H
-#define KMERGUTS_SYNTH_H
+#ifndef KMERGUTS_BENCH_H
+#define KMERGUTS_BENCH_H
 
-#include "kmerguts.h"
+#include "../../include/kmerguts.h"
 
 #ifdef __cplusplus
 extern "C" {

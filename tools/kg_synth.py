@@ -5,7 +5,7 @@ function.index (KGJ:345-373) and FASTA (KGJ:1132-1192), the C0 fixture derived f
 reference ships as test data, and the family/protein/genome generators of SURVEY.md section 8(d).
 
 The synthetic universe is defined with integer-only counter hashing (splitmix64 finaliser) so that the CUDA generators
-in kmergutsjava_b200/csrc/kg_synth.cu produce the very same bytes for the large configurations.
+in tools/benchlib/kg_bench.cu produce the very same bytes for the large configurations.
 """
 from __future__ import annotations
 
@@ -38,7 +38,7 @@ def mix64(x):
 
 
 def hash3(seed, a, b):
-    """h(seed, a, b) = mix64(mix64(seed + a) ^ (b * MB)); the same formula is in kg_synth.cu."""
+    """h(seed, a, b) = mix64(mix64(seed + a) ^ (b * MB)); the same formula is in tools/benchlib/kg_bench.cu."""
     with np.errstate(over="ignore"):
         return mix64(mix64(U64(seed) + np.asarray(a, dtype=U64)) ^ (np.asarray(b, dtype=U64) * _MB))
 
