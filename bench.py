@@ -5,13 +5,17 @@ synthetic 200M-signature table, 1M random-length synthetic proteins, protein mod
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port) on host cores
 
-A step = one pass of the hot path (patch -> encode+probe -> gather -> run FSM -> CALL/OTU records) over one batch of
-1M proteins.  `value` = lookups/s with the proteins already resident in HBM; `e2e` = the same through the C-ABI call
-kg_run() with pinned HOST buffers (H2D of the sequences and D2H of calls + OTU counts inside the timed region).
-Inputs (table 1.8 GB + 0.3 GB of residues per step) are far larger than the 126 MB L2, so no explicit L2 flush is done.
+A step = one pass of the hot path (patch -> encode+probe -> run FSM -> CALL/OTU records) over one batch of 1M proteins.
+`value` = lookups/s with the proteins already resident in HBM; `e2e` = the same through the C-ABI call with pinned HOST
+buffers (H2D of the sequences and D2H of calls + OTU counts inside the timed region): kg_run_packed_aa on the 5-bit residue
+codes the library's ingest produces (kg_pack_aa), with the call on raw characters (kg_run) reported beside it.
+Inputs (table 8.6 GB + 0.3 GB of residues per step) are far larger than the 126 MB L2, so no explicit L2 flush is done.
+
+After the headline the same process runs reduced-time legs of BASELINE.json configs[2], [3] and [4] (bench_legs.py) and adds
+their results -- with their parity checks -- to the JSON line as `configs2`, `configs3`, `configs4`; at N > 1 the configs[4]
+leg goes through the library's own NCCL communicator (hash-sharded table, k-mers exchanged over NVLink).
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -28,7 +32,7 @@ from tools import kg_synth as synth  # noqa: E402
 from tools import kg_benchlib as bl  # noqa: E402
 
 BYTES_PER_LOOKUP_AA = 33.0  # one 32-byte table sector + 1 residue byte
-
+WORKLOAD = "configs[1]: synthetic 200M-signature table, 1M random-length synthetic proteins, protein mode"
 
 T_START = time.time()
 
@@ -46,10 +50,14 @@ def parse_args():
     ap.add_argument("--families", type=int, default=2_000_000)
     ap.add_argument("--sigs", type=int, default=200_000_000)
     ap.add_argument("--proteins", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="proteins in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="proteins in the CPU baseline sample (0 = the whole step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e2", action="store_true", help="skip the two-thread variant of the end-to-end measurement")
+    ap.add_argument("--no-legs", action="store_true", help="skip the configs[2] / [3] / [4] legs")
+    ap.add_argument("--legs", default="2,3,4", help="which legs to run")
+    ap.add_argument("--orfs", type=int, default=100_000_000, help="configs[3]: proteins in the whole job")
+    ap.add_argument("--c4-families", type=int, default=0, help="configs[4]: families (0 = 1.4 M per GPU, ~2e9 signatures on 8 GPUs)")
     return ap.parse_args()
 
 
@@ -100,10 +108,13 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
-def dist_setup(args):
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # more point-to-point channels for the library's exchanges in the configs[4] leg (NCCL reads these once per process)
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "64")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "64")
     import torch
     dist = None
     if world > 1:
@@ -113,27 +124,10 @@ def dist_setup(args):
     return world, rank, local, torch, dist
 
 
-def all_max(torch, dist, x, local):
-    if dist is None:
-        return x
-    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
-def all_sum(torch, dist, x, local):
-    if dist is None:
-        return x
-    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
-
-
-def barrier(torch, dist, local):
-    torch.cuda.synchronize(local)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize(local)
+def workload_config(args, nsig, residues):
+    """The keys that define the workload: identical in both arms (the reference arm emits exactly this dict)."""
+    return {"workload": WORKLOAD, "signatures": int(nsig), "families": args.families, "proteins_per_gpu": args.proteins,
+            "residues_per_gpu": int(residues), "table_replicated": True}
 
 
 def build_inputs(kg, ctx, args, rank):
@@ -153,34 +147,50 @@ def build_inputs(kg, ctx, args, rank):
     return u, (dk, dp, nsig), table, (ds, do, total), timing
 
 
-def cpu_reference_run(kgo, otable, sb, off, threads):
-    t0 = time.time()
-    ref = kgo.run(otable, kgo.make_params(aa=True), sb, off, kgo.STREAM_JOIN, threads=threads)
-    return ref, time.time() - t0
-
-
-def sample_host(kg, ctx, ds, do, nsample):
+def sample_host(ctx, ds, do, nsample):
     off = bl.to_host(ctx, do, 8 * (nsample + 1)).view(np.uint64).copy()
     sb = bl.to_host(ctx, ds, int(off[-1]))
     return sb, off
 
 
+def timed_calls(plumb, clocks, steps, warmup, call):
+    """W untimed + K timed calls bracketed by barrier + synchronize; returns (seconds max over ranks, lookups of this rank, last stats)."""
+    for _ in range(warmup):
+        call().free()
+    plumb.barrier()
+    w0 = time.time()
+    t0 = time.perf_counter()
+    lookups, st = 0, None
+    for _ in range(steps):
+        r = call()
+        st = r.stats
+        lookups += st.num_kmers
+        r.free()
+    plumb.barrier()
+    dt = plumb.reduce([time.perf_counter() - t0], "MAX")[0]
+    clocks.window(w0, time.time())
+    return dt, lookups, st
+
+
 def run_ours(args):
-    world, rank, local, torch, dist = dist_setup(args)
+    world, rank, local, torch, dist = dist_setup()
     import kmergutsjava_b200 as kg
+    import bench_legs as legs
+    plumb = legs.Plumbing(torch, dist, rank, world, local)
     ctx = kg.Context(local)
     u, (dk, dp, nsig), table, (ds, do, total), prep = build_inputs(kg, ctx, args, rank)
     ti = table.info
     params = kg.default_params()
     batch = ctx.batch_from_device(kg.MODE_AA, ds, do, args.proteins, total)
+    warm = max(args.warmup, 3)
 
     # ---- device-resident throughput ----
     clocks = ClockSampler(local)
     clocks.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         ctx.run_batch(table, batch, params).free()
-        log("warm-up step done")
-    barrier(torch, dist, local)
+    log("warm-up done")
+    plumb.barrier()
     w0 = time.time()
     t0 = time.perf_counter()
     probe_ms, dev_ms, lookups, launches, st = [], [], 0, 0, None
@@ -192,57 +202,69 @@ def run_ours(args):
         lookups += st.num_kmers
         launches += st.num_launches
         r.free()
-    barrier(torch, dist, local)
-    dt = all_max(torch, dist, time.perf_counter() - t0, local)
+    plumb.barrier()
+    dt = plumb.reduce([time.perf_counter() - t0], "MAX")[0]
     clocks.window(w0, time.time())
-    total_lookups = all_sum(torch, dist, float(lookups), local)
-    total_proteins = float(args.proteins * args.steps * world)
+    total_lookups = plumb.reduce([float(lookups)])[0]
     value = total_lookups / dt
     log(f"device-resident: {value:.3e} lookups/s")
 
-    # ---- end to end through kg_run with pinned host buffers ----
+    # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
     if not args.no_e2e:
         h_seq = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
         h_off = torch.empty(args.proteins + 1, dtype=torch.int64, pin_memory=True)
         kg._check(bl.lib().kg_device_to_host(ctx._h, h_seq.data_ptr(), ds, total))
         kg._check(bl.lib().kg_device_to_host(ctx._h, h_off.data_ptr(), do, 8 * (args.proteins + 1)))
-        d2h = 0
-        for _ in range(max(args.warmup, 3)):
-            ctx.run_ptr(table, kg.MODE_AA, h_seq.data_ptr(), h_off.data_ptr(), args.proteins, params).free()
-        barrier(torch, dist, local)
-        w0 = time.time()
-        t0 = time.perf_counter()
-        e_lookups = 0
-        for _ in range(args.steps):
-            r = ctx.run_ptr(table, kg.MODE_AA, h_seq.data_ptr(), h_off.data_ptr(), args.proteins, params)
-            s2 = r.stats
-            e_lookups += s2.num_kmers
-            d2h = s2.num_calls * kg.CALL_DTYPE.itemsize + args.proteins * kg.OTU_DTYPE.itemsize + 64
-            r.free()
-        barrier(torch, dist, local)
-        edt = all_max(torch, dist, time.perf_counter() - t0, local)
-        clocks.window(w0, time.time())
-        e2e = {"value": all_sum(torch, dist, float(e_lookups), local) / edt, "unit": "lookups/s",
-               "h2d_bytes_per_step": int(total + 8 * (args.proteins + 1)), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * edt / args.steps}
+        # the library's ingest form: toAminoAcidOff codes, 8 per 5 bytes (kg_pack_aa; packing is host work OUTSIDE the call,
+        # like FASTA parsing -- its rate is reported as pack_GBps)
+        h_goff = torch.empty(args.proteins + 1, dtype=torch.int64, pin_memory=True)
+        kg._check(kg.lib().kg_pack_aa(h_seq.data_ptr(), h_off.data_ptr(), args.proteins, None, h_goff.data_ptr(), 1))
+        ngroups = int(h_goff[-1])
+        h_pk = torch.empty(5 * ngroups + 64, dtype=torch.uint8, pin_memory=True)
+        pack_threads = min(os.cpu_count() or 1, 16)
+        tp = time.perf_counter()
+        kg._check(kg.lib().kg_pack_aa(h_seq.data_ptr(), h_off.data_ptr(), args.proteins, h_pk.data_ptr(), h_goff.data_ptr(), pack_threads))
+        pack_s = time.perf_counter() - tp
 
-        # The same end-to-end call from TWO host threads, each with its own context (streams, scratch, pools) and its own
+        def d2h_bytes(s):   # what the call copies back per step: dense calls + a count byte per protein (+ the used OTU pairs, below)
+            return int(s.num_calls * kg.CALL_DTYPE.itemsize + args.proteins)
+
+        def pk_call():
+            return ctx.run_packed_aa_ptr(table, h_pk.data_ptr(), h_goff.data_ptr(), args.proteins, params)
+
+        def raw_call():
+            return ctx.run_ptr(table, kg.MODE_AA, h_seq.data_ptr(), h_off.data_ptr(), args.proteins, params)
+
+        r0 = pk_call()
+        n_entries = len(r0.otus_compact[1])
+        r0.free()
+        edt, e_lookups, s2 = timed_calls(plumb, clocks, args.steps, warm, pk_call)
+        e2e = {"value": plumb.reduce([float(e_lookups)])[0] / edt, "unit": "lookups/s",
+               "h2d_bytes_per_step": int(5 * ngroups + 8 * (args.proteins + 1)),
+               "d2h_bytes_per_step": d2h_bytes(s2) + 8 * n_entries, "ms_per_step": 1e3 * edt / args.steps,
+               "call": "kg_run_packed_aa: 5-bit residue codes (kg_pack_aa) in, calls + compact OTU counts out",
+               "pack_GBps": round(total / pack_s / 1e9, 2), "pack_threads": pack_threads}
+        log(f"e2e (packed): {e2e['value']:.3e} lookups/s")
+        rdt, r_lookups, s3 = timed_calls(plumb, clocks, args.steps, warm, raw_call)
+        e2e["raw_bytes_call"] = {"value": plumb.reduce([float(r_lookups)])[0] / rdt, "unit": "lookups/s", "ms_per_step": 1e3 * rdt / args.steps,
+                                 "h2d_bytes_per_step": int(total + 8 * (args.proteins + 1)), "d2h_bytes_per_step": d2h_bytes(s3) + 8 * n_entries,
+                                 "call": "kg_run: one byte per residue, as FastaCallback.nextEntry receives them (KGJ:780)"}
+        # The same packed call from TWO host threads, each with its own context (streams, scratch, pools) and its own
         # pinned buffers, alternating steps: the copies of one call overlap the kernels of the other.  Reported next to
         # `e2e` (which stays the single synchronous call); every step still moves its inputs in and its records out.
         if not args.no_e2e2:
-            import threading
             ctx2 = kg.Context(local)
             table.attach(ctx2)
-            h_seq2 = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
-            h_seq2.copy_(h_seq)
-            lanes = [(ctx, h_seq), (ctx2, h_seq2)]
+            h_pk2 = torch.empty(5 * ngroups + 64, dtype=torch.uint8, pin_memory=True)
+            h_pk2.copy_(h_pk)
+            lanes = [(ctx, h_pk), (ctx2, h_pk2)]
             counts = [0, 0]
 
             def lane(k, nsteps):
-                c, hs = lanes[k]
+                c, hp = lanes[k]
                 for _ in range(nsteps):
-                    r2 = c.run_ptr(table, kg.MODE_AA, hs.data_ptr(), h_off.data_ptr(), args.proteins, params)
+                    r2 = c.run_packed_aa_ptr(table, hp.data_ptr(), h_goff.data_ptr(), args.proteins, params)
                     counts[k] += r2.stats.num_kmers
                     r2.free()
 
@@ -255,20 +277,22 @@ def run_ours(args):
 
             both(6)
             counts[:] = [0, 0]
-            barrier(torch, dist, local)
+            plumb.barrier()
             w0 = time.time()
             t0 = time.perf_counter()
             both(args.steps)
-            barrier(torch, dist, local)
-            edt2 = all_max(torch, dist, time.perf_counter() - t0, local)
+            plumb.barrier()
+            edt2 = plumb.reduce([time.perf_counter() - t0], "MAX")[0]
             clocks.window(w0, time.time())
-            e2e["two_threads"] = {"value": all_sum(torch, dist, float(sum(counts)), local) / edt2, "unit": "lookups/s",
+            e2e["two_threads"] = {"value": plumb.reduce([float(sum(counts))])[0] / edt2, "unit": "lookups/s",
                                   "ms_per_step": 1e3 * edt2 / args.steps,
                                   "note": "two host threads, one context each, alternate the steps (same bytes in and out per step)"}
             ctx2.close()
-
+            del h_pk2
+        del h_seq, h_off, h_pk, h_goff
+        log("e2e done")
     clk = clocks.stop()
-    log("e2e done")
+
     # ---- rooflines ----
     hbm_peak, peak_src = measured_peaks()
     probe_s = float(np.mean(probe_ms)) * 1e-3
@@ -279,58 +303,87 @@ def run_ours(args):
         for tpb, infl in ((256, 4), (256, 8), (512, 4), (1024, 2), (128, 8)):
             r_probe = max(r_probe, bl.probe_roofline_table(ctx, table, 1 << 28, tpb, infl))
     traffic, traffic_src = None, None
-    try:    # dram__bytes_read.sum + dram__bytes_write.sum of k_probe from the committed `ncu --set full` capture of this workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tj["signatures"] == int(nsig) and tj["proteins"] == args.proteins:
-            traffic, traffic_src = tj["k_probe_dram_bytes_per_launch"], tj["source"]
-    except Exception:
-        pass
+    for name in ("r02_traffic.json", "r01_traffic.json"):  # dram__bytes_read.sum + dram__bytes_write.sum of the probe kernel, `ncu --set full`
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if tj["signatures"] == int(nsig) and tj["proteins"] == args.proteins:
+                traffic, traffic_src = tj["k_probe_dram_bytes_per_launch"], tj["source"]
+                break
+        except Exception:
+            pass
+    cascade = st.ms_filter > 0
     roofline = {"bound": "hbm", "achieved": round(achieved_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved_gbs / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": lookups_per_step * BYTES_PER_LOOKUP_AA, "peak_source": peak_src,
-                "kernel": "k_probe", "kernel_ms": round(probe_s * 1e3, 4),
+                "kernel": "k_filter + k_refilter + k_probe2 (probe cascade, three launches)" if cascade else "k_probe",
+                "kernel_ms": round(probe_s * 1e3, 4),
                 "bytes_per_lookup": BYTES_PER_LOOKUP_AA, "lookups_per_launch": lookups_per_step,
                 "probe_roofline_sectors_per_s": r_probe,
                 "frac_of_probe_roofline": round(lookups_per_step / probe_s / r_probe, 4) if r_probe else None,
                 "kernel_share_of_step": round(float(np.mean(probe_ms)) / float(np.mean(dev_ms)), 4)}
 
-    # ---- CPU baseline + parity on the sample (rank 0, N=1 only) ----
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- CPU baseline + parity on the whole step (rank 0, N=1 only) ----
+    cpu = parity = full = None
+    otable = None
+    threads = os.cpu_count() or 1
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    if want_cpu:
         from oracle import kgo
+        from tests.parity import assert_same
         kgo.build()
-        threads = os.cpu_count() or 1
         num_slots = 3 * nsig + 1  # load 1/3: at 1/2 the reference hash (key % numSigs) clusters so badly that no prime near 2n avoids running off the end
         t0 = time.time()
         log("roofline done; building the reference-format image for the CPU baseline")
         img = bl.synth_reference_image(ctx, dk, dp, nsig, num_slots)
         num_slots = int(img[:8].view(np.int64)[0])
         otable = kgo.Table(borrow=img)
-        log("image on host")
         t_img = time.time() - t0
-        nsample = args.cpu_sample or min(args.proteins, 64000 * threads)
-        sb, off = sample_host(kg, ctx, ds, do, nsample)
-        ref, secs = cpu_reference_run(kgo, otable, sb, off, threads)
-        log(f"cpu baseline done in {secs:.1f}s")
+        log("image on host")
+        nsample = args.cpu_sample or args.proteins
+        sb, off = sample_host(ctx, ds, do, nsample)
+        t0 = time.time()
+        ref = kgo.run(otable, kgo.make_params(aa=True), sb, off, kgo.STREAM_JOIN, threads=threads)
+        secs = time.time() - t0
+        log(f"cpu baseline (reference algorithm, {threads} shards) done in {secs:.1f}s")
         cpu = {"value": ref.num_kmers / secs, "unit": "lookups/s", "cores": threads, "kind": "port",
                "sample": f"first {nsample} proteins of the step ({ref.num_kmers} lookups) against the full table in the "
                          f"reference's own 24-byte-slot format ({num_slots} slots); reference algorithm (comparator sort + "
                          f"one pass over the table stream, KGJ:944-1034) run as {threads} independent single-threaded shards; "
                          f"{secs:.1f} s; C port of the Java (no JVM in this image)",
                "image_build_s": round(t_img, 1)}
-        # parity of the same sample: GPU calls / OTU counts vs the oracle's, bit for bit
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from tests.parity import assert_same
+        # parity of the same sample: GPU hits / calls / OTU counts vs the oracle's, bit for bit -- through BOTH host calls
         g = ctx.run(table, kg.MODE_AA, sb, off, kg.default_params(emit_hits=1))
-        assert_same(g, ref, what="bench sample")
-        parity = f"bit-exact on the {nsample}-protein sample: {len(ref.hits)} hits, {len(ref.calls)} calls"
+        assert_same(g, ref, what="bench sample (kg_run)")
         g.free()
+        pk, goff = kg.pack_aa(sb, off, threads=min(threads, 16))
+        g = ctx.run_packed_aa(table, pk, goff, kg.default_params(emit_hits=1))
+        assert_same(g, ref, what="bench sample (kg_run_packed_aa)")
+        g.free()
+        del pk, goff
+        parity = (f"bit-exact on the {nsample}-protein sample, kg_run and kg_run_packed_aa: {len(ref.hits)} hits, "
+                  f"{len(ref.calls)} calls, OTU counts")
+        # SURVEY 8(d) asks for two more CPU rows: the reference algorithm on ONE thread (what KmerGutsJava really is: no Thread /
+        # executor anywhere in KGJ) and a best-effort direct-probe variant on all host cores
+        n1 = max(1000, nsample // 16)
+        off1 = off[:n1 + 1].copy()
+        t0 = time.time()
+        r1 = kgo.run(otable, kgo.make_params(aa=True), sb[:int(off1[-1])], off1, kgo.STREAM_JOIN, threads=1)
+        s1 = time.time() - t0
+        cpu["single_thread"] = {"value": r1.num_kmers / s1, "unit": "lookups/s", "cores": 1,
+                                "sample": f"first {n1} proteins ({r1.num_kmers} lookups), same table; the one pass over the "
+                                          f"{num_slots}-slot table stream is paid whatever the batch size (KGJ:992-999); {s1:.1f} s"}
+        t0 = time.time()
+        r2 = kgo.run(otable, kgo.make_params(aa=True), sb, off, kgo.DIRECT_PROBE, threads=threads)
+        s2_ = time.time() - t0
+        assert len(r2.calls) == len(ref.calls) and r2.num_kmers == ref.num_kmers
+        cpu["direct_probe_all_cores"] = {"value": r2.num_kmers / s2_, "unit": "lookups/s", "cores": threads,
+                                         "sample": f"the same {nsample} proteins, in-memory linear probing of the same 24-byte-slot "
+                                                   f"table instead of the stream join (not the reference's algorithm: best-effort CPU); {s2_:.1f} s"}
+        log("cpu rows done")
+        del ref, r1, r2, sb, off
 
-    # ---- size-independent property at FULL size: lookups, hits and a checksum over every hit's (position, payload) must
-    # equal those of the naive one-thread-per-position kernel (no prefilter, no queue, byte-wise reads, full table lookup)
-    full = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # size-independent property at FULL size: lookups, hits and a checksum over every hit's (position, payload) must
+        # equal those of the naive one-thread-per-position kernel (no prefilter, no queue, byte-wise reads, full table lookup)
         valid, nh, chk = bl.naive_scan_aa(ctx, table, ds, do, args.proteins, total)
         g = ctx.run_batch(table, batch, kg.default_params(emit_hits=1))
         gs = g.stats
@@ -341,38 +394,60 @@ def run_ours(args):
         full = f"lookups ({valid}), hits ({nh}) and hit checksum equal the naive kernel's on all {args.proteins} proteins"
         log("full-size cross-check done")
 
+    # ---- the other BASELINE.json configs, reduced-time legs (bench_legs.py) ----
+    leg_out = {}
+    which = set() if args.no_legs else set(args.legs.split(","))
+    lsteps = max(3, min(args.steps, 10))
+    if "2" in which:
+        leg_out["configs2"] = legs.configs2(kg, ctx, table, u, plumb, steps=lsteps, otable=otable,
+                                            parity_genomes=50 if otable is not None else 0, threads=threads, log=log)
+        log("configs2 leg done")
+    if "3" in which:
+        leg_out["configs3"] = legs.configs3(kg, ctx, table, u, plumb, orfs=args.orfs, otable=otable, threads=threads, log=log)
+        log("configs3 leg done")
+    stats_keep = {"hits": int(st.num_hits), "calls": int(st.num_calls), "prepare": st.ms_prepare, "probe": st.ms_probe, "group": st.ms_group,
+                  "device": st.ms_device, "filter": st.ms_filter, "refilter": st.ms_refilter, "lines": st.ms_lines,
+                  "s1": int(st.num_survivors1), "s2": int(st.num_survivors2)}
+    batch.free()
+    table.free()
+    otable = None
+    for p in (dk, dp, ds, do):
+        bl.device_free(p)
+    if "4" in which:
+        leg_out["configs4"] = legs.configs4(kg, ctx, plumb, proteins=args.proteins, steps=lsteps, families=args.c4_families, log=log)
+        log("configs4 leg done")
+
     if rank == 0:
         out = {
             "metric": "8-mer lookups/sec", "value": value, "unit": "lookups/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic 200M-signature table, 1M random-length synthetic proteins, protein mode",
-                       "signatures": int(nsig), "families": args.families, "proteins_per_gpu": args.proteins,
-                       "residues_per_gpu": int(total), "table_replicated": True,
-                       "l2": "inputs larger than L2 (table %.2f GB, residues %.2f GB per step); no flush" % (ti.device_bytes / 1e9, total / 1e9),
+            "config": workload_config(args, nsig, total),
+            "detail": {"l2": "inputs larger than L2 (table %.2f GB, residues %.2f GB per step); no flush" % (ti.device_bytes / 1e9, total / 1e9),
                        "table_buckets": int(ti.num_buckets), "table_flagged_buckets": int(ti.flagged_buckets),
-                       "hits_per_step": int(st.num_hits), "calls_per_step": int(st.num_calls)},
-            "proteins_per_s": total_proteins / dt,
+                       "hits_per_step": stats_keep["hits"], "calls_per_step": stats_keep["calls"]},
+            "proteins_per_s": float(args.proteins * args.steps * world) / dt,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity, "parity_full_size": full, "prep": prep,
-            "stage_ms": {"prepare": round(st.ms_prepare, 4), "probe": round(st.ms_probe, 4), "group": round(st.ms_group, 4),
-                         "device_total": round(st.ms_device, 4), "probe_filter": round(st.ms_filter, 4),
-                         "probe_refilter": round(st.ms_refilter, 4), "probe_lines": round(st.ms_lines, 4),
-                         "survivors_filter1": int(st.num_survivors1), "survivors_filter2": int(st.num_survivors2)},
+            "stage_ms": {"prepare": round(stats_keep["prepare"], 4), "probe": round(stats_keep["probe"], 4),
+                         "group": round(stats_keep["group"], 4), "device_total": round(stats_keep["device"], 4)},
         }
+        if cascade:
+            out["stage_ms"].update({"probe_filter": round(stats_keep["filter"], 4), "probe_refilter": round(stats_keep["refilter"], 4),
+                                    "probe_lines": round(stats_keep["lines"], 4), "survivors_filter1": stats_keep["s1"],
+                                    "survivors_filter2": stats_keep["s2"]})
+        out.update(leg_out)
         print(json.dumps(out))
-    batch.free()
-    table.free()
-    for p in (dk, dp, ds, do):
-        bl.device_free(p)
     ctx.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def run_reference(args):
-    """The reference's CPU algorithm (C port: no JVM here) on the host cores, same config / metric / unit.  The GPU is
-    used only OUTSIDE the timed region, to generate the synthetic inputs in the reference's own table format."""
+    """The reference's CPU algorithm (C port: no JVM here) on the host cores: same config / metric / unit, and every step is the
+    WHOLE 1M-protein batch of configs[1].  The GPU is used only OUTSIDE the timed region, to generate the synthetic inputs in
+    the reference's own table format (tools/benchlib); nothing of the product path runs inside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -389,29 +464,32 @@ def run_reference(args):
     bl.device_free(dp)
     otable = kgo.Table(borrow=img)
     threads = os.cpu_count() or 1
-    nsample = args.cpu_sample or min(args.proteins, 16000 * threads)
-    ds, do, total = bl.synth_proteins(ctx, u, 0, nsample, seed=1)
-    sb, off = sample_host(kg, ctx, ds, do, nsample)
+    nsample = args.cpu_sample or args.proteins
+    ds, do, total = bl.synth_proteins(ctx, u, 0, args.proteins, seed=1)
+    sb, off = sample_host(ctx, ds, do, nsample)
     bl.device_free(ds)
     bl.device_free(do)
     ctx.close()
-    for _ in range(args.warmup):
-        cpu_reference_run(kgo, otable, sb, off, threads)
+
+    def step():
+        return kgo.run(otable, kgo.make_params(aa=True), sb, off, kgo.STREAM_JOIN, threads=threads)
+
+    warm = min(args.warmup, 1)   # CPU code has nothing to warm beyond the page cache: one untimed step is plenty
+    for _ in range(warm):
+        step()
     t0 = time.perf_counter()
     lookups = 0
     for _ in range(args.steps):
-        ref, _ = cpu_reference_run(kgo, otable, sb, off, threads)
-        lookups += ref.num_kmers
+        lookups += step().num_kmers
     dt = time.perf_counter() - t0
     value = lookups / dt
-    sample = (f"each step = first {nsample} proteins of configs[1] ({lookups // args.steps} lookups) against the full "
-              f"{nsig}-signature table in the reference's 24-byte-slot format ({num_slots} slots)")
+    sample = (f"each step = {'all' if nsample == args.proteins else 'the first'} {nsample} proteins of configs[1] "
+              f"({lookups // args.steps} lookups) against the full {nsig}-signature table in the reference's 24-byte-slot format ({num_slots} slots)")
     print(json.dumps({
         "impl": "reference", "metric": "8-mer lookups/sec", "value": value, "unit": "lookups/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "configs[1]: synthetic 200M-signature table, 1M random-length synthetic proteins, protein mode",
-                   "signatures": int(nsig), "families": args.families, "proteins_per_step": nsample},
+        "config": workload_config(args, nsig, total),
         "cpu_baseline": {"value": value, "unit": "lookups/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "reference algorithm (comparator sort + one pass over the table stream, KGJ:944-1034) as "
                                  f"{threads} independent single-threaded shards; C port of the Java (no JVM in this image)"},

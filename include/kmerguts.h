@@ -82,6 +82,11 @@ typedef struct kg_otu {
     int32_t oI[KG_OI_BUFSZ];
 } kg_otu;
 
+typedef struct kg_otu_entry { /* one used slot of the OTU buffer (OtuCount, KGJ:1221-1224) */
+    int32_t count;
+    int32_t oI;
+} kg_otu_entry;
+
 /* One table hit (Hit, KGJ:1213-1219, plus its container), sorted by (seq, strand_frame, pos). */
 typedef struct kg_hit {
     uint32_t seq;
@@ -159,6 +164,18 @@ void kg_params_default(kg_params* p);
 int kg_run(kg_context* ctx, const kg_table* table, int mode, const uint8_t* seq_bytes, const uint64_t* offsets,
            size_t n, const kg_params* params, kg_result** result);
 
+/* The same call for proteins that are ALREADY residue codes, 5 bits each (the host feed, ~1 byte per lookup
+ * over PCIe, is the bottleneck of the end-to-end call).  prepareQuery maps every character through toAminoAcidOff before
+ * addKmers sees it (KGJ:1055-1058); kg_pack_aa does that mapping on the host and packs 8 codes into 5 bytes:
+ *   code 0..19 = residue (PROT_ALPHA order, KGJ:94-96), 20 = any other character (KGJ:173), 31 = padding.
+ * Sequence s occupies groups [group_offsets[s], group_offsets[s+1]) of 5 bytes, kg_pack_aa_groups(len) = ceil((len+1)/8) of
+ * them: at least one padding code follows the last residue.  Results are identical to kg_run on the original characters.
+ * kg_pack_aa with packed == NULL only fills group_offsets (so the caller can size `packed`: 5 * group_offsets[n] bytes). */
+uint64_t kg_pack_aa_groups(uint64_t len);
+int kg_pack_aa(const uint8_t* seq_bytes, const uint64_t* offsets, size_t n, uint8_t* packed, uint64_t* group_offsets, int threads);
+int kg_run_packed_aa(kg_context* ctx, const kg_table* table, const uint8_t* packed, const uint64_t* group_offsets, size_t n,
+                     const kg_params* params, kg_result** result);
+
 /* Split form: keep the sequences resident in HBM and run the device pipeline on them (possibly many times). */
 int kg_batch_upload(kg_context* ctx, int mode, const uint8_t* seq_bytes, const uint64_t* offsets, size_t n,
                     kg_batch** batch);
@@ -176,6 +193,10 @@ int kg_result_fetch(kg_result* result); /* D2H of calls, OTU counts and (if requ
 int kg_result_stats(const kg_result* result, kg_run_stats* stats);
 int kg_result_calls(kg_result* result, const kg_call** calls, size_t* n);
 int kg_result_otus(kg_result* result, const kg_otu** otus, size_t* n); /* one per sequence */
+/* The same counts without the unused slots: n_per_seq[s] entries belong to sequence s, in buffer order, consecutively in
+ * `entries`.  This is the form kg_run / kg_run_packed_aa copy back from the GPU (most sequences use 0-2 of the 5 slots);
+ * kg_result_otus expands it on first use. */
+int kg_result_otus_compact(kg_result* result, const uint8_t** n_per_seq, const kg_otu_entry** entries, size_t* n_seqs, size_t* n_entries);
 int kg_result_hits(kg_result* result, const kg_hit** hits, size_t* n); /* needs params.emit_hits */
 void kg_result_free(kg_result* result);
 

@@ -21,6 +21,7 @@ MODE_DNA, MODE_AA = 0, 1
 CALL_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("start", "<i4"), ("end", "<i4"), ("count", "<i4"), ("fI", "<i4"),
                        ("weighted", "<f4"), ("hits_before", "<i4")])
 OTU_DTYPE = np.dtype([("n", "<i4"), ("count", "<i4", (5,)), ("oI", "<i4", (5,))])
+OTU_ENTRY_DTYPE = np.dtype([("count", "<i4"), ("oI", "<i4")])
 HIT_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("pos", "<i4"), ("oI", "<i4"), ("avg", "<i4"), ("fI", "<i4"),
                       ("wt", "<f4")])
 
@@ -28,7 +29,7 @@ HIT_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("pos", "<i4"), ("oI", "<i4
 EXPORTS = [
     "kg_init", "kg_shutdown", "kg_last_error", "kg_version",
     "kg_table_load", "kg_table_load_file", "kg_table_from_image", "kg_table_from_device_entries", "kg_table_get_info",
-    "kg_table_save", "kg_table_load_cached", "kg_table_load_cached_checked", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
+    "kg_table_save", "kg_table_load_cached", "kg_table_load_cached_checked", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_run_packed_aa", "kg_pack_aa", "kg_pack_aa_groups", "kg_result_otus_compact", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
     "kg_batch_run", "kg_result_fetch", "kg_result_stats", "kg_result_calls", "kg_result_otus", "kg_result_hits",
     "kg_result_free",
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
@@ -97,6 +98,9 @@ def lib() -> C.CDLL:
         "kg_table_load_cached_checked": (i32, [vp, C.c_char_p, C.c_char_p, pp]),
         "kg_params_default": (None, [C.POINTER(Params)]),
         "kg_run": (i32, [vp, vp, i32, vp, vp, sz, C.POINTER(Params), pp]),
+        "kg_run_packed_aa": (i32, [vp, vp, vp, vp, sz, C.POINTER(Params), pp]),
+        "kg_pack_aa": (i32, [vp, vp, sz, vp, vp, i32]), "kg_pack_aa_groups": (u64, [u64]),
+        "kg_result_otus_compact": (i32, [vp, pp, pp, C.POINTER(sz), C.POINTER(sz)]),
         "kg_batch_upload": (i32, [vp, i32, vp, vp, sz, pp]),
         "kg_batch_from_device": (i32, [vp, i32, vp, vp, sz, u64, pp]), "kg_batch_free": (None, [vp]),
         "kg_batch_run": (i32, [vp, vp, vp, C.POINTER(Params), pp]), "kg_result_fetch": (i32, [vp]),
@@ -129,6 +133,18 @@ def lib() -> C.CDLL:
 def _check(rc: int):
     if rc != 0:
         raise KgError(rc, lib().kg_last_error().decode(errors="replace"))
+
+
+def pack_aa(seq_bytes: np.ndarray, offsets: np.ndarray, threads: int = 1):
+    """kg_pack_aa: (packed uint8[5 * groups], group_offsets uint64[n+1]) -- toAminoAcidOff codes, 8 per 5 bytes."""
+    seq_bytes = np.ascontiguousarray(seq_bytes, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    goff = np.zeros(n + 1, dtype=np.uint64)
+    _check(lib().kg_pack_aa(seq_bytes.ctypes.data, offsets.ctypes.data, n, None, goff.ctypes.data, 1))
+    packed = np.empty(5 * int(goff[-1]), dtype=np.uint8)
+    _check(lib().kg_pack_aa(seq_bytes.ctypes.data, offsets.ctypes.data, n, packed.ctypes.data, goff.ctypes.data, threads))
+    return packed, goff
 
 
 def default_params(**kw) -> Params:
@@ -220,6 +236,17 @@ class Context:
     def run_ptr(self, table: "Table", mode: int, seq_ptr: int, off_ptr: int, n: int, params: Params) -> "Result":
         h = C.c_void_p()
         _check(lib().kg_run(self._h, table._h, mode, seq_ptr, off_ptr, n, C.byref(params), C.byref(h)))
+        return Result(h)
+
+    def run_packed_aa(self, table: "Table", packed: np.ndarray, group_offsets: np.ndarray, params: Params) -> "Result":
+        """kg_run for proteins in the 5-bit packed form of pack_aa()."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        group_offsets = np.ascontiguousarray(group_offsets, dtype=np.uint64)
+        return self.run_packed_aa_ptr(table, packed.ctypes.data, group_offsets.ctypes.data, len(group_offsets) - 1, params)
+
+    def run_packed_aa_ptr(self, table: "Table", packed_ptr: int, goff_ptr: int, n: int, params: Params) -> "Result":
+        h = C.c_void_p()
+        _check(lib().kg_run_packed_aa(self._h, table._h, packed_ptr, goff_ptr, n, C.byref(params), C.byref(h)))
         return Result(h)
 
     def upload(self, mode: int, seq_bytes: np.ndarray, offsets: np.ndarray) -> "Batch":
@@ -365,6 +392,13 @@ class Result:
     @property
     def hits(self) -> np.ndarray:
         return self._arr(lib().kg_result_hits, HIT_DTYPE)
+
+    @property
+    def otus_compact(self):
+        """(n_per_seq uint8[n], entries [(count, oI)]): the OTU counts without the unused slots (kg_result_otus_compact)."""
+        pn, pe, ns, ne = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+        _check(lib().kg_result_otus_compact(self._h, C.byref(pn), C.byref(pe), C.byref(ns), C.byref(ne)))
+        return _view(pn.value, ns.value, np.dtype("u1")), _view(pe.value, ne.value, OTU_ENTRY_DTYPE)
 
     def fetch(self):
         _check(lib().kg_result_fetch(self._h))

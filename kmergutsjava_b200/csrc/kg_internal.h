@@ -32,6 +32,8 @@ struct kg_batch {
     uint64_t* d_off = nullptr; // n+1
     bool owns_input = true;
     DevBuf seq_buf, off_buf;  // pooled storage behind d_seq / d_off when owns_input
+    DevBuf pk_buf;            // packed protein input (kg_run_packed_aa): the 5-bit form as uploaded, unpacked into seq_buf
+    bool padded = false;      // ... in which every sequence is padded with zero bytes to a multiple of 8 positions
     // derived by prepare(): virtual sequences
     uint64_t nv = 0;          // n (aa) or 6n (dna)
     uint64_t vtotal = 0;      // residue-stream length
@@ -55,6 +57,12 @@ struct kg_result {
     DevBuf d_hits;    // kg_hit[num_hits] when params.emit_hits
     // host
     HostBuf h_calls, h_otus, h_hits; // pinned, from the context's pool
+    // compact OTU counts (kg_run / kg_run_packed_aa bring these home instead of 44 bytes per sequence)
+    DevBuf d_otu_n, d_otu_entries;   // uint8 per sequence, kg_otu_entry per used buffer entry
+    HostBuf h_otu_n, h_otu_entries;
+    uint64_t num_otu_entries = 0;
+    bool want_compact_otus = false;  // pipe_enqueue: also build the compact form
+    bool otus_compact = false;       // the host holds the compact form (h_otus is then filled on demand)
     bool fetched = false;
 };
 

@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <functional>
+#include <thread>
+#include <vector>
 #include <chrono>
 
 #include "kg_device.cuh"
@@ -69,10 +71,67 @@ __global__ void k_patch_aa(uint8_t* __restrict__ seq, const uint64_t* __restrict
     if (b > a) seq[b - 1] = 0;
 }
 
-// offsets of a slice of a larger batch -> offsets relative to the slice
-__global__ void k_rebase(uint64_t* __restrict__ off, uint64_t n1, uint64_t base) {
+// offsets of a slice of a larger batch -> offsets relative to the slice (scale = 8 turns group offsets of the packed
+// form into residue offsets)
+__global__ void k_rebase(uint64_t* __restrict__ off, uint64_t n1, uint64_t base, uint64_t scale) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n1) off[i] -= base;
+    if (i < n1) off[i] = (off[i] - base) * scale;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed protein input (include/kmerguts.h, kg_pack_aa): 8 residue codes in 5 bytes.  One thread turns one group back into
+// 8 stream bytes that the encoder's LUT reads exactly like the original characters: codes 0..19 -> the letter,
+// 20 (anything toAminoAcidOff maps to 20, KGJ:111-175) -> 'X', 31 (padding after the last residue) -> 0 (separator).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_unpack_aa(const uint8_t* __restrict__ packed, uint64_t ngroups, uint2* __restrict__ stream8) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const uint8_t* p = packed + 5 * g;
+    uint64_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) bits |= (uint64_t)p[i] << (8 * i);
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t c = (uint32_t)(bits >> (5 * i)) & 31u;
+        const uint32_t ch = c < 20u ? (uint32_t)"ACDEFGHIKLMNPQRSTVWY"[c] : (c == 31u ? 0u : (uint32_t)'X');
+        w[i >> 2] |= ch << (8 * (i & 3));
+    }
+    stream8[g] = make_uint2(w[0], w[1]);
+}
+// the padded layout of the packed form: the last residue of a protein is the last non-zero byte of its (multiple-of-8) span
+__global__ void k_patch_aa_padded(uint8_t* __restrict__ seq, const uint64_t* __restrict__ off, uint64_t n) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint64_t a = off[s];
+    uint64_t b = off[s + 1];
+    for (int k = 0; k < 9 && b > a && seq[b - 1] == 0; k++) b--;
+    if (b > a) seq[b - 1] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// OTU-COUNTS records for the trip home: most proteins carry 0-2 of the 5 entries, so kg_run copies one count byte per
+// sequence plus the used (count, oI) pairs instead of 44 bytes per sequence.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_otu_counts(const kg_otu* __restrict__ otus, uint64_t n, uint32_t* __restrict__ cnt, uint8_t* __restrict__ cnt8,
+                             const unsigned long long* __restrict__ ctr) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    // a pass whose hit buffers overflowed is repeated by the host: the FSM has not written its records then
+    const uint32_t c = (s < n && !ctr[KG_CTR_OVERFLOW]) ? min((uint32_t)otus[s].n, (uint32_t)KG_OI_BUFSZ) : 0u;
+    cnt[s] = c;
+    if (s < n) cnt8[s] = (uint8_t)c;
+}
+__global__ void k_otu_pack(const kg_otu* __restrict__ otus, uint64_t n, const uint32_t* __restrict__ first, kg_otu_entry* __restrict__ out) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t o = first[s], c = first[s + 1] - o;
+    for (uint32_t k = 0; k < c; k++) {
+        kg_otu_entry e;
+        e.count = otus[s].count[k];
+        e.oI = otus[s].oI[k];
+        out[o + k] = e;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1257,6 +1316,7 @@ __global__ void k_emit_hits(const uint64_t* __restrict__ voff, uint64_t nv, int 
 constexpr int KG_MAX_PARTS = 16;
 struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them let slice s+1 queue up behind slice s
     DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
+    DevBuf otu_cnt, otu_first;                                   // kg_run: OTU entries per sequence and their exclusive scan
     DevBuf queue, tile_qcnt;                                     // probe cascade: survivors (8 KB slice per tile) and their counts
     DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
     DevBuf fk_a, fi_a;                                           // per-sequence path: class histogram / cursors, sequence permutation
@@ -1275,12 +1335,13 @@ struct RunScratch { // grow-only device scratch kept per context (so repeated ru
     PipeSlot slot[2];
     uint64_t hit_cap_seen = 0;   // hits of the largest run so far (+ slack): sizes the next run's buffers
     uint64_t calls_seen = 0;     // calls of the largest kg_run so far: sizes the pinned result buffer
+    uint64_t otu_entries_seen = 0; // likewise, (count, oI) pairs
 };
 RunScratch& scratch_of(kg_context* ctx) {
     if (!ctx->scratch) {
         RunScratch* sc = new RunScratch();
         for (auto& sl : sc->slot) {
-            cudaMallocHost(&sl.h_ctr, (KG_CTR_COUNT + 1) * sizeof(uint64_t));
+            cudaMallocHost(&sl.h_ctr, (KG_CTR_COUNT + 2) * sizeof(uint64_t)); // + call total, + OTU entry total
             for (auto& e : sl.ev) cudaEventCreate(&e);
             for (auto& e : sl.part_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         }
@@ -1435,7 +1496,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     RunScratch& sc = scratch_of(ctx);
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
-                          &sl.call_off, &sl.ctr, &sl.queue, &sl.tile_qcnt, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
+                          &sl.call_off, &sl.ctr, &sl.otu_cnt, &sl.otu_first, &sl.queue, &sl.tile_qcnt, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
                           &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_crank,
                           &sl.o_run_oi, &sl.o_run_crank})
             b->release();
@@ -1545,6 +1606,7 @@ extern "C" void kg_batch_free(kg_batch* b) {
     }
     pool_give_dev(b->ctx, &b->vseq);
     pool_give_dev(b->ctx, &b->voff);
+    pool_give_dev(b->ctx, &b->pk_buf);
     delete b;
 }
 
@@ -1555,7 +1617,10 @@ int kg_batch_prepare(kg_batch* b, cudaStream_t st, uint32_t* launches) {
         b->nv = b->n;
         b->vtotal = b->total;
         if (b->n) {
-            k_patch_aa<<<blocks_for(b->n, 256), 256, 0, st>>>(b->d_seq, b->d_off, b->n);
+            // k_patch_aa is idempotent (a repeated pass after a hit-buffer overflow patches again, harmlessly); the padded
+            // variant finds the last residue by its value, so it must run exactly once per batch
+            if (!b->padded) k_patch_aa<<<blocks_for(b->n, 256), 256, 0, st>>>(b->d_seq, b->d_off, b->n);
+            else if (!b->prepared) k_patch_aa_padded<<<blocks_for(b->n, 256), 256, 0, st>>>(b->d_seq, b->d_off, b->n);
             (*launches)++;
         }
         b->prepared = true;
@@ -1831,6 +1896,24 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
         sl.launches += 10;
         CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + cap, 4, cudaMemcpyDeviceToHost, st));
     }
+    sl.h_ctr[KG_CTR_COUNT + 1] = 0;
+    if (r->want_compact_otus && b->n) { // kg_run: the OTU counts go home as a count byte per sequence + the used pairs
+        const uint64_t ns = b->n;
+        KG_TRY(sl.otu_cnt.ensure((ns + 1) * 4));
+        KG_TRY(sl.otu_first.ensure((ns + 1) * 4));
+        auto need = [&](DevBuf* buf, size_t bytes) -> int {
+            if (buf->cap >= bytes) return KG_OK;
+            pool_give_dev(ctx, buf);
+            return pool_take_dev(ctx, bytes, buf);
+        };
+        KG_TRY(need(&r->d_otu_n, ns));
+        KG_TRY(need(&r->d_otu_entries, std::max<uint64_t>(std::min<uint64_t>(ns * KG_OI_BUFSZ, hit_cap), 1024) * sizeof(kg_otu_entry)));
+        k_otu_counts<<<blocks_for(ns + 1, 256), 256, 0, st>>>(r->d_otus.as<kg_otu>(), ns, sl.otu_cnt.as<uint32_t>(), r->d_otu_n.as<uint8_t>(), d_ctr);
+        KG_TRY(exclusive_sum_u32(ctx, sl.otu_cnt.as<uint32_t>(), sl.otu_first.as<uint32_t>(), ns + 1, st));
+        k_otu_pack<<<blocks_for(ns, 256), 256, 0, st>>>(r->d_otus.as<kg_otu>(), ns, sl.otu_first.as<uint32_t>(), r->d_otu_entries.as<kg_otu_entry>());
+        CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT + 1], sl.otu_first.as<uint32_t>() + ns, 4, cudaMemcpyDeviceToHost, st));
+        sl.launches += 3;
+    }
     cudaEventRecord(sl.ev[3], st);
     return KG_OK;
 }
@@ -1951,9 +2034,13 @@ extern "C" int kg_result_fetch(kg_result* r) {
 // are independent, KGJ:528/540); slice i+1 is copied to the device (copy stream) while slice i runs (compute stream) and
 // the records of slice i-1 travel back (third stream), so the end-to-end time approaches max(H2D, device) instead of
 // their sum.  Pinned caller buffers make the copies truly asynchronous; pageable ones still work.
-extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const uint8_t* seq_bytes, const uint64_t* offsets,
-                      size_t n, const kg_params* params, kg_result** out) {
+// `packed`: seq_bytes / offsets are the 5-bit form of kg_pack_aa (offsets in groups of 8 residues = 5 bytes); the slice is
+// unpacked on the device into the same residue stream (every sequence padded to a multiple of 8 positions).
+static int run_host_impl(kg_context* ctx, const kg_table* table, int mode, bool packed, const uint8_t* seq_bytes, const uint64_t* offsets,
+                         size_t n, const kg_params* params, kg_result** out) {
     if (!ctx || !table || !out || !offsets || (mode != KG_MODE_AA && mode != KG_MODE_DNA)) KG_FAIL(KG_EINVAL, "kg_run: bad argument");
+    if (packed && mode != KG_MODE_AA) KG_FAIL(KG_EINVAL, "kg_run_packed_aa: protein mode only");
+    const uint64_t unit_pos = packed ? 8 : 1; // stream positions per offset unit (a group of the packed form = 5 bytes = 8 positions)
     if (table->shard_count > 1) KG_FAIL(KG_EINVAL, "kg_run: the table is shard %d of %d; use kg_batch_run_sharded", table->shard_rank, table->shard_count);
     KG_TRY(check_params(params));
     if (offsets[0] != 0) KG_FAIL(KG_EINVAL, "kg_run: offsets[0] must be 0");
@@ -1966,7 +2053,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     // slice plan
     // about six slices per call, 24..96 MB of residues each (a slice costs ~0.4 ms of host-side API calls, so many
     // small slices would make the host the bottleneck; few large ones expose the first upload)
-    uint64_t target = std::min<uint64_t>(std::max<uint64_t>(offsets[n] / 6, 24ull << 20), 96ull << 20);
+    uint64_t target = std::min<uint64_t>(std::max<uint64_t>(offsets[n] * unit_pos / 6, 24ull << 20), 96ull << 20); // in stream positions
     uint64_t ramp = 8;
     if (mode == KG_MODE_DNA) {
         // Long contigs: every slice pays ~1.5 ms of latency-bound tails (the longest segment in k_fsm_seg, the OTU fold
@@ -1976,7 +2063,9 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     }
     if (const char* e = getenv("KG_SLICE_MB")) target = (uint64_t)atoll(e) << 20;
     if (target < 65536) target = 65536;
-    const uint64_t hard = mode == KG_MODE_AA ? KG_MAX_STREAM : KG_MAX_STREAM / 2 - 64 * (uint64_t)n; // dna: 2 residues per nucleotide
+    uint64_t hard = mode == KG_MODE_AA ? KG_MAX_STREAM : KG_MAX_STREAM / 2 - 64 * (uint64_t)n; // dna: 2 residues per nucleotide
+    target /= unit_pos; // from here on in offset units (groups when packed)
+    hard /= unit_pos;
     // the first slices are small (target/ramp, doubling): nothing can overlap the very first upload, so keep it short
     std::vector<size_t> cut{0};
     if (const char* e = getenv("KG_SLICE_RAMP")) ramp = std::max(1, atoi(e));
@@ -2004,7 +2093,7 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     // device records of finished slices stay alive until their D2H copies are done: a ring of KEEP slices, each fenced
     // by an event on the D2H stream, so that the buffers return to the pool (no cudaMalloc in steady state)
     constexpr int KEEP = 3;
-    DevBuf keep[KEEP][3];
+    DevBuf keep[KEEP][5];
     bool keep_used[KEEP] = {false, false, false};
     // uploads run UP-1 slices ahead of the compute stream: the copy engine never waits for a slice to finish
     constexpr size_t UP = 4;
@@ -2024,8 +2113,9 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         const size_t a = cut[s], b = cut[s + 1], cnt = b - a;
         for (size_t i = a; i < b; i++)
             if (offsets[i + 1] < offsets[i]) KG_FAIL(KG_EINVAL, "kg_run: offsets must be non-decreasing (at %zu)", i);
-        const uint64_t bytes = offsets[b] - offsets[a];
-        if (bytes > hard) KG_FAIL(KG_ERANGE, "kg_run: sequence %zu alone exceeds the per-call limit", a);
+        const uint64_t units = offsets[b] - offsets[a];
+        if (units > hard) KG_FAIL(KG_ERANGE, "kg_run: sequence %zu alone exceeds the per-call limit", a);
+        const uint64_t bytes = units * unit_pos; // residue-stream bytes of the slice
         kg_batch* bt = new kg_batch();
         bt->ctx = ctx;
         bt->mode = mode;
@@ -2047,14 +2137,26 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         }
         cudaStream_t cs = ctx->copy_stream;
         CU(cudaMemsetAsync(bt->d_seq + bytes, 0, 64, cs));
-        if (bytes) CU(cudaMemcpyAsync(bt->d_seq, seq_bytes + offsets[a], bytes, cudaMemcpyHostToDevice, cs));
+        if (packed) {
+            bt->padded = true;
+            KG_TRY(pool_take_dev(ctx, units * 5 + 64, &bt->pk_buf));
+            if (units) {
+                CU(cudaMemcpyAsync(bt->pk_buf.p, seq_bytes + 5 * offsets[a], units * 5, cudaMemcpyHostToDevice, cs));
+                k_unpack_aa<<<blocks_for(units, 256), 256, 0, cs>>>(bt->pk_buf.as<uint8_t>(), units, reinterpret_cast<uint2*>(bt->d_seq));
+            }
+        } else if (bytes) {
+            CU(cudaMemcpyAsync(bt->d_seq, seq_bytes + offsets[a], bytes, cudaMemcpyHostToDevice, cs));
+        }
         CU(cudaMemcpyAsync(bt->d_off, offsets + a, (cnt + 1) * 8, cudaMemcpyHostToDevice, cs));
-        if (offsets[a]) k_rebase<<<blocks_for(cnt + 1, 256), 256, 0, cs>>>(bt->d_off, cnt + 1, offsets[a]);
+        if (offsets[a] || packed) k_rebase<<<blocks_for(cnt + 1, 256), 256, 0, cs>>>(bt->d_off, cnt + 1, offsets[a], packed ? 8 : 1);
         CU(cudaEventRecord(ctx->up_ev[s % UP], cs));
         return KG_OK;
     };
 
-    if ((rc = pool_take_host(ctx, std::max<size_t>(n, 1) * sizeof(kg_otu), &R->h_otus)) != KG_OK) return fail(rc);
+    // OTU counts travel home compact: a count byte per sequence + the used (count, oI) pairs (kg_result_otus expands on demand)
+    if ((rc = pool_take_host(ctx, std::max<size_t>(n, 1), &R->h_otu_n)) != KG_OK) return fail(rc);
+    if ((rc = pool_take_host(ctx, std::max<uint64_t>(sc.otu_entries_seen + sc.otu_entries_seen / 4, 1u << 16) * sizeof(kg_otu_entry), &R->h_otu_entries)) != KG_OK) return fail(rc);
+    uint64_t nentries = 0;
     if ((rc = pool_take_host(ctx, std::max<uint64_t>(sc.calls_seen + sc.calls_seen / 4, 1u << 16) * sizeof(kg_call), &R->h_calls)) != KG_OK) return fail(rc);
     if (params->emit_hits && (rc = pool_take_host(ctx, std::max<uint64_t>(sc.hit_cap_seen, 1u << 16) * sizeof(kg_hit), &R->h_hits)) != KG_OK) return fail(rc);
     auto grow = [&](HostBuf* hb, uint64_t need_bytes, uint64_t used_bytes) -> int { // rare: first run, or a batch unlike the last
@@ -2078,10 +2180,13 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
             pool_give_dev(ctx, &pt.d_calls);
             pool_give_dev(ctx, &pt.d_otus);
             pool_give_dev(ctx, &pt.d_hits);
+            pool_give_dev(ctx, &pt.d_otu_n);
+            pool_give_dev(ctx, &pt.d_otu_entries);
         }
     };
     auto enqueue = [&](size_t s) -> int { // slice s runs as soon as its bytes have landed; nothing here waits for the GPU
         cudaStreamWaitEvent(ctx->stream, ctx->up_ev[s % UP], 0);
+        part[s & 1].want_compact_otus = true;
         return pipe_enqueue(ctx, sc.slot[s & 1], table, slot[s % UP], params, &part[s & 1], sc.hit_cap_seen, (uint32_t)cut[s]);
     };
     for (size_t s = 0; s < std::min(nslices, UP - 1); s++)
@@ -2115,7 +2220,11 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
         cudaStream_t ds = ctx->d2h_stream;
         if ((rc = grow(&R->h_calls, (ncalls + ps.num_calls) * sizeof(kg_call), ncalls * sizeof(kg_call))) != KG_OK) { drop_parts(); return fail(rc); }
         if (ps.num_calls) cudaMemcpyAsync((kg_call*)R->h_calls.p + ncalls, pr.d_calls.p, ps.num_calls * sizeof(kg_call), cudaMemcpyDeviceToHost, ds);
-        if (bt->n) cudaMemcpyAsync((kg_otu*)R->h_otus.p + cut[s], pr.d_otus.p, bt->n * sizeof(kg_otu), cudaMemcpyDeviceToHost, ds);
+        const uint64_t slice_entries = sc.slot[s & 1].h_ctr[KG_CTR_COUNT + 1];
+        if ((rc = grow(&R->h_otu_entries, (nentries + slice_entries) * sizeof(kg_otu_entry), nentries * sizeof(kg_otu_entry))) != KG_OK) { drop_parts(); return fail(rc); }
+        if (bt->n) cudaMemcpyAsync((uint8_t*)R->h_otu_n.p + cut[s], pr.d_otu_n.p, bt->n, cudaMemcpyDeviceToHost, ds);
+        if (slice_entries) cudaMemcpyAsync((kg_otu_entry*)R->h_otu_entries.p + nentries, pr.d_otu_entries.p, slice_entries * sizeof(kg_otu_entry), cudaMemcpyDeviceToHost, ds);
+        nentries += slice_entries;
         if (params->emit_hits) {
             if ((rc = grow(&R->h_hits, (nhits + ps.num_hits) * sizeof(kg_hit), nhits * sizeof(kg_hit))) != KG_OK) { drop_parts(); return fail(rc); }
             if (ps.num_hits) cudaMemcpyAsync((kg_hit*)R->h_hits.p + nhits, pr.d_hits.p, ps.num_hits * sizeof(kg_hit), cudaMemcpyDeviceToHost, ds);
@@ -2125,9 +2234,11 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
             keep[k][0] = pr.d_calls;
             keep[k][1] = pr.d_otus;
             keep[k][2] = pr.d_hits;
+            keep[k][3] = pr.d_otu_n;
+            keep[k][4] = pr.d_otu_entries;
             keep_used[k] = true;
             cudaEventRecord(ctx->d2h_ev[k], ds);
-            pr.d_calls = pr.d_otus = pr.d_hits = DevBuf();
+            pr.d_calls = pr.d_otus = pr.d_hits = pr.d_otu_n = pr.d_otu_entries = DevBuf();
         }
         ncalls += ps.num_calls;
         nhits += ps.num_hits;
@@ -2155,8 +2266,69 @@ extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const ui
     R->stats.num_calls = ncalls;
     R->stats.num_hits = nhits;
     sc.calls_seen = std::max<uint64_t>(sc.calls_seen, ncalls);
+    sc.otu_entries_seen = std::max<uint64_t>(sc.otu_entries_seen, nentries);
+    R->num_otu_entries = nentries;
+    R->otus_compact = true;
     R->fetched = true;
     *out = R;
+    return KG_OK;
+}
+
+extern "C" int kg_run(kg_context* ctx, const kg_table* table, int mode, const uint8_t* seq_bytes, const uint64_t* offsets,
+                      size_t n, const kg_params* params, kg_result** out) {
+    return run_host_impl(ctx, table, mode, false, seq_bytes, offsets, n, params, out);
+}
+
+extern "C" int kg_run_packed_aa(kg_context* ctx, const kg_table* table, const uint8_t* packed, const uint64_t* group_offsets, size_t n,
+                                const kg_params* params, kg_result** out) {
+    return run_host_impl(ctx, table, KG_MODE_AA, true, packed, group_offsets, n, params, out);
+}
+
+// toAminoAcidOff (KGJ:111-175) on the host -- what prepareQuery does before addKmers (KGJ:1055-1058) -- then 8 codes in 5 bytes
+extern "C" uint64_t kg_pack_aa_groups(uint64_t len) { return (len + 1 + 7) / 8; }
+
+extern "C" int kg_pack_aa(const uint8_t* seq_bytes, const uint64_t* offsets, size_t n, uint8_t* packed, uint64_t* group_offsets, int threads) {
+    if (!offsets || !group_offsets || (offsets[n] && !seq_bytes)) KG_FAIL(KG_EINVAL, "kg_pack_aa: null argument");
+    uint8_t lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = 20;
+    for (int i = 0; i < 20; i++) lut[(unsigned char)"ACDEFGHIKLMNPQRSTVWY"[i]] = (uint8_t)i;
+    uint64_t g = 0;
+    for (size_t s = 0; s < n; s++) { // the layout first (cheap), so that the packing itself can run on any number of threads
+        if (offsets[s + 1] < offsets[s]) KG_FAIL(KG_EINVAL, "kg_pack_aa: offsets must be non-decreasing (at %zu)", s);
+        group_offsets[s] = g;
+        g += kg_pack_aa_groups(offsets[s + 1] - offsets[s]);
+    }
+    group_offsets[n] = g;
+    if (!packed) return KG_OK; // layout only: the caller sizes its buffer with group_offsets[n] * 5
+    auto work = [&](size_t s0, size_t s1) {
+        for (size_t s = s0; s < s1; s++) {
+            const uint8_t* src = seq_bytes + offsets[s];
+            const uint64_t len = offsets[s + 1] - offsets[s];
+            uint8_t* dst = packed + 5 * group_offsets[s];
+            const uint64_t ng = group_offsets[s + 1] - group_offsets[s];
+            for (uint64_t q = 0; q < ng; q++) {
+                uint64_t bits = 0;
+                for (int i = 0; i < 8; i++) {
+                    const uint64_t r = 8 * q + i;
+                    bits |= (uint64_t)(r < len ? lut[src[r]] : 31) << (5 * i);
+                }
+                for (int i = 0; i < 5; i++) dst[5 * q + i] = (uint8_t)(bits >> (8 * i));
+            }
+        }
+    };
+    const int T = std::max(1, std::min<int>(threads, 64));
+    if (T == 1 || n < 1024) {
+        work(0, n);
+        return KG_OK;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) { // equal numbers of groups per thread
+        const uint64_t g0 = g * t / T, g1 = g * (t + 1) / T;
+        const size_t s0 = (size_t)(std::lower_bound(group_offsets, group_offsets + n, g0) - group_offsets);
+        const size_t s1 = t + 1 == T ? n : (size_t)(std::lower_bound(group_offsets, group_offsets + n, g1) - group_offsets);
+        th.emplace_back(work, s0, s1);
+    }
+    for (auto& x : th) x.join();
     return KG_OK;
 }
 
@@ -2175,8 +2347,51 @@ extern "C" int kg_result_calls(kg_result* r, const kg_call** calls, size_t* n) {
 extern "C" int kg_result_otus(kg_result* r, const kg_otu** otus, size_t* n) {
     if (!r || !otus || !n) KG_FAIL(KG_EINVAL, "kg_result_otus: null argument");
     KG_TRY(kg_result_fetch(r));
+    if (r->otus_compact && !r->h_otus.p) { // kg_run brought the counts home compact: expand once, on demand
+        KG_TRY(pool_take_host(r->ctx, std::max<uint64_t>(r->n, 1) * sizeof(kg_otu), &r->h_otus));
+        kg_otu* o = (kg_otu*)r->h_otus.p;
+        const uint8_t* cn = (const uint8_t*)r->h_otu_n.p;
+        const kg_otu_entry* en = (const kg_otu_entry*)r->h_otu_entries.p;
+        memset(o, 0, r->n * sizeof(kg_otu));
+        uint64_t e = 0;
+        for (uint64_t s = 0; s < r->n; s++) {
+            o[s].n = cn[s];
+            for (int k = 0; k < cn[s]; k++, e++) {
+                o[s].count[k] = en[e].count;
+                o[s].oI[k] = en[e].oI;
+            }
+        }
+    }
     *otus = (const kg_otu*)r->h_otus.p;
     *n = r->n;
+    return KG_OK;
+}
+extern "C" int kg_result_otus_compact(kg_result* r, const uint8_t** n_per_seq, const kg_otu_entry** entries, size_t* n_seqs, size_t* n_entries) {
+    if (!r || !n_per_seq || !entries || !n_seqs || !n_entries) KG_FAIL(KG_EINVAL, "kg_result_otus_compact: null argument");
+    KG_TRY(kg_result_fetch(r));
+    if (!r->otus_compact) { // a kg_batch_run result holds full records: compact them once
+        const kg_otu* o = (const kg_otu*)r->h_otus.p;
+        uint64_t tot = 0;
+        for (uint64_t s = 0; s < r->n; s++) tot += (uint64_t)o[s].n;
+        KG_TRY(pool_take_host(r->ctx, std::max<uint64_t>(r->n, 1), &r->h_otu_n));
+        KG_TRY(pool_take_host(r->ctx, std::max<uint64_t>(tot, 1) * sizeof(kg_otu_entry), &r->h_otu_entries));
+        uint8_t* cn = (uint8_t*)r->h_otu_n.p;
+        kg_otu_entry* en = (kg_otu_entry*)r->h_otu_entries.p;
+        uint64_t e = 0;
+        for (uint64_t s = 0; s < r->n; s++) {
+            cn[s] = (uint8_t)o[s].n;
+            for (int k = 0; k < o[s].n; k++, e++) {
+                en[e].count = o[s].count[k];
+                en[e].oI = o[s].oI[k];
+            }
+        }
+        r->num_otu_entries = tot;
+        r->otus_compact = true;
+    }
+    *n_per_seq = (const uint8_t*)r->h_otu_n.p;
+    *entries = (const kg_otu_entry*)r->h_otu_entries.p;
+    *n_seqs = r->n;
+    *n_entries = r->num_otu_entries;
     return KG_OK;
 }
 extern "C" int kg_result_hits(kg_result* r, const kg_hit** hits, size_t* n) {
@@ -2193,9 +2408,13 @@ extern "C" void kg_result_free(kg_result* r) {
     pool_give_dev(r->ctx, &r->d_calls);
     pool_give_dev(r->ctx, &r->d_otus);
     pool_give_dev(r->ctx, &r->d_hits);
+    pool_give_dev(r->ctx, &r->d_otu_n);
+    pool_give_dev(r->ctx, &r->d_otu_entries);
     pool_give_host(r->ctx, &r->h_calls);
     pool_give_host(r->ctx, &r->h_otus);
     pool_give_host(r->ctx, &r->h_hits);
+    pool_give_host(r->ctx, &r->h_otu_n);
+    pool_give_host(r->ctx, &r->h_otu_entries);
     delete r;
 }
 

@@ -106,6 +106,67 @@ def test_probe_variants(kg, ctx, oracle, universe, monkeypatch, probe, stages):
     t.free()
 
 
+@pytest.mark.parametrize("flags", FLAGS[:3])
+def test_packed_aa_input_and_compact_otus(kg, ctx, oracle, universe, monkeypatch, flags):
+    """kg_run_packed_aa (5-bit residue codes, 8 per 5 bytes, unpacked on the device) must give exactly what kg_run gives on
+    the original characters -- hits, calls and OTU counts, edge sequences included -- and the compact OTU form that both
+    calls bring home expands to the oracle's records.  Small slices so that the call runs through several pipeline slices."""
+    u, img, _ = universe
+    monkeypatch.setenv("KG_SLICE_MB", "1")
+    seqs = u.proteins(900, seed=55) + [b"", b"A", b"ACDEFGH", b"ACDEFGHI", b"ACDEFGHIK", b"acdefghiklmnp", b"ACDEFGHIKXLMNPQRSTVWY\x00\x00",
+                                       b"", b"WWWWWWWWWWWWWWWW", b"ACDEFGHIKLMNPQRS", b"ACDEFGHIKLMNPQRST"] + u.proteins(300, seed=56)
+    sb, off = oracle.concat(seqs)
+    packed, goff = kg.pack_aa(sb, off, threads=3)
+    t = ctx.table_from_image(img)
+    p = kg.default_params(emit_hits=1, **flags)
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True, **flags), sb, off, oracle.DIRECT_PROBE)
+    a = ctx.run(t, kg.MODE_AA, sb, off, p)
+    b = ctx.run_packed_aa(t, packed, goff, p)
+    assert_same(a, ref, what=f"kg_run {flags}")
+    assert_same(b, ref, what=f"kg_run_packed_aa {flags}")
+    for r in (a, b):
+        n_per, ent = r.otus_compact
+        assert n_per.dtype == np.uint8 and len(n_per) == len(seqs)
+        assert np.array_equal(n_per, ref.otus["n"].astype(np.uint8))
+        flat_c = np.concatenate([ref.otus["count"][i][:n] for i, n in enumerate(ref.otus["n"])] + [np.zeros(0, np.int32)])
+        flat_o = np.concatenate([ref.otus["oI"][i][:n] for i, n in enumerate(ref.otus["n"])] + [np.zeros(0, np.int32)])
+        assert np.array_equal(ent["count"], flat_c) and np.array_equal(ent["oI"], flat_o)
+    assert a.stats.num_kmers == b.stats.num_kmers == ref.num_kmers
+    # a device-resident result (kg_batch_run) serves the compact form too
+    bt = ctx.upload(kg.MODE_AA, sb, off)
+    c = ctx.run_batch(t, bt, p)
+    n_per, ent = c.otus_compact
+    assert np.array_equal(n_per, ref.otus["n"].astype(np.uint8)) and len(ent) == int(ref.otus["n"].sum())
+    for x in (a, b, c):
+        x.free()
+    bt.free()
+    t.free()
+
+
+def test_packed_first_call_with_overflowing_slice(kg, oracle, universe, monkeypatch):
+    """Regression (r02): on a FRESH context the hit buffers of slice s+1 are sized from slice s; a slice with more hits
+    overflows them and the pass is repeated -- the repeat must not patch the padded residue stream a second time (it dropped
+    the last allowed window of every protein of that slice).  Sparse proteins first, dense ones last, small slices."""
+    u, img, _ = universe
+    monkeypatch.setenv("KG_SLICE_MB", "1")
+    alpha = np.frombuffer(synth.PROT_ALPHA.encode(), np.uint8)
+    rng = np.random.default_rng(3)
+    sparse = [bytes(rng.choice(alpha, 300)) for _ in range(9000)]          # ~no hits: tiny hit buffers
+    dense = [alpha[u.consensus(f % 300)].tobytes() for f in range(9000)]   # a third of the windows hit
+    sb, off = oracle.concat(sparse + dense)
+    packed, goff = kg.pack_aa(sb, off, threads=2)
+    ref = oracle.run(oracle.Table(data=img), oracle.make_params(aa=True), sb, off, oracle.DIRECT_PROBE, threads=4)
+    for which in ("packed", "raw"):
+        c = kg.Context(0)   # fresh: no buffer sizes remembered
+        t = c.table_from_image(img)
+        p = kg.default_params(emit_hits=1)
+        res = c.run_packed_aa(t, packed, goff, p) if which == "packed" else c.run(t, kg.MODE_AA, sb, off, p)
+        assert_same(res, ref, what=f"first call, {which}")
+        res.free()
+        t.free()
+        c.close()
+
+
 KATS = json.load(open(os.path.join(GOLD, "fsm_kats.json")))
 
 

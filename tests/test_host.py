@@ -159,3 +159,27 @@ def test_java_format_matches_oracle(oracle):
         for prec in (6, 3):
             assert kg.java_format_f(v, prec) == oracle.java_format_f(v, prec), (v, prec)
     assert kg.java_format_f(1 / 128) == "0.007813"
+
+
+def test_pack_aa_layout_and_codes():
+    """kg_pack_aa (include/kmerguts.h): toAminoAcidOff codes (KGJ:111-175), 8 per 5 bytes, ceil((len+1)/8) groups per sequence
+    (at least one padding code 31 after the last residue); one thread and many threads give the same bytes."""
+    import kmergutsjava_b200 as kg
+    from oracle import kgo
+    rng = np.random.default_rng(7)
+    alpha = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYXacdx*-\x00 BZUO", np.uint8)
+    seqs = [bytes(rng.choice(alpha, int(L))) for L in list(rng.integers(0, 70, 1500)) + [0, 1, 7, 8, 9, 15, 16, 17, 4000]]
+    sb, off = kgo.concat(seqs)
+    packed, goff = kg.pack_aa(sb, off, threads=1)
+    packed_mt, goff_mt = kg.pack_aa(sb, off, threads=5)
+    assert np.array_equal(packed, packed_mt) and np.array_equal(goff, goff_mt)
+    assert [int(goff[i + 1] - goff[i]) for i in range(len(seqs))] == [(len(s) + 1 + 7) // 8 for s in seqs]
+    assert all(kg.lib().kg_pack_aa_groups(L) == (L + 1 + 7) // 8 for L in (0, 1, 7, 8, 1000))
+    code = {c: i for i, c in enumerate(b"ACDEFGHIKLMNPQRSTVWY")}
+    for i in (0, 3, 700, len(seqs) - 1, len(seqs) - 2, len(seqs) - 9):
+        s = seqs[i]
+        raw = packed[5 * int(goff[i]):5 * int(goff[i + 1])]
+        bits = int.from_bytes(raw.tobytes(), "little")
+        got = [(bits >> (5 * k)) & 31 for k in range(8 * int(goff[i + 1] - goff[i]))]
+        assert got[:len(s)] == [code.get(c, 20) for c in s]
+        assert got[len(s):] == [31] * (len(got) - len(s)) and len(got) > len(s)

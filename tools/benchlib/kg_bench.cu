@@ -147,10 +147,10 @@ __global__ void k_prot_fill(DevUniverse u, uint64_t first, uint64_t n, uint64_t 
 // ---- genomes (configs[2]): genes = family consensus proteins back-translated with a uniformly chosen synonymous codon,
 // random strand, separated by random spacers; spacer bases are uniform ACGT; ~1e-5 of all bases become N ----
 __device__ __constant__ char c_gcode[65] = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
-__global__ void k_genome_background(uint8_t* __restrict__ out, uint64_t total, uint64_t seed) {
+__global__ void k_genome_background(uint8_t* __restrict__ out, uint64_t total, uint64_t seed, uint64_t base_pos) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const uint64_t h = hash3(seed ^ 0x77, i, 0);
+    const uint64_t h = hash3(seed ^ 0x77, base_pos + i, 0);
     out[i] = ((h >> 8) % 100000ull == 0) ? (uint8_t)'N' : (uint8_t)"ACGT"[h & 3];
 }
 struct GenePlan { // one gene: where it starts in the concatenated genome stream, which family, which strand
@@ -159,11 +159,12 @@ struct GenePlan { // one gene: where it starts in the concatenated genome stream
     uint32_t minus;
 };
 __global__ void k_genome_genes(DevUniverse u, const GenePlan* __restrict__ plan, uint64_t ngenes, uint64_t seed,
-                               uint8_t* __restrict__ out) {
-    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per gene
+                               uint8_t* __restrict__ out, uint64_t gene_base) {
+    const uint64_t gl = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per gene
     const int lane = threadIdx.x & 31;
-    if (g >= ngenes) return;
-    const GenePlan gp = plan[g];
+    if (gl >= ngenes) return;
+    const GenePlan gp = plan[gl];
+    const uint64_t g = gene_base + gl; // index of the gene in the whole job: a range of genomes gets the bytes the full job gets
     const uint32_t L = family_len(u, gp.family);
     const char* alpha = "ACDEFGHIKLMNPQRSTVWY";
     for (uint32_t c = lane; c < L; c += 32) {
@@ -464,6 +465,11 @@ extern "C" int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t
 
 extern "C" int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t n_genomes, uint64_t length, uint64_t seed,
                                 uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes) {
+    return kg_synth_genomes_range(ctx, u, 0, n_genomes, length, seed, d_seq, d_off, total_bytes);
+}
+
+extern "C" int kg_synth_genomes_range(kg_context* ctx, const kg_universe* u, uint64_t first, uint64_t n_genomes, uint64_t length, uint64_t seed,
+                                      uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes) {
     if (!ctx || !u || !d_seq || !d_off || !total_bytes || length < 64) KG_FAIL(KG_EINVAL, "kg_synth_genomes: bad argument");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -473,19 +479,23 @@ extern "C" int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t 
     // gene plan on the host (a few thousand genes per genome): spacer ~ 1 + geometric(mean 120), family uniform
     std::vector<GenePlan> plan;
     std::vector<uint64_t> off(n_genomes + 1);
-    uint64_t ctr = 0;
-    for (uint64_t gi = 0; gi < n_genomes; gi++) {
-        off[gi] = gi * length;
+    uint64_t ctr = 0, gene_base = 0, ngenes_seen = 0;
+    for (uint64_t gj = 0; gj < first + n_genomes; gj++) { // the plan of the genomes before `first` is walked too: the counter runs on
+        const bool keep = gj >= first;
+        const uint64_t gi = keep ? gj - first : 0;
+        if (gj == first) gene_base = ngenes_seen;
+        if (keep) off[gi] = gi * length;
         uint64_t pos = 0;
         for (;;) {
-            const uint64_t h = hash3(seed ^ 0x99, gi, ctr++);
+            const uint64_t h = hash3(seed ^ 0x99, gj, ctr++);
             uint64_t gap = 1;
             for (uint64_t r = h >> 20; gap < 2000 && (r % 120) != 0; r = smix64(r)) gap++;
             const uint32_t fam = (uint32_t)((h >> 1) % u->n_families);
             const uint32_t L = u->lenq[hash3(u->seed, fam, 0xFFFFFFFFull) & 4095];
             pos += gap;
             if (pos + 3ull * L > length) break;
-            plan.push_back(GenePlan{gi * length + pos, fam, (uint32_t)(h & 1)});
+            if (keep) plan.push_back(GenePlan{gi * length + pos, fam, (uint32_t)(h & 1)});
+            ngenes_seen++;
             pos += 3ull * L;
         }
     }
@@ -500,8 +510,8 @@ extern "C" int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t 
     CU(cudaMemsetAsync(seq + total, 0, 64, st));
     CU(cudaMemcpyAsync(doff, off.data(), (n_genomes + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dplan, plan.data(), plan.size() * sizeof(GenePlan), cudaMemcpyHostToDevice, st));
-    k_genome_background<<<blocks_for(total, 256), 256, 0, st>>>(seq, total, seed);
-    if (!plan.empty()) k_genome_genes<<<blocks_for(plan.size() * 32, 256), 256, 0, st>>>(du, dplan, plan.size(), seed, seq);
+    k_genome_background<<<blocks_for(total, 256), 256, 0, st>>>(seq, total, seed, first * length);
+    if (!plan.empty()) k_genome_genes<<<blocks_for(plan.size() * 32, 256), 256, 0, st>>>(du, dplan, plan.size(), seed, seq, gene_base);
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     cudaFree(dplan);

@@ -48,6 +48,9 @@ int kg_synth_proteins(kg_context* ctx, const kg_universe* u, uint64_t first, uin
  * uniformly chosen synonymous codons on a random strand, separated by random spacers of uniform ACGT; ~1e-5 N. */
 int kg_synth_genomes(kg_context* ctx, const kg_universe* u, uint64_t n_genomes, uint64_t length, uint64_t seed,
                      uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes);
+/* genomes first .. first+n_genomes-1 of the same job, byte for byte (a rank's share when the genomes are dealt to several GPUs) */
+int kg_synth_genomes_range(kg_context* ctx, const kg_universe* u, uint64_t first, uint64_t n_genomes, uint64_t length, uint64_t seed,
+                           uint8_t** d_seq, uint64_t** d_off, uint64_t* total_bytes);
 
 /* kmer.table.mem_map image (24-byte header + num_slots 24-byte LE entries, linear probing WITHOUT wrap-around, last
  * slot empty) built on the device from (keys, payload).  num_slots = the first prime >= min_slots for which no probe

@@ -37,6 +37,7 @@ def lib() -> C.CDLL:
         "kg_synth_signatures_sharded": (i32, [vp, C.POINTER(UniverseStruct), u64, i32, i32, pp, pp, C.POINTER(u64)]),
         "kg_synth_proteins": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_genomes": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, pp, pp, C.POINTER(u64)]),
+        "kg_synth_genomes_range": (i32, [vp, C.POINTER(UniverseStruct), u64, u64, u64, u64, pp, pp, C.POINTER(u64)]),
         "kg_synth_reference_image": (i32, [vp, vp, vp, u64, u64, C.POINTER(u64), pp, C.POINTER(C.c_double)]),
         "kg_synth_naive_scan_aa": (i32, [vp, vp, vp, vp, u64, u64, vp]),
         "kg_synth_hits_checksum": (i32, [vp, vp, u64, vp, C.POINTER(u64)]),
@@ -111,6 +112,18 @@ def synth_genomes(ctx: Context, u, n_genomes: int, length: int, seed: int):
     us = make_universe(u)
     _check(lib().kg_synth_genomes(ctx._h, C.byref(us), n_genomes, length, seed, C.byref(ds), C.byref(do), C.byref(total)))
     return ds.value, do.value, total.value
+
+
+def synth_genomes_range(ctx: Context, u, first: int, n_genomes: int, length: int, seed: int):
+    """Genomes first .. first+n-1 of the job synth_genomes(n_total) generates, byte for byte."""
+    ds, do, total = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    us = make_universe(u)
+    _check(lib().kg_synth_genomes_range(ctx._h, C.byref(us), first, n_genomes, length, seed, C.byref(ds), C.byref(do), C.byref(total)))
+    return ds.value, do.value, total.value
+
+
+def to_host_at(ctx: Context, d_ptr: int, offset: int, nbytes: int) -> np.ndarray:
+    return to_host(ctx, d_ptr + offset, nbytes)
 
 
 def synth_reference_image(ctx: Context, d_keys: int, d_payload: int, n: int, min_slots: int) -> np.ndarray:
