@@ -1,4 +1,4 @@
-// tools/java/GoldenDump.java -- pins the CPU oracle (oracle/kg_oracle.c) to the REAL KmerGutsJava on any box with a JDK.
+// tests/java_pin/GoldenDump.java -- pins the CPU oracle (oracle/kg_oracle.c) to the REAL KmerGutsJava on any box with a JDK.
 //
 // This image has no JVM (java, javac, jshell are absent), so the repo's parity chain ends at the C restatement of the
 // reference ("parity unpinned").  This class closes the chain in one command on a machine that has a JDK and a checkout
@@ -14,7 +14,7 @@
 //                                                   of SURVEY.md 8(d) (the -d runs on a prefix of each fixture: their
 //                                                   after-hit / after-call dumps grow quadratically).
 //
-// tools/java/pin_oracle.sh runs both and compares with what the oracle gives (tools/java/pin_oracle.py compare) and with
+// tests/java_pin/pin_oracle.sh runs both and compares with what the oracle gives (tests/java_pin/pin_oracle.py compare) and with
 // the SHA-256 values committed in tests/golden/c0_report_sha256.json.  Nothing here is used by the product or the tests.
 package kmergutsjava;
 

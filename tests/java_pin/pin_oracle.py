@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/java/pin_oracle.py -- the Python half of tools/java/pin_oracle.sh (pinning the oracle to the real Java).
+"""tests/java_pin/pin_oracle.py -- the Python half of tests/java_pin/pin_oracle.sh (pinning the oracle to the real Java).
 
     prepare <workdir>   builds the configs[0] fixture (KmerData/ from the committed E. coli .faa.gz), writes kats.txt for
                         GoldenDump, runs the ORACLE on the eight configs[0] runs and checks its reports against the SHA-256

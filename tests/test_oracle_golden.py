@@ -1,6 +1,6 @@
-"""The pin between the CPU oracle and the real Java (tools/java/): the oracle's reports for the configs[0] runs -- the
+"""The pin between the CPU oracle and the real Java (tests/java_pin/): the oracle's reports for the configs[0] runs -- the
 reference's own E. coli fixtures, protein mode and 6-frame mode, the four flag sets of SURVEY.md 8(d) -- must hash to the
-values committed in tests/golden/c0_report_sha256.json.  Those are the values tools/java/pin_oracle.sh compares the
+values committed in tests/golden/c0_report_sha256.json.  Those are the values tests/java_pin/pin_oracle.sh compares the
 UNMODIFIED KmerGutsJava's reports with on a box that has a JDK (none exists in this image), so "oracle == committed hashes"
 here plus "Java == committed hashes" there pins every GPU-vs-oracle test of this suite to the Java."""
 import importlib.util
@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _pin():
-    spec = importlib.util.spec_from_file_location("pin_oracle", os.path.join(ROOT, "tools", "java", "pin_oracle.py"))
+    spec = importlib.util.spec_from_file_location("pin_oracle", os.path.join(ROOT, "tests", "java_pin", "pin_oracle.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
@@ -40,6 +40,6 @@ def test_kat_text_for_the_java_driver(tmp_path):
     assert len(lines) == len(kats) + sum(len(k["hits"]) for k in kats)
     exp = pin.expected_kat_text()
     assert exp.count("KAT ") == 21 and "CALL\t0\t47\t5\t7\tF7\t2.500000" in exp and "OTU-COUNTS\tkat[0]\t3-3\t2-6\t2-2\t1-5\t1-4" in exp
-    src = open(os.path.join(ROOT, "tools", "java", "GoldenDump.java")).read()
+    src = open(os.path.join(ROOT, "tests", "java_pin", "GoldenDump.java")).read()
     for name in ("gatherHits", "tabulateOtuDataForContig", "minHits", "maxGap", "minWeightedHits", "orderConstraint", "KmerGutsJava.main"):
         assert name in src
