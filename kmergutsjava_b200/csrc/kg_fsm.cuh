@@ -38,43 +38,55 @@ __device__ __forceinline__ void kg_otu_update(KgOtuBuf& u, int oI) { kg_otu_upda
 //
 // The list is always sorted by count, non-increasing: a new or overwritten entry starts at the end and bubbles past every
 // entry with a count <= its own (KGJ:432-437), and an incremented entry only ever moves forward.  So the bubbling has a
-// closed form -- the entry lands behind the entries ahead of it whose count is LARGER, the ones in between shift back by
-// one -- and the whole update is a handful of independent compares and selects instead of a chain of dependent swaps
-// (the OTU fold of a long contig is one such update after the other: its latency is what counts).
+// closed form -- the entry lands behind the entries whose count is LARGER, the ones between that place and its old one
+// shift back by one.  The OTU fold of a long contig is one such update after the other, so what counts is the LENGTH OF
+// THE DEPENDENT CHAIN, and the update is written as one-hot selects with no branch and no index arithmetic:
+//   e[i]  = entry i holds oI                         (at most one)
+//   C     = m + the matched count                    (an OR of five masked counts: one of them at most is non-zero)
+//   g[i]  = c[i] > C, i < 4                          (a prefix 1..10..0 because the list is sorted; the matched entry and
+//                                                     everything behind it have a count < C, the victim of an overwrite is
+//                                                     entry 4 and an appended entry lands on an empty slot whose count is 0,
+//                                                     so no "ahead of the old place" test is needed)
+//   le[i] = i <= old place j                         (found: no match before i; not found: j = min(n, 4), KGJ:419-426)
+//   new[i] = g[i] ? old[i] : (i == 0 || g[i-1]) ? (oI, C) : le[i] ? old[i-1] : old[i]
+// About nine dependent operations instead of ~27 (r01: 287 cycles per update in k_otu_fold).
 __device__ __forceinline__ void kg_otu_update_n(KgOtuBuf& u, int oI, int m) {
-    unsigned eq = 0;
+    bool e[KG_OI_BUFSZ];
 #pragma unroll
-    for (int i = 0; i < KG_OI_BUFSZ; i++) eq |= (unsigned)(i < u.n && u.o[i] == oI) << i;
-    int j, C;
-    if (eq) { // KGJ:415-418 found
-        j = __ffs(eq) - 1;
-        C = m;
+    for (int i = 0; i < KG_OI_BUFSZ; i++) e[i] = i < u.n && u.o[i] == oI;
+    const bool found = e[0] | e[1] | e[2] | e[3] | e[4];
+    const int C = m + ((e[0] ? u.c[0] : 0) | (e[1] ? u.c[1] : 0) | (e[2] ? u.c[2] : 0) | (e[3] ? u.c[3] : 0) | (e[4] ? u.c[4] : 0));
+    bool le[KG_OI_BUFSZ]; // le[0] is always true and never read
+    bool before = false;  // a match at an index < i
 #pragma unroll
-        for (int i = 0; i < KG_OI_BUFSZ; i++) C += (i == j) ? u.c[i] : 0;
-    } else if (u.n == KG_OI_BUFSZ) { // overwrite the last entry (KGJ:419-421)
-        j = KG_OI_BUFSZ - 1;
-        C = m;
-    } else { // append (KGJ:422-426)
-        j = u.n;
-        u.n++;
-        C = m;
+    for (int i = 1; i < KG_OI_BUFSZ; i++) {
+        before |= e[i - 1];
+        le[i] = found ? !before : i <= u.n;
     }
-    int p = 0; // entries ahead of j with a larger count stay in front (KGJ:432-437 stops at the first prev.count > cur.count)
+    int tc[KG_OI_BUFSZ], to[KG_OI_BUFSZ]; // what slot i holds if the new entry lands in front of it (independent of C)
 #pragma unroll
-    for (int i = 0; i < KG_OI_BUFSZ - 1; i++) p += (i < j && u.c[i] > C);
+    for (int i = 1; i < KG_OI_BUFSZ; i++) {
+        tc[i] = le[i] ? u.c[i - 1] : u.c[i];
+        to[i] = le[i] ? u.o[i - 1] : u.o[i];
+    }
+    bool g[KG_OI_BUFSZ];
+#pragma unroll
+    for (int i = 0; i < KG_OI_BUFSZ - 1; i++) g[i] = u.c[i] > C;
+    g[KG_OI_BUFSZ - 1] = false;
     int nc[KG_OI_BUFSZ], no[KG_OI_BUFSZ];
+    nc[0] = g[0] ? u.c[0] : C;
+    no[0] = g[0] ? u.o[0] : oI;
 #pragma unroll
-    for (int i = 0; i < KG_OI_BUFSZ; i++) {
-        const bool shifted = i > p && i <= j; // entries p..j-1 move back by one
-        const int pc = i > 0 ? u.c[i - 1] : 0, po = i > 0 ? u.o[i - 1] : 0;
-        nc[i] = i == p ? C : (shifted ? pc : u.c[i]);
-        no[i] = i == p ? oI : (shifted ? po : u.o[i]);
+    for (int i = 1; i < KG_OI_BUFSZ; i++) {
+        nc[i] = g[i] ? u.c[i] : (g[i - 1] ? C : tc[i]);
+        no[i] = g[i] ? u.o[i] : (g[i - 1] ? oI : to[i]);
     }
 #pragma unroll
     for (int i = 0; i < KG_OI_BUFSZ; i++) {
         u.c[i] = nc[i];
         u.o[i] = no[i];
     }
+    u.n += (!found && u.n < KG_OI_BUFSZ);
 }
 
 struct KgFsmParams {
@@ -174,6 +186,22 @@ struct KgFsm {
     // body of the for loop of gatherHits, KGJ:468-510
     template <class Emit>
     __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, Emit& emit) {
+        // Fast path -- the hit extends the open run of its own function (most hits inside a gene): no gap (KGJ:477), the
+        // list is not empty so currentFI stays (KGJ:486), no order constraint (KGJ:490), room in the list (KGJ:496), and
+        // the pair-switch test cannot fire because currentFI == ph.fI (KGJ:503).  What is left of the general path below
+        // is exactly these statements; one predictable branch instead of eight.
+        if (n > 0 && n < KG_MAX_HITS_PER_SEQ - 2 && h.fI == cur && !p.order_constraint &&
+            (int)((unsigned)l1.pos + (unsigned)p.max_gap) >= h.pos) {
+            consumed++;
+            n++;
+            l2 = l1;
+            l1 = h;
+            cnt++;
+            w = __fadd_rn(w, h.wt);
+            last_match = h.pos;
+            count_otu(h.oI);
+            return;
+        }
         consumed++;
         if (n > 0 && (int)((unsigned)l1.pos + (unsigned)p.max_gap) < h.pos) { // KGJ:477-484 (Java int wrap-around kept)
             if (n >= p.min_hits) process(p, emit);
@@ -208,13 +236,9 @@ struct KgFsm {
 // applies them in order afterwards.
 // ---------------------------------------------------------------------------------------------------------------
 struct KgSegRuns { // where a segment's OTU runs go: sparse slots starting at the segment's first hit index
-    int* run_oi;
-    uint32_t* run_m;
+    int2* run; // (OTU index, length)
     uint32_t n; // runs of emitted calls
-    __device__ __forceinline__ void put(uint32_t at, int oi, uint32_t m) {
-        run_oi[at] = oi;
-        run_m[at] = m;
-    }
+    __device__ __forceinline__ void put(uint32_t at, int oi, uint32_t m) { run[at] = make_int2(oi, (int)m); }
 };
 
 struct KgFsmSeg {
@@ -298,6 +322,19 @@ struct KgFsmSeg {
     }
     template <class Emit>
     __device__ __forceinline__ void hit(const KgFsmParams& p, const KgHitLite& h, Emit& emit, KgSegRuns& runs) {
+        // fast path: see KgFsm::hit
+        if (n > 0 && n < KG_MAX_HITS_PER_SEQ - 2 && h.fI == cur && !p.order_constraint &&
+            (int)((unsigned)l1.pos + (unsigned)p.max_gap) >= h.pos) {
+            consumed++;
+            n++;
+            l2 = l1;
+            l1 = h;
+            cnt++;
+            w = __fadd_rn(w, h.wt);
+            last_match = h.pos;
+            count_oi(h.oI, runs);
+            return;
+        }
         consumed++;
         if (n > 0 && (int)((unsigned)l1.pos + (unsigned)p.max_gap) < h.pos) {
             if (n >= p.min_hits) process(p, emit, runs);

@@ -1108,41 +1108,155 @@ __global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, 
 // ---------------------------------------------------------------------------------------------------------------
 // segment path (long contigs; kg_fsm.cuh explains why a container can be cut at gaps > max_gap)
 // ---------------------------------------------------------------------------------------------------------------
-// container of every position-ordered hit + "a segment starts here"
-__global__ void k_seg_flags(const uint64_t* __restrict__ voff, uint64_t nv, const uint32_t* __restrict__ hit_pos,
-                            const uint32_t* __restrict__ tile_out, uint32_t ntiles, uint32_t cap, int max_gap,
-                            uint32_t* __restrict__ hit_v, uint32_t* __restrict__ seg_flag,
-                            const unsigned long long* __restrict__ ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cap) return;
-    const uint32_t nhits = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
-    if (i >= nhits) {
-        seg_flag[i] = 0;
+// All kernels of this path size their work from counters that live on the device (hits, segments): their grids are
+// fixed (tiles of the batch, or a few blocks per SM walking a grid-stride loop), never "one thread per slot of the hit
+// buffer" -- the buffer is sized for the worst case and walking it cost more than the work itself (r02 launch list:
+// 1.2 ms of 3.6 ms in kernels whose threads found nothing to do).
+//
+// k_tile_bnd: which tiles contain the start of a container.  Two hits less than max_gap apart whose tiles hold no
+// container start belong to the same container; only the others need the binary search over the offsets.
+__global__ void k_tile_bnd(const uint64_t* __restrict__ voff, uint64_t nv, uint32_t ntiles, uint8_t* __restrict__ tile_bnd) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const uint64_t t = voff[v] >> TILE_SHIFT;
+    if (t < ntiles) tile_bnd[t] = 1;
+}
+
+// k_gather_seg: the gather of k_gather (GATHER_TILES tiles per block, walked as one flat range) fused with the segment
+// cut: hit g starts a segment when it is the first hit of its container or lies more than max_gap behind hit g-1
+// (KGJ:477-478; kg_fsm.cuh explains why the FSM state is empty there).  The block's segment starts are compacted, in
+// order, into seg_tmp[o0 ...] (o0 = rank of the block's first hit: a block never has more starts than hits) and counted
+// in blk_cnt; k_seg_offsets / k_seg_place turn that into the dense seg_begin list.
+constexpr int GS_BLK = 256;
+__global__ __launch_bounds__(GS_BLK) void k_gather_seg(const uint32_t* __restrict__ chunk_pos, const int4* __restrict__ chunk_payload,
+                                                       const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_out, uint32_t ntiles,
+                                                       const uint64_t* __restrict__ voff, uint64_t nv, const uint8_t* __restrict__ tile_bnd, int max_gap,
+                                                       uint32_t* __restrict__ hit_pos, int4* __restrict__ hit_payload,
+                                                       uint32_t* __restrict__ seg_tmp, uint32_t* __restrict__ blk_cnt,
+                                                       const unsigned long long* __restrict__ ctr) {
+    __shared__ uint32_t s_out[GATHER_TILES + 1], s_base[GATHER_TILES];
+    __shared__ uint32_t s_pos[GS_BLK], s_wcnt[GS_BLK / 32], s_prev, s_run;
+    const uint32_t t0 = blockIdx.x * GATHER_TILES;
+    if (ctr[KG_CTR_OVERFLOW]) { // the host repeats the pass with larger buffers
+        if (threadIdx.x == 0) blk_cnt[blockIdx.x] = 0;
         return;
     }
-    const uint32_t g = hit_pos[i];
-    const uint64_t v = seq_of(voff, nv, g);
-    hit_v[i] = (uint32_t)v;
-    bool start = i == 0;
-    if (!start) {
-        const uint32_t gp = hit_pos[i - 1];
-        start = (uint64_t)gp < voff[v] || g - gp > (uint32_t)max_gap;
+    const uint32_t nt = min((uint32_t)GATHER_TILES, ntiles - t0);
+    if (threadIdx.x <= nt) s_out[threadIdx.x] = tile_out[t0 + threadIdx.x];
+    if (threadIdx.x < nt) s_base[threadIdx.x] = tile_base[t0 + threadIdx.x];
+    __syncthreads();
+    const uint32_t o0 = s_out[0], total = s_out[nt] - o0;
+    if (threadIdx.x == 0) {
+        s_run = 0;
+        uint32_t prev = 0xFFFFFFFFu; // position of hit o0 - 1: the last hit of the last non-empty tile before this block
+        if (o0 > 0) {
+            uint32_t lo = 0, hi = t0; // largest tp < t0 with tile_out[tp] < o0  (tile_out[0] = 0 < o0)
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (tile_out[mid] < o0) lo = mid;
+                else hi = mid;
+            }
+            prev = chunk_pos[tile_base[lo] + (o0 - 1 - tile_out[lo])];
+        }
+        s_prev = prev;
     }
-    seg_flag[i] = start;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t j0 = 0; j0 < total; j0 += GS_BLK) {
+        const uint32_t j = j0 + threadIdx.x;
+        const bool valid = j < total;
+        const uint32_t g = o0 + j; // rank of the hit in position order
+        uint32_t pos = 0;
+        if (valid) {
+            uint32_t lo = 0, hi = nt; // the last tile that starts at or before g (empty tiles share their successor's start)
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_out[mid] <= g) lo = mid;
+                else hi = mid;
+            }
+            const uint32_t src = s_base[lo] + (g - s_out[lo]);
+            pos = chunk_pos[src];
+            const int4 pl = chunk_payload[src];
+            hit_pos[g] = pos;
+            hit_payload[g] = pl;
+        }
+        s_pos[threadIdx.x] = pos;
+        __syncthreads();
+        bool start = false;
+        if (valid) {
+            const uint32_t prev = threadIdx.x ? s_pos[threadIdx.x - 1] : s_prev;
+            if (prev == 0xFFFFFFFFu || pos - prev > (uint32_t)max_gap) {
+                start = true;
+            } else {
+                const uint32_t tp = prev >> TILE_SHIFT, tc = pos >> TILE_SHIFT;
+                if (tc - tp > 1 || tile_bnd[tp] || tile_bnd[tc]) start = (uint64_t)prev < voff[seq_of(voff, nv, pos)];
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, start);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = s_run, all = 0;
+#pragma unroll
+        for (int w = 0; w < GS_BLK / 32; w++) {
+            before += w < warp ? s_wcnt[w] : 0u;
+            all += s_wcnt[w];
+        }
+        if (start) seg_tmp[o0 + before + __popc(bal & ((1u << lane) - 1u))] = g;
+        __syncthreads();
+        if (threadIdx.x == GS_BLK - 1) s_prev = pos; // only read again when the next pass exists, i.e. this one was full
+        if (threadIdx.x == 0) s_run += all;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = s_run;
 }
-__global__ void k_seg_begin(const uint32_t* __restrict__ seg_flag, const uint32_t* __restrict__ seg_id,
-                            const uint32_t* __restrict__ tile_out, uint32_t ntiles, uint32_t cap,
-                            uint32_t* __restrict__ seg_begin, uint32_t* __restrict__ nseg_out,
-                            const unsigned long long* __restrict__ ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cap) return;
-    const uint32_t nhits = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
-    if (i < nhits && seg_flag[i]) seg_begin[seg_id[i] - 1] = i;
-    if (i == 0) {
-        const uint32_t ns = nhits ? seg_id[nhits - 1] : 0u;
-        nseg_out[0] = ns;
-        seg_begin[ns] = nhits;
+// one block: exclusive scan of the per-block segment counts; nseg and the closing seg_begin entry
+__global__ __launch_bounds__(1024) void k_seg_offsets(const uint32_t* __restrict__ blk_cnt, uint32_t nblk, uint32_t* __restrict__ blk_off,
+                                                      const uint32_t* __restrict__ tile_out, uint32_t ntiles, uint32_t* __restrict__ seg_begin,
+                                                      uint32_t* __restrict__ nseg_out, const unsigned long long* __restrict__ ctr) {
+    __shared__ uint32_t s_w[32], s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i0 = 0; i0 < nblk; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t v = i < nblk ? blk_cnt[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_w[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if (lane >= d) w += y;
+            }
+            s_w[lane] = w; // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry, wbase = warp ? s_w[warp - 1] : 0u;
+        if (i < nblk) blk_off[i] = carry + wbase + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + wbase + x;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        const uint32_t ns = s_carry;
+        nseg_out[0] = ns;
+        seg_begin[ns] = ctr[KG_CTR_OVERFLOW] ? 0u : tile_out[ntiles];
+    }
+}
+__global__ __launch_bounds__(GS_BLK) void k_seg_place(const uint32_t* __restrict__ seg_tmp, const uint32_t* __restrict__ blk_cnt,
+                                                      const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ tile_out,
+                                                      uint32_t* __restrict__ seg_begin) {
+    const uint32_t cnt = blk_cnt[blockIdx.x], off = blk_off[blockIdx.x];
+    if (!cnt) return;
+    const uint32_t o0 = tile_out[blockIdx.x * GATHER_TILES];
+    for (uint32_t k = threadIdx.x; k < cnt; k += GS_BLK) seg_begin[off + k] = seg_tmp[o0 + k];
 }
 // lo[v] = rank of the first hit at or after the start of container v (v = nv gives the number of hits)
 __global__ void k_lo(const uint64_t* __restrict__ voff, uint64_t nv, const uint32_t* __restrict__ hit_pos,
@@ -1160,105 +1274,295 @@ __global__ void k_lo(const uint64_t* __restrict__ voff, uint64_t nv, const uint3
     }
     lo[v] = a;
 }
-__global__ __launch_bounds__(128) void k_fsm_seg(const uint64_t* __restrict__ voff, const uint32_t* __restrict__ hit_pos,
-                                                 const int4* __restrict__ hit_payload, const uint32_t* __restrict__ hit_v,
-                                                 const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg,
-                                                 const uint32_t* __restrict__ lo, uint32_t cap, KgFsmParams p,
-                                                 KgDevCall* __restrict__ sparse, uint32_t* __restrict__ seg_calls,
-                                                 int* __restrict__ run_oi, uint32_t* __restrict__ run_m, uint32_t* __restrict__ seg_runs) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cap) return;
-    if (j >= nseg[0]) {
-        seg_calls[j] = 0;
-        seg_runs[j] = 0;
-        return;
+// Segments are handed to the FSM threads grouped by length (a gene of 300 hits next to a stray segment of one hit left the
+// average lane idle 82 % of the time: ncu, r02).  A counting sort over a count that lives on the device (grid-stride
+// loops); the classes are exact up to 16 hits and then four per octave, so the lanes of a warp differ by < 25 %; the
+// longest segments come first.  (Unlike the per-sequence path no segment gets a warp to itself: 3 % of the segments of a
+// genome have 256 hits or more, and a warp per long segment was most of the kernel's instruction count.)
+constexpr int SEG_CLASSES = 96;
+__device__ __forceinline__ uint32_t seg_class(uint32_t hits) { // 0 = most hits
+    uint32_t c = hits;
+    if (hits >= 16) {
+        const int e = 31 - __clz(hits);                       // 4 ..
+        c = 16 + 4 * (e - 4) + ((hits >> (e - 2)) & 3u);      // 16 .. 16 + 4*27 + 3
     }
-    const uint32_t a = seg_begin[j], b = seg_begin[j + 1];
-    const uint32_t v = hit_v[a];
-    const uint32_t base = (uint32_t)voff[v];
-    KgFsmSeg f;
-    f.begin((int)(a - lo[v])); // HIT lines of this container printed before the segment
-    SparseEmit emit{sparse + a / (uint32_t)p.min_hits};
-    KgSegRuns runs{run_oi + a, run_m + a, 0u};
-    uint32_t npos = hit_pos[a]; // hit i+1 is loaded while hit i goes through the FSM
-    int4 npl = hit_payload[a];
-    for (uint32_t i = a; i < b; i++) {
-        const uint32_t pos = npos;
-        const int4 pl = npl;
-        if (i + 1 < b) {
-            npos = hit_pos[i + 1];
-            npl = hit_payload[i + 1];
-        }
-        KgHitLite h = {(int)(pos - base), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
-        f.hit(p, h, emit, runs);
-    }
-    // In the reference the run that ends at a gap is processed when the NEXT hit of the container arrives, after that
-    // hit's HIT line (KGJ:472-480); only the container's last run is processed after the loop (KGJ:511-513).
-    if (j + 1 < nseg[0] && hit_v[b] == v) f.consumed++;
-    f.end(p, emit, runs);
-    seg_calls[j] = (uint32_t)f.ncalls;
-    seg_runs[j] = runs.n;
+    return (SEG_CLASSES - 1) - min(c, (uint32_t)SEG_CLASSES - 1);
 }
-__global__ void k_compact_calls_seg(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ seg_begin,
-                                    const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ hit_v,
-                                    const uint32_t* __restrict__ call_off, uint32_t cap, int per_seq, int min_hits,
-                                    uint32_t seq_base, kg_call* __restrict__ out) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cap || j >= nseg[0]) return;
-    const uint32_t o = call_off[j], c = call_off[j + 1] - o, a = seg_begin[j], v = hit_v[a];
-    const KgDevCall* src = sparse + a / (uint32_t)min_hits;
-    for (uint32_t k = 0; k < c; k++) {
-        const KgDevCall d = src[k];
-        kg_call r;
-        r.seq = seq_base + v / (uint32_t)per_seq;
-        r.strand_frame = (int32_t)(v % (uint32_t)per_seq);
-        r.start = d.start;
-        r.end = d.end;
-        r.count = d.count;
-        r.fI = d.fI;
-        r.weighted = d.weighted;
-        r.hits_before = d.hits_before;
-        out[o + k] = r;
+__global__ __launch_bounds__(256) void k_seg_hist(const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg,
+                                                  uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[SEG_CLASSES];
+    if (threadIdx.x < SEG_CLASSES) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = nseg[0];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        atomicAdd(&sh[seg_class(seg_begin[j + 1] - seg_begin[j])], 1u);
+    __syncthreads();
+    if (threadIdx.x < SEG_CLASSES && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ __launch_bounds__(256) void k_seg_scatter(const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg,
+                                                     const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
+    __shared__ uint32_t start[SEG_CLASSES], sh_cnt[SEG_CLASSES], sh_base[SEG_CLASSES];
+    const uint32_t n = nseg[0];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int c = 0; c < SEG_CLASSES; c++) {
+            start[c] = acc;
+            acc += hist[c];
+        }
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += stride) {
+        if (threadIdx.x < SEG_CLASSES) sh_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t s = j0 + threadIdx.x;
+        uint32_t cls = 0, mine = 0;
+        if (s < n) {
+            cls = seg_class(seg_begin[s + 1] - seg_begin[s]);
+            mine = atomicAdd(&sh_cnt[cls], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < SEG_CLASSES && sh_cnt[threadIdx.x]) sh_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], sh_cnt[threadIdx.x]);
+        __syncthreads();
+        if (s < n) perm[start[cls] + sh_base[cls] + mine] = s;
+        __syncthreads();
+    }
+}
+// One thread per segment, 32 segments of about the same length per warp -- but a thread that walks its own hit list
+// straight from global memory touches a different 128-byte line than its 31 neighbours on every step, and with ~10^5 such
+// streams open at once the lines are evicted from L1 and L2 before their other seven hits are used (ncu r02: better
+// balanced warps made the kernel SLOWER, 1.1 -> 1.6 ms).  So the warp refills a small shared-memory window for all its
+// segments together: FS_CHUNK hits per lane, fetched with coalesced loads (eight lanes read the eight positions / payloads
+// of one segment: one sector / one line), then every lane steps its FSM through its own window.  Each line of the hit
+// arrays is read once.
+constexpr int FS_CHUNK = 8, FS_BLK = 128;
+constexpr int FS_PSTRIDE = FS_CHUNK + 1; // padded strides: conflict-free shared-memory reads by lane
+__global__ __launch_bounds__(FS_BLK) void k_fsm_seg(const uint64_t* __restrict__ voff, uint64_t nv, const uint32_t* __restrict__ hit_pos,
+                                                    const int4* __restrict__ hit_payload, const uint32_t* __restrict__ seg_begin,
+                                                    const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ perm,
+                                                    const uint32_t* __restrict__ lo, KgFsmParams p, KgDevCall* __restrict__ sparse,
+                                                    uint2* __restrict__ seg_cnt, uint32_t* __restrict__ seg_v, int2* __restrict__ run) {
+    __shared__ uint32_t s_pos[FS_BLK / 32][32 * FS_PSTRIDE];
+    __shared__ int4 s_pl[FS_BLK / 32][32 * FS_PSTRIDE];
+    const uint32_t ns = nseg[0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane >> 3, k8 = lane & 7; // refill: lane = (which of four segments, which of its next eight hits)
+    uint32_t* wpos = s_pos[warp];
+    int4* wpl = s_pl[warp];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t t0 = blockIdx.x * blockDim.x + warp * 32; t0 < ns; t0 += stride) { // t0 is warp-uniform
+        const uint32_t tix = t0 + (uint32_t)lane;
+        const bool have = tix < ns;
+        uint32_t j = 0, a = 0, b = 0, v = 0, base = 0;
+        KgFsmSeg f;
+        f.begin(0);
+        if (have) {
+            j = perm[tix];
+            a = seg_begin[j];
+            b = seg_begin[j + 1];
+            v = (uint32_t)seq_of(voff, nv, hit_pos[a]);
+            base = (uint32_t)voff[v];
+            f.begin((int)(a - lo[v])); // HIT lines of this container printed before the segment
+        }
+        SparseEmit emit{sparse + a / (uint32_t)p.min_hits};
+        KgSegRuns runs{run + a, 0u};
+        // software pipeline: the loads of window w+1 are in flight (in registers) while the lanes step through window w
+        uint32_t i = a;
+        uint32_t rp[32 / 4];
+        int4 rl[32 / 4];
+        auto fetch = [&](uint32_t from) {
+#pragma unroll
+            for (int t = 0; t < 32 / 4; t++) {
+                const int src = 4 * t + sub;
+                const uint32_t is = __shfl_sync(0xFFFFFFFFu, from, src), bs = __shfl_sync(0xFFFFFFFFu, b, src);
+                const uint32_t idx = min(is + (uint32_t)k8, bs ? bs - 1 : 0u); // clamped: a valid hit, never used past the end
+                rp[t] = hit_pos[idx];
+                rl[t] = hit_payload[idx];
+            }
+        };
+        fetch(i);
+        while (__any_sync(0xFFFFFFFFu, i < b)) {
+#pragma unroll
+            for (int t = 0; t < 32 / 4; t++) {
+                wpos[(4 * t + sub) * FS_PSTRIDE + k8] = rp[t];
+                wpl[(4 * t + sub) * FS_PSTRIDE + k8] = rl[t];
+            }
+            __syncwarp();
+            const uint32_t inext = min(b, i + FS_CHUNK);
+            if (__any_sync(0xFFFFFFFFu, inext < b)) fetch(inext);
+#pragma unroll 1
+            for (int k = 0; k < FS_CHUNK; k++) {
+                if (i + k < b) {
+                    const uint32_t pos = wpos[lane * FS_PSTRIDE + k];
+                    const int4 pl = wpl[lane * FS_PSTRIDE + k];
+                    KgHitLite h = {(int)(pos - base), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
+                    f.hit(p, h, emit, runs);
+                }
+            }
+            i = inext;
+            __syncwarp();
+        }
+        if (have) {
+            // In the reference the run that ends at a gap is processed when the NEXT hit of the container arrives, after that
+            // hit's HIT line (KGJ:472-480); only the container's last run is processed after the loop (KGJ:511-513).
+            if (j + 1 < ns && (uint64_t)hit_pos[b] < voff[v + 1]) f.consumed++;
+            f.end(p, emit, runs);
+            seg_cnt[j] = make_uint2((uint32_t)f.ncalls, runs.n);
+            seg_v[j] = v;
+        }
+    }
+}
+// Exclusive scan of the (calls, OTU runs) pairs over a count that lives on the device: three small launches with a fixed grid
+// (per-block sums over contiguous chunks, one block scans the sums, every block scans its chunk).
+constexpr int SCAN_BLOCKS = 256, SCAN_BLK = 256;
+__device__ __forceinline__ uint2 add2(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ uint2 shfl_up2(uint2 v, int d) {
+    return make_uint2(__shfl_up_sync(0xFFFFFFFFu, v.x, d), __shfl_up_sync(0xFFFFFFFFu, v.y, d));
+}
+// inclusive scan across the block; returns the block total in `total`
+__device__ __forceinline__ uint2 block_scan2(uint2 v, uint2* s_w /* SCAN_BLK / 32 */, uint2& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint2 y = shfl_up2(x, d);
+        if (lane >= d) x = add2(x, y);
+    }
+    __syncthreads(); // s_w may still be read from the previous call
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint2 wbase = make_uint2(0, 0), all = make_uint2(0, 0);
+#pragma unroll
+    for (int w = 0; w < SCAN_BLK / 32; w++) {
+        if (w < warp) wbase = add2(wbase, s_w[w]);
+        all = add2(all, s_w[w]);
+    }
+    total = all;
+    return add2(x, wbase);
+}
+__device__ __forceinline__ void scan_chunk(uint32_t n, uint32_t& c0, uint32_t& c1) {
+    const uint32_t per = ((n + SCAN_BLOCKS - 1) / SCAN_BLOCKS + SCAN_BLK - 1) / SCAN_BLK * SCAN_BLK;
+    c0 = min(n, blockIdx.x * per);
+    c1 = min(n, c0 + per);
+}
+__global__ __launch_bounds__(SCAN_BLK) void k_scan2_sums(const uint2* __restrict__ in, const uint32_t* __restrict__ nptr, uint2* __restrict__ part) {
+    __shared__ uint2 s_w[SCAN_BLK / 32];
+    uint32_t c0, c1;
+    scan_chunk(nptr[0], c0, c1);
+    uint2 acc = make_uint2(0, 0);
+    for (uint32_t i = c0 + threadIdx.x; i < c1; i += SCAN_BLK) acc = add2(acc, in[i]);
+    uint2 total;
+    block_scan2(acc, s_w, total);
+    if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+__global__ __launch_bounds__(SCAN_BLK) void k_scan2_top(uint2* __restrict__ part, const uint32_t* __restrict__ nptr, uint2* __restrict__ out,
+                                                        uint32_t* __restrict__ totals) {
+    static_assert(SCAN_BLOCKS == SCAN_BLK, "one pass");
+    __shared__ uint2 s_w[SCAN_BLK / 32];
+    const uint2 v = part[threadIdx.x];
+    uint2 total;
+    const uint2 inc = block_scan2(v, s_w, total);
+    part[threadIdx.x] = make_uint2(inc.x - v.x, inc.y - v.y);
+    if (threadIdx.x == 0) {
+        out[nptr[0]] = total;
+        totals[0] = total.x;
+        totals[1] = total.y;
+    }
+}
+__global__ __launch_bounds__(SCAN_BLK) void k_scan2_apply(const uint2* __restrict__ in, const uint32_t* __restrict__ nptr, const uint2* __restrict__ part,
+                                                          uint2* __restrict__ out) {
+    __shared__ uint2 s_w[SCAN_BLK / 32];
+    uint32_t c0, c1;
+    scan_chunk(nptr[0], c0, c1);
+    uint2 run = part[blockIdx.x];
+    for (uint32_t i0 = c0; i0 < c1; i0 += SCAN_BLK) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint2 v = i < c1 ? in[i] : make_uint2(0, 0);
+        uint2 total;
+        const uint2 inc = block_scan2(v, s_w, total);
+        if (i < c1) out[i] = make_uint2(run.x + inc.x - v.x, run.y + inc.y - v.y);
+        run = add2(run, total);
+    }
+}
+// calls (tagged with sequence and frame) and OTU runs, packed in segment order = print order (+0,+1,+2,-0,-1,-2 and
+// ascending positions, KGJ:540-557)
+__global__ __launch_bounds__(256) void k_compact_seg(const KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ seg_begin,
+                                                     const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ seg_v,
+                                                     const uint2* __restrict__ seg_off, const int2* __restrict__ run, int per_seq,
+                                                     int min_hits, uint32_t seq_base, kg_call* __restrict__ out, int2* __restrict__ dense) {
+    const uint32_t ns = nseg[0];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < ns; j += gridDim.x * blockDim.x) {
+        const uint2 o = seg_off[j], e = seg_off[j + 1];
+        if (o.x == e.x) continue; // no call, hence no runs either
+        const uint32_t a = seg_begin[j], v = seg_v[j];
+        const KgDevCall* src = sparse + a / (uint32_t)min_hits;
+        for (uint32_t k = 0; k < e.x - o.x; k++) {
+            const KgDevCall d = src[k];
+            kg_call r;
+            r.seq = seq_base + v / (uint32_t)per_seq;
+            r.strand_frame = (int32_t)(v % (uint32_t)per_seq);
+            r.start = d.start;
+            r.end = d.end;
+            r.count = d.count;
+            r.fI = d.fI;
+            r.weighted = d.weighted;
+            r.hits_before = d.hits_before;
+            out[o.x + k] = r;
+        }
+        for (uint32_t k = 0; k < e.y - o.y; k++) dense[o.y + k] = run[a + k];
     }
 }
 // OTU-COUNTS (KGJ:413-438, 516-524): replay, in order, the OTU index of every hit a CALL counted.  Only the fold of the
 // five-entry buffer is inherently sequential per sequence.  k_fsm_seg leaves, per segment, the run-length encoded OTU
-// indices of its calls (sparse slots from the segment's first hit index); k_compact_runs packs them in segment order
-// (= print order: +0,+1,+2,-0,-1,-2 and ascending positions, KGJ:540-557) and k_otu_fold folds one sequence per warp.
-__global__ void k_compact_runs(const uint32_t* __restrict__ seg_begin, const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ run_off,
-                               const int* __restrict__ run_oi, const uint32_t* __restrict__ run_m, uint32_t cap,
-                               int* __restrict__ dense_oi, uint32_t* __restrict__ dense_m) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cap || j >= nseg[0]) return;
-    const uint32_t o = run_off[j], c = run_off[j + 1] - o, a = seg_begin[j];
-    for (uint32_t k = 0; k < c; k++) {
-        dense_oi[o + k] = run_oi[a + k];
-        dense_m[o + k] = run_m[a + k];
-    }
-}
-// One warp per sequence: 32 runs arrive per coalesced load, every lane then applies them in order (all lanes hold the
-// same buffer; the updates depend on each other, the loads do not).
-__global__ __launch_bounds__(128) void k_otu_fold(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const uint32_t* __restrict__ seg_id,
-                                                  const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ run_off,
-                                                  const int* __restrict__ dense_oi, const uint32_t* __restrict__ dense_m,
-                                                  const uint32_t* __restrict__ tile_out, uint32_t ntiles, kg_otu* __restrict__ otus,
-                                                  const unsigned long long* __restrict__ ctr) {
-    const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+// indices of its calls; k_compact_seg packs them in print order; here one warp folds one sequence: 32 runs arrive per
+// coalesced load (the next 32 are already on their way) and wait in shared memory, every lane applies them in order (all
+// lanes hold the same buffer).  The update has no branch (kg_otu_update_n) and the shared-memory reads do not depend on
+// the buffer, so what is left is the dependent chain of the updates themselves (~5 k per 5 Mbp contig).
+__global__ __launch_bounds__(32) void k_otu_fold(const uint32_t* __restrict__ lo, uint64_t nseq, int per_seq, const uint32_t* __restrict__ seg_begin,
+                                                 const uint32_t* __restrict__ nseg, const uint2* __restrict__ seg_off,
+                                                 const int2* __restrict__ dense, kg_otu* __restrict__ otus,
+                                                 const unsigned long long* __restrict__ ctr) {
+    __shared__ int2 s_run[2][32];
+    const uint64_t s = blockIdx.x;
+    const int lane = threadIdx.x;
     if (s >= nseq || ctr[KG_CTR_OVERFLOW]) return;
-    const uint32_t nhits = tile_out[ntiles];
-    const uint32_t a = lo[s * per_seq], b = lo[(s + 1) * per_seq];
-    // the first hit of a container always starts a segment, so these are segment numbers (seg_id = inclusive scan of starts)
-    const uint32_t sa = a < nhits ? seg_id[a] - 1 : nseg[0], sb = b < nhits ? seg_id[b] - 1 : nseg[0];
-    const uint32_t r0 = run_off[sa], r1 = run_off[sb];
+    const uint32_t ns = nseg[0];
+    // the first hit of a container always starts a segment: the sequence's runs are those of the segments from the one that
+    // begins at lo[first container] up to the one that begins at lo[first container of the next sequence]
+    uint32_t rr[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const uint32_t a = lo[(s + e) * per_seq];
+        uint32_t x = 0, y = ns; // first segment with seg_begin >= a (seg_begin[ns] = number of hits)
+        while (x < y) {
+            const uint32_t mid = (x + y) >> 1;
+            if (seg_begin[mid] < a) x = mid + 1;
+            else y = mid;
+        }
+        rr[e] = seg_off[x].y;
+    }
+    const uint32_t r0 = rr[0], r1 = rr[1];
     KgOtuBuf u;
     kg_otu_clear(u);
-    for (uint32_t r = r0; r < r1; r += 32) {
-        const uint32_t idx = r + (uint32_t)lane;
-        const int o = idx < r1 ? dense_oi[idx] : 0;
-        const uint32_t m = idx < r1 ? dense_m[idx] : 0u;
+    int2 nxt = r0 + lane < r1 ? dense[r0 + lane] : make_int2(0, 0);
+    int buf = 0;
+    for (uint32_t r = r0; r < r1; r += 32, buf ^= 1) {
+        s_run[buf][lane] = nxt;
+        __syncwarp();
+        const uint32_t idx = r + 32 + (uint32_t)lane;
+        nxt = idx < r1 ? dense[idx] : make_int2(0, 0);
         const int cnt = (int)min(32u, r1 - r);
-        for (int k = 0; k < cnt; k++) kg_otu_update_n(u, __shfl_sync(0xFFFFFFFFu, o, k), (int)__shfl_sync(0xFFFFFFFFu, m, k));
+        if (cnt == 32) {
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const int2 q = s_run[buf][k];
+                kg_otu_update_n(u, q.x, q.y);
+            }
+        } else {
+            for (int k = 0; k < cnt; k++) {
+                const int2 q = s_run[buf][k];
+                kg_otu_update_n(u, q.x, q.y);
+            }
+        }
     }
     if (lane == 0) {
         kg_otu o;
@@ -1320,8 +1624,8 @@ struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them le
     DevBuf queue, tile_qcnt;                                     // probe cascade: survivors (8 KB slice per tile) and their counts
     DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
     DevBuf fk_a, fi_a;                                           // per-sequence path: class histogram / cursors, sequence permutation
-    DevBuf hit_v, seg_flag, seg_id, seg_begin, nseg;              // segment path
-    DevBuf o_oi, o_cidx, o_c01, o_crank, o_run_oi, o_run_crank;  // segment path: OTU runs (sparse oI / length, per-segment count, its scan, dense oI / length)
+    DevBuf seg_tmp, seg_v, seg_perm, seg_begin, seg_cnt, seg_off, nseg, tile_bnd, blk_cnt, blk_off, scan_part; // segment path
+    DevBuf o_run, o_dense;                                       // segment path: OTU runs (oI, length) per segment (sparse) and packed in print order
     bool seg = false;                                            // which FSM path the enqueued run uses
     uint64_t* h_ctr = nullptr; // pinned, KG_CTR_COUNT + 1 (the last slot receives the call total)
     cudaEvent_t ev[6] = {};    // begin, probe begin, probe end, end, cascade: first filter done, second filter done
@@ -1425,13 +1729,6 @@ int exclusive_sum_u32(kg_context* ctx, const uint32_t* in, uint32_t* out, size_t
     CU(cub::DeviceScan::ExclusiveSum(scan_tmp_of(ctx, st).p, bytes, in, out, n, st));
     return KG_OK;
 }
-int inclusive_sum_u32(kg_context* ctx, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
-    size_t bytes = 0;
-    CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, n, st));
-    KG_TRY(scan_tmp_of(ctx, st).ensure(bytes));
-    CU(cub::DeviceScan::InclusiveSum(scan_tmp_of(ctx, st).p, bytes, in, out, n, st));
-    return KG_OK;
-}
 int exclusive_sum_u64(kg_context* ctx, const uint64_t* in, uint64_t* out, size_t n, cudaStream_t st) {
     size_t bytes = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, st));
@@ -1496,9 +1793,9 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     RunScratch& sc = scratch_of(ctx);
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
-                          &sl.call_off, &sl.ctr, &sl.otu_cnt, &sl.otu_first, &sl.queue, &sl.tile_qcnt, &sl.hit_pos, &sl.hit_payload, &sl.hit_v, &sl.seg_flag, &sl.seg_id, &sl.seg_begin,
-                          &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_crank,
-                          &sl.o_run_oi, &sl.o_run_crank})
+                          &sl.call_off, &sl.ctr, &sl.otu_cnt, &sl.otu_first, &sl.queue, &sl.tile_qcnt, &sl.hit_pos, &sl.hit_payload, &sl.seg_tmp, &sl.seg_v, &sl.seg_perm, &sl.seg_begin,
+                          &sl.seg_cnt, &sl.seg_off, &sl.tile_bnd, &sl.blk_cnt, &sl.blk_off, &sl.scan_part,
+                          &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_run, &sl.o_dense})
             b->release();
         if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
         for (auto& e : sl.ev)
@@ -1851,50 +2148,59 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
         CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
     } else { // long contigs: position-ordered hits -> segments at gaps > max_gap -> one thread per segment -> OTU replay
         const uint32_t cap = (uint32_t)hit_cap;
+        const uint32_t nblk = blocks_for(ntiles, GATHER_TILES);
         KG_TRY(sl.hit_pos.ensure((size_t)cap * 4));
         KG_TRY(sl.hit_payload.ensure((size_t)cap * sizeof(int4)));
-        KG_TRY(sl.hit_v.ensure((size_t)cap * 4));
-        KG_TRY(sl.seg_flag.ensure((size_t)cap * 4));
-        KG_TRY(sl.seg_id.ensure((size_t)cap * 4));
+        KG_TRY(sl.seg_tmp.ensure((size_t)cap * 4));
+        KG_TRY(sl.seg_v.ensure((size_t)cap * 4));
+        KG_TRY(sl.seg_perm.ensure((size_t)cap * 4));
         KG_TRY(sl.seg_begin.ensure(((size_t)cap + 1) * 4));
+        KG_TRY(sl.seg_cnt.ensure(((size_t)cap + 1) * 8));
+        KG_TRY(sl.seg_off.ensure(((size_t)cap + 1) * 8));
         KG_TRY(sl.nseg.ensure(16));
-        KG_TRY(sl.call_cnt.ensure(((size_t)cap + 1) * 4)); // per segment here
-        KG_TRY(sl.call_off.ensure(((size_t)cap + 1) * 4));
+        KG_TRY(sl.tile_bnd.ensure((size_t)ntiles + 1));
+        KG_TRY(sl.blk_cnt.ensure(((size_t)nblk + 1) * 4));
+        KG_TRY(sl.blk_off.ensure(((size_t)nblk + 1) * 4));
+        KG_TRY(sl.scan_part.ensure(SCAN_BLOCKS * 8));
+        KG_TRY(sl.fk_a.ensure(2 * SEG_CLASSES * 4));
+        KG_TRY(sl.o_run.ensure(((size_t)cap + 1) * 8));
+        KG_TRY(sl.o_dense.ensure(((size_t)cap + 1) * 8));
+        uint32_t* nseg = sl.nseg.as<uint32_t>(); // [0] segments, [2] calls, [3] OTU runs
+        uint32_t* hist = sl.fk_a.as<uint32_t>();
+        const unsigned wide = (unsigned)ctx->sm_count * 8; // grid of the kernels that walk a device-side count
+        CU(cudaMemsetAsync(sl.tile_bnd.p, 0, (size_t)ntiles + 1, st));
+        CU(cudaMemsetAsync(hist, 0, 2 * SEG_CLASSES * 4, st));
+        CU(cudaMemsetAsync(nseg, 0, 16, st));
+        if (nv) k_tile_bnd<<<blocks_for(nv, 256), 256, 0, st>>>(b->voffsets(), nv, ntiles, sl.tile_bnd.as<uint8_t>());
         if (ntiles) {
-            k_gather<<<blocks_for(ntiles, GATHER_TILES), 256, 0, st>>>(sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(),
-                                                                          sl.tile_base.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
-                                                                          sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), d_ctr);
-            sl.launches++;
+            k_gather_seg<<<nblk, GS_BLK, 0, st>>>(sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(), sl.tile_base.as<uint32_t>(),
+                                                  sl.tile_out.as<uint32_t>(), ntiles, b->voffsets(), nv, sl.tile_bnd.as<uint8_t>(), prm->max_gap,
+                                                  sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), sl.seg_tmp.as<uint32_t>(),
+                                                  sl.blk_cnt.as<uint32_t>(), d_ctr);
+            k_seg_offsets<<<1, 1024, 0, st>>>(sl.blk_cnt.as<uint32_t>(), nblk, sl.blk_off.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
+                                              sl.seg_begin.as<uint32_t>(), nseg, d_ctr);
+            k_seg_place<<<nblk, GS_BLK, 0, st>>>(sl.seg_tmp.as<uint32_t>(), sl.blk_cnt.as<uint32_t>(), sl.blk_off.as<uint32_t>(),
+                                                 sl.tile_out.as<uint32_t>(), sl.seg_begin.as<uint32_t>());
         }
-        k_seg_flags<<<blocks_for(cap, 256), 256, 0, st>>>(b->voffsets(), nv, sl.hit_pos.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles, cap,
-                                                         prm->max_gap, sl.hit_v.as<uint32_t>(), sl.seg_flag.as<uint32_t>(), d_ctr);
-        KG_TRY(inclusive_sum_u32(ctx, sl.seg_flag.as<uint32_t>(), sl.seg_id.as<uint32_t>(), cap, st));
-        k_seg_begin<<<blocks_for(cap, 256), 256, 0, st>>>(sl.seg_flag.as<uint32_t>(), sl.seg_id.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
-                                                         cap, sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), d_ctr);
         k_lo<<<blocks_for(nv + 1, 256), 256, 0, st>>>(b->voffsets(), nv, sl.hit_pos.as<uint32_t>(), sl.tile_out.as<uint32_t>(), ntiles,
                                                      sl.lo.as<uint32_t>(), d_ctr);
-        for (DevBuf* d : {&sl.o_oi, &sl.o_cidx, &sl.o_c01, &sl.o_crank, &sl.o_run_oi, &sl.o_run_crank}) KG_TRY(d->ensure(((size_t)cap + 1) * 4));
-        k_fsm_seg<<<blocks_for(cap, 128), 128, 0, st>>>(b->voffsets(), sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), sl.hit_v.as<uint32_t>(),
-                                                       sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), sl.lo.as<uint32_t>(), cap, fp,
-                                                       sl.sparse.as<KgDevCall>(), sl.call_cnt.as<uint32_t>(), sl.o_oi.as<int>(),
-                                                       sl.o_cidx.as<uint32_t>(), sl.o_c01.as<uint32_t>());
-        CU(cudaMemsetAsync(sl.call_cnt.as<uint32_t>() + cap, 0, 4, st));
-        KG_TRY(exclusive_sum_u32(ctx, sl.call_cnt.as<uint32_t>(), sl.call_off.as<uint32_t>(), (size_t)cap + 1, st));
-        k_compact_calls_seg<<<blocks_for(cap, 256), 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(),
-                                                                 sl.hit_v.as<uint32_t>(), sl.call_off.as<uint32_t>(), cap, per_seq, prm->min_hits,
-                                                                 seq_base, r->d_calls.as<kg_call>());
-        // OTU-COUNTS: the runs k_fsm_seg listed per segment, packed in print order, folded one sequence per warp
-        CU(cudaMemsetAsync(sl.o_c01.as<uint32_t>() + cap, 0, 4, st));
-        KG_TRY(exclusive_sum_u32(ctx, sl.o_c01.as<uint32_t>(), sl.o_crank.as<uint32_t>(), (size_t)cap + 1, st));
-        k_compact_runs<<<blocks_for(cap, 256), 256, 0, st>>>(sl.seg_begin.as<uint32_t>(), sl.nseg.as<uint32_t>(), sl.o_crank.as<uint32_t>(),
-                                                            sl.o_oi.as<int>(), sl.o_cidx.as<uint32_t>(), cap, sl.o_run_oi.as<int>(),
-                                                            sl.o_run_crank.as<uint32_t>());
+        k_seg_hist<<<wide, 256, 0, st>>>(sl.seg_begin.as<uint32_t>(), nseg, hist);
+        k_seg_scatter<<<wide, 256, 0, st>>>(sl.seg_begin.as<uint32_t>(), nseg, hist, hist + SEG_CLASSES, sl.seg_perm.as<uint32_t>());
+        k_fsm_seg<<<wide * 2, FS_BLK, 0, st>>>(b->voffsets(), nv, sl.hit_pos.as<uint32_t>(), sl.hit_payload.as<int4>(), sl.seg_begin.as<uint32_t>(),
+                                            nseg, sl.seg_perm.as<uint32_t>(), sl.lo.as<uint32_t>(), fp, sl.sparse.as<KgDevCall>(),
+                                            sl.seg_cnt.as<uint2>(), sl.seg_v.as<uint32_t>(), sl.o_run.as<int2>());
+        k_scan2_sums<<<SCAN_BLOCKS, SCAN_BLK, 0, st>>>(sl.seg_cnt.as<uint2>(), nseg, sl.scan_part.as<uint2>());
+        k_scan2_top<<<1, SCAN_BLK, 0, st>>>(sl.scan_part.as<uint2>(), nseg, sl.seg_off.as<uint2>(), nseg + 2);
+        k_scan2_apply<<<SCAN_BLOCKS, SCAN_BLK, 0, st>>>(sl.seg_cnt.as<uint2>(), nseg, sl.scan_part.as<uint2>(), sl.seg_off.as<uint2>());
+        k_compact_seg<<<wide, 256, 0, st>>>(sl.sparse.as<KgDevCall>(), sl.seg_begin.as<uint32_t>(), nseg, sl.seg_v.as<uint32_t>(),
+                                            sl.seg_off.as<uint2>(), sl.o_run.as<int2>(), per_seq, prm->min_hits, seq_base,
+                                            r->d_calls.as<kg_call>(), sl.o_dense.as<int2>());
+        // OTU-COUNTS: the runs k_fsm_seg listed per segment, packed in print order, folded one sequence per thread
         if (b->n)
-            k_otu_fold<<<blocks_for(b->n * 32, 128), 128, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.seg_id.as<uint32_t>(), sl.nseg.as<uint32_t>(),
-                                                                  sl.o_crank.as<uint32_t>(), sl.o_run_oi.as<int>(), sl.o_run_crank.as<uint32_t>(),
-                                                                  sl.tile_out.as<uint32_t>(), ntiles, r->d_otus.as<kg_otu>(), d_ctr);
-        sl.launches += 10;
-        CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], sl.call_off.as<uint32_t>() + cap, 4, cudaMemcpyDeviceToHost, st));
+            k_otu_fold<<<(unsigned)b->n, 32, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, sl.seg_begin.as<uint32_t>(), nseg,
+                                                      sl.seg_off.as<uint2>(), sl.o_dense.as<int2>(), r->d_otus.as<kg_otu>(), d_ctr);
+        sl.launches += 13;
+        CU(cudaMemcpyAsync(&sl.h_ctr[KG_CTR_COUNT], nseg + 2, 4, cudaMemcpyDeviceToHost, st));
     }
     sl.h_ctr[KG_CTR_COUNT + 1] = 0;
     if (r->want_compact_otus && b->n) { // kg_run: the OTU counts go home as a count byte per sequence + the used pairs
@@ -1969,6 +2275,19 @@ static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_
         launches += 2;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
+    }
+    if (sl.seg && getenv("KG_DEBUG_SEG")) { // developer aid: segment length distribution of this run
+        uint32_t ns = 0, tot[2] = {0, 0};
+        cudaMemcpy(&ns, sl.nseg.p, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(tot, sl.nseg.as<uint32_t>() + 2, 8, cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> sb((size_t)ns + 1);
+        cudaMemcpy(sb.data(), sl.seg_begin.p, ((size_t)ns + 1) * 4, cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> len(ns);
+        for (uint32_t i = 0; i < ns; i++) len[i] = sb[i + 1] - sb[i];
+        std::sort(len.begin(), len.end());
+        if (ns)
+            fprintf(stderr, "[kg seg] %u segments, %u calls, %u OTU runs; hits/segment median %u p99 %u p99.9 %u max %u\n", ns, tot[0], tot[1],
+                    len[ns / 2], len[(size_t)ns * 99 / 100], len[(size_t)ns * 999 / 1000], len[ns - 1]);
     }
     r->stats.num_sequences = b->n;
     r->stats.num_positions = b->vtotal;
