@@ -1027,82 +1027,110 @@ __global__ void k_fsm_scatter(const uint32_t* __restrict__ lo, uint64_t nseq, in
     }
 }
 
-__global__ __launch_bounds__(128) void k_fsm(const uint64_t* __restrict__ voff, uint64_t nseq, int per_seq,
-                                             const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_out,
-                                             uint32_t ntiles, const uint32_t* __restrict__ chunk_pos,
-                                             const int4* __restrict__ chunk_payload, KgFsmParams p,
-                                             KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ lo,
-                                             const uint32_t* __restrict__ perm, uint32_t* __restrict__ call_cnt,
-                                             kg_otu* __restrict__ otus, const unsigned long long* __restrict__ ctr) {
+// The hits of a sequence are read through a shared-memory window that the warp refills for all its 32 sequences together:
+// FW hits per lane, fetched with coalesced loads (eight lanes read the next eight positions / payloads of one sequence: one
+// sector / one line) instead of 32 lanes each pulling on a line of their own -- with ~10^5 such streams open at once the
+// lines were evicted before their other hits were used and the kernel waited on memory at 41 % occupancy (ncu, r01).
+constexpr int FW = 8, FW_STRIDE = FW + 1, FSM_BLK = 128;
+__global__ __launch_bounds__(FSM_BLK) void k_fsm(const uint64_t* __restrict__ voff, uint64_t nseq, int per_seq,
+                                                 const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ tile_out,
+                                                 uint32_t ntiles, const uint32_t* __restrict__ chunk_pos,
+                                                 const int4* __restrict__ chunk_payload, KgFsmParams p,
+                                                 KgDevCall* __restrict__ sparse, const uint32_t* __restrict__ lo,
+                                                 const uint32_t* __restrict__ perm, uint32_t* __restrict__ call_cnt,
+                                                 kg_otu* __restrict__ otus, const unsigned long long* __restrict__ ctr) {
+    __shared__ uint32_t s_pos[FSM_BLK / 32][32 * FW_STRIDE];
+    __shared__ int4 s_pl[FSM_BLK / 32][32 * FW_STRIDE];
     const uint64_t tix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tix >= nseq) return;
-    const uint64_t s = perm[tix];
+    const bool have = tix < nseq;
+    const uint64_t s = have ? perm[tix] : 0;
     if (ctr[KG_CTR_OVERFLOW]) { // some tile could not claim its chunk: the host repeats the pass with larger buffers
-        for (int k = 0; k < per_seq; k++) call_cnt[s * per_seq + k] = 0;
+        if (have)
+            for (int k = 0; k < per_seq; k++) call_cnt[s * per_seq + k] = 0;
         return;
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane >> 3, k8 = lane & 7; // refill: lane = (which of four sequences, which of its next eight hits)
+    uint32_t* wpos = s_pos[warp];
+    int4* wpl = s_pl[warp];
     KgFsm f;
     f.begin_sequence();
     for (int k = 0; k < per_seq; k++) {
         const uint64_t v = s * per_seq + k;
-        const uint32_t x0 = (uint32_t)voff[v], x1 = (uint32_t)voff[v + 1];
-        uint32_t t = x0 >> TILE_SHIFT;
-        const uint32_t rank = lo[v]; // k_lo_tiles
-        uint32_t e = 0, cnt = 0, base = 0;
-        if (t < ntiles) {
-            const uint32_t o = tile_out[t];
-            cnt = tile_out[t + 1] - o;
-            base = tile_base[t];
-            e = rank - o;
-        }
-        f.begin_container();
-        SparseEmit emit{sparse + rank / (uint32_t)p.min_hits};
-        bool done = x1 <= x0;
-        while (!done && t < ntiles) {
-            // software-pipelined by one hit: the loads of hit e+1 are in flight while hit e goes through the FSM (a long
-            // protein is a chain of ~10^3 dependent steps on one thread; this halves its latency per step)
-            uint32_t g_n = 0;
-            int4 pl_n = make_int4(0, 0, 0, 0);
-            if (e < cnt) {
-                g_n = chunk_pos[base + e];
-                pl_n = chunk_payload[base + e];
-            }
-            while (e < cnt) {
-                const uint32_t g = g_n;
-                const int4 pl = pl_n;
-                e++;
-                if (e < cnt) {
-                    g_n = chunk_pos[base + e];
-                    pl_n = chunk_payload[base + e];
-                }
-                if (g >= x1) {
-                    done = true;
-                    break;
-                }
-                KgHitLite h = {(int)(g - x0), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
-                f.hit(p, h, emit);
-            }
-            if (done) break;
-            t++;
-            if (((uint64_t)t << TILE_SHIFT) >= x1) break;
-            if (t < ntiles) {
+        uint32_t x0 = 0, x1 = 0, t = 0, rank = 0, e = 0, cnt = 0, base = 0;
+        bool done = true;
+        if (have) {
+            x0 = (uint32_t)voff[v];
+            x1 = (uint32_t)voff[v + 1];
+            t = x0 >> TILE_SHIFT;
+            rank = lo[v]; // k_lo_tiles
+            if (t < ntiles && x1 > x0) {
                 const uint32_t o = tile_out[t];
                 cnt = tile_out[t + 1] - o;
                 base = tile_base[t];
-                e = 0;
+                e = rank - o;
+                done = false;
             }
         }
-        f.end_container(p, emit);
-        call_cnt[v] = (uint32_t)f.ncalls;
-    }
-    kg_otu o;
-    o.n = f.otu_c.n;
+        f.begin_container();
+        SparseEmit emit{sparse + rank / (uint32_t)p.min_hits};
+        while (__any_sync(0xFFFFFFFFu, !done)) {
+            const uint32_t rem = done ? 0u : cnt - e;
 #pragma unroll
-    for (int i = 0; i < KG_OI_BUFSZ; i++) {
-        o.count[i] = f.otu_c.c[i];
-        o.oI[i] = f.otu_c.o[i];
+            for (int q = 0; q < 32 / 4; q++) {
+                const int src = 4 * q + sub;
+                const uint32_t from = __shfl_sync(0xFFFFFFFFu, base + e, src), rs = __shfl_sync(0xFFFFFFFFu, rem, src);
+                if ((uint32_t)k8 < rs) {
+                    wpos[src * FW_STRIDE + k8] = chunk_pos[from + k8];
+                    wpl[src * FW_STRIDE + k8] = chunk_payload[from + k8];
+                }
+            }
+            __syncwarp();
+            const uint32_t wn = min(rem, (uint32_t)FW);
+#pragma unroll 1
+            for (int j = 0; j < FW; j++) {
+                if (!done && (uint32_t)j < wn) {
+                    const uint32_t g = wpos[lane * FW_STRIDE + j];
+                    if (g >= x1) {
+                        done = true; // the chunk goes on with the next sequence's hits
+                    } else {
+                        const int4 pl = wpl[lane * FW_STRIDE + j];
+                        KgHitLite h = {(int)(g - x0), pl.z, pl.y, pl.x, __int_as_float(pl.w)};
+                        f.hit(p, h, emit);
+                    }
+                }
+            }
+            __syncwarp();
+            if (!done) {
+                e += wn;
+                if (e >= cnt) { // next tile of this sequence, if any
+                    t++;
+                    if (t >= ntiles || ((uint64_t)t << TILE_SHIFT) >= x1) {
+                        done = true;
+                    } else {
+                        const uint32_t o = tile_out[t];
+                        cnt = tile_out[t + 1] - o;
+                        base = tile_base[t];
+                        e = 0;
+                    }
+                }
+            }
+        }
+        if (have) {
+            f.end_container(p, emit);
+            call_cnt[v] = (uint32_t)f.ncalls;
+        }
     }
-    otus[s] = o;
+    if (have) {
+        kg_otu o;
+        o.n = f.otu_c.n;
+#pragma unroll
+        for (int i = 0; i < KG_OI_BUFSZ; i++) {
+            o.count[i] = f.otu_c.c[i];
+            o.oI[i] = f.otu_c.o[i];
+        }
+        otus[s] = o;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -2131,7 +2159,7 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
             CU(cudaMemsetAsync(hist, 0, 2 * FSM_CLASSES * 4, st));
             k_fsm_hist<<<blocks_for(b->n, 256), 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, hist);
             k_fsm_scatter<<<blocks_for(b->n, 256), 256, 0, st>>>(sl.lo.as<uint32_t>(), b->n, per_seq, hist, hist + FSM_CLASSES, sl.fi_a.as<uint32_t>());
-            k_fsm<<<blocks_for(b->n, 128), 128, 0, st>>>(b->voffsets(), b->n, per_seq, sl.tile_base.as<uint32_t>(),
+            k_fsm<<<blocks_for(b->n, FSM_BLK), FSM_BLK, 0, st>>>(b->voffsets(), b->n, per_seq, sl.tile_base.as<uint32_t>(),
                                                         sl.tile_out.as<uint32_t>(), ntiles, sl.chunk_pos.as<uint32_t>(),
                                                         sl.chunk_payload.as<int4>(), fp, sl.sparse.as<KgDevCall>(), sl.lo.as<uint32_t>(),
                                                         sl.fi_a.as<uint32_t>(), sl.call_cnt.as<uint32_t>(), r->d_otus.as<kg_otu>(), d_ctr);
