@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e2", action="store_true", help="skip the two-thread variant of the end-to-end measurement")
     ap.add_argument("--no-legs", action="store_true", help="skip the configs[2] / [3] / [4] legs")
+    ap.add_argument("--no-table-load", action="store_true", help="skip the reference-format table load measurement")
     ap.add_argument("--legs", default="2,3,4", help="which legs to run")
     ap.add_argument("--orfs", type=int, default=100_000_000, help="configs[3]: proteins in the whole job")
     ap.add_argument("--c4-families", type=int, default=0, help="configs[4]: families (0 = 1.4 M per GPU, ~2e9 signatures on 8 GPUs)")
@@ -323,7 +324,7 @@ def run_ours(args):
                 "kernel_share_of_step": round(float(np.mean(probe_ms)) / float(np.mean(dev_ms)), 4)}
 
     # ---- CPU baseline + parity on the whole step (rank 0, N=1 only) ----
-    cpu = parity = full = None
+    cpu = parity = full = table_load = None
     otable = None
     threads = os.cpu_count() or 1
     want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
@@ -381,6 +382,9 @@ def run_ours(args):
                                                    f"table instead of the stream join (not the reference's algorithm: best-effort CPU); {s2_:.1f} s"}
         log("cpu rows done")
         del ref, r1, r2, sb, off
+        if not args.no_table_load:
+            table_load = legs.table_load(kg, ctx, img, table, batch, params, log=log)
+            log("table load leg done")
 
         # size-independent property at FULL size: lookups, hits and a checksum over every hit's (position, payload) must
         # equal those of the naive one-thread-per-position kernel (no prefilter, no queue, byte-wise reads, full table lookup)
@@ -428,7 +432,7 @@ def run_ours(args):
                        "hits_per_step": stats_keep["hits"], "calls_per_step": stats_keep["calls"]},
             "proteins_per_s": float(args.proteins * args.steps * world) / dt,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "parity": parity, "parity_full_size": full, "prep": prep,
+            "parity": parity, "parity_full_size": full, "prep": prep, "table_load": table_load,
             "stage_ms": {"prepare": round(stats_keep["prepare"], 4), "probe": round(stats_keep["probe"], 4),
                          "group": round(stats_keep["group"], 4), "device_total": round(stats_keep["device"], 4)},
         }

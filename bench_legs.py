@@ -54,6 +54,87 @@ def _pinned_copy(kg, ctx, torch, d_ptr, nbytes, dtype=None, pad=0):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# loading the reference-format kmer.table.mem_map[.gz] (kg_table_load_file: the host only moves bytes, the
+# slots are parsed on the device).  The 200M-signature image the CPU arm uses is written to a scratch file, loaded back and
+# the loaded table must answer the headline batch exactly like the table built from the device-side generator.
+# ---------------------------------------------------------------------------------------------------------------------
+def _scratch_dir(nbytes):
+    for d in (os.environ.get("KG_BENCH_TMP"), "/dev/shm", "/tmp"):
+        if d and os.path.isdir(d):
+            st = os.statvfs(d)
+            if st.f_bavail * st.f_frsize > nbytes + (1 << 30):
+                return d
+    return None
+
+
+def table_load(kg, ctx, img, table, batch, params, gz_bytes=256 << 20, log=lambda m: None):
+    import gzip
+    import tempfile
+    out = {"what": "kg_table_load_file on the reference's own format (24-byte header + 24-byte slots, KGJ:933-935, 995-999)"}
+    nbytes = int(img.nbytes)
+    d = _scratch_dir(nbytes)
+    if d is None:
+        out["skipped"] = "no scratch directory with %.1f GB free" % (nbytes / 1e9)
+        return out
+    tmp = tempfile.mkdtemp(prefix="kg_table_", dir=d)
+    plain = os.path.join(tmp, "kmer.table.mem_map")
+    try:
+        t0 = time.time()
+        with open(plain, "wb") as f:
+            step = 256 << 20
+            for o in range(0, nbytes, step):
+                f.write(memoryview(img[o:o + step]))
+        out["write_s"] = round(time.time() - t0, 2)
+        log(f"table image written to {plain} ({nbytes / 1e9:.1f} GB, {out['write_s']} s)")
+        ref = ctx.run_batch(table, batch, params)
+        want = (ref.stats.num_kmers, ref.stats.num_hits, ref.stats.num_calls, int(table.info.num_signatures))
+        ref.free()
+        secs = []
+        for _ in range(2):   # the second load reads the page cache only
+            t0 = time.time()
+            t2 = ctx.load_table_file(plain)
+            secs.append(time.time() - t0)
+            got = ctx.run_batch(t2, batch, params)
+            have = (got.stats.num_kmers, got.stats.num_hits, got.stats.num_calls, int(t2.info.num_signatures))
+            info = t2.info
+            got.free()
+            t2.free()
+            if have != want:
+                raise SystemExit(f"table loaded from the file answers differently: {have} vs {want}")
+        table.attach(ctx)   # the persisting-L2 window goes back to the bench's own table
+        out.update({"file_bytes": nbytes, "slots": int(info.num_slots), "signatures": int(info.num_signatures),
+                    "unreachable": int(info.num_unreachable), "tail_run": int(info.tail_run),
+                    "load_s": [round(x, 3) for x in secs], "table_load_s": round(min(secs), 3), "GBps": round(nbytes / min(secs) / 1e9, 2),
+                    "parity": "the loaded table answers the headline batch like the generated one (lookups, hits, calls, signatures)"})
+        # .gz: inflate (one thread, zlib) is the bound; a prefix of the image with a patched slot count keeps this short
+        nslots = min((gz_bytes - 24) // 24, (nbytes - 24) // 24)
+        small = np.empty(24 + 24 * nslots, dtype=np.uint8)
+        small[:] = img[:small.size]
+        small[:8].view(np.int64)[0] = nslots
+        gzp = os.path.join(tmp, "small.mem_map.gz")
+        with gzip.open(gzp, "wb", compresslevel=1) as f:
+            f.write(memoryview(small))
+        t0 = time.time()
+        t3 = ctx.load_table_file(gzp)
+        gz_s = time.time() - t0
+        t4 = ctx.table_from_image(small)
+        same = (int(t3.info.num_signatures), int(t3.info.num_unreachable), int(t3.info.tail_run)) == \
+               (int(t4.info.num_signatures), int(t4.info.num_unreachable), int(t4.info.tail_run))
+        t3.free()
+        t4.free()
+        table.attach(ctx)
+        if not same:
+            raise SystemExit(".gz load and in-memory image load disagree")
+        out["gz"] = {"inflated_bytes": int(small.size), "file_bytes": os.path.getsize(gzp), "load_s": round(gz_s, 3),
+                     "inflated_GBps": round(small.size / gz_s / 1e9, 3), "note": "one zlib inflate thread feeds the same device-side parser"}
+    finally:
+        for fn in os.listdir(tmp):
+            os.remove(os.path.join(tmp, fn))
+        os.rmdir(tmp)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # configs[2]: 6-frame contig mode, G synthetic genomes of L bp against the replicated table
 # ---------------------------------------------------------------------------------------------------------------------
 def configs2(kg, ctx, table, u, plumb, genomes=50, length=5_000_000, steps=5, warmup=3, e2e=True, otable=None,

@@ -186,6 +186,12 @@ class Context:
         _check(lib().kg_table_load(self._h, data_dir.encode(), C.byref(h)))
         return Table(self, h)
 
+    def load_table_file(self, path: str) -> "Table":
+        """One reference-format file (kmer.table.mem_map, or .gz by its suffix, KGJ:927)."""
+        h = C.c_void_p()
+        _check(lib().kg_table_load_file(self._h, path.encode(), C.byref(h)))
+        return Table(self, h)
+
     def load_table_cached(self, path: str, data_dir: Optional[str] = None) -> "Table":
         """data_dir given: only if the cache was built from the kmer.table.mem_map[.gz] that directory holds now."""
         h = C.c_void_p()

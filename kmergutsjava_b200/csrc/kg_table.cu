@@ -6,14 +6,20 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <stdarg.h>
 #include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "kg_device.cuh"
 #include "kg_internal.h"
@@ -60,110 +66,7 @@ static double filter_bits_per_key();
 static int filter_stages();
 static void pin_filter(kg_context* ctx, const kg_table* t, bool force);
 
-// ---------------------------------------------------------------------------------------------------------------
-// reference-format image parser (streaming, so a 10-100 GB file never has to sit in host memory twice)
-// ---------------------------------------------------------------------------------------------------------------
 namespace {
-
-struct ImageParser {
-    int64_t num_slots = 0, entry_size = 0, version = 0;
-    bool header_done = false;
-    uint8_t carry[24];
-    size_t ncarry = 0;
-    int64_t slot = 0, run_start = 0;
-    bool in_run = false;
-    int64_t unreachable = 0, unmatchable = 0;
-    int shard_rank = 0, shard_count = 1; // hash-sharded table: keep the keys this rank owns
-    int64_t not_owned = 0;
-    std::vector<uint64_t> keys;
-    std::vector<int4> payload;
-    std::string error;
-
-    bool header(const uint8_t* h) {
-        memcpy(&num_slots, h, 8);      // readLongLE x3, KGJ:933-935 (x86 is little-endian)
-        memcpy(&entry_size, h + 8, 8);
-        memcpy(&version, h + 16, 8);
-        header_done = true;
-        if (entry_size != 24) { // KGJ:992 skips by entrySize but KGJ:995-999 always reads 24 bytes
-            error = "kmer table: entrySize " + std::to_string(entry_size) + " != 24 is not readable by the reference either";
-            return false;
-        }
-        if (num_slots <= 0) {
-            error = "kmer table: numSigs " + std::to_string(num_slots) + " <= 0";
-            return false;
-        }
-        size_t guess = (size_t)std::min<int64_t>(num_slots / 2 + 16, (int64_t)1 << 33);
-        keys.reserve(guess);
-        payload.reserve(guess);
-        return true;
-    }
-    inline void entry(const uint8_t* e) {
-        int64_t k;
-        memcpy(&k, e, 8);
-        if (k > KG_MAX_ENCODED) { // empty slot, KGJ:1000: every pending probe chain ends here
-            in_run = false;
-        } else {
-            if (!in_run) {
-                in_run = true;
-                run_start = slot;
-            }
-            if (k >= 0 && k < KG_MAX_ENCODED) {
-                // The reference probes slots h, h+1, ... (h = key % numSigs) until an empty slot, with NO wrap-around
-                // (KGJ:959-1026).  It can therefore return this slot iff h lies inside the occupied run that ends here.
-                int64_t h = k % num_slots;
-                if (h >= run_start && h <= slot) {
-                    if (shard_count > 1 && (int)kg_owner_of((uint64_t)k, (uint32_t)shard_count) != shard_rank) {
-                        not_owned++;
-                        slot++;
-                        return;
-                    }
-                    int4 p;
-                    memcpy(&p, e + 8, 16); // otuIndex, avgFromEnd, functionIndex, functionWt bits (KGJ:996-999)
-                    keys.push_back((uint64_t)k);
-                    payload.push_back(p);
-                } else {
-                    unreachable++;
-                }
-            } else {
-                unmatchable++; // occupies a slot (extends chains) but no valid 8-mer encodes to it
-            }
-        }
-        slot++;
-    }
-    bool feed(const uint8_t* p, size_t n) {
-        if (ncarry) {
-            size_t need = 24 - ncarry, take = std::min(need, n);
-            memcpy(carry + ncarry, p, take);
-            ncarry += take;
-            p += take;
-            n -= take;
-            if (ncarry < 24) return true;
-            ncarry = 0;
-            if (!header_done) {
-                if (!header(carry)) return false;
-            } else {
-                entry(carry);
-            }
-        }
-        if (!header_done && n >= 24) {
-            if (!header(p)) return false;
-            p += 24;
-            n -= 24;
-        }
-        if (header_done) {
-            size_t whole = n / 24;
-            for (size_t i = 0; i < whole; i++) entry(p + 24 * i);
-            p += whole * 24;
-            n -= whole * 24;
-        }
-        if (n) {
-            memcpy(carry, p, n);
-            ncarry = n;
-        }
-        return true;
-    }
-    int64_t tail_run() const { return in_run ? slot - run_start : 0; }
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 // device builder
@@ -325,23 +228,26 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
     t->num_buckets = nb;
     k_init_buckets<<<blocks_for(nb_total * KG_LINE_UINT4, 256), 256, 0, st>>>(t->d_lines, nb_total);
 
-    unsigned long long* d_ctr = nullptr; // [0] scatter overflow, [1] flagged buckets, [2] verify failures
-    CU(cudaMalloc(&d_ctr, 4 * sizeof(unsigned long long)));
+    struct Tmp : DevBuf { // freed on every return path (a failed build must not leak gigabytes: the caller may retry)
+        ~Tmp() { release(); }
+    };
+    Tmp ctr_buf, comp_a_buf, comp_b_buf, idx_a_buf, idx_b_buf, flag_buf, nsel_buf, tb_buf;
+    KG_TRY(ctr_buf.ensure(4 * sizeof(unsigned long long)));
+    unsigned long long* d_ctr = ctr_buf.as<unsigned long long>(); // [0] scatter overflow, [1] flagged buckets, [2] verify failures
     CU(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), st));
     size_t n_unique = n;
 
     if (n > 0) {
-        uint64_t *comp_a = nullptr, *comp_b = nullptr;
-        uint32_t *idx_a = nullptr, *idx_b = nullptr;
-        long long* tb = nullptr;
-        uint8_t* flag = nullptr;
-        size_t* d_nsel = nullptr;
-        CU(cudaMalloc(&comp_a, n * 8));
-        CU(cudaMalloc(&comp_b, n * 8));
-        CU(cudaMalloc(&idx_a, n * 4));
-        CU(cudaMalloc(&idx_b, n * 4));
-        CU(cudaMalloc(&flag, n));
-        CU(cudaMalloc(&d_nsel, sizeof(size_t)));
+        KG_TRY(comp_a_buf.ensure(n * 8));
+        KG_TRY(comp_b_buf.ensure(n * 8));
+        KG_TRY(idx_a_buf.ensure(n * 4));
+        KG_TRY(idx_b_buf.ensure(n * 4));
+        KG_TRY(flag_buf.ensure(n));
+        KG_TRY(nsel_buf.ensure(sizeof(size_t)));
+        uint64_t *comp_a = comp_a_buf.as<uint64_t>(), *comp_b = comp_b_buf.as<uint64_t>();
+        uint32_t *idx_a = idx_a_buf.as<uint32_t>(), *idx_b = idx_b_buf.as<uint32_t>();
+        uint8_t* flag = flag_buf.as<uint8_t>();
+        size_t* d_nsel = nsel_buf.as<size_t>();
         k_make_composite<<<blocks_for(n, 256), 256, 0, st>>>(d_keys, n, nb, comp_a, idx_a);
 
         int end_bit = 35;
@@ -371,7 +277,8 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
         comp = comp_o;
         idx = idx_o;
 
-        CU(cudaMalloc(&tb, n_unique * 8));
+        KG_TRY(tb_buf.ensure(std::max<size_t>(n_unique, 1) * 8));
+        long long* tb = tb_buf.as<long long>();
         k_slot_bias<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, tb);
         size_t scan_bytes = 0;
         CU(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, tb, tb, MaxI64(), n_unique, st));
@@ -404,18 +311,10 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
         }
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
-        cudaFree(comp_a);
-        cudaFree(comp_b);
-        cudaFree(idx_a);
-        cudaFree(idx_b);
-        cudaFree(flag);
-        cudaFree(d_nsel);
-        cudaFree(tb);
     }
     unsigned long long h_ctr[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(d_ctr);
     if (h_ctr[0]) KG_FAIL(KG_EFORMAT, "table build: %llu keys spilled past the tail buckets (load %.2f too high?)", h_ctr[0], load);
     if (h_ctr[2]) KG_FAIL(KG_ECUDA, "table build: %llu stored keys are not found again", h_ctr[2]);
     t->info.num_signatures = (int64_t)n_unique;
@@ -439,44 +338,6 @@ static double table_load_factor() {
     return (v > 0.05 && v < 0.95) ? v : 0.50; // 3 keys per 6-key bucket on average: ~3 % of buckets overflow
 }
 
-static int table_from_parser(kg_context* ctx, ImageParser& ps, kg_table** out) {
-    if (!ps.header_done) KG_FAIL(KG_EIO, "kmer table: EOF inside the 24-byte header");
-    CU(cudaSetDevice(ctx->device));
-    kg_table* t = new kg_table();
-    t->ctx = ctx;
-    t->info.num_slots = ps.num_slots;
-    t->info.entry_size = ps.entry_size;
-    t->info.version = ps.version;
-    t->info.num_unreachable = ps.unreachable + ps.unmatchable;
-    t->info.tail_run = ps.tail_run();
-    t->shard_rank = ps.shard_rank;
-    t->shard_count = ps.shard_count;
-    size_t n = ps.keys.size();
-    uint64_t* d_keys = nullptr;
-    int4* d_payload = nullptr;
-    int rc = KG_OK;
-    do {
-        if (n) {
-            if (cudaMalloc(&d_keys, n * 8) != cudaSuccess || cudaMalloc(&d_payload, n * sizeof(int4)) != cudaSuccess) {
-                kg_set_error("table: device allocation for %zu entries failed", n);
-                rc = KG_ENOMEM;
-                break;
-            }
-            cudaMemcpyAsync(d_keys, ps.keys.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream);
-            cudaMemcpyAsync(d_payload, ps.payload.data(), n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream);
-        }
-        rc = build_on_device(ctx, d_keys, d_payload, n, table_load_factor(), true, t);
-    } while (0);
-    if (d_keys) cudaFree(d_keys);
-    if (d_payload) cudaFree(d_payload);
-    if (rc != KG_OK) {
-        kg_table_free(t);
-        return rc;
-    }
-    *out = t;
-    return KG_OK;
-}
-
 static int check_shard(int rank, int nranks) {
     if (nranks < 1 || nranks > KG_MAX_RANKS || rank < 0 || rank >= nranks) KG_FAIL(KG_EINVAL, "shard %d of %d: need 0 <= rank < nranks <= %d", rank, nranks, KG_MAX_RANKS);
     return KG_OK;
@@ -487,62 +348,406 @@ extern "C" int kg_shard_owner(uint64_t key, int nranks) {
     return (int)kg_owner_of(key, (uint32_t)nranks);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Reference-format loader, parsed ON THE DEVICE.  The file is a header of three little-endian int64
+// (numSigs = slot count, entrySize, version; KGJ:933-935) followed by 24-byte slots {int64 key; int32 otuIndex; int32
+// avgFromEnd; int32 functionIndex; float32 functionWt} (KGJ:995-999).  The host only moves bytes: reader threads pread()
+// 48 MiB chunks of whole slots into a ring of pinned buffers (one inflating thread for .gz -- a gzip stream cannot be cut),
+// the copy stream uploads them, and per chunk the compute stream
+//   k_ld_mark     t[i] = index after slot i if the slot is empty (key > 20^8, KGJ:1000), else 0
+//   max-scan      run start of every slot = index after the last empty slot before it (carried from chunk to chunk in
+//                 a device-resident LdState, so no host round trip orders the chunks)
+//   k_ld_flag     the reference probes h = key % numSigs, h+1, ... up to the first empty slot and never wraps
+//                 (KGJ:959-1026): slot s is reachable iff h lies inside the occupied run that ends at s.  Counts the
+//                 unreachable / unmatchable slots and (hash-sharded table) the keys of other ranks
+//   select+gather the kept (key, payload) pairs, appended in SLOT order (of two equal keys the earlier slot wins)
+// No std::vector of entries on the host (r01: 24 bytes x reachable keys of host RAM and a single-threaded push_back loop).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t LD_SLOTS = 1u << 21;      // slots per chunk
+constexpr size_t LD_CHUNK = LD_SLOTS * 24; // 48 MiB
+constexpr int LD_NBUF = 4;                 // pinned host buffers
+constexpr int LD_READERS = 3;
+
+struct LdState { // device-resident parser state, carried from chunk to chunk in stream order
+    long long carry;            // index after the last empty slot so far = start of the occupied run that reaches the next slot
+    unsigned long long n_out;   // entries kept so far
+    unsigned long long unreachable, unmatchable, not_owned;
+    unsigned long long nsel;    // entries kept from the chunk in flight
+    unsigned long long last_occ; // the last slot seen is occupied
+    unsigned long long overflow; // the output arrays were too small (cannot happen: the host sizes them from an upper bound)
+};
+
+__global__ void k_ld_mark(const unsigned long long* __restrict__ raw, uint32_t n, long long g0, long long* __restrict__ t) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long key = (long long)raw[3 * (size_t)i];
+    t[i] = key > (long long)KG_MAX_ENCODED ? g0 + (long long)i + 1 : 0;
+}
+__global__ void k_ld_flag(const unsigned long long* __restrict__ raw, uint32_t n, long long g0, const long long* __restrict__ rs,
+                          long long num_slots, uint32_t rank, uint32_t nranks, LdState* __restrict__ st, uint8_t* __restrict__ flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false, unreach = false, unmatch = false, foreign = false;
+    if (i < n) {
+        const long long key = (long long)raw[3 * (size_t)i];
+        if (key <= (long long)KG_MAX_ENCODED) { // occupied
+            if (key >= 0 && key < (long long)KG_MAX_ENCODED) {
+                const long long run_start = max(rs[i], st->carry), h = key % num_slots, slot = g0 + (long long)i;
+                if (h >= run_start && h <= slot) {
+                    if (nranks > 1 && kg_owner_of((uint64_t)key, nranks) != rank) foreign = true;
+                    else keep = true;
+                } else {
+                    unreach = true;
+                }
+            } else {
+                unmatch = true; // occupies a slot (extends chains) but no valid 8-mer encodes to it
+            }
+        }
+        flag[i] = keep;
+    }
+    const unsigned a = __ballot_sync(0xFFFFFFFFu, unreach), b = __ballot_sync(0xFFFFFFFFu, unmatch), c = __ballot_sync(0xFFFFFFFFu, foreign);
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&st->unreachable, (unsigned long long)__popc(a));
+        if (b) atomicAdd(&st->unmatchable, (unsigned long long)__popc(b));
+        if (c) atomicAdd(&st->not_owned, (unsigned long long)__popc(c));
+    }
+}
+__global__ void k_ld_gather(const unsigned long long* __restrict__ raw, const uint32_t* __restrict__ sel, LdState* __restrict__ st,
+                            uint64_t* __restrict__ keys, int4* __restrict__ payload, unsigned long long cap) {
+    const unsigned long long nsel = st->nsel, base = st->n_out;
+    if (base + nsel > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->overflow = 1;
+        return;
+    }
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nsel; j += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long* e = raw + 3 * (size_t)sel[j];
+        keys[base + j] = e[0];
+        const unsigned long long lo = e[1], hi = e[2]; // otuIndex | avgFromEnd << 32, functionIndex | functionWt bits << 32
+        payload[base + j] = make_int4((int)(uint32_t)lo, (int)(uint32_t)(lo >> 32), (int)(uint32_t)hi, (int)(uint32_t)(hi >> 32));
+    }
+}
+__global__ void k_ld_advance(const unsigned long long* __restrict__ raw, const long long* __restrict__ rs, uint32_t n, LdState* __restrict__ st) {
+    if (!st->overflow) st->n_out += st->nsel;
+    st->carry = max(st->carry, rs[n - 1]);
+    st->last_occ = (long long)raw[3 * (size_t)(n - 1)] <= (long long)KG_MAX_ENCODED;
+}
+
+struct SlotLoader {
+    kg_context* ctx = nullptr;
+    int rank = 0, nranks = 1;
+    int64_t num_slots = 0, entry_size = 0, version = 0;
+    uint8_t* h_buf[LD_NBUF] = {};
+    cudaEvent_t ev_h2d[LD_NBUF] = {};
+    uint8_t* d_raw[2] = {};
+    cudaEvent_t ev_done[2] = {};
+    DevBuf t, flag, sel, keys, payload, state, tmp;
+    uint64_t cap = 0, upper = 0, slots_done = 0, chunks = 0;
+
+    ~SlotLoader() {
+        for (auto& b : h_buf)
+            if (b) cudaFreeHost(b);
+        for (auto& e : ev_h2d)
+            if (e) cudaEventDestroy(e);
+        for (auto& b : d_raw)
+            if (b) cudaFree(b);
+        for (auto& e : ev_done)
+            if (e) cudaEventDestroy(e);
+        for (DevBuf* d : {&t, &flag, &sel, &keys, &payload, &state, &tmp}) d->release();
+    }
+    int header(const uint8_t* h) { // readLongLE x3, KGJ:933-935 (x86 is little-endian)
+        memcpy(&num_slots, h, 8);
+        memcpy(&entry_size, h + 8, 8);
+        memcpy(&version, h + 16, 8);
+        if (entry_size != 24) // KGJ:992 skips by entrySize but KGJ:995-999 always reads 24 bytes
+            KG_FAIL(KG_EFORMAT, "kmer table: entrySize %lld != 24 is not readable by the reference either", (long long)entry_size);
+        if (num_slots <= 0) KG_FAIL(KG_EFORMAT, "kmer table: numSigs %lld <= 0", (long long)num_slots);
+        return KG_OK;
+    }
+    int init(kg_context* c, int rk, int nr, uint64_t expect_slots, bool exact_size) {
+        ctx = c;
+        rank = rk;
+        nranks = nr;
+        CU(cudaSetDevice(ctx->device));
+        const size_t chunk = (size_t)std::min<uint64_t>(LD_CHUNK, std::max<uint64_t>(expect_slots, 1) * 24);
+        for (auto& b : h_buf) CU(cudaMallocHost(&b, chunk));
+        for (auto& e : ev_h2d) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& b : d_raw) CU(cudaMalloc(&b, chunk));
+        for (auto& e : ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const size_t ns = chunk / 24;
+        KG_TRY(t.ensure(ns * 8));
+        KG_TRY(flag.ensure(ns));
+        KG_TRY(sel.ensure(ns * 4));
+        KG_TRY(state.ensure(sizeof(LdState)));
+        CU(cudaMemsetAsync(state.p, 0, sizeof(LdState), ctx->stream));
+        // the table is an open-addressing table: normally 1/3 to 1/2 of the slots hold a key; the arrays grow if more do
+        uint64_t guess = std::max<uint64_t>(expect_slots, 1) * 6 / 10 / (uint64_t)nranks + 2 * ns;
+        guess = std::min<uint64_t>(guess, std::max<uint64_t>(expect_slots, 1));
+        if (!exact_size) guess = std::min<uint64_t>(guess, 64ull << 20); // .gz: the header's slot count is all there is to go by
+        return grow(guess);
+    }
+    int grow(uint64_t want) {
+        if (want <= cap) return KG_OK;
+        DevBuf nk, np;
+        KG_TRY(nk.ensure(want * 8));
+        if (int rc = np.ensure(want * sizeof(int4)); rc != KG_OK) {
+            nk.release();
+            return rc;
+        }
+        const uint64_t live = std::min<uint64_t>(cap, upper); // called with the stream drained and `upper` exact
+        if (live) {
+            CU(cudaMemcpyAsync(nk.p, keys.p, live * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(np.p, payload.p, live * sizeof(int4), cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        keys.release();
+        payload.release();
+        keys = nk;
+        payload = np;
+        cap = want;
+        return KG_OK;
+    }
+    // host buffer for the next chunks: buffer b is free once the upload of the chunk that used it has completed
+    uint8_t* buffer(uint64_t chunk_no) {
+        cudaEventSynchronize(ev_h2d[chunk_no % LD_NBUF]);
+        return h_buf[chunk_no % LD_NBUF];
+    }
+    // nbytes of whole slots sit in buffer(chunk_no); chunks are submitted in order
+    int submit(uint64_t chunk_no, size_t nbytes) {
+        const uint32_t n = (uint32_t)(nbytes / 24);
+        if (!n) return KG_OK;
+        const int hb = (int)(chunk_no % LD_NBUF), db = (int)(chunks & 1);
+        cudaStream_t cs = ctx->copy_stream, st = ctx->stream;
+        // Room for everything this chunk could keep.  `upper` counts every slot submitted since the exact count was last
+        // read; when it reaches the capacity the stream is drained once, the exact count read, and the arrays grow if
+        // the table really is that full (one or two drains per file at the usual 1/3 - 1/2 occupancy).
+        if (upper + n > cap) {
+            CU(cudaStreamSynchronize(st));
+            LdState now;
+            CU(cudaMemcpy(&now, state.p, sizeof now, cudaMemcpyDeviceToHost));
+            upper = now.n_out;
+            if (upper + n > cap) KG_TRY(grow(std::max<uint64_t>(upper + n, cap + cap / 2)));
+        }
+        upper += n;
+        CU(cudaStreamWaitEvent(cs, ev_done[db], 0)); // the kernels of chunk - 2 are done with this device buffer
+        CU(cudaMemcpyAsync(d_raw[db], h_buf[hb], (size_t)n * 24, cudaMemcpyHostToDevice, cs));
+        CU(cudaEventRecord(ev_h2d[hb], cs));
+        CU(cudaStreamWaitEvent(st, ev_h2d[hb], 0));
+        const unsigned long long* raw = (const unsigned long long*)d_raw[db];
+        const long long g0 = (long long)slots_done;
+        LdState* ds = state.as<LdState>();
+        k_ld_mark<<<blocks_for(n, 256), 256, 0, st>>>(raw, n, g0, t.as<long long>());
+        size_t b1 = 0, b2 = 0;
+        CU(cub::DeviceScan::InclusiveScan(nullptr, b1, t.as<long long>(), t.as<long long>(), MaxI64(), n, st));
+        thrust::counting_iterator<uint32_t> iota(0);
+        CU(cub::DeviceSelect::Flagged(nullptr, b2, iota, flag.as<uint8_t>(), sel.as<uint32_t>(), &ds->nsel, n, st));
+        KG_TRY(tmp.ensure(std::max(b1, b2)));
+        CU(cub::DeviceScan::InclusiveScan(tmp.p, b1, t.as<long long>(), t.as<long long>(), MaxI64(), n, st));
+        k_ld_flag<<<blocks_for(n, 256), 256, 0, st>>>(raw, n, g0, t.as<long long>(), (long long)num_slots, (uint32_t)rank, (uint32_t)nranks, ds,
+                                                     flag.as<uint8_t>());
+        CU(cub::DeviceSelect::Flagged(tmp.p, b2, iota, flag.as<uint8_t>(), sel.as<uint32_t>(), &ds->nsel, n, st));
+        k_ld_gather<<<ctx->sm_count * 4, 256, 0, st>>>(raw, sel.as<uint32_t>(), ds, keys.as<uint64_t>(), payload.as<int4>(), cap);
+        k_ld_advance<<<1, 1, 0, st>>>(raw, t.as<long long>(), n, ds);
+        CU(cudaEventRecord(ev_done[db], st));
+        slots_done += n;
+        chunks++;
+        CU(cudaGetLastError());
+        return KG_OK;
+    }
+    int finish(kg_table** out) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        LdState fin;
+        CU(cudaMemcpy(&fin, state.p, sizeof fin, cudaMemcpyDeviceToHost));
+        if (fin.overflow) KG_FAIL(KG_ECUDA, "table loader: output arrays overflowed (internal error)");
+        kg_table* tb = new kg_table();
+        tb->ctx = ctx;
+        tb->info.num_slots = num_slots;
+        tb->info.entry_size = entry_size;
+        tb->info.version = version;
+        tb->info.num_unreachable = (int64_t)(fin.unreachable + fin.unmatchable);
+        tb->info.tail_run = fin.last_occ ? (int64_t)slots_done - (int64_t)fin.carry : 0;
+        tb->shard_rank = rank;
+        tb->shard_count = nranks;
+        // the parser's own buffers are no longer needed while the builder runs
+        for (DevBuf* d : {&t, &flag, &sel, &tmp}) d->release();
+        for (auto& b : d_raw) {
+            if (b) cudaFree(b);
+            b = nullptr;
+        }
+        const int rc = build_on_device(ctx, keys.as<uint64_t>(), payload.as<int4>(), (size_t)fin.n_out, table_load_factor(), true, tb);
+        if (rc != KG_OK) {
+            kg_table_free(tb);
+            return rc;
+        }
+        *out = tb;
+        return KG_OK;
+    }
+};
+
+// Random-access source (a plain file or an image in memory): reader threads fill the pinned ring ahead of the submitting thread.
+struct RandomSource {
+    int fd = -1;                  // plain file, or
+    const uint8_t* image = nullptr; // image in host memory
+    uint64_t body = 0;            // bytes of whole slots after the 24-byte header
+    bool read(uint64_t off, uint8_t* dst, size_t n) const {
+        if (image) {
+            memcpy(dst, image + 24 + off, n);
+            return true;
+        }
+        size_t got = 0;
+        while (got < n) {
+            const ssize_t r = pread(fd, dst + got, n - got, (off_t)(24 + off + got));
+            if (r <= 0) return false;
+            got += (size_t)r;
+        }
+        return true;
+    }
+};
+
+int load_random(kg_context* ctx, const RandomSource& src, const uint8_t* header24, int rank, int nranks, kg_table** table) {
+    SlotLoader ld;
+    KG_TRY(ld.header(header24));
+    const uint64_t nslots = src.body / 24;
+    KG_TRY(ld.init(ctx, rank, nranks, nslots, true));
+    const size_t chunk = (size_t)std::min<uint64_t>(LD_CHUNK, std::max<uint64_t>(nslots, 1) * 24);
+    const uint64_t nchunks = (nslots * 24 + chunk - 1) / chunk;
+    // ready[c % NBUF] = c + 1 once chunk c has been read; free_upto = chunks whose host buffer may be overwritten
+    std::mutex m;
+    std::condition_variable cv;
+    uint64_t ready[LD_NBUF] = {}, free_upto = LD_NBUF;
+    bool failed = false;
+    auto reader = [&](int tid) {
+        for (uint64_t c = (uint64_t)tid; c < nchunks; c += LD_READERS) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return c < free_upto || failed; });
+                if (failed) return;
+            }
+            const uint64_t off = c * chunk;
+            const size_t n = (size_t)std::min<uint64_t>(chunk, nslots * 24 - off);
+            const bool ok = src.read(off, ld.h_buf[c % LD_NBUF], n);
+            std::lock_guard<std::mutex> lk(m);
+            if (!ok) failed = true;
+            ready[c % LD_NBUF] = c + 1;
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> th;
+    const int nthreads = (int)std::min<uint64_t>(LD_READERS, nchunks);
+    for (int i = 0; i < nthreads; i++) th.emplace_back(reader, i);
+    int rc = KG_OK;
+    for (uint64_t c = 0; c < nchunks && rc == KG_OK; c++) {
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return ready[c % LD_NBUF] == c + 1 || failed; });
+            if (failed) {
+                kg_set_error("kmer table: read error");
+                rc = KG_EIO;
+                break;
+            }
+        }
+        const uint64_t off = c * chunk;
+        rc = ld.submit(c, (size_t)std::min<uint64_t>(chunk, nslots * 24 - off));
+        if (rc != KG_OK) break;
+        // the buffer of chunk c can be refilled (by chunk c + NBUF) once its upload is complete
+        cudaEventSynchronize(ld.ev_h2d[c % LD_NBUF]);
+        std::lock_guard<std::mutex> lk(m);
+        free_upto = c + 1 + LD_NBUF;
+        cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(m);
+        if (rc != KG_OK) failed = true;
+        cv.notify_all();
+    }
+    for (auto& t : th) t.join();
+    if (rc != KG_OK) return rc;
+    return ld.finish(table);
+}
+
+int load_gz(kg_context* ctx, const char* path, int rank, int nranks, kg_table** table) {
+    gzFile g = gzopen(path, "rb");
+    if (!g) KG_FAIL(KG_EIO, "cannot open %s", path);
+    gzbuffer(g, 1 << 20);
+    auto read_fully = [&](uint8_t* dst, size_t n, bool* err) -> size_t {
+        size_t got = 0;
+        while (got < n) {
+            const int r = gzread(g, dst + got, (unsigned)std::min<size_t>(n - got, 1u << 30));
+            if (r < 0) *err = true;
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        return got;
+    };
+    uint8_t hdr[24];
+    bool err = false;
+    int rc = KG_OK;
+    SlotLoader ld;
+    do {
+        if (read_fully(hdr, 24, &err) != 24) {
+            kg_set_error(err ? "gzip error reading %s" : "kmer table: EOF inside the 24-byte header (%s)", path);
+            rc = err ? KG_EIO : KG_EIO;
+            break;
+        }
+        if ((rc = ld.header(hdr)) != KG_OK) break;
+        if ((rc = ld.init(ctx, rank, nranks, (uint64_t)ld.num_slots, false)) != KG_OK) break;
+        const size_t chunk = (size_t)std::min<uint64_t>(LD_CHUNK, (uint64_t)ld.num_slots * 24);
+        for (uint64_t c = 0;; c++) { // the inflate of chunk c+1 overlaps the upload and the kernels of chunk c
+            uint8_t* buf = ld.buffer(c);
+            const size_t got = read_fully(buf, chunk, &err);
+            if (err) {
+                kg_set_error("gzip error reading %s", path);
+                rc = KG_EIO;
+                break;
+            }
+            if ((rc = ld.submit(c, got / 24 * 24)) != KG_OK) break;
+            if (got < chunk) break;
+        }
+    } while (0);
+    gzclose(g);
+    if (rc != KG_OK) return rc;
+    return ld.finish(table);
+}
+} // namespace
+
 extern "C" int kg_table_from_image_sharded(kg_context* ctx, const void* image, size_t nbytes, int rank, int nranks, kg_table** table) {
     if (!ctx || !image || !table) KG_FAIL(KG_EINVAL, "kg_table_from_image: null argument");
     KG_TRY(check_shard(rank, nranks));
-    ImageParser ps;
-    ps.shard_rank = rank;
-    ps.shard_count = nranks;
-    if (!ps.feed((const uint8_t*)image, nbytes)) KG_FAIL(KG_EFORMAT, "%s", ps.error.c_str());
-    return table_from_parser(ctx, ps, table);
+    if (nbytes < 24) KG_FAIL(KG_EIO, "kmer table: EOF inside the 24-byte header");
+    RandomSource src;
+    src.image = (const uint8_t*)image;
+    src.body = (nbytes - 24) / 24 * 24;
+    return load_random(ctx, src, (const uint8_t*)image, rank, nranks, table);
 }
 
 extern "C" int kg_table_from_image(kg_context* ctx, const void* image, size_t nbytes, kg_table** table) {
-    if (!ctx || !image || !table) KG_FAIL(KG_EINVAL, "kg_table_from_image: null argument");
-    ImageParser ps;
-    if (!ps.feed((const uint8_t*)image, nbytes)) KG_FAIL(KG_EFORMAT, "%s", ps.error.c_str());
-    return table_from_parser(ctx, ps, table);
+    return kg_table_from_image_sharded(ctx, image, nbytes, 0, 1, table);
 }
 
 static int load_file_impl(kg_context* ctx, const char* path, int rank, int nranks, kg_table** table) {
     if (!ctx || !path || !table) KG_FAIL(KG_EINVAL, "kg_table_load_file: null argument");
-    ImageParser ps;
-    ps.shard_rank = rank;
-    ps.shard_count = nranks;
-    std::vector<uint8_t> buf(8u << 20);
-    size_t len = strlen(path);
-    bool gz = len > 3 && strcmp(path + len - 3, ".gz") == 0; // the reference keys on the suffix (KGJ:927)
+    const size_t len = strlen(path);
+    const bool gz = len > 3 && strcmp(path + len - 3, ".gz") == 0; // the reference keys on the suffix (KGJ:927)
+    int rc;
     if (gz) {
-        gzFile g = gzopen(path, "rb");
-        if (!g) KG_FAIL(KG_EIO, "cannot open %s", path);
-        gzbuffer(g, 1 << 20);
-        for (;;) {
-            int got = gzread(g, buf.data(), (unsigned)buf.size());
-            if (got < 0) {
-                gzclose(g);
-                KG_FAIL(KG_EIO, "gzip error reading %s", path);
-            }
-            if (got == 0) break;
-            if (!ps.feed(buf.data(), (size_t)got)) {
-                gzclose(g);
-                KG_FAIL(KG_EFORMAT, "%s: %s", path, ps.error.c_str());
-            }
-        }
-        gzclose(g);
+        rc = load_gz(ctx, path, rank, nranks, table);
     } else {
-        FILE* f = fopen(path, "rb");
-        if (!f) KG_FAIL(KG_EIO, "cannot open %s", path);
-        for (;;) {
-            size_t got = fread(buf.data(), 1, buf.size(), f);
-            if (got == 0) break;
-            if (!ps.feed(buf.data(), got)) {
-                fclose(f);
-                KG_FAIL(KG_EFORMAT, "%s: %s", path, ps.error.c_str());
-            }
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) KG_FAIL(KG_EIO, "cannot open %s", path);
+        struct stat fst;
+        uint8_t hdr[24];
+        if (fstat(fd, &fst) != 0 || fst.st_size < 24 || pread(fd, hdr, 24, 0) != 24) {
+            close(fd);
+            KG_FAIL(KG_EIO, "kmer table: EOF inside the 24-byte header (%s)", path);
         }
-        fclose(f);
+        posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+        RandomSource src;
+        src.fd = fd;
+        src.body = ((uint64_t)fst.st_size - 24) / 24 * 24;
+        rc = load_random(ctx, src, hdr, rank, nranks, table);
+        close(fd);
     }
-    KG_TRY(table_from_parser(ctx, ps, table));
+    if (rc != KG_OK) return rc;
     struct stat sst;
     if (stat(path, &sst) == 0) {
         (*table)->src_size = (uint64_t)sst.st_size;
