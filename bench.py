@@ -247,6 +247,35 @@ def run_ours(args):
                "call": "kg_run_packed_aa: 5-bit residue codes (kg_pack_aa) in, calls + compact OTU counts out",
                "pack_GBps": round(total / pack_s / 1e9, 2), "pack_threads": pack_threads}
         log(f"e2e (packed): {e2e['value']:.3e} lookups/s")
+        # Ceiling of the host link: the SAME bytes in and out per step and nothing else (one cudaMemcpyAsync each way from / to
+        # pinned memory, both directions at once, all ranks together) -- what the end-to-end call could reach if every kernel
+        # were free.  At N = 8 all ranks share one host's memory system; e2e is to be read against this number.
+        d_in = torch.empty(e2e["h2d_bytes_per_step"], dtype=torch.uint8, device=f"cuda:{local}")
+        d_out = torch.empty(e2e["d2h_bytes_per_step"], dtype=torch.uint8, device=f"cuda:{local}")
+        h_in = torch.empty(e2e["h2d_bytes_per_step"], dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty(e2e["d2h_bytes_per_step"], dtype=torch.uint8, pin_memory=True)
+        s_in, s_out = torch.cuda.Stream(local), torch.cuda.Stream(local)
+
+        def copy_step():
+            with torch.cuda.stream(s_in):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out.copy_(d_out, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+
+        for _ in range(3):
+            copy_step()
+        plumb.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            copy_step()
+        plumb.barrier()
+        cdt = plumb.reduce([time.perf_counter() - t0], "MAX")[0]
+        e2e["copy_only_ms_per_step"] = 1e3 * cdt / args.steps
+        e2e["copy_only_GBps_all_ranks"] = round(world * (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) * args.steps / cdt / 1e9, 1)
+        e2e["e2e_over_copy_only"] = round(e2e["ms_per_step"] / e2e["copy_only_ms_per_step"], 3)
+        del d_in, d_out, h_in, h_out
         rdt, r_lookups, s3 = timed_calls(plumb, clocks, args.steps, warm, raw_call)
         e2e["raw_bytes_call"] = {"value": plumb.reduce([float(r_lookups)])[0] / rdt, "unit": "lookups/s", "ms_per_step": 1e3 * rdt / args.steps,
                                  "h2d_bytes_per_step": int(total + 8 * (args.proteins + 1)), "d2h_bytes_per_step": d2h_bytes(s3) + 8 * n_entries,

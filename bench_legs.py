@@ -347,7 +347,9 @@ def configs4(kg, ctx, plumb, proteins=1_000_000, steps=10, warmup=3, families=0,
     out = {"workload": f"configs[4]: hash-sharded table, {int(tot_sigs)} signatures over {world} GPU(s), {proteins} proteins per rank",
            "n_gpus": world, "steps": steps, "ms_per_step": 1e3 * dt_max / steps, "lookups_per_s": tot_lookups / dt_max,
            "proteins_per_s": proteins * world * steps / dt_max, "signatures": int(tot_sigs), "shard_bytes_rank0": int(ti.device_bytes),
-           "transport": comm.transport if hasattr(comm, "transport") else ("nccl" if world > 1 else "none"),
+           "transport": "none" if world == 1 else
+                        ("nccl send/recv of staged bins" if os.environ.get("KG_SHARD_TRANSPORT", "direct") != "direct" else
+                         "direct: k_route / k_answer store into the peers' buffers (CUDA IPC over NVLink), in-band counts and flags; NCCL only for the bootstrap"),
            "scaling": "weak (proteins and signatures per GPU fixed)",
            "rank0_phase_ms": dict(zip(["route", "keys_exchange", "answer", "replies_exchange", "merge_and_fsm", "total_host"],
                                       [round(float(x), 3) for x in phases])),

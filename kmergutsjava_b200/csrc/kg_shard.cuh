@@ -78,8 +78,15 @@ constexpr int SHARD_CNT_SLOTS = 2 * KG_MAX_RANKS; // [0, R): keys per owner; [KG
 // tile's entries are first sorted by owner in shared memory and then copied out run by run, so that every bin receives
 // one contiguous, coalesced burst per tile whatever the number of owners (scattered 4-byte stores made the kernel
 // 1.9x slower with eight bins than with two).
+// Where an owner's bin lives: this rank's own staging buffer (NCCL / copy transports move it afterwards) or -- the direct
+// transport -- this rank's region of the OWNER's receive buffer, mapped into this process (peer memory over NVLink): the
+// coalesced burst k_route writes per tile and owner then IS the exchange, and no staging copy or NCCL kernel follows.
+struct RouteDst {
+    uint32_t* lo[KG_MAX_RANKS];
+    uint8_t* hi[KG_MAX_RANKS];
+};
 __global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__ stream, uint32_t vtotal, uint32_t tile0, uint32_t nranks, unsigned long long cap,
-                                                     uint32_t* __restrict__ send_lo, uint8_t* __restrict__ send_hi, uint32_t* __restrict__ send_pos,
+                                                     RouteDst dst, uint32_t* __restrict__ send_pos,
                                                      unsigned long long* __restrict__ send_cnt) {
     __shared__ uint8_t lut[256];
     __shared__ uint32_t cnt[KG_MAX_RANKS];
@@ -140,8 +147,8 @@ __global__ __launch_bounds__(PROBE_BLK) void k_route(const uint8_t* __restrict__
         while (e >= first[o + 1]) o++;
         const unsigned long long slot = base[o] + (e - first[o]);
         if (slot < cap) { // a bin that overflows is only counted: the host repeats the pass with the exact capacity
-            __stcs(send_lo + o * cap + slot, st_lo[e]); // streamed: keep the L2 for the prefilter of the answer kernel
-            __stcs(send_hi + o * cap + slot, st_hi[e]);
+            __stcs(dst.lo[o] + slot, st_lo[e]); // streamed: keep the L2 for the prefilter of the answer kernel
+            __stcs(dst.hi[o] + slot, st_hi[e]);
             __stcs(send_pos + o * cap + slot, st_pos[e]);
         }
     }
@@ -152,14 +159,26 @@ struct AnswerPlan {
     uint32_t nseg;
     uint32_t tile_first[KG_MAX_RANKS + 1];
     unsigned long long seg_off[KG_MAX_RANKS + 1];
+    // direct transport: the segments are fixed-capacity regions (seg_off[s] = s * cap) and how many keys rank s really sent
+    // is only known on the device (it arrived with the keys); blocks past the end of a segment find nothing to do
+    const unsigned long long* dev_cnt;
+    // direct transport: block b works on segment (b + rot) % nseg, tile b / nseg.  Replies are stored straight into the
+    // asker's memory, so every GPU must be writing to ALL its peers all the time: with the segments one after the other, the
+    // eight GPUs of a box all answered rank 0 first, then rank 1, ... and the step waited 48 ms on one ingress link at a time
+    // (r02, N = 8).  rot = this rank, so that GPU r also starts on a different peer than GPU r + 1.
+    uint32_t interleave, rot;
+};
+// where the replies for asker s go: this rank's reply buffer (moved afterwards) or its region of the ASKER's buffer (peer memory)
+struct ReplyDst {
+    uint32_t* idx[KG_MAX_RANKS];
+    int4* payload[KG_MAX_RANKS];
 };
 
 // k_probe with the encoder replaced by "read the key": prefilter -> survivor queue -> dense probing -> hits out.  A hit
 // becomes a reply {index of the query inside its segment, payload} appended to the segment's reply region (which
 // starts at the segment's own offset: there are never more replies than queries).
 __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32_t* __restrict__ recv_lo, const uint8_t* __restrict__ recv_hi, AnswerPlan plan, KgTableView tab,
-                                                                    uint32_t* __restrict__ reply_idx, int4* __restrict__ reply_payload,
-                                                                    unsigned long long* __restrict__ reply_cnt, uint32_t flags) {
+                                                                    ReplyDst dst, unsigned long long* __restrict__ reply_cnt, uint32_t flags) {
     extern __shared__ int4 smem_dyn[];
     int4* pstage = smem_dyn;
     unsigned long long* queue = reinterpret_cast<unsigned long long*>(smem_dyn + TILE);
@@ -167,14 +186,22 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32
     __shared__ uint32_t warp_a[PROBE_BLK / 32], warp_b[PROBE_BLK / 32];
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x;
+    uint32_t s = 0, tile;
+    if (plan.interleave) {
+        s = (blockIdx.x % plan.nseg + plan.rot) % plan.nseg;
+        tile = blockIdx.x / plan.nseg;
+    } else {
+        while (s + 1 < plan.nseg && blockIdx.x >= plan.tile_first[s + 1]) s++;
+        tile = blockIdx.x - plan.tile_first[s];
+    }
+    unsigned long long n_s = plan.seg_off[s + 1] - plan.seg_off[s];
+    if (plan.dev_cnt) n_s = min(n_s, plan.dev_cnt[s]);
+    if ((unsigned long long)tile * TILE >= n_s) return; // (uniform per block, before any barrier)
     if (tid < TILE / 32) hitbits[tid] = 0;
     __syncthreads();
-    uint32_t s = 0;
-    while (s + 1 < plan.nseg && blockIdx.x >= plan.tile_first[s + 1]) s++;
-    const unsigned long long n_s = plan.seg_off[s + 1] - plan.seg_off[s];
     const uint32_t* klo = recv_lo + plan.seg_off[s];
     const uint8_t* khi = recv_hi + plan.seg_off[s];
-    const unsigned long long k0 = (unsigned long long)(blockIdx.x - plan.tile_first[s]) * TILE + (unsigned long long)tid * PT;
+    const unsigned long long k0 = (unsigned long long)tile * TILE + (unsigned long long)tid * PT;
     const uint64_t pol_keep = kg_policy_evict_last();
     const uint64_t pol_stream = (flags & 1u) ? kg_policy_evict_normal() : kg_policy_evict_first();
 
@@ -217,15 +244,28 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32
     const uint32_t ho = block_excl_scan(__popc(hitmask), warp_b, &total);
     if (tid == 0) s_base = total ? atomicAdd(&reply_cnt[s], (unsigned long long)total) : 0ull;
     __syncthreads();
+    // The block's replies leave as ONE contiguous run, written by consecutive threads: the destination may be the asker's
+    // memory on the other side of NVLink, where a warp store that scatters 32 separate 16-byte pieces (thread t writing its
+    // own hits one after the other) becomes 32 small packets -- k_answer took 16.6 instead of ~9 ms at N = 8 (r02).  The
+    // hit positions are listed in block order in the (now idle) survivor queue.
+    uint32_t* list = reinterpret_cast<uint32_t*>(queue);
     if (hitmask) {
-        unsigned long long o = plan.seg_off[s] + s_base + ho;
-        uint32_t m = hitmask;
+        uint32_t at = ho, m = hitmask;
         while (m) {
             const int i = __ffs(m) - 1;
             m &= m - 1;
-            __stcs(reply_idx + o, (uint32_t)(k0 + i));
-            __stcs(reply_payload + o, pstage[tid * PT + i]);
-            o++;
+            list[at++] = (uint32_t)(tid * PT + i);
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t* ridx = dst.idx[s] + s_base;
+        int4* rpay = dst.payload[s] + s_base;
+        const unsigned long long t0 = (unsigned long long)tile * TILE;
+        for (uint32_t e = tid; e < total; e += PROBE_BLK) {
+            const uint32_t p = list[e];
+            __stcs(ridx + e, (uint32_t)(t0 + p));
+            __stcs(rpay + e, pstage[p]);
         }
     }
 }
@@ -237,6 +277,7 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_answer(const uint32
 struct ScatterPlan {
     uint32_t nseg;
     unsigned long long first[KG_MAX_RANKS + 1];
+    const unsigned long long* dev_n; // direct transport: replies of owner o = dev_n[o], known on the device only
 };
 // Merge, step 1: one bit per residue position that has a hit (the bitmap stays in L2: one bit per position).  Every
 // thread takes MERGE_U replies of one owner, a block apart, and issues their loads together: the kernels of the merge are
@@ -246,8 +287,9 @@ __global__ __launch_bounds__(256) void k_mark_replies(const uint32_t* __restrict
                                                       const unsigned long long* __restrict__ send_cnt, const uint32_t* __restrict__ send_pos,
                                                       uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ ctr) {
     const uint32_t o = blockIdx.x % plan.nseg; // owners interleaved block by block (see ScatterPlan)
-    const unsigned long long n = plan.first[o + 1] - plan.first[o], j0 = (unsigned long long)(blockIdx.x / plan.nseg) * (256 * MERGE_U) + threadIdx.x;
-    const unsigned long long nsent = send_cnt[o];
+    const unsigned long long n = plan.dev_n ? min(plan.dev_n[o], cap) : plan.first[o + 1] - plan.first[o];
+    const unsigned long long j0 = (unsigned long long)(blockIdx.x / plan.nseg) * (256 * MERGE_U) + threadIdx.x;
+    const unsigned long long nsent = min(send_cnt[o], cap);
     uint32_t idx[MERGE_U], pos[MERGE_U];
     bool on[MERGE_U];
 #pragma unroll
@@ -281,8 +323,9 @@ __global__ __launch_bounds__(256) void k_place_replies(const uint32_t* __restric
                                                        const uint32_t* __restrict__ word_rank, uint32_t hit_cap, uint32_t* __restrict__ chunk_pos,
                                                        int4* __restrict__ chunk_payload) {
     const uint32_t o = blockIdx.x % plan.nseg;
-    const unsigned long long n = plan.first[o + 1] - plan.first[o], j0 = (unsigned long long)(blockIdx.x / plan.nseg) * (256 * PLACE_U) + threadIdx.x;
-    const unsigned long long nsent = send_cnt[o];
+    const unsigned long long n = plan.dev_n ? min(plan.dev_n[o], cap) : plan.first[o + 1] - plan.first[o];
+    const unsigned long long j0 = (unsigned long long)(blockIdx.x / plan.nseg) * (256 * PLACE_U) + threadIdx.x;
+    const unsigned long long nsent = min(send_cnt[o], cap);
     uint32_t idx[PLACE_U], pos[PLACE_U], bits[PLACE_U], rank[PLACE_U];
     int4 pay[PLACE_U];
     bool on[PLACE_U];
@@ -313,7 +356,8 @@ __global__ __launch_bounds__(256) void k_place_replies(const uint32_t* __restric
 
 // step 4: the per-tile view of that list (what k_probe's phase D publishes), and the run's counters
 __global__ void k_tile_meta(const uint32_t* __restrict__ word_rank, uint32_t ntiles, uint32_t hit_cap, uint32_t* __restrict__ tile_base,
-                            uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr, unsigned long long kmers) {
+                            uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr, unsigned long long kmers,
+                            const unsigned long long* __restrict__ kmers_dev) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     constexpr uint32_t WPT = TILE / 32;
@@ -322,9 +366,85 @@ __global__ void k_tile_meta(const uint32_t* __restrict__ word_rank, uint32_t nti
     tile_cnt[t] = e - b;
     if (t == ntiles - 1) {
         ctr[KG_CTR_HITS] = e;
-        ctr[KG_CTR_KMERS] = kmers;
+        ctr[KG_CTR_KMERS] = kmers_dev ? kmers_dev[0] : kmers;
         if (e > hit_cap) ctr[KG_CTR_OVERFLOW] = 1ull;
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Direct transport ("the exchange hidden behind probing").  Every rank owns ONE exchange buffer, mapped into
+// all its peers (CUDA IPC between processes, plain peer access inside one process):
+//
+//     PeerCtl                      counters and arrival flags, written by the PEERS
+//     recv_lo / recv_hi  [R][cap]  region s: the keys rank s routed to this rank      <- written by s's k_route
+//     rr_idx / rr_payload [R][cap] region o: the hits owner o found for this rank     <- written by o's k_answer
+//
+// so the coalesced burst k_route writes per tile and owner, and the run of replies a k_answer block appends, ARE the
+// exchange: no staging bins, no send/recv kernels competing with the probes for SMs, no per-chunk all-gather of counters.
+// The counts travel in-band: after its kernel a rank stores, into every peer's PeerCtl, how much it wrote there, fences,
+// and raises that peer's flag to the step's epoch (k_publish); the consumer's stream holds a one-block kernel that waits
+// for the R flags (k_wait, bounded by a timeout).  Re-use is safe without a further barrier: a rank routes step n+1 only
+// after its merge of step n, i.e. after every owner's "replies of step n complete" flag, which each owner raises after it
+// has finished READING that rank's keys; and an owner writes the replies of step n+1 only after the asker's keys of step
+// n+1, which the asker sends after its merge of step n has read the replies of step n.
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerCtl {
+    unsigned long long key_cnt[KG_MAX_RANKS];      // [s] keys rank s sent me in the current step
+    unsigned long long max_bin[KG_MAX_RANKS];      // [s] the largest bin rank s filled (for anybody): > cap means everybody repeats the step
+    unsigned long long reply_cnt[KG_MAX_RANKS];    // [o] replies owner o sent me
+    unsigned long long flag_keys[KG_MAX_RANKS];    // [s] epoch of the last step whose keys from s are complete
+    unsigned long long flag_replies[KG_MAX_RANKS]; // [o] likewise for the replies of owner o
+    unsigned long long timed_out;                  // set by this rank's own k_wait
+};
+struct PeerBases {
+    uint8_t* base[KG_MAX_RANKS];
+};
+struct PeerLayout { // byte offsets inside an exchange buffer
+    uint64_t cap = 0, recv_lo = 0, recv_hi = 0, rr_idx = 0, rr_payload = 0, total = 0;
+    void set(uint64_t R, uint64_t c) {
+        auto up = [](uint64_t x) { return (x + 4095) & ~4095ull; };
+        cap = c;
+        recv_lo = 4096;
+        recv_hi = up(recv_lo + R * c * 4);
+        rr_idx = up(recv_hi + R * c);
+        rr_payload = up(rr_idx + R * c * 4);
+        total = up(rr_payload + R * c * 16);
+    }
+};
+// phase 0: keys (my_cnt = send_cnt), phase 1: replies (my_cnt = reply_cnt).  One thread per peer.
+__global__ void k_publish(PeerBases pb, int me, int R, int phase, const unsigned long long* __restrict__ my_cnt, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p >= R) return;
+    PeerCtl* pc = reinterpret_cast<PeerCtl*>(pb.base[p]);
+    __threadfence_system(); // the data stores of the kernel before this one are ordered before what follows
+    if (phase == 0) {
+        unsigned long long mx = 0;
+        for (int o = 0; o < R; o++) mx = max(mx, my_cnt[o]);
+        pc->key_cnt[me] = my_cnt[p];
+        pc->max_bin[me] = mx;
+    } else {
+        pc->reply_cnt[me] = my_cnt[p];
+    }
+    __threadfence_system();
+    volatile unsigned long long* flag = phase == 0 ? &pc->flag_keys[me] : &pc->flag_replies[me];
+    *flag = epoch;
+}
+__global__ void k_wait(PeerCtl* mine, int R, int phase, unsigned long long epoch, unsigned long long timeout_ns) {
+    const int p = threadIdx.x;
+    if (p >= R) return;
+    volatile unsigned long long* flag = phase == 0 ? &mine->flag_keys[p] : &mine->flag_replies[p];
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*flag < epoch) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { // a peer died or never called: report instead of hanging the GPU
+            mine->timed_out = 1;
+            break;
+        }
+    }
+    __threadfence_system();
 }
 
 } // namespace
@@ -362,6 +482,14 @@ struct kg_comm {
     DevBuf bitmap, word_cnt, word_rank; // merge
     cudaEvent_t ev_begin = nullptr;
     kg_shard_stats stats = {};
+    // direct transport
+    DevBuf xbuf;                        // this rank's exchange buffer (PeerLayout)
+    PeerLayout xl;
+    PeerBases xpeers = {};              // every rank's buffer as this process sees it ([rank] = xbuf.p)
+    bool xopened[KG_MAX_RANKS] = {};    // peers mapped with cudaIpcOpenMemHandle (to be closed)
+    uint64_t xepoch = 0;
+    DevBuf xstage;                      // small device staging for the bootstrap all-gathers
+    PeerCtl* h_ctl = nullptr;           // pinned copy of the control block, read after a step
 };
 
 namespace {
@@ -411,9 +539,14 @@ int shard_route(kg_comm* c, ShardChunk& k, kg_batch* b, cudaStream_t st) {
     CU(cudaMemsetAsync(k.send_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
     k.h[CAP_SLOT] = k.cap; // travels with the counters: every rank can see who overflowed
     CU(cudaMemcpyAsync(k.send_cnt.as<unsigned long long>() + CAP_SLOT, &k.h[CAP_SLOT], 8, cudaMemcpyHostToDevice, st));
+    RouteDst dst = {};
+    for (uint32_t o = 0; o < R; o++) {
+        dst.lo[o] = k.send_lo.as<uint32_t>() + o * k.cap;
+        dst.hi[o] = k.send_hi.as<uint8_t>() + o * k.cap;
+    }
     if (ntiles)
-        k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, k.tile0, R, k.cap, k.send_lo.as<uint32_t>(), k.send_hi.as<uint8_t>(),
-                                              k.send_pos.as<uint32_t>(), k.send_cnt.as<unsigned long long>());
+        k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)vtotal, k.tile0, R, k.cap, dst, k.send_pos.as<uint32_t>(),
+                                              k.send_cnt.as<unsigned long long>());
     cudaEventRecord(k.ev_route, st);
     return KG_OK;
 }
@@ -569,9 +702,14 @@ int shard_answer(kg_comm* c, ShardChunk& k, const kg_table* table, bool sync) {
     shard_l2_setaside(table, true);
     CU(cudaStreamWaitEvent(st, k.ev_keys, 0));
     CU(cudaMemsetAsync(k.reply_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
+    ReplyDst rdst = {};
+    for (int s = 0; s < R; s++) {
+        rdst.idx[s] = k.reply_idx.as<uint32_t>() + k.recv_off[s];
+        rdst.payload[s] = k.reply_payload.as<int4>() + k.recv_off[s];
+    }
     if (tiles)
-        k_answer<<<(unsigned)tiles, PROBE_BLK, PROBE_SMEM, st>>>(k.recv_lo.as<uint32_t>(), k.recv_hi.as<uint8_t>(), plan, table->view(), k.reply_idx.as<uint32_t>(),
-                                                                 k.reply_payload.as<int4>(), k.reply_cnt.as<unsigned long long>(), probe_flags());
+        k_answer<<<(unsigned)tiles, PROBE_BLK, PROBE_SMEM, st>>>(k.recv_lo.as<uint32_t>(), k.recv_hi.as<uint8_t>(), plan, table->view(), rdst,
+                                                                 k.reply_cnt.as<unsigned long long>(), probe_flags());
     cudaEventRecord(k.ev_answer, st);
     if (sync) {
         CU(cudaMemcpyAsync(k.h + 32, k.reply_cnt.p, SHARD_CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
@@ -650,7 +788,8 @@ int shard_exchange_replies(kg_comm* c, ShardChunk& k, int ci, cudaStream_t st) {
 }
 
 // ---- merge: replies of all chunks -> per-tile hit chunks -> the unchanged rest of the pipeline ----
-int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result** out) {
+int dx_collect(kg_comm* c, ShardChunk& k);
+int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params* prm, kg_result** out, bool direct = false) {
     kg_context* ctx = c->ctx;
     const int R = c->nranks, H = c->nchunks;
     const uint64_t vtotal = b->vtotal;
@@ -666,10 +805,20 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
             sp[h].first[o + 1] = sp[h].first[o] + k.rr_n[o];
             longest = std::max(longest, k.rr_n[o]);
         }
+        if (direct) { // the reply counts are on the device (PeerCtl): walk the regions up to their capacity
+            longest = k.cap;
+            sp[h].dev_n = reinterpret_cast<PeerCtl*>(c->xbuf.p)->reply_cnt;
+        }
         grid[h] = (unsigned)(blocks_for(longest, 256 * MERGE_U) * (uint64_t)R);
         grid_place[h] = (unsigned)(blocks_for(longest, 256 * PLACE_U) * (uint64_t)R);
         nhits += sp[h].first[R];
         kmers += k.kmers;
+    }
+    const uint32_t* rr_idx_of[KG_MAX_CHUNKS];
+    const int4* rr_payload_of[KG_MAX_CHUNKS];
+    for (int h = 0; h < H; h++) {
+        rr_idx_of[h] = direct ? reinterpret_cast<const uint32_t*>(c->xbuf.as<uint8_t>() + c->xl.rr_idx) : c->ch[h].rr_idx.as<uint32_t>();
+        rr_payload_of[h] = direct ? reinterpret_cast<const int4*>(c->xbuf.as<uint8_t>() + c->xl.rr_payload) : c->ch[h].rr_payload.as<int4>();
     }
     const uint32_t nwords = ntiles * (uint32_t)(TILE / 32);
     const size_t bitmap_bytes = ((size_t)nwords + 1) * 4;
@@ -683,7 +832,7 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
             const ShardChunk& k = c->ch[h];
             CU(cudaStreamWaitEvent(st, k.ev_replies, 0));
             if (grid[h])
-                k_mark_replies<<<grid[h], 256, 0, st>>>(k.rr_idx.as<uint32_t>(), sp[h], k.cap, k.send_cnt.as<unsigned long long>(), k.send_pos.as<uint32_t>(),
+                k_mark_replies<<<grid[h], 256, 0, st>>>(rr_idx_of[h], sp[h], k.cap, k.send_cnt.as<unsigned long long>(), k.send_pos.as<uint32_t>(),
                                                         c->bitmap.as<uint32_t>(), d_ctr);
         }
         k_word_popc<<<blocks_for((size_t)nwords + 1, 256), 256, 0, st>>>(c->bitmap.as<uint32_t>(), nwords, c->word_cnt.as<uint32_t>());
@@ -691,12 +840,13 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
         for (int h = 0; h < H; h++) {
             const ShardChunk& k = c->ch[h];
             if (grid_place[h])
-                k_place_replies<<<grid_place[h], 256, 0, st>>>(k.rr_idx.as<uint32_t>(), k.rr_payload.as<int4>(), sp[h], k.cap, k.send_cnt.as<unsigned long long>(),
+                k_place_replies<<<grid_place[h], 256, 0, st>>>(rr_idx_of[h], rr_payload_of[h], sp[h], k.cap, k.send_cnt.as<unsigned long long>(),
                                                          k.send_pos.as<uint32_t>(), c->bitmap.as<uint32_t>(), c->word_rank.as<uint32_t>(), (uint32_t)hit_cap,
                                                          sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>());
         }
         k_tile_meta<<<blocks_for(ntiles, 256), 256, 0, st>>>(c->word_rank.as<uint32_t>(), ntiles, (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
-                                                           sl.tile_cnt.as<uint32_t>(), d_ctr, kmers);
+                                                           sl.tile_cnt.as<uint32_t>(), d_ctr, kmers,
+                                                           direct ? c->ch[0].send_cnt.as<unsigned long long>() + KG_MAX_RANKS : nullptr);
         sl.launches += 3 + 2 * (uint32_t)H;
         return KG_OK;
     };
@@ -705,8 +855,18 @@ int shard_merge(kg_comm* c, const kg_table* table, kg_batch* b, const kg_params*
     kg_result* r = new kg_result();
     r->ctx = ctx;
     RunScratch& sc = scratch_of(ctx);
-    int rc = pipe_enqueue(ctx, sc.slot[0], table, b, prm, r, std::max<uint64_t>(nhits, 1), 0, &stage);
+    int rc = pipe_enqueue(ctx, sc.slot[0], table, b, prm, r, direct ? sc.hit_cap_seen : std::max<uint64_t>(nhits, 1), 0, &stage);
     if (rc == KG_OK) rc = pipe_finish(ctx, sc.slot[0], table, b, prm, r, 0, &stage);
+    if (rc == KG_OK && direct) { // the counts of the step, now that it is over
+        rc = dx_collect(c, c->ch[0]);
+        nhits = 0;
+        for (int o = 0; o < R; o++) nhits += c->ch[0].rr_n[o];
+    }
+    if (rc == KG_OK && direct && c->ch[0].cap_seen > c->xl.cap) { // some bin overflowed somewhere: the caller repeats the step
+        kg_result_free(r);
+        *out = nullptr;
+        return KG_OK;
+    }
     if (rc == KG_OK && r->stats.num_hits != nhits) {
         // distinct replies always land on distinct positions; fewer bits than replies means a peer answered a query twice
         kg_set_error("kg_batch_run_sharded: %llu replies but %llu hit positions", (unsigned long long)nhits, (unsigned long long)r->stats.num_hits);
@@ -756,6 +916,164 @@ int shard_begin(kg_comm* c, kg_batch* b, int want_chunks) {
     for (int h = 0; h < H; h++) {
         c->ch[h].tile0 = (uint32_t)((uint64_t)ntiles * h / H);
         c->ch[h].tile1 = (uint32_t)((uint64_t)ntiles * (h + 1) / H);
+    }
+    return KG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// direct transport, host side
+// ---------------------------------------------------------------------------------------------------------------
+bool shard_direct_wanted() { // KG_SHARD_TRANSPORT=nccl | copy selects the staged transports (bins + send/recv or peer copies)
+    const char* e = getenv("KG_SHARD_TRANSPORT");
+    return !e || !strcmp(e, "direct");
+}
+uint64_t dx_cap_wanted(const kg_comm* c, const kg_batch* b) { // an even split plus an eighth
+    const uint64_t R = (uint64_t)c->nranks, positions = ((b->vtotal + TILE - 1) >> TILE_SHIFT) * (uint64_t)TILE;
+    return R == 1 ? std::max<uint64_t>(positions, 1) : positions / R + positions / (8 * R) + 4096;
+}
+// bootstrap all-gather of a few bytes per rank over NCCL (host-synchronous; also serves as a barrier)
+int allgather_host(kg_comm* c, const void* mine, size_t bytes, void* all) {
+    NcclApi& nc = nccl_api();
+    KG_TRY(c->xstage.ensure(bytes * ((size_t)c->nranks + 1)));
+    uint8_t* d = c->xstage.as<uint8_t>();
+    cudaStream_t st = c->comm_stream;
+    CU(cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, st));
+    NC(nc.AllGather(d, d + bytes, bytes, ncclUint8, c->nccl, st));
+    CU(cudaMemcpyAsync(all, d + bytes, bytes * (size_t)c->nranks, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return KG_OK;
+}
+void dx_close(kg_comm* c) {
+    for (int p = 0; p < KG_MAX_RANKS; p++) {
+        if (c->xopened[p]) cudaIpcCloseMemHandle(c->xpeers.base[p]);
+        c->xopened[p] = false;
+        c->xpeers.base[p] = nullptr;
+    }
+    cudaGetLastError();
+}
+int dx_alloc(kg_comm* c, uint64_t cap) {
+    c->xbuf.release();
+    c->xl.set((uint64_t)c->nranks, cap);
+    KG_TRY(c->xbuf.ensure(c->xl.total));
+    CU(cudaMemset(c->xbuf.p, 0, 4096));
+    if (!c->h_ctl) CU(cudaMallocHost(&c->h_ctl, sizeof(PeerCtl)));
+    return KG_OK;
+}
+// Collective (one process per GPU): agree on the capacity, (re)allocate, map everybody's buffer.  Called before the first
+// step and after a step in which some bin overflowed -- every rank sees that in its PeerCtl, so they all come here.
+int dx_setup(kg_comm* c, uint64_t want_cap) {
+    const int R = c->nranks;
+    uint64_t caps[KG_MAX_RANKS] = {};
+    KG_TRY(allgather_host(c, &want_cap, 8, caps)); // also a barrier: nobody is inside the previous step any more
+    uint64_t cap = c->xl.cap;
+    for (int p = 0; p < R; p++) cap = std::max(cap, caps[p]);
+    if (c->xbuf.p && cap == c->xl.cap) return KG_OK;
+    CU(cudaStreamSynchronize(c->ctx->stream));
+    dx_close(c);
+    uint64_t zero = 0, zeros[KG_MAX_RANKS];
+    KG_TRY(allgather_host(c, &zero, 8, zeros)); // every rank has unmapped its peers before anybody frees
+    KG_TRY(dx_alloc(c, cap));
+    cudaIpcMemHandle_t mine, all[KG_MAX_RANKS];
+    CU(cudaIpcGetMemHandle(&mine, c->xbuf.p));
+    KG_TRY(allgather_host(c, &mine, sizeof mine, all));
+    for (int p = 0; p < R; p++) {
+        if (p == c->rank) {
+            c->xpeers.base[p] = c->xbuf.as<uint8_t>();
+        } else {
+            void* q = nullptr;
+            CU(cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess));
+            c->xpeers.base[p] = (uint8_t*)q;
+            c->xopened[p] = true;
+        }
+    }
+    KG_TRY(allgather_host(c, &zero, 8, zeros)); // everybody's control block is zeroed and mapped before anyone writes
+    return KG_OK;
+}
+// keys: encode, bin by owner, store every bin straight into its owner's buffer; tell the owners how much arrived
+int dx_route(kg_comm* c, kg_batch* b, bool flags) {
+    ShardChunk& k = c->ch[0];
+    const uint32_t R = (uint32_t)c->nranks, me = (uint32_t)c->rank;
+    cudaStream_t st = c->ctx->stream;
+    k.cap = c->xl.cap;
+    const uint32_t ntiles = k.tile1 - k.tile0;
+    KG_TRY(k.send_cnt.ensure(SHARD_CNT_SLOTS * 8));
+    KG_TRY(k.reply_cnt.ensure(SHARD_CNT_SLOTS * 8));
+    KG_TRY(k.send_pos.ensure(R * k.cap * 4));
+    CU(cudaMemsetAsync(k.send_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
+    RouteDst dst = {};
+    for (uint32_t o = 0; o < R; o++) {
+        dst.lo[o] = reinterpret_cast<uint32_t*>(c->xpeers.base[o] + c->xl.recv_lo) + (size_t)me * k.cap;
+        dst.hi[o] = c->xpeers.base[o] + c->xl.recv_hi + (size_t)me * k.cap;
+    }
+    if (ntiles)
+        k_route<<<ntiles, PROBE_BLK, 0, st>>>(b->stream(), (uint32_t)b->vtotal, k.tile0, R, k.cap, dst, k.send_pos.as<uint32_t>(),
+                                              k.send_cnt.as<unsigned long long>());
+    cudaEventRecord(k.ev_route, st);
+    c->xepoch++;
+    k_publish<<<1, 32, 0, st>>>(c->xpeers, (int)me, (int)R, 0, k.send_cnt.as<unsigned long long>(), c->xepoch);
+    if (flags) k_wait<<<1, 32, 0, st>>>(reinterpret_cast<PeerCtl*>(c->xbuf.p), (int)R, 0, c->xepoch, 20ull * 1000000000ull);
+    cudaEventRecord(k.ev_keys, st);
+    CU(cudaGetLastError());
+    return KG_OK;
+}
+// answer: probe what arrived; a hit's reply goes straight into the asker's buffer
+int dx_answer(kg_comm* c, const kg_table* table, bool flags) {
+    ShardChunk& k = c->ch[0];
+    const int R = c->nranks, me = c->rank;
+    cudaStream_t st = c->ctx->stream;
+    PeerCtl* ctl = reinterpret_cast<PeerCtl*>(c->xbuf.p);
+    const uint64_t tps = (k.cap + TILE - 1) >> TILE_SHIFT;
+    if (tps * (uint64_t)R > 0x7FFFFFFFull) KG_FAIL(KG_ERANGE, "kg_batch_run_sharded: exchange regions of %llu keys", (unsigned long long)k.cap);
+    AnswerPlan plan = {};
+    plan.nseg = (uint32_t)R;
+    ReplyDst rdst = {};
+    for (int s = 0; s <= R; s++) {
+        plan.tile_first[s] = (uint32_t)(tps * (uint64_t)s);
+        plan.seg_off[s] = k.cap * (uint64_t)s;
+    }
+    plan.dev_cnt = ctl->key_cnt;
+    plan.interleave = 1;
+    plan.rot = (uint32_t)me;
+    for (int s = 0; s < R; s++) {
+        rdst.idx[s] = reinterpret_cast<uint32_t*>(c->xpeers.base[s] + c->xl.rr_idx) + (size_t)me * k.cap;
+        rdst.payload[s] = reinterpret_cast<int4*>(c->xpeers.base[s] + c->xl.rr_payload) + (size_t)me * k.cap;
+    }
+    shard_l2_setaside(table, true);
+    CU(cudaMemsetAsync(k.reply_cnt.p, 0, SHARD_CNT_SLOTS * 8, st));
+    k_answer<<<(unsigned)(tps * (uint64_t)R), PROBE_BLK, PROBE_SMEM, st>>>(reinterpret_cast<const uint32_t*>(c->xbuf.as<uint8_t>() + c->xl.recv_lo),
+                                                                          c->xbuf.as<uint8_t>() + c->xl.recv_hi, plan, table->view(), rdst,
+                                                                          k.reply_cnt.as<unsigned long long>(), probe_flags());
+    cudaEventRecord(k.ev_answer, st);
+    c->xepoch++;
+    k_publish<<<1, 32, 0, st>>>(c->xpeers, me, R, 1, k.reply_cnt.as<unsigned long long>(), c->xepoch);
+    if (flags) k_wait<<<1, 32, 0, st>>>(ctl, R, 1, c->xepoch, 20ull * 1000000000ull);
+    cudaEventRecord(k.ev_replies, st);
+    CU(cudaGetLastError());
+    return KG_OK;
+}
+// after the step (the stream is idle): counters -> host, statistics, sanity
+int dx_collect(kg_comm* c, ShardChunk& k) {
+    const int R = c->nranks;
+    cudaStream_t st = c->ctx->stream;
+    CU(cudaMemcpyAsync(c->h_ctl, c->xbuf.p, sizeof(PeerCtl), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(k.h, k.send_cnt.p, (KG_MAX_RANKS + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(k.h + 32, k.reply_cnt.p, KG_MAX_RANKS * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (c->h_ctl->timed_out) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: a peer did not arrive within 20 s (did every rank call?)");
+    uint64_t worst = 0;
+    for (int s = 0; s < R; s++) worst = std::max<uint64_t>(worst, c->h_ctl->max_bin[s]);
+    k.cap_seen = worst; // > capacity: somebody's bin overflowed -- every rank reads the same numbers and repeats the step
+    k.cap = c->xl.cap;
+    shard_take_counts(c, k, k.h);
+    k.cap_seen = worst;
+    for (int s = 0; s < R; s++) {
+        k.recv_n[s] = std::min<uint64_t>(c->h_ctl->key_cnt[s], k.cap);
+        k.reply_n[s] = k.h[32 + s];
+        k.rr_n[s] = std::min<uint64_t>(c->h_ctl->reply_cnt[s], k.cap);
+        c->stats.keys_received += k.recv_n[s];
+        c->stats.replies_sent += k.reply_n[s];
+        c->stats.replies_received += k.rr_n[s];
+        if (s != c->rank) c->stats.bytes_sent += k.send_n[s] * 5 + k.reply_n[s] * (4 + sizeof(int4));
     }
     return KG_OK;
 }
@@ -869,7 +1187,10 @@ extern "C" void kg_comm_free(kg_comm* c) {
         for (cudaEvent_t e : {k.ev_route, k.ev_keys, k.ev_answer, k.ev_replies})
             if (e) cudaEventDestroy(e);
     }
-    for (DevBuf* d : {&c->bitmap, &c->word_cnt, &c->word_rank}) d->release();
+    for (DevBuf* d : {&c->bitmap, &c->word_cnt, &c->word_rank, &c->xstage}) d->release();
+    dx_close(c);
+    c->xbuf.release();
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->group && --c->group->alive == 0) delete c->group;
     delete c;
@@ -901,6 +1222,26 @@ extern "C" int kg_batch_run_sharded(kg_comm* c, const kg_table* shard, kg_batch*
         const kg_table* t;
         ~Restore() { shard_l2_setaside(t, true); }
     } restore{shard};
+    if (c->nccl && shard_direct_wanted()) {
+        // Direct transport: route -> (flags) -> answer -> (flags) -> merge, all on the compute stream, one host wait at the end.
+        for (int attempt = 0;; attempt++) {
+            KG_TRY(shard_begin(c, batch, 1));
+            if (!c->xbuf.p) KG_TRY(dx_setup(c, dx_cap_wanted(c, batch)));
+            KG_TRY(dx_route(c, batch, true));
+            KG_TRY(dx_answer(c, shard, true));
+            // The persisting-L2 set-aside is a device-wide limit that is switched from the host, not in stream order: it is on
+            // (for the prefilter) while route and answer run and must be off for the merge, so the host waits for the replies
+            // here -- the one wait inside a step (the merge's own wait ends it).
+            CU(cudaEventSynchronize(c->ch[0].ev_replies));
+            KG_TRY(shard_merge(c, shard, batch, params, result, true));
+            if (*result) break;
+            if (attempt) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: bin overflow persisted at capacity %llu", (unsigned long long)c->xl.cap);
+            // a skewed batch (or a larger one than the buffers were made for): all ranks have read the same max_bin values
+            KG_TRY(dx_setup(c, c->ch[0].cap_seen + c->ch[0].cap_seen / 32 + 4096));
+        }
+        c->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return KG_OK;
+    }
     KG_TRY(shard_begin(c, batch, shard_chunks_wanted(c, batch)));
     const int H = c->nchunks;
     if (!c->nccl) { // a single rank: the whole path without an interconnect
@@ -963,6 +1304,63 @@ extern "C" int kg_batch_run_sharded_local(kg_comm* const* comms, const kg_table*
             rc = fn(r);
         }
     };
+    auto sync_all = [&]() {
+        each([&](int r) {
+            if (cudaStreamSynchronize(comms[r]->ctx->stream) != cudaSuccess) {
+                kg_set_error("kg_batch_run_sharded_local: %s", cudaGetErrorString(cudaGetLastError()));
+                return (int)KG_ECUDA;
+            }
+            return (int)KG_OK;
+        });
+    };
+    if (shard_direct_wanted() && nranks > 1) {
+        // The direct transport inside one process: the same kernels store into their peers' buffers (peer access between
+        // devices, plain pointers on one device); the phases are separated by host synchronisation instead of arrival flags
+        // (virtual ranks may share one stream, where a waiting kernel would wait for work queued behind it).
+        for (int attempt = 0; rc == KG_OK; attempt++) {
+            each([&](int r) { return shard_begin(comms[r], batches[r], 1); });
+            uint64_t cap = 0;
+            bool fresh = false;
+            for (int r = 0; r < nranks; r++) {
+                cap = std::max(cap, std::max(dx_cap_wanted(comms[r], batches[r]), comms[r]->xl.cap));
+                if (attempt) cap = std::max<uint64_t>(cap, comms[r]->ch[0].cap_seen + comms[r]->ch[0].cap_seen / 32 + 4096);
+            }
+            for (int r = 0; r < nranks; r++) fresh = fresh || !comms[r]->xbuf.p || comms[r]->xl.cap != cap;
+            if (fresh) {
+                sync_all();
+                each([&](int r) { return dx_alloc(comms[r], cap); });
+                for (int r = 0; r < nranks && rc == KG_OK; r++)
+                    for (int p = 0; p < nranks; p++) comms[r]->xpeers.base[p] = comms[p]->xbuf.as<uint8_t>();
+            }
+            each([&](int r) { return dx_route(comms[r], batches[r], false); });
+            sync_all();
+            each([&](int r) { return dx_answer(comms[r], shards[r], false); });
+            sync_all();
+            each([&](int r) { return shard_merge(comms[r], shards[r], batches[r], params, &results[r], true); });
+            if (rc != KG_OK) break;
+            bool again = false;
+            for (int r = 0; r < nranks; r++) again = again || !results[r];
+            if (!again) break;
+            for (int r = 0; r < nranks; r++) {
+                kg_result_free(results[r]);
+                results[r] = nullptr;
+            }
+            if (attempt) {
+                kg_set_error("kg_batch_run_sharded_local: bin overflow persisted at capacity %llu", (unsigned long long)cap);
+                rc = KG_ECUDA;
+            }
+        }
+        if (rc != KG_OK) {
+            for (int r = 0; r < nranks; r++) {
+                kg_result_free(results[r]);
+                results[r] = nullptr;
+            }
+            return rc;
+        }
+        const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        for (int r = 0; r < nranks; r++) comms[r]->stats.ms_total = ms;
+        return KG_OK;
+    }
     // every phase ends host-synchronised on every rank before the next one reads its neighbours' buffers
     each([&](int r) { int e = shard_begin(comms[r], batches[r], 1); return e != KG_OK ? e : shard_route_sync(comms[r], comms[r]->ch[0], batches[r], comms[r]->ctx->stream); });
     each([&](int r) { return shard_exchange_keys(comms[r], comms[r]->ch[0], 0, batches[r], comms[r]->ctx->stream); });

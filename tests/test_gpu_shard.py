@@ -30,6 +30,17 @@ def ctx(kg):
     c.close()
 
 
+@pytest.fixture(autouse=True, params=["direct", "staged"])
+def transport(request, monkeypatch):
+    """Both exchanges: `direct` = k_route / k_answer store straight into the peer's buffer (the default), `staged` = bins that
+    are moved afterwards (peer copies here, NCCL send/recv between processes)."""
+    if request.param == "staged":
+        monkeypatch.setenv("KG_SHARD_TRANSPORT", "copy")
+    else:
+        monkeypatch.delenv("KG_SHARD_TRANSPORT", raising=False)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def universe():
     u = synth.Universe(n_families=300, seed=0x4B470003)
@@ -218,15 +229,18 @@ def _gpu_count():
         return 0
 
 
-def _nccl_two_processes(kg):
+def _nccl_two_processes(kg, transport):
     """The NCCL transport: two processes, one GPU each, the id handed over through a file.  Only DEFINED as a test on a box
     with two GPUs: NCCL refuses two ranks on one device ("Duplicate GPU detected"), and two processes that wait for each
     other's kernels on one GPU are ruled out by the profiling guide (Xid 109), so a one-GPU box covers the exchange with
     virtual ranks in one process (above) and bench.py's configs4 leg covers the NCCL transport at N >= 2."""
     import tempfile
+    env = dict(os.environ)
+    if env.get("KG_SHARD_TRANSPORT") == "copy":
+        env["KG_SHARD_TRANSPORT"] = "nccl"
     with tempfile.TemporaryDirectory() as d:
         procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "shard_nccl_worker.py"), str(r), "2", d],
-                                  cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+                                  cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
         outs = []
         for p in procs:
             try:
