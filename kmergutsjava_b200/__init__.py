@@ -35,6 +35,8 @@ EXPORTS = [
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
     "kg_functions_load", "kg_functions_read", "kg_functions_count", "kg_functions_name", "kg_functions_free",
     "kg_format_java_f", "kg_report_write", "kg_main",
+    "kg_fasta_stream_open", "kg_fasta_stream_next", "kg_fasta_stream_close",
+    "kg_report_open", "kg_report_add", "kg_report_close", "kg_call_dna_range",
     "kg_shard_owner", "kg_comm_unique_id", "kg_comm_init", "kg_comm_init_local", "kg_comm_free", "kg_comm_last_stats",
     "kg_table_load_sharded", "kg_table_from_image_sharded", "kg_table_from_device_entries_sharded",
     "kg_batch_run_sharded", "kg_batch_run_sharded_local",
@@ -114,6 +116,11 @@ def lib() -> C.CDLL:
         "kg_format_java_f": (i32, [C.c_float, i32, C.c_char_p, sz]),
         "kg_report_write": (i32, [C.c_char_p, i32, i32, vp, vp, vp, vp]),
         "kg_main": (i32, [i32, C.POINTER(C.c_char_p)]),
+        "kg_fasta_stream_open": (i32, [C.c_char_p, sz, pp]), "kg_fasta_stream_next": (i32, [vp, pp]),
+        "kg_fasta_stream_close": (None, [vp]),
+        "kg_report_open": (i32, [C.c_char_p, pp]), "kg_report_add": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "kg_report_close": (i32, [vp]),
+        "kg_call_dna_range": (i32, [vp, u64, C.POINTER(u64), C.POINTER(u64), C.c_char_p]),
         "kg_shard_owner": (i32, [u64, i32]), "kg_comm_unique_id": (i32, [vp]),
         "kg_comm_init": (i32, [vp, i32, i32, vp, pp]), "kg_comm_init_local": (i32, [pp, i32, pp]),
         "kg_comm_free": (None, [vp]), "kg_comm_last_stats": (i32, [vp, C.POINTER(ShardStats)]),
@@ -415,12 +422,38 @@ class Result:
             self._h = C.c_void_p()
 
 
+def call_dna_range(call, contig_len: int):
+    """(begin, end, strand) of a CALL of a 6-frame run on the contig: 0-based, inclusive (kg_call_dna_range)."""
+    rec = np.zeros(1, dtype=CALL_DTYPE)
+    for f in CALL_DTYPE.names:
+        rec[f] = call[f]
+    b, e, sd = C.c_uint64(), C.c_uint64(), C.create_string_buffer(2)
+    _check(lib().kg_call_dna_range(rec.ctypes.data, contig_len, C.byref(b), C.byref(e), sd))
+    return int(b.value), int(e.value), sd.raw[:1].decode()
+
+
+def fasta_batches(path: str, batch_bytes: int):
+    """kg_fasta_stream_*: the file as a sequence of Fasta objects of about batch_bytes of text each (whole records)."""
+    h = C.c_void_p()
+    _check(lib().kg_fasta_stream_open(path.encode(), batch_bytes, C.byref(h)))
+    try:
+        while True:
+            b = C.c_void_p()
+            _check(lib().kg_fasta_stream_next(h, C.byref(b)))
+            if not b:
+                break
+            yield Fasta(None, _h=b)
+    finally:
+        lib().kg_fasta_stream_close(h)
+
+
 class Fasta:
     """readFasta (KGJ:1132-1192) through the host library."""
 
-    def __init__(self, path: str):
-        self._h = C.c_void_p()
-        _check(lib().kg_fasta_read(path.encode(), C.byref(self._h)))
+    def __init__(self, path, _h=None):
+        self._h = _h if _h is not None else C.c_void_p()
+        if _h is None:
+            _check(lib().kg_fasta_read(path.encode(), C.byref(self._h)))
         L = lib()
         self.n = L.kg_fasta_count(self._h)
         self.ids = [L.kg_fasta_id(self._h, i).decode(errors="replace") for i in range(self.n)]

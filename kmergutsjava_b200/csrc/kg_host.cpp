@@ -191,27 +191,18 @@ size_t next_caption_line(std::string_view text, size_t from) {
 // readFasta, KGJ:1132-1192.  The text is cut at caption lines into one range per thread; a caption line puts the
 // reference's reader into the same state wherever it comes from, so the ranges parse independently and concatenate.
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
-    if (!path || !out) {
-        kg_set_error("kg_fasta_read: null argument");
-        return KG_EINVAL;
-    }
-    std::string text;
-    if (!read_all(path, text)) {
-        kg_set_error("cannot read %s", path);
-        return KG_EIO;
-    }
+static int parse_text(std::string_view text, size_t end, kg_fasta** out) { // text[0, end); a caption line starts at `end` if end < size
     size_t min_chunk = 4u << 20;
     if (const char* e = getenv("KG_FASTA_CHUNK")) min_chunk = std::max<size_t>(1, (size_t)atoll(e)); // tests: many tiny ranges
     unsigned hw = std::thread::hardware_concurrency();
-    size_t want = std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, text.size() / min_chunk + 1});
+    size_t want = std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, end / min_chunk + 1});
     std::vector<size_t> cut{0};
     for (size_t k = 1; k < want; k++) {
-        size_t p = next_caption_line(text, std::max(cut.back() + 1, text.size() / want * k));
-        if (p >= text.size()) break;
+        size_t p = next_caption_line(text.substr(0, end), std::max(cut.back() + 1, end / want * k));
+        if (p >= end) break;
         if (p > cut.back()) cut.push_back(p);
     }
-    cut.push_back(text.size());
+    cut.push_back(end);
     const size_t parts = cut.size() - 1;
     std::vector<kg_fasta> part(parts);
     std::vector<std::string> errs(parts);
@@ -263,6 +254,105 @@ extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
     *out = fa;
     return KG_OK;
 }
+
+extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
+    if (!path || !out) {
+        kg_set_error("kg_fasta_read: null argument");
+        return KG_EINVAL;
+    }
+    std::string text;
+    if (!read_all(path, text)) {
+        kg_set_error("cannot read %s", path);
+        return KG_EIO;
+    }
+    return parse_text(text, text.size(), out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same reader over a file that is consumed in batches of whole records: the text is cut at caption
+// lines, like the ranges of the parallel reader, so every batch parses as the sequential reader would have parsed it and
+// the concatenation of the batches equals kg_fasta_read of the whole file.  Memory is bounded by the batch size (plus
+// the longest single record).
+// ---------------------------------------------------------------------------------------------------------------
+struct kg_fasta_stream {
+    gzFile g = nullptr; // gzopen reads plain files too, but the reference decides by NAME (KGJ:764): a plain FILE otherwise
+    FILE* f = nullptr;
+    std::string buf;
+    size_t batch = 0;
+    bool eof = false;
+    bool fill(size_t upto) {
+        std::vector<char> tmp(4u << 20);
+        while (!eof && buf.size() < upto) {
+            long got = g ? (long)gzread(g, tmp.data(), (unsigned)tmp.size()) : (long)fread(tmp.data(), 1, tmp.size(), f);
+            if (got < 0) return false;
+            if (got == 0) eof = true;
+            else buf.append(tmp.data(), (size_t)got);
+        }
+        return true;
+    }
+};
+extern "C" int kg_fasta_stream_open(const char* path, size_t batch_bytes, kg_fasta_stream** out) {
+    if (!path || !out) {
+        kg_set_error("kg_fasta_stream_open: null argument");
+        return KG_EINVAL;
+    }
+    kg_fasta_stream* s = new kg_fasta_stream();
+    s->batch = std::max<size_t>(batch_bytes, 1);
+    if (has_suffix(path, ".gz")) {
+        s->g = gzopen(path, "rb");
+        if (s->g) gzbuffer(s->g, 1 << 20);
+    } else {
+        s->f = fopen(path, "rb");
+    }
+    if (!s->g && !s->f) {
+        delete s;
+        kg_set_error("cannot read %s", path);
+        return KG_EIO;
+    }
+    *out = s;
+    return KG_OK;
+}
+extern "C" int kg_fasta_stream_next(kg_fasta_stream* s, kg_fasta** batch) {
+    if (!s || !batch) {
+        kg_set_error("kg_fasta_stream_next: null argument");
+        return KG_EINVAL;
+    }
+    *batch = nullptr;
+    size_t want = s->batch;
+    size_t cut;
+    for (;;) {
+        if (!s->fill(want + 1)) {
+            kg_set_error("kg_fasta_stream_next: read error");
+            return KG_EIO;
+        }
+        if (s->buf.empty()) return KG_OK; // end of the file
+        if (s->eof && s->buf.size() <= want) {
+            cut = s->buf.size();
+            break;
+        }
+        cut = next_caption_line(s->buf, std::min(want, s->buf.size() - 1));
+        // The candidate must be followed by at least one more byte of text: a '>' that is the last byte read so far is a
+        // caption line whichever bytes follow, but its record has to stay whole in the NEXT batch, which it does (cut before it).
+        if (cut < s->buf.size()) break;
+        if (s->eof) {
+            cut = s->buf.size();
+            break;
+        }
+        want = std::max(want * 2, s->buf.size() + (4u << 20)); // a record longer than the batch: read on to its end
+    }
+    if (cut == 0) cut = s->buf.size(); // (only when the buffer is one record without a further caption)
+    int rc = parse_text(s->buf, cut, batch);
+    if (rc != KG_OK) return rc;
+    s->buf.erase(0, cut);
+    return KG_OK;
+}
+extern "C" void kg_fasta_stream_close(kg_fasta_stream* s) {
+    if (!s) return;
+    if (s->g) gzclose(s->g);
+    if (s->f) fclose(s->f);
+    delete s;
+}
+
 extern "C" size_t kg_fasta_count(const kg_fasta* f) { return f ? f->ids.size() : 0; }
 extern "C" const char* kg_fasta_id(const kg_fasta* f, size_t i) { return (f && i < f->ids.size()) ? f->ids[i].c_str() : nullptr; }
 extern "C" const uint8_t* kg_fasta_bytes(const kg_fasta* f) { return f ? f->bytes.data() : nullptr; }
@@ -376,12 +466,91 @@ extern "C" int kg_format_java_f(float v, int precision, char* out, size_t outlen
 // ---------------------------------------------------------------------------------------------------------------
 // report, KGJ:810-818
 // ---------------------------------------------------------------------------------------------------------------
+struct kg_report {
+    FILE* out = nullptr;
+    bool own = false, header_done = false;
+    std::string path;
+};
+extern "C" int kg_report_open(const char* path, kg_report** out) {
+    if (!out) {
+        kg_set_error("kg_report_open: null argument");
+        return KG_EINVAL;
+    }
+    kg_report* r = new kg_report();
+    r->out = path ? fopen(path, "w") : stdout;
+    r->own = path != nullptr;
+    r->path = path ? path : "stdout";
+    if (!r->out) {
+        delete r;
+        kg_set_error("cannot write %s", path);
+        return KG_EIO;
+    }
+    *out = r;
+    return KG_OK;
+}
+extern "C" int kg_report_close(kg_report* r) {
+    if (!r) return KG_OK;
+    int rc = KG_OK;
+    if (r->own ? fclose(r->out) != 0 : fflush(r->out) != 0) {
+        kg_set_error("kg_report_close: write to %s failed", r->path.c_str());
+        rc = KG_EIO;
+    }
+    delete r;
+    return rc;
+}
+extern "C" int kg_call_dna_range(const kg_call* c, uint64_t contig_len, uint64_t* begin, uint64_t* end, char* strand) {
+    if (!c || !begin || !end || !strand) {
+        kg_set_error("kg_call_dna_range: null argument");
+        return KG_EINVAL;
+    }
+    if (c->strand_frame < 0 || c->strand_frame > 5 || c->start < 0 || c->end < c->start) {
+        kg_set_error("kg_call_dna_range: not a call of a 6-frame run (strand_frame %d, %d..%d)", c->strand_frame, c->start, c->end);
+        return KG_EINVAL;
+    }
+    // residue r of frame f is the codon at nucleotides f + 3r .. f + 3r + 2 of the strand that was translated (KGJ:320-343);
+    // the minus frames are frames of the full reverse complement (KGJ:1068-1071): x on it is L - 1 - x on the contig
+    const uint64_t f = (uint64_t)(c->strand_frame % 3), a = f + 3ull * (uint64_t)c->start, b = f + 3ull * (uint64_t)c->end + 2;
+    if (b >= contig_len) {
+        kg_set_error("kg_call_dna_range: residues %d..%d of frame %d lie outside a contig of %llu nucleotides", c->start, c->end,
+                     c->strand_frame, (unsigned long long)contig_len);
+        return KG_ERANGE;
+    }
+    const bool minus = c->strand_frame >= 3;
+    *strand = minus ? '-' : '+';
+    *begin = minus ? contig_len - 1 - b : a;
+    *end = minus ? contig_len - 1 - a : b;
+    return KG_OK;
+}
+static int report_add(kg_report* rep, int mode, int flags, const kg_fasta* fa, const kg_functions* fn, const kg_table* table, kg_result* result);
+extern "C" int kg_report_add(kg_report* rep, int mode, int flags, const kg_fasta* fa, const kg_functions* fn, const kg_table* table,
+                             kg_result* result) {
+    if (!rep) {
+        kg_set_error("kg_report_add: null argument");
+        return KG_EINVAL;
+    }
+    return report_add(rep, mode, flags, fa, fn, table, result);
+}
 extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_fasta* fa, const kg_functions* fn,
                                const kg_table* table, kg_result* result) {
     if (!fa || !fn || !result) {
         kg_set_error("kg_report_write: null argument");
         return KG_EINVAL;
     }
+    kg_report* rep = nullptr;
+    int rc = kg_report_open(path, &rep);
+    if (rc != KG_OK) return rc;
+    rc = report_add(rep, mode, debug, fa, fn, table, result);
+    const int rc2 = kg_report_close(rep);
+    return rc != KG_OK ? rc : rc2;
+}
+static int report_add(kg_report* rep, int mode, int flags, const kg_fasta* fa, const kg_functions* fn, const kg_table* table, kg_result* result) {
+    if (!fa || !fn || !result) {
+        kg_set_error("kg_report_add: null argument");
+        return KG_EINVAL;
+    }
+    const int debug = flags & 1;
+    const bool dna_ranges = (flags & 2) && mode != KG_MODE_AA;
+    const char* path = rep->own ? rep->path.c_str() : nullptr;
     const kg_call* calls = nullptr;
     const kg_otu* otus = nullptr;
     const kg_hit* hits = nullptr;
@@ -395,12 +564,17 @@ extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_f
         kg_set_error("kg_report_write: result has %zu sequences, FASTA has %zu", notus, n);
         return KG_EINVAL;
     }
-    FILE* out = path ? fopen(path, "w") : stdout;
-    if (!out) {
-        kg_set_error("cannot write %s", path);
-        return KG_EIO;
-    }
-    if (debug && table) { // KGJ:951-954
+    // functionArray.get(currentFI) throws for an index outside function.index and aborts the run (KGJ:403): a table that
+    // does not belong to this function.index must not turn into CALL lines with an empty name
+    for (size_t c = 0; c < ncalls; c++)
+        if (calls[c].fI < 0 || (size_t)calls[c].fI >= fn->names.size()) {
+            kg_set_error("CALL with function index %d but function.index has %zu names (the reference throws at KGJ:403): table and "
+                         "function.index do not belong together", calls[c].fI, fn->names.size());
+            return KG_EFORMAT;
+        }
+    FILE* out = rep->out;
+    if (debug && table && !rep->header_done) { // KGJ:951-954
+        rep->header_done = true;
         kg_table_info ti;
         kg_table_get_info(table, &ti);
         fprintf(out, "Kmer-table info: numSigs=%lld, entrySize=%lld, version=%lld\n", (long long)ti.num_slots,
@@ -470,8 +644,15 @@ extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_f
                     const kg_call& cl = calls[c];
                     kg_format_java_f(cl.weighted, 6, wbuf, sizeof wbuf);
                     put("CALL\t"); num(cl.start); put("\t"); num(cl.end); put("\t"); num(cl.count); put("\t"); num(cl.fI); put("\t"); // KGJ:398-404
-                    if (cl.fI >= 0 && (size_t)cl.fI < fn->names.size()) put(fn->names[(size_t)cl.fI]);
+                    put(fn->names[(size_t)cl.fI]);
                     put("\t"); put(wbuf); put("\n");
+                    if (dna_ranges) { // extension (-c): the reference prints protein coordinates of the frame only (KGJ:398-401)
+                        uint64_t b0 = 0, e0 = 0;
+                        char sd = '+';
+                        if (kg_call_dna_range(&cl, (uint64_t)len, &b0, &e0, &sd) == KG_OK) {
+                            put("DNA-RANGE\t"); num((long long)b0); put("\t"); num((long long)e0); put("\t"); buf.push_back(sd); put("\n");
+                        }
+                    }
                 }
                 flush_hits(0x7FFFFFFF);
             }
@@ -507,12 +688,9 @@ extern "C" int kg_report_write(const char* path, int mode, int debug, const kg_f
             if (!bufs[t].empty()) io_ok = fwrite(bufs[t].data(), 1, bufs[t].size(), out) == bufs[t].size();
     }
     if (!io_ok) {
-        if (path) fclose(out);
         kg_set_error("kg_report_write: write to %s failed", path ? path : "stdout");
         return KG_EIO;
     }
-    if (path) fclose(out);
-    else fflush(out);
     return KG_OK;
 }
 
@@ -535,6 +713,10 @@ static void usage() { // KGJ:618-635
     puts(" -l - (optional) limit for input Kmer array (long, default = 20,000,000)");
     puts(" -G - (extension) CUDA device index (default 0)");
     puts(" -C - (extension) cache file of the GPU table layout: read if present and valid, else written after loading -D");
+    puts(" -B - (extension) stream the query in batches of about this many megabytes of FASTA text (bounded memory; an id");
+    puts("      repeated in two different batches is reported in both, where the reference keeps only the last)");
+    puts(" -c - (extension) after every CALL of a DNA run, a line DNA-RANGE<TAB>begin<TAB>end<TAB>strand (0-based, inclusive,");
+    puts("      on the contig as given)");
 }
 
 extern "C" int kg_main(int argc, char** argv) {
@@ -543,6 +725,8 @@ extern "C" int kg_main(int argc, char** argv) {
     bool aa = false, debug = false;
     const char *dir = nullptr, *query = nullptr, *outp = nullptr, *cache = nullptr;
     int device = 0;
+    long batch_mb = 0;
+    bool dna_ranges = false;
     std::string err;
     for (int i = 1; i < argc && err.empty(); i++) {
         std::string a = argv[i];
@@ -567,6 +751,8 @@ extern "C" int kg_main(int argc, char** argv) {
             case 't': case 'l': value(); break;
             case 'G': device = atoi(value()); break;
             case 'C': cache = value(); break;
+            case 'B': batch_mb = atol(value()); break;
+            case 'c': dna_ranges = true; break;
             default: err = "Unknown parameter: " + a;
         }
     }
@@ -611,6 +797,50 @@ extern "C" int kg_main(int argc, char** argv) {
             if (cache && kg_table_save(ctx, table, cache) != KG_OK) fprintf(stderr, "Warning: %s\n", kg_last_error());
         }
         info("Table load time: " + std::to_string(ms(t0, now())) + " ms.");
+        const int rflags = (debug ? 1 : 0) | (dna_ranges ? 2 : 0);
+        if (batch_mb > 0) { // streaming: batch i+1 is read and parsed while batch i is on the GPU and in the report writer
+            kg_fasta_stream* fs = nullptr;
+            kg_report* rep = nullptr;
+            if (kg_fasta_stream_open(query, (size_t)batch_mb << 20, &fs) != KG_OK) break;
+            if (kg_report_open(outp, &rep) != KG_OK) {
+                kg_fasta_stream_close(fs);
+                break;
+            }
+            auto t1 = now();
+            kg_fasta* nextb = nullptr;
+            int nrc = kg_fasta_stream_next(fs, &nextb);
+            std::string nerr = nrc != KG_OK ? kg_last_error() : "";
+            bool ok = nrc == KG_OK;
+            size_t nbatches = 0;
+            while (ok && nextb) {
+                fa = nextb;
+                nextb = nullptr;
+                std::thread reader([&] {
+                    nrc = kg_fasta_stream_next(fs, &nextb);
+                    if (nrc != KG_OK) nerr = kg_last_error(); // thread-local message: carried over by hand
+                });
+                ok = kg_run(ctx, table, aa ? KG_MODE_AA : KG_MODE_DNA, kg_fasta_bytes(fa), kg_fasta_offsets(fa), kg_fasta_count(fa), &prm, &res) == KG_OK &&
+                     kg_report_add(rep, aa ? KG_MODE_AA : KG_MODE_DNA, rflags, fa, fn, table, res) == KG_OK;
+                reader.join();
+                kg_result_free(res);
+                res = nullptr;
+                kg_fasta_free(fa);
+                fa = nullptr;
+                nbatches++;
+                if (ok && nrc != KG_OK) {
+                    kg_set_error("%s", nerr.c_str());
+                    ok = false;
+                }
+            }
+            if (!ok && nrc != KG_OK && nbatches == 0) kg_set_error("%s", nerr.c_str());
+            kg_fasta_free(nextb);
+            kg_fasta_stream_close(fs);
+            const bool closed = kg_report_close(rep) == KG_OK;
+            if (!ok || !closed) break;
+            info("Streaming time (" + std::to_string(nbatches) + " batches): " + std::to_string(ms(t1, now())) + " ms.");
+            rc = 0;
+            break;
+        }
         auto t1 = now();
         if (kg_fasta_read(query, &fa) != KG_OK) break; // KGJ:778
         info("Preparation time: " + std::to_string(ms(t1, now())) + " ms.");
@@ -618,7 +848,7 @@ extern "C" int kg_main(int argc, char** argv) {
         if (kg_run(ctx, table, aa ? KG_MODE_AA : KG_MODE_DNA, kg_fasta_bytes(fa), kg_fasta_offsets(fa), kg_fasta_count(fa), &prm, &res) != KG_OK) break;
         info("Lookup time: " + std::to_string(ms(t2, now())) + " ms.");
         auto t3 = now();
-        if (kg_report_write(outp, aa ? KG_MODE_AA : KG_MODE_DNA, debug, fa, fn, table, res) != KG_OK) break;
+        if (kg_report_write(outp, aa ? KG_MODE_AA : KG_MODE_DNA, rflags, fa, fn, table, res) != KG_OK) break;
         info("Grouping time: " + std::to_string(ms(t3, now())) + " ms.");
         rc = 0;
     } while (0);

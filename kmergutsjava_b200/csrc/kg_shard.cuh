@@ -649,19 +649,24 @@ int shard_exchange_keys(kg_comm* c, ShardChunk& k, int ci, kg_batch* b, cudaStre
     if (c->nccl) {
         NcclApi& nc = nccl_api();
         NC(nc.GroupStart());
-        for (int p = 0; p < R; p++) {
-            if (p == c->rank) continue;
-            if (k.send_n[p]) {
-                NC(nc.Send(sl + p * k.cap, k.send_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Send(sh + p * k.cap, k.send_n[p], ncclUint8, p, c->nccl, st));
+        const int grc = [&]() -> int { // a failure inside the group must still close it
+            for (int p = 0; p < R; p++) {
+                if (p == c->rank) continue;
+                if (k.send_n[p]) {
+                    NC(nc.Send(sl + p * k.cap, k.send_n[p], ncclUint32, p, c->nccl, st));
+                    NC(nc.Send(sh + p * k.cap, k.send_n[p], ncclUint8, p, c->nccl, st));
+                }
+                if (k.recv_n[p]) {
+                    NC(nc.Recv(rl + k.recv_off[p], k.recv_n[p], ncclUint32, p, c->nccl, st));
+                    NC(nc.Recv(rh + k.recv_off[p], k.recv_n[p], ncclUint8, p, c->nccl, st));
+                }
+                c->stats.bytes_sent += k.send_n[p] * 5;
             }
-            if (k.recv_n[p]) {
-                NC(nc.Recv(rl + k.recv_off[p], k.recv_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Recv(rh + k.recv_off[p], k.recv_n[p], ncclUint8, p, c->nccl, st));
-            }
-            c->stats.bytes_sent += k.send_n[p] * 5;
-        }
-        NC(nc.GroupEnd());
+            return KG_OK;
+        }();
+        const ncclResult_t ge = nc.GroupEnd();
+        if (grc != KG_OK) return grc;
+        NC(ge);
         if (k.send_n[c->rank]) {
             CU(cudaMemcpyAsync(rl + k.recv_off[c->rank], sl + c->rank * k.cap, k.send_n[c->rank] * 4, cudaMemcpyDeviceToDevice, st));
             CU(cudaMemcpyAsync(rh + k.recv_off[c->rank], sh + c->rank * k.cap, k.send_n[c->rank], cudaMemcpyDeviceToDevice, st));
@@ -751,19 +756,24 @@ int shard_exchange_replies(kg_comm* c, ShardChunk& k, int ci, cudaStream_t st) {
     if (c->nccl) {
         NcclApi& nc = nccl_api();
         NC(nc.GroupStart());
-        for (int p = 0; p < R; p++) {
-            if (p == c->rank) continue;
-            if (k.reply_n[p]) {
-                NC(nc.Send(k.reply_idx.as<uint32_t>() + k.recv_off[p], k.reply_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Send(k.reply_payload.as<int4>() + k.recv_off[p], k.reply_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
-                c->stats.bytes_sent += k.reply_n[p] * (4 + sizeof(int4));
+        const int grc = [&]() -> int {
+            for (int p = 0; p < R; p++) {
+                if (p == c->rank) continue;
+                if (k.reply_n[p]) {
+                    NC(nc.Send(k.reply_idx.as<uint32_t>() + k.recv_off[p], k.reply_n[p], ncclUint32, p, c->nccl, st));
+                    NC(nc.Send(k.reply_payload.as<int4>() + k.recv_off[p], k.reply_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
+                    c->stats.bytes_sent += k.reply_n[p] * (4 + sizeof(int4));
+                }
+                if (k.rr_n[p]) {
+                    NC(nc.Recv(ri + p * k.cap, k.rr_n[p], ncclUint32, p, c->nccl, st));
+                    NC(nc.Recv(rp + p * k.cap, k.rr_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
+                }
             }
-            if (k.rr_n[p]) {
-                NC(nc.Recv(ri + p * k.cap, k.rr_n[p], ncclUint32, p, c->nccl, st));
-                NC(nc.Recv(rp + p * k.cap, k.rr_n[p] * sizeof(int4), ncclUint8, p, c->nccl, st));
-            }
-        }
-        NC(nc.GroupEnd());
+            return KG_OK;
+        }();
+        const ncclResult_t ge = nc.GroupEnd();
+        if (grc != KG_OK) return grc;
+        NC(ge);
         const int me = c->rank;
         if (k.reply_n[me]) {
             CU(cudaMemcpyAsync(ri + me * k.cap, k.reply_idx.as<uint32_t>() + k.recv_off[me], k.reply_n[me] * 4, cudaMemcpyDeviceToDevice, st));

@@ -145,6 +145,54 @@ def test_c0_cli_table_cache(kg, oracle, c0, tmp_path):
             os.remove(d / "kmer.table.mem_map")  # only the cache can serve the second run
 
 
+@pytest.mark.parametrize("mode", ["aa", "dna"])
+def test_c0_cli_streaming_and_dna_ranges(kg, oracle, c0, tmp_path, mode):
+    """-B (extension): the query is read, run and reported in batches of whole records; with unique ids the report is the
+    one-shot report (and the oracle's).  -c (extension): a DNA-RANGE line after every CALL of a 6-frame run."""
+    base = ["-a", "-D", c0, "-q", FAA] if mode == "aa" else ["-D", c0, "-q", FNA]   # aa: ~4 batches of 1 MB; dna: one contig
+    o_out = str(tmp_path / "o.txt")
+    oracle.run_cli(base + ["-o", o_out])
+    want = _strip(open(o_out).read(), False)
+    outs = {}
+    for name, extra in (("oneshot", []), ("stream", ["-B", "1"]), ("stream_c", ["-B", "1", "-c"])):
+        g_out = str(tmp_path / f"{name}.txt")
+        r = subprocess.run([kg.CLI_PATH] + base + extra + ["-o", g_out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[name] = _strip(open(g_out).read(), False)
+        if name != "oneshot":
+            assert "batches" in r.stdout
+    assert outs["oneshot"] == want and outs["stream"] == want
+    plain = [l for l in outs["stream_c"] if not l.startswith("DNA-RANGE")]
+    assert plain == want
+    ranges = [l for l in outs["stream_c"] if l.startswith("DNA-RANGE")]
+    if mode == "aa":
+        assert not ranges
+    else:
+        ncalls = sum(l.startswith("CALL") for l in want)
+        assert len(ranges) == ncalls > 100
+        for i, l in enumerate(outs["stream_c"]):
+            if l.startswith("DNA-RANGE"):
+                call = outs["stream_c"][i - 1].split("\t")
+                _, b, e, sd = l.split("\t")
+                assert call[0] == "CALL" and (int(e) - int(b) + 1) == 3 * (int(call[2]) - int(call[1]) + 1) and sd in "+-"
+
+
+def test_report_rejects_function_index_outside_the_index(kg, oracle, c0, tmp_path):
+    """functionArray.get(currentFI) throws in the reference (KGJ:403); a function.index that is too short for the
+    table must not produce CALL lines with an empty name."""
+    import shutil
+    d = tmp_path / "KmerData"
+    shutil.copytree(c0, d)
+    lines = open(d / "function.index").read().splitlines()
+    with open(d / "function.index", "w") as f:
+        f.write("\n".join(lines[:5]) + "\n")
+    ids, descr, seqs = synth.read_fasta_simple(FAA)
+    q = str(tmp_path / "q.faa")
+    synth.write_fasta(q, ids[:300], seqs[:300])
+    r = subprocess.run([kg.CLI_PATH, "-a", "-D", str(d), "-q", q, "-o", str(tmp_path / "g.txt")], capture_output=True, text=True)
+    assert r.returncode != 0 and "function index" in r.stderr and "KGJ:403" in r.stderr
+
+
 def test_c0_cli_stale_table_cache(kg, oracle, c0, tmp_path):
     """-C with a cache that was built from ANOTHER kmer.table.mem_map than the one in -D: the cache records the
     source's size and mtime, the command line notices the mismatch, rebuilds from -D and reports what -D says."""

@@ -183,3 +183,82 @@ def test_pack_aa_layout_and_codes():
         got = [(bits >> (5 * k)) & 31 for k in range(8 * int(goff[i + 1] - goff[i]))]
         assert got[:len(s)] == [code.get(c, 20) for c in s]
         assert got[len(s):] == [31] * (len(got) - len(s)) and len(got) > len(s)
+
+
+def test_fasta_stream_equals_whole_file(tmp_path, monkeypatch):
+    """kg_fasta_stream_*: the batches, concatenated, are exactly what kg_fasta_read gives for the whole file -- for any batch
+    size, line ending, blank lines, records longer than a batch, plain and .gz."""
+    import gzip
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(400):
+        n = int(rng.integers(1, 900)) if i % 37 else 20000
+        seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYXacgt "), n))
+        w = int(rng.integers(20, 90))
+        lines = [seq[j:j + w] for j in range(0, n, w)]
+        if i % 11 == 0:
+            lines.insert(1, "")            # a blank line inside a record is kept out of the sequence but ends nothing
+        recs.append((f">seq{i} description {i}", lines))
+    for eol in ("\n", "\r\n", "\r"):
+        text = "".join(cap + eol + eol.join(lines) + eol for cap, lines in recs)
+        plain = tmp_path / "q.fa"
+        plain.write_bytes(text.encode())
+        gz = tmp_path / "q.fa.gz"
+        with gzip.open(gz, "wb") as f:
+            f.write(text.encode())
+        whole = kg.Fasta(str(plain))
+        for path in (plain, gz):
+            for batch in (1, 700, 5000, 64 << 10, 1 << 30):
+                ids, chunks, lens, nb = [], [], [], 0
+                for b in kg.fasta_batches(str(path), batch):
+                    ids += b.ids
+                    chunks.append(b.bytes)
+                    lens += list(np.diff(b.offsets.astype(np.int64)))
+                    assert b.n > 0
+                    nb += 1
+                    b.free()
+                assert ids == whole.ids, (eol, batch)
+                assert lens == list(np.diff(whole.offsets.astype(np.int64)))
+                assert np.array_equal(np.concatenate(chunks), whole.bytes)
+                if batch == 1:
+                    assert nb == len(recs)       # every record alone
+                if batch == 1 << 30:
+                    assert nb == 1
+        whole.free()
+    # a reader error (caption without a sequence) surfaces from the batch that holds it
+    bad = tmp_path / "bad.fa"
+    bad.write_text(">a\nACGT\n>b\n>c\nAC\n")
+    with pytest.raises(kg.KgError) as e:
+        for b in kg.fasta_batches(str(bad), 1):
+            b.free()
+    assert "No sequence for caption: b" in str(e.value)
+
+
+def test_call_dna_range(oracle):
+    """kg_call_dna_range: the nucleotides it names, read on the strand it names, translate to the residues of the call."""
+    rng = np.random.default_rng(9)
+    L = 3001
+    contig = "".join(rng.choice(list("ACGT"), L))
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    rc = "".join(comp[c] for c in reversed(contig))
+    code = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF"   # KGJ:88-93
+    idx = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+    def translate(s, off):
+        return "".join(code[idx[s[i]] * 16 + idx[s[i + 1]] * 4 + idx[s[i + 2]]] for i in range(off, len(s) - 2, 3))
+
+    for sf in range(6):
+        strand_seq = contig if sf < 3 else rc
+        prot = translate(strand_seq, sf % 3)
+        for _ in range(50):
+            a = int(rng.integers(0, len(prot) - 8))
+            b = int(rng.integers(a + 7, len(prot)))
+            call = {"seq": 0, "sf": sf, "start": a, "end": b, "count": 5, "fI": 0, "weighted": 1.0, "hits_before": 0}
+            begin, end, sd = kg.call_dna_range(call, L)
+            assert sd == ("+" if sf < 3 else "-") and 0 <= begin <= end < L and (end - begin + 1) == 3 * (b - a + 1)
+            piece = contig[begin:end + 1]
+            if sd == "-":
+                piece = "".join(comp[c] for c in reversed(piece))
+            assert translate(piece, 0) == prot[a:b + 1]
+    with pytest.raises(kg.KgError):
+        kg.call_dna_range({"seq": 0, "sf": 0, "start": 0, "end": L, "count": 5, "fI": 0, "weighted": 1.0, "hits_before": 0}, L)
