@@ -16,10 +16,17 @@
  * Results are bit-identical to kg_batch_run against the unsharded table: a lookup returns the payload stored under the
  * key wherever it lives, and everything after the lookup is the same code.
  *
+ * Transports.  "direct" (default): every rank's exchange buffer is mapped into its peers (CUDA IPC between processes, peer
+ * access inside one process); k_route stores every k-mer straight into its OWNER's buffer and k_answer every hit straight into
+ * the ASKER's, so the NVLink transfers happen inside the kernels that produce the data; counts and arrival flags travel
+ * in-band and NCCL only bootstraps (capacity agreement, IPC handles).  KG_SHARD_TRANSPORT=nccl (one process per GPU) or =copy
+ * (local groups) selects the staged transport: bins that are moved afterwards by grouped ncclSend/ncclRecv or peer copies.
+ * Every rank of a communicator must use the same setting.
+ *
  * One process per GPU: kg_comm_init is collective (rank 0 makes an id with kg_comm_unique_id, the host application
  * hands it to every rank over whatever channel it has -- MPI, a file, a socket -- like ncclUniqueId).
- * Environment: KG_SHARD_CHUNKS (1-4, default 4; must be the same on every rank) cuts a step into pieces whose exchanges
- * overlap the kernels of the other pieces.  While a sharded step runs, the device's persisting-L2 set-aside is switched on
+ * Environment: KG_SHARD_CHUNKS (NCCL transport only; 1-4, default 4; must be the same on every rank) cuts a step into pieces
+ * whose exchanges overlap the kernels of the other pieces.  While a sharded step runs, the device's persisting-L2 set-aside is switched on
  * for the answer phase only and restored when the call returns (it is a device-wide limit: another context probing a
  * replicated table on the same GPU at that moment runs without it for a few milliseconds).
  * NCCL (libnccl.so.2) is loaded on first use and only when nranks > 1.  kg_comm_init_local puts all ranks into ONE

@@ -198,7 +198,9 @@ static void pin_filter(kg_context* ctx, const kg_table* t, bool force) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
     const size_t fbytes = (size_t)t->filter_words * 8;
-    const size_t carve = std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize);
+    size_t carve = std::min<size_t>(fbytes, (size_t)prop.persistingL2CacheMaxSize);
+    if (const char* e = getenv("KG_L2_CARVE_MB")) // experiments: a set-aside larger than the filter (slack for uneven L2 slices)
+        carve = std::min<size_t>((size_t)atoll(e) << 20, (size_t)prop.persistingL2CacheMaxSize);
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
     t->l2_carve = carve;
     cudaStreamAttrValue av = {};
@@ -206,6 +208,7 @@ static void pin_filter(kg_context* ctx, const kg_table* t, bool force) {
     av.accessPolicyWindow.num_bytes = std::min<size_t>(fbytes, (size_t)prop.accessPolicyMaxWindowSize);
     // a filter larger than the carve-out: that fraction of its lines persists, the rest competes normally
     av.accessPolicyWindow.hitRatio = fbytes > carve ? (float)((double)carve / (double)fbytes) : 1.0f;
+    if (const char* e = getenv("KG_L2_HIT_RATIO")) av.accessPolicyWindow.hitRatio = (float)atof(e);
     av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     av.accessPolicyWindow.missProp = fbytes > carve ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
