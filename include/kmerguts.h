@@ -188,6 +188,14 @@ void kg_batch_free(kg_batch* batch);
 /* Device pipeline only; results stay on the device until kg_result_fetch. */
 int kg_batch_run(kg_context* ctx, const kg_table* table, kg_batch* batch, const kg_params* params,
                  kg_result** result);
+/* n resident batches (the same batch may appear more than once), two in flight: the run FSM of batch i overlaps the probe of
+ * batch i+1.  results[i] is what kg_batch_run(batches[i]) would have returned. */
+int kg_batch_run_many(kg_context* ctx, const kg_table* table, kg_batch* const* batches, size_t n, const kg_params* params,
+                      kg_result** results);
+/* The same pipeline with the caller in the loop: at most two batches in flight per context; kg_batch_collect returns the
+ * results in submission order.  submit(0); for i: submit(i+1); collect -> result i; use it; kg_result_free. */
+int kg_batch_submit(kg_context* ctx, const kg_table* table, kg_batch* batch, const kg_params* params);
+int kg_batch_collect(kg_context* ctx, kg_result** result);
 int kg_result_fetch(kg_result* result); /* D2H of calls, OTU counts and (if requested) hits; idempotent */
 
 int kg_result_stats(const kg_result* result, kg_run_stats* stats);

@@ -30,7 +30,7 @@ EXPORTS = [
     "kg_init", "kg_shutdown", "kg_last_error", "kg_version",
     "kg_table_load", "kg_table_load_file", "kg_table_from_image", "kg_table_from_device_entries", "kg_table_get_info",
     "kg_table_save", "kg_table_load_cached", "kg_table_load_cached_checked", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_run_packed_aa", "kg_pack_aa", "kg_pack_aa_groups", "kg_result_otus_compact", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
-    "kg_batch_run", "kg_result_fetch", "kg_result_stats", "kg_result_calls", "kg_result_otus", "kg_result_hits",
+    "kg_batch_run", "kg_batch_run_many", "kg_batch_submit", "kg_batch_collect", "kg_result_fetch", "kg_result_stats", "kg_result_calls", "kg_result_otus", "kg_result_hits",
     "kg_result_free",
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
     "kg_functions_load", "kg_functions_read", "kg_functions_count", "kg_functions_name", "kg_functions_free",
@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
         "kg_batch_upload": (i32, [vp, i32, vp, vp, sz, pp]),
         "kg_batch_from_device": (i32, [vp, i32, vp, vp, sz, u64, pp]), "kg_batch_free": (None, [vp]),
         "kg_batch_run": (i32, [vp, vp, vp, C.POINTER(Params), pp]), "kg_result_fetch": (i32, [vp]),
+        "kg_batch_run_many": (i32, [vp, vp, pp, sz, C.POINTER(Params), pp]),
+        "kg_batch_submit": (i32, [vp, vp, vp, C.POINTER(Params)]), "kg_batch_collect": (i32, [vp, pp]),
         "kg_result_stats": (i32, [vp, C.POINTER(RunStats)]),
         "kg_result_calls": (i32, [vp, pp, C.POINTER(sz)]), "kg_result_otus": (i32, [vp, pp, C.POINTER(sz)]),
         "kg_result_hits": (i32, [vp, pp, C.POINTER(sz)]), "kg_result_free": (None, [vp]),
@@ -273,6 +275,33 @@ class Context:
         h = C.c_void_p()
         _check(lib().kg_batch_from_device(self._h, mode, d_seq, d_off, n, total, C.byref(h)))
         return Batch(self, h)
+
+    def run_batch_many(self, table: "Table", batches: Sequence["Batch"], params: Params) -> list["Result"]:
+        """kg_batch_run_many: resident batches, two in flight (the FSM of batch i overlaps the probe of batch i+1)."""
+        n = len(batches)
+        arr = (C.c_void_p * n)(*[b._h for b in batches])
+        out = (C.c_void_p * n)()
+        _check(lib().kg_batch_run_many(self._h, table._h, arr, n, C.byref(params), out))
+        return [Result(C.c_void_p(out[i])) for i in range(n)]
+
+    def run_batches(self, table: "Table", batches, params: Params):
+        """kg_batch_submit / kg_batch_collect: yields the results in order with two batches in flight; the caller frees each
+        result before asking for the next, so the buffers recycle."""
+        it = iter(batches)
+        pending = 0
+        for b in it:
+            _check(lib().kg_batch_submit(self._h, table._h, b._h, C.byref(params)))
+            pending += 1
+            if pending == 2:
+                h = C.c_void_p()
+                _check(lib().kg_batch_collect(self._h, C.byref(h)))
+                pending -= 1
+                yield Result(h)
+        while pending:
+            h = C.c_void_p()
+            _check(lib().kg_batch_collect(self._h, C.byref(h)))
+            pending -= 1
+            yield Result(h)
 
     def run_batch(self, table: "Table", batch: "Batch", params: Params) -> "Result":
         h = C.c_void_p()

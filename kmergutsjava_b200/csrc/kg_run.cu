@@ -1668,6 +1668,13 @@ struct RunScratch { // grow-only device scratch kept per context (so repeated ru
     uint64_t hit_cap_seen = 0;   // hits of the largest run so far (+ slack): sizes the next run's buffers
     uint64_t calls_seen = 0;     // calls of the largest kg_run so far: sizes the pinned result buffer
     uint64_t otu_entries_seen = 0; // likewise, (count, oI) pairs
+    struct InFlight {              // kg_batch_submit / kg_batch_collect
+        kg_result* r = nullptr;
+        kg_batch* b = nullptr;
+        const kg_table* t = nullptr;
+        kg_params p = {};
+    } inflight[2];
+    int inflight_head = 0, inflight_n = 0;
 };
 RunScratch& scratch_of(kg_context* ctx) {
     if (!ctx->scratch) {
@@ -2352,6 +2359,90 @@ extern "C" int kg_batch_run(kg_context* ctx, const kg_table* table, kg_batch* ba
         return rc;
     }
     *out = r;
+    return KG_OK;
+}
+
+// Submit / collect: the same two-in-flight pipeline with the caller in the loop -- it consumes (and frees) result i while
+// batch i+1 runs, so the result buffers cycle through the context's pool instead of piling up.
+extern "C" int kg_batch_submit(kg_context* ctx, const kg_table* table, kg_batch* batch, const kg_params* params) {
+    if (!ctx || !table || !batch) KG_FAIL(KG_EINVAL, "kg_batch_submit: null argument");
+    if (table->shard_count > 1) KG_FAIL(KG_EINVAL, "kg_batch_submit: the table is shard %d of %d; use kg_batch_run_sharded", table->shard_rank, table->shard_count);
+    KG_TRY(check_params(params));
+    CU(cudaSetDevice(ctx->device));
+    RunScratch& sc = scratch_of(ctx);
+    if (sc.inflight_n >= 2) KG_FAIL(KG_EINVAL, "kg_batch_submit: two batches are in flight already; collect one first");
+    const int slot = (sc.inflight_head + sc.inflight_n) & 1;
+    RunScratch::InFlight& f = sc.inflight[slot];
+    f.r = new kg_result();
+    f.r->ctx = ctx;
+    f.b = batch;
+    f.t = table;
+    f.p = *params;
+    const int rc = pipe_enqueue(ctx, sc.slot[slot], table, batch, params, f.r, sc.hit_cap_seen, 0);
+    if (rc != KG_OK) {
+        cudaDeviceSynchronize();
+        kg_result_free(f.r);
+        f.r = nullptr;
+        return rc;
+    }
+    sc.inflight_n++;
+    return KG_OK;
+}
+extern "C" int kg_batch_collect(kg_context* ctx, kg_result** out) {
+    if (!ctx || !out) KG_FAIL(KG_EINVAL, "kg_batch_collect: null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    RunScratch& sc = scratch_of(ctx);
+    if (!sc.inflight_n) KG_FAIL(KG_EINVAL, "kg_batch_collect: nothing in flight");
+    const int slot = sc.inflight_head & 1;
+    RunScratch::InFlight& f = sc.inflight[slot];
+    const int rc = pipe_finish(ctx, sc.slot[slot], f.t, f.b, &f.p, f.r, 0);
+    sc.inflight_head ^= 1;
+    sc.inflight_n--;
+    if (rc != KG_OK) {
+        cudaDeviceSynchronize();
+        kg_result_free(f.r);
+        f.r = nullptr;
+        return rc;
+    }
+    *out = f.r;
+    f.r = nullptr;
+    return KG_OK;
+}
+
+// Several resident batches, two in flight: the pipeline of batch i+1 is enqueued (second pipeline slot) before the host waits
+// for batch i, so the run FSM and the call compaction of batch i -- on their own stream, with a tail of a few long sequences
+// on a mostly idle GPU -- overlap the probe of batch i+1.  Results are those of n separate kg_batch_run calls.
+extern "C" int kg_batch_run_many(kg_context* ctx, const kg_table* table, kg_batch* const* batches, size_t n, const kg_params* params,
+                                 kg_result** results) {
+    if (!ctx || !table || (n && (!batches || !results))) KG_FAIL(KG_EINVAL, "kg_batch_run_many: null argument");
+    if (table->shard_count > 1) KG_FAIL(KG_EINVAL, "kg_batch_run_many: the table is shard %d of %d; use kg_batch_run_sharded", table->shard_rank, table->shard_count);
+    KG_TRY(check_params(params));
+    CU(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n; i++) {
+        if (!batches[i]) KG_FAIL(KG_EINVAL, "kg_batch_run_many: batch %zu is null", i);
+        results[i] = nullptr;
+    }
+    RunScratch& sc = scratch_of(ctx);
+    int rc = KG_OK;
+    auto enqueue = [&](size_t i) -> int {
+        results[i] = new kg_result();
+        results[i]->ctx = ctx;
+        return pipe_enqueue(ctx, sc.slot[i & 1], table, batches[i], params, results[i], sc.hit_cap_seen, 0);
+    };
+    if (n) rc = enqueue(0);
+    for (size_t i = 0; i < n && rc == KG_OK; i++) {
+        if (i + 1 < n) rc = enqueue(i + 1);
+        if (rc == KG_OK) rc = pipe_finish(ctx, sc.slot[i & 1], table, batches[i], params, results[i], 0);
+    }
+    if (rc != KG_OK) {
+        cudaDeviceSynchronize(); // nothing may still be writing into a result that is about to be freed
+        for (size_t i = 0; i < n; i++) {
+            kg_result_free(results[i]);
+            results[i] = nullptr;
+        }
+        return rc;
+    }
     return KG_OK;
 }
 

@@ -3,6 +3,8 @@ hit positions, function/OTU ids, calls and (because the fp32 sum keeps the refer
 import json
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -488,3 +490,39 @@ def test_two_contexts_share_a_table(kg, ctx, oracle, universe):
             out[k][rep].free()
     ctx2.close()
     t.free()
+
+
+def test_run_batch_many_equals_single_runs(kg, ctx, oracle):
+    """kg_batch_run_many (two batches in flight): every result equals the one kg_batch_run gives for that batch."""
+    u = synth.Universe(n_families=300, seed=0x4B470011)
+    keys, otu, avg, fi, wt = u.signatures()
+    table = ctx.table_from_image(synth.build_table_image(keys, otu, avg, fi, wt))
+    params = kg.default_params(emit_hits=1)
+    batches, singles = [], []
+    for k, (mode, n) in enumerate([(kg.MODE_AA, 700), (kg.MODE_AA, 5), (kg.MODE_DNA, 3), (kg.MODE_AA, 1200), (kg.MODE_AA, 0)]):
+        seqs = u.proteins(n, seed=50 + k) if mode == kg.MODE_AA else [synth.genome(u, 30000, seed=60 + k, index=i) for i in range(n)]
+        sb, off = oracle.concat(seqs)
+        batches.append(ctx.upload(mode, sb, off))
+    order = [0, 1, 2, 3, 4, 0, 3]          # a batch may appear more than once
+    for i in order:
+        singles.append(ctx.run_batch(table, batches[i], params))
+    many = ctx.run_batch_many(table, [batches[i] for i in order], params)
+    assert len(many) == len(order)
+    piped = list(ctx.run_batches(table, [batches[i] for i in order], params))   # submit / collect, two in flight
+    for a, b in zip(piped, singles):
+        for name in ("hits", "calls", "otus"):
+            assert getattr(a, name).tobytes() == getattr(b, name).tobytes(), name
+    for r in piped:
+        r.free()
+    with pytest.raises(kg.KgError):
+        kg._check(kg.lib().kg_batch_collect(ctx._h, C.byref(C.c_void_p())))   # nothing in flight
+    for a, b in zip(many, singles):
+        for name in ("hits", "calls", "otus"):
+            assert getattr(a, name).tobytes() == getattr(b, name).tobytes(), name
+        assert a.stats.num_kmers == b.stats.num_kmers
+    assert sum(len(r.calls) for r in many) > 50
+    for r in many + singles:
+        r.free()
+    for b in batches:
+        b.free()
+    table.free()
