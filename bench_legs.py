@@ -6,6 +6,7 @@ Every leg returns a dict (ms per step, lookups/s, stage times, a parity string).
 (oracle/ is test infrastructure: bench.py is one of the places allowed to run it, as the checker), except for the
 full-size property of configs[4] (hits of every rank against every shard with the naive kernel, summed over the ranks).
 """
+import ctypes as C
 import os
 import sys
 import time
@@ -188,8 +189,40 @@ def configs2(kg, ctx, table, u, plumb, genomes=50, length=5_000_000, steps=5, wa
                 ctx.run_ptr(table, kg.MODE_DNA, h_seq.data_ptr(), h_off.data_ptr(), mine, params).free()
         plumb.barrier()
         edt = plumb.reduce([time.perf_counter() - t0], "MAX")[0] / steps
-        out["e2e"] = {"ms_per_step": edt * 1e3, "mbp_per_s": genomes * length / edt / 1e6, "lookups_per_s": lookups / edt,
-                      "h2d_bytes_per_step_per_gpu": int(total + 8 * (mine + 1))}
+        raw = {"ms_per_step": edt * 1e3, "mbp_per_s": genomes * length / edt / 1e6, "lookups_per_s": lookups / edt,
+               "h2d_bytes_per_step_per_gpu": int(total + 8 * (mine + 1)), "call": "kg_run: one byte per nucleotide"}
+        # the library's ingest form: 2 bits per nucleotide + the positions of the non-ACGTU characters (kg_pack_dna; the packing
+        # is host work outside the call, like FASTA parsing)
+        pk_bytes = 0
+        if mine:
+            sb_np = np.frombuffer((C.c_uint8 * total).from_address(h_seq.data_ptr()), dtype=np.uint8)
+            off_np = np.frombuffer((C.c_uint64 * (mine + 1)).from_address(h_off.data_ptr()), dtype=np.uint64)
+            pk, boff, exc = kg.pack_dna(sb_np, off_np, threads=min(os.cpu_count() or 1, 16))
+            h_pk = torch.empty(pk.nbytes, dtype=torch.uint8, pin_memory=True)
+            h_pk.numpy()[:] = pk
+            h_boff = torch.from_numpy(boff.view(np.int64)).pin_memory()
+            h_exc = torch.from_numpy(np.ascontiguousarray(exc if len(exc) else np.zeros(1, np.uint64)).view(np.int64)).pin_memory()
+            pk_bytes = int(boff[-1]) + 16 * (mine + 1) + 8 * len(exc)
+
+            def pk_call():
+                return ctx.run_packed_dna_ptr(table, h_pk.data_ptr(), h_off.data_ptr(), h_boff.data_ptr(), h_exc.data_ptr() if len(exc) else None,
+                                              len(exc), mine, params)
+            chk = pk_call()
+            if st is not None and (chk.stats.num_kmers, chk.stats.num_hits, chk.stats.num_calls) != (st.num_kmers, st.num_hits, st.num_calls):
+                raise SystemExit("configs2: kg_run_packed_dna disagrees with the device-resident run")
+            chk.free()
+            for _ in range(warmup):
+                pk_call().free()
+        plumb.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            if mine:
+                pk_call().free()
+        plumb.barrier()
+        pdt = plumb.reduce([time.perf_counter() - t0], "MAX")[0] / steps
+        out["e2e"] = {"ms_per_step": pdt * 1e3, "mbp_per_s": genomes * length / pdt / 1e6, "lookups_per_s": lookups / pdt,
+                      "h2d_bytes_per_step_per_gpu": pk_bytes, "call": "kg_run_packed_dna: 2-bit nucleotides + exception list in, calls + compact OTU counts out",
+                      "raw_bytes_call": raw}
     if parity_genomes and rank == 0 and otable is not None and mine:
         from oracle import kgo
         from tests.parity import assert_same

@@ -176,6 +176,17 @@ int kg_pack_aa(const uint8_t* seq_bytes, const uint64_t* offsets, size_t n, uint
 int kg_run_packed_aa(kg_context* ctx, const kg_table* table, const uint8_t* packed, const uint64_t* group_offsets, size_t n,
                      const kg_params* params, kg_result** result);
 
+/* The same for 6-frame input: prepareQuery / translate only ever look at dnaChar() of a nucleotide (KGJ:294-318, 320-343), so a
+ * contig travels as 2 bits per nucleotide (aA 0, cC 1, gG 2, tTuU 3; four per byte, low bits first, every contig starting on
+ * a byte: contig s occupies bytes [byte_offsets[s], byte_offsets[s+1]) = ceil(len / 4)) plus the sorted positions -- in the
+ * space of `offsets` -- of every other character (dnaChar 4).  kg_pack_dna with packed == NULL fills byte_offsets and
+ * *n_exceptions only; the second call wants *n_exceptions = the room in `exceptions`.  Results are identical to kg_run. */
+int kg_pack_dna(const uint8_t* seq_bytes, const uint64_t* offsets, size_t n, uint8_t* packed, uint64_t* byte_offsets,
+                uint64_t* exceptions, size_t* n_exceptions, int threads);
+int kg_run_packed_dna(kg_context* ctx, const kg_table* table, const uint8_t* packed, const uint64_t* offsets,
+                      const uint64_t* byte_offsets, const uint64_t* exceptions, size_t n_exceptions, size_t n,
+                      const kg_params* params, kg_result** result);
+
 /* Split form: keep the sequences resident in HBM and run the device pipeline on them (possibly many times). */
 int kg_batch_upload(kg_context* ctx, int mode, const uint8_t* seq_bytes, const uint64_t* offsets, size_t n,
                     kg_batch** batch);

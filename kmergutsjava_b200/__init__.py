@@ -29,7 +29,7 @@ HIT_DTYPE = np.dtype([("seq", "<u4"), ("sf", "<i4"), ("pos", "<i4"), ("oI", "<i4
 EXPORTS = [
     "kg_init", "kg_shutdown", "kg_last_error", "kg_version",
     "kg_table_load", "kg_table_load_file", "kg_table_from_image", "kg_table_from_device_entries", "kg_table_get_info",
-    "kg_table_save", "kg_table_load_cached", "kg_table_load_cached_checked", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_run_packed_aa", "kg_pack_aa", "kg_pack_aa_groups", "kg_result_otus_compact", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
+    "kg_table_save", "kg_table_load_cached", "kg_table_load_cached_checked", "kg_table_attach", "kg_table_free", "kg_params_default", "kg_run", "kg_run_packed_aa", "kg_pack_aa", "kg_pack_aa_groups", "kg_pack_dna", "kg_run_packed_dna", "kg_result_otus_compact", "kg_batch_upload", "kg_batch_from_device", "kg_batch_free",
     "kg_batch_run", "kg_batch_run_many", "kg_batch_submit", "kg_batch_collect", "kg_result_fetch", "kg_result_stats", "kg_result_calls", "kg_result_otus", "kg_result_hits",
     "kg_result_free",
     "kg_fasta_read", "kg_fasta_count", "kg_fasta_id", "kg_fasta_bytes", "kg_fasta_offsets", "kg_fasta_free",
@@ -102,6 +102,8 @@ def lib() -> C.CDLL:
         "kg_run": (i32, [vp, vp, i32, vp, vp, sz, C.POINTER(Params), pp]),
         "kg_run_packed_aa": (i32, [vp, vp, vp, vp, sz, C.POINTER(Params), pp]),
         "kg_pack_aa": (i32, [vp, vp, sz, vp, vp, i32]), "kg_pack_aa_groups": (u64, [u64]),
+        "kg_pack_dna": (i32, [vp, vp, sz, vp, vp, vp, C.POINTER(sz), i32]),
+        "kg_run_packed_dna": (i32, [vp, vp, vp, vp, vp, vp, sz, sz, C.POINTER(Params), pp]),
         "kg_result_otus_compact": (i32, [vp, pp, pp, C.POINTER(sz), C.POINTER(sz)]),
         "kg_batch_upload": (i32, [vp, i32, vp, vp, sz, pp]),
         "kg_batch_from_device": (i32, [vp, i32, vp, vp, sz, u64, pp]), "kg_batch_free": (None, [vp]),
@@ -154,6 +156,21 @@ def pack_aa(seq_bytes: np.ndarray, offsets: np.ndarray, threads: int = 1):
     packed = np.empty(5 * int(goff[-1]), dtype=np.uint8)
     _check(lib().kg_pack_aa(seq_bytes.ctypes.data, offsets.ctypes.data, n, packed.ctypes.data, goff.ctypes.data, threads))
     return packed, goff
+
+
+def pack_dna(seq_bytes: np.ndarray, offsets: np.ndarray, threads: int = 1):
+    """kg_pack_dna: (packed 2-bit nucleotides, byte offsets (n + 1), sorted positions of the non-ACGTU characters)."""
+    seq_bytes = np.ascontiguousarray(seq_bytes, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    boff = np.zeros(n + 1, dtype=np.uint64)
+    ne = C.c_size_t(0)
+    _check(lib().kg_pack_dna(seq_bytes.ctypes.data, offsets.ctypes.data, n, None, boff.ctypes.data, None, C.byref(ne), threads))
+    packed = np.zeros(int(boff[-1]) + 64, dtype=np.uint8)
+    exc = np.zeros(max(int(ne.value), 1), dtype=np.uint64)
+    _check(lib().kg_pack_dna(seq_bytes.ctypes.data, offsets.ctypes.data, n, packed.ctypes.data, boff.ctypes.data, exc.ctypes.data,
+                             C.byref(ne), threads))
+    return packed, boff, exc[:int(ne.value)]
 
 
 def default_params(**kw) -> Params:
@@ -258,6 +275,18 @@ class Context:
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         group_offsets = np.ascontiguousarray(group_offsets, dtype=np.uint64)
         return self.run_packed_aa_ptr(table, packed.ctypes.data, group_offsets.ctypes.data, len(group_offsets) - 1, params)
+
+    def run_packed_dna(self, table: "Table", packed: np.ndarray, offsets: np.ndarray, byte_offsets: np.ndarray, exceptions: np.ndarray,
+                       params: Params) -> "Result":
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        return self.run_packed_dna_ptr(table, packed.ctypes.data, offsets.ctypes.data, byte_offsets.ctypes.data,
+                                       exceptions.ctypes.data if len(exceptions) else None, len(exceptions), len(offsets) - 1, params,
+                                       _keep=(packed, offsets, byte_offsets, exceptions))
+
+    def run_packed_dna_ptr(self, table: "Table", packed_ptr, off_ptr, boff_ptr, exc_ptr, n_exc: int, n: int, params: Params, _keep=None) -> "Result":
+        h = C.c_void_p()
+        _check(lib().kg_run_packed_dna(self._h, table._h, packed_ptr, off_ptr, boff_ptr, exc_ptr, n_exc, n, C.byref(params), C.byref(h)))
+        return Result(h)
 
     def run_packed_aa_ptr(self, table: "Table", packed_ptr: int, goff_ptr: int, n: int, params: Params) -> "Result":
         h = C.c_void_p()

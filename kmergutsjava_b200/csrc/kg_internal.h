@@ -32,7 +32,8 @@ struct kg_batch {
     uint64_t* d_off = nullptr; // n+1
     bool owns_input = true;
     DevBuf seq_buf, off_buf;  // pooled storage behind d_seq / d_off when owns_input
-    DevBuf pk_buf;            // packed protein input (kg_run_packed_aa): the 5-bit form as uploaded, unpacked into seq_buf
+    DevBuf pk_buf;            // packed input (kg_run_packed_aa: 5-bit residues; kg_run_packed_dna: 2-bit nucleotides) as uploaded, unpacked into seq_buf
+    DevBuf aux_buf, exc_buf;  // kg_run_packed_dna: the slice's packed byte offsets, positions of the non-ACGT characters
     bool padded = false;      // ... in which every sequence is padded with zero bytes to a multiple of 8 positions
     // derived by prepare(): virtual sequences
     uint64_t nv = 0;          // n (aa) or 6n (dna)

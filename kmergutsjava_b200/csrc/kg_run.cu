@@ -100,6 +100,34 @@ __global__ void k_unpack_aa(const uint8_t* __restrict__ packed, uint64_t ngroups
     stream8[g] = make_uint2(w[0], w[1]);
 }
 // the padded layout of the packed form: the last residue of a protein is the last non-zero byte of its (multiple-of-8) span
+// ---------------------------------------------------------------------------------------------------------------
+// packed 6-frame input (kg_pack_dna / kg_run_packed_dna): 2 bits per nucleotide (dnaChar, KGJ:294-318: aA 0, cC 1, gG 2, tTuU 3),
+// four per byte, every contig starting on a byte; the rare other characters (dnaChar 4) travel as a sorted list of
+// positions.  Unpacked into the 1-byte-per-nucleotide stream the translation kernel reads: 'A' 'C' 'G' 'T', and 'N' at the
+// listed positions -- translate() only ever looks at dnaChar() of a nucleotide, so the results cannot differ.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_unpack_dna(const uint8_t* __restrict__ packed, uint64_t nbytes, const uint64_t* __restrict__ boff, uint64_t boff0,
+                             const uint64_t* __restrict__ off, uint64_t n, uint8_t* __restrict__ seq) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nbytes) return;
+    uint64_t lo = 0, hi = n; // contig c with boff[c] - boff0 <= q < boff[c + 1] - boff0 (empty contigs own no byte)
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (boff[mid] - boff0 <= q) lo = mid;
+        else hi = mid;
+    }
+    const uint64_t r = (q - (boff[lo] - boff0)) * 4, len = off[lo + 1] - off[lo];
+    const uint32_t b = packed[q];
+    uint8_t* dst = seq + off[lo] + r; // off is already relative to the slice
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (r + k < len) dst[k] = (uint8_t)((0x54474341u >> (8 * ((b >> (2 * k)) & 3u))) & 0xFFu); // "ACGT"
+}
+__global__ void k_mark_dna_exceptions(const uint64_t* __restrict__ exc, uint64_t n, uint64_t base, uint8_t* __restrict__ seq) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) seq[exc[i] - base] = 'N';
+}
+
 __global__ void k_patch_aa_padded(uint8_t* __restrict__ seq, const uint64_t* __restrict__ off, uint64_t n) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -1939,6 +1967,8 @@ extern "C" void kg_batch_free(kg_batch* b) {
     pool_give_dev(b->ctx, &b->vseq);
     pool_give_dev(b->ctx, &b->voff);
     pool_give_dev(b->ctx, &b->pk_buf);
+    pool_give_dev(b->ctx, &b->aux_buf);
+    pool_give_dev(b->ctx, &b->exc_buf);
     delete b;
 }
 
@@ -2474,8 +2504,13 @@ extern "C" int kg_result_fetch(kg_result* r) {
 // their sum.  Pinned caller buffers make the copies truly asynchronous; pageable ones still work.
 // `packed`: seq_bytes / offsets are the 5-bit form of kg_pack_aa (offsets in groups of 8 residues = 5 bytes); the slice is
 // unpacked on the device into the same residue stream (every sequence padded to a multiple of 8 positions).
+struct DnaPacked { // kg_run_packed_dna: seq_bytes is the 2-bit form
+    const uint64_t* byte_offsets; // n + 1
+    const uint64_t* exceptions;   // sorted nucleotide positions (in the caller's offset space) whose dnaChar is 4
+    size_t n_exceptions;
+};
 static int run_host_impl(kg_context* ctx, const kg_table* table, int mode, bool packed, const uint8_t* seq_bytes, const uint64_t* offsets,
-                         size_t n, const kg_params* params, kg_result** out) {
+                         size_t n, const kg_params* params, kg_result** out, const DnaPacked* dp = nullptr) {
     if (!ctx || !table || !out || !offsets || (mode != KG_MODE_AA && mode != KG_MODE_DNA)) KG_FAIL(KG_EINVAL, "kg_run: bad argument");
     if (packed && mode != KG_MODE_AA) KG_FAIL(KG_EINVAL, "kg_run_packed_aa: protein mode only");
     const uint64_t unit_pos = packed ? 8 : 1; // stream positions per offset unit (a group of the packed form = 5 bytes = 8 positions)
@@ -2582,11 +2617,30 @@ static int run_host_impl(kg_context* ctx, const kg_table* table, int mode, bool 
                 CU(cudaMemcpyAsync(bt->pk_buf.p, seq_bytes + 5 * offsets[a], units * 5, cudaMemcpyHostToDevice, cs));
                 k_unpack_aa<<<blocks_for(units, 256), 256, 0, cs>>>(bt->pk_buf.as<uint8_t>(), units, reinterpret_cast<uint2*>(bt->d_seq));
             }
-        } else if (bytes) {
+        } else if (bytes && !dp) {
             CU(cudaMemcpyAsync(bt->d_seq, seq_bytes + offsets[a], bytes, cudaMemcpyHostToDevice, cs));
         }
         CU(cudaMemcpyAsync(bt->d_off, offsets + a, (cnt + 1) * 8, cudaMemcpyHostToDevice, cs));
         if (offsets[a] || packed) k_rebase<<<blocks_for(cnt + 1, 256), 256, 0, cs>>>(bt->d_off, cnt + 1, offsets[a], packed ? 8 : 1);
+        if (dp && bytes) { // 2-bit nucleotides + the positions of the other characters: a quarter of the bytes cross the host link
+            const uint64_t pb0 = dp->byte_offsets[a], pbytes = dp->byte_offsets[b] - pb0;
+            if (dp->byte_offsets[b] < pb0) KG_FAIL(KG_EINVAL, "kg_run_packed_dna: byte offsets must be non-decreasing");
+            KG_TRY(pool_take_dev(ctx, pbytes + 64, &bt->pk_buf));
+            KG_TRY(pool_take_dev(ctx, (cnt + 1) * 8, &bt->aux_buf));
+            CU(cudaMemcpyAsync(bt->pk_buf.p, seq_bytes + pb0, pbytes, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(bt->aux_buf.p, dp->byte_offsets + a, (cnt + 1) * 8, cudaMemcpyHostToDevice, cs));
+            if (pbytes)
+                k_unpack_dna<<<blocks_for(pbytes, 256), 256, 0, cs>>>(bt->pk_buf.as<uint8_t>(), pbytes, bt->aux_buf.as<uint64_t>(), pb0, bt->d_off, cnt,
+                                                                      bt->d_seq);
+            const uint64_t* e0 = std::lower_bound(dp->exceptions, dp->exceptions + dp->n_exceptions, offsets[a]);
+            const uint64_t* e1 = std::lower_bound(e0, dp->exceptions + dp->n_exceptions, offsets[b]);
+            if (e1 > e0) {
+                const uint64_t ne = (uint64_t)(e1 - e0);
+                KG_TRY(pool_take_dev(ctx, ne * 8, &bt->exc_buf));
+                CU(cudaMemcpyAsync(bt->exc_buf.p, e0, ne * 8, cudaMemcpyHostToDevice, cs));
+                k_mark_dna_exceptions<<<blocks_for(ne, 256), 256, 0, cs>>>(bt->exc_buf.as<uint64_t>(), ne, offsets[a], bt->d_seq);
+            }
+        }
         CU(cudaEventRecord(ctx->up_ev[s % UP], cs));
         return KG_OK;
     };
@@ -2768,6 +2822,95 @@ extern "C" int kg_pack_aa(const uint8_t* seq_bytes, const uint64_t* offsets, siz
     }
     for (auto& x : th) x.join();
     return KG_OK;
+}
+
+extern "C" int kg_pack_dna(const uint8_t* seq_bytes, const uint64_t* offsets, size_t n, uint8_t* packed, uint64_t* byte_offsets,
+                           uint64_t* exceptions, size_t* n_exceptions, int threads) {
+    if (!offsets || !byte_offsets || !n_exceptions || (offsets[n] && !seq_bytes)) KG_FAIL(KG_EINVAL, "kg_pack_dna: null argument");
+    uint8_t lut[256]; // dnaChar, KGJ:294-318
+    for (int i = 0; i < 256; i++) lut[i] = 4;
+    lut['a'] = lut['A'] = 0;
+    lut['c'] = lut['C'] = 1;
+    lut['g'] = lut['G'] = 2;
+    lut['t'] = lut['T'] = lut['u'] = lut['U'] = 3;
+    uint64_t pb = 0;
+    for (size_t s = 0; s < n; s++) {
+        if (offsets[s + 1] < offsets[s]) KG_FAIL(KG_EINVAL, "kg_pack_dna: offsets must be non-decreasing (at %zu)", s);
+        byte_offsets[s] = pb;
+        pb += (offsets[s + 1] - offsets[s] + 3) / 4;
+    }
+    byte_offsets[n] = pb;
+    // threads take equal ranges of nucleotides; a range may start inside a contig, but always on one of its packed bytes
+    const int T = std::max(1, std::min<int>(threads, 64));
+    const uint64_t total = offsets[n];
+    std::vector<std::vector<uint64_t>> exc((size_t)T);
+    std::vector<size_t> s_first((size_t)T + 1, n);
+    std::vector<uint64_t> p_first((size_t)T + 1, total);
+    for (int t = 0; t < T; t++) { // first nucleotide of thread t: rounded down to a packed-byte boundary of its contig
+        uint64_t x = total * (uint64_t)t / (uint64_t)T;
+        size_t sidx = (size_t)(std::upper_bound(offsets, offsets + n + 1, x) - offsets);
+        sidx = sidx ? sidx - 1 : 0;
+        if (sidx >= n) {
+            s_first[t] = n;
+            p_first[t] = total;
+            continue;
+        }
+        x = offsets[sidx] + (x - offsets[sidx]) / 4 * 4;
+        s_first[t] = sidx;
+        p_first[t] = x;
+    }
+    p_first[0] = 0;
+    s_first[0] = 0;
+    auto work = [&](int t) {
+        size_t sidx = s_first[t];
+        uint64_t x = p_first[t];
+        const uint64_t end = p_first[t + 1];
+        while (x < end && sidx < n) {
+            const uint64_t a = offsets[sidx], b = offsets[sidx + 1];
+            if (x >= b) {
+                sidx++;
+                continue;
+            }
+            const uint64_t stop = std::min(b, end);
+            for (uint64_t g0 = x; g0 < stop; g0 += 4) { // one packed byte (g0 - a is a multiple of 4)
+                uint32_t v = 0;
+                const uint64_t g1 = std::min(g0 + 4, b);
+                for (uint64_t g = g0; g < g1; g++) {
+                    const uint8_t c = lut[seq_bytes[g]];
+                    if (c == 4) exc[t].push_back(g);
+                    else v |= (uint32_t)c << (2 * (g - g0));
+                }
+                if (packed) packed[byte_offsets[sidx] + (g0 - a) / 4] = (uint8_t)v;
+            }
+            x = stop;
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    size_t ne = 0;
+    for (auto& v : exc) ne += v.size();
+    if (packed) {
+        if (ne > *n_exceptions) KG_FAIL(KG_EINVAL, "kg_pack_dna: room for %zu exceptions, %zu found (call with packed = NULL first)", *n_exceptions, ne);
+        if (ne && !exceptions) KG_FAIL(KG_EINVAL, "kg_pack_dna: null exceptions");
+        size_t k = 0;
+        for (auto& v : exc)
+            for (uint64_t g : v) exceptions[k++] = g; // ascending: the threads' ranges ascend
+    }
+    *n_exceptions = ne;
+    return KG_OK;
+}
+
+extern "C" int kg_run_packed_dna(kg_context* ctx, const kg_table* table, const uint8_t* packed, const uint64_t* offsets,
+                                 const uint64_t* byte_offsets, const uint64_t* exceptions, size_t n_exceptions, size_t n,
+                                 const kg_params* params, kg_result** out) {
+    if (!byte_offsets || (n_exceptions && !exceptions)) KG_FAIL(KG_EINVAL, "kg_run_packed_dna: null argument");
+    DnaPacked dp = {byte_offsets, exceptions, n_exceptions};
+    return run_host_impl(ctx, table, KG_MODE_DNA, false, packed, offsets, n, params, out, &dp);
 }
 
 extern "C" int kg_result_stats(const kg_result* r, kg_run_stats* s) {

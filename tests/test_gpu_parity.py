@@ -526,3 +526,38 @@ def test_run_batch_many_equals_single_runs(kg, ctx, oracle):
     for b in batches:
         b.free()
     table.free()
+
+
+def test_packed_dna_equals_raw(kg, ctx, oracle):
+    """kg_run_packed_dna (2-bit nucleotides + exception list over the host link) gives the records of kg_run on the characters:
+    genomes with N / IUPAC / lowercase / U, empty and tiny contigs, several slices."""
+    u = synth.Universe(n_families=300, seed=0x4B470012)
+    keys, otu, avg, fi, wt = u.signatures()
+    table = ctx.table_from_image(synth.build_table_image(keys, otu, avg, fi, wt))
+    rng = np.random.default_rng(12)
+    contigs = []
+    for i in range(7):
+        g = bytearray(synth.genome(u, 40000 + 1000 * i, seed=80 + i, index=i))
+        for p in rng.integers(0, len(g), 40):
+            g[int(p)] = int(rng.choice(np.frombuffer(b"NRYnacgtU", dtype=np.uint8)))
+        contigs.append(bytes(g))
+    contigs[3:3] = [b"", b"AC", b"ACGTACGTA", b"NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN"]
+    sb, off = oracle.concat(contigs)
+    packed, boff, exc = kg.pack_dna(sb, off, threads=4)
+    assert len(exc) > 100 and packed.nbytes < sb.nbytes / 3.9
+    for flags in (dict(), dict(min_hits=3, max_gap=50)):
+        params = kg.default_params(emit_hits=1, **flags)
+        raw = ctx.run(table, kg.MODE_DNA, sb, off, params)
+        os.environ["KG_SLICE_MB"] = "1"          # cut the call into several slices: the exception list is cut with them
+        try:
+            pk = ctx.run_packed_dna(table, packed, off, boff, exc, params)
+        finally:
+            del os.environ["KG_SLICE_MB"]
+        for name in ("hits", "calls", "otus"):
+            assert getattr(pk, name).tobytes() == getattr(raw, name).tobytes(), (name, flags)
+        assert len(raw.calls) > 20
+        ref = oracle.run(oracle.Table(data=synth.build_table_image(keys, otu, avg, fi, wt)), oracle.make_params(aa=False, **flags), sb, off, oracle.DIRECT_PROBE)
+        assert_same(pk, ref, what=f"packed dna {flags}")
+        raw.free()
+        pk.free()
+    table.free()

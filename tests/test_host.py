@@ -262,3 +262,34 @@ def test_call_dna_range(oracle):
             assert translate(piece, 0) == prot[a:b + 1]
     with pytest.raises(kg.KgError):
         kg.call_dna_range({"seq": 0, "sf": 0, "start": 0, "end": L, "count": 5, "fI": 0, "weighted": 1.0, "hits_before": 0}, L)
+
+
+def test_pack_dna_layout_and_codes():
+    """kg_pack_dna: 2 bits per nucleotide in dnaChar's codes (KGJ:294-318), four per byte, low bits first, every contig on a byte
+    boundary; every other character in the exception list; any number of threads gives the same bytes."""
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"ACGTacgtUuNnRYKMSWBDHV*- X", dtype=np.uint8)
+    seqs = [b"", b"A", b"ACG", b"ACGT", b"ACGTN", b"nnnn"] + [bytes(rng.choice(alphabet, int(rng.integers(0, 3000)), p=None)) for _ in range(60)]
+    seqs.append(bytes(rng.choice(alphabet[:4], 1 << 18)))
+    sb = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(x) for x in seqs])
+    code = np.full(256, 4, dtype=np.uint8)
+    for ch, c in zip(b"aAcCgGtTuU", [0, 0, 1, 1, 2, 2, 3, 3, 3, 3]):
+        code[ch] = c
+    want_exc = np.nonzero(code[sb] == 4)[0].astype(np.uint64)
+    ref = None
+    for threads in (1, 3, 16):
+        packed, boff, exc = kg.pack_dna(sb, off, threads=threads)
+        assert np.array_equal(exc, want_exc)
+        assert list(np.diff(boff.astype(np.int64))) == [(len(x) + 3) // 4 for x in seqs]
+        if ref is None:
+            ref = packed.copy()
+            for s, x in enumerate(seqs):
+                b = packed[int(boff[s]):int(boff[s + 1])]
+                dec = np.stack([(b >> (2 * k)) & 3 for k in range(4)], axis=1).reshape(-1)[:len(x)]
+                c = code[np.frombuffer(x, dtype=np.uint8)]
+                assert np.array_equal(dec[c != 4], c[c != 4])
+                assert not dec[c == 4].any()          # an exception's two bits are 0
+        else:
+            assert np.array_equal(packed, ref)
