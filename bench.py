@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--no-table-load", action="store_true", help="skip the reference-format table load measurement")
     ap.add_argument("--legs", default="2,3,4", help="which legs to run")
     ap.add_argument("--orfs", type=int, default=100_000_000, help="configs[3]: proteins in the whole job")
-    ap.add_argument("--c4-families", type=int, default=0, help="configs[4]: families (0 = 1.4 M per GPU, ~2e9 signatures on 8 GPUs)")
+    ap.add_argument("--c4-families", type=int, default=0, help="configs[4]: families (0 = 1.41 M per GPU, 2.0e9 signatures on 8 GPUs)")
     return ap.parse_args()
 
 

@@ -334,7 +334,7 @@ def configs3(kg, ctx, table, u, plumb, orfs=100_000_000, batch=1_000_000, otable
 # ---------------------------------------------------------------------------------------------------------------------
 # configs[4]: hash-sharded table across the ranks, k-mers exchanged over NVLink inside the library (kmerguts_shard.h)
 # ---------------------------------------------------------------------------------------------------------------------
-C4_FAMILIES_PER_GPU = 1_400_000   # x 8 GPUs at keep = 700/1024: a little over 2e9 distinct signatures (BASELINE configs[4])
+C4_FAMILIES_PER_GPU = 1_410_000   # x 8 GPUs at keep = 700/1024: 2.005e9 distinct signatures (BASELINE configs[4]: 2 B)
 C4_KEEP = 700
 
 

@@ -65,7 +65,7 @@ def local_main(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--families", type=int, default=0, help="0 = 1.4 M per GPU (about 250 M signatures per shard, 2e9 on 8 GPUs)")
+    ap.add_argument("--families", type=int, default=0, help="0 = 1.41 M per GPU (about 250 M signatures per shard, 2.0e9 on 8 GPUs)")
     ap.add_argument("--keep", type=int, default=legs.C4_KEEP, help="signature density, per 1024 consensus windows")
     ap.add_argument("--proteins", type=int, default=1_000_000, help="per rank")
     ap.add_argument("--steps", type=int, default=10)
