@@ -360,7 +360,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": round(achieved_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved_gbs / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": lookups_per_step * BYTES_PER_LOOKUP_AA, "peak_source": peak_src,
-                "kernel": "k_filter + k_refilter + k_probe2 (probe cascade, three launches)" if cascade else "k_probe",
+                "kernel": ("k_probe_half<0> + k_probe_half<1> (two passes, one per half of the key space)" if os.environ.get("KG_FILTER_HALVES", "0") not in ("", "0")
+                           else "k_filter + k_refilter + k_probe2 (probe cascade, three launches)" if cascade else "k_probe"),
                 "kernel_ms": round(probe_s * 1e3, 4),
                 "bytes_per_lookup": BYTES_PER_LOOKUP_AA, "lookups_per_launch": lookups_per_step,
                 "probe_roofline_sectors_per_s": r_probe,

@@ -69,6 +69,10 @@ struct KgTableView {
     // L2 AFTER the first one: the two never have to be resident together.  0 words = no second stage.
     const unsigned long long* filter2;
     uint32_t filter2_words;
+    // "halves" (kg_run.cu, k_probe_half): filter holds the keys whose hash has its top bit clear, filter2 (same size) the
+    // others; the probe runs as two passes over the batch, one per half, so that each half has the L2 set-aside to itself and
+    // every key gets twice the filter bits
+    uint32_t halves;
 };
 
 // On B200 an L2 miss always brings in the whole 128-byte line (ncu: ~124 B of DRAM reads per random 32-byte sector
@@ -109,6 +113,11 @@ __host__ __device__ __forceinline__ uint32_t kg_filter_word(uint64_t m, uint32_t
 __host__ __device__ __forceinline__ unsigned long long kg_filter_mask(uint64_t m) {
     const uint32_t b = (uint32_t)(m >> 11) * 0x85EBCA77u;
     return (1ull << (b >> 26)) | (1ull << ((b >> 20) & 63u));
+}
+// halves: which half a key belongs to, and its word inside that half (the bits below the top one pick the word)
+__host__ __device__ __forceinline__ uint32_t kg_filter_half(uint64_t m) { return (uint32_t)(m >> 63); }
+__host__ __device__ __forceinline__ uint32_t kg_filter_half_word(uint64_t m, uint32_t words) {
+    return (uint32_t)((((m << 1) >> 32) * (uint64_t)words) >> 32);
 }
 // second-stage prefilter (the probe cascade, kg_run.cu): same construction on an independent multiplier, so that a false
 // positive of the first filter is an (almost) independent draw in the second

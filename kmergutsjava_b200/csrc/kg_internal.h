@@ -10,6 +10,7 @@ struct kg_table {
     unsigned long long* d_filter = nullptr;
     uint32_t filter_words = 0;
     uint32_t filter2_words = 0;          // second-stage prefilter: stored right behind the first in d_filter
+    uint32_t filter_halves = 0;          // d_filter = [half 0 | half 1], each filter_words long (= filter2_words): two-pass probe
     uint64_t src_size = 0;               // the reference-format file this table was parsed from (0 = not from a file):
     int64_t src_mtime_ns = 0;            //   identity recorded in the cache file (kg_table_save)
     kg_table_info info = {};

@@ -551,6 +551,140 @@ __global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe(const uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// encode + probe in TWO PASSES, one per half of the key space (tables built with KG_FILTER_HALVES=1).
+//
+// The fused kernel's excess DRAM traffic is bucket lines fetched for false positives of the prefilter (10 of 22 GB on
+// configs[1]) and prefilter words that fell out of L2 (4 GB); the false-positive rate is set by the filter bits that fit the
+// L2 set-aside AT ONE TIME (2.7 bits per key: 0.28).  Here every key belongs to one of two halves (top bit of its filter
+// hash) and each half has a filter of that size of its own (5.4 bits per key: ~0.10).  Pass 0 runs the whole batch against
+// half 0 -- every window is encoded, the windows of the other half are dropped before they cost a load -- with filter 0 in
+// the set-aside, pass 1 the same against half 1.  Unlike the cascade (profiles/r02_probe_cascade.md) no survivor queue goes
+// through global memory and no window is filtered twice; the price is the second encode.  Pass 0 leaves its hits in
+// per-tile chunks of its own; pass 1 loads the chunk of its tile into the shared-memory staging area next to its own
+// hits (a position belongs to exactly one half) and emits the merged tile in position order, so everything downstream
+// sees exactly what k_probe would have written.
+// ---------------------------------------------------------------------------------------------------------------
+template <int HALF>
+__global__ __launch_bounds__(PROBE_BLK, KG_PROBE_OCC) void k_probe_half(const uint8_t* __restrict__ stream, uint32_t vtotal, KgTableView tab,
+                                                                        uint32_t* __restrict__ chunk_pos, int4* __restrict__ chunk_payload,
+                                                                        uint32_t hit_cap, uint32_t* __restrict__ tile_base,
+                                                                        uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ ctr,
+                                                                        const uint32_t* __restrict__ prev_pos, const int4* __restrict__ prev_payload,
+                                                                        const uint32_t* __restrict__ prev_base, const uint32_t* __restrict__ prev_cnt,
+                                                                        uint32_t flags) {
+    extern __shared__ int4 smem_dyn[];
+    int4* pstage = smem_dyn;
+    unsigned long long* queue = reinterpret_cast<unsigned long long*>(smem_dyn + TILE);
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t hitbits[TILE / 32];
+    __shared__ uint32_t warp_a[PROBE_BLK / 32], warp_b[PROBE_BLK / 32], warp_kmers[PROBE_BLK / 32];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += PROBE_BLK) lut[i] = (i >= 'A' && i <= 'Z') ? c_aa_code[i - 'A'] : 20;
+    if (tid < TILE / 32) hitbits[tid] = 0;
+    __syncthreads();
+    const uint64_t pol_keep = kg_policy_evict_last();
+    const uint64_t pol_stream = (flags & 1u) ? kg_policy_evict_normal() : kg_policy_evict_first();
+    const uint32_t p0 = blockIdx.x * (uint32_t)TILE + (uint32_t)tid * PT;
+    const unsigned long long* filt = HALF ? tab.filter2 : tab.filter;
+
+    // pass 1: the hits pass 0 found in this tile (issued first: their latency hides behind the encode)
+    uint32_t pv_cnt = 0, pv_base = 0, pv_pos = 0;
+    int4 pv_pl = make_int4(0, 0, 0, 0);
+    if (HALF) {
+        pv_cnt = prev_cnt[blockIdx.x];
+        pv_base = prev_base[blockIdx.x];
+        if ((uint32_t)tid < pv_cnt && pv_base != 0xFFFFFFFFu) {
+            pv_pos = __ldcs(prev_pos + pv_base + tid);
+            pv_pl = __ldcs(prev_payload + pv_base + tid);
+        }
+    }
+
+    // ---- A: encode + this half's prefilter ----
+    uint32_t pass = 0, nk = 0;
+    uint32_t q[PT + 4];
+    if (p0 < vtotal) {
+        const uint32_t valid = encode_windows(stream, p0, vtotal, lut, q);
+        uint32_t mine = 0;
+        unsigned long long fw[PT];
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            fw[i] = 0;
+            if ((valid >> i) & 1u) {
+                const uint64_t h = kg_fhash1((uint64_t)q[i] * 160000ull + q[i + 4]);
+                if (kg_filter_half(h) == (uint32_t)HALF) {
+                    mine |= 1u << i;
+                    fw[i] = kg_load_filter_word(filt, kg_filter_half_word(h, tab.filter_words), pol_keep);
+                }
+            }
+        }
+        nk = __popc(mine); // every valid window is counted in exactly one of the two passes
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            const unsigned long long fm = kg_filter_mask(kg_fhash1((uint64_t)q[i] * 160000ull + q[i + 4]));
+            pass |= (uint32_t)((fw[i] & fm) == fm) << i;
+        }
+        pass &= mine;
+    }
+    // ---- B ----
+    uint32_t nsurv;
+    uint32_t qo = block_excl_scan(__popc(pass), warp_a, &nsurv);
+#pragma unroll
+    for (int i = 0; i < PT; i++)
+        if ((pass >> i) & 1u) queue[qo++] = ((uint64_t)q[i] * 160000ull + q[i + 4]) | ((unsigned long long)(tid * PT + i) << 35);
+    const uint32_t wk = __reduce_add_sync(0xFFFFFFFFu, nk);
+    if ((tid & 31) == 0) warp_kmers[tid >> 5] = wk;
+    __syncthreads();
+    // ---- C ----
+    probe_queue(tab, queue, nsurv, pstage, hitbits, pol_stream);
+    if (HALF && pv_base != 0xFFFFFFFFu) { // merge pass 0's hits of this tile (disjoint positions)
+        const uint32_t t0 = blockIdx.x * (uint32_t)TILE;
+        if ((uint32_t)tid < pv_cnt) {
+            const uint32_t lp = pv_pos - t0;
+            pstage[lp] = pv_pl;
+            atomicOr(&hitbits[lp >> 5], 1u << (lp & 31));
+        }
+        for (uint32_t e = tid + PROBE_BLK; e < pv_cnt; e += PROBE_BLK) { // tiles with more than 128 hits in pass 0
+            const uint32_t lp = __ldcs(prev_pos + pv_base + e) - t0;
+            pstage[lp] = __ldcs(prev_payload + pv_base + e);
+            atomicOr(&hitbits[lp >> 5], 1u << (lp & 31));
+        }
+    }
+    __syncthreads();
+    // ---- D ----
+    const uint32_t hitmask = (hitbits[(tid * PT) >> 5] >> ((tid * PT) & 31)) & ((1u << PT) - 1u);
+    uint32_t total;
+    const uint32_t ho = block_excl_scan(__popc(hitmask), warp_b, &total);
+    if (tid == 0) {
+        uint32_t kmers = 0;
+#pragma unroll
+        for (int w = 0; w < PROBE_BLK / 32; w++) kmers += warp_kmers[w];
+        if (kmers) atomicAdd(&ctr[KG_CTR_KMERS], (unsigned long long)kmers);
+        unsigned long long base = 0;
+        if (total) base = atomicAdd(&ctr[HALF ? KG_CTR_HITS : KG_CTR_CLAIM], (unsigned long long)total); // pass 0 claims from its own counter
+        uint32_t b32 = 0xFFFFFFFFu;
+        if (base + total <= (unsigned long long)hit_cap) b32 = (uint32_t)base;
+        else ctr[KG_CTR_OVERFLOW] = 1ull;
+        s_base = b32;
+        tile_base[blockIdx.x] = b32;
+        tile_cnt[blockIdx.x] = total;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (base != 0xFFFFFFFFu && hitmask) {
+        uint32_t o = base + ho;
+        uint32_t m = hitmask;
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            chunk_pos[o] = p0 + (uint32_t)i;
+            chunk_payload[o] = pstage[tid * PT + i];
+            o++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // encode + probe as a CASCADE of three kernels (the default when the table carries a second prefilter).
 //
 // Why: the fused kernel above keeps one 64 MiB prefilter in L2 WHILE 15 GB of bucket lines stream through the same L2;
@@ -1678,6 +1812,8 @@ struct PipeSlot { // everything ONE in-flight pipeline run needs; two of them le
     DevBuf tile_base, tile_cnt, tile_out, chunk_pos, chunk_payload, lo, sparse, call_cnt, call_off, ctr;
     DevBuf otu_cnt, otu_first;                                   // kg_run: OTU entries per sequence and their exclusive scan
     DevBuf queue, tile_qcnt;                                     // probe cascade: survivors (8 KB slice per tile) and their counts
+    DevBuf half_pos, half_payload, half_base, half_cnt;          // two-pass probe: hits of pass 0 (per-tile chunks)
+    bool halves = false;
     DevBuf hit_pos, hit_payload;                                 // position-ordered hits (segment path, "-d")
     DevBuf fk_a, fi_a;                                           // per-sequence path: class histogram / cursors, sequence permutation
     DevBuf seg_tmp, seg_v, seg_perm, seg_begin, seg_cnt, seg_off, nseg, tile_bnd, blk_cnt, blk_off, scan_part; // segment path
@@ -1843,6 +1979,8 @@ extern "C" int kg_init(int device, kg_context** out) {
     for (auto& ev : ctx->d2h_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->up_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
+    CU(cudaFuncSetAttribute(k_probe_half<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
+    CU(cudaFuncSetAttribute(k_probe_half<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROBE_SMEM));
     CU(cudaMallocHost(&ctx->h_counters, (KG_CTR_COUNT + 1) * sizeof(uint64_t)));
     memset(ctx->h_counters, 0, (KG_CTR_COUNT + 1) * sizeof(uint64_t));
     *out = ctx;
@@ -1856,7 +1994,7 @@ extern "C" void kg_shutdown(kg_context* ctx) {
     RunScratch& sc = scratch_of(ctx);
     for (auto& sl : sc.slot) {
         for (DevBuf* b : {&sl.tile_base, &sl.tile_cnt, &sl.tile_out, &sl.chunk_pos, &sl.chunk_payload, &sl.lo, &sl.sparse, &sl.call_cnt,
-                          &sl.call_off, &sl.ctr, &sl.otu_cnt, &sl.otu_first, &sl.queue, &sl.tile_qcnt, &sl.hit_pos, &sl.hit_payload, &sl.seg_tmp, &sl.seg_v, &sl.seg_perm, &sl.seg_begin,
+                          &sl.call_off, &sl.ctr, &sl.otu_cnt, &sl.otu_first, &sl.queue, &sl.tile_qcnt, &sl.half_pos, &sl.half_payload, &sl.half_base, &sl.half_cnt, &sl.hit_pos, &sl.hit_payload, &sl.seg_tmp, &sl.seg_v, &sl.seg_perm, &sl.seg_begin,
                           &sl.seg_cnt, &sl.seg_off, &sl.tile_bnd, &sl.blk_cnt, &sl.blk_off, &sl.scan_part,
                           &sl.nseg, &sl.fk_a, &sl.fi_a, &sl.o_run, &sl.o_dense})
             b->release();
@@ -2037,7 +2175,7 @@ static uint32_t probe_flags() { // experiment switches: bit 0 = no evict_first o
 
 // Which probe: the three-kernel cascade (tables with a second prefilter) or the fused kernel.  KG_PROBE=fused|cascade.
 static bool use_cascade(const kg_table* table) {
-    if (!table->filter_words || !table->filter2_words) return false;
+    if (!table->filter_words || !table->filter2_words || table->filter_halves) return false;
     if (const char* e = getenv("KG_PROBE")) return strcmp(e, "fused") != 0;
     return true;
 }
@@ -2086,6 +2224,7 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
                         uint64_t hit_cap_hint, uint32_t seq_base, const ProbeStage* custom = nullptr) {
     cudaStream_t st = ctx->stream;
     sl.launches = 0;
+    sl.halves = false;
     cudaEventRecord(sl.ev[0], st);
     if (!custom) KG_TRY(kg_batch_prepare(b, st, &sl.launches));
     const uint64_t nv = b->nv, vtotal = b->vtotal;
@@ -2169,6 +2308,25 @@ static int pipe_enqueue(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg
             cudaEventRecord(sl.part_ev[KG_MAX_PARTS], ls);
             cudaStreamWaitEvent(st, sl.part_ev[KG_MAX_PARTS], 0);
         }
+    } else if (ntiles && table->filter_halves) { // two passes, one per half of the key space (k_probe_half)
+        sl.cascade = false;
+        const KgTableView tv = table->view();
+        const size_t wbytes = (size_t)tv.filter_words * 8;
+        KG_TRY(sl.half_pos.ensure(hit_cap * 4));
+        KG_TRY(sl.half_payload.ensure(hit_cap * sizeof(int4)));
+        KG_TRY(sl.half_base.ensure(((size_t)ntiles + 1) * 4));
+        KG_TRY(sl.half_cnt.ensure(((size_t)ntiles + 1) * 4));
+        CU(launch_windowed(k_probe_half<0>, dim3(ntiles), dim3(PROBE_BLK), PROBE_SMEM, st, tv.filter, wbytes, b->stream(), (uint32_t)vtotal, tv,
+                           sl.half_pos.as<uint32_t>(), sl.half_payload.as<int4>(), (uint32_t)hit_cap, sl.half_base.as<uint32_t>(),
+                           sl.half_cnt.as<uint32_t>(), d_ctr, (const uint32_t*)nullptr, (const int4*)nullptr, (const uint32_t*)nullptr,
+                           (const uint32_t*)nullptr, probe_flags()));
+        cudaEventRecord(sl.ev[4], st);
+        CU(launch_windowed(k_probe_half<1>, dim3(ntiles), dim3(PROBE_BLK), PROBE_SMEM, st, tv.filter2, wbytes, b->stream(), (uint32_t)vtotal, tv,
+                           sl.chunk_pos.as<uint32_t>(), sl.chunk_payload.as<int4>(), (uint32_t)hit_cap, sl.tile_base.as<uint32_t>(),
+                           sl.tile_cnt.as<uint32_t>(), d_ctr, (const uint32_t*)sl.half_pos.as<uint32_t>(), (const int4*)sl.half_payload.as<int4>(),
+                           (const uint32_t*)sl.half_base.as<uint32_t>(), (const uint32_t*)sl.half_cnt.as<uint32_t>(), probe_flags()));
+        sl.halves = true;
+        sl.launches += 2;
     } else if (ntiles) {
         sl.cascade = false;
         k_probe<<<ntiles, PROBE_BLK, PROBE_SMEM, st>>>(b->stream(), (uint32_t)vtotal, table->view(), sl.chunk_pos.as<uint32_t>(),
@@ -2314,6 +2472,10 @@ static int pipe_finish(kg_context* ctx, PipeSlot& sl, const kg_table* table, kg_
     cudaEventElapsedTime(&r->stats.ms_probe, sl.ev[1], sl.ev[2]);
     cudaEventElapsedTime(&r->stats.ms_group, sl.ev[2], sl.ev[3]);
     r->stats.ms_filter = r->stats.ms_refilter = r->stats.ms_lines = 0.f;
+    if (sl.halves && !custom && ntiles_of(b)) { // two-pass probe: the passes, in the cascade's fields
+        cudaEventElapsedTime(&r->stats.ms_filter, sl.ev[1], sl.ev[4]);
+        cudaEventElapsedTime(&r->stats.ms_lines, sl.ev[4], sl.ev[2]);
+    }
     if (sl.cascade && sl.cascade_parts == 1 && !custom && ntiles_of(b)) {
         cudaEventElapsedTime(&r->stats.ms_filter, sl.ev[1], sl.ev[4]);
         cudaEventElapsedTime(&r->stats.ms_refilter, sl.ev[4], sl.ev[5]);

@@ -147,6 +147,13 @@ __global__ void k_filter2_build(const uint64_t* __restrict__ comp, size_t n, uns
     atomicOr(&filter2[kg_filter2_word(m, filter2_words)], kg_filter2_mask(m));
 }
 
+__global__ void k_filter_halves_build(const uint64_t* __restrict__ comp, size_t n, unsigned long long* __restrict__ filter, uint32_t words) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t m = kg_fhash1(comp[r] & 0x7FFFFFFFFull);
+    atomicOr(&filter[(size_t)kg_filter_half(m) * words + kg_filter_half_word(m, words)], kg_filter_mask(m));
+}
+
 __global__ void k_count_flagged(const uint32_t* __restrict__ words, size_t nbuckets_total, unsigned long long* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool f = i < nbuckets_total && (words[i * (KG_LINE_UINT4 * 4) + 6] & KG_W6_FLAG);
@@ -182,6 +189,7 @@ KgTableView kg_table::view() const {
     v.filter_words = filter_words;
     v.filter2 = filter2_words ? d_filter + filter_words : nullptr;
     v.filter2_words = filter2_words;
+    v.halves = filter_halves;
     return v;
 }
 
@@ -194,7 +202,7 @@ static void pin_filter(kg_context* ctx, const kg_table* t, bool force) {
     // A table with a second prefilter is probed by the cascade (kg_run.cu): each filter has the L2 to itself during its
     // stage, and a persisting set-aside only takes L2 away from the bucket-line stage (measured: 3.5 vs 2.8 ms).  The fused
     // kernel and the hash-sharded mode's k_answer (one filter against streaming lines) keep the window.
-    if (!force && t->filter2_words && t->shard_count == 1 && !getenv("KG_CASCADE_PERSIST")) return;
+    if (!force && t->filter2_words && !t->filter_halves && t->shard_count == 1 && !getenv("KG_CASCADE_PERSIST")) return;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
     const size_t fbytes = (size_t)t->filter_words * 8;
@@ -203,6 +211,10 @@ static void pin_filter(kg_context* ctx, const kg_table* t, bool force) {
         carve = std::min<size_t>((size_t)atoll(e) << 20, (size_t)prop.persistingL2CacheMaxSize);
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
     t->l2_carve = carve;
+    if (t->filter_halves) { // the two halves take turns in the set-aside: each pass launches with its own window (kg_run.cu)
+        cudaGetLastError();
+        return;
+    }
     cudaStreamAttrValue av = {};
     av.accessPolicyWindow.base_ptr = t->d_filter;
     av.accessPolicyWindow.num_bytes = std::min<size_t>(fbytes, (size_t)prop.accessPolicyMaxWindowSize);
@@ -295,13 +307,22 @@ static int build_on_device(kg_context* ctx, const uint64_t* d_keys, const int4* 
             if (const char* e = getenv("KG_FILTER_MAX_MB")) max_bytes = (uint64_t)atoll(e) << 20; // experiments
             if (bytes > max_bytes) bytes = max_bytes;
             if (bytes < 4096) bytes = 4096;
+            const bool halves = getenv("KG_FILTER_HALVES") && atoi(getenv("KG_FILTER_HALVES")) > 0 && t->shard_count == 1;
+            if (halves) { // two filters of up to the cap each, one per half of the keys: twice the bits per key
+                bytes = std::min<uint64_t>((uint64_t)((double)n_unique * 0.5 * 2.0 * filter_bits_per_key() / 8.0), max_bytes);
+                if (bytes < 4096) bytes = 4096;
+            }
             t->filter_words = (uint32_t)(bytes / 8) & ~15u; // whole 128-byte lines, so that the second filter starts on one
-            t->filter2_words = filter_stages() >= 2 ? t->filter_words : 0;
+            t->filter2_words = (halves || filter_stages() >= 2) ? t->filter_words : 0;
+            t->filter_halves = halves ? 1u : 0u;
             const size_t fwords = (size_t)t->filter_words + t->filter2_words;
             CU(cudaMalloc(&t->d_filter, fwords * 8));
             CU(cudaMemsetAsync(t->d_filter, 0, fwords * 8, st));
-            k_filter_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter, t->filter_words);
-            if (t->filter2_words)
+            if (t->filter_halves)
+                k_filter_halves_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter, t->filter_words);
+            else
+                k_filter_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter, t->filter_words);
+            if (t->filter2_words && !t->filter_halves)
                 k_filter2_build<<<blocks_for(n_unique, 256), 256, 0, st>>>(comp, n_unique, t->d_filter + t->filter_words, t->filter2_words);
             pin_filter(ctx, t, false);
         }
@@ -928,6 +949,7 @@ extern "C" int kg_table_save(kg_context* ctx, const kg_table* t, const char* pat
     h.num_buckets = t->num_buckets;
     h.filter_words = t->filter_words;
     h.filter2_words = t->filter2_words;
+    h.pad0 = t->filter_halves;
     h.src_size = t->src_size;
     h.src_mtime_ns = t->src_mtime_ns;
     KG_TRY(body_check_of(ctx, t, &h.body_check));
@@ -981,6 +1003,7 @@ extern "C" int kg_table_load_cached(kg_context* ctx, const char* path, kg_table*
     t->num_buckets = h.num_buckets;
     t->filter_words = h.filter_words;
     t->filter2_words = h.filter2_words;
+    t->filter_halves = h.pad0;
     t->src_size = h.src_size;
     t->src_mtime_ns = h.src_mtime_ns;
     t->shard_rank = h.shard_rank;

@@ -76,14 +76,17 @@ def test_dna_parity(kg, ctx, oracle, universe, flags):
     t.free()
 
 
-@pytest.mark.parametrize("probe,stages", [("cascade", "2"), ("fused", "2"), ("fused", "1"), ("fused", "0")],
-                         ids=["cascade", "fused", "fused-one-filter", "fused-no-filter"])
+@pytest.mark.parametrize("probe,stages", [("cascade", "2"), ("fused", "2"), ("fused", "1"), ("fused", "0"), ("halves", "1")],
+                         ids=["cascade", "fused", "fused-one-filter", "fused-no-filter", "two-pass-halves"])
 def test_probe_variants(kg, ctx, oracle, universe, monkeypatch, probe, stages):
     """The probe stage exists as a three-kernel cascade (two prefilters that take turns in L2, the default) and as one
     fused kernel (one prefilter, also what the hash-sharded mode's k_answer shares its code with): both must give the
     oracle's hits, in aa mode and in 6-frame mode, with dense tiles (a protein of the table's own windows) included."""
     u, img, _ = universe
-    monkeypatch.setenv("KG_PROBE", probe)
+    if probe == "halves":   # k_probe_half: one pass per half of the key space, each with its own filter
+        monkeypatch.setenv("KG_FILTER_HALVES", "1")
+    else:
+        monkeypatch.setenv("KG_PROBE", probe)
     if stages == "0":
         monkeypatch.setenv("KG_FILTER_BITS", "0")
     else:
@@ -98,7 +101,7 @@ def test_probe_variants(kg, ctx, oracle, universe, monkeypatch, probe, stages):
     assert len(ref.hits) > 5000
     assert_same(res, ref, what=f"aa {probe} {stages}")
     st = res.stats
-    assert (st.ms_filter > 0) == (probe == "cascade"), (st.ms_filter, st.ms_refilter, st.ms_lines)
+    assert (st.ms_filter > 0) == (probe in ("cascade", "halves")), (st.ms_filter, st.ms_refilter, st.ms_lines)
     res.free()
     sb, off = oracle.concat([synth.genome(u, 40000, seed=41, index=i) for i in range(2)])
     res = ctx.run(t, kg.MODE_DNA, sb, off, kg.default_params(emit_hits=1))
