@@ -488,6 +488,7 @@ struct kg_comm {
     PeerBases xpeers = {};              // every rank's buffer as this process sees it ([rank] = xbuf.p)
     bool xopened[KG_MAX_RANKS] = {};    // peers mapped with cudaIpcOpenMemHandle (to be closed)
     uint64_t xepoch = 0;
+    bool direct_off = false;            // mapping the peers failed somewhere: this communicator uses the staged NCCL transport
     DevBuf xstage;                      // small device staging for the bootstrap all-gathers
     PeerCtl* h_ctl = nullptr;           // pinned copy of the control block, read after a step
 };
@@ -983,20 +984,39 @@ int dx_setup(kg_comm* c, uint64_t want_cap) {
     uint64_t zero = 0, zeros[KG_MAX_RANKS];
     KG_TRY(allgather_host(c, &zero, 8, zeros)); // every rank has unmapped its peers before anybody frees
     KG_TRY(dx_alloc(c, cap));
+    // Mapping a peer's buffer can fail where CUDA IPC or peer access is not available (some container set-ups, GPUs without
+    // a P2P path).  No rank may then use the direct transport: the outcome is all-gathered and, if anybody failed, every rank
+    // drops its buffer and the communicator falls back to the staged NCCL transport for good.
     cudaIpcMemHandle_t mine, all[KG_MAX_RANKS];
-    CU(cudaIpcGetMemHandle(&mine, c->xbuf.p));
+    uint64_t ok = cudaIpcGetMemHandle(&mine, c->xbuf.p) == cudaSuccess && !getenv("KG_SHARD_FAIL_IPC");
+    if (!ok) memset(&mine, 0, sizeof mine);
     KG_TRY(allgather_host(c, &mine, sizeof mine, all));
-    for (int p = 0; p < R; p++) {
+    uint64_t oks[KG_MAX_RANKS] = {};
+    KG_TRY(allgather_host(c, &ok, 8, oks));
+    for (int p = 0; p < R; p++) ok = ok && oks[p];
+    for (int p = 0; p < R && ok; p++) {
         if (p == c->rank) {
             c->xpeers.base[p] = c->xbuf.as<uint8_t>();
         } else {
             void* q = nullptr;
-            CU(cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess));
+            if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = 0;
+                break;
+            }
             c->xpeers.base[p] = (uint8_t*)q;
             c->xopened[p] = true;
         }
     }
-    KG_TRY(allgather_host(c, &zero, 8, zeros)); // everybody's control block is zeroed and mapped before anyone writes
+    cudaGetLastError();
+    KG_TRY(allgather_host(c, &ok, 8, oks)); // also: everybody's control block is zeroed and mapped before anyone writes
+    for (int p = 0; p < R; p++) ok = ok && oks[p];
+    if (!ok) {
+        dx_close(c);
+        KG_TRY(allgather_host(c, &zero, 8, zeros)); // everybody has unmapped before anybody frees
+        c->xbuf.release();
+        c->xl = PeerLayout();
+        c->direct_off = true;
+    }
     return KG_OK;
 }
 // keys: encode, bin by owner, store every bin straight into its owner's buffer; tell the owners how much arrived
@@ -1232,11 +1252,12 @@ extern "C" int kg_batch_run_sharded(kg_comm* c, const kg_table* shard, kg_batch*
         const kg_table* t;
         ~Restore() { shard_l2_setaside(t, true); }
     } restore{shard};
-    if (c->nccl && shard_direct_wanted()) {
+    if (c->nccl && shard_direct_wanted() && !c->direct_off && !c->xbuf.p) KG_TRY(dx_setup(c, dx_cap_wanted(c, batch))); // collective; may switch direct_off on
+    if (c->nccl && shard_direct_wanted() && !c->direct_off) {
         // Direct transport: route -> (flags) -> answer -> (flags) -> merge, all on the compute stream, one host wait at the end.
+        bool done = false;
         for (int attempt = 0;; attempt++) {
             KG_TRY(shard_begin(c, batch, 1));
-            if (!c->xbuf.p) KG_TRY(dx_setup(c, dx_cap_wanted(c, batch)));
             KG_TRY(dx_route(c, batch, true));
             KG_TRY(dx_answer(c, shard, true));
             // The persisting-L2 set-aside is a device-wide limit that is switched from the host, not in stream order: it is on
@@ -1244,13 +1265,19 @@ extern "C" int kg_batch_run_sharded(kg_comm* c, const kg_table* shard, kg_batch*
             // here -- the one wait inside a step (the merge's own wait ends it).
             CU(cudaEventSynchronize(c->ch[0].ev_replies));
             KG_TRY(shard_merge(c, shard, batch, params, result, true));
-            if (*result) break;
+            if (*result) {
+                done = true;
+                break;
+            }
             if (attempt) KG_FAIL(KG_ECUDA, "kg_batch_run_sharded: bin overflow persisted at capacity %llu", (unsigned long long)c->xl.cap);
             // a skewed batch (or a larger one than the buffers were made for): all ranks have read the same max_bin values
             KG_TRY(dx_setup(c, c->ch[0].cap_seen + c->ch[0].cap_seen / 32 + 4096));
+            if (c->direct_off) break; // the larger buffers could not be mapped: the staged transport takes the step
         }
-        c->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        return KG_OK;
+        if (done) {
+            c->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            return KG_OK;
+        }
     }
     KG_TRY(shard_begin(c, batch, shard_chunks_wanted(c, batch)));
     const int H = c->nchunks;

@@ -46,8 +46,11 @@ def main():
     otable = kgo.Table(data=img)
     seqs = u.proteins(6000, seed=9)
     mine = seqs[len(seqs) * rank // nranks: len(seqs) * (rank + 1) // nranks]
+    # step 3 is three times the first batch: with the direct transport the exchange buffers (sized by the first step) overflow,
+    # every rank sees it in its control block, and the buffers are re-made and re-mapped collectively before the step repeats
     for step, (mode, share) in enumerate([(kg.MODE_AA, mine), (kg.MODE_AA, mine[: 7 * rank]),
-                                          (kg.MODE_DNA, [synth.genome(u, 20000, seed=40 + rank, index=i) for i in range(2)])]):
+                                          (kg.MODE_DNA, [synth.genome(u, 20000, seed=40 + rank, index=i) for i in range(2)]),
+                                          (kg.MODE_AA, mine * 3)]):
         sb, off = kgo.concat(share)
         params = kg.default_params(emit_hits=1)
         b = ctx.upload(mode, sb, off)

@@ -238,6 +238,15 @@ def _nccl_two_processes(kg, transport):
     env = dict(os.environ)
     if env.get("KG_SHARD_TRANSPORT") == "copy":
         env["KG_SHARD_TRANSPORT"] = "nccl"
+    variants = [env]
+    if transport == "direct":   # the peers' buffers cannot be mapped (simulated): every rank falls back to the staged transport
+        variants.append(dict(env, KG_SHARD_FAIL_IPC="1"))
+    for env in variants:
+        _two_processes_once(env)
+
+
+def _two_processes_once(env):
+    import tempfile
     with tempfile.TemporaryDirectory() as d:
         procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "shard_nccl_worker.py"), str(r), "2", d],
                                   cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
