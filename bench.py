@@ -178,6 +178,19 @@ def run_ours(args):
     import kmergutsjava_b200 as kg
     import bench_legs as legs
     plumb = legs.Plumbing(torch, dist, rank, world, local)
+
+    def guarded(name, leg):
+        """The legs come after the headline measurement: at N = 1 a leg that fails (a parity check included) is reported in
+        its own object instead of costing the whole JSON line.  At N > 1 a rank cannot leave a collective leg alone, so there
+        the failure stays fatal for the job."""
+        try:
+            return leg()
+        except (Exception, SystemExit) as e:
+            if world > 1:
+                raise
+            log(f"{name} leg FAILED: {e!r}")
+            return {"error": f"{type(e).__name__}: {e}"[:2000]}
+
     ctx = kg.Context(local)
     u, (dk, dp, nsig), table, (ds, do, total), prep = build_inputs(kg, ctx, args, rank)
     ti = table.info
@@ -428,7 +441,7 @@ def run_ours(args):
         log("cpu rows done")
         del ref, r1, r2, sb, off
         if not args.no_table_load:
-            table_load = legs.table_load(kg, ctx, img, table, batch, params, log=log)
+            table_load = guarded("table_load", lambda: legs.table_load(kg, ctx, img, table, batch, params, log=log))
             log("table load leg done")
 
         # size-independent property at FULL size: lookups, hits and a checksum over every hit's (position, payload) must
@@ -448,11 +461,13 @@ def run_ours(args):
     which = set() if args.no_legs else set(args.legs.split(","))
     lsteps = max(3, min(args.steps, 10))
     if "2" in which:
-        leg_out["configs2"] = legs.configs2(kg, ctx, table, u, plumb, steps=lsteps, otable=otable,
-                                            parity_genomes=50 if otable is not None else 0, threads=threads, log=log)
+        leg_out["configs2"] = guarded("configs2", lambda: legs.configs2(kg, ctx, table, u, plumb, steps=lsteps, otable=otable,
+                                                                        parity_genomes=50 if otable is not None else 0,
+                                                                        threads=threads, log=log))
         log("configs2 leg done")
     if "3" in which:
-        leg_out["configs3"] = legs.configs3(kg, ctx, table, u, plumb, orfs=args.orfs, otable=otable, threads=threads, log=log)
+        leg_out["configs3"] = guarded("configs3", lambda: legs.configs3(kg, ctx, table, u, plumb, orfs=args.orfs, otable=otable,
+                                                                        threads=threads, log=log))
         log("configs3 leg done")
     stats_keep = {"hits": int(st.num_hits), "calls": int(st.num_calls), "prepare": st.ms_prepare, "probe": st.ms_probe, "group": st.ms_group,
                   "device": st.ms_device, "filter": st.ms_filter, "refilter": st.ms_refilter, "lines": st.ms_lines,
@@ -463,7 +478,8 @@ def run_ours(args):
     for p in (dk, dp, ds, do):
         bl.device_free(p)
     if "4" in which:
-        leg_out["configs4"] = legs.configs4(kg, ctx, plumb, proteins=args.proteins, steps=lsteps, families=args.c4_families, log=log)
+        leg_out["configs4"] = guarded("configs4", lambda: legs.configs4(kg, ctx, plumb, proteins=args.proteins, steps=lsteps,
+                                                                        families=args.c4_families, log=log))
         log("configs4 leg done")
 
     if rank == 0:
