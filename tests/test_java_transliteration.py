@@ -1,0 +1,321 @@
+"""The reference's OWN SOURCE, executed here without a JVM, against the CPU oracle.
+
+tests/java_pin/j2py.py transliterates the unmodified lib/src/kmergutsjava/KmerGutsJava.java into Python statement by statement
+(it knows Java syntax and Java's arithmetic, nothing about k-mers); these tests run that text -- main(), run(), readFasta,
+lookup, gatherHits, processSetOfHits, the scalar helpers -- on small inputs and demand what the oracle gives, byte for byte.
+The full-size runs of the same comparison (the eight configs[0] reports) are recorded in
+tests/golden/java_transliteration_pin.json by tests/java_pin/transliterated_pin.py and asserted in test_oracle_golden.py.
+
+Needs the reference checkout (KG_REFERENCE, default /root/reference): present where the CPU suite runs, absent on the GPU
+boxes -- there the module is skipped.  No GPU, and nothing of the product is involved."""
+import ctypes as C
+import gzip
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tools import kg_synth as synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("KG_REFERENCE", "/root/reference")
+JAVA = os.path.join(REF, "lib", "src", "kmergutsjava", "KmerGutsJava.java")
+pytestmark = pytest.mark.skipif(not os.path.exists(JAVA), reason="the reference checkout is not on this box")
+
+FAA = os.path.join(ROOT, "tests", "data", "Ecoli_K12_W3110.faa.gz")
+FNA = os.path.join(ROOT, "tests", "data", "Ecoli_K12_W3110.fna.gz")
+FLAGSETS = [[], ["-d"], ["-O"], ["-m", "3", "-g", "50", "-M", "2"]]
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def pin():
+    return _load("pin_oracle", os.path.join(ROOT, "tests", "java_pin", "pin_oracle.py"))
+
+
+@pytest.fixture(scope="module")
+def java(tmp_path_factory):
+    """(module holding the transliterated classes, the runtime module)"""
+    tp = _load("transliterated_pin", os.path.join(ROOT, "tests", "java_pin", "transliterated_pin.py"))
+    mod, _ = tp.load_reference(JAVA, str(tmp_path_factory.mktemp("kgj") / "kgj_transliterated.py"))
+    return mod, sys.modules["j2py_runtime"], tp
+
+
+@pytest.fixture(scope="module")
+def small_c0(tmp_path_factory):
+    """configs[0] in small (SURVEY 8(d) C0 rule).  Protein mode: the table derived from the first 300 E. coli proteins, queried
+    with the first 150.  6-frame mode: the table derived from ALL proteins (the .faa.gz is not in genome order, so a small
+    table would leave a genome prefix almost without hits), queried with the first 60 kb of the genome."""
+    d = tmp_path_factory.mktemp("c0small")
+    ids, descr, seqs = synth.read_fasta_simple(FAA)
+    sub = str(d / "first300.faa.gz")
+    plain = str(d / "first300.faa")
+    synth.write_fasta(plain, ids[:300], seqs[:300], descr=descr[:300])
+    with open(plain, "rb") as f, gzip.open(sub, "wb") as g:
+        g.write(f.read())
+    data = str(d / "KmerData")
+    synth.build_c0_fixture(sub, data)
+    data_all = str(d / "KmerDataAll")
+    synth.build_c0_fixture(FAA, data_all)
+    faa = str(d / "q.faa")
+    synth.write_fasta(faa, ids[:150], seqs[:150], descr=descr[:150])
+    gids, _, gseqs = synth.read_fasta_simple(FNA)
+    fna = str(d / "q.fna")
+    synth.write_fasta(fna, gids[:1], [gseqs[0][:60_000]])
+    return {"aa": (data, faa), "dna": (data_all, fna)}, faa, fna, d
+
+
+def _both(oracle, pin, java, args, out_dir, tag):
+    """The same command line through the oracle's CLI and through the transliterated KmerGutsJava.main -> stripped texts"""
+    mod = java[0]
+    o, j = os.path.join(out_dir, tag + ".oracle.txt"), os.path.join(out_dir, tag + ".java.txt")
+    oracle.run_cli(list(args) + ["-o", o])
+    mod.KmerGutsJava.main(list(args) + ["-o", j])
+    return pin.strip(open(o, errors="replace").read()), pin.strip(open(j, errors="replace").read())
+
+
+def test_scalar_helpers_and_tables(oracle, java):
+    """KGJ:85-99, 111-175, 177-272, 274-318 against the oracle's C restatements, every byte value"""
+    K = java[0].KmerGutsJava
+    L = oracle.lib()
+    assert (K.K, K.CORE, K.MAX_ENCODED, K.MAX_HITS_PER_SEQ, K.OI_BUFSZ, K.VERSION) == (8, 20 ** 7, 20 ** 8, 40000, 5, 1)
+    L.kgo_genetic_code.restype = C.c_char
+    assert [c for c in K.GENETIC_CODE] == [L.kgo_genetic_code(i).decode() for i in range(64)]
+    assert "".join(K.PROT_ALPHA) == synth.PROT_ALPHA
+    for c in range(256):
+        assert K.toAminoAcidOff(chr(c)) == L.kgo_to_amino_acid_off(c), c
+        assert ord(K.compl(chr(c))) == L.kgo_compl(c), c
+        assert K.dnaChar(chr(c)) == L.kgo_dna_char(c), c
+    L.kgo_encoded_kmer.restype = C.c_int64
+    L.kgo_encoded_kmer.argtypes = [C.c_char_p, C.c_size_t]
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        codes = rng.integers(0, 22 if rng.random() < 0.3 else 20, 12).astype(np.uint8)
+        for pos in range(5):
+            assert K.encodedKmer([int(x) for x in codes], pos) == L.kgo_encoded_kmer(codes.tobytes(), pos)
+    assert K.encodedKmer([19] * 8, 0) == 20 ** 8 - 1 and K.encodedKmer([1] + [0] * 7, 0) == 20 ** 7
+    L.kgo_rev_comp.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
+    L.kgo_translate.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
+    alphabet = b"ACGTacgtuUNnRYKMSWBDHVxX-*"
+    for n in list(range(0, 14)) + [50, 301]:
+        seq = bytes(alphabet[int(i)] for i in rng.integers(0, len(alphabet), n)) if n < 301 else bytes(b"ACGT"[int(i)] for i in rng.integers(0, 4, n))
+        rc = C.create_string_buffer(max(n, 1))
+        L.kgo_rev_comp(seq, n, rc)
+        assert "".join(K.revComp(list(seq.decode()))) == rc.raw[:n].decode()
+        plen = n // 3 + 1                                    # KGJ:1061: the buffers are reused across the frames
+        pseq, piseq = C.create_string_buffer(plen), C.create_string_buffer(plen)
+        jp, ji = ["\0"] * plen, [0] * plen
+        for frame in range(3):
+            L.kgo_translate(seq, n, frame, pseq, piseq, plen)
+            K.translate(list(seq.decode()), frame, jp, ji)
+            assert [x for x in piseq.raw] == ji, (n, frame)
+            assert [ord(c) if isinstance(c, str) else c for c in jp] == [x for x in pseq.raw], (n, frame)
+
+
+def test_gather_hits_on_the_hand_traced_vectors(java, pin, tmp_path):
+    """KGJ:457-514 + 385-455 + 516-524 on tests/golden/fsm_kats.json: the text Java prints == the text the KAT file implies"""
+    mod, rt, tp = java
+    pin.write_kats(str(tmp_path / "kats.txt"))
+    tp.run_kats(mod, str(tmp_path / "kats.txt"), str(tmp_path / "java_kats.txt"))
+    assert open(tmp_path / "java_kats.txt").read() == pin.expected_kat_text()
+
+
+@pytest.mark.parametrize("flags", FLAGSETS, ids=lambda f: "_".join(f) or "default")
+@pytest.mark.parametrize("mode", ["aa", "dna"])
+def test_main_reports_equal_the_oracles(oracle, pin, java, small_c0, mode, flags):
+    """KmerGutsJava.main (KGJ:560-654) -> run (742-820) -> readFasta, prepareQuery, the comparator sort, lookup (944-1034),
+    processAASeq / processSeq: whole reports, wall-clock lines dropped, byte for byte -- incl. the -d dumps (HIT lines,
+    after-hit / after-call lists, `Kmers found`), which the product's report omits but the oracle prints."""
+    dirs, faa, fna, d = small_c0
+    data, q = dirs[mode]
+    args = (["-a"] if mode == "aa" else []) + flags + ["-D", data, "-q", q]
+    o, j = _both(oracle, pin, java, args, str(d), f"{mode}_{'_'.join(flags)}")
+    assert j == o
+    assert o.count("\nCALL\t") > (30 if mode == "aa" else 15) and o.count("OTU-COUNTS") == (150 if mode == "aa" else 1)
+
+
+def test_duplicate_ids_and_odd_fasta(oracle, pin, java, small_c0):
+    """Q10 (LinkedHashMap: first position, last length, last container), Q11 (lines are appended untrimmed), Q2 (lower case is
+    invalid), \\r\\n and blank lines: the same report from both"""
+    dirs, faa, fna, d = small_c0
+    data = dirs["aa"][0]
+    ids, descr, seqs = synth.read_fasta_simple(faa)
+    s = [x.decode() for x in seqs]
+    text = (f">{ids[0]} first copy\n{s[0]}\n>{ids[1]}\r\n{s[1][:80]} \r\n{s[1][80:]}\r\n\n>{ids[0]} second copy, shorter\n{s[2]}\n"
+            f"  >{ids[3]}\tx\n\n \n{s[3].lower()}\n{s[3]}\n>{ids[4]}\n{s[4][:50]}X{s[4][51:]}\n")
+    q = str(d / "odd.faa")
+    open(q, "w", newline="").write(text)
+    for flags in ([], ["-d"]):
+        o, j = _both(oracle, pin, java, ["-a"] + flags + ["-D", data, "-q", q], str(d), "odd" + "".join(flags))
+        assert j == o
+        assert o.count("PROTEIN-ID") == 4 and f"PROTEIN-ID\t{ids[0]}\t{len(s[2])}\n" in o
+
+
+def _write_dir(d, img, nfun):
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "kmer.table.mem_map"), "wb").write(img)
+    synth.write_function_index(d, [f"FUNC_{i:03d}" for i in range(nfun)])
+    return d
+
+
+def test_lookup_on_malformed_tables(oracle, pin, java, tmp_path):
+    """KGJ:959-1026 where it is most delicate: a key outside its probe chain (never found), a repeated key (the first copy
+    wins), an occupied-but-unmatchable slot (20^8: extends chains), and a chain that runs off the end of the file
+    (EOFException -> lookup aborted, earlier hits kept, `Error: null` in the -d report; KGJ:799-802, 1102-1103)."""
+    prot = b"MKVLAAGIVGLCAHHHWYYRRDDEEFFGGHHIIKKLLMMNNPPQQ"
+    wk = synth.window_keys(synth.aa_codes(prot))
+    n = len(wk)
+    img = bytearray(synth.build_table_image(wk, np.arange(n), np.arange(n) + 100, np.full(n, 5), np.ones(n, np.float32), num_slots=211))
+    ent = np.frombuffer(img, dtype=synth.ENTRY_DTYPE, offset=24)
+    occ = np.flatnonzero(ent["which"] <= synth.MAX_ENCODED)
+    empty = np.flatnonzero(ent["which"] > synth.MAX_ENCODED)
+    victim = occ[3]
+    far = [e for e in empty if e > 0 and e + 1 < 211 and ent["which"][e - 1] > synth.MAX_ENCODED and ent["which"][e + 1] > synth.MAX_ENCODED
+           and e != ent["which"][victim] % 211][0]
+    ent[far] = ent[victim]
+    ent["which"][victim] = synth.EMPTY_KEY
+    dup = [s for s in occ if s != victim and s + 1 < 210 and ent["which"][s + 1] > synth.MAX_ENCODED and s + 1 != far][0]
+    ent[dup + 1] = ent[dup]
+    ent["fi"][dup + 1] = 99
+    um = [e for e in empty if e not in (far, dup + 1) and e + 1 < 211][-1]
+    ent["which"][um] = synth.MAX_ENCODED
+    d1 = _write_dir(str(tmp_path / "malformed"), bytes(img), 100)
+    q = str(tmp_path / "q.faa")
+    synth.write_fasta(q, ["p1", "p2"], [prot, prot[5:] + prot[:9]])
+    for flags in (["-m", "2"], ["-d", "-m", "2"]):
+        o, j = _both(oracle, pin, java, ["-a"] + flags + ["-D", d1, "-q", q], str(tmp_path), "mal" + "".join(flags))
+        assert j == o
+        assert "CALL\t" in o and "\t99\t" not in o
+    # the chain that runs off the end of the file
+    prot2 = b"MKVLAAGIVGLCAHHHWYYRR"
+    keys = synth.window_keys(synth.aa_codes(prot2))
+    m = len(keys)
+    good = synth.build_table_image(keys, np.zeros(m), np.zeros(m), np.ones(m), np.ones(m, np.float32), num_slots=101)
+    ent2 = np.frombuffer(good, dtype=synth.ENTRY_DTYPE, offset=24).copy()
+    ent2["which"][100] = 12345
+    probe = (20 ** 8 - 1) - ((20 ** 8 - 1 - 100) % 101)
+    codes, v = [], probe
+    for _ in range(8):
+        codes.append(v % 20)
+        v //= 20
+    seq2 = bytes(synth.PROT_ALPHA[c].encode()[0] for c in reversed(codes)) + b"A"
+    d2 = _write_dir(str(tmp_path / "eof"), good[:24] + ent2.tobytes(), 2)
+    q2 = str(tmp_path / "q2.faa")
+    synth.write_fasta(q2, ["whole", "runs_off_the_end"], [prot2, seq2])
+    for flags in (["-m", "2"], ["-d", "-m", "2"]):
+        o, j = _both(oracle, pin, java, ["-a"] + flags + ["-D", d2, "-q", q2], str(tmp_path), "eof" + "".join(flags))
+        assert j == o
+    assert "Error: null" in o and "CALL\t" in o
+
+
+def test_read_fasta_fuzz(oracle, java, tmp_path):
+    """readFasta (KGJ:1132-1192) on adversarial text -- blank lines, lines of blanks, blanks before '>', a lone '>', \\r and
+    \\r\\n, captions without a sequence, text before the first caption: same records or the same first error as the oracle's
+    reader (which tests/test_host.py in turn holds the product's multi-threaded reader to)."""
+    from tests.test_host import _oracle_fasta
+    mod, rt, _ = java
+    rng = np.random.default_rng(11)
+    caps = [b">id%d desc\n", b"  >sp%d\tx y\n", b">dup\n", b">id%d\r\n", b">\t id%d  two  words \n"]
+    seqs = [b"ACDEFGHIK\n", b"LMNP QRST \r\n", b"VWY\r", b"A\n", b"XX>notcaption\n", b"ACGT" * 30 + b"\n", b"\x0bAC\x0c\n"]
+    blanks = [b" \n", b"\n", b"  \t \n", b">\n", b"\r\n", b"\x01\n"]
+    n_err = n_ok = 0
+
+    class Collect(rt.JObject):
+        def __init__(self):
+            self.rec = []
+
+        def nextEntry(self, id_, seq, descr):
+            self.rec.append((id_, seq, descr))
+
+    for trial in range(150):
+        parts = []
+        for r in range(int(rng.integers(1, 20))):
+            c = caps[int(rng.integers(0, len(caps)))]
+            parts.append(c % (100 * trial + r) if b"%d" in c else c)
+            while rng.random() < 0.3:
+                parts.append(blanks[int(rng.integers(0, len(blanks)))])
+            if rng.random() < 0.97:
+                for _ in range(int(rng.integers(1, 5))):
+                    parts.append(seqs[int(rng.integers(0, len(seqs)))])
+                    if rng.random() < 0.2:
+                        parts.append(blanks[int(rng.integers(0, 3))])
+        body = b"".join(parts)
+        if trial % 10 == 0:
+            body = b"garbage before the first caption\n" + body
+        if trial % 7 == 0:
+            body = b"\n \nA\n" + body
+        if trial % 9 == 0 and body.endswith(b"\n"):
+            body = body[:-1]
+        path = str(tmp_path / f"fz{trial}.fa")
+        open(path, "wb").write(body)
+        want = _oracle_fasta(oracle, path)
+        cb = Collect()
+        try:
+            mod.KmerGutsJava.readFasta(rt.BufferedReader(rt.FileReader(rt.File(path))), cb)
+            got = cb.rec
+        except rt.IllegalStateException as e:
+            got = e.getMessage()
+        if isinstance(want, str):
+            assert got == want, (trial, body)
+            n_err += 1
+        else:
+            assert isinstance(got, list), (trial, got, body)
+            assert [g[0] for g in got] == want[0], (trial, body)
+            assert "".join(g[1] for g in got).encode("latin-1") == bytes(want[1]), (trial, body)
+            assert np.array_equal(np.cumsum([0] + [len(g[1]) for g in got]), want[2]), (trial, body)
+            n_ok += 1
+    assert n_err > 15 and n_ok > 40
+
+
+def test_function_index_reader(java, tmp_path):
+    """loadIndexedArray, KGJ:345-373"""
+    mod, rt, _ = java
+    p = tmp_path / "function.index"
+    p.write_text("0\thypothetical protein\n1\tDNA polymerase (EC 2.7.7.7)\n2\t\n")
+    names = mod.KmerGutsJava.loadIndexedArray(rt.File(str(p)))
+    assert [names.get(i) for i in range(names.size())] == ["hypothetical protein", "DNA polymerase (EC 2.7.7.7)", ""]
+    p.write_text("0\ta\n2\tb\n")
+    with pytest.raises(rt.IllegalStateException) as e:
+        mod.KmerGutsJava.loadIndexedArray(rt.File(str(p)))
+    assert e.value.getMessage() == "Your index must be dense and in order (see line 1)"
+
+
+def test_the_tool_refuses_what_it_does_not_model():
+    """j2py.py must fail loudly on Java it has no rule for, never guess"""
+    j2py = _load("j2py", os.path.join(ROOT, "tests", "java_pin", "j2py.py"))
+    for bad in ("class A { void f() { outer: for (;;) { break outer; } } }",
+                "class A { void f() { try (java.io.Reader r = null) { } } }",
+                "class A { <T> T f(T x) { return x; } }",
+                "class A { void f(int x) { switch (x) { default: return; case 1: return; } } }",
+                "class A { void f(int[] a, int i) { int y = a[i]++ + 1; } }"):
+        with pytest.raises(j2py.ParseError):
+            j2py.transliterate(bad)
+    # and a few constructs it does model, checked against hand-computed Java results
+    src = """class T {
+      static int wrap() { int x = 2147483647; x += 1; return x; }
+      static long mix(int a) { long v = 0; for (int i = 0; i < 5; i++) { if (i == 2) continue; v = v * 31 + (a << i); } return v; }
+      static int div() { return (-7) / 2 * 10 + (-7) % 3; }
+      static float fsum() { float s = 0; for (int i = 0; i < 10; i++) s += 0.1f; return s; }
+      static int sw(char c) { int r = 0; switch (c) { case 'a': r += 1; case 'b': r += 10; break; case 'c': r += 100; default: r += 1000; } return r; }
+      static int post() { int i = 3; int[] a = new int[8]; a[i++] = i; a[i--] = i + 10; return a[3] * 100 + a[4] + i; }
+      static String cat(int n) { return "n=" + n + 1 + (n + 1) + 'c' + 1.5 + null + true; }
+    }"""
+    ns = {}
+    sys.path.insert(0, os.path.join(ROOT, "tests", "java_pin"))
+    exec(j2py.transliterate(src), ns)
+    T = ns["T"]
+    assert T.wrap() == -2147483648
+    assert T.mix(3) == ((((3 << 0) * 31 + (3 << 1)) * 31 + (3 << 3)) * 31 + (3 << 4))
+    assert T.div() == -31
+    assert T.fsum() == float(np.float32(sum([np.float32(0.1)] * 10, np.float32(0))))
+    assert [T.sw(c) for c in "abcd"] == [11, 10, 1100, 1000]
+    assert T.post() == 4 * 100 + 13 + 3   # the index is evaluated before the right-hand side
+    assert T.cat(4) == "n=415c1.5nulltrue"
