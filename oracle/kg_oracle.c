@@ -1,10 +1,18 @@
 /*
  * oracle/kg_oracle.c -- CPU restatement of KmerGutsJava's hot path (plain C).
  *
- * TEST INFRASTRUCTURE ONLY (see kg_oracle.h).  PARITY UNPINNED: the reference
- * holds no golden vectors for this path and cannot be run here (no JVM); the
- * pins are the hand-traced KATs in tests/golden/, the independent Python
- * restatement in oracle/kg_oracle_py.py and stream-join == direct-probe.
+ * TEST INFRASTRUCTURE ONLY (see kg_oracle.h).  PARITY PIN: the reference
+ * holds no golden vectors for this path and no JVM exists in the build image,
+ * so the reference's OWN SOURCE is executed instead: tests/java_pin/j2py.py
+ * transliterates the unmodified KmerGutsJava.java into Python statement by
+ * statement (it knows Java syntax and arithmetic, nothing about k-mers) and
+ * the reports KmerGutsJava.main writes that way for the eight configs[0] runs
+ * are byte-identical to this oracle's (tests/golden/java_transliteration_pin.json,
+ * tests/test_java_transliteration.py, tests/test_oracle_golden.py).  Still
+ * never run on a real JVM: tests/java_pin/pin_oracle.sh is the one command
+ * for that.  Further pins: the hand-traced KATs in tests/golden/, the
+ * independent Python restatement in oracle/kg_oracle_py.py, stream-join ==
+ * direct-probe.
  *
  * Every function cites the lines of lib/src/kmergutsjava/KmerGutsJava.java
  * ("KGJ") it restates.  Structure follows the reference's call order:

@@ -6,14 +6,20 @@
  * cpu_baseline / --impl reference legs use it, and only as the checker or as
  * the timed CPU baseline -- never as a product path.
  *
- * PARITY UNPINNED: the reference (lib/src/kmergutsjava/KmerGutsJava.java,
- * "KGJ" below) ships no k-mer table, no golden output and no asserting test
+ * PARITY PIN: the reference (lib/src/kmergutsjava/KmerGutsJava.java, "KGJ"
+ * below) ships no k-mer table, no golden output and no asserting test
  * (test/src/kmergutsjava/test/KmerGutsJavaServerTest.java:76-86), and no JVM
- * exists in this image, so this restatement cannot be checked against outputs
- * of the reference itself.  It is pinned instead by (i) hand-traced
- * known-answer vectors (tests/golden/), (ii) an independently written pure
- * Python restatement (oracle/kg_oracle_py.py) and (iii) the equality of its
- * two lookup variants (sort-merge stream join == direct probe).
+ * exists in this image.  What is checked against the reference ITSELF: its
+ * unmodified source, transliterated statement by statement into Python by
+ * tests/java_pin/j2py.py (a Java-syntax tool that knows nothing about k-mers)
+ * and executed, writes reports byte-identical to this restatement's for the
+ * eight configs[0] runs, malformed tables, odd FASTA text and the FSM vectors
+ * (tests/test_java_transliteration.py; full-size record:
+ * tests/golden/java_transliteration_pin.json).  NOT yet run on a real JVM
+ * (tests/java_pin/pin_oracle.sh does that in one command).  Further pins:
+ * (i) hand-traced known-answer vectors (tests/golden/), (ii) an independently
+ * written pure Python restatement (oracle/kg_oracle_py.py), (iii) the equality
+ * of the two lookup variants (sort-merge stream join == direct probe).
  */
 #ifndef KG_ORACLE_H
 #define KG_ORACLE_H

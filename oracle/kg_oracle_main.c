@@ -1,6 +1,7 @@
 /*
  * oracle/kg_oracle_main.c -- command line of the CPU oracle, mirroring KmerGutsJava.main (KGJ:560-654).
- * TEST INFRASTRUCTURE ONLY (see kg_oracle.h).  PARITY UNPINNED (no reference golden output exists).
+ * TEST INFRASTRUCTURE ONLY (see kg_oracle.h).  PARITY PIN: see kg_oracle.c (the reference's own source,
+ * executed through tests/java_pin/j2py.py, writes byte-identical reports; no JVM run yet).
  *
  *   kmer_guts_oracle [-a] [-d] [-m N] [-M N] [-O] [-g N] -D DataDir -q query.fasta[.gz] [-o out] [-V direct|stream]
  *

@@ -1,7 +1,7 @@
 """oracle/kg_oracle_py.py -- second, independently written restatement of KmerGutsJava's hot path.
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED: the reference ships no golden vectors for this path and cannot be run
-in this image (no JVM).  This file exists so that the C oracle (oracle/kg_oracle.c) is checked by something that
+TEST INFRASTRUCTURE ONLY.  The reference ships no golden vectors for this path and cannot be run in this image (no JVM;
+its source IS executed through tests/java_pin/j2py.py, see oracle/kg_oracle.h).  This file exists so that the C oracle (oracle/kg_oracle.c) is checked by something that
 was written separately from it, in a different style (pure Python objects, dictionary probe chains), directly from
 lib/src/kmergutsjava/KmerGutsJava.java ("KGJ").  Pure-Python loops: small cases only.
 """

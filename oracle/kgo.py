@@ -1,7 +1,7 @@
 """oracle/kgo.py -- ctypes loader for the C oracle (oracle/kg_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs, never by kmergutsjava_b200/.  PARITY UNPINNED (see oracle/kg_oracle.h).
+--impl reference legs, never by kmergutsjava_b200/.  Parity pin: see oracle/kg_oracle.h (the reference's own source executed through tests/java_pin/j2py.py).
 """
 from __future__ import annotations
 

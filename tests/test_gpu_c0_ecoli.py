@@ -74,6 +74,19 @@ def test_c0_reports_identical(kg, oracle, c0, tmp_path, mode, flags):
     if a != b:
         bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:5]
         raise AssertionError(f"{len(bad)}+ differing lines, first: {bad}")
+    if not small:
+        # ... and, without the oracle in between: the GPU report hashes to the value committed under tests/golden/, which is
+        # what the reference's own Java source wrote for this run when it was executed through tests/java_pin/ (a JVM via
+        # pin_oracle.sh, or the mechanical transliteration recorded in tests/golden/java_transliteration_pin.json)
+        import hashlib
+        import json
+        golden = os.path.join(os.path.dirname(__file__), "golden")
+        name = {(): "default", ("-O",): "order"}.get(tuple(flags), "m3g50M2")
+        want = json.load(open(os.path.join(golden, "c0_report_sha256.json")))[f"{mode}_{name}"]
+        assert hashlib.sha256("".join(x + "\n" for x in b).encode()).hexdigest() == want
+        rec = os.path.join(golden, "java_transliteration_pin.json")
+        if os.path.exists(rec):
+            assert json.load(open(rec))["reports"][f"{mode}_{name}"] == want
 
 
 def test_c0_library_level(kg, oracle, c0):

@@ -43,3 +43,20 @@ def test_kat_text_for_the_java_driver(tmp_path):
     src = open(os.path.join(ROOT, "tests", "java_pin", "GoldenDump.java")).read()
     for name in ("gatherHits", "tabulateOtuDataForContig", "minHits", "maxGap", "minWeightedHits", "orderConstraint", "KmerGutsJava.main"):
         assert name in src
+
+
+def test_transliterated_java_reports_are_the_committed_hashes():
+    """tests/golden/java_transliteration_pin.json records what the reference's unmodified Java source printed for the eight
+    configs[0] runs when tests/java_pin/transliterated_pin.py executed it (mechanical Java -> Python transliteration; the image
+    has no JVM): every report must be the one the oracle hashes to, i.e. the value every GPU-vs-oracle test is pinned to."""
+    import hashlib
+    pin = _pin()
+    rec = json.load(open(os.path.join(ROOT, "tests", "golden", "java_transliteration_pin.json")))
+    want = json.load(open(pin.GOLDEN))
+    assert rec["compare_exit_code"] == 0
+    assert set(rec["reports"]) == {k for k in want if k not in ("kmer.table.mem_map", "function.index")} and len(rec["reports"]) == 8
+    assert all(rec["reports"][k] == want[k] for k in rec["reports"])
+    assert rec["fsm_kats_sha256"] == hashlib.sha256(pin.expected_kat_text().encode()).hexdigest()
+    java = os.path.join(os.environ.get("KG_REFERENCE", "/root/reference"), "lib", "src", "kmergutsjava", "KmerGutsJava.java")
+    if os.path.exists(java):   # the record was made from exactly the source that is here
+        assert hashlib.sha256(open(java, encoding="utf-8").read().encode()).hexdigest() == rec["java_source_sha256"]

@@ -1,5 +1,6 @@
 """The CPU oracle against the hand-traced known-answer vectors (tests/golden/fsm_kats.json) and the scalar KATs of
-SURVEY.md section 8(c).  The reference has no golden vectors for this path (parity unpinned); these are the pins."""
+SURVEY.md section 8(c).  The reference has no golden vectors for this path ; these are hand-traced pins (the reference's own source reproduces them through
+tests/java_pin/j2py.py: tests/test_java_transliteration.py)."""
 import json
 import os
 
