@@ -319,3 +319,78 @@ def test_the_tool_refuses_what_it_does_not_model():
     assert [T.sw(c) for c in "abcd"] == [11, 10, 1100, 1000]
     assert T.post() == 4 * 100 + 13 + 3   # the index is evaluated before the right-hand side
     assert T.cat(4) == "n=415c1.5nulltrue"
+
+
+def _java_fsm(java, flags, hits_rec):
+    """gatherHits (KGJ:457) + tabulateOtuDataForContig (KGJ:516) of the transliterated source on one container -> the text"""
+    import io
+    mod, rt, _ = java
+    k = mod.KmerGutsJava()
+    k.minHits, k.maxGap = flags.get("min_hits", 5), flags.get("max_gap", 200)
+    k.minWeightedHits, k.orderConstraint = flags.get("min_weighted_hits", 0), bool(flags.get("order_constraint", False))
+    lst, max_fi = rt.ArrayList(), 0
+    for h in hits_rec:
+        x = mod.Hit()
+        x.from0InProt, x.fI, x.oI, x.avgOffFromEnd, x.functionWt = int(h["pos"]), int(h["fI"]), int(h["oI"]), int(h["avg"]), float(h["wt"])
+        max_fi = max(max_fi, x.fI)
+        lst.add(x)
+    buf = io.StringIO()
+    pw = rt.PrintWriter(buf)
+    k.gatherHits(0, "+", 0, lst, rt.ArrayList(["F%d" % i for i in range(max_fi + 1)]), otu := rt.ArrayList(), pw)
+    k.tabulateOtuDataForContig("x", 0, otu, pw)
+    return buf.getvalue()
+
+
+def _oracle_fsm_text(oracle, flags, hits_rec):
+    calls, otu = oracle.gather_hits(oracle.make_params(aa=True, **flags), hits_rec, max_calls=1 << 16)
+    out = [f"CALL\t{int(c['start'])}\t{int(c['end'])}\t{int(c['count'])}\t{int(c['fI'])}\tF{int(c['fI'])}\t"
+           f"{oracle.java_format_f(float(c['weighted']))}\n" for c in calls]
+    k = int(otu["n"][0])
+    out.append("OTU-COUNTS\tx[0]" + "".join(f"\t{int(otu['count'][0][j])}-{int(otu['oI'][0][j])}" for j in range(k)) + "\n")
+    return "".join(out)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fsm_fuzz_java_source_vs_oracle(oracle, java, seed):
+    """Random adversarial hit lists (runs of one function, pair switches, singletons, gaps around max_gap, ties in the OTU
+    counts, order-constraint offsets, fp32 weights) through the SOURCE's gatherHits / processSetOfHits and through the oracle's:
+    the printed CALL and OTU-COUNTS lines must be the same text (the generator is test_oracle_cross's)."""
+    rng = np.random.default_rng(900 + seed)
+    for case in range(30):
+        n = int(rng.integers(0, 140))
+        pos = np.sort(rng.choice(3000, size=n, replace=False)) if n else np.zeros(0, int)
+        if case % 3 == 0 and n:
+            pos = np.unique(np.cumsum(rng.choice([1, 1, 2, 5, 190, 200, 201, 230], size=n)))
+            n = len(pos)
+        fI = rng.integers(1, 4, size=n)
+        for i in range(1, n):
+            if rng.random() < 0.7:
+                fI[i] = fI[i - 1]
+        oI = rng.integers(0, 8, size=n)
+        avg = (3000 - pos + rng.integers(-25, 25, size=n)) if n else np.zeros(0, int)
+        wt = (rng.integers(1, 600, size=n) / 256.0).astype(np.float32)
+        if case % 5 == 1:
+            wt = rng.random(n).astype(np.float32)   # weights that are not dyadic: the fp32 sum and its %f rounding matter
+        flags = dict(order_constraint=bool(rng.integers(2)), min_hits=int(rng.integers(2, 7)), min_weighted_hits=int(rng.integers(0, 4)),
+                     max_gap=int(rng.choice([0, 5, 50, 200, 1000])))
+        hits = np.zeros(n, dtype=oracle.HIT_DTYPE)
+        hits["pos"], hits["fI"], hits["oI"], hits["avg"], hits["wt"] = pos, fI, oI, avg, wt
+        assert _java_fsm(java, flags, hits) == _oracle_fsm_text(oracle, flags, hits), (seed, case, flags)
+
+
+def test_open_run_cap_java_source_vs_oracle(oracle, java):
+    """Q9 (KGJ:496-504): MAX_HITS_PER_SEQ - 2 = 39998 hits in an open run; later hits are not appended, yet the pair-switch test
+    still runs on them -- 41 000 hits of one function, then a foreign pair, then a new run"""
+    n = 41000
+    hits = np.zeros(n + 12, dtype=oracle.HIT_DTYPE)
+    hits["pos"] = np.arange(n + 12)
+    hits["fI"][:n] = 7
+    hits["fI"][n:n + 2] = 9
+    hits["fI"][n + 2:] = 7
+    hits["oI"] = np.arange(n + 12) % 3
+    hits["avg"] = 50000 - np.arange(n + 12)
+    hits["wt"] = np.float32(0.5)
+    for flags in (dict(), dict(order_constraint=True)):
+        want = _oracle_fsm_text(oracle, flags, hits)
+        assert "\t39998\t7\t" in want
+        assert _java_fsm(java, flags, hits) == want
