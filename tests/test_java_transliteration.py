@@ -85,7 +85,8 @@ def _both(oracle, pin, java, args, out_dir, tag):
 def test_scalar_helpers_and_tables(oracle, java):
     """KGJ:85-99, 111-175, 177-272, 274-318 against the oracle's C restatements, every byte value"""
     K = java[0].KmerGutsJava
-    L = oracle.lib()
+    L = C.CDLL(oracle.lib()._name)   # a private handle: the argtypes set below must not leak into other tests' calls
+    L.kgo_to_amino_acid_off.restype = L.kgo_compl.restype = L.kgo_dna_char.restype = C.c_int
     assert (K.K, K.CORE, K.MAX_ENCODED, K.MAX_HITS_PER_SEQ, K.OI_BUFSZ, K.VERSION) == (8, 20 ** 7, 20 ** 8, 40000, 5, 1)
     L.kgo_genetic_code.restype = C.c_char
     assert [c for c in K.GENETIC_CODE] == [L.kgo_genetic_code(i).decode() for i in range(64)]
