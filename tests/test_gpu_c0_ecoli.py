@@ -89,6 +89,32 @@ def test_c0_reports_identical(kg, oracle, c0, tmp_path, mode, flags):
             assert json.load(open(rec))["reports"][f"{mode}_{name}"] == want
 
 
+def test_reports_equal_the_java_written_goldens(kg, tmp_path):
+    """No oracle in this one: tests/golden/java_reports/*.txt were written by the reference's own Java source (executed through
+    tests/java_pin/j2py.py, see make_small_goldens.py); the inputs are rebuilt from the committed E. coli fixtures (hashes in
+    the manifest) and the product's command line must write the same text, byte for byte."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_small_goldens", os.path.join(os.path.dirname(__file__), "java_pin", "make_small_goldens.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    manifest = json.load(open(os.path.join(g.OUT, "manifest.json")))
+    inputs, shas = g.small_inputs(str(tmp_path))
+    assert shas == manifest["inputs"]
+    n = 0
+    for item, args in g.runs(inputs):
+        out = str(tmp_path / (item + ".gpu.txt"))
+        r = subprocess.run([kg.CLI_PATH, *args, "-o", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        want = open(os.path.join(g.OUT, item + ".txt"), newline="").read()
+        got = g.strip(open(out, errors="replace").read())
+        if got != want:
+            bad = [(i, x, y) for i, (x, y) in enumerate(zip(want.splitlines(), got.splitlines())) if x != y][:3]
+            raise AssertionError(f"{item}: {len(want.splitlines())} vs {len(got.splitlines())} lines; first differences (java, gpu): {bad}")
+        n += 1
+    assert n == 6
+
+
 def test_c0_library_level(kg, oracle, c0):
     ctx = kg.Context(0)
     table = ctx.load_table(c0)

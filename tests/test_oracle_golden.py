@@ -60,3 +60,25 @@ def test_transliterated_java_reports_are_the_committed_hashes():
     java = os.path.join(os.environ.get("KG_REFERENCE", "/root/reference"), "lib", "src", "kmergutsjava", "KmerGutsJava.java")
     if os.path.exists(java):   # the record was made from exactly the source that is here
         assert hashlib.sha256(open(java, encoding="utf-8").read().encode()).hexdigest() == rec["java_source_sha256"]
+
+
+def test_oracle_writes_the_java_written_golden_reports(tmp_path):
+    """tests/golden/java_reports/*.txt were written by the reference's own source (tests/java_pin/make_small_goldens.py); the
+    inputs are rebuilt here from the committed E. coli fixtures (their hashes are in the manifest) and the oracle must write
+    the same texts.  The GPU suite diffs the product's reports against the same files."""
+    from oracle import kgo
+    spec = importlib.util.spec_from_file_location("make_small_goldens", os.path.join(ROOT, "tests", "java_pin", "make_small_goldens.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    kgo.build()
+    manifest = json.load(open(os.path.join(g.OUT, "manifest.json")))
+    inputs, shas = g.small_inputs(str(tmp_path))
+    assert shas == manifest["inputs"]
+    items = list(g.runs(inputs))
+    assert [i for i, _ in items] == sorted(manifest["reports"], key=[i for i, _ in items].index) and len(items) == 6
+    for item, args in items:
+        out = str(tmp_path / (item + ".txt"))
+        kgo.run_cli(args + ["-o", out])
+        want = open(os.path.join(g.OUT, item + ".txt"), newline="").read()
+        assert g.strip(open(out, errors="replace").read()) == want, item
+        assert want.count("\nCALL\t") >= 50
