@@ -395,3 +395,42 @@ def test_open_run_cap_java_source_vs_oracle(oracle, java):
         want = _oracle_fsm_text(oracle, flags, hits)
         assert "\t39998\t7\t" in want
         assert _java_fsm(java, flags, hits) == want
+
+
+SYN_FLAGS = [[], ["-O"], ["-m", "3", "-g", "50", "-M", "2"], ["-m", "2", "-g", "5"], ["-d", "-m", "4"]]
+
+
+@pytest.fixture(scope="module")
+def synthetic(tmp_path_factory):
+    """A seeded synthetic universe (tools/kg_synth: 60 families, homologs with substitutions, decoys, X) as KmerData + FASTA,
+    with the edge sequences of SURVEY 8(c): shorter than / exactly K and K+1 residues, lower case, X and *, DNA shorter than a
+    codon, lower-case DNA, U for T, IUPAC codes."""
+    d = tmp_path_factory.mktemp("syn")
+    u = synth.Universe(n_families=60, seed=0x4B470001)
+    keys, otu, avg, fi, wt = u.signatures()
+    data = _write_dir(str(d / "KmerData"), synth.build_table_image(keys, otu, avg, fi, wt), int(fi.max()) + 1)
+    prots = u.proteins(40, seed=5) + [b"A", b"ACDEFGH", b"ACDEFGHI", b"ACDEFGHIK", b"acdefghiklmnp", b"ACDEFGHIKXLMNPQRSTVWY*ACDEFGHIK"]
+    prots.append(u.proteins(1, seed=6)[0].lower() + u.proteins(1, seed=6)[0])
+    faa = str(d / "q.faa")
+    synth.write_fasta(faa, [f"p{i}" for i in range(len(prots))], prots)
+    g0, g1 = synth.genome(u, 6000, seed=7, index=0), synth.genome(u, 6000, seed=7, index=1)
+    iupac = bytearray(synth.genome(u, 3001, seed=8))
+    for i, c in zip(range(50, 3000, 97), b"NRYKMSWBDHVnrykmswbdhv-*" * 2):
+        iupac[i] = c
+    dnas = [g0, g1.lower(), g0.replace(b"T", b"U"), bytes(iupac), b"AC", b"ATG", b"ATGAAACCCGGGTTTACGTACGTAGCTAGCTAGCATCGATCGAT",
+            synth.genome(u, 3002, seed=9)]
+    fna = str(d / "q.fna")
+    synth.write_fasta(fna, [f"c{i}" for i in range(len(dnas))], dnas)
+    return data, faa, fna, d
+
+
+@pytest.mark.parametrize("flags", SYN_FLAGS, ids=lambda f: "_".join(f) or "default")
+@pytest.mark.parametrize("mode", ["aa", "dna"])
+def test_synthetic_universe_reports(oracle, pin, java, synthetic, mode, flags):
+    data, faa, fna, d = synthetic
+    args = (["-a"] if mode == "aa" else []) + flags + ["-D", data, "-q", faa if mode == "aa" else fna]
+    o, j = _both(oracle, pin, java, args, str(d), f"syn_{mode}_{'_'.join(flags)}")
+    assert j == o
+    assert o.count("\nCALL\t") > 5
+    if mode == "dna":
+        assert all(f"\t{s}\t{f}\n" in o for s in "+-" for f in range(3))
