@@ -434,3 +434,64 @@ def test_synthetic_universe_reports(oracle, pin, java, synthetic, mode, flags):
     assert o.count("\nCALL\t") > 5
     if mode == "dna":
         assert all(f"\t{s}\t{f}\n" in o for s in "+-" for f in range(3))
+
+
+def test_runtime_follows_the_java_api():
+    """Spot checks of tests/java_pin/j2py_runtime.py against behaviour the Java API documents (values below are what a JVM
+    prints / throws; none of this needs the reference checkout, but the module is skipped as a whole without it)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "java_pin"))
+    import j2py_runtime as rt
+    f32 = rt._f32
+    # Formatter %f: float widened to double, shortest repr, HALF_UP  (C's printf gives 0.007812 for the first one)
+    assert rt.String.format_("%f", 0.0078125) == "0.007813"
+    assert rt.String.format_("%f", f32(1.0000001)) == "1.000000" and rt.String.format_("%f", f32(0.1) * 1) == "0.100000"
+    assert rt.String.format_("%f", 2.5) == "2.500000" and rt.String.format_("%f", 0) == "0.000000"
+    assert rt.String.format_("%1.3f", f32(0.0005)) == "0.001" and rt.String.format_("%1.3f", 1.0005) == "1.001"   # 1.0005 is 1.000499999999999989... in binary: HALF_UP works on the DECIMAL repr
+    assert rt.String.format_("%1.3f", -0.25) == "-0.250"
+    assert rt.String.format_("CALL\t%d\t%s\t%c|%5d|%-4s|%%", 7, None, "x", 42, "ab") == "CALL\t7\tnull\tx|   42|ab  |%"
+    # int / long / float arithmetic
+    assert rt._i32(0x7FFFFFFF + 1) == -0x80000000 and rt._i64(2 ** 63) == -2 ** 63 and rt._i8(200) == -56
+    assert rt._idiv(-7, 2) == -3 and rt._idiv(7, -2) == -3 and rt._rem(-7, 3) == -1 and rt._rem(7, -3) == 1
+    assert rt._cast_int(3.99) == 3 and rt._cast_int(-3.99) == -3 and rt._cast_int(1e20) == 0x7FFFFFFF and rt._cast_int(float("nan")) == 0
+    assert rt._cast_long(0xFF) << 56 == 0xFF << 56 and rt._i64(0xFF << 56) == -(1 << 56)
+    with pytest.raises(rt.ArithmeticException):
+        rt._rem(5, 0)
+    assert rt.Float.intBitsToFloat(0x3F000000) == 0.5 and rt.Float.intBitsToFloat(-1) != rt.Float.intBitsToFloat(-1)   # NaN
+    assert rt.Math.abs_(-0x80000000) == -0x80000000 and rt.Math.abs_(-5) == 5
+    # String
+    assert rt._s_trim("\x00\t a b \r\n\x1f") == "a b" and rt._s_trim(" x") == " x"   # only <= U+0020 goes
+    assert rt._cat("n=", 1.0) == "n=1.0" and rt._cat("x", 1e7) == "x1.0E7" and rt._cat(None, True) == "nulltrue"
+    with pytest.raises(rt.StringIndexOutOfBoundsException):
+        rt._s_substring("abc", 0, -1)
+    assert rt._s_hashCode("hello") == 99162322 and rt._s_hashCode("polygenelubricants") == -0x80000000
+    st = rt.StringTokenizer(" a\tb  c ", " \t")
+    assert [st.nextToken() for _ in range(3)] == ["a", "b", "c"] and not st.hasMoreTokens()
+    for bad in ("", " 1", "1 ", "1.0", "2147483648", None):
+        with pytest.raises(rt.NumberFormatException):
+            rt.Integer.parseInt(bad)
+    assert rt.Integer.parseInt("-2147483648") == -0x80000000 and rt.Integer.parseInt("+7") == 7
+    # collections
+    a = rt.ArrayList()
+    a.add("x")
+    for i in (-1, 1):
+        with pytest.raises(rt.IndexOutOfBoundsException):
+            a.get(i)
+    m = rt.LinkedHashMap()
+    for k, v in (("b", 1), ("a", 2), ("b", 3)):
+        m.put(k, v)
+    assert [k for k in m.keySet()] == ["b", "a"] and m.get("b") == 3 and m.get("zz") is None   # re-insertion keeps the place
+    lst = rt.ArrayList([3, 1, 2, 1])
+
+    class ByParity(rt.JObject):
+        def compare(self, x, y):
+            return rt.Integer.compare(x % 2, y % 2)
+    rt.Collections.sort(lst, ByParity())
+    assert list(lst) == [2, 3, 1, 1]   # stable
+    # BufferedReader.readLine: \n, \r and \r\n end a line; no empty line after a final terminator
+    br = rt.BufferedReader(rt.InputStreamReader(rt.InputStream(b"a\nb\r\nc\rd\n\n e ")))
+    lines = []
+    while (line := br.readLine()) is not None:
+        lines.append(line)
+    assert lines == ["a", "b", "c", "d", "", " e "]
+    s = rt.InputStream(bytes([1, 255]))
+    assert [s.read(), s.read(), s.read()] == [1, 255, -1] and rt.InputStream(b"abcdef").skip(10) == 6
