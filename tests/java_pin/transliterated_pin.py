@@ -21,7 +21,6 @@ import hashlib
 import importlib.util
 import json
 import os
-import struct
 import subprocess
 import sys
 import time
