@@ -175,6 +175,42 @@ def test_packed_first_call_with_overflowing_slice(kg, oracle, universe, monkeypa
 KATS = json.load(open(os.path.join(GOLD, "fsm_kats.json")))
 
 
+JAVA_VECTORS = json.load(open(os.path.join(GOLD, "java_fsm_vectors.json")))["vectors"]
+
+
+@pytest.mark.parametrize("fsm", ["seq", "seg"])
+def test_fsm_vectors_printed_by_the_java_source_on_gpu(kg, ctx, fsm, monkeypatch):
+    """No oracle in this one: the 64 vectors of tests/golden/java_fsm_vectors.json carry the CALL / OTU-COUNTS lines the
+    reference's own Java source printed for them (tests/java_pin/make_fsm_vectors.py).  Each vector becomes a random protein
+    whose windows at the vector's positions are the only table entries; both FSM paths must give Java's numbers (the weighted
+    score as the text %f prints)."""
+    monkeypatch.setenv("KG_FSM", fsm)
+    rng = np.random.default_rng(4321)
+    ncalls = 0
+    for vec in JAVA_VECTORS:
+        L = max(h[0] for h in vec["hits"]) + 40
+        prot = bytes(rng.choice(np.frombuffer(synth.PROT_ALPHA.encode(), np.uint8), L))
+        wk = synth.window_keys(synth.aa_codes(prot))
+        pos = [h[0] for h in vec["hits"]]
+        if len(np.unique(wk[pos])) != len(pos):
+            continue   # a repeated 8-mer among the chosen windows (never seen at these lengths): skip rather than alias two hits
+        img = synth.build_table_image(wk[pos], [h[2] for h in vec["hits"]], [h[4] for h in vec["hits"]],
+                                      [h[1] for h in vec["hits"]], np.array([h[3] for h in vec["hits"]], np.float32))
+        t = ctx.table_from_image(img)
+        res = ctx.run(t, kg.MODE_AA, np.frombuffer(prot, np.uint8), np.array([0, L], np.uint64), kg.default_params(emit_hits=1, **vec["params"]))
+        hit_pos = set(int(x) for x in res.hits["pos"])
+        assert set(pos) <= hit_pos, vec["name"]
+        if hit_pos == set(pos):   # (a window elsewhere in the random protein may equal a table key: then the vector is not this run)
+            got = [[int(c["start"]), int(c["end"]), int(c["count"]), int(c["fI"]), kg.java_format_f(float(c["weighted"]), 6)] for c in res.calls]
+            assert got == vec["calls"], vec["name"]
+            o = res.otus[0]
+            assert [[int(o["count"][j]), int(o["oI"][j])] for j in range(int(o["n"]))] == vec["otu"], vec["name"]
+            ncalls += len(got)
+        res.free()
+        t.free()
+    assert ncalls > 120
+
+
 @pytest.mark.parametrize("kat", KATS, ids=[k["name"] for k in KATS])
 def test_fsm_kats_on_gpu(kg, ctx, kat):
     """The hand-traced FSM vectors, driven through the whole GPU path: a random protein whose windows at the KAT's

@@ -30,6 +30,23 @@ def test_fsm_kat_c_oracle(oracle, kat):
     assert [[int(otu["count"][0][j]), int(otu["oI"][0][j])] for j in range(n)] == kat["otu"]
 
 
+JAVA_VECTORS = json.load(open(os.path.join(GOLD, "java_fsm_vectors.json")))["vectors"]
+
+
+@pytest.mark.parametrize("vec", JAVA_VECTORS, ids=[v["name"] for v in JAVA_VECTORS])
+def test_fsm_vectors_printed_by_the_java_source(oracle, vec):
+    """tests/golden/java_fsm_vectors.json: 64 adversarial hit lists whose CALL / OTU-COUNTS lines were printed by the
+    reference's own source (tests/java_pin/make_fsm_vectors.py); the weighted score is compared as the text %f gives."""
+    hits = np.zeros(len(vec["hits"]), dtype=oracle.HIT_DTYPE)
+    for i, (pos, fI, oI, wt, avg) in enumerate(vec["hits"]):
+        hits[i] = (0, 0, pos, oI, avg, fI, wt)
+    calls, otu = oracle.gather_hits(_params(oracle, vec["params"]), hits)
+    got = [[int(c["start"]), int(c["end"]), int(c["count"]), int(c["fI"]), oracle.java_format_f(float(c["weighted"]))] for c in calls]
+    assert got == vec["calls"]
+    n = int(otu["n"][0])
+    assert [[int(otu["count"][0][j]), int(otu["oI"][0][j])] for j in range(n)] == vec["otu"]
+
+
 @pytest.mark.parametrize("kat", KATS, ids=[k["name"] for k in KATS])
 def test_fsm_kat_py_oracle(kat):
     p = kat["params"]
