@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -17,15 +19,36 @@
 #include <string>
 #include <string_view>
 #include <thread>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
 void kg_set_error(const char* fmt, ...); // kg_table.cu
 
+// vector<T> whose resize() leaves new elements uninitialised (the reader's threads write every byte themselves; a
+// value-initialising resize of a few hundred MB is a serial memset in front of them)
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = NoInitAlloc<U>;
+    };
+    NoInitAlloc() = default;
+    template <class U>
+    NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <class U>
+    void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+        ::new (static_cast<void*>(p)) U;
+    }
+    template <class U, class... A>
+    void construct(U* p, A&&... a) {
+        ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
 struct kg_fasta {
     std::vector<std::string> ids;
-    std::vector<uint8_t> bytes;
-    std::vector<uint64_t> off{0};
+    std::vector<uint8_t, NoInitAlloc<uint8_t>> bytes;
+    std::vector<uint64_t, NoInitAlloc<uint64_t>> off{0};
 };
 struct kg_functions {
     std::vector<std::string> names;
@@ -109,15 +132,34 @@ namespace {
 
 // The reference's reader (KGJ:1132-1192) over text[begin, end).  `begin` is 0 or the start of a caption line and `end` is
 // the start of a caption line or the end of the text, so that the state machine enters every range in the state the
-// sequential reader would be in.  Returns false with the reference's message in err.
-bool parse_fasta_range(std::string_view whole, size_t begin, size_t end, kg_fasta& fa, std::string& err, int* code) {
+// sequential reader would be in.  Returns false with the reference's message in err.  What happens to a record is the
+// sink's business: the reader runs twice over every range, once to COUNT (records, sequence bytes) and once to WRITE
+// straight into the final arrays at the places the counts of the earlier ranges give -- the same state machine both times.
+struct CountSink {
+    size_t nseq = 0, nbytes = 0;
+    void line(std::string_view l) { nbytes += l.size(); }
+    void record(std::string_view) { nseq++; }
+};
+struct WriteSink {
+    kg_fasta* fa;
+    size_t seq, byte; // next record index, next byte position
+    void line(std::string_view l) {
+        memcpy(fa->bytes.data() + byte, l.data(), l.size());
+        byte += l.size();
+    }
+    void record(std::string_view name) {
+        fa->ids[seq].assign(name);
+        fa->off[++seq] = byte;
+    }
+};
+template <class Sink>
+bool parse_fasta_range(std::string_view whole, size_t begin, size_t end, Sink& sink, std::string& err, int* code) {
     Lines in{whole.substr(0, end), begin};
-    fa.bytes.reserve(end - begin);
     std::string_view cur;
     bool have = in.next(cur); // str1
     for (;;) {
         // look for the next caption; lines whose trimmed length is <= 1 are skipped (KGJ:1145, 1161)
-        std::string name;
+        std::string_view name;
         bool got_caption = false;
         while (have) {
             std::string_view t = jtrim(cur);
@@ -128,7 +170,7 @@ bool parse_fasta_range(std::string_view whole, size_t begin, size_t end, kg_fast
                     while (a < r.size() && (r[a] == ' ' || r[a] == '\t')) a++;
                     size_t b = a;
                     while (b < r.size() && r[b] != ' ' && r[b] != '\t') b++;
-                    name.assign(r.substr(a, b - a));
+                    name = r.substr(a, b - a);
                     got_caption = true;
                     break;
                 }
@@ -144,21 +186,20 @@ bool parse_fasta_range(std::string_view whole, size_t begin, size_t end, kg_fast
             std::string_view t = have ? jtrim(cur) : std::string_view();
             if (!have && end < whole.size()) t = std::string_view(">"); // the next range starts with a caption line
             if ((!have && end >= whole.size()) || (!t.empty() && t[0] == '>')) {
-                err = "No sequence for caption: " + name; // KGJ:1170
+                err = "No sequence for caption: " + std::string(name); // KGJ:1170
                 *code = KG_EFORMAT;
                 return false;
             }
             if (!t.empty()) break;
         }
         for (;;) { // KGJ:1175-1180: lines are appended as they are, blanks and inner spaces included
-            fa.bytes.insert(fa.bytes.end(), cur.begin(), cur.end());
+            sink.line(cur);
             have = in.next(cur);
             if (!have) break;
             std::string_view t = jtrim(cur);
             if (!t.empty() && t[0] == '>') break;
         }
-        fa.ids.push_back(std::move(name));
-        fa.off.push_back(fa.bytes.size());
+        sink.record(name);
     }
     return true;
 }
@@ -192,7 +233,7 @@ size_t next_caption_line(std::string_view text, size_t from) {
 // reference's reader into the same state wherever it comes from, so the ranges parse independently and concatenate.
 // ---------------------------------------------------------------------------------------------------------------
 static int parse_text(std::string_view text, size_t end, kg_fasta** out) { // text[0, end); a caption line starts at `end` if end < size
-    size_t min_chunk = 4u << 20;
+    size_t min_chunk = 1u << 20;
     if (const char* e = getenv("KG_FASTA_CHUNK")) min_chunk = std::max<size_t>(1, (size_t)atoll(e)); // tests: many tiny ranges
     unsigned hw = std::thread::hardware_concurrency();
     size_t want = std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, end / min_chunk + 1});
@@ -204,68 +245,93 @@ static int parse_text(std::string_view text, size_t end, kg_fasta** out) { // te
     }
     cut.push_back(end);
     const size_t parts = cut.size() - 1;
-    std::vector<kg_fasta> part(parts);
-    std::vector<std::string> errs(parts);
-    std::vector<int> codes(parts, KG_OK);
-    auto work = [&](size_t k) {
-        if (!parse_fasta_range(text, cut[k], cut[k + 1], part[k], errs[k], &codes[k]) && codes[k] == KG_OK) codes[k] = KG_EFORMAT;
-    };
-    if (parts == 1) {
-        work(0);
-    } else {
+    auto in_parallel = [&](auto&& work) {
+        if (parts == 1) {
+            work(0);
+            return;
+        }
         std::vector<std::thread> th;
         for (size_t k = 1; k < parts; k++) th.emplace_back(work, k);
         work(0);
         for (auto& t : th) t.join();
-    }
+    };
+    // pass 1: how many records and sequence bytes every range holds (and whether it parses at all)
+    std::vector<CountSink> cnt(parts);
+    std::vector<std::string> errs(parts);
+    std::vector<int> codes(parts, KG_OK);
+    in_parallel([&](size_t k) {
+        if (!parse_fasta_range(text, cut[k], cut[k + 1], cnt[k], errs[k], &codes[k]) && codes[k] == KG_OK) codes[k] = KG_EFORMAT;
+    });
     for (size_t k = 0; k < parts; k++)
         if (codes[k] != KG_OK) { // the first failing range holds the error the sequential reader would have met first
             kg_set_error("%s", errs[k].c_str());
             return codes[k];
         }
-    kg_fasta* fa = new kg_fasta();
-    if (parts == 1) {
-        *fa = std::move(part[0]);
-    } else {
-        size_t nseq = 0, nbytes = 0;
-        std::vector<size_t> seq0(parts), byte0(parts);
-        for (size_t k = 0; k < parts; k++) {
-            seq0[k] = nseq;
-            byte0[k] = nbytes;
-            nseq += part[k].ids.size();
-            nbytes += part[k].bytes.size();
-        }
-        fa->ids.resize(nseq);
-        fa->bytes.resize(nbytes);
-        fa->off.resize(nseq + 1);
-        fa->off[0] = 0;
-        auto merge = [&](size_t k) {
-            if (!part[k].bytes.empty()) memcpy(fa->bytes.data() + byte0[k], part[k].bytes.data(), part[k].bytes.size());
-            for (size_t i = 0; i < part[k].ids.size(); i++) {
-                fa->ids[seq0[k] + i] = std::move(part[k].ids[i]);
-                fa->off[seq0[k] + i + 1] = byte0[k] + part[k].off[i + 1];
-            }
-        };
-        std::vector<std::thread> th;
-        for (size_t k = 1; k < parts; k++) th.emplace_back(merge, k);
-        merge(0);
-        for (auto& t : th) t.join();
+    size_t nseq = 0, nbytes = 0;
+    std::vector<size_t> seq0(parts), byte0(parts);
+    for (size_t k = 0; k < parts; k++) {
+        seq0[k] = nseq;
+        byte0[k] = nbytes;
+        nseq += cnt[k].nseq;
+        nbytes += cnt[k].nbytes;
     }
+    // pass 2: every range writes its records where they belong (the pages of the arrays are first touched by the writers)
+    kg_fasta* fa = new kg_fasta();
+    fa->ids.resize(nseq);
+    fa->bytes.resize(nbytes);
+    fa->off.resize(nseq + 1);
+    fa->off[0] = 0;
+    in_parallel([&](size_t k) {
+        WriteSink w{fa, seq0[k], byte0[k]};
+        parse_fasta_range(text, cut[k], cut[k + 1], w, errs[k], &codes[k]);
+    });
     *out = fa;
     return KG_OK;
 }
+
+// a plain file is mapped, not copied (the parser only needs a view of the text)
+struct MappedText {
+    const char* p = nullptr;
+    size_t n = 0;
+    bool mapped = false;
+    std::string owned;
+    std::string_view view() const { return mapped ? std::string_view(p, n) : std::string_view(owned); }
+    ~MappedText() {
+        if (mapped && p) munmap(const_cast<char*>(p), n);
+    }
+    bool open(const std::string& path) {
+        if (!has_suffix(path, ".gz")) {
+            const int fd = ::open(path.c_str(), O_RDONLY);
+            if (fd < 0) return false;
+            struct stat st;
+            if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+                void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) {
+                    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                    p = static_cast<const char*>(m);
+                    n = (size_t)st.st_size;
+                    mapped = true;
+                    ::close(fd);
+                    return true;
+                }
+            }
+            ::close(fd);
+        }
+        return read_all(path, owned); // .gz, pipes, empty files, or no mmap
+    }
+};
 
 extern "C" int kg_fasta_read(const char* path, kg_fasta** out) {
     if (!path || !out) {
         kg_set_error("kg_fasta_read: null argument");
         return KG_EINVAL;
     }
-    std::string text;
-    if (!read_all(path, text)) {
+    MappedText text;
+    if (!text.open(path)) {
         kg_set_error("cannot read %s", path);
         return KG_EIO;
     }
-    return parse_text(text, text.size(), out);
+    return parse_text(text.view(), text.view().size(), out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

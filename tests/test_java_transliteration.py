@@ -264,6 +264,24 @@ def test_read_fasta_fuzz(oracle, java, tmp_path):
             got = cb.rec
         except rt.IllegalStateException as e:
             got = e.getMessage()
+        # ... and the PRODUCT's multi-threaded reader (kg_fasta_read, host part of the library: no GPU involved) against the
+        # Java source directly, cut into tiny ranges so that its two parsing passes meet every kind of range boundary
+        import kmergutsjava_b200 as kg
+        for chunk in ("1", "53"):
+            os.environ["KG_FASTA_CHUNK"] = chunk
+            try:
+                f = kg.Fasta(path)
+                prod = (f.ids, bytes(f.bytes), [int(x) for x in f.offsets])
+                f.free()
+            except kg.KgError as e:
+                prod = str(e)
+            finally:
+                os.environ.pop("KG_FASTA_CHUNK", None)
+            if isinstance(got, str):
+                assert isinstance(prod, str) and got in prod, (trial, chunk, prod, got)
+            else:
+                assert prod == ([g[0] for g in got], "".join(g[1] for g in got).encode("latin-1"),
+                                [int(x) for x in np.cumsum([0] + [len(g[1]) for g in got])]), (trial, chunk, body)
         if isinstance(want, str):
             assert got == want, (trial, body)
             n_err += 1
