@@ -513,3 +513,37 @@ def test_runtime_follows_the_java_api():
     assert lines == ["a", "b", "c", "d", "", " e "]
     s = rt.InputStream(bytes([1, 255]))
     assert [s.read(), s.read(), s.read()] == [1, 255, -1] and rt.InputStream(b"abcdef").skip(10) == 6
+
+
+def test_external_merge_drops_query_kmers_q4(java, synthetic, tmp_path):
+    """SURVEY.md Q4 (KGJ:683-715, 832-853): when more than inputSizeLimit query k-mers are in flight, the source spills sorted
+    runs to files and merges them -- and mergeTwoQueryKmerFiles copies only ONE leftover record after its main loop (KGJ:705-709),
+    so the tail of the longer run is lost and the lookup sees fewer k-mers.  That is why parity is defined on the in-RAM path
+    (<= 20 M k-mers per run, the default limit; sequences are independent, so larger inputs are batches of that).  Executed here
+    through the transliterated source: same input, in RAM and with a small limit."""
+    import re
+    mod, rt, _ = java
+    data, faa, fna, d = synthetic
+
+    def run(limit, name):
+        k = mod.KmerGutsJava()
+        k.aa, k.debug = True, True
+        if limit:
+            k.inputSizeLimit, k.tempDirPath = limit, str(tmp_path / f"spill{limit}")
+        out = str(tmp_path / name)
+        pw = rt.PrintWriter(rt.FileWriter(rt.File(out)))
+        k.run(rt.File(data), rt.File(faa), pw, False)
+        pw.close()
+        text = open(out).read()
+        m = re.search(r"Kmers found: (\d+) \(pos-count=(\d+)\)", text)
+        return int(m.group(1)), int(m.group(2)), text
+
+    found_ram, pos_ram, _ = run(0, "ram.txt")
+    assert pos_ram > 500
+    lost = []
+    for limit in (4000, 1500, 400):
+        found, pos, text = run(limit, f"ext{limit}.txt")
+        assert not os.listdir(str(tmp_path / f"spill{limit}"))      # the temporary files are deleted (KGJ:874-887)
+        assert pos <= pos_ram and found <= found_ram
+        lost.append(pos_ram - pos)
+    assert max(lost) > 0, "the external merge kept every k-mer: Q4 would not be a quirk"
