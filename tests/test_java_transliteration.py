@@ -547,3 +547,30 @@ def test_external_merge_drops_query_kmers_q4(java, synthetic, tmp_path):
         assert pos <= pos_ram and found <= found_ram
         lost.append(pos_ram - pos)
     assert max(lost) > 0, "the external merge kept every k-mer: Q4 would not be a quirk"
+
+
+def test_fenced_quirks_q3_q8_as_the_source_behaves(java, synthetic, monkeypatch):
+    """The two behaviours the product deliberately does NOT reproduce, shown on the source:
+    Q8  minHits = 1: processSetOfHits indexes hits[n-2] of a one-hit run (KGJ:442) -> IndexOutOfBounds; the ABI requires min_hits >= 2.
+    Q3  -t / -l can never succeed: `case 't'` has no break and falls into `case 'l'`, which has none either and falls into
+        `default`, which throws (KGJ:605-610); after ANY flag error main prints the usage text and carries on into
+        new File(null) (KGJ:616-647).  The product's command line accepts and ignores both and exits 2 on a flag error."""
+    mod, rt, _ = java
+    data, faa, fna, d = synthetic
+    k = mod.KmerGutsJava()
+    k.minHits = 1
+    h = mod.Hit()
+    h.from0InProt, h.fI, h.oI, h.functionWt, h.avgOffFromEnd = 10, 3, 1, 1.0, 100
+    h2 = mod.Hit()
+    h2.from0InProt, h2.fI, h2.oI, h2.functionWt, h2.avgOffFromEnd = 500, 3, 1, 1.0, 100
+    import io
+    with pytest.raises(rt.IndexOutOfBoundsException):
+        k.gatherHits(0, "+", 0, rt.ArrayList([h, h2]), rt.ArrayList(["F%d" % i for i in range(5)]), rt.ArrayList(), rt.PrintWriter(io.StringIO()))
+    # -l 5: the value parses, then `default` throws.  -t 5: falls into case 'l', which polls the NEXT flag as its number.
+    for flag, message in (("-l", "Error: Unknown parameter: -l"), ("-t", 'Error: For input string: "-D"')):
+        buf = io.StringIO()
+        monkeypatch.setattr(rt.System, "out", rt.PrintStream(buf))
+        with pytest.raises(rt.NullPointerException):
+            mod.KmerGutsJava.main([flag, "5", "-D", data, "-q", faa])
+        out = buf.getvalue()
+        assert message in out and "Usage: kmer_guts [options] -D DataDir" in out
