@@ -83,10 +83,13 @@ class ParseError(Exception):
 
 
 class Parser:
-    def __init__(self, src):
+    def __init__(self, src, lenient=False):
+        """lenient: SYNTAX CHECK ONLY -- also accept constructors, records, try-with-resources, lambdas, X.class and
+        annotation arguments (the repo's own Java files use them); the emitter has no rule for those nodes and refuses them."""
         self.src = src
         self.t = tokenize(src)
         self.i = 0
+        self.lenient = lenient
 
     # ---- token helpers ----
     def peek(self, k=0):
@@ -175,6 +178,10 @@ class Parser:
             if self.at("@"):
                 self.i += 1
                 self.ident()
+                while self.at(".") and self.peek(1).kind == "id":
+                    self.i += 2
+                if self.lenient and self.at("("):
+                    self.args()
                 continue
             if self.peek().text in MODIFIERS:
                 mods.add(self.peek().text)
@@ -186,12 +193,17 @@ class Parser:
         mods = self.modifiers()
         if self.accept("interface"):
             kind = "interface"
+        elif self.lenient and self.at("record") and self.peek(1).kind == "id" and self.peek(2).text == "(":
+            self.i += 1
+            kind = "record"
         else:
             self.expect("class")
             kind = "class"
         name = self.ident()
         if self.at("<"):
             self._skip_generic_args()
+        if kind == "record":
+            self.params()
         while self.at("extends") or self.at("implements"):
             self.i += 1
             self.try_type()
@@ -209,9 +221,19 @@ class Parser:
                 continue
             save = self.i
             mods = self.modifiers()
-            if self.at("class") or self.at("interface"):
+            if self.at("class") or self.at("interface") or \
+                    (self.lenient and self.at("record") and self.peek(1).kind == "id" and self.peek(2).text == "("):
                 self.i = save
                 members.append(self.type_decl())
+                continue
+            if self.lenient and self.peek().text == cname and self.peek(1).text == "(":   # constructor
+                self.i += 1
+                params = self.params()
+                if self.accept("throws"):
+                    self.try_type()
+                    while self.accept(","):
+                        self.try_type()
+                members.append(("ctor", mods, params, self.block()))
                 continue
             if self.at("<"):
                 raise ParseError(f"line {self.line()}: generic methods are not supported")
@@ -386,9 +408,18 @@ class Parser:
             self.expect(";")
             return ("throw", e)
         if self.accept("try"):
+            resources = []
             if self.at("("):
-                raise ParseError(f"line {ln}: try-with-resources is not supported")
+                if not self.lenient:
+                    raise ParseError(f"line {ln}: try-with-resources is not supported")
+                self.i += 1
+                while not self.accept(")"):
+                    d = self.try_local_decl()
+                    resources.append(d if d is not None else ("expr", self.expr()))
+                    self.accept(";")
             body = self.block()
+            if resources:
+                body = ("unsupported", "try-with-resources", resources, body)
             catches, fin = [], None
             while self.accept("catch"):
                 self.expect("(")
@@ -530,6 +561,23 @@ class Parser:
         if tk.kind == "chr":
             self.i += 1
             return ("chr", tk.text)
+        if self.lenient and tk.text == "(":   # ( params ) -> body
+            j, depth = self.i, 0
+            while True:
+                t = self.t[j].text
+                depth += (t == "(") - (t == ")")
+                j += 1
+                if depth == 0 or self.t[j].kind == "eof":
+                    break
+            if self.t[j].text == "->":
+                self.i = j + 1
+                return ("unsupported", "lambda", self.block() if self.at("{") else self.expr())
+        if self.lenient and tk.kind == "id" and tk.text not in KEYWORDS and self.peek(1).text == "->":
+            self.i += 2
+            return ("unsupported", "lambda", self.block() if self.at("{") else self.expr())
+        if self.lenient and tk.text in PRIMITIVES and self.peek(1).text == "." and self.peek(2).text == "class":
+            self.i += 3
+            return ("unsupported", "class literal")
         if tk.text == "(":
             self.i += 1
             e = self.expr()
@@ -585,7 +633,10 @@ class Parser:
 
     def postfix(self, e):
         while True:
-            if self.at("."):
+            if self.lenient and self.at(".") and self.peek(1).text == "class":
+                self.i += 2
+                e = ("unsupported", "class literal")
+            elif self.at("."):
                 self.i += 1
                 name = self.ident()
                 if self.at("("):
@@ -1283,6 +1334,12 @@ class FunctionEmitter:
             lines.append(self.pad(extra + 1) + "break")
             return lines
         raise ParseError(f"cannot emit statement {k}")
+
+
+def syntax_check(java_source):
+    """Parse only, with the lenient grammar: raises ParseError (with a line number) on anything that is not Java as this parser
+    knows it.  For the repo's own Java files, which no compiler has ever seen (no JDK in the image)."""
+    return Parser(java_source, lenient=True).compilation_unit()
 
 
 def transliterate(java_source):
