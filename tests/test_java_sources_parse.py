@@ -59,3 +59,71 @@ def test_binding_names_the_abi_it_binds(j2py):
     headers = "".join(open(os.path.join(ROOT, "include", h)).read() for h in os.listdir(os.path.join(ROOT, "include")))
     declared = set(re.findall(r"\b(kg_[a-z_0-9]+)\s*\(", headers))
     assert wanted <= declared, sorted(wanted - declared)
+
+
+def test_binding_descriptors_match_the_c_declarations():
+    """Every FunctionDescriptor of the FFM binding against the C declaration of the symbol in include/*.h: same arity, and per
+    argument pointer -> ADDRESS, int -> JAVA_INT, size_t / uint64_t -> JAVA_LONG, float -> JAVA_FLOAT; return int -> JAVA_INT,
+    void -> ofVoid, pointer -> ADDRESS.  (A mismatch compiles fine on a JVM and corrupts the call at run time.)"""
+    src = open(FILES[0]).read()
+    inc = os.path.join(ROOT, "include")
+    headers = "".join(open(os.path.join(inc, h)).read() for h in sorted(os.listdir(inc)))
+    headers = re.sub(r"/\*.*?\*/", " ", headers, flags=re.S)
+    headers = re.sub(r"//[^\n]*", " ", headers)
+
+    def kind(ctype):
+        t = ctype.strip()
+        if "*" in t or "[" in t:
+            return "ADDRESS"
+        base = re.sub(r"\b(const|unsigned|signed)\b", "", t).split()
+        base = base[0] if base else ""
+        return {"int": "JAVA_INT", "int32_t": "JAVA_INT", "uint32_t": "JAVA_INT", "size_t": "JAVA_LONG", "uint64_t": "JAVA_LONG",
+                "int64_t": "JAVA_LONG", "long": "JAVA_LONG", "float": "JAVA_FLOAT", "void": "void"}.get(base, "?" + t)
+
+    checked = 0
+    for name, how, args in re.findall(r'h\("(kg_[a-z_0-9]+)",\s*FunctionDescriptor\.(of|ofVoid)\(([^;]*?)\)\);', src):
+        m = re.search(r"([\w\s\*]+?)\b" + name + r"\s*\(([^)]*)\)\s*;", headers)
+        assert m, f"{name} is not declared in include/"
+        ret, params = m.group(1), m.group(2)
+        cparams = [] if params.strip() in ("", "void") else [kind(re.sub(r"\b\w+\s*(\[[^\]]*\])?\s*$", lambda x: x.group(1) or "", p.strip())
+                                                                  if not p.strip().endswith("*") else p) for p in params.split(",")]
+        jargs = [a.strip() for a in args.split(",") if a.strip()]
+        if how == "of":
+            jret, jargs = jargs[0], jargs[1:]
+        else:
+            jret = "void"
+        assert jret == kind(ret), (name, jret, ret)
+        assert jargs == cparams, (name, jargs, cparams, params)
+        checked += 1
+    assert checked >= 15
+
+
+def test_binding_struct_layouts_match_the_c_structs():
+    """PARAMS / CALL / OTU / HIT of the FFM binding against kg_params / kg_call / kg_otu / kg_hit in include/kmerguts.h: same
+    field names in the same order, int32/uint32 -> JAVA_INT, float -> JAVA_FLOAT, int32[5] -> sequenceLayout(5, JAVA_INT); and
+    the hard-coded byte offsets the reader uses (o + 4, o + 24 ...) are the ones these layouts imply."""
+    src = open(FILES[0]).read()
+    hdr = open(os.path.join(ROOT, "include", "kmerguts.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    bufsz = int(re.search(r"#define\s+KG_OI_BUFSZ\s+(\d+)", hdr).group(1))
+    for jname, cname in (("PARAMS", "kg_params"), ("CALL", "kg_call"), ("OTU", "kg_otu"), ("HIT", "kg_hit")):
+        body = re.search(r"typedef struct " + cname + r"\s*\{(.*?)\}\s*" + cname + r"\s*;", hdr, re.S).group(1)
+        cfields = []
+        for decl in body.split(";"):
+            m = re.match(r"\s*(u?int32_t|float)\s+(\w+)\s*(\[\s*(\w+)\s*\])?\s*$", decl)
+            if m:
+                n = None if m.group(4) is None else (bufsz if m.group(4) == "KG_OI_BUFSZ" else int(m.group(4)))
+                cfields.append((m.group(2), "JAVA_FLOAT" if m.group(1) == "float" else "JAVA_INT", n))
+            else:
+                assert not decl.strip(), (cname, decl)
+        jbody = re.search(r"StructLayout " + jname + r" = MemoryLayout\.structLayout\((.*?)\);", src, re.S).group(1)
+        jfields = []
+        for m in re.finditer(r'(?:MemoryLayout\.sequenceLayout\((\d+),\s*(JAVA_\w+)\)|(JAVA_\w+))\.withName\("(\w+)"\)', jbody):
+            jfields.append((m.group(4), m.group(2) or m.group(3), int(m.group(1)) if m.group(1) else None))
+        assert jfields == cfields, (jname, jfields, cfields)
+    # offsets used when the records are read back
+    call_reads = re.findall(r"cs\.get\((JAVA_\w+), o(?: \+ (\d+))?\)", src)
+    assert [(t, int(o or 0)) for t, o in call_reads] == [("JAVA_INT", 0), ("JAVA_INT", 4), ("JAVA_INT", 8), ("JAVA_INT", 12), ("JAVA_INT", 16),
+                                                          ("JAVA_INT", 20), ("JAVA_FLOAT", 24), ("JAVA_INT", 28)]
+    assert "o + 4 + 4L * j" in src and "o + 24 + 4L * j" in src and bufsz == 5     # kg_otu: n, count[5] at 4, oI[5] at 24
+    assert [int(x) for x in re.findall(r"p\.set\(JAVA_INT, (\d+),", src)] == [0, 4, 8, 12, 16]   # kg_params
