@@ -9,6 +9,11 @@ REF=${1:?usage: pin_oracle.sh <KmerGutsJava checkout> [workdir]}
 W=${2:-/tmp/kg_pin}
 HERE=$(cd "$(dirname "$0")/../.." && pwd)
 cd "$HERE"
+if ! command -v javac > /dev/null || ! command -v java > /dev/null; then
+  # no JDK on this box: execute the same unmodified source through the mechanical transliterator instead (tests/java_pin/j2py.py)
+  echo "no javac/java here: running KmerGutsJava.java through tests/java_pin/transliterated_pin.py"
+  exec python tests/java_pin/transliterated_pin.py "$REF" "$W"
+fi
 python tests/java_pin/pin_oracle.py prepare "$W"
 mkdir -p "$W/classes"
 javac -nowarn -d "$W/classes" "$REF/lib/src/kmergutsjava/KmerGutsJava.java" tests/java_pin/GoldenDump.java
